@@ -1,0 +1,191 @@
+/*
+ * b200icp.h -- C-ABI of libb200icp.so, the B200 (sm_100a) ICP registration core that
+ * drops in behind norlab_icp_mapper's Mapper::processInput / Map::updatePose path.
+ *
+ * The reference has no FFI: its seams are C++ objects from libpointmatcher (`PM::ICPSequence`,
+ * `PM::Transformation`, `Nabo::NNS`) and its own `MapperModule` plugin interface.  Every entry
+ * point below names the reference call site it replaces (file:line under the reference tree);
+ * INTEGRATION.md shows the C++ shim a maintainer would put between those call sites and this
+ * header.  Conventions shared by every function:
+ *
+ *   - All matrices are column-major fp32, exactly the memory of the reference's Eigen types:
+ *     a cloud's `features` is (dim+1) x N with the homogeneous row last, `normals` is dim x N,
+ *     a TransformationParameters is (dim+1) x (dim+1).
+ *   - Plain pointers and sizes only.  "_device" variants take CUDA device pointers that live on
+ *     the context's device; the unsuffixed variants take host pointers and do the copies.
+ *   - Every function returns a b200icp_status; the message for the last failure on a context is
+ *     returned by b200icp_last_error().  No C++ exception crosses this boundary.
+ *   - A context is bound to one device and one stream.  Calls on one context must be serialised
+ *     by the caller -- the reference already does this with `icpMapLock` (Mapper.cpp:212,
+ *     Map.cpp:110,177,527,580).  Different contexts are independent.
+ *   - There is no CPU fallback: if CUDA is unavailable b200icp_create fails with
+ *     B200ICP_ERR_CUDA.
+ */
+#ifndef B200ICP_H
+#define B200ICP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ICP_ABI_VERSION 1
+
+typedef enum b200icp_status {
+    B200ICP_OK = 0,
+    B200ICP_ERR_INVALID_ARG = 1,   /* bad pointer / size / unknown enum                               */
+    B200ICP_ERR_CUDA = 2,          /* CUDA runtime failure, message in last_error                     */
+    B200ICP_ERR_NO_MAP = 3,        /* register/match before set_map                                   */
+    B200ICP_ERR_CONVERGENCE = 4,   /* LPM ConvergenceError: "no point to minimize", empty quantile    */
+    B200ICP_ERR_BOUND = 5,         /* LPM BoundTransformationChecker: "limit out of bounds"           */
+    B200ICP_ERR_NAN = 6,           /* LPM checkers: "abs rotation/translation norm not a number"      */
+    B200ICP_ERR_TRANSFORM = 7,     /* LPM TransformationError: rotation block is not orthonormal      */
+    B200ICP_ERR_INVALID_FIELD = 8, /* LPM InvalidField: e.g. point-to-plane without map normals       */
+    B200ICP_ERR_NOT_IMPLEMENTED = 9
+} b200icp_status;
+
+/* icp.outlierFilters entries (libpointmatcher OutlierFiltersImpl); weights multiply. */
+typedef enum b200icp_outlier_kind {
+    B200ICP_OUTLIER_TRIMMED_DIST = 1, /* param = ratio;   w = dist2 <= quantile(finite dist2, ratio)  */
+    B200ICP_OUTLIER_MAX_DIST = 2,     /* param = maxDist; w = dist2 <= maxDist^2                      */
+    B200ICP_OUTLIER_MIN_DIST = 3,     /* param = minDist; w = dist2 >= minDist^2                      */
+    B200ICP_OUTLIER_MEDIAN_DIST = 4   /* param = factor;  w = dist2 <= factor * median(finite dist2)  */
+} b200icp_outlier_kind;
+
+/* icp.errorMinimizer */
+typedef enum b200icp_minimizer_kind {
+    B200ICP_MIN_POINT_TO_PLANE = 0,
+    B200ICP_MIN_POINT_TO_POINT = 1,
+    B200ICP_MIN_IDENTITY = 2 /* examples/config.yaml:62-63 */
+} b200icp_minimizer_kind;
+
+#define B200ICP_MAX_OUTLIER_FILTERS 4
+
+/*
+ * The `icp:` YAML node of the reference (Mapper.cpp:70-78 -> PM::ICPSequence::loadFromYamlNode),
+ * flattened.  Field names follow the libpointmatcher parameter names.
+ */
+typedef struct b200icp_config {
+    int32_t dim; /* 2 or 3 (Mapper ctor `is3D`, Mapper.h:53)                                        */
+    /* matcher: KDTreeMatcher (docs/MapperConfiguration.md:175-179) */
+    int32_t knn;       /* 1..32                                                                     */
+    float max_dist;    /* metres; +inf = unbounded (LPM default)                                    */
+    float epsilon;     /* accepted for config compatibility; the search is always exact (eps = 0)   */
+    /* outlierFilters (product of all) */
+    int32_t n_outlier;
+    int32_t outlier_kind[B200ICP_MAX_OUTLIER_FILTERS];
+    float outlier_param[B200ICP_MAX_OUTLIER_FILTERS];
+    /* errorMinimizer */
+    int32_t minimizer;
+    /* transformationCheckers */
+    int32_t max_iteration_count; /* CounterTransformationChecker; <=0 means absent                */
+    int32_t use_differential;    /* DifferentialTransformationChecker                             */
+    float min_diff_rot_err;
+    float min_diff_trans_err;
+    int32_t smooth_length;
+    int32_t use_bound; /* BoundTransformationChecker                                              */
+    float max_rotation_norm;
+    float max_translation_norm;
+    /* implementation knobs (no reference counterpart) */
+    int32_t sort_reading; /* 1: Morton-sort the reading once per registration (default)          */
+    int32_t use_graph;    /* 1: replay the iteration as a CUDA graph when the chain allows it    */
+    int32_t nn_variant;   /* 0: default kernel; other values select experimental variants        */
+    int32_t reserved[5];
+} b200icp_config;
+
+/* What `icp(input)` leaves behind for the caller (Mapper.cpp:213,219). */
+typedef struct b200icp_result {
+    float overlap;            /* errorMinimizer->getOverlap() == weightedPointUsedRatio (last iter) */
+    float point_used_ratio;   /* ErrorElements::pointUsedRatio of the last iteration              */
+    int32_t iterations;       /* iterations executed                                              */
+    int32_t max_iter_reached; /* Counter checker fired                                            */
+    int64_t pairs_last_iter;  /* number of pairs kept by the last iteration                       */
+} b200icp_result;
+
+/* Device timings of the last b200icp_register* call, measured with CUDA events on ctx's stream. */
+typedef struct b200icp_timing {
+    float total_ms;       /* whole registration, first kernel to pose ready                        */
+    float nn_ms_sum;      /* sum over iterations of the correspondence-search kernel (profiling on) */
+    int32_t nn_launches;  /* how many launches nn_ms_sum covers                                    */
+    int32_t kernel_launches; /* kernels launched by the call (all of them ours + the sort)         */
+    float setmap_ms;      /* last b200icp_set_map*: mean-centre + index build                      */
+    int32_t reserved[3];
+} b200icp_timing;
+
+typedef struct b200icp_ctx b200icp_ctx;
+
+int32_t b200icp_abi_version(void);
+
+/* Fill *cfg with: knn 1, maxDist inf, eps 0, Trimmed 0.85, PointToPlane, Counter 40 +
+ * Differential(1e-3, 1e-3, 3) -- the matcher/outlier/minimiser/checker part of
+ * PM::ICPSequence::setDefault() (Mapper.cpp:77). */
+void b200icp_config_default(b200icp_config* cfg, int32_t dim);
+
+/* Construct the ICP object (replaces the `PM::ICPSequence icp` member, Mapper.h:23, configured at
+ * Mapper.cpp:72/77). */
+int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** out);
+void b200icp_destroy(b200icp_ctx* ctx);
+const char* b200icp_last_error(const b200icp_ctx* ctx); /* ctx may be NULL: creation errors */
+void* b200icp_stream(b200icp_ctx* ctx);                 /* the cudaStream_t all work is issued on */
+int32_t b200icp_set_profiling(b200icp_ctx* ctx, int32_t on); /* per-kernel event timing (adds syncs) */
+int32_t b200icp_get_timing(const b200icp_ctx* ctx, b200icp_timing* out);
+
+/* icp.setMap(cloud) -- Map.cpp:111,178,528,581.  Copies the cloud, mean-centres it
+ * (T_refIn_refMean) and builds the spatial index that replaces libnabo's kd-tree.
+ * normals may be NULL unless the minimiser is point-to-plane (then B200ICP_ERR_INVALID_FIELD is
+ * reported by register, as LPM does).  n == 0 is ignored and returns B200ICP_ERR_NO_MAP state
+ * unchanged (LPM: "Ignoring attempt to create a map from an empty cloud", returns false). */
+int32_t b200icp_set_map(b200icp_ctx* ctx, const float* features, int32_t feature_rows,
+                        const float* normals, int64_t n);
+int32_t b200icp_set_map_device(b200icp_ctx* ctx, const float* d_features, int32_t feature_rows,
+                               const float* d_normals, int64_t n);
+int64_t b200icp_map_size(const b200icp_ctx* ctx);
+
+/* correction = icp(input) + errorMinimizer->getOverlap() -- Mapper.cpp:213,219.
+ * `reading` is the scan already moved by the estimated pose (Mapper.cpp:197).  T_init may be NULL
+ * (identity: the overload the reference calls).  T_out receives the (dim+1)x(dim+1) correction. */
+int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq,
+                         const float* T_init, float* T_out, b200icp_result* result);
+int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_t feature_rows,
+                                int64_t nq, const float* T_init, float* T_out,
+                                b200icp_result* result);
+
+/* matcher->findClosests(cloud) against the current map -- the KDTreeMatcher step of the loop and
+ * the direct Nabo::NNS::knn call sites (PointDistanceMapperModule.cpp:36).  `queries` are in the
+ * map frame; ids index the cloud given to set_map; dists are squared; missing = -1 / +inf.
+ * Output is knn x nq, column-major (ids[i*knn + j] = j-th neighbour of query i). */
+int32_t b200icp_match(b200icp_ctx* ctx, const float* queries, int32_t feature_rows, int64_t nq,
+                      int32_t* ids, float* dists2);
+
+/* Nabo::NNS::create(ref) + knn(query, k, eps=0, ALLOW_SELF_MATCH, maxRadius) on arbitrary clouds
+ * (PointDistanceMapperModule.cpp:33-36, DynamicPointsMapperModule.cpp:75-78, and the self-kNN of
+ * SurfaceNormalDataPointsFilter).  No centring.  Host pointers. */
+int32_t b200icp_knn(b200icp_ctx* ctx, const float* ref, int32_t ref_rows, int64_t nref,
+                    const float* queries, int32_t query_rows, int64_t nq, int32_t dim, int32_t k,
+                    float max_radius, int32_t* ids, float* dists2);
+
+/* PM::Transformation("RigidTransformation")->compute(cloud, T) -- Mapper.cpp:197,221;
+ * Map.cpp:523,525.  In place on host buffers; normals may be NULL.  Fails with
+ * B200ICP_ERR_TRANSFORM when |1 - det R| > 1e-3. */
+int32_t b200icp_transform(b200icp_ctx* ctx, float* features, int32_t feature_rows, float* normals,
+                          int64_t n, const float* T);
+
+/* Device-pointer variant of b200icp_transform (features/normals live on ctx's device). */
+int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows,
+                                 float* d_normals, int64_t n, const float* T);
+
+/* Introspection (no reference counterpart; used by tests and the bench):
+ *  - the translation of T_refIn_refMean chosen by the last set_map (ICPSequence::setMap's mean),
+ *  - the cell edge and grid dimensions of the spatial index,
+ *  - per-iteration T_iter of the last registration (refMean frame, (dim+1)^2 column-major each;
+ *    enable with b200icp_set_trace before registering; get_trace returns the iteration count). */
+int32_t b200icp_get_map_mean(const b200icp_ctx* ctx, float* mean3);
+int32_t b200icp_get_grid_info(const b200icp_ctx* ctx, float* cell_edge, int32_t* dims3);
+int32_t b200icp_set_trace(b200icp_ctx* ctx, int32_t on);
+int32_t b200icp_get_trace(const b200icp_ctx* ctx, float* out, int32_t max_iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ICP_H */

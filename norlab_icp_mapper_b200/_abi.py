@@ -1,0 +1,93 @@
+"""ctypes mirror of include/b200icp.h (struct layouts and enums).  Pure declarations: shared by the
+product binding (icp.py) and by the tests' oracle binding so both speak the same config."""
+import ctypes as C
+
+ABI_VERSION = 1
+MAX_OUTLIER_FILTERS = 4
+
+# b200icp_status
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_MAP, ERR_CONVERGENCE, ERR_BOUND, ERR_NAN, ERR_TRANSFORM, \
+    ERR_INVALID_FIELD, ERR_NOT_IMPLEMENTED = range(10)
+# b200icp_outlier_kind
+OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST = 1, 2, 3, 4
+# b200icp_minimizer_kind
+MIN_POINT_TO_PLANE, MIN_POINT_TO_POINT, MIN_IDENTITY = 0, 1, 2
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("knn", C.c_int32),
+        ("max_dist", C.c_float),
+        ("epsilon", C.c_float),
+        ("n_outlier", C.c_int32),
+        ("outlier_kind", C.c_int32 * MAX_OUTLIER_FILTERS),
+        ("outlier_param", C.c_float * MAX_OUTLIER_FILTERS),
+        ("minimizer", C.c_int32),
+        ("max_iteration_count", C.c_int32),
+        ("use_differential", C.c_int32),
+        ("min_diff_rot_err", C.c_float),
+        ("min_diff_trans_err", C.c_float),
+        ("smooth_length", C.c_int32),
+        ("use_bound", C.c_int32),
+        ("max_rotation_norm", C.c_float),
+        ("max_translation_norm", C.c_float),
+        ("sort_reading", C.c_int32),
+        ("use_graph", C.c_int32),
+        ("nn_variant", C.c_int32),
+        ("reserved", C.c_int32 * 5),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("overlap", C.c_float),
+        ("point_used_ratio", C.c_float),
+        ("iterations", C.c_int32),
+        ("max_iter_reached", C.c_int32),
+        ("pairs_last_iter", C.c_int64),
+    ]
+
+
+class Timing(C.Structure):
+    _fields_ = [
+        ("total_ms", C.c_float),
+        ("nn_ms_sum", C.c_float),
+        ("nn_launches", C.c_int32),
+        ("kernel_launches", C.c_int32),
+        ("setmap_ms", C.c_float),
+        ("reserved", C.c_int32 * 3),
+    ]
+
+
+def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("trimmed", 0.85),),
+                minimizer="point_to_plane", max_iteration_count=40, differential=None, bound=None,
+                sort_reading=1, use_graph=1, nn_variant=0):
+    """Build a Config from the names used in the reference's `icp:` YAML node
+    (docs/MapperConfiguration.md:172-189)."""
+    kinds = {"trimmed": OUTLIER_TRIMMED_DIST, "max_dist": OUTLIER_MAX_DIST,
+             "min_dist": OUTLIER_MIN_DIST, "median": OUTLIER_MEDIAN_DIST}
+    mins = {"point_to_plane": MIN_POINT_TO_PLANE, "point_to_point": MIN_POINT_TO_POINT,
+            "identity": MIN_IDENTITY}
+    c = Config()
+    c.dim, c.knn, c.max_dist, c.epsilon = dim, knn, max_dist, epsilon
+    if len(outliers) > MAX_OUTLIER_FILTERS:
+        raise ValueError("too many outlier filters")
+    c.n_outlier = len(outliers)
+    for i, (name, param) in enumerate(outliers):
+        c.outlier_kind[i] = kinds[name]
+        c.outlier_param[i] = param
+    c.minimizer = mins[minimizer]
+    c.max_iteration_count = max_iteration_count
+    if differential is not None:
+        c.use_differential = 1
+        c.min_diff_rot_err, c.min_diff_trans_err, c.smooth_length = differential
+    else:
+        c.use_differential, c.min_diff_rot_err, c.min_diff_trans_err, c.smooth_length = 0, 1e-3, 1e-3, 3
+    if bound is not None:
+        c.use_bound = 1
+        c.max_rotation_norm, c.max_translation_norm = bound
+    else:
+        c.use_bound, c.max_rotation_norm, c.max_translation_norm = 0, 1.0, 1.0
+    c.sort_reading, c.use_graph, c.nn_variant = sort_reading, use_graph, nn_variant
+    return c

@@ -1,0 +1,73 @@
+"""Loader for libb200icp.so (the C-ABI in include/b200icp.h).
+
+The library is built in-tree by `make -C norlab_icp_mapper_b200/csrc` (or `__graft_entry__.build()`).
+There is NO fallback: if the shared object is missing this raises, and if no B200 is present
+`b200icp_create` fails with B200ICP_ERR_CUDA and the wrappers raise.
+"""
+import ctypes as C
+import os
+
+from ._abi import Config, Result, Timing
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libb200icp.so")
+
+# every symbol include/b200icp.h declares (tests check the export list against the header)
+SYMBOLS = [
+    "b200icp_abi_version", "b200icp_config_default", "b200icp_create", "b200icp_destroy",
+    "b200icp_last_error", "b200icp_stream", "b200icp_set_profiling", "b200icp_get_timing",
+    "b200icp_set_map", "b200icp_set_map_device", "b200icp_map_size", "b200icp_register",
+    "b200icp_register_device", "b200icp_match", "b200icp_knn", "b200icp_transform",
+    "b200icp_transform_device", "b200icp_get_map_mean", "b200icp_get_grid_info",
+    "b200icp_set_trace", "b200icp_get_trace",
+]
+
+_lib = None
+
+
+class B200ICPError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"[b200icp status {status}] {message}")
+        self.status = status
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            f"{SO_PATH} is missing: build it with `make -C norlab_icp_mapper_b200/csrc` "
+            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.b200icp_abi_version.restype = i32
+    L.b200icp_config_default.argtypes = [C.POINTER(Config), i32]
+    L.b200icp_config_default.restype = None
+    L.b200icp_create.argtypes = [C.POINTER(Config), i32, C.POINTER(vp)]
+    L.b200icp_destroy.argtypes = [vp]
+    L.b200icp_destroy.restype = None
+    L.b200icp_last_error.argtypes = [vp]
+    L.b200icp_last_error.restype = C.c_char_p
+    L.b200icp_stream.argtypes = [vp]
+    L.b200icp_stream.restype = vp
+    L.b200icp_set_profiling.argtypes = [vp, i32]
+    L.b200icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.b200icp_set_map.argtypes = [vp, vp, i32, vp, i64]
+    L.b200icp_set_map_device.argtypes = [vp, vp, i32, vp, i64]
+    L.b200icp_map_size.argtypes = [vp]
+    L.b200icp_map_size.restype = i64
+    L.b200icp_register.argtypes = [vp, vp, i32, i64, vp, vp, C.POINTER(Result)]
+    L.b200icp_register_device.argtypes = [vp, vp, i32, i64, vp, vp, C.POINTER(Result)]
+    L.b200icp_match.argtypes = [vp, vp, i32, i64, vp, vp]
+    L.b200icp_knn.argtypes = [vp, vp, i32, i64, vp, i32, i64, i32, i32, f32, vp, vp]
+    L.b200icp_transform.argtypes = [vp, vp, i32, vp, i64, vp]
+    L.b200icp_transform_device.argtypes = [vp, vp, i32, vp, i64, vp]
+    L.b200icp_get_map_mean.argtypes = [vp, vp]
+    L.b200icp_get_grid_info.argtypes = [vp, C.POINTER(f32), vp]
+    L.b200icp_set_trace.argtypes = [vp, i32]
+    L.b200icp_get_trace.argtypes = [vp, vp, i32]
+    if L.b200icp_abi_version() != 1:
+        raise ImportError("libb200icp.so ABI version mismatch")
+    _lib = L
+    return L

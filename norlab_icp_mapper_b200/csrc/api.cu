@@ -1,0 +1,703 @@
+// api.cu -- the C-ABI of libb200icp.so (include/b200icp.h): context, setMap, register, match,
+// knn, transform.  Host-side orchestration only; all arithmetic is in index.cu / knn.cu / icp.cu.
+// There is no CPU fallback anywhere in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace b200;
+
+struct b200icp_ctx {
+    b200icp_config cfg{};
+    IcpParams prm{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    GridIndex map;
+    bool has_map = false;
+    int64_t map_n = 0;
+    GridIndex aux;  // index for b200icp_knn on arbitrary clouds
+    IcpBuffers buf;
+    float* d_stage_a = nullptr;  // uploads: features
+    float* d_stage_b = nullptr;  // uploads: normals / queries
+    size_t stage_a_bytes = 0, stage_b_bytes = 0;
+    int32_t* d_out_ids = nullptr;
+    float* d_out_d2 = nullptr;
+    float4* d_q4 = nullptr;
+    int64_t cap_out = 0, cap_q4 = 0;
+    int* d_scalar_nq = nullptr;
+    char* h_pinned = nullptr;  // [0, 1024): state image to upload, [1024, 2048): state read back, [2048..): ints
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_map0 = nullptr, ev_map1 = nullptr;
+    std::vector<cudaEvent_t> nn_events;
+    bool profiling = false;
+    bool want_trace = false;
+    std::vector<float> h_trace;  // T_iter after each iteration of the last registration (4x4 each)
+    b200icp_timing timing{};
+    std::string err;
+};
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_create_mutex;
+
+int32_t fail(b200icp_ctx* ctx, int32_t code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+int32_t fail_cuda(b200icp_ctx* ctx, cudaError_t e, const char* what) {
+    cudaGetLastError();  // clear sticky-less error state
+    return fail(ctx, B200ICP_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(expr)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (expr);                                      \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #expr);      \
+    } while (0)
+
+template <typename T>
+cudaError_t grow(T*& p, size_t& have_bytes, size_t need_bytes) {
+    if (need_bytes <= have_bytes && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    have_bytes = 0;
+    const size_t cap = need_bytes + need_bytes / 4 + 4096;
+    cudaError_t e = cudaMalloc((void**)&p, cap);
+    if (e == cudaSuccess) have_bytes = cap;
+    return e;
+}
+
+void mat4_identity(float* M) {
+    for (int i = 0; i < 16; ++i) M[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+void mat4_mul(const float* A, const float* B, float* C) {
+    float tmp[16];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            float acc = 0.f;
+            for (int k = 0; k < 4; ++k) acc += A[k * 4 + r] * B[c * 4 + k];
+            tmp[c * 4 + r] = acc;
+        }
+    memcpy(C, tmp, sizeof(tmp));
+}
+// (dim+1)^2 column-major <-> embedded 4x4 column-major
+void embed(const float* T, int dim, float* M) {
+    mat4_identity(M);
+    if (!T) return;
+    const int n = dim + 1;
+    for (int r = 0; r < dim; ++r) {
+        for (int c = 0; c < dim; ++c) M[c * 4 + r] = T[c * n + r];
+        M[12 + r] = T[dim * n + r];
+    }
+}
+void extract(const float* M, int dim, float* T) {
+    const int n = dim + 1;
+    for (int i = 0; i < n * n; ++i) T[i] = 0.f;
+    for (int r = 0; r < dim; ++r) {
+        for (int c = 0; c < dim; ++c) T[c * n + r] = M[c * 4 + r];
+        T[dim * n + r] = M[12 + r];
+    }
+    T[n * n - 1] = 1.f;
+}
+float det3(const float* M) {
+    return M[0] * (M[5] * M[10] - M[9] * M[6]) - M[4] * (M[1] * M[10] - M[9] * M[2]) + M[8] * (M[1] * M[6] - M[5] * M[2]);
+}
+void quat_from_M(const float* T, float* q) {
+    float R[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r][c] = T[c * 4 + r];
+    float t = R[0][0] + R[1][1] + R[2][2];
+    if (t > 0.f) {
+        t = std::sqrt(t + 1.f);
+        q[0] = 0.5f * t;
+        t = 0.5f / t;
+        q[1] = (R[2][1] - R[1][2]) * t;
+        q[2] = (R[0][2] - R[2][0]) * t;
+        q[3] = (R[1][0] - R[0][1]) * t;
+    } else {
+        int i = 0;
+        if (R[1][1] > R[0][0]) i = 1;
+        if (R[2][2] > R[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.f);
+        q[1 + i] = 0.5f * t;
+        t = 0.5f / t;
+        q[0] = (R[k][j] - R[j][k]) * t;
+        q[1 + j] = (R[j][i] + R[i][j]) * t;
+        q[1 + k] = (R[k][i] + R[i][k]) * t;
+    }
+}
+
+int32_t validate_config(const b200icp_config* c, std::string& why) {
+    if (!c) return why = "null config", B200ICP_ERR_INVALID_ARG;
+    if (c->dim != 2 && c->dim != 3) return why = "dim must be 2 or 3", B200ICP_ERR_INVALID_ARG;
+    if (c->knn < 1 || c->knn > 32) return why = "knn must be in [1, 32]", B200ICP_ERR_INVALID_ARG;
+    if (!(c->max_dist > 0.f)) return why = "maxDist must be positive", B200ICP_ERR_INVALID_ARG;
+    if (c->n_outlier < 0 || c->n_outlier > B200ICP_MAX_OUTLIER_FILTERS) return why = "too many outlier filters", B200ICP_ERR_INVALID_ARG;
+    int quant = 0;
+    for (int f = 0; f < c->n_outlier; ++f) {
+        const int kd = c->outlier_kind[f];
+        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_MEDIAN_DIST) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
+        if (kd == B200ICP_OUTLIER_TRIMMED_DIST || kd == B200ICP_OUTLIER_MEDIAN_DIST) ++quant;
+        if (kd == B200ICP_OUTLIER_TRIMMED_DIST && !(c->outlier_param[f] >= 0.f && c->outlier_param[f] <= 1.f))
+            return why = "quantile must be between 0 and 1", B200ICP_ERR_INVALID_ARG;
+    }
+    if (quant > 1) return why = "at most one quantile-based outlier filter (Trimmed or Median) per chain", B200ICP_ERR_NOT_IMPLEMENTED;
+    if (c->minimizer < B200ICP_MIN_POINT_TO_PLANE || c->minimizer > B200ICP_MIN_IDENTITY) return why = "unknown error minimizer", B200ICP_ERR_INVALID_ARG;
+    if (c->use_differential && (c->smooth_length < 1 || c->smooth_length > 7)) return why = "smoothLength must be in [1, 7]", B200ICP_ERR_INVALID_ARG;
+    return B200ICP_OK;
+}
+
+int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
+    IcpBuffers& b = ctx->buf;
+    const int rows = ctx->cfg.dim + 1;
+    const int K = ctx->cfg.knn;
+    if (!b.state) {
+        CK(cudaMalloc((void**)&b.state, kStateBytes));
+        CK(cudaMalloc((void**)&b.hist, 3 * kHistBins * sizeof(uint32_t)));
+        CK(cudaMemset(b.hist, 0, 3 * kHistBins * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
+    }
+    if (nq > b.cap_nq) {
+        const int64_t cap = nq + nq / 4 + 1024;
+        cudaFree(b.reading_in);
+        cudaFree(b.reading);
+        cudaFree(b.reading_tmp);
+        cudaFree(b.match_pos);
+        cudaFree(b.match_d2);
+        b.reading_in = nullptr;
+        b.reading = b.reading_tmp = nullptr;
+        b.match_pos = nullptr;
+        b.match_d2 = nullptr;
+        b.cap_nq = 0;
+        CK(cudaMalloc((void**)&b.reading_in, (size_t)cap * rows * sizeof(float)));
+        CK(cudaMalloc((void**)&b.reading, (size_t)cap * sizeof(float4)));
+        CK(cudaMalloc((void**)&b.reading_tmp, (size_t)cap * sizeof(float4)));
+        CK(cudaMalloc((void**)&b.match_pos, (size_t)cap * K * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&b.match_d2, (size_t)cap * K * sizeof(float)));
+        b.cap_nq = cap;
+    }
+    return B200ICP_OK;
+}
+
+int32_t ensure_query_buffers(b200icp_ctx* ctx, int64_t nq, int k) {
+    if (nq * k > ctx->cap_out) {
+        const int64_t cap = nq * k + nq * k / 4 + 1024;
+        cudaFree(ctx->d_out_ids);
+        cudaFree(ctx->d_out_d2);
+        ctx->d_out_ids = nullptr;
+        ctx->d_out_d2 = nullptr;
+        ctx->cap_out = 0;
+        CK(cudaMalloc((void**)&ctx->d_out_ids, (size_t)cap * sizeof(int32_t)));
+        CK(cudaMalloc((void**)&ctx->d_out_d2, (size_t)cap * sizeof(float)));
+        ctx->cap_out = cap;
+    }
+    if (nq > ctx->cap_q4) {
+        const int64_t cap = nq + nq / 4 + 1024;
+        cudaFree(ctx->d_q4);
+        ctx->d_q4 = nullptr;
+        ctx->cap_q4 = 0;
+        CK(cudaMalloc((void**)&ctx->d_q4, (size_t)cap * sizeof(float4)));
+        ctx->cap_q4 = cap;
+    }
+    return B200ICP_OK;
+}
+
+int bits_for(uint64_t v) {
+    int b = 1;
+    while (b < 32 && (1ull << b) < v) ++b;
+    return b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t b200icp_abi_version(void) { return B200ICP_ABI_VERSION; }
+
+void b200icp_config_default(b200icp_config* cfg, int32_t dim) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->dim = dim;
+    cfg->knn = 1;
+    cfg->max_dist = INFINITY;
+    cfg->epsilon = 0.f;
+    cfg->n_outlier = 1;
+    cfg->outlier_kind[0] = B200ICP_OUTLIER_TRIMMED_DIST;
+    cfg->outlier_param[0] = 0.85f;
+    cfg->minimizer = B200ICP_MIN_POINT_TO_PLANE;
+    cfg->max_iteration_count = 40;
+    cfg->use_differential = 1;
+    cfg->min_diff_rot_err = 1e-3f;
+    cfg->min_diff_trans_err = 1e-3f;
+    cfg->smooth_length = 3;
+    cfg->use_bound = 0;
+    cfg->max_rotation_norm = 1.f;
+    cfg->max_translation_norm = 1.f;
+    cfg->sort_reading = 1;
+    cfg->use_graph = 1;
+    cfg->nn_variant = 0;
+}
+
+const char* b200icp_last_error(const b200icp_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_create_error.c_str();
+}
+
+int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** out) {
+    std::lock_guard<std::mutex> lock(g_create_mutex);
+    if (!out) return g_create_error = "null out pointer", B200ICP_ERR_INVALID_ARG;
+    *out = nullptr;
+    std::string why;
+    const int32_t vc = validate_config(cfg, why);
+    if (vc != B200ICP_OK) return g_create_error = why, vc;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        g_create_error = std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+        return B200ICP_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) return g_create_error = "bad device ordinal", B200ICP_ERR_INVALID_ARG;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return g_create_error = cudaGetErrorString(e), B200ICP_ERR_CUDA;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return g_create_error = cudaGetErrorString(e), B200ICP_ERR_CUDA;
+    if (prop.major != 10) {
+        g_create_error = "libb200icp.so is built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return B200ICP_ERR_CUDA;
+    }
+    b200icp_ctx* ctx = new b200icp_ctx();
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    IcpParams& p = ctx->prm;
+    p.dim = cfg->dim;
+    p.knn = cfg->knn;
+    p.max_r2 = std::isinf(cfg->max_dist) ? INFINITY : cfg->max_dist * cfg->max_dist;
+    p.n_outlier = cfg->n_outlier;
+    p.quantile_filter = -1;
+    p.quantile = 0.f;
+    for (int f = 0; f < cfg->n_outlier; ++f) {
+        p.outlier_kind[f] = cfg->outlier_kind[f];
+        p.outlier_param[f] = cfg->outlier_param[f];
+        if (cfg->outlier_kind[f] == B200ICP_OUTLIER_TRIMMED_DIST) {
+            p.quantile_filter = f;
+            p.quantile = cfg->outlier_param[f];
+        } else if (cfg->outlier_kind[f] == B200ICP_OUTLIER_MEDIAN_DIST) {
+            p.quantile_filter = f;
+            p.quantile = 0.5f;
+        }
+    }
+    p.minimizer = cfg->minimizer;
+    p.max_iteration_count = cfg->max_iteration_count;
+    p.use_differential = cfg->use_differential;
+    p.min_diff_rot_err = cfg->min_diff_rot_err;
+    p.min_diff_trans_err = cfg->min_diff_trans_err;
+    p.smooth_length = cfg->smooth_length;
+    p.use_bound = cfg->use_bound;
+    p.max_rotation_norm = cfg->max_rotation_norm;
+    p.max_translation_norm = cfg->max_translation_norm;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev_map0) == cudaSuccess && cudaEventCreate(&ctx->ev_map1) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_pinned, 4096) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->d_scalar_nq, 64) == cudaSuccess;
+    if (!ok) {
+        g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        b200icp_destroy(ctx);
+        return B200ICP_ERR_CUDA;
+    }
+    *out = ctx;
+    return B200ICP_OK;
+}
+
+void b200icp_destroy(b200icp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    grid_free(ctx->map);
+    grid_free(ctx->aux);
+    IcpBuffers& b = ctx->buf;
+    cudaFree(b.reading_in);
+    cudaFree(b.reading);
+    cudaFree(b.reading_tmp);
+    cudaFree(b.match_pos);
+    cudaFree(b.match_d2);
+    cudaFree(b.hist);
+    cudaFree(b.partials);
+    cudaFree(b.state);
+    cudaFree(b.trace);
+    cudaFree(ctx->d_stage_a);
+    cudaFree(ctx->d_stage_b);
+    cudaFree(ctx->d_out_ids);
+    cudaFree(ctx->d_out_d2);
+    cudaFree(ctx->d_q4);
+    cudaFree(ctx->d_scalar_nq);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (cudaEvent_t ev : ctx->nn_events) cudaEventDestroy(ev);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_map0) cudaEventDestroy(ctx->ev_map0);
+    if (ctx->ev_map1) cudaEventDestroy(ctx->ev_map1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* b200icp_stream(b200icp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t b200icp_set_profiling(b200icp_ctx* ctx, int32_t on) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    ctx->profiling = on != 0;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_get_timing(const b200icp_ctx* ctx, b200icp_timing* out) {
+    if (!ctx || !out) return B200ICP_ERR_INVALID_ARG;
+    *out = ctx->timing;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_set_trace(b200icp_ctx* ctx, int32_t on) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    ctx->want_trace = on != 0;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_get_trace(const b200icp_ctx* ctx, float* out, int32_t max_iterations) {
+    if (!ctx || (max_iterations > 0 && !out)) return -1;
+    const int dim = ctx->cfg.dim, n = dim + 1;
+    const int have = (int)(ctx->h_trace.size() / 16);
+    const int cnt = std::min(have, std::max(max_iterations, 0));
+    for (int i = 0; i < cnt; ++i) extract(ctx->h_trace.data() + (size_t)i * 16, dim, out + (size_t)i * n * n);
+    return have;
+}
+
+int64_t b200icp_map_size(const b200icp_ctx* ctx) { return (ctx && ctx->has_map) ? ctx->map_n : 0; }
+
+int32_t b200icp_get_map_mean(const b200icp_ctx* ctx, float* mean3) {
+    if (!ctx || !mean3) return B200ICP_ERR_INVALID_ARG;
+    for (int d = 0; d < 3; ++d) mean3[d] = ctx->map.mean[d];
+    return B200ICP_OK;
+}
+
+int32_t b200icp_get_grid_info(const b200icp_ctx* ctx, float* cell_edge, int32_t* dims3) {
+    if (!ctx || !ctx->has_map) return B200ICP_ERR_NO_MAP;
+    if (cell_edge) *cell_edge = ctx->map.view.h;
+    if (dims3) {
+        dims3[0] = ctx->map.view.nx;
+        dims3[1] = ctx->map.view.ny;
+        dims3[2] = ctx->map.view.nz;
+    }
+    return B200ICP_OK;
+}
+
+int32_t b200icp_set_map_device(b200icp_ctx* ctx, const float* d_features, int32_t feature_rows, const float* d_normals,
+                               int64_t n) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (feature_rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
+    if (n < 0 || n > (int64_t)INT32_MAX - 1024) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad point count");
+    if (n == 0) return B200ICP_OK;  // LPM: "Ignoring attempt to create a map from an empty cloud"
+    if (!d_features) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null features");
+    CK(cudaSetDevice(ctx->device));
+    float cell_hint = 0.f;
+    if (const char* env = getenv("B200ICP_CELL_EDGE")) cell_hint = (float)atof(env);
+    CK(cudaEventRecord(ctx->ev_map0, ctx->stream));
+    CK(grid_build(ctx->map, d_features, feature_rows, ctx->cfg.dim, d_normals, n, /*centre=*/true, cell_hint, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_map1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_map0, ctx->ev_map1);
+    ctx->timing.setmap_ms = ms;
+    ctx->has_map = true;
+    ctx->map_n = n;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_set_map(b200icp_ctx* ctx, const float* features, int32_t feature_rows, const float* normals, int64_t n) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (feature_rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
+    if (n < 0 || n > (int64_t)INT32_MAX - 1024) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad point count");
+    if (n == 0) return B200ICP_OK;
+    if (!features) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null features");
+    CK(cudaSetDevice(ctx->device));
+    const size_t fb = (size_t)n * feature_rows * sizeof(float);
+    const size_t nb = (size_t)n * ctx->cfg.dim * sizeof(float);
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb));
+    CK(cudaMemcpyAsync(ctx->d_stage_a, features, fb, cudaMemcpyHostToDevice, ctx->stream));
+    if (normals) {
+        CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, nb));
+        CK(cudaMemcpyAsync(ctx->d_stage_b, normals, nb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return b200icp_set_map_device(ctx, ctx->d_stage_a, feature_rows, normals ? ctx->d_stage_b : nullptr, n);
+}
+
+// The ICP loop on device-resident reading points.
+static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int32_t rows, int64_t nq, const float* T_init,
+                                  float* T_out, b200icp_result* result) {
+    const int dim = ctx->cfg.dim;
+    const IcpParams& p = ctx->prm;
+    IcpBuffers& b = ctx->buf;
+    cudaStream_t s = ctx->stream;
+
+    float Tinit4[16], Tmean[16], Tmean_inv[16], Tpre[16];
+    embed(T_init, dim, Tinit4);
+    mat4_identity(Tmean);
+    mat4_identity(Tmean_inv);
+    for (int d = 0; d < dim; ++d) {
+        Tmean[12 + d] = ctx->map.mean[d];
+        Tmean_inv[12 + d] = -ctx->map.mean[d];
+    }
+    mat4_mul(Tmean_inv, Tinit4, Tpre);
+    if (std::fabs(1.f - det3(Tpre)) > 1e-3f)
+        return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
+    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE && !ctx->map.has_normals)
+        return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Cannot find descriptor normals in reference (PointToPlaneErrorMinimizer)");
+
+    // state image
+    IcpState* hs = reinterpret_cast<IcpState*>(ctx->h_pinned);
+    memset(ctx->h_pinned, 0, kStateBytes);
+    mat4_identity(hs->T);
+    hs->nq = (int)nq;
+    quat_from_M(hs->T, hs->dq[0]);
+    hs->dcount = 1;
+    quat_from_M(hs->T, hs->bq0);
+    CK(cudaEventRecord(ctx->ev_begin, s));
+    CK(cudaMemcpyAsync(b.state, ctx->h_pinned, kStateBytes, cudaMemcpyHostToDevice, s));
+    int launches = 0;
+
+    // reading -> refMean frame (+ optional cell sort for locality; results do not depend on order
+    // except for the summation order of the error terms)
+    const bool do_sort = ctx->cfg.sort_reading != 0 && nq > 1024;
+    if (do_sort) {
+        CK(ensure_scratch(ctx->map, nq));
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s));
+        const GridView& v = ctx->map.view;
+        CK(sort_pairs(ctx->map, ctx->map.keys_in, ctx->map.keys_out, ctx->map.vals_in, ctx->map.vals_out, nq,
+                      bits_for((uint64_t)v.nx * v.ny * v.nz), s));
+        CK(launch_gather_reading(b.reading_tmp, ctx->map.vals_out, b.reading, nq, s));
+        launches += 4;
+    } else {
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading, nullptr, nullptr, nullptr, nq, s));
+        launches += 1;
+    }
+
+    const bool fixed_count = p.max_iteration_count > 0 && !p.use_differential && !p.use_bound;
+    const int hard_cap = p.max_iteration_count > 0 ? p.max_iteration_count : 10000;
+    const int chunk = fixed_count ? hard_cap : 8;
+    if (ctx->profiling && (int)ctx->nn_events.size() < 2 * hard_cap) {
+        const size_t want = (size_t)2 * std::min(hard_cap, 512);
+        while (ctx->nn_events.size() < want) {
+            cudaEvent_t ev;
+            CK(cudaEventCreate(&ev));
+            ctx->nn_events.push_back(ev);
+        }
+    }
+    constexpr int kTraceCap = 512;
+    if (ctx->want_trace && !b.trace) CK(cudaMalloc((void**)&b.trace, (size_t)kTraceCap * 16 * sizeof(float)));
+    float* const trace_keep = b.trace;
+    if (!ctx->want_trace || hard_cap > kTraceCap) b.trace = nullptr;  // kernels see null -> no trace writes
+    struct RestoreTrace {
+        IcpBuffers& b;
+        float* keep;
+        ~RestoreTrace() { b.trace = keep; }
+    } restore_trace{b, trace_keep};
+    IcpState* out_state = reinterpret_cast<IcpState*>(ctx->h_pinned + kStateBytes);
+    int issued = 0, nn_timed = 0;
+    while (true) {
+        const int upto = std::min(hard_cap, issued + chunk);
+        for (; issued < upto; ++issued) {
+            const bool time_it = ctx->profiling && (size_t)(2 * nn_timed + 1) < ctx->nn_events.size();
+            if (time_it) CK(cudaEventRecord(ctx->nn_events[2 * nn_timed], s));
+            CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
+                          /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+            if (time_it) {
+                CK(cudaEventRecord(ctx->nn_events[2 * nn_timed + 1], s));
+                ++nn_timed;
+            }
+            ++launches;
+            CK(launch_iteration_tail(p, ctx->map, b, issued, s, &launches));
+        }
+        CK(cudaMemcpyAsync(out_state, b.state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->ev_end, s));
+        CK(cudaStreamSynchronize(s));
+        if (out_state->done || issued >= hard_cap) break;
+    }
+
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
+    ctx->timing.total_ms = ms;
+    ctx->timing.kernel_launches = launches;
+    ctx->timing.nn_ms_sum = 0.f;
+    ctx->timing.nn_launches = 0;
+    const int executed = out_state->iter;
+    for (int i = 0; i < nn_timed && i < std::max(executed, 1); ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ctx->nn_events[2 * i], ctx->nn_events[2 * i + 1]) == cudaSuccess) {
+            ctx->timing.nn_ms_sum += t;
+            ctx->timing.nn_launches += 1;
+        }
+    }
+
+    ctx->h_trace.clear();
+    if (b.trace && executed > 0) {
+        ctx->h_trace.resize((size_t)executed * 16);
+        CK(cudaMemcpy(ctx->h_trace.data(), b.trace, ctx->h_trace.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (result) {
+        result->overlap = out_state->overlap;
+        result->point_used_ratio = out_state->used_ratio;
+        result->iterations = out_state->iter;
+        result->max_iter_reached = out_state->max_iter_reached;
+        result->pairs_last_iter = out_state->pairs;
+    }
+    // return T_refIn_refMean * T_iter * T_refMean_dataIn
+    float tmp[16], Tfull[16];
+    mat4_mul(out_state->T, Tpre, tmp);
+    mat4_mul(Tmean, tmp, Tfull);
+    extract(Tfull, dim, T_out);
+    switch (out_state->status) {
+        case B200ICP_OK: return B200ICP_OK;
+        case B200ICP_ERR_CONVERGENCE: return fail(ctx, B200ICP_ERR_CONVERGENCE, "ConvergenceError: no point to minimize / no outlier to filter");
+        case B200ICP_ERR_BOUND: return fail(ctx, B200ICP_ERR_BOUND, "ConvergenceError: limit out of bounds");
+        case B200ICP_ERR_NAN: return fail(ctx, B200ICP_ERR_NAN, "ConvergenceError: abs rotation/translation norm not a number");
+        case B200ICP_ERR_TRANSFORM: return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
+        default: return fail(ctx, out_state->status, "device reported an error");
+    }
+}
+
+static int32_t register_checks(b200icp_ctx* ctx, const float* reading, int32_t rows, int64_t nq, float* T_out) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (!T_out) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null T_out");
+    if (rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
+    if (nq < 0 || nq > (int64_t)INT32_MAX / 64) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad point count");
+    if (nq > 0 && !reading) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null reading");
+    if (!ctx->has_map) {  // LPM ICPSequence::operator(): no map -> identity
+        float I4[16];
+        mat4_identity(I4);
+        extract(I4, ctx->cfg.dim, T_out);
+        return fail(ctx, B200ICP_ERR_NO_MAP, "no map: call b200icp_set_map first");
+    }
+    if (nq == 0) return fail(ctx, B200ICP_ERR_CONVERGENCE, "ConvergenceError: empty reading (no point to minimize)");
+    return B200ICP_OK;
+}
+
+int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_t feature_rows, int64_t nq, const float* T_init,
+                                float* T_out, b200icp_result* result) {
+    if (result) memset(result, 0, sizeof(*result));
+    const int32_t rc = register_checks(ctx, d_reading, feature_rows, nq, T_out);
+    if (rc != B200ICP_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int32_t eb = ensure_icp_buffers(ctx, nq);
+    if (eb != B200ICP_OK) return eb;
+    return register_on_device(ctx, d_reading, feature_rows, nq, T_init, T_out, result);
+}
+
+int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq, const float* T_init,
+                         float* T_out, b200icp_result* result) {
+    if (result) memset(result, 0, sizeof(*result));
+    const int32_t rc = register_checks(ctx, reading, feature_rows, nq, T_out);
+    if (rc != B200ICP_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int32_t eb = ensure_icp_buffers(ctx, nq);
+    if (eb != B200ICP_OK) return eb;
+    CK(cudaMemcpyAsync(ctx->buf.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return register_on_device(ctx, ctx->buf.reading_in, feature_rows, nq, T_init, T_out, result);
+}
+
+static int32_t run_queries(b200icp_ctx* ctx, GridIndex& g, const float* queries, int32_t rows, int64_t nq, int dim, int k,
+                           float max_r2, bool centre, int32_t* ids, float* dists2) {
+    const int32_t eb = ensure_query_buffers(ctx, nq, k);
+    if (eb != B200ICP_OK) return eb;
+    cudaStream_t s = ctx->stream;
+    const size_t qb = (size_t)nq * rows * sizeof(float);
+    CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, qb));
+    CK(cudaMemcpyAsync(ctx->d_stage_b, queries, qb, cudaMemcpyHostToDevice, s));
+    float Tpre[16];
+    mat4_identity(Tpre);
+    if (centre)
+        for (int d = 0; d < dim; ++d) Tpre[12 + d] = -g.mean[d];
+    CK(launch_prep_reading(ctx->d_stage_b, rows, dim, Tpre, ctx->d_q4, nullptr, nullptr, nullptr, nq, s));
+    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+    *h_nq = (int)nq;
+    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(launch_knn(g.view, ctx->d_q4, ctx->d_scalar_nq, (int)nq, nullptr, k, max_r2, ctx->d_out_ids, ctx->d_out_d2,
+                  /*want_original_ids=*/1, ctx->cfg.nn_variant, s));
+    CK(cudaMemcpyAsync(ids, ctx->d_out_ids, (size_t)nq * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(dists2, ctx->d_out_d2, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_match(b200icp_ctx* ctx, const float* queries, int32_t feature_rows, int64_t nq, int32_t* ids, float* dists2) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (feature_rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
+    if (nq < 0 || (nq > 0 && (!queries || !ids || !dists2))) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad arguments");
+    if (!ctx->has_map) return fail(ctx, B200ICP_ERR_NO_MAP, "no map: call b200icp_set_map first");
+    if (nq == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    return run_queries(ctx, ctx->map, queries, feature_rows, nq, ctx->cfg.dim, ctx->cfg.knn, ctx->prm.max_r2, true, ids, dists2);
+}
+
+int32_t b200icp_knn(b200icp_ctx* ctx, const float* ref, int32_t ref_rows, int64_t nref, const float* queries, int32_t query_rows,
+                    int64_t nq, int32_t dim, int32_t k, float max_radius, int32_t* ids, float* dists2) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if ((dim != 2 && dim != 3) || ref_rows < dim || query_rows < dim) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad dim / rows");
+    if (k < 1 || k > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "k must be in [1, 32]");
+    if (nref <= 0 || nref > (int64_t)INT32_MAX - 1024 || !ref) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad reference cloud");
+    if (nq < 0 || (nq > 0 && (!queries || !ids || !dists2))) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad queries");
+    if (!(max_radius > 0.f)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "max_radius must be positive (inf allowed)");
+    if (nq == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)nref * ref_rows * sizeof(float);
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, rb));
+    CK(cudaMemcpyAsync(ctx->d_stage_a, ref, rb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(grid_build(ctx->aux, ctx->d_stage_a, ref_rows, dim, nullptr, nref, /*centre=*/false, 0.f, ctx->stream));
+    const float max_r2 = std::isinf(max_radius) ? INFINITY : max_radius * max_radius;
+    return run_queries(ctx, ctx->aux, queries, query_rows, nq, dim, k, max_r2, false, ids, dists2);
+}
+
+int32_t b200icp_transform(b200icp_ctx* ctx, float* features, int32_t feature_rows, float* normals, int64_t n, const float* T) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = feature_rows - 1;
+    if ((dim != 2 && dim != 3) || !T || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad arguments");
+    float M[16];
+    embed(T, dim, M);
+    if (std::fabs(1.f - det3(M)) > 1e-3f)
+        return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
+    if (n == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t fb = (size_t)n * feature_rows * sizeof(float), nb = (size_t)n * dim * sizeof(float);
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb));
+    CK(cudaMemcpyAsync(ctx->d_stage_a, features, fb, cudaMemcpyHostToDevice, s));
+    if (normals) {
+        CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, nb));
+        CK(cudaMemcpyAsync(ctx->d_stage_b, normals, nb, cudaMemcpyHostToDevice, s));
+    }
+    CK(launch_transform(ctx->d_stage_a, feature_rows, dim, normals ? ctx->d_stage_b : nullptr, n, M, s));
+    CK(cudaMemcpyAsync(features, ctx->d_stage_a, fb, cudaMemcpyDeviceToHost, s));
+    if (normals) CK(cudaMemcpyAsync(normals, ctx->d_stage_b, nb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows, float* d_normals, int64_t n,
+                                 const float* T) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = feature_rows - 1;
+    if ((dim != 2 && dim != 3) || !T || n < 0 || (n > 0 && !d_features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad arguments");
+    float M[16];
+    embed(T, dim, M);
+    if (std::fabs(1.f - det3(M)) > 1e-3f)
+        return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_transform(d_features, feature_rows, dim, d_normals, n, M, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ICP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// common.cuh -- types shared by the translation units of libb200icp.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "b200icp.h"
+
+namespace b200 {
+
+constexpr int kSMs = 148;        // B200
+constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
+constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
+constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)
+constexpr int kMaxAccBlocks = 2 * kSMs;
+
+// Uniform grid over a cloud; points sorted by linear cell id (x fastest), so the cells
+// [x0..x1] of one (y, z) row are one contiguous run of `pts`.
+struct GridView {
+    const float4* __restrict__ pts;          // (x, y, z, bit-cast original index), cell-sorted
+    const uint32_t* __restrict__ cell_start; // n_cells + 1 exclusive prefix
+    float ox, oy, oz;                        // grid origin (min corner)
+    float h, inv_h;                          // cell edge
+    float slack;                             // safety margin in grid units for boundary distances
+    int nx, ny, nz;
+    int n;                                   // points
+};
+
+// Device-resident state of one registration (one `icp(input)` call). 4x4 column-major always;
+// the 2-D case is embedded (z row/column = identity) so one set of kernels serves both.
+struct IcpState {
+    float T[16];  // T_iter (refMean frame)
+    int nq;       // reading points (device-side so captured graphs do not depend on it)
+    int iter;     // iterations completed
+    int done;     // loop finished (checker said stop, or error)
+    int status;   // b200icp_status
+    int max_iter_reached;
+    float overlap, used_ratio;
+    long long pairs;
+    float limit;       // last quantile limit (diagnostic)
+    unsigned int ticket;  // last-block election in the accumulate kernel
+    int counter;          // CounterTransformationChecker
+    int dcount;           // DifferentialTransformationChecker ring fill
+    float dq[8][4];
+    float dt[8][3];
+    float bq0[4];
+    float bt0[3];
+};
+
+static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");
+
+// Radix-select bookkeeping; lives kSelectOffset bytes after IcpState in the same allocation.
+struct SelectState {
+    uint32_t bin[3];
+    uint32_t rank[3];
+    unsigned int ticket[3];
+    uint32_t pad;
+};
+constexpr int kSelectOffset = 512;
+constexpr int kStateBytes = 1024;
+
+struct IcpParams {  // by-value kernel argument, constant for the life of a context
+    int dim;
+    int knn;
+    float max_r2;  // maxDist^2 (inf allowed)
+    int n_outlier;
+    int outlier_kind[B200ICP_MAX_OUTLIER_FILTERS];
+    float outlier_param[B200ICP_MAX_OUTLIER_FILTERS];
+    int quantile_filter;  // index of the Trimmed/Median filter or -1
+    float quantile;       // ratio (Trimmed) or 0.5 (Median)
+    int minimizer;
+    int max_iteration_count;
+    int use_differential;
+    float min_diff_rot_err, min_diff_trans_err;
+    int smooth_length;
+    int use_bound;
+    float max_rotation_norm, max_translation_norm;
+};
+
+// ---- index.cu ------------------------------------------------------------------------------
+struct GridIndex {
+    GridView view{};
+    float4* pts = nullptr;
+    float4* normals = nullptr;  // cell-sorted (nx, ny, nz, 0) or null
+    uint32_t* cell_start = nullptr;
+    int64_t cap_pts = 0, cap_normals = 0, cap_cells = 0;
+    bool has_normals = false;
+    // scratch
+    float4* tmp_pts = nullptr;
+    uint32_t *keys_in = nullptr, *keys_out = nullptr, *vals_in = nullptr, *vals_out = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    unsigned long long* d_reduce = nullptr;  // bbox + fixed-point sums
+    int64_t cap_scratch = 0;
+    float mean[3] = {0, 0, 0};
+};
+
+// Build the grid over `n` points given as `rows` floats each (device pointer, first dim floats
+// are coordinates).  centre=true subtracts the fixed-point mean first (ICPSequence::setMap).
+// cell_hint <= 0 lets the builder choose the cell edge.
+cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, const float* d_normals,
+                       int64_t n, bool centre, float cell_hint, cudaStream_t s);
+void grid_free(GridIndex& g);
+cudaError_t ensure_scratch(GridIndex& g, int64_t n);  // sort scratch for at least n pairs
+
+// Stable radix sort of (key, value) pairs on `s` using g's scratch (also used to cell-sort readings).
+cudaError_t sort_pairs(GridIndex& scratch_owner, uint32_t* keys_in, uint32_t* keys_out,
+                       uint32_t* vals_in, uint32_t* vals_out, int64_t n, int end_bit, cudaStream_t s);
+
+// ---- knn.cu --------------------------------------------------------------------------------
+// queries: float4 (x, y, z, *) in the grid's frame, optionally moved by state->T first.
+// out_ids: cell-sorted positions (want_original_ids = 0) or original indices (1); -1 = none.
+cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_nq, int nq_capacity,
+                       const IcpState* d_state_or_null, int k, float max_r2, int32_t* out_ids,
+                       float* out_d2, int want_original_ids, int variant, cudaStream_t s);
+
+// ---- icp.cu --------------------------------------------------------------------------------
+struct IcpBuffers {
+    float* reading_in = nullptr;   // raw (dim+1) x N upload
+    float4* reading = nullptr;     // reading in the refMean frame (T_refMean_dataIn applied)
+    float4* reading_tmp = nullptr; // pre-sort
+    int32_t* match_pos = nullptr;  // knn x N
+    float* match_d2 = nullptr;
+    uint32_t* hist = nullptr;      // max_iter x 3 x kHistBins
+    double* partials = nullptr;    // kMaxAccBlocks x kAccSlots
+    IcpState* state = nullptr;
+    float* trace = nullptr;        // max_iter x 16
+    int64_t cap_nq = 0;
+    int cap_iter = 0;
+};
+
+cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
+                                float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,
+                                uint32_t* d_vals, int64_t nq, cudaStream_t s);
+cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,
+                                  cudaStream_t s);
+cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
+                                  cudaStream_t s, int* launches);
+cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals, int64_t n,
+                             const float* T16 /*host, 4x4*/, cudaStream_t s);
+
+}  // namespace b200

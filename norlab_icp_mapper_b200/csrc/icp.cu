@@ -1,0 +1,750 @@
+// icp.cu -- everything in one ICP iteration after the correspondence search, plus the rigid
+// transform kernels.
+//
+// Replaces, inside PM::ICPSequence::operator() (/root/reference/norlab_icp_mapper/Mapper.cpp:213,
+// restated in SURVEY.md 3.2 / Appendix A):
+//   outlierFilters.compute          -> exact radix-select of the distance quantile (3 histogram
+//                                      passes over the float bit patterns) + threshold tests
+//   ErrorElements + errorMinimizer  -> one fused gather/accumulate kernel: 27 point-to-plane sums
+//                                      (21 upper-triangular entries of A, 6 of b) or 16
+//                                      point-to-point sums, fp32 products accumulated in fp64 with
+//                                      warp shuffles, fixed-order two-stage reduction (run-to-run
+//                                      deterministic), then the last block solves the 6x6 / SVD,
+//                                      composes T_iter and runs the transformation checkers.
+//   transformations.apply           -> fused into the consumers (T_iter is applied on the fly).
+// No host synchronisation happens inside the loop: the state lives in IcpState on the device.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+struct Mat4 {
+    float m[16];
+};
+
+__device__ __forceinline__ float3 apply_T(const float* __restrict__ T, const float4& r) {
+    float3 o;
+    o.x = __fadd_rn(__fmaf_rn(T[8], r.z, __fmaf_rn(T[4], r.y, __fmul_rn(T[0], r.x))), T[12]);
+    o.y = __fadd_rn(__fmaf_rn(T[9], r.z, __fmaf_rn(T[5], r.y, __fmul_rn(T[1], r.x))), T[13]);
+    o.z = __fadd_rn(__fmaf_rn(T[10], r.z, __fmaf_rn(T[6], r.y, __fmul_rn(T[2], r.x))), T[14]);
+    return o;
+}
+
+// ---- reading preparation: (dim+1) x N upload -> float4 in the refMean frame ---------------------
+__global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restrict__ in, int rows, int dim, Mat4 Tpre,
+                                                           float4* __restrict__ out, GridView g, uint32_t* __restrict__ keys,
+                                                           uint32_t* __restrict__ vals, long long nq) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float4 r;
+    r.x = in[i * rows + 0];
+    r.y = in[i * rows + 1];
+    r.z = (dim == 3) ? in[i * rows + 2] : 0.f;
+    r.w = 1.f;
+    const float3 p = apply_T(Tpre.m, r);
+    out[i] = make_float4(p.x, p.y, p.z, 1.f);
+    if (keys) {
+        const float lim = 16777216.f;
+        const int cx = min((int)floorf(fminf(fmaxf((p.x - g.ox) * g.inv_h, 0.f), lim)), g.nx - 1);
+        const int cy = min((int)floorf(fminf(fmaxf((p.y - g.oy) * g.inv_h, 0.f), lim)), g.ny - 1);
+        const int cz = min((int)floorf(fminf(fmaxf((p.z - g.oz) * g.inv_h, 0.f), lim)), g.nz - 1);
+        keys[i] = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_reading_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ perm,
+                                                             float4* __restrict__ out, long long nq) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < nq) out[i] = in[perm[i]];
+}
+
+// ---- RigidTransformation::compute (Mapper.cpp:197,221; Map.cpp:523,525) --------------------------
+__global__ void __launch_bounds__(256) transform_kernel(float* __restrict__ feat, int rows, int dim, float* __restrict__ normals,
+                                                        long long n, Mat4 T) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 r;
+    r.x = feat[i * rows + 0];
+    r.y = feat[i * rows + 1];
+    r.z = (dim == 3) ? feat[i * rows + 2] : 0.f;
+    r.w = 1.f;
+    const float3 p = apply_T(T.m, r);
+    feat[i * rows + 0] = p.x;
+    feat[i * rows + 1] = p.y;
+    if (dim == 3) feat[i * rows + 2] = p.z;
+    if (normals) {
+        float4 v;
+        v.x = normals[i * dim + 0];
+        v.y = normals[i * dim + 1];
+        v.z = (dim == 3) ? normals[i * dim + 2] : 0.f;
+        const float* M = T.m;
+        const float ox = __fmaf_rn(M[8], v.z, __fmaf_rn(M[4], v.y, __fmul_rn(M[0], v.x)));
+        const float oy = __fmaf_rn(M[9], v.z, __fmaf_rn(M[5], v.y, __fmul_rn(M[1], v.x)));
+        const float oz = __fmaf_rn(M[10], v.z, __fmaf_rn(M[6], v.y, __fmul_rn(M[2], v.x)));
+        normals[i * dim + 0] = ox;
+        normals[i * dim + 1] = oy;
+        if (dim == 3) normals[i * dim + 2] = oz;
+    }
+}
+
+// ---- exact quantile of the finite squared distances (LPM Matches::getDistsQuantile) -------------
+// Block-wide: smallest bin b with cumulative count > rank.  Returns total; writes bin/residual.
+__device__ uint32_t block_pick(const uint32_t* hist, int nbins, uint32_t rank, bool rank_is_fraction, float q,
+                               uint32_t* out_bin, uint32_t* out_res, uint32_t* s_scan /* 256+2 */) {
+    const int tid = threadIdx.x;
+    const int per = nbins / 256;
+    uint32_t loc[8];
+    uint32_t sum = 0;
+    for (int j = 0; j < per; ++j) {
+        loc[j] = __ldcg(hist + tid * per + j);
+        sum += loc[j];
+    }
+    s_scan[tid] = sum;
+    __syncthreads();
+    // inclusive Hillis-Steele scan over 256 partials
+    for (int off = 1; off < 256; off <<= 1) {
+        uint32_t v = (tid >= off) ? s_scan[tid - off] : 0u;
+        __syncthreads();
+        s_scan[tid] += v;
+        __syncthreads();
+    }
+    const uint32_t total = s_scan[255];
+    if (rank_is_fraction) {
+        // idx = size_t(values.size() * quantile) evaluated in fp32; quantile == 1 -> max element
+        rank = (q == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * q);
+        if (total && rank >= total) rank = total - 1u;
+    }
+    const uint32_t incl = s_scan[tid];
+    const uint32_t excl = incl - sum;
+    if (total && rank >= excl && rank < incl) {
+        uint32_t run = excl;
+        for (int j = 0; j < per; ++j) {
+            if (rank < run + loc[j]) {
+                *out_bin = (uint32_t)(tid * per + j);
+                *out_res = rank - run;
+                break;
+            }
+            run += loc[j];
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+
+template <int PASS>
+__global__ void __launch_bounds__(256) hist_kernel(IcpState* __restrict__ st, SelectState* __restrict__ sel,
+                                                   const float* __restrict__ d2, int knn, uint32_t* __restrict__ hist, float quantile) {
+    if (st->done) return;
+    __shared__ uint32_t sh[kHistBins];
+    __shared__ uint32_t s_scan[258];
+    __shared__ bool s_last;
+    const int nbins = (PASS == 2) ? 1024 : kHistBins;
+    for (int i = threadIdx.x; i < nbins; i += 256) sh[i] = 0u;
+    __syncthreads();
+    const long long m = (long long)st->nq * knn;
+    uint32_t prefix = 0;
+    if (PASS == 1) prefix = sel->bin[0];
+    if (PASS == 2) prefix = (sel->bin[0] << 11) | sel->bin[1];
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < m; e += (long long)gridDim.x * 256ll) {
+        const uint32_t bits = __float_as_uint(d2[e]);
+        if (PASS == 0) {
+            if (bits < 0x7f800000u) atomicAdd(&sh[bits >> 21], 1u);
+        } else if (PASS == 1) {
+            if ((bits >> 21) == prefix) atomicAdd(&sh[(bits >> 10) & 2047u], 1u);
+        } else {
+            if ((bits >> 10) == prefix) atomicAdd(&sh[bits & 1023u], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t* gh = hist + PASS * kHistBins;
+    for (int i = threadIdx.x; i < nbins; i += 256)
+        if (sh[i]) atomicAdd(&gh[i], sh[i]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&sel->ticket[PASS], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ uint32_t s_bin, s_res;
+    if (threadIdx.x == 0) {
+        s_bin = 0;
+        s_res = 0;
+    }
+    __syncthreads();
+    const uint32_t rank_in = (PASS == 0) ? 0u : sel->rank[PASS - 1];
+    const uint32_t total = block_pick(gh, nbins, rank_in, PASS == 0, quantile, &s_bin, &s_res, s_scan);
+    for (int i = threadIdx.x; i < nbins; i += 256) gh[i] = 0u;  // ready for the next iteration
+    if (threadIdx.x == 0) {
+        sel->bin[PASS] = s_bin;
+        sel->rank[PASS] = s_res;
+        sel->ticket[PASS] = 0u;
+        if (PASS == 0 && total == 0) {  // LPM: ConvergenceError("no outlier to filter")
+            st->status = B200ICP_ERR_CONVERGENCE;
+            st->done = 1;
+        }
+        if (PASS == 2) st->limit = __uint_as_float((sel->bin[0] << 21) | (sel->bin[1] << 10) | s_bin);
+    }
+}
+
+// ---- small dense linear algebra on one thread ----------------------------------------------------
+__device__ int llt_f32(float* A, int n) {
+    for (int k = 0; k < n; ++k) {
+        float x = A[k * n + k];
+        for (int j = 0; j < k; ++j) x -= A[j * n + k] * A[j * n + k];
+        if (!(x > 0.f)) return k + 1;
+        x = sqrtf(x);
+        A[k * n + k] = x;
+        for (int i = k + 1; i < n; ++i) {
+            float v = A[k * n + i];
+            for (int j = 0; j < k; ++j) v -= A[j * n + i] * A[j * n + k];
+            A[k * n + i] = v / x;
+        }
+    }
+    return 0;
+}
+
+__device__ void jacobi_eig_f64(double* A, int n, double* V, double* w) {
+    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) off += A[q * n + p] * A[q * n + p];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[q * n + p];
+                if (fabs(apq) < 1e-300) continue;
+                const double app = A[p * n + p], aqq = A[q * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = A[p * n + k], akq = A[q * n + k];
+                    A[p * n + k] = c * akp - s * akq;
+                    A[q * n + k] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = A[k * n + p], aqk = A[k * n + q];
+                    A[k * n + p] = c * apk - s * aqk;
+                    A[k * n + q] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = V[p * n + k], vkq = V[q * n + k];
+                    V[p * n + k] = c * vkp - s * vkq;
+                    V[q * n + k] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+
+// LPM solvePossiblyUnderdeterminedLinearSystem: llt when A is invertible, else min-norm solution.
+__device__ void solve_normal_eq(const float* A_in, const float* b, float* x, int n) {
+    float L[36];
+    for (int i = 0; i < n * n; ++i) L[i] = A_in[i];
+    float maxdiag = 0.f;
+    for (int i = 0; i < n; ++i) maxdiag = fmaxf(maxdiag, fabsf(A_in[i * n + i]));
+    bool ok = (llt_f32(L, n) == 0);
+    if (ok) {
+        const float thr = (float)n * 1.1920929e-7f * maxdiag;
+        for (int i = 0; i < n; ++i)
+            if (!(L[i * n + i] * L[i * n + i] > thr)) ok = false;
+    }
+    if (ok) {
+        float y[6];
+        for (int i = 0; i < n; ++i) {
+            float v = b[i];
+            for (int j = 0; j < i; ++j) v -= L[j * n + i] * y[j];
+            y[i] = v / L[i * n + i];
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            float v = y[i];
+            for (int j = i + 1; j < n; ++j) v -= L[i * n + j] * x[j];
+            x[i] = v / L[i * n + i];
+        }
+        bool bad = false;
+        for (int i = 0; i < n; ++i)
+            if (isnan(x[i])) bad = true;
+        if (!bad) return;
+    }
+    double Ad[36], V[36], w[6];
+    for (int i = 0; i < n * n; ++i) Ad[i] = (double)A_in[i];
+    jacobi_eig_f64(Ad, n, V, w);
+    double wmax = 0.0;
+    for (int i = 0; i < n; ++i) wmax = fmax(wmax, fabs(w[i]));
+    double xd[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = 0; e < n; ++e) {
+        if (!(fabs(w[e]) > 1e-6 * wmax)) continue;
+        double proj = 0.0;
+        for (int i = 0; i < n; ++i) proj += V[e * n + i] * (double)b[i];
+        proj /= w[e];
+        for (int i = 0; i < n; ++i) xd[i] += proj * V[e * n + i];
+    }
+    for (int i = 0; i < n; ++i) x[i] = (float)xd[i];
+}
+
+__device__ void quat_from_T(const float* T, float* q /* w x y z */) {
+    float R[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r][c] = T[c * 4 + r];
+    float t = R[0][0] + R[1][1] + R[2][2];
+    if (t > 0.f) {
+        t = sqrtf(t + 1.f);
+        q[0] = 0.5f * t;
+        t = 0.5f / t;
+        q[1] = (R[2][1] - R[1][2]) * t;
+        q[2] = (R[0][2] - R[2][0]) * t;
+        q[3] = (R[1][0] - R[0][1]) * t;
+    } else {
+        int i = 0;
+        if (R[1][1] > R[0][0]) i = 1;
+        if (R[2][2] > R[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrtf(R[i][i] - R[j][j] - R[k][k] + 1.f);
+        q[1 + i] = 0.5f * t;
+        t = 0.5f / t;
+        q[0] = (R[k][j] - R[j][k]) * t;
+        q[1 + j] = (R[j][i] + R[i][j]) * t;
+        q[1 + k] = (R[k][i] + R[i][k]) * t;
+    }
+}
+
+__device__ float quat_angular_distance(const float* a, const float* b) {
+    const float bw = b[0], bx = -b[1], by = -b[2], bz = -b[3];
+    const float w = a[0] * bw - a[1] * bx - a[2] * by - a[3] * bz;
+    const float x = a[0] * bx + a[1] * bw + a[2] * bz - a[3] * by;
+    const float y = a[0] * by + a[2] * bw + a[3] * bx - a[1] * bz;
+    const float z = a[0] * bz + a[3] * bw + a[1] * by - a[2] * bx;
+    return 2.f * atan2f(sqrtf(x * x + y * y + z * z), fabsf(w));
+}
+
+__device__ void mat4_mul(const float* A, const float* B, float* C) {
+    float tmp[16];
+    for (int c = 0; c < 4; ++c)
+        for (int r = 0; r < 4; ++r) {
+            float acc = 0.f;
+            for (int k = 0; k < 4; ++k) acc += A[k * 4 + r] * B[c * 4 + k];
+            tmp[c * 4 + r] = acc;
+        }
+    for (int i = 0; i < 16; ++i) C[i] = tmp[i];
+}
+
+// LPM PointToPlaneErrorMinimizer::compute_in_place tail: solve, AngleAxis / Rotation2D.
+__device__ void delta_point_to_plane(const double* S, int dim, float* dT) {
+    float A6[36], b6[6];
+    for (int c = 0; c < 6; ++c)
+        for (int r = 0; r <= c; ++r) {
+            const float v = (float)S[c * (c + 1) / 2 + r];
+            A6[c * 6 + r] = v;
+            A6[r * 6 + c] = v;
+        }
+    for (int i = 0; i < 6; ++i) b6[i] = (float)S[21 + i];
+    for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
+    if (dim == 3) {
+        float x[6];
+        solve_normal_eq(A6, b6, x, 6);
+        const float nrm2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+        const float ang = sqrtf(nrm2);
+        float ax[3] = {x[0], x[1], x[2]};
+        if (nrm2 > 0.f)
+            for (int d = 0; d < 3; ++d) ax[d] = x[d] / ang;
+        const float s = sinf(ang), c = cosf(ang);
+        const float sx = s * ax[0], sy = s * ax[1], sz = s * ax[2];
+        const float cx = (1.f - c) * ax[0], cy = (1.f - c) * ax[1], cz = (1.f - c) * ax[2];
+        float R[3][3];
+        float tmp = cx * ax[1];
+        R[0][1] = tmp - sz;
+        R[1][0] = tmp + sz;
+        tmp = cx * ax[2];
+        R[0][2] = tmp + sy;
+        R[2][0] = tmp - sy;
+        tmp = cy * ax[2];
+        R[1][2] = tmp - sx;
+        R[2][1] = tmp + sx;
+        R[0][0] = cx * ax[0] + c;
+        R[1][1] = cy * ax[1] + c;
+        R[2][2] = cz * ax[2] + c;
+        bool bad = false;
+        for (int r = 0; r < 3; ++r)
+            for (int cc = 0; cc < 3; ++cc)
+                if (isnan(R[r][cc])) bad = true;
+        if (!bad)
+            for (int r = 0; r < 3; ++r)
+                for (int cc = 0; cc < 3; ++cc) dT[cc * 4 + r] = R[r][cc];
+        for (int d = 0; d < 3; ++d) dT[12 + d] = x[3 + d];
+    } else {
+        // z = 0 embedding: F = [0, 0, c, nx, ny, 0] -> unknowns (theta, tx, ty) are rows 2, 3, 4
+        float A3[9], b3[3], x[3];
+        const int id[3] = {2, 3, 4};
+        for (int c = 0; c < 3; ++c) {
+            for (int r = 0; r < 3; ++r) A3[c * 3 + r] = A6[id[c] * 6 + id[r]];
+            b3[c] = b6[id[c]];
+        }
+        solve_normal_eq(A3, b3, x, 3);
+        const float s = sinf(x[0]), c = cosf(x[0]);
+        dT[0] = c;
+        dT[1] = s;
+        dT[4] = -s;
+        dT[5] = c;
+        dT[12] = x[1];
+        dT[13] = x[2];
+    }
+}
+
+// LPM PointToPointErrorMinimizer::compute_in_place: weighted centroids, SVD of the cross-covariance.
+__device__ void delta_point_to_point(const double* S, int dim, float* dT) {
+    for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
+    const double sw = S[0];
+    double mp[3], mq[3];
+    for (int d = 0; d < 3; ++d) {
+        mp[d] = S[1 + d] / sw;
+        mq[d] = S[4 + d] / sw;
+    }
+    double M[9];
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) M[c * dim + r] = S[7 + c * 3 + r] - sw * mq[r] * mp[c];
+    double MtM[9], V[9], ev[3];
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+            double a = 0;
+            for (int j = 0; j < dim; ++j) a += M[r * dim + j] * M[c * dim + j];
+            MtM[c * dim + r] = a;
+        }
+    jacobi_eig_f64(MtM, dim, V, ev);
+    int order[3] = {0, 1, 2};
+    for (int a = 0; a < dim; ++a)
+        for (int bb = a + 1; bb < dim; ++bb)
+            if (ev[order[bb]] > ev[order[a]]) {
+                const int tt = order[a];
+                order[a] = order[bb];
+                order[bb] = tt;
+            }
+    double U[9], Vs[9];
+    for (int e = 0; e < dim; ++e)
+        for (int r = 0; r < dim; ++r) Vs[e * dim + r] = V[order[e] * dim + r];
+    for (int e = 0; e < dim; ++e) {
+        double u[3] = {0, 0, 0}, nn = 0;
+        for (int r = 0; r < dim; ++r) {
+            for (int c = 0; c < dim; ++c) u[r] += M[c * dim + r] * Vs[e * dim + c];
+            nn += u[r] * u[r];
+        }
+        nn = sqrt(nn);
+        for (int r = 0; r < dim; ++r) U[e * dim + r] = (nn > 0) ? u[r] / nn : 0.0;
+    }
+    if (dim == 3) {
+        double* u0 = U;
+        double* u1 = U + 3;
+        double* u2 = U + 6;
+        const double cx[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+        const double sgn = (cx[0] * u2[0] + cx[1] * u2[1] + cx[2] * u2[2]) < 0 ? -1.0 : 1.0;
+        for (int r = 0; r < 3; ++r) u2[r] = sgn * cx[r];
+    } else {
+        double* u0 = U;
+        double* u1 = U + 2;
+        const double px[2] = {-u0[1], u0[0]};
+        const double sgn = (px[0] * u1[0] + px[1] * u1[1]) < 0 ? -1.0 : 1.0;
+        u1[0] = sgn * px[0];
+        u1[1] = sgn * px[1];
+    }
+    double R[9];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int r = 0; r < dim; ++r)
+            for (int c = 0; c < dim; ++c) {
+                double a = 0;
+                for (int e = 0; e < dim; ++e) a += U[e * dim + r] * Vs[e * dim + c];
+                R[c * dim + r] = a;
+            }
+        const double det = (dim == 2) ? R[0] * R[3] - R[2] * R[1]
+                                      : R[0] * (R[4] * R[8] - R[7] * R[5]) - R[3] * (R[1] * R[8] - R[7] * R[2]) +
+                                            R[6] * (R[1] * R[5] - R[4] * R[2]);
+        if (det >= 0) break;
+        for (int c = 0; c < dim; ++c) Vs[(dim - 1) * dim + c] = -Vs[(dim - 1) * dim + c];
+    }
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) dT[c * 4 + r] = (float)R[c * dim + r];
+    for (int r = 0; r < dim; ++r) {
+        float a = 0.f;
+        for (int c = 0; c < dim; ++c) a += dT[c * 4 + r] * (float)mp[c];
+        dT[12 + r] = (float)mq[r] - a;
+    }
+}
+
+// Tail of one iteration, run by one thread: T_iter = dT * T_iter, then the checkers
+// (LPM TransformationCheckersImpl.cpp: Counter, Differential, Bound).
+__device__ void finish_iteration(const IcpParams& prm, IcpState* st, const double* S, int n_sums, float* trace) {
+    const double pairs = S[n_sums - 1];
+    const double wsum = S[n_sums - 2];
+    const double denom = (double)prm.knn * (double)st->nq;
+    if (pairs == 0.0) {  // LPM: ConvergenceError("ErrorMnimizer: no point to minimize")
+        st->status = B200ICP_ERR_CONVERGENCE;
+        st->done = 1;
+        return;
+    }
+    float dT[16];
+    if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE)
+        delta_point_to_plane(S, prm.dim, dT);
+    else if (prm.minimizer == B200ICP_MIN_POINT_TO_POINT)
+        delta_point_to_point(S, prm.dim, dT);
+    else
+        for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
+    float T[16];
+    for (int i = 0; i < 16; ++i) T[i] = st->T[i];
+    mat4_mul(dT, T, T);
+    for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+    st->pairs = (long long)pairs;
+    st->used_ratio = (float)pairs / (float)denom;
+    st->overlap = (float)wsum / (float)denom;
+    const int it = st->iter;
+    if (trace)
+        for (int i = 0; i < 16; ++i) trace[(size_t)it * 16 + i] = T[i];
+    st->iter = it + 1;
+
+    bool iterate = true;
+    if (prm.max_iteration_count > 0) {
+        st->counter += 1;
+        if (st->counter >= prm.max_iteration_count) {
+            st->max_iter_reached = 1;
+            st->done = 1;
+            return;
+        }
+    }
+    if (prm.use_differential) {
+        const int smooth = min(max(prm.smooth_length, 1), 7);
+        const int slot = st->dcount % 8;
+        quat_from_T(T, st->dq[slot]);
+        for (int d = 0; d < 3; ++d) st->dt[slot][d] = T[12 + d];
+        st->dcount += 1;
+        float vr = 0.f, vt = 0.f;
+        if (st->dcount > smooth) {
+            for (int j = st->dcount - 1; j >= st->dcount - smooth; --j) {
+                const int a = j % 8, b = (j - 1) % 8;
+                vr += fabsf(quat_angular_distance(st->dq[a], st->dq[b]));
+                const float dx = st->dt[a][0] - st->dt[b][0], dy = st->dt[a][1] - st->dt[b][1], dz = st->dt[a][2] - st->dt[b][2];
+                vt += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+            }
+            vr /= (float)smooth;
+            vt /= (float)smooth;
+            if (vr < prm.min_diff_rot_err && vt < prm.min_diff_trans_err) iterate = false;
+        }
+        if (isnan(vr) || isnan(vt)) {
+            st->status = B200ICP_ERR_NAN;
+            st->done = 1;
+            return;
+        }
+    }
+    if (prm.use_bound) {
+        float qc[4];
+        quat_from_T(T, qc);
+        const float vr = quat_angular_distance(qc, st->bq0);
+        float vt = 0.f;
+        for (int d = 0; d < 3; ++d) vt += (T[12 + d] - st->bt0[d]) * (T[12 + d] - st->bt0[d]);
+        vt = sqrtf(vt);
+        if (isnan(vr) || isnan(vt)) {
+            st->status = B200ICP_ERR_NAN;
+            st->done = 1;
+            return;
+        }
+        if (vr > prm.max_rotation_norm || vt > prm.max_translation_norm) {
+            st->status = B200ICP_ERR_BOUND;
+            st->done = 1;
+            return;
+        }
+    }
+    if (prm.max_iteration_count <= 0 && !prm.use_differential) iterate = false;
+    if (!iterate) {
+        st->done = 1;
+        return;
+    }
+    // the next transformations.apply(stepReading, T_iter) checks orthonormality
+    const float det = T[0] * (T[5] * T[10] - T[9] * T[6]) - T[4] * (T[1] * T[10] - T[9] * T[2]) + T[8] * (T[1] * T[6] - T[5] * T[2]);
+    if (fabsf(1.f - det) > 1e-3f) {
+        st->status = B200ICP_ERR_TRANSFORM;
+        st->done = 1;
+    }
+}
+
+// ---- ErrorElements + error minimiser sums --------------------------------------------------------
+// MIN: 0 point-to-plane (29 sums), 1 point-to-point (18 sums), 2 identity (2 sums).
+template <int MIN>
+struct SumLayout;
+template <>
+struct SumLayout<0> {
+    static constexpr int N = 29;
+};
+template <>
+struct SumLayout<1> {
+    static constexpr int N = 18;
+};
+template <>
+struct SumLayout<2> {
+    static constexpr int N = 2;
+};
+
+template <int MIN>
+__global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView g, const float4* __restrict__ nrm,
+                                                         const float4* __restrict__ reading, const int32_t* __restrict__ mpos,
+                                                         const float* __restrict__ md2, IcpState* __restrict__ st,
+                                                         double* __restrict__ partials, float* __restrict__ trace) {
+    if (st->done) return;
+    constexpr int NS = SumLayout<MIN>::N;
+    const int nq = st->nq;
+    const int K = prm.knn;
+    const long long m = (long long)nq * K;
+    float T[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) T[i] = st->T[i];
+    const float qlimit = st->limit;
+
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) acc[i] = 0.0;
+
+    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < m; e += (long long)gridDim.x * 256ll) {
+        const int pos = mpos[e];
+        if (pos < 0) continue;
+        const float d = md2[e];
+        if (d == CUDART_INF_F) continue;
+        float w = 1.f;
+        for (int f = 0; f < prm.n_outlier; ++f) {
+            const float p = prm.outlier_param[f];
+            bool keep = true;
+            switch (prm.outlier_kind[f]) {
+                case B200ICP_OUTLIER_TRIMMED_DIST: keep = d <= qlimit; break;
+                case B200ICP_OUTLIER_MEDIAN_DIST: keep = d <= p * qlimit; break;
+                case B200ICP_OUTLIER_MAX_DIST: keep = d <= p * p; break;
+                case B200ICP_OUTLIER_MIN_DIST: keep = d >= p * p; break;
+            }
+            w *= keep ? 1.f : 0.f;
+        }
+        if (w == 0.f) continue;
+        const long long i = e / K;
+        const float3 p = apply_T(T, __ldg(reading + i));
+        const float4 q = __ldg(g.pts + pos);
+        if (MIN == 0) {
+            const float4 n = __ldg(nrm + pos);
+            float F[6];
+            F[0] = p.y * n.z - p.z * n.y;
+            F[1] = p.z * n.x - p.x * n.z;
+            F[2] = p.x * n.y - p.y * n.x;
+            F[3] = n.x;
+            F[4] = n.y;
+            F[5] = n.z;
+            const float dot = (p.x - q.x) * n.x + (p.y - q.y) * n.y + (p.z - q.z) * n.z;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const float wf = w * F[c];
+#pragma unroll
+                for (int r = 0; r <= c; ++r) acc[c * (c + 1) / 2 + r] += (double)(wf * F[r]);
+                acc[21 + c] -= (double)(wf * dot);
+            }
+        } else if (MIN == 1) {
+            const float pv[3] = {p.x, p.y, p.z}, qv[3] = {q.x, q.y, q.z};
+            acc[0] += (double)w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                acc[1 + c] += (double)(w * pv[c]);
+                acc[4 + c] += (double)(w * qv[c]);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += (double)w * (double)qv[r] * (double)pv[c];
+            }
+        }
+        acc[NS - 2] += (double)w;
+        acc[NS - 1] += 1.0;
+    }
+
+    // warp shuffle reduction, then one partial per block
+    __shared__ double s_part[8][NS];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) s_part[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v += s_part[wv][threadIdx.x];
+        partials[(size_t)blockIdx.x * kAccSlots + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // fixed-order final reduction -> deterministic sums
+    __shared__ double s_sum[kAccSlots];
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partials + (size_t)b * kAccSlots + threadIdx.x);
+        s_sum[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->ticket = 0u;
+        finish_iteration(prm, st, s_sum, NS, trace);
+    }
+}
+
+}  // namespace
+
+// ---- host launchers -------------------------------------------------------------------------------
+cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16, float4* d_out,
+                                const GridView* g_for_keys, uint32_t* d_keys, uint32_t* d_vals, int64_t nq, cudaStream_t s) {
+    if (nq <= 0) return cudaSuccess;
+    Mat4 T;
+    memcpy(T.m, Tpre16, sizeof(T.m));
+    GridView g{};
+    if (g_for_keys) g = *g_for_keys;
+    prep_reading_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, rows, dim, T, d_out, g, g_for_keys ? d_keys : nullptr,
+                                                                      d_vals, (long long)nq);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq, cudaStream_t s) {
+    if (nq <= 0) return cudaSuccess;
+    gather_reading_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, d_perm, d_out, (long long)nq);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals, int64_t n, const float* T16, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    Mat4 T;
+    memcpy(T.m, T16, sizeof(T.m));
+    transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_feat, rows, dim, d_normals, (long long)n, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it, cudaStream_t s, int* launches) {
+    (void)it;
+    SelectState* sel = reinterpret_cast<SelectState*>(reinterpret_cast<char*>(b.state) + kSelectOffset);
+    const long long m = (long long)b.cap_nq * p.knn;
+    if (p.quantile_filter >= 0) {
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((m + 255) / 256, kSMs));
+        hist_kernel<0><<<blocks, 256, 0, s>>>(b.state, sel, b.match_d2, p.knn, b.hist, p.quantile);
+        hist_kernel<1><<<blocks, 256, 0, s>>>(b.state, sel, b.match_d2, p.knn, b.hist, p.quantile);
+        hist_kernel<2><<<blocks, 256, 0, s>>>(b.state, sel, b.match_d2, p.knn, b.hist, p.quantile);
+        *launches += 3;
+    }
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((m + 255) / 256, kMaxAccBlocks));
+    const float4* nrm = g.has_normals ? g.normals : nullptr;
+    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE)
+        accumulate_kernel<0><<<blocks, 256, 0, s>>>(p, g.view, nrm, b.reading, b.match_pos, b.match_d2, b.state, b.partials, b.trace);
+    else if (p.minimizer == B200ICP_MIN_POINT_TO_POINT)
+        accumulate_kernel<1><<<blocks, 256, 0, s>>>(p, g.view, nrm, b.reading, b.match_pos, b.match_d2, b.state, b.partials, b.trace);
+    else
+        accumulate_kernel<2><<<blocks, 256, 0, s>>>(p, g.view, nrm, b.reading, b.match_pos, b.match_d2, b.state, b.partials, b.trace);
+    *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace b200

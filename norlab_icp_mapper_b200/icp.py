@@ -1,0 +1,173 @@
+"""Python face of the B200 ICP core, shaped like the reference's use of `PM::ICPSequence`
+(/root/reference/norlab_icp_mapper/Mapper.h:23): `setMap(cloud)` (Map.cpp:111,178,528,581),
+`icp(input)` (Mapper.cpp:213) and `errorMinimizer->getOverlap()` (Mapper.cpp:219).
+
+Clouds are numpy arrays of shape (N, dim+1), C-contiguous fp32 -- byte-identical to the reference's
+column-major (dim+1) x N `DataPoints::features`.  Transforms are returned as ordinary (dim+1, dim+1)
+numpy matrices (row-major view of the math matrix).  Everything runs in libb200icp.so on the GPU;
+errors that libpointmatcher raises as C++ exceptions surface as B200ICPError with the C-ABI status.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._abi import Config, Result, Timing, make_config  # noqa: F401  (re-exported)
+from ._lib import B200ICPError, load
+
+
+def _cloud(a, rows=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or (rows is not None and a.shape[1] != rows):
+        raise ValueError(f"expected an (N, {rows}) array, got {a.shape}")
+    return a
+
+
+def _T_to_colmajor(T, n):
+    T = np.asarray(T, dtype=np.float32)
+    if T.shape != (n, n):
+        raise ValueError(f"expected a ({n}, {n}) transform")
+    return np.ascontiguousarray(T.T).ravel()
+
+
+class ICP:
+    """One `PM::ICPSequence`: a context bound to one GPU and one stream."""
+
+    def __init__(self, cfg: Config, device: int = 0):
+        self._L = load()
+        self.cfg = cfg
+        self.dim = cfg.dim
+        self.n = cfg.dim + 1
+        h = C.c_void_p()
+        rc = self._L.b200icp_create(C.byref(cfg), device, C.byref(h))
+        if rc != _abi.OK:
+            raise B200ICPError(rc, self._L.b200icp_last_error(None).decode())
+        self._h = h
+        self.last_result = Result()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200icp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _abi.OK:
+            raise B200ICPError(rc, self._L.b200icp_last_error(self._h).decode())
+
+    # -- icp.setMap(cloud) -------------------------------------------------------------------
+    def set_map(self, features, normals=None):
+        features = _cloud(features, self.n)
+        nptr = None
+        if normals is not None:
+            normals = _cloud(normals, self.dim)
+            if len(normals) != len(features):
+                raise ValueError("normals and features differ in length")
+            nptr = normals.ctypes.data
+        self._check(self._L.b200icp_set_map(self._h, features.ctypes.data, self.n, nptr, len(features)))
+        return len(features) > 0
+
+    def set_map_device(self, d_features_ptr, n, d_normals_ptr=None):
+        self._check(self._L.b200icp_set_map_device(self._h, d_features_ptr, self.n, d_normals_ptr, n))
+
+    def has_map(self):
+        return self._L.b200icp_map_size(self._h) > 0
+
+    def map_mean(self):
+        m = np.zeros(3, np.float32)
+        self._check(self._L.b200icp_get_map_mean(self._h, m.ctypes.data))
+        return m
+
+    def grid_info(self):
+        h = C.c_float()
+        dims = np.zeros(3, np.int32)
+        self._check(self._L.b200icp_get_grid_info(self._h, C.byref(h), dims.ctypes.data))
+        return h.value, tuple(int(x) for x in dims)
+
+    # -- correction = icp(input) ---------------------------------------------------------------
+    def __call__(self, reading, T_init=None):
+        reading = _cloud(reading, self.n)
+        tptr = None
+        if T_init is not None:
+            T_cm = _T_to_colmajor(T_init, self.n)
+            tptr = T_cm.ctypes.data
+        T_out = np.zeros(self.n * self.n, np.float32)
+        res = Result()
+        rc = self._L.b200icp_register(self._h, reading.ctypes.data, self.n, len(reading), tptr, T_out.ctypes.data, C.byref(res))
+        self.last_result = res
+        self._check(rc)
+        return T_out.reshape(self.n, self.n).T.copy()
+
+    def register_device(self, d_reading_ptr, nq, T_init=None):
+        tptr = None
+        if T_init is not None:
+            T_cm = _T_to_colmajor(T_init, self.n)
+            tptr = T_cm.ctypes.data
+        T_out = np.zeros(self.n * self.n, np.float32)
+        res = Result()
+        rc = self._L.b200icp_register_device(self._h, d_reading_ptr, self.n, nq, tptr, T_out.ctypes.data, C.byref(res))
+        self.last_result = res
+        self._check(rc)
+        return T_out.reshape(self.n, self.n).T.copy()
+
+    def get_overlap(self):
+        """errorMinimizer->getOverlap() of the last registration (Mapper.cpp:219)."""
+        return float(self.last_result.overlap)
+
+    # -- matcher->findClosests / Nabo::NNS::knn ------------------------------------------------
+    def match(self, queries):
+        queries = _cloud(queries, self.n)
+        k = self.cfg.knn
+        ids = np.empty((len(queries), k), np.int32)
+        d2 = np.empty((len(queries), k), np.float32)
+        self._check(self._L.b200icp_match(self._h, queries.ctypes.data, self.n, len(queries), ids.ctypes.data, d2.ctypes.data))
+        return ids, d2
+
+    def knn(self, ref, queries, k, dim=None, max_radius=float("inf")):
+        ref, queries = _cloud(ref), _cloud(queries)
+        dim = dim or self.dim
+        ids = np.empty((len(queries), k), np.int32)
+        d2 = np.empty((len(queries), k), np.float32)
+        self._check(self._L.b200icp_knn(self._h, ref.ctypes.data, ref.shape[1], len(ref), queries.ctypes.data,
+                                        queries.shape[1], len(queries), dim, k, max_radius, ids.ctypes.data, d2.ctypes.data))
+        return ids, d2
+
+    # -- RigidTransformation::compute ------------------------------------------------------------
+    def transform(self, features, T, normals=None):
+        features = _cloud(features).copy()
+        rows = features.shape[1]
+        T_cm = _T_to_colmajor(T, rows)
+        nptr = None
+        if normals is not None:
+            normals = _cloud(normals, rows - 1).copy()
+            nptr = normals.ctypes.data
+        self._check(self._L.b200icp_transform(self._h, features.ctypes.data, rows, nptr, len(features), T_cm.ctypes.data))
+        return features, normals
+
+    # -- instrumentation ---------------------------------------------------------------------------
+    def stream(self):
+        return self._L.b200icp_stream(self._h)
+
+    def set_profiling(self, on=True):
+        self._check(self._L.b200icp_set_profiling(self._h, int(on)))
+
+    def set_trace(self, on=True):
+        self._check(self._L.b200icp_set_trace(self._h, int(on)))
+
+    def trace(self):
+        have = self._L.b200icp_get_trace(self._h, None, 0)
+        if have <= 0:
+            return np.zeros((0, self.n, self.n), np.float32)
+        buf = np.zeros((have, self.n * self.n), np.float32)
+        self._L.b200icp_get_trace(self._h, buf.ctypes.data, have)
+        return buf.reshape(have, self.n, self.n).transpose(0, 2, 1).copy()
+
+    def timing(self):
+        t = Timing()
+        self._check(self._L.b200icp_get_timing(self._h, C.byref(t)))
+        return t
