@@ -110,7 +110,9 @@ typedef struct b200icp_timing {
     int32_t nn_launches;  /* how many launches nn_ms_sum covers                                    */
     int32_t kernel_launches; /* kernels launched by the call (all of them ours + the sort)         */
     float setmap_ms;      /* last b200icp_set_map*: mean-centre + index build                      */
-    int32_t reserved[3];
+    float select_ms_sum;  /* sum over iterations of the quantile-select kernel (profiling on)      */
+    float acc_ms_sum;     /* sum over iterations of the accumulate/solve kernel (profiling on)     */
+    int32_t reserved[1];
 } b200icp_timing;
 
 typedef struct b200icp_ctx b200icp_ctx;

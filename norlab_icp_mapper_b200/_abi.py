@@ -56,7 +56,9 @@ class Timing(C.Structure):
         ("nn_launches", C.c_int32),
         ("kernel_launches", C.c_int32),
         ("setmap_ms", C.c_float),
-        ("reserved", C.c_int32 * 3),
+        ("select_ms_sum", C.c_float),
+        ("acc_ms_sum", C.c_float),
+        ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -306,6 +306,7 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     ok = ok && cudaEventCreate(&ctx->ev_map0) == cudaSuccess && cudaEventCreate(&ctx->ev_map1) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_pinned, 4096) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_scalar_nq, 64) == cudaSuccess;
+    ok = ok && icp_device_setup() == cudaSuccess;
     if (!ok) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         b200icp_destroy(ctx);
@@ -374,6 +375,13 @@ int32_t b200icp_get_trace(const b200icp_ctx* ctx, float* out, int32_t max_iterat
     const int cnt = std::min(have, std::max(max_iterations, 0));
     for (int i = 0; i < cnt; ++i) extract(ctx->h_trace.data() + (size_t)i * 16, dim, out + (size_t)i * n * n);
     return have;
+}
+
+/* development aid (not in the public header): globaltimer stamps of the last iteration, see B200_STAMP */
+int32_t b200icp_debug_stamps(const b200icp_ctx* ctx, unsigned long long* out32) {
+    if (!ctx || !out32) return B200ICP_ERR_INVALID_ARG;
+    memcpy(out32, ctx->h_pinned + kStateBytes + kDebugOffset, 32 * sizeof(unsigned long long));
+    return B200ICP_OK;
 }
 
 int64_t b200icp_map_size(const b200icp_ctx* ctx) { return (ctx && ctx->has_map) ? ctx->map_n : 0; }
@@ -488,8 +496,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     const bool fixed_count = p.max_iteration_count > 0 && !p.use_differential && !p.use_bound;
     const int hard_cap = p.max_iteration_count > 0 ? p.max_iteration_count : 10000;
     const int chunk = fixed_count ? hard_cap : 8;
-    if (ctx->profiling && (int)ctx->nn_events.size() < 2 * hard_cap) {
-        const size_t want = (size_t)2 * std::min(hard_cap, 512);
+    if (ctx->profiling && (int)ctx->nn_events.size() < 4 * hard_cap) {
+        const size_t want = (size_t)4 * std::min(hard_cap, 512);
         while (ctx->nn_events.size() < want) {
             cudaEvent_t ev;
             CK(cudaEventCreate(&ev));
@@ -510,18 +518,23 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     while (true) {
         const int upto = std::min(hard_cap, issued + chunk);
         for (; issued < upto; ++issued) {
-            const bool time_it = ctx->profiling && (size_t)(2 * nn_timed + 1) < ctx->nn_events.size();
-            if (time_it) CK(cudaEventRecord(ctx->nn_events[2 * nn_timed], s));
-            CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
-                          /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+            const bool time_it = ctx->profiling && (size_t)(4 * nn_timed + 3) < ctx->nn_events.size();
+            cudaEvent_t* ev = time_it ? &ctx->nn_events[4 * nn_timed] : nullptr;
+            if (time_it) CK(cudaEventRecord(ev[0], s));
+            if (issued > 0 && p.knn == 1 && !(ctx->cfg.nn_variant & 2))  // warm: previous matches bound the search
+                CK(launch_nn1_warm(ctx->map.view, b.reading, (int)nq, b.state, p.max_r2, b.match_pos, b.match_d2, ctx->cfg.nn_variant, s));
+            else
+                CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
+                              /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+            if (time_it) CK(cudaEventRecord(ev[1], s));
+            ++launches;
+            CK(launch_iteration_tail(p, ctx->map, b, issued, s, &launches, time_it ? ev[2] : nullptr));
             if (time_it) {
-                CK(cudaEventRecord(ctx->nn_events[2 * nn_timed + 1], s));
+                CK(cudaEventRecord(ev[3], s));
                 ++nn_timed;
             }
-            ++launches;
-            CK(launch_iteration_tail(p, ctx->map, b, issued, s, &launches));
         }
-        CK(cudaMemcpyAsync(out_state, b.state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(out_state, b.state, kStateBytes, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(ctx->ev_end, s));
         CK(cudaStreamSynchronize(s));
         if (out_state->done || issued >= hard_cap) break;
@@ -531,17 +544,19 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
     ctx->timing.total_ms = ms;
     ctx->timing.kernel_launches = launches;
-    ctx->timing.nn_ms_sum = 0.f;
+    ctx->timing.nn_ms_sum = ctx->timing.select_ms_sum = ctx->timing.acc_ms_sum = 0.f;
     ctx->timing.nn_launches = 0;
     const int executed = out_state->iter;
     for (int i = 0; i < nn_timed && i < std::max(executed, 1); ++i) {
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, ctx->nn_events[2 * i], ctx->nn_events[2 * i + 1]) == cudaSuccess) {
+        cudaEvent_t* ev = &ctx->nn_events[4 * i];
+        if (cudaEventElapsedTime(&t, ev[0], ev[1]) == cudaSuccess) {
             ctx->timing.nn_ms_sum += t;
             ctx->timing.nn_launches += 1;
         }
+        if (cudaEventElapsedTime(&t, ev[1], ev[2]) == cudaSuccess) ctx->timing.select_ms_sum += t;
+        if (cudaEventElapsedTime(&t, ev[2], ev[3]) == cudaSuccess) ctx->timing.acc_ms_sum += t;
     }
-
     ctx->h_trace.clear();
     if (b.trace && executed > 0) {
         ctx->h_trace.resize((size_t)executed * 16);

@@ -14,7 +14,8 @@ constexpr int kSMs = 148;        // B200
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
 constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)
-constexpr int kMaxAccBlocks = 2 * kSMs;
+constexpr int kAccBlocks = 128;      // accumulate-kernel grid (one partial each, summed in fixed order)
+constexpr int kMaxAccBlocks = kAccBlocks;
 
 // Uniform grid over a cloud; points sorted by linear cell id (x fastest), so the cells
 // [x0..x1] of one (y, z) row are one contiguous run of `pts`.
@@ -59,6 +60,17 @@ struct SelectState {
     uint32_t pad;
 };
 constexpr int kSelectOffset = 512;
+constexpr int kDebugOffset = 640;  // 32 x uint64 globaltimer stamps of the last iteration (development aid)
+#ifdef B200ICP_STAMPS
+#define B200_STAMP(st, i)                                                                         \
+    do {                                                                                          \
+        unsigned long long t_;                                                                    \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                    \
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(st) + b200::kDebugOffset)[i] = t_; \
+    } while (0)
+#else
+#define B200_STAMP(st, i) do { } while (0)
+#endif
 constexpr int kStateBytes = 1024;
 
 struct IcpParams {  // by-value kernel argument, constant for the life of a context
@@ -116,6 +128,10 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
                        const IcpState* d_state_or_null, int k, float max_r2, int32_t* out_ids,
                        float* out_d2, int want_original_ids, int variant, cudaStream_t s);
 
+// Warm k = 1 search for ICP iterations >= 1: match_pos holds the previous matches on entry.
+cudaError_t launch_nn1_warm(const GridView& g, const float4* d_reading, int nq_capacity, const IcpState* st,
+                            float max_r2, int32_t* match_pos, float* match_d2, int variant, cudaStream_t s);
+
 // ---- icp.cu --------------------------------------------------------------------------------
 struct IcpBuffers {
     float* reading_in = nullptr;   // raw (dim+1) x N upload
@@ -136,8 +152,10 @@ cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const floa
                                 uint32_t* d_vals, int64_t nq, cudaStream_t s);
 cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,
                                   cudaStream_t s);
+cudaError_t icp_device_setup();
+// ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
-                                  cudaStream_t s, int* launches);
+                                  cudaStream_t s, int* launches, cudaEvent_t ev_mid);
 cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals, int64_t n,
                              const float* T16 /*host, 4x4*/, cudaStream_t s);
 

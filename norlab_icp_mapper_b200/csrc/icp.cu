@@ -91,41 +91,60 @@ __global__ void __launch_bounds__(256) transform_kernel(float* __restrict__ feat
 }
 
 // ---- exact quantile of the finite squared distances (LPM Matches::getDistsQuantile) -------------
-// Block-wide: smallest bin b with cumulative count > rank.  Returns total; writes bin/residual.
-__device__ uint32_t block_pick(const uint32_t* hist, int nbins, uint32_t rank, bool rank_is_fraction, float q,
-                               uint32_t* out_bin, uint32_t* out_res, uint32_t* s_scan /* 256+2 */) {
-    const int tid = threadIdx.x;
-    const int per = nbins / 256;
-    uint32_t loc[8];
+// One thread-block cluster of kSelCtas CTAs does the whole 3-pass radix select in ONE launch: each
+// CTA keeps its slice of the distances in shared memory (read from L2 once), builds a shared-memory
+// histogram per pass, merges it into a tiny global histogram, and the hardware cluster barrier
+// separates the passes.  Every CTA then picks the bucket redundantly (2048 words from L2).
+constexpr int kSelCtas = 8;
+constexpr int kSelThreads = 512;
+constexpr int kSelCache = 47 * 1024;  // floats cached per CTA (188 KB of dynamic shared memory)
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// Block-wide (kSelThreads threads): smallest bin with cumulative count > rank.
+__device__ uint32_t select_pick(const uint32_t* hist, int nbins, uint32_t rank, bool rank_is_fraction, float q,
+                                uint32_t* s_bin, uint32_t* s_res, uint32_t* s_warp /* kSelThreads / 32 + 1 */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = nbins / kSelThreads;  // 4 or 2
+    uint32_t loc[4];
     uint32_t sum = 0;
-    for (int j = 0; j < per; ++j) {
-        loc[j] = __ldcg(hist + tid * per + j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        loc[j] = (j < per) ? __ldcg(hist + tid * per + j) : 0u;
         sum += loc[j];
     }
-    s_scan[tid] = sum;
-    __syncthreads();
-    // inclusive Hillis-Steele scan over 256 partials
-    for (int off = 1; off < 256; off <<= 1) {
-        uint32_t v = (tid >= off) ? s_scan[tid - off] : 0u;
-        __syncthreads();
-        s_scan[tid] += v;
-        __syncthreads();
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
     }
-    const uint32_t total = s_scan[255];
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kSelThreads / 32; ++w) {
+        const uint32_t v = s_warp[w];
+        if (w < warp) before += v;
+        total += v;
+    }
+    incl += before;
     if (rank_is_fraction) {
         // idx = size_t(values.size() * quantile) evaluated in fp32; quantile == 1 -> max element
         rank = (q == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * q);
         if (total && rank >= total) rank = total - 1u;
     }
-    const uint32_t incl = s_scan[tid];
     const uint32_t excl = incl - sum;
     if (total && rank >= excl && rank < incl) {
         uint32_t run = excl;
-        for (int j = 0; j < per; ++j) {
-            if (rank < run + loc[j]) {
-                *out_bin = (uint32_t)(tid * per + j);
-                *out_res = rank - run;
-                break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < per && rank >= run && rank < run + loc[j]) {
+                *s_bin = (uint32_t)(tid * per + j);
+                *s_res = rank - run;
             }
             run += loc[j];
         }
@@ -134,80 +153,89 @@ __device__ uint32_t block_pick(const uint32_t* hist, int nbins, uint32_t rank, b
     return total;
 }
 
-
-template <int PASS>
-__global__ void __launch_bounds__(256) hist_kernel(IcpState* __restrict__ st, SelectState* __restrict__ sel,
-                                                   const float* __restrict__ d2, int knn, uint32_t* __restrict__ hist, float quantile) {
-    if (st->done) return;
+__global__ void __cluster_dims__(kSelCtas, 1, 1) __launch_bounds__(kSelThreads)
+    select_kernel(IcpState* __restrict__ st, const float* __restrict__ d2, int knn, uint32_t* __restrict__ hist, float quantile) {
+    if (st->done) return;  // uniform over the cluster
+    const bool stamper = blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamper) B200_STAMP(st, 0);
+    extern __shared__ uint4 s_cache4[];
     __shared__ uint32_t sh[kHistBins];
-    __shared__ uint32_t s_scan[258];
-    __shared__ bool s_last;
-    const int nbins = (PASS == 2) ? 1024 : kHistBins;
-    for (int i = threadIdx.x; i < nbins; i += 256) sh[i] = 0u;
-    __syncthreads();
-    const long long m = (long long)st->nq * knn;
-    uint32_t prefix = 0;
-    if (PASS == 1) prefix = sel->bin[0];
-    if (PASS == 2) prefix = (sel->bin[0] << 11) | sel->bin[1];
-    for (long long e = blockIdx.x * 256ll + threadIdx.x; e < m; e += (long long)gridDim.x * 256ll) {
-        const uint32_t bits = __float_as_uint(d2[e]);
-        if (PASS == 0) {
-            if (bits < 0x7f800000u) atomicAdd(&sh[bits >> 21], 1u);
-        } else if (PASS == 1) {
-            if ((bits >> 21) == prefix) atomicAdd(&sh[(bits >> 10) & 2047u], 1u);
-        } else {
-            if ((bits >> 10) == prefix) atomicAdd(&sh[bits & 1023u], 1u);
-        }
-    }
-    __syncthreads();
-    uint32_t* gh = hist + PASS * kHistBins;
-    for (int i = threadIdx.x; i < nbins; i += 256)
-        if (sh[i]) atomicAdd(&gh[i], sh[i]);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&sel->ticket[PASS], 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    __shared__ uint32_t s_scan[kSelThreads / 32 + 1];
     __shared__ uint32_t s_bin, s_res;
-    if (threadIdx.x == 0) {
-        s_bin = 0;
-        s_res = 0;
+    // this CTA's slice, in units of 4 distances (16-byte loads; the buffer is padded past m)
+    const int m = st->nq * knn;
+    const int m4 = (m + 3) >> 2;
+    const int chunk4 = (m4 + kSelCtas - 1) / kSelCtas;
+    const int lo4 = min(m4, chunk4 * (int)blockIdx.x), hi4 = min(m4, lo4 + chunk4);
+    const int n4 = hi4 - lo4;
+    const bool cached = n4 * 4 <= kSelCache;
+    const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(d2) + lo4;
+    uint32_t prefix = 0, rank = 0, total = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int nbins = (pass == 2) ? 1024 : kHistBins;
+        for (int i = threadIdx.x; i < nbins; i += kSelThreads) sh[i] = 0u;
+        if (threadIdx.x == 0) {
+            s_bin = 0;
+            s_res = 0;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int i = threadIdx.x; i < n4; i += kSelThreads) {
+            uint4 v;
+            if (pass == 0 || !cached) {
+                v = __ldg(src4 + i);
+                // entries past m (padding of the last group of 4) can never be selected
+                const int e = (lo4 + i) * 4;
+                if (e + 1 >= m) v.y = 0xffffffffu;
+                if (e + 2 >= m) v.z = 0xffffffffu;
+                if (e + 3 >= m) v.w = 0xffffffffu;
+                if (cached) s_cache4[i] = v;
+            } else {
+                v = s_cache4[i];
+            }
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t bits = w[c];
+                if (pass == 0) {
+                    if (bits < 0x7f800000u) atomicAdd(&sh[bits >> 21], 1u);  // finite only
+                } else if (pass == 1) {
+                    if ((bits >> 21) == prefix) atomicAdd(&sh[(bits >> 10) & 2047u], 1u);
+                } else {
+                    if ((bits >> 10) == prefix) atomicAdd(&sh[bits & 1023u], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (stamper) B200_STAMP(st, 1 + pass * 3);
+        uint32_t* gh = hist + pass * kHistBins;
+        for (int i = threadIdx.x; i < nbins; i += kSelThreads)
+            if (sh[i]) atomicAdd(&gh[i], sh[i]);
+        __threadfence();
+        cluster_sync_all();
+        if (stamper) B200_STAMP(st, 2 + pass * 3);
+        const uint32_t tot = select_pick(gh, nbins, rank, pass == 0, quantile, &s_bin, &s_res, s_scan);
+        if (pass == 0) total = tot;
+        rank = s_res;
+        prefix = (pass == 0) ? s_bin : ((prefix << (pass == 1 ? 11 : 10)) | s_bin);
+        __syncthreads();
+        if (stamper) B200_STAMP(st, 3 + pass * 3);
     }
-    __syncthreads();
-    const uint32_t rank_in = (PASS == 0) ? 0u : sel->rank[PASS - 1];
-    const uint32_t total = block_pick(gh, nbins, rank_in, PASS == 0, quantile, &s_bin, &s_res, s_scan);
-    for (int i = threadIdx.x; i < nbins; i += 256) gh[i] = 0u;  // ready for the next iteration
-    if (threadIdx.x == 0) {
-        sel->bin[PASS] = s_bin;
-        sel->rank[PASS] = s_res;
-        sel->ticket[PASS] = 0u;
-        if (PASS == 0 && total == 0) {  // LPM: ConvergenceError("no outlier to filter")
+    // everyone has read the histograms: clear them for the next iteration
+    cluster_sync_all();
+    for (int i = blockIdx.x * kSelThreads + threadIdx.x; i < 3 * kHistBins; i += kSelCtas * kSelThreads) hist[i] = 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (total == 0) {  // LPM: ConvergenceError("no outlier to filter")
             st->status = B200ICP_ERR_CONVERGENCE;
             st->done = 1;
         }
-        if (PASS == 2) st->limit = __uint_as_float((sel->bin[0] << 21) | (sel->bin[1] << 10) | s_bin);
+        st->limit = __uint_as_float(prefix);
+        B200_STAMP(st, 10);
     }
 }
 
 // ---- small dense linear algebra on one thread ----------------------------------------------------
-__device__ int llt_f32(float* A, int n) {
-    for (int k = 0; k < n; ++k) {
-        float x = A[k * n + k];
-        for (int j = 0; j < k; ++j) x -= A[j * n + k] * A[j * n + k];
-        if (!(x > 0.f)) return k + 1;
-        x = sqrtf(x);
-        A[k * n + k] = x;
-        for (int i = k + 1; i < n; ++i) {
-            float v = A[k * n + i];
-            for (int j = 0; j < k; ++j) v -= A[j * n + i] * A[j * n + k];
-            A[k * n + i] = v / x;
-        }
-    }
-    return 0;
-}
-
-__device__ void jacobi_eig_f64(double* A, int n, double* V, double* w) {
+__device__ __noinline__ void jacobi_eig_f64(double* A, int n, double* V, double* w) {
     for (int i = 0; i < n * n; ++i) V[i] = 0.0;
     for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
     for (int sweep = 0; sweep < 60; ++sweep) {
@@ -243,35 +271,9 @@ __device__ void jacobi_eig_f64(double* A, int n, double* V, double* w) {
     for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
 }
 
-// LPM solvePossiblyUnderdeterminedLinearSystem: llt when A is invertible, else min-norm solution.
-__device__ void solve_normal_eq(const float* A_in, const float* b, float* x, int n) {
-    float L[36];
-    for (int i = 0; i < n * n; ++i) L[i] = A_in[i];
-    float maxdiag = 0.f;
-    for (int i = 0; i < n; ++i) maxdiag = fmaxf(maxdiag, fabsf(A_in[i * n + i]));
-    bool ok = (llt_f32(L, n) == 0);
-    if (ok) {
-        const float thr = (float)n * 1.1920929e-7f * maxdiag;
-        for (int i = 0; i < n; ++i)
-            if (!(L[i * n + i] * L[i * n + i] > thr)) ok = false;
-    }
-    if (ok) {
-        float y[6];
-        for (int i = 0; i < n; ++i) {
-            float v = b[i];
-            for (int j = 0; j < i; ++j) v -= L[j * n + i] * y[j];
-            y[i] = v / L[i * n + i];
-        }
-        for (int i = n - 1; i >= 0; --i) {
-            float v = y[i];
-            for (int j = i + 1; j < n; ++j) v -= L[i * n + j] * x[j];
-            x[i] = v / L[i * n + i];
-        }
-        bool bad = false;
-        for (int i = 0; i < n; ++i)
-            if (isnan(x[i])) bad = true;
-        if (!bad) return;
-    }
+// Minimum-norm least-squares fallback (rank-deficient A), kept out of line: it is never on the
+// common path and must not inflate the register allocation of the accumulate kernel.
+__device__ __noinline__ void solve_min_norm(const float* A_in, const float* b, float* x, int n) {
     double Ad[36], V[36], w[6];
     for (int i = 0; i < n * n; ++i) Ad[i] = (double)A_in[i];
     jacobi_eig_f64(Ad, n, V, w);
@@ -323,81 +325,148 @@ __device__ float quat_angular_distance(const float* a, const float* b) {
     return 2.f * atan2f(sqrtf(x * x + y * y + z * z), fabsf(w));
 }
 
-__device__ void mat4_mul(const float* A, const float* B, float* C) {
-    float tmp[16];
-    for (int c = 0; c < 4; ++c)
-        for (int r = 0; r < 4; ++r) {
-            float acc = 0.f;
-            for (int k = 0; k < 4; ++k) acc += A[k * 4 + r] * B[c * 4 + k];
-            tmp[c * 4 + r] = acc;
+// LPM PointToPlaneErrorMinimizer::compute_in_place tail: solve, AngleAxis / Rotation2D.
+// Runs on ONE WARP: lane r < 6 owns row r of [A | b] (entries rounded to fp32 like the reference's
+// float matrices), Gauss-Jordan elimination in fp64 with shuffles, everything in registers.  The
+// pivots of the elimination are the squares of the Cholesky diagonal, so the reference's
+// "is A invertible" decision (LLT succeeds) is the same test; the rank-deficient case falls back
+// to the minimum-norm solution on lane 0.  Result: x[6] identical in every lane.
+__device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/) {
+    const unsigned full = 0xffffffffu;
+    const int r = min(lane, 5);
+    double a[7];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const int lo = min(r, c), hi = max(r, c);
+        a[c] = (double)(float)S[hi * (hi + 1) / 2 + lo];
+    }
+    a[6] = (double)(float)S[21 + r];
+    if (dim == 2) {  // z = 0 embedding: rows/columns 0, 1, 5 are empty -> x = 0 there
+        if (r == 0) a[0] = 1.0;
+        if (r == 1) a[1] = 1.0;
+        if (r == 5) a[5] = 1.0;
+    }
+    double diag = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+        if (c == r) diag = fabs(a[c]);
+    double maxdiag = (lane < 6) ? diag : 0.0;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(full, maxdiag, off));
+    maxdiag = fmax(maxdiag, __shfl_xor_sync(full, maxdiag, 8));  // lanes 0..7 hold the max over lanes 0..5 (6, 7 contribute copies of row 5)
+    maxdiag = __shfl_sync(full, maxdiag, 0);
+    const double thr = 6.0 * 1.1920929e-7 * maxdiag;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double pk[7];
+#pragma unroll
+        for (int c = k; c < 7; ++c) pk[c] = __shfl_sync(full, a[c], k);
+        const double piv = pk[k];
+        if (!(piv > thr)) ok = false;
+        if (lane != k) {
+            const double f = a[k] / piv;
+#pragma unroll
+            for (int c = k; c < 7; ++c) a[c] -= f * pk[c];
         }
-    for (int i = 0; i < 16; ++i) C[i] = tmp[i];
+    }
+    double xr = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+        if (c == r) xr = a[6] / a[c];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = (float)__shfl_sync(full, xr, i);
+    bool bad = !ok;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (isnan(x[i])) bad = true;
+    if (bad) {  // rare: rank-deficient normal equations
+        if (lane == 0) {
+            float A6[36], b6[6], xs[6] = {0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < 6; ++c)
+                for (int rr = 0; rr <= c; ++rr) {
+                    const float v = (float)S[c * (c + 1) / 2 + rr];
+                    A6[c * 6 + rr] = v;
+                    A6[rr * 6 + c] = v;
+                }
+            for (int i = 0; i < 6; ++i) b6[i] = (float)S[21 + i];
+            if (dim == 3) {
+                solve_min_norm(A6, b6, xs, 6);
+            } else {
+                float A3[9], b3[3], x3[3];
+                const int id[3] = {2, 3, 4};
+                for (int c = 0; c < 3; ++c) {
+                    for (int rr = 0; rr < 3; ++rr) A3[c * 3 + rr] = A6[id[c] * 6 + id[rr]];
+                    b3[c] = b6[id[c]];
+                }
+                solve_min_norm(A3, b3, x3, 3);
+                xs[2] = x3[0];
+                xs[3] = x3[1];
+                xs[4] = x3[2];
+            }
+            for (int i = 0; i < 6; ++i) s_x[i] = xs[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = s_x[i];
+    }
 }
 
-// LPM PointToPlaneErrorMinimizer::compute_in_place tail: solve, AngleAxis / Rotation2D.
-__device__ void delta_point_to_plane(const double* S, int dim, float* dT) {
-    float A6[36], b6[6];
-    for (int c = 0; c < 6; ++c)
-        for (int r = 0; r <= c; ++r) {
-            const float v = (float)S[c * (c + 1) / 2 + r];
-            A6[c * 6 + r] = v;
-            A6[r * 6 + c] = v;
-        }
-    for (int i = 0; i < 6; ++i) b6[i] = (float)S[21 + i];
-    for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
+// x -> dT (R column-major in dT[0..8], t in dT[9..11]); Eigen AngleAxis(|r|, r/|r|) / Rotation2D.
+__device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT) {
+    dT[0] = 1.f; dT[1] = 0.f; dT[2] = 0.f;
+    dT[3] = 0.f; dT[4] = 1.f; dT[5] = 0.f;
+    dT[6] = 0.f; dT[7] = 0.f; dT[8] = 1.f;
     if (dim == 3) {
-        float x[6];
-        solve_normal_eq(A6, b6, x, 6);
         const float nrm2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
         const float ang = sqrtf(nrm2);
-        float ax[3] = {x[0], x[1], x[2]};
-        if (nrm2 > 0.f)
-            for (int d = 0; d < 3; ++d) ax[d] = x[d] / ang;
-        const float s = sinf(ang), c = cosf(ang);
-        const float sx = s * ax[0], sy = s * ax[1], sz = s * ax[2];
-        const float cx = (1.f - c) * ax[0], cy = (1.f - c) * ax[1], cz = (1.f - c) * ax[2];
-        float R[3][3];
-        float tmp = cx * ax[1];
-        R[0][1] = tmp - sz;
-        R[1][0] = tmp + sz;
-        tmp = cx * ax[2];
-        R[0][2] = tmp + sy;
-        R[2][0] = tmp - sy;
-        tmp = cy * ax[2];
-        R[1][2] = tmp - sx;
-        R[2][1] = tmp + sx;
-        R[0][0] = cx * ax[0] + c;
-        R[1][1] = cy * ax[1] + c;
-        R[2][2] = cz * ax[2] + c;
-        bool bad = false;
-        for (int r = 0; r < 3; ++r)
-            for (int cc = 0; cc < 3; ++cc)
-                if (isnan(R[r][cc])) bad = true;
-        if (!bad)
-            for (int r = 0; r < 3; ++r)
-                for (int cc = 0; cc < 3; ++cc) dT[cc * 4 + r] = R[r][cc];
-        for (int d = 0; d < 3; ++d) dT[12 + d] = x[3 + d];
-    } else {
-        // z = 0 embedding: F = [0, 0, c, nx, ny, 0] -> unknowns (theta, tx, ty) are rows 2, 3, 4
-        float A3[9], b3[3], x[3];
-        const int id[3] = {2, 3, 4};
-        for (int c = 0; c < 3; ++c) {
-            for (int r = 0; r < 3; ++r) A3[c * 3 + r] = A6[id[c] * 6 + id[r]];
-            b3[c] = b6[id[c]];
+        float ax0 = x[0], ax1 = x[1], ax2 = x[2];
+        if (nrm2 > 0.f) {
+            ax0 = x[0] / ang;
+            ax1 = x[1] / ang;
+            ax2 = x[2] / ang;
         }
-        solve_normal_eq(A3, b3, x, 3);
-        const float s = sinf(x[0]), c = cosf(x[0]);
+        const float s = sinf(ang), c = cosf(ang);
+        const float sx = s * ax0, sy = s * ax1, sz = s * ax2;
+        const float cx = (1.f - c) * ax0, cy = (1.f - c) * ax1, cz = (1.f - c) * ax2;
+        float R[9];  // column-major
+        float tmp = cx * ax1;
+        R[3] = tmp - sz;  // (0,1)
+        R[1] = tmp + sz;  // (1,0)
+        tmp = cx * ax2;
+        R[6] = tmp + sy;  // (0,2)
+        R[2] = tmp - sy;  // (2,0)
+        tmp = cy * ax2;
+        R[7] = tmp - sx;  // (1,2)
+        R[5] = tmp + sx;  // (2,1)
+        R[0] = cx * ax0 + c;
+        R[4] = cy * ax1 + c;
+        R[8] = cz * ax2 + c;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            if (isnan(R[i])) bad = true;
+        if (!bad) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dT[i] = R[i];
+        }
+        dT[9] = x[3];
+        dT[10] = x[4];
+        dT[11] = x[5];
+    } else {  // unknowns of the z = 0 embedding: theta = x[2], t = (x[3], x[4])
+        const float s = sinf(x[2]), c = cosf(x[2]);
         dT[0] = c;
         dT[1] = s;
-        dT[4] = -s;
-        dT[5] = c;
-        dT[12] = x[1];
-        dT[13] = x[2];
+        dT[3] = -s;
+        dT[4] = c;
+        dT[9] = x[3];
+        dT[10] = x[4];
+        dT[11] = 0.f;
     }
 }
 
 // LPM PointToPointErrorMinimizer::compute_in_place: weighted centroids, SVD of the cross-covariance.
-__device__ void delta_point_to_point(const double* S, int dim, float* dT) {
+__device__ __noinline__ void delta_point_to_point(const double* S, int dim, float* dT) {
     for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
     const double sw = S[0];
     double mp[3], mq[3];
@@ -474,27 +543,26 @@ __device__ void delta_point_to_point(const double* S, int dim, float* dT) {
     }
 }
 
-// Tail of one iteration, run by one thread: T_iter = dT * T_iter, then the checkers
+// Tail of one iteration, run by lane 0: T_iter = dT * T_iter, bookkeeping, then the checkers
 // (LPM TransformationCheckersImpl.cpp: Counter, Differential, Bound).
-__device__ void finish_iteration(const IcpParams& prm, IcpState* st, const double* S, int n_sums, float* trace) {
-    const double pairs = S[n_sums - 1];
-    const double wsum = S[n_sums - 2];
+__device__ __noinline__ void finish_iteration(const IcpParams& prm, IcpState* st, const float* dT12, double pairs, double wsum,
+                                              float* trace) {
     const double denom = (double)prm.knn * (double)st->nq;
-    if (pairs == 0.0) {  // LPM: ConvergenceError("ErrorMnimizer: no point to minimize")
-        st->status = B200ICP_ERR_CONVERGENCE;
-        st->done = 1;
-        return;
-    }
-    float dT[16];
-    if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE)
-        delta_point_to_plane(S, prm.dim, dT);
-    else if (prm.minimizer == B200ICP_MIN_POINT_TO_POINT)
-        delta_point_to_point(S, prm.dim, dT);
-    else
-        for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
     float T[16];
-    for (int i = 0; i < 16; ++i) T[i] = st->T[i];
-    mat4_mul(dT, T, T);
+    {
+        float old[16];
+        for (int i = 0; i < 16; ++i) old[i] = st->T[i];
+        // T = [R t; 0 1] * old   (same accumulation order as the oracle's 4x4 product)
+        for (int c = 0; c < 4; ++c) {
+            for (int r = 0; r < 3; ++r) {
+                float acc = 0.f;
+                for (int k = 0; k < 3; ++k) acc += dT12[k * 3 + r] * old[c * 4 + k];
+                acc += dT12[9 + r] * old[c * 4 + 3];
+                T[c * 4 + r] = acc;
+            }
+            T[c * 4 + 3] = old[c * 4 + 3];
+        }
+    }
     for (int i = 0; i < 16; ++i) st->T[i] = T[i];
     st->pairs = (long long)pairs;
     st->used_ratio = (float)pairs / (float)denom;
@@ -568,6 +636,40 @@ __device__ void finish_iteration(const IcpParams& prm, IcpState* st, const doubl
     }
 }
 
+// Everything after the sums, on warp 0 of the last block.
+__device__ __forceinline__ void finish_warp(const IcpParams& prm, IcpState* st, const double* S, int n_sums, float* trace,
+                                            float* s_scratch /* smem[16] */) {
+    const int lane = threadIdx.x & 31;
+    const double pairs = S[n_sums - 1];
+    const double wsum = S[n_sums - 2];
+    if (pairs == 0.0) {  // LPM: ConvergenceError("ErrorMnimizer: no point to minimize")
+        if (lane == 0) {
+            st->status = B200ICP_ERR_CONVERGENCE;
+            st->done = 1;
+        }
+        return;
+    }
+    float dT[12];
+    if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE) {
+        float x[6];
+        solve6_warp(S, prm.dim, lane, x, s_scratch);
+        delta_from_x(x, prm.dim, dT);
+    } else {
+        if (lane == 0) {
+            float d16[16];
+            for (int i = 0; i < 16; ++i) d16[i] = (i % 5 == 0) ? 1.f : 0.f;
+            if (prm.minimizer == B200ICP_MIN_POINT_TO_POINT) delta_point_to_point(S, prm.dim, d16);
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r) s_scratch[c * 3 + r] = d16[c * 4 + r];
+            for (int r = 0; r < 3; ++r) s_scratch[9 + r] = d16[12 + r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 12; ++i) dT[i] = s_scratch[i];
+    }
+    if (lane == 0) finish_iteration(prm, st, dT, pairs, wsum, trace);
+}
+
 // ---- ErrorElements + error minimiser sums --------------------------------------------------------
 // MIN: 0 point-to-plane (29 sums), 1 point-to-point (18 sums), 2 identity (2 sums).
 template <int MIN>
@@ -591,6 +693,7 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
                                                          const float* __restrict__ md2, IcpState* __restrict__ st,
                                                          double* __restrict__ partials, float* __restrict__ trace) {
     if (st->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) B200_STAMP(st, 11);
     constexpr int NS = SumLayout<MIN>::N;
     const int nq = st->nq;
     const int K = prm.knn;
@@ -600,9 +703,11 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
     for (int i = 0; i < 16; ++i) T[i] = st->T[i];
     const float qlimit = st->limit;
 
-    double acc[NS];
+    // per-thread sums stay in fp32 (a thread sees only a handful of pairs); everything above the
+    // thread level is accumulated in fp64 in a fixed order
+    float acc[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) acc[i] = 0.0;
+    for (int i = 0; i < NS; ++i) acc[i] = 0.f;
 
     for (long long e = blockIdx.x * 256ll + threadIdx.x; e < m; e += (long long)gridDim.x * 256ll) {
         const int pos = mpos[e];
@@ -639,40 +744,43 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
             for (int c = 0; c < 6; ++c) {
                 const float wf = w * F[c];
 #pragma unroll
-                for (int r = 0; r <= c; ++r) acc[c * (c + 1) / 2 + r] += (double)(wf * F[r]);
-                acc[21 + c] -= (double)(wf * dot);
+                for (int r = 0; r <= c; ++r) acc[c * (c + 1) / 2 + r] += wf * F[r];
+                acc[21 + c] -= wf * dot;
             }
         } else if (MIN == 1) {
             const float pv[3] = {p.x, p.y, p.z}, qv[3] = {q.x, q.y, q.z};
-            acc[0] += (double)w;
+            acc[0] += w;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                acc[1 + c] += (double)(w * pv[c]);
-                acc[4 + c] += (double)(w * qv[c]);
+                acc[1 + c] += w * pv[c];
+                acc[4 + c] += w * qv[c];
 #pragma unroll
-                for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += (double)w * (double)qv[r] * (double)pv[c];
+                for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += w * qv[r] * pv[c];
             }
         }
-        acc[NS - 2] += (double)w;
-        acc[NS - 1] += 1.0;
+        acc[NS - 2] += w;
+        acc[NS - 1] += 1.f;
     }
 
+    if (blockIdx.x == 0 && threadIdx.x == 0) B200_STAMP(st, 12);
     // warp shuffle reduction, then one partial per block
     __shared__ double s_part[8][NS];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-        double v = acc[i];
+        double v = (double)acc[i];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
         if (lane == 0) s_part[warp][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x < NS) {
+    if (threadIdx.x < kAccSlots) {
         double v = 0.0;
+        if (threadIdx.x < NS) {
 #pragma unroll
-        for (int wv = 0; wv < 8; ++wv) v += s_part[wv][threadIdx.x];
+            for (int wv = 0; wv < 8; ++wv) v += s_part[wv][threadIdx.x];
+        }
         partials[(size_t)blockIdx.x * kAccSlots + threadIdx.x] = v;
     }
     __threadfence();
@@ -681,17 +789,40 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (threadIdx.x == 0) B200_STAMP(st, 13);
     // fixed-order final reduction -> deterministic sums
+    __shared__ double s_red[8][kAccSlots];
     __shared__ double s_sum[kAccSlots];
+    {
+        const int slot = threadIdx.x & 31, part = threadIdx.x >> 5;
+        constexpr int PER = (kAccBlocks + 7) / 8;
+        double tmp[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {  // all loads in flight together, then a fixed-order sum
+            const unsigned b = part + 8u * j;
+            tmp[j] = (b < gridDim.x) ? __ldcg(partials + (size_t)b * kAccSlots + slot) : 0.0;
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v += tmp[j];
+        s_red[part][slot] = v;
+    }
+    __syncthreads();
     if (threadIdx.x < NS) {
         double v = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partials + (size_t)b * kAccSlots + threadIdx.x);
+#pragma unroll
+        for (int part = 0; part < 8; ++part) v += s_red[part][threadIdx.x];
         s_sum[threadIdx.x] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        st->ticket = 0u;
-        finish_iteration(prm, st, s_sum, NS, trace);
+    __shared__ float s_scratch[16];
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) {
+            st->ticket = 0u;
+            B200_STAMP(st, 14);
+        }
+        finish_warp(prm, st, s_sum, NS, trace, s_scratch);
+        if (threadIdx.x == 0) B200_STAMP(st, 15);
     }
 }
 
@@ -724,18 +855,21 @@ cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals,
     return cudaGetLastError();
 }
 
-cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it, cudaStream_t s, int* launches) {
+cudaError_t icp_device_setup() {  // once per device (context creation)
+    return cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSelCache * sizeof(uint32_t)));
+}
+
+cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it, cudaStream_t s, int* launches,
+                                  cudaEvent_t ev_mid) {
     (void)it;
-    SelectState* sel = reinterpret_cast<SelectState*>(reinterpret_cast<char*>(b.state) + kSelectOffset);
     const long long m = (long long)b.cap_nq * p.knn;
     if (p.quantile_filter >= 0) {
-        const int blocks = (int)std::max<long long>(1, std::min<long long>((m + 255) / 256, kSMs));
-        hist_kernel<0><<<blocks, 256, 0, s>>>(b.state, sel, b.match_d2, p.knn, b.hist, p.quantile);
-        hist_kernel<1><<<blocks, 256, 0, s>>>(b.state, sel, b.match_d2, p.knn, b.hist, p.quantile);
-        hist_kernel<2><<<blocks, 256, 0, s>>>(b.state, sel, b.match_d2, p.knn, b.hist, p.quantile);
-        *launches += 3;
+        const size_t dyn = (size_t)kSelCache * sizeof(uint32_t);
+        select_kernel<<<kSelCtas, kSelThreads, dyn, s>>>(b.state, b.match_d2, p.knn, b.hist, p.quantile);
+        *launches += 1;
     }
-    const int blocks = (int)std::max<long long>(1, std::min<long long>((m + 255) / 256, kMaxAccBlocks));
+    if (ev_mid) cudaEventRecord(ev_mid, s);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((m + 511) / 512, kAccBlocks));
     const float4* nrm = g.has_normals ? g.normals : nullptr;
     if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE)
         accumulate_kernel<0><<<blocks, 256, 0, s>>>(p, g.view, nrm, b.reading, b.match_pos, b.match_d2, b.state, b.partials, b.trace);

@@ -55,7 +55,7 @@ struct Acc1 {
         for (uint32_t j = s + lig; j < e; j += G) {
             const float4 p = __ldg(pts + j);
             const float dd = dist2_exact(qx, qy, qz, p);
-            if (dd < d) {
+            if (dd < d || (dd == d && j < (uint32_t)pos)) {  // ties: lowest cell-sorted position wins
                 d = dd;
                 pos = (int)j;
             }
@@ -210,6 +210,96 @@ __device__ __forceinline__ void visit_shell(const GridView& g, Acc& acc, float q
     }
 }
 
+// Cold search: walk Chebyshev shells around the query's cell until the k-th best is inside the
+// radius the visited block guarantees (or the whole grid has been seen).
+template <int G, typename Acc>
+__device__ __forceinline__ void search_shells(const GridView& g, Acc& acc, float qx, float qy, float qz, float max_r2,
+                                              int variant, int lig, unsigned gmask) {
+    // grid coordinates (same fp32 expression as the builder's cell_coord)
+    const float lim = 1.0e8f;
+    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
+    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
+    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
+    const int cx = floor_to_int(ux), cy = floor_to_int(uy), cz = floor_to_int(uz);
+    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+    // first shell that can touch the grid
+    int R0 = 0;
+    R0 = max(R0, cx < 0 ? -cx : (cx > g.nx - 1 ? cx - (g.nx - 1) : 0));
+    R0 = max(R0, cy < 0 ? -cy : (cy > g.ny - 1 ? cy - (g.ny - 1) : 0));
+    R0 = max(R0, cz < 0 ? -cz : (cz > g.nz - 1 ? cz - (g.nz - 1) : 0));
+    int R = R0, Rprev = R0 - 1;
+    if ((variant & 1) && R0 == 0) R = 1;  // variant bit 0: no own-cell pre-pass
+    const bool finite_q = (fabsf(qx) < 3.0e38f) && (fabsf(qy) < 3.0e38f) && (fabsf(qz) < 3.0e38f);  // false for NaN too
+    if (!finite_q) return;
+    while (true) {
+        const float tau = acc.tau(gmask, max_r2);
+        visit_shell<G, Acc>(g, acc, qx, qy, qz, ux, uy, uz, cx, cy, cz, R, Rprev, tau, slack, max_r2, lig, gmask);
+        // radius guaranteed by the visited block: distance to the nearest face that still has cells behind it
+        float gu = CUDART_INF_F;
+        if (cx - R > 0) gu = fminf(gu, ux - (float)(cx - R));
+        if (cx + R < g.nx - 1) gu = fminf(gu, (float)(cx + R + 1) - ux);
+        if (cy - R > 0) gu = fminf(gu, uy - (float)(cy - R));
+        if (cy + R < g.ny - 1) gu = fminf(gu, (float)(cy + R + 1) - uy);
+        if (cz - R > 0) gu = fminf(gu, uz - (float)(cz - R));
+        if (cz + R < g.nz - 1) gu = fminf(gu, (float)(cz + R + 1) - uz);
+        if (gu == CUDART_INF_F) break;  // whole grid visited
+        const float gm = fmaxf(gu - slack, 0.f) * g.h;
+        if (acc.tau(gmask, max_r2) <= gm * gm) break;
+        Rprev = R;
+        R = R + 1;
+    }
+}
+
+// Warm search (k = 1, ICP iterations >= 1): the previous iteration's match is a real map point, so
+// its distance to the moved query bounds the new nearest distance.  Every cell that intersects the
+// ball of that radius is scanned in ONE pass -- no shell walk, no pre-pass.  Each lane of the group
+// owns whole (y, z) rows of the ball's cover, so the loads of different rows are in flight together
+// and the inner loop has no cross-lane traffic; the result is exact for the same reason the bound
+// is valid, and identical to the cold search thanks to the (dist2, position) tie rule.
+template <int G>
+__device__ __forceinline__ void search_ball(const GridView& g, float qx, float qy, float qz, float tau, float& bd, int& bp,
+                                            int lig) {
+    const float lim = 1.0e8f;
+    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
+    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
+    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
+    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+    const float rt = fminf(sqrtf(tau) * g.inv_h + slack, 3.0e8f);
+    const int ylo = max(0, floor_to_int(fmaxf(uy - rt, -1.f)));
+    const int yhi = min(g.ny - 1, floor_to_int(fminf(uy + rt, (float)g.ny)));
+    const int zlo = max(0, floor_to_int(fmaxf(uz - rt, -1.f)));
+    const int zhi = min(g.nz - 1, floor_to_int(fminf(uz + rt, (float)g.nz)));
+    const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
+    if (wy <= 0 || wz <= 0) return;
+    const int nrows = wy * wz;
+    for (int r = lig; r < nrows; r += G) {
+        const int y = ylo + r % wy, z = zlo + r / wy;
+        // distance from the query to the row's y/z slab (0 when inside it)
+        float gy = fmaxf(fmaxf((float)y - uy, uy - (float)(y + 1)), 0.f);
+        float gz = fmaxf(fmaxf((float)z - uz, uz - (float)(z + 1)), 0.f);
+        gy = fmaxf(gy - slack, 0.f) * g.h;
+        gz = fmaxf(gz - slack, 0.f) * g.h;
+        const float gyz2 = gy * gy + gz * gz;
+        if (gyz2 > tau) continue;
+        const float rx = fminf(sqrtf(fmaxf(tau - gyz2, 0.f)) * g.inv_h + slack, 3.0e8f);
+        const int xa = max(0, floor_to_int(fmaxf(ux - rx, -1.f)));
+        const int xb = min(g.nx - 1, floor_to_int(fminf(ux + rx, (float)g.nx)));
+        if (xa > xb) continue;
+        const uint32_t* row = g.cell_start + ((size_t)z * g.ny + y) * (size_t)g.nx;
+        const uint32_t s = __ldg(row + xa), e = __ldg(row + xb + 1);
+#pragma unroll 4
+        for (uint32_t j = s; j < e; ++j) {
+            const float4 p = __ldg(g.pts + j);
+            const float dd = dist2_exact(qx, qy, qz, p);
+            if (dd < bd || (dd == bd && j < (uint32_t)bp)) {
+                bd = dd;
+                bp = (int)j;
+            }
+        }
+        tau = fminf(tau, bd);
+    }
+}
+
 template <int G, typename Acc>
 __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __restrict__ queries, const int* __restrict__ d_nq,
                                                   const IcpState* __restrict__ state, int k, float max_r2,
@@ -231,44 +321,9 @@ __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __re
         qy = __fadd_rn(__fmaf_rn(T[9], q4.z, __fmaf_rn(T[5], q4.y, __fmul_rn(T[1], q4.x))), T[13]);
         qz = __fadd_rn(__fmaf_rn(T[10], q4.z, __fmaf_rn(T[6], q4.y, __fmul_rn(T[2], q4.x))), T[14]);
     }
-    // grid coordinates (same fp32 expression as the builder's cell_coord)
-    const float lim = 1.0e8f;
-    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
-    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
-    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
-    const int cx = floor_to_int(ux), cy = floor_to_int(uy), cz = floor_to_int(uz);
-    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
-
     Acc acc;
     acc.init(k);
-
-    // first shell that can touch the grid
-    int R0 = 0;
-    R0 = max(R0, cx < 0 ? -cx : (cx > g.nx - 1 ? cx - (g.nx - 1) : 0));
-    R0 = max(R0, cy < 0 ? -cy : (cy > g.ny - 1 ? cy - (g.ny - 1) : 0));
-    R0 = max(R0, cz < 0 ? -cz : (cz > g.nz - 1 ? cz - (g.nz - 1) : 0));
-    int R = R0, Rprev = R0 - 1;
-    if ((variant & 1) && R0 == 0) R = 1;  // variant bit 0: no own-cell pre-pass
-    const bool finite_q = (fabsf(qx) < 3.0e38f) && (fabsf(qy) < 3.0e38f) && (fabsf(qz) < 3.0e38f);  // false for NaN too
-    if (finite_q) {
-        while (true) {
-            const float tau = acc.tau(gmask, max_r2);
-            visit_shell<G, Acc>(g, acc, qx, qy, qz, ux, uy, uz, cx, cy, cz, R, Rprev, tau, slack, max_r2, lig, gmask);
-            // radius guaranteed by the visited block: distance to the nearest face that still has cells behind it
-            float gu = CUDART_INF_F;
-            if (cx - R > 0) gu = fminf(gu, ux - (float)(cx - R));
-            if (cx + R < g.nx - 1) gu = fminf(gu, (float)(cx + R + 1) - ux);
-            if (cy - R > 0) gu = fminf(gu, uy - (float)(cy - R));
-            if (cy + R < g.ny - 1) gu = fminf(gu, (float)(cy + R + 1) - uy);
-            if (cz - R > 0) gu = fminf(gu, uz - (float)(cz - R));
-            if (cz + R < g.nz - 1) gu = fminf(gu, (float)(cz + R + 1) - uz);
-            if (gu == CUDART_INF_F) break;  // whole grid visited
-            const float gm = fmaxf(gu - slack, 0.f) * g.h;
-            if (acc.tau(gmask, max_r2) <= gm * gm) break;
-            Rprev = R;
-            R = R + 1;
-        }
-    }
+    search_shells<G, Acc>(g, acc, qx, qy, qz, max_r2, variant, lig, gmask);
     float od;
     int op;
     acc.finish(gmask, lig, k, max_r2, od, op);
@@ -280,6 +335,72 @@ __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __re
         out_ids[o] = id;
         out_d2[o] = od;
     }
+}
+
+// ICP iterations >= 1, k = 1: match_pos holds the previous iteration's matches on entry.
+template <int G>
+__global__ void __launch_bounds__(256) nn1_warm_kernel(GridView g, const float4* __restrict__ reading,
+                                                       const IcpState* __restrict__ state, float max_r2,
+                                                       int32_t* __restrict__ match_pos, float* __restrict__ match_d2, int) {
+    if (state->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) B200_STAMP(const_cast<IcpState*>(state), 16);
+    const int nq = state->nq;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const long long qi = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
+    if (qi >= nq) return;
+    const float4 q4 = __ldg(reading + qi);
+    const int prev = match_pos[qi];
+    const float* T = state->T;
+    const float qx = __fadd_rn(__fmaf_rn(T[8], q4.z, __fmaf_rn(T[4], q4.y, __fmul_rn(T[0], q4.x))), T[12]);
+    const float qy = __fadd_rn(__fmaf_rn(T[9], q4.z, __fmaf_rn(T[5], q4.y, __fmul_rn(T[1], q4.x))), T[13]);
+    const float qz = __fadd_rn(__fmaf_rn(T[10], q4.z, __fmaf_rn(T[6], q4.y, __fmul_rn(T[2], q4.x))), T[14]);
+    float bd = CUDART_INF_F;
+    int bp = -1;
+    const bool finite_q = (fabsf(qx) < 3.0e38f) && (fabsf(qy) < 3.0e38f) && (fabsf(qz) < 3.0e38f);
+    if (finite_q) {
+        float tau = max_r2;
+        if (prev >= 0) {
+            const float dprev = dist2_exact(qx, qy, qz, __ldg(g.pts + prev));
+            if (dprev <= max_r2) {
+                tau = dprev;
+                bd = dprev;
+                bp = prev;
+            }
+        }
+        // tau == inf only when maxDist is unbounded AND the cold search of iteration 0 found
+        // nothing, i.e. the map cannot offer this query a neighbour at all: leave it unmatched.
+        if (tau < CUDART_INF_F) search_ball<G>(g, qx, qy, qz, tau, bd, bp, lig);
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(gmask, bd, o);
+        const int op = __shfl_xor_sync(gmask, bp, o);
+        if (od < bd || (od == bd && (unsigned)op < (unsigned)bp)) {
+            bd = od;
+            bp = op;
+        }
+    }
+    if (!(bd <= max_r2)) {
+        bd = CUDART_INF_F;
+        bp = -1;
+    }
+    if (lig == 0) {
+        match_pos[qi] = bp;
+        match_d2[qi] = bd;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) B200_STAMP(const_cast<IcpState*>(state), 17);
+}
+
+template <int G>
+cudaError_t launch_warm_one(const GridView& g, const float4* reading, int cap, const IcpState* st, float max_r2,
+                            int32_t* pos, float* d2, int variant, cudaStream_t s) {
+    const int per_block = 256 / G;
+    const int blocks = (cap + per_block - 1) / per_block;
+    if (blocks <= 0) return cudaSuccess;
+    nn1_warm_kernel<G><<<blocks, 256, 0, s>>>(g, reading, st, max_r2, pos, d2, variant);
+    return cudaGetLastError();
 }
 
 template <int G, typename Acc>
@@ -300,6 +421,8 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
     if (k < 1 || k > 32) return cudaErrorInvalidValue;
     if (k == 1) {
         switch ((variant >> 4) & 0xf) {  // experimental: lanes per query for k = 1
+            case 5: return launch_one<1, Acc1<1>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
+            case 6: return launch_one<2, Acc1<2>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
             case 4: return launch_one<4, Acc1<4>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
             case 1: return launch_one<16, Acc1<16>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
             case 2: return launch_one<32, Acc1<32>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
@@ -309,6 +432,16 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
     if (k <= 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s);
     if (k <= 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s);
     return launch_one<32, AccK<32>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s);
+}
+
+cudaError_t launch_nn1_warm(const GridView& g, const float4* d_reading, int nq_capacity, const IcpState* st, float max_r2,
+                            int32_t* match_pos, float* match_d2, int variant, cudaStream_t s) {
+    switch ((variant >> 8) & 0xf) {  // experimental: lanes per query in the warm search
+        case 1: return launch_warm_one<1>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
+        case 2: return launch_warm_one<2>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
+        case 8: return launch_warm_one<8>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
+        default: return launch_warm_one<4>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
+    }
 }
 
 }  // namespace b200

@@ -1,0 +1,25 @@
+"""Development aid: per-phase globaltimer stamps of the last ICP iteration (build with EXTRA=-DB200ICP_STAMPS)."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from norlab_icp_mapper_b200 import synth
+from norlab_icp_mapper_b200.icp import ICP, make_config
+d = synth.make_pair_3d()
+cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
+g = ICP(cfg); g.set_map(d["map"], d["normals"])
+names = {0: "sel start", 1: "sel p0 hist", 2: "sel p0 sync", 3: "sel p0 pick", 4: "sel p1 hist", 5: "sel p1 sync", 6: "sel p1 pick",
+         7: "sel p2 hist", 8: "sel p2 sync", 9: "sel p2 pick", 10: "sel end", 11: "acc start(b0)", 12: "acc loop done(b0)",
+         13: "acc last-block ticket", 14: "acc reduced", 15: "acc finished", 16: "nn start(b0)", 17: "nn end(last block)"}
+for rep in range(3):
+    g(d["reading"])
+    st = np.zeros(32, np.uint64)
+    g._L.b200icp_debug_stamps.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    g._L.b200icp_debug_stamps(g._h, st.ctypes.data)
+    order = sorted([i for i in names if st[i] > 0], key=lambda i: st[i])
+    t0 = st[order[0]]
+    print("rep", rep, "total_ms", g.timing().total_ms)
+    prev = t0
+    for i in order:
+        print(f"   {names[i]:24s} +{(int(st[i]) - int(t0)) / 1e3:8.2f} us  (d {(int(st[i]) - int(prev)) / 1e3:6.2f})")
+        prev = st[i]
