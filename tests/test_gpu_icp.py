@@ -1,0 +1,215 @@
+"""Parity of the CUDA ICP loop (through the C-ABI) with the oracle: final pose within the BASELINE
+tolerance (1e-4 rad, 1e-3 m), same iteration counts / pair counts, same error behaviour."""
+import numpy as np
+import pytest
+
+from norlab_icp_mapper_b200 import _abi, synth
+from norlab_icp_mapper_b200._abi import make_config
+
+pytestmark = pytest.mark.gpu
+TOL_RAD, TOL_M = 1e-4, 1e-3
+
+
+@pytest.fixture(scope="module")
+def pair3d():
+    return synth.make_pair_3d(n_map=200_000, n_scan=20_000)
+
+
+@pytest.fixture(scope="module")
+def pair2d():
+    return synth.make_pair_2d()
+
+
+def _both(oracle, cfg, d, T_init=None):
+    from norlab_icp_mapper_b200.icp import ICP
+    o = oracle.OracleICP(cfg)
+    o.set_map(d["map"], d["normals"])
+    rc, T_o, res_o, tr_o, _ = o.register(d["reading"], T_init=T_init, want_trace=True)
+    g = ICP(cfg)
+    g.set_trace(True)
+    g.set_map(d["map"], d["normals"])
+    T_g = g(d["reading"], T_init=T_init)
+    res_g, tr_g = g.last_result, g.trace()
+    g.close()
+    assert rc == _abi.OK
+    return T_g, res_g, tr_g, T_o, res_o, tr_o
+
+
+CHAINS_3D = [
+    dict(knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30),
+    dict(knn=6, max_dist=2.0, outliers=(("max_dist", 1.0),), minimizer="point_to_plane", max_iteration_count=10),
+    dict(knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=40, differential=(1e-3, 1e-3, 3)),
+    dict(knn=1, max_dist=1.0, outliers=(("median", 3.0),), minimizer="point_to_plane", max_iteration_count=15),
+    dict(knn=3, max_dist=1.5, outliers=(("min_dist", 0.001), ("trimmed", 0.9)), minimizer="point_to_plane", max_iteration_count=15),
+    dict(knn=1, max_dist=float("inf"), outliers=(("trimmed", 0.7),), minimizer="point_to_plane", max_iteration_count=20),
+    dict(knn=1, max_dist=1.0, outliers=(), minimizer="point_to_plane", max_iteration_count=40, differential=(1e-3, 1e-3, 3)),
+    dict(knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=20, sort_reading=0),
+]
+
+
+@pytest.mark.parametrize("chain", CHAINS_3D)
+def test_pose_parity_3d(oracle, pair3d, chain):
+    cfg = make_config(dim=3, **chain)
+    T_g, res_g, tr_g, T_o, res_o, tr_o = _both(oracle, cfg, pair3d)
+    er, et = synth.pose_error(T_g, T_o)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res_g.iterations == res_o.iterations and res_g.max_iter_reached == res_o.max_iter_reached
+    assert abs(res_g.overlap - res_o.overlap) < 2e-3
+    assert abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.002 * max(res_o.pairs_last_iter, 1) + 2
+    n = min(len(tr_g), len(tr_o))
+    for i in range(n):  # the whole trajectory of T_iter agrees, not only the end point
+        e = synth.pose_error(tr_g[i], tr_o[i])
+        assert e[0] <= 5 * TOL_RAD and e[1] <= 5 * TOL_M, (i, e)
+
+
+@pytest.mark.parametrize("chain", [dict(knn=8, max_dist=0.5, outliers=(), minimizer="point_to_point", max_iteration_count=30),
+                                   dict(knn=1, max_dist=0.5, outliers=(("trimmed", 0.9),), minimizer="point_to_plane", max_iteration_count=30),
+                                   dict(knn=2, max_dist=0.5, outliers=(("median", 3.0),), minimizer="point_to_plane", max_iteration_count=20)])
+def test_pose_parity_2d(oracle, pair2d, chain):
+    cfg = make_config(dim=2, **chain)
+    T_g, res_g, _, T_o, res_o, _ = _both(oracle, cfg, pair2d)
+    assert T_g.shape == (3, 3)
+    er, et = synth.pose_error(T_g, T_o)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res_g.iterations == res_o.iterations
+
+
+def test_unconverged_trajectory_parity(oracle):
+    """SURVEY.md 8d's original perturbation (3 deg yaw at 80 m range) does not converge in 30
+    iterations; the two implementations must still walk the same path."""
+    d = synth.make_pair_3d(n_map=200_000, n_scan=20_000, drpy_deg=(1.0, -1.0, 3.0))
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
+    T_g, res_g, _, T_o, res_o, _ = _both(oracle, cfg, d)
+    er, et = synth.pose_error(T_g, T_o)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+
+
+def test_initial_transform_argument(oracle, pair3d):
+    """icp(cloud, T_init): registering the raw scan with T_init = T_est equals registering the
+    pre-transformed reading with identity (Mapper.cpp:197,213)."""
+    from norlab_icp_mapper_b200.icp import ICP
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=20)
+    g = ICP(cfg)
+    g.set_map(pair3d["map"], pair3d["normals"])
+    T_a = g(pair3d["reading"])
+    T_b = g(pair3d["scan"], T_init=pair3d["T_est"].astype(np.float32))
+    o = oracle.OracleICP(cfg)
+    o.set_map(pair3d["map"], pair3d["normals"])
+    rc, T_ob, *_ = o.register(pair3d["scan"], T_init=pair3d["T_est"].astype(np.float32))
+    g.close()
+    e = synth.pose_error(T_b, T_ob)
+    assert e[0] <= TOL_RAD and e[1] <= TOL_M
+    e = synth.pose_error(T_b, T_a @ pair3d["T_est"])
+    assert e[0] <= 5e-4 and e[1] <= 5e-3
+
+
+def test_golden_corrections(golden):
+    from norlab_icp_mapper_b200.icp import ICP
+    for key, kw in (("T_plane_k6_it10", dict(knn=6, outliers=(), minimizer="point_to_plane", max_iteration_count=10)),
+                    ("T_plane_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)),
+                    ("T_point_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=30))):
+        g = ICP(make_config(dim=3, max_dist=2.0, **kw))
+        g.set_map(golden["map"], golden["normals"])
+        T = g(golden["reading"])
+        ids, d2 = g.match(golden["reading"])
+        g.close()
+        er, et = synth.pose_error(T, golden[key])
+        assert er <= TOL_RAD and et <= TOL_M, (key, er, et)
+        k = kw["knn"]
+        gd2 = golden[f"knn{k}_d2"]
+        gd2 = np.where(gd2 > 4.0, np.inf, gd2)  # match() applies the chain's maxDist 2.0
+        fin = np.isfinite(gd2)
+        assert np.array_equal(np.isfinite(d2), fin)
+
+
+def test_run_to_run_determinism(pair3d):
+    from norlab_icp_mapper_b200.icp import ICP
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
+    outs = []
+    for variant in (0, 0, 2):  # 2 = warm-started search disabled: results must not depend on the search strategy
+        cfg.nn_variant = variant
+        g = ICP(cfg)
+        g.set_map(pair3d["map"], pair3d["normals"])
+        outs.append((g(pair3d["reading"]), g(pair3d["reading"])))
+        g.close()
+    for a, b in outs:
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
+
+
+def test_error_behaviour_matches_libpointmatcher(oracle, pair3d):
+    from norlab_icp_mapper_b200.icp import ICP, B200ICPError
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=5)
+    g = ICP(cfg)
+    with pytest.raises(B200ICPError) as e:  # no map yet
+        g(pair3d["reading"])
+    assert e.value.status == _abi.ERR_NO_MAP
+    assert g.set_map(np.zeros((0, 4), np.float32)) is False and not g.has_map()  # LPM ignores an empty cloud
+    g.set_map(pair3d["map"], None)
+    with pytest.raises(B200ICPError) as e:  # point-to-plane needs reference normals
+        g(pair3d["reading"])
+    assert e.value.status == _abi.ERR_INVALID_FIELD
+    g.set_map(pair3d["map"], pair3d["normals"])
+    far = pair3d["reading"].copy()
+    far[:, :3] += 1000.0
+    with pytest.raises(B200ICPError) as e:  # nothing within maxDist: ConvergenceError
+        g(far)
+    assert e.value.status == _abi.ERR_CONVERGENCE
+    bad = np.eye(4, dtype=np.float32)
+    bad[0, 0] = 1.1
+    with pytest.raises(B200ICPError) as e:  # TransformationError
+        g(pair3d["reading"], T_init=bad)
+    assert e.value.status == _abi.ERR_TRANSFORM
+    with pytest.raises(B200ICPError) as e:
+        g(np.zeros((0, 4), np.float32))
+    assert e.value.status == _abi.ERR_CONVERGENCE
+    T = g(pair3d["reading"])  # the context survives errors
+    assert np.isfinite(T).all()
+    g.close()
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30,
+                      bound=(1.0, 0.05))
+    g = ICP(cfg)
+    g.set_map(pair3d["map"], pair3d["normals"])
+    with pytest.raises(B200ICPError) as e:  # BoundTransformationChecker
+        g(pair3d["reading"])
+    assert e.value.status == _abi.ERR_BOUND
+    g.close()
+
+
+def test_rigid_transform_bit_exact(oracle):
+    from norlab_icp_mapper_b200.icp import ICP, B200ICPError
+    rng = np.random.default_rng(2)
+    g = ICP(make_config())
+    for dim in (3, 2):
+        pts = synth.homog(rng.normal(scale=50, size=(10_000, dim)))
+        nrm = rng.normal(size=(10_000, dim)).astype(np.float32)
+        T = synth.make_T((1, 2, 3), (10, 20, 30)) if dim == 3 else synth.make_T2((1, 2), 33.0)
+        out, on = g.transform(pts, T, nrm)
+        rc, oo, onn = oracle.transform(pts, T, nrm)
+        assert np.array_equal(out, oo) and np.array_equal(on, onn)
+    T = synth.make_T((0, 0, 0))
+    T[1, 1] = 0.9
+    with pytest.raises(B200ICPError) as e:
+        g.transform(pts if dim == 3 else synth.homog(rng.normal(size=(4, 3))), T)
+    assert e.value.status == _abi.ERR_TRANSFORM
+    g.close()
+
+
+def test_full_size_config2(oracle):
+    """BASELINE config 2 at full size: pose parity with the oracle and with the known truth."""
+    from norlab_icp_mapper_b200.icp import ICP
+    d = synth.make_pair_3d()
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
+    g = ICP(cfg)
+    g.set_map(d["map"], d["normals"])
+    T_g = g(d["reading"])
+    res = g.last_result
+    g.close()
+    o = oracle.OracleICP(cfg)
+    o.set_map(d["map"], d["normals"])
+    rc, T_o, res_o, _, _ = o.register(d["reading"])
+    er, et = synth.pose_error(T_g, T_o)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res.iterations == 30 and res.pairs_last_iter == res_o.pairs_last_iter
+    er, et = synth.pose_error(T_g, d["correction_true"])
+    assert er <= 1e-4 and et <= 1e-3

@@ -1,0 +1,154 @@
+"""The oracle's ICP loop (libpointmatcher restatement): closed-form checks, the numpy second opinion,
+the golden file, the checkers and the error behaviour."""
+import numpy as np
+import pytest
+
+import numpy_icp
+from norlab_icp_mapper_b200 import _abi, synth
+from norlab_icp_mapper_b200._abi import make_config
+
+TOL_RAD, TOL_M = 1e-4, 1e-3  # BASELINE.json north_star tolerance
+
+
+@pytest.fixture(scope="module")
+def pair3d():
+    return synth.make_pair_3d(n_map=60_000, n_scan=6_000, world_size=(80.0, 80.0), n_boxes=12, scan_radius=35.0)
+
+
+@pytest.fixture(scope="module")
+def pair2d():
+    return synth.make_pair_2d(n_map=40_000, n_scan=4_000)
+
+
+def _run(oracle, cfg, d, **kw):
+    o = oracle.OracleICP(cfg)
+    assert o.set_map(d["map"], d["normals"]) == _abi.OK
+    return o, o.register(d["reading"], **kw)
+
+
+def test_point_to_plane_recovers_truth(oracle, pair3d):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
+    o, (rc, T, res, trace, secs) = _run(oracle, cfg, pair3d, want_trace=True)
+    assert rc == _abi.OK and res.iterations == 30 and res.max_iter_reached == 1
+    er, et = synth.pose_error(T, pair3d["correction_true"])
+    assert er < 5e-4 and et < 5e-3  # 1 cm sensor noise bounds what any ICP can recover
+    assert abs(res.overlap - 0.85) < 2e-3  # weightedPointUsedRatio of the trimmed filter
+    assert len(trace) == 30
+
+
+@pytest.mark.parametrize("minimizer,knn,outliers", [("point_to_plane", 1, (("trimmed", 0.85),)), ("point_to_plane", 6, (("max_dist", 0.7),)),
+                                                    ("point_to_point", 1, (("trimmed", 0.7),)), ("point_to_plane", 1, (("median", 3.0),)),
+                                                    ("point_to_plane", 2, (("min_dist", 0.001), ("max_dist", 0.8)))])
+def test_oracle_agrees_with_numpy_second_opinion_3d(oracle, pair3d, minimizer, knn, outliers):
+    cfg = make_config(dim=3, knn=knn, max_dist=1.0, outliers=outliers, minimizer=minimizer, max_iteration_count=12)
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair3d)
+    assert rc == _abi.OK
+    T_np = numpy_icp.icp(pair3d["map"][:, :3], pair3d["normals"], pair3d["reading"][:, :3], knn_k=knn, max_dist=1.0,
+                         outliers=outliers, minimizer=minimizer, iterations=12)
+    er, et = synth.pose_error(T, T_np)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+
+
+@pytest.mark.parametrize("minimizer,knn", [("point_to_point", 8), ("point_to_plane", 1)])
+def test_oracle_agrees_with_numpy_second_opinion_2d(oracle, pair2d, minimizer, knn):
+    cfg = make_config(dim=2, knn=knn, max_dist=0.5, outliers=(), minimizer=minimizer, max_iteration_count=15)
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair2d)
+    assert rc == _abi.OK and T.shape == (3, 3)
+    T_np = numpy_icp.icp(pair2d["map"][:, :2], pair2d["normals"], pair2d["reading"][:, :2], knn_k=knn, max_dist=0.5,
+                         outliers=(), minimizer=minimizer, iterations=15)
+    er, et = synth.pose_error(T, T_np)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res.overlap == pytest.approx(res.point_used_ratio)
+
+
+def test_golden_corrections(oracle, golden):
+    d = dict(map=golden["map"], normals=golden["normals"], reading=golden["reading"])
+    for key, kw in (("T_plane_k6_it10", dict(knn=6, outliers=(), minimizer="point_to_plane", max_iteration_count=10)),
+                    ("T_plane_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)),
+                    ("T_point_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=30))):
+        cfg = make_config(dim=3, max_dist=2.0, **kw)
+        _, (rc, T, res, _, _) = _run(oracle, cfg, d)
+        assert rc == _abi.OK
+        er, et = synth.pose_error(T, golden[key])
+        assert er <= TOL_RAD and et <= TOL_M, (key, er, et)
+
+
+def test_trimmed_quantile_index_semantics(oracle):
+    """limit = sorted(finite dists)[size_t(n * ratio)], weights = dist <= limit (ties included)."""
+    m = np.array([[float(i), 0, 0, 1] for i in range(10)], np.float32)
+    n = np.tile(np.array([[0, 1, 0]], np.float32), (10, 1))
+    off = np.array([0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.07, 0.08, 0.09, 0.10], np.float32)
+    reading = m.copy()
+    reading[:, 1] += off
+    for ratio, expected_pairs in ((0.5, 6), (0.85, 9), (1.0, 10), (0.0, 1)):
+        cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", ratio),), minimizer="identity", max_iteration_count=1)
+        o = oracle.OracleICP(cfg)
+        o.set_map(m, n)
+        rc, T, res, _, _ = o.register(reading)
+        assert rc == _abi.OK and res.pairs_last_iter == expected_pairs, (ratio, res.pairs_last_iter)
+        assert np.allclose(T, np.eye(4))  # IdentityErrorMinimizer (examples/config.yaml:62-63)
+
+
+def test_counter_and_differential_checkers(oracle, pair3d):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=7)
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair3d)
+    assert res.iterations == 7 and res.max_iter_reached == 1
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=40,
+                      differential=(1e-3, 1e-3, 3))
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair3d)
+    assert rc == _abi.OK and 3 <= res.iterations < 40 and res.max_iter_reached == 0
+
+
+def test_bound_checker_raises(oracle, pair3d):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30,
+                      bound=(1.0, 0.05))  # the 0.37 m initial error exceeds a 5 cm bound
+    o, (rc, T, res, _, _) = _run(oracle, cfg, pair3d)
+    assert rc == _abi.ERR_BOUND and "bound" in o.last_error()
+
+
+def test_error_paths(oracle, pair3d):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=5)
+    o = oracle.OracleICP(cfg)
+    rc, T, res, _, _ = o.register(pair3d["reading"])  # no map: LPM returns identity
+    assert rc == _abi.ERR_NO_MAP and np.allclose(T, np.eye(4))
+    o.set_map(pair3d["map"], None)  # point-to-plane without normals: InvalidField
+    rc, *_ = o.register(pair3d["reading"])
+    assert rc == _abi.ERR_INVALID_FIELD
+    o.set_map(pair3d["map"], pair3d["normals"])
+    far = pair3d["reading"].copy()
+    far[:, :3] += 1000.0  # nothing within maxDist: "no outlier to filter"
+    rc, *_ = o.register(far)
+    assert rc == _abi.ERR_CONVERGENCE
+    bad = np.eye(4, dtype=np.float32)
+    bad[0, 0] = 1.1  # not a rotation: TransformationError
+    rc, *_ = o.register(pair3d["reading"], T_init=bad)
+    assert rc == _abi.ERR_TRANSFORM
+
+
+def test_rigid_transform(oracle):
+    rng = np.random.default_rng(2)
+    pts = synth.homog(rng.normal(size=(100, 3)))
+    nrm = rng.normal(size=(100, 3)).astype(np.float32)
+    T = synth.make_T((1, 2, 3), (10, 20, 30))
+    rc, out, on = oracle.transform(pts, T, nrm)
+    assert rc == _abi.OK
+    np.testing.assert_allclose(out[:, :3], synth.apply_T(T, pts), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(on, nrm @ T[:3, :3].T, rtol=1e-5, atol=1e-5)
+    assert np.all(out[:, 3] == 1.0)
+    T[0, 0] += 0.01
+    rc, _, _ = oracle.transform(pts, T)
+    assert rc == _abi.ERR_TRANSFORM
+
+
+def test_point_distance_and_normals(oracle, golden):
+    m = golden["map"]
+    rng = np.random.default_rng(3)
+    inp = synth.homog(m[rng.choice(len(m), 500), :3] + rng.normal(0, 0.2, (500, 3)))
+    kept, keep = oracle.point_distance_keep(m, inp, 0.15)
+    ids, d2 = numpy_icp.knn(m[:, :3], inp[:, :3], 1)
+    expect = d2[:, 0] >= 0.15 ** 2
+    assert kept == keep.sum() and (keep == expect).mean() > 0.995  # fp32/fp64 threshold ties
+    rc, nrm = oracle.surface_normals(m, 10)
+    g = golden["normals"]
+    cosang = np.abs(np.einsum("ij,ij->i", nrm, g))
+    assert rc == _abi.OK and np.median(cosang) > 0.9999 and (cosang > 0.999).mean() > 0.97
