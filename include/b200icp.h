@@ -173,6 +173,49 @@ int32_t b200icp_knn(b200icp_ctx* ctx, const float* ref, int32_t ref_rows, int64_
 int32_t b200icp_transform(b200icp_ctx* ctx, float* features, int32_t feature_rows, float* normals,
                           int64_t n, const float* T);
 
+/* ---- the device-resident local map (Map::localPointCloud, Map.h:38-46) ---------------------------
+ * b200icp_set_map* also (re)initialises this store: every point of the cloud, map frame, all
+ * "loaded".  The calls below are the steps of Map::updateLocalPointCloud (Map.cpp:502-534) and of
+ * the cell window of Map::updatePose (Map.cpp:246-460) on that store; the spatial index is rebuilt
+ * from the loaded points by b200icp_map_commit (== icp.setMap(localPointCloud), Map.cpp:111,178,528). */
+
+/* PointDistanceMapperModule::inPlaceUpdateMap (MapperModules/PointDistanceMapperModule.cpp:28-50):
+ * 1-NN (eps 0, no radius) of every input point against the local map -- on the live index, no
+ * second kd-tree -- keep those with dist2 >= minDistNewPoint^2, append them in input order
+ * (map.concatenate: the map's normals survive only if input_normals is given).  On an empty local
+ * map this is createMap (:9-19): the whole input is taken.  `input` is in the map frame (host
+ * pointers).  keep_out (optional): n_in bytes, 1 = appended. */
+int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, int32_t feature_rows,
+                                          int64_t n_in, const float* input_normals,
+                                          float min_dist_new_point, int64_t* n_added, uint8_t* keep_out);
+
+/* SurfaceNormalDataPointsFilter{knn} over the whole local map (the `post:` chain of
+ * examples/config.yaml:26-27 applied at Map.cpp:523-525): self k-NN, centred covariance,
+ * eigenvector of the smallest eigenvalue -> `normals` (unit, sign arbitrary).  Computed in the map
+ * frame: k-NN sets and normals are invariant/covariant under the rigid sensor<->map transform the
+ * reference wraps around the filter, so the two whole-map transforms are not needed. */
+int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn);
+
+/* Map::loadCells (load = 1, Map.cpp:71-128) / Map::unloadCells (load = 0, Map.cpp:140-230) for the
+ * slab {startRow, endRow, startColumn, endColumn, startAisle, endAisle} of 20 m cells.  Points never
+ * leave HBM: unloading clears their `loaded` flag (the reference moves them to the CellManager),
+ * loading sets it again.  Does not rebuild the index (call b200icp_map_commit). */
+int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed);
+
+/* icp.setMap(localPointCloud): rebuild the index over the loaded points.  An empty local cloud is
+ * ignored like LPM does (the previous index stays). */
+int32_t b200icp_map_commit(b200icp_ctx* ctx);
+
+/* Point counts: local (Map::localPointCloud) and global (local + parked cells, Map.cpp:538-562). */
+int32_t b200icp_map_counts(const b200icp_ctx* ctx, int64_t* n_local, int64_t* n_global);
+int32_t b200icp_map_has_normals(const b200icp_ctx* ctx);
+
+/* Map::getLocalPointCloud (global = 0) / getGlobalPointCloud (global = 1): copy to host buffers of
+ * `capacity` points ((dim+1) x N features, dim x N normals or NULL).  With features == NULL only
+ * *n_out is written. */
+int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, float* normals,
+                             int64_t capacity, int64_t* n_out);
+
 /* Device-pointer variant of b200icp_transform (features/normals live on ctx's device). */
 int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows,
                                  float* d_normals, int64_t n, const float* T);

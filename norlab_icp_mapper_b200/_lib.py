@@ -19,7 +19,9 @@ SYMBOLS = [
     "b200icp_set_map", "b200icp_set_map_device", "b200icp_map_size", "b200icp_register",
     "b200icp_register_device", "b200icp_match", "b200icp_knn", "b200icp_transform",
     "b200icp_transform_device", "b200icp_get_map_mean", "b200icp_get_grid_info",
-    "b200icp_set_trace", "b200icp_get_trace",
+    "b200icp_set_trace", "b200icp_get_trace", "b200icp_map_insert_point_distance",
+    "b200icp_map_surface_normals", "b200icp_map_window", "b200icp_map_commit", "b200icp_map_counts",
+    "b200icp_map_has_normals", "b200icp_map_download",
 ]
 
 _lib = None
@@ -67,6 +69,13 @@ def load():
     L.b200icp_get_grid_info.argtypes = [vp, C.POINTER(f32), vp]
     L.b200icp_set_trace.argtypes = [vp, i32]
     L.b200icp_get_trace.argtypes = [vp, vp, i32]
+    L.b200icp_map_insert_point_distance.argtypes = [vp, vp, i32, i64, vp, f32, C.POINTER(i64), vp]
+    L.b200icp_map_surface_normals.argtypes = [vp, i32]
+    L.b200icp_map_window.argtypes = [vp, i32, vp, C.POINTER(i64)]
+    L.b200icp_map_commit.argtypes = [vp]
+    L.b200icp_map_counts.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.b200icp_map_has_normals.argtypes = [vp]
+    L.b200icp_map_download.argtypes = [vp, i32, vp, vp, i64, C.POINTER(i64)]
     if L.b200icp_abi_version() != 1:
         raise ImportError("libb200icp.so ABI version mismatch")
     _lib = L

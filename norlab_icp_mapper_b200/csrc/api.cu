@@ -20,6 +20,10 @@ struct b200icp_ctx {
     GridIndex map;
     bool has_map = false;
     int64_t map_n = 0;
+    MapStore store;  // the device-resident map the index is built from
+    bool index_stale = false;
+    uint8_t* d_keep = nullptr;
+    int64_t cap_keep = 0;
     GridIndex aux;  // index for b200icp_knn on arbitrary clouds
     IcpBuffers buf;
     float* d_stage_a = nullptr;  // uploads: features
@@ -214,6 +218,28 @@ int bits_for(uint64_t v) {
     return b;
 }
 
+// icp.setMap(localPointCloud): rebuild the spatial index from the loaded points of the store.
+int32_t commit_index(b200icp_ctx* ctx) {
+    MapStore& st = ctx->store;
+    cudaStream_t s = ctx->stream;
+    if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, ctx->map, s));
+    ctx->index_stale = false;
+    if (st.n_active == 0) return B200ICP_OK;  // LPM: "Ignoring attempt to create a map from an empty cloud"
+    float cell_hint = 0.f;
+    if (const char* env = getenv("B200ICP_CELL_EDGE")) cell_hint = (float)atof(env);
+    CK(cudaEventRecord(ctx->ev_map0, s));
+    CK(grid_build(ctx->map, reinterpret_cast<const float*>(st.feat), 4, ctx->cfg.dim, st.has_normals ? st.nrm : nullptr, st.n_active,
+                  /*centre=*/true, cell_hint, s, st.all_loaded ? nullptr : st.active));
+    CK(cudaEventRecord(ctx->ev_map1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_map0, ctx->ev_map1);
+    ctx->timing.setmap_ms = ms;
+    ctx->has_map = true;
+    ctx->map_n = st.n_active;
+    return B200ICP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -322,6 +348,8 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     grid_free(ctx->map);
     grid_free(ctx->aux);
+    store_free(ctx->store);
+    cudaFree(ctx->d_keep);
     IcpBuffers& b = ctx->buf;
     cudaFree(b.reading_in);
     cudaFree(b.reading);
@@ -411,18 +439,8 @@ int32_t b200icp_set_map_device(b200icp_ctx* ctx, const float* d_features, int32_
     if (n == 0) return B200ICP_OK;  // LPM: "Ignoring attempt to create a map from an empty cloud"
     if (!d_features) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null features");
     CK(cudaSetDevice(ctx->device));
-    float cell_hint = 0.f;
-    if (const char* env = getenv("B200ICP_CELL_EDGE")) cell_hint = (float)atof(env);
-    CK(cudaEventRecord(ctx->ev_map0, ctx->stream));
-    CK(grid_build(ctx->map, d_features, feature_rows, ctx->cfg.dim, d_normals, n, /*centre=*/true, cell_hint, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_map1, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev_map0, ctx->ev_map1);
-    ctx->timing.setmap_ms = ms;
-    ctx->has_map = true;
-    ctx->map_n = n;
-    return B200ICP_OK;
+    CK(store_set(ctx->store, d_features, feature_rows, ctx->cfg.dim, d_normals, n, ctx->stream));
+    return commit_index(ctx);
 }
 
 int32_t b200icp_set_map(b200icp_ctx* ctx, const float* features, int32_t feature_rows, const float* normals, int64_t n) {
@@ -712,6 +730,166 @@ int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t fe
     CK(cudaSetDevice(ctx->device));
     CK(launch_transform(d_features, feature_rows, dim, d_normals, n, M, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return B200ICP_OK;
+}
+
+/* ---- device-resident map: Map::updateLocalPointCloud / updatePose pieces -------------------------- */
+
+int32_t b200icp_map_commit(b200icp_ctx* ctx) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return commit_index(ctx);
+}
+
+int32_t b200icp_map_counts(const b200icp_ctx* ctx, int64_t* n_local, int64_t* n_global) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (n_local) *n_local = ctx->store.n_active;
+    if (n_global) *n_global = ctx->store.n;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_has_normals(const b200icp_ctx* ctx) { return (ctx && ctx->store.has_normals) ? 1 : 0; }
+
+int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                                          const float* input_normals, float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
+    if (n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+    if (n_added) *n_added = 0;
+    if (n_in == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    MapStore& st = ctx->store;
+    if (st.n_active > 0 && ctx->index_stale) {
+        const int32_t rc = commit_index(ctx);
+        if (rc != B200ICP_OK) return rc;
+    }
+    const size_t fb = (size_t)n_in * feature_rows * sizeof(float), nb = (size_t)n_in * dim * sizeof(float);
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + 256));
+    float* d_in = ctx->d_stage_a;
+    float* d_in_nrm = input_normals ? ctx->d_stage_a + ((fb + 255) / 256) * 64 : nullptr;
+    CK(cudaMemcpyAsync(d_in, input, fb, cudaMemcpyHostToDevice, s));
+    if (input_normals) CK(cudaMemcpyAsync(d_in_nrm, input_normals, nb, cudaMemcpyHostToDevice, s));
+    const int32_t eb = ensure_query_buffers(ctx, n_in, 1);
+    if (eb != B200ICP_OK) return eb;
+    if (st.n_active > 0) {
+        // Nabo::NNS::knn(input, k = 1, eps = 0, no radius) against the map -- on the live index
+        float Tpre[16];
+        mat4_identity(Tpre);
+        for (int d = 0; d < dim; ++d) Tpre[12 + d] = -ctx->map.mean[d];
+        CK(launch_prep_reading(d_in, feature_rows, dim, Tpre, ctx->d_q4, nullptr, nullptr, nullptr, n_in, s));
+        int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+        *h_nq = (int)n_in;
+        CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(launch_knn(ctx->map.view, ctx->d_q4, ctx->d_scalar_nq, (int)n_in, nullptr, 1, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+                      /*want_original_ids=*/1, ctx->cfg.nn_variant, s));
+    } else {  // createMap: the first cloud is taken as it is (PointDistanceMapperModule.cpp:9-19)
+        CK(cudaMemsetAsync(ctx->d_out_ids, 0xff, (size_t)n_in * sizeof(int32_t), s));
+        if (st.n == 0) st.has_normals = input_normals != nullptr;
+    }
+    if (keep_out && n_in > ctx->cap_keep) {
+        cudaFree(ctx->d_keep);
+        ctx->d_keep = nullptr;
+        ctx->cap_keep = 0;
+        CK(cudaMalloc((void**)&ctx->d_keep, (size_t)(n_in + n_in / 4 + 1024)));
+        ctx->cap_keep = n_in + n_in / 4 + 1024;
+    }
+    int64_t kept = 0;
+    const bool first = st.n == 0;
+    if (first) CK(store_reserve(st, dim, n_in, s));
+    if (first && input_normals) st.has_normals = true;  // nothing to intersect descriptors with yet
+    CK(store_insert_point_distance(st, ctx->map, d_in, feature_rows, dim, d_in_nrm, n_in, ctx->d_out_ids, min_dist_new_point, &kept,
+                                   keep_out ? ctx->d_keep : nullptr, s));
+    if (keep_out) CK(cudaMemcpyAsync(keep_out, ctx->d_keep, (size_t)n_in, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (kept > 0) ctx->index_stale = true;
+    if (n_added) *n_added = kept;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (knn < 1 || knn > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "knn must be in [1, 32]");
+    CK(cudaSetDevice(ctx->device));
+    MapStore& st = ctx->store;
+    if (st.n_active == 0) return B200ICP_OK;
+    if (ctx->index_stale || !ctx->has_map) {
+        const int32_t rc = commit_index(ctx);
+        if (rc != B200ICP_OK) return rc;
+    }
+    cudaStream_t s = ctx->stream;
+    const int64_t n = ctx->map.view.n;
+    const int32_t eb = ensure_query_buffers(ctx, n, knn);
+    if (eb != B200ICP_OK) return eb;
+    if (n > ctx->map.cap_normals) {
+        cudaFree(ctx->map.normals);
+        ctx->map.normals = nullptr;
+        ctx->map.cap_normals = 0;
+        CK(cudaMalloc((void**)&ctx->map.normals, (size_t)(n + n / 4 + 1024) * sizeof(float4)));
+        ctx->map.cap_normals = n + n / 4 + 1024;
+    }
+    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+    *h_nq = (int)n;
+    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+    // self k-NN: the queries are the cell-sorted map points themselves (neighbouring threads share cells)
+    CK(launch_knn(ctx->map.view, ctx->map.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+                  /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+    CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->map.normals, st.nrm, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->map.has_normals = true;
+    st.has_normals = true;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed) {
+    if (!ctx || !slab6) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int32_t slab[6];
+    memcpy(slab, slab6, sizeof(slab));
+    if (ctx->cfg.dim == 2) slab[4] = slab[5] = 0;  // Map.cpp:73-77,142-146
+    int64_t changed = 0;
+    CK(store_window(ctx->store, load, slab, &changed, ctx->stream));
+    if (changed > 0) {
+        ctx->store.all_loaded = false;
+        ctx->store.n_active += load ? changed : -changed;
+        ctx->index_stale = true;
+    }
+    if (n_changed) *n_changed = changed;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, float* normals, int64_t capacity, int64_t* n_out) {
+    if (!ctx || !n_out) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    MapStore& st = ctx->store;
+    const int dim = ctx->cfg.dim, rows = dim + 1;
+    const int64_t want = global ? st.n : st.n_active;
+    *n_out = want;
+    if (!features || want == 0) return B200ICP_OK;
+    if (capacity < want) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
+    std::vector<float4> f((size_t)st.n);
+    std::vector<uint8_t> l((size_t)st.n);
+    std::vector<float> nr;
+    CK(cudaMemcpy(f.data(), st.feat, f.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost));
+    const bool want_n = normals && st.has_normals;
+    if (want_n) {
+        nr.resize((size_t)st.n * dim);
+        CK(cudaMemcpy(nr.data(), st.nrm, nr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    int64_t o = 0;
+    for (int64_t i = 0; i < st.n; ++i) {
+        if (!global && !l[i]) continue;
+        features[o * rows + 0] = f[i].x;
+        features[o * rows + 1] = f[i].y;
+        if (dim == 3) features[o * rows + 2] = f[i].z;
+        features[o * rows + dim] = 1.f;
+        if (want_n)
+            for (int c = 0; c < dim; ++c) normals[o * dim + c] = nr[i * dim + c];
+        ++o;
+    }
+    *n_out = o;
     return B200ICP_OK;
 }
 

@@ -112,14 +112,41 @@ struct GridIndex {
 // Build the grid over `n` points given as `rows` floats each (device pointer, first dim floats
 // are coordinates).  centre=true subtracts the fixed-point mean first (ICPSequence::setMap).
 // cell_hint <= 0 lets the builder choose the cell edge.
+// d_subset (optional): n indices into the cloud; the grid is then built over those points only and
+// pts[].w / the normals gather keep referring to positions in the full cloud.
 cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, const float* d_normals,
-                       int64_t n, bool centre, float cell_hint, cudaStream_t s);
+                       int64_t n, bool centre, float cell_hint, cudaStream_t s, const uint32_t* d_subset = nullptr);
 void grid_free(GridIndex& g);
 cudaError_t ensure_scratch(GridIndex& g, int64_t n);  // sort scratch for at least n pairs
 
 // Stable radix sort of (key, value) pairs on `s` using g's scratch (also used to cell-sort readings).
 cudaError_t sort_pairs(GridIndex& scratch_owner, uint32_t* keys_in, uint32_t* keys_out,
                        uint32_t* vals_in, uint32_t* vals_out, int64_t n, int end_bit, cudaStream_t s);
+
+// ---- mapupd.cu -----------------------------------------------------------------------------
+// Device-resident map: every point ever inserted, in insertion order, map frame. `loaded` marks
+// membership of Map::localPointCloud; the rest is what the reference parks in its CellManager.
+struct MapStore {
+    float4* feat = nullptr;      // (x, y, z, 1)
+    float* nrm = nullptr;        // dim floats per point
+    uint8_t* loaded = nullptr;
+    uint32_t* active = nullptr;  // indices of the loaded points (valid after store_compact_active)
+    uint32_t *tmp_u32a = nullptr, *tmp_u32b = nullptr;
+    unsigned long long* d_counter = nullptr;
+    int64_t n = 0, cap = 0, n_active = 0, cap_tmp = 0;
+    bool has_normals = false;
+    bool all_loaded = true;
+};
+void store_free(MapStore& m);
+cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s);
+cudaError_t store_set(MapStore& m, const float* d_in, int rows, int dim, const float* d_normals, int64_t n, cudaStream_t s);
+cudaError_t store_compact_active(MapStore& m, GridIndex& scratch, cudaStream_t s);
+cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* changed, cudaStream_t s);
+cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const float* d_in, int rows, int dim,
+                                        const float* d_in_nrm, int64_t n_in, const int32_t* d_nn_id, float min_dist,
+                                        int64_t* n_kept, uint8_t* d_keep_out, cudaStream_t s);
+cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d_nn_pos, float4* d_nrm_sorted,
+                           float* d_store_nrm, cudaStream_t s);
 
 // ---- knn.cu --------------------------------------------------------------------------------
 // queries: float4 (x, y, z, *) in the grid's frame, optionally moved by state->T first.

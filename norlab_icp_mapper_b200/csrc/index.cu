@@ -33,13 +33,15 @@ inline float ordered_to_float(unsigned int u) {
 
 // out[0..2]: exact fixed-point coordinate sums (2^-16 m units, two's complement);
 // out[3..5] / out[6..8]: min / max per axis in order-preserving uint encoding.
-__global__ void __launch_bounds__(256) bbox_sum_kernel(const float* __restrict__ feat, int rows, int dim,
-                                                       long long n, unsigned long long* __restrict__ out) {
+__global__ void __launch_bounds__(256) bbox_sum_kernel(const float* __restrict__ feat_all, int rows, int dim, long long n,
+                                                       const uint32_t* __restrict__ subset,
+                                                       unsigned long long* __restrict__ out) {
     long long sum[3] = {0, 0, 0};
     unsigned int mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float* feat = feat_all + (subset ? (long long)subset[i] : i) * rows;
         for (int d = 0; d < dim; ++d) {
-            const float v = feat[i * rows + d];
+            const float v = feat[d];
             sum[d] += __double2ll_rn((double)v * 65536.0);
             const unsigned int o = float_to_ordered(v);
             mn[d] = min(mn[d], o);
@@ -68,16 +70,18 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv_h, int n) 
     return min(c, n - 1);
 }
 
-__global__ void __launch_bounds__(256) cell_key_kernel(const float* __restrict__ feat, int rows, int dim, long long n,
-                                                       float mx, float my, float mz, GridView g,
+__global__ void __launch_bounds__(256) cell_key_kernel(const float* __restrict__ feat_all, int rows, int dim, long long n,
+                                                       const uint32_t* __restrict__ subset, float mx, float my, float mz, GridView g,
                                                        float4* __restrict__ tmp_pts, uint32_t* __restrict__ keys,
                                                        uint32_t* __restrict__ vals, uint32_t* __restrict__ cell_count) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float x = feat[i * rows + 0] - mx;
-    const float y = feat[i * rows + 1] - my;
-    const float z = (dim == 3) ? feat[i * rows + 2] - mz : 0.f;
-    tmp_pts[i] = make_float4(x, y, z, __int_as_float((int)i));
+    const long long src = subset ? (long long)subset[i] : i;
+    const float* feat = feat_all + src * rows;
+    const float x = feat[0] - mx;
+    const float y = feat[1] - my;
+    const float z = (dim == 3) ? feat[2] - mz : 0.f;
+    tmp_pts[i] = make_float4(x, y, z, __int_as_float((int)src));  // .w = index into the caller's cloud
     const int cx = cell_coord(x, g.ox, g.inv_h, g.nx);
     const int cy = cell_coord(y, g.oy, g.inv_h, g.ny);
     const int cz = cell_coord(z, g.oz, g.inv_h, g.nz);
@@ -92,12 +96,13 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const float4* __rest
                                                             float4* __restrict__ pts, float4* __restrict__ nrm) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n) return;
-    const uint32_t src = perm[j];
-    pts[j] = tmp_pts[src];
+    const float4 p = tmp_pts[perm[j]];
+    pts[j] = p;
     if (nrm) {
-        const float nx = normals[(long long)src * dim + 0];
-        const float ny = normals[(long long)src * dim + 1];
-        const float nz = (dim == 3) ? normals[(long long)src * dim + 2] : 0.f;
+        const long long src = __float_as_int(p.w);
+        const float nx = normals[src * dim + 0];
+        const float ny = normals[src * dim + 1];
+        const float nz = (dim == 3) ? normals[src * dim + 2] : 0.f;
         nrm[j] = make_float4(nx, ny, nz, 0.f);
     }
 }
@@ -169,7 +174,7 @@ static int bits_for(uint64_t v) {
 }
 
 cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, const float* d_normals, int64_t n,
-                       bool centre, float cell_hint, cudaStream_t s) {
+                       bool centre, float cell_hint, cudaStream_t s, const uint32_t* d_subset) {
     cudaError_t e;
     if ((e = ensure_scratch(g, n)) != cudaSuccess) return e;
 
@@ -178,7 +183,7 @@ cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, con
     if ((e = cudaMemcpyAsync(g.d_reduce, h_red, sizeof(h_red), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
     {
         const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * kSMs);
-        bbox_sum_kernel<<<blocks, 256, 0, s>>>(d_feat, rows, dim, (long long)n, g.d_reduce);
+        bbox_sum_kernel<<<blocks, 256, 0, s>>>(d_feat, rows, dim, (long long)n, d_subset, g.d_reduce);
     }
     if ((e = cudaMemcpyAsync(h_red, g.d_reduce, sizeof(h_red), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -258,7 +263,7 @@ cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, con
     // ---- pass 2: keys + per-cell counts; scan; stable sort; gather ---------------------------
     if ((e = cudaMemsetAsync(g.cell_start, 0, (size_t)(n_cells + 1) * sizeof(uint32_t), s)) != cudaSuccess) return e;
     const int blocks = (int)((n + 255) / 256);
-    cell_key_kernel<<<blocks, 256, 0, s>>>(d_feat, rows, dim, (long long)n, g.mean[0], g.mean[1], g.mean[2], v, g.tmp_pts,
+    cell_key_kernel<<<blocks, 256, 0, s>>>(d_feat, rows, dim, (long long)n, d_subset, g.mean[0], g.mean[1], g.mean[2], v, g.tmp_pts,
                                            g.keys_in, g.vals_in, g.cell_start);
     size_t bytes = g.cub_tmp_bytes;
     if ((e = cub::DeviceScan::ExclusiveSum(g.cub_tmp, bytes, g.cell_start, g.cell_start, (int)(n_cells + 1), s)) != cudaSuccess)

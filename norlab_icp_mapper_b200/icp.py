@@ -149,6 +149,49 @@ class ICP:
         self._check(self._L.b200icp_transform(self._h, features.ctypes.data, rows, nptr, len(features), T_cm.ctypes.data))
         return features, normals
 
+    # -- device-resident local map (Map::updateLocalPointCloud / updatePose pieces) -----------------
+    def map_insert_point_distance(self, input_features, min_dist_new_point, input_normals=None, want_keep=False):
+        """PointDistanceMapperModule::inPlaceUpdateMap on the device map.  Returns (n_added, keep mask or None)."""
+        inp = _cloud(input_features, self.n)
+        nptr = None
+        if input_normals is not None:
+            input_normals = _cloud(input_normals, self.dim)
+            nptr = input_normals.ctypes.data
+        added = C.c_int64()
+        keep = np.zeros(len(inp), np.uint8) if want_keep else None
+        self._check(self._L.b200icp_map_insert_point_distance(self._h, inp.ctypes.data, self.n, len(inp), nptr, min_dist_new_point,
+                                                              C.byref(added), keep.ctypes.data if want_keep else None))
+        return added.value, (keep.astype(bool) if want_keep else None)
+
+    def map_surface_normals(self, knn):
+        self._check(self._L.b200icp_map_surface_normals(self._h, knn))
+
+    def map_window(self, load, slab):
+        slab = np.ascontiguousarray(slab, np.int32)
+        assert slab.shape == (6,)
+        changed = C.c_int64()
+        self._check(self._L.b200icp_map_window(self._h, int(load), slab.ctypes.data, C.byref(changed)))
+        return changed.value
+
+    def map_commit(self):
+        self._check(self._L.b200icp_map_commit(self._h))
+
+    def map_counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.b200icp_map_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def map_download(self, global_map=False):
+        n = C.c_int64()
+        self._check(self._L.b200icp_map_download(self._h, int(global_map), None, None, 0, C.byref(n)))
+        feat = np.zeros((n.value, self.n), np.float32)
+        has_n = bool(self._L.b200icp_map_has_normals(self._h))
+        nrm = np.zeros((n.value, self.dim), np.float32) if has_n else None
+        if n.value:
+            self._check(self._L.b200icp_map_download(self._h, int(global_map), feat.ctypes.data, nrm.ctypes.data if has_n else None,
+                                                     n.value, C.byref(n)))
+        return feat[:n.value], (nrm[:n.value] if has_n else None)
+
     # -- instrumentation ---------------------------------------------------------------------------
     def stream(self):
         return self._L.b200icp_stream(self._h)

@@ -1,0 +1,115 @@
+"""Device-resident map update steps against the oracle: PointDistance insert (bit-exact keep mask),
+SurfaceNormal post filter, the 20 m cell window, and that ICP after an update sees the new map."""
+import numpy as np
+import pytest
+
+from norlab_icp_mapper_b200 import synth
+from norlab_icp_mapper_b200._abi import make_config
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def gpu():
+    from norlab_icp_mapper_b200.icp import ICP
+    g = ICP(make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=15))
+    yield g
+    g.close()
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return synth.make_pair_3d(n_map=150_000, n_scan=15_000)
+
+
+def test_point_distance_insert_matches_oracle(gpu, oracle, pair):
+    gpu.set_map(pair["map"], pair["normals"])
+    inp = pair["reading"].copy()
+    inp[:, :3] = synth.apply_T(pair["correction_true"], pair["reading"])  # the input arrives in the map frame
+    inp = inp.astype(np.float32)
+    for min_dist in (0.05, 0.15, 0.5):
+        gpu.set_map(pair["map"], pair["normals"])
+        added, keep = gpu.map_insert_point_distance(inp, min_dist, want_keep=True)
+        kept, okeep = oracle.point_distance_keep(pair["map"], inp, min_dist)
+        assert np.array_equal(keep, okeep), (min_dist, (keep != okeep).sum())
+        assert added == kept == keep.sum()
+        n_local, n_global = gpu.map_counts()
+        assert n_local == n_global == len(pair["map"]) + kept
+        feat, nrm = gpu.map_download()
+        assert nrm is None  # DataPoints::concatenate drops the map's normals when the input has none
+        assert np.array_equal(feat[:len(pair["map"])], pair["map"])
+        assert np.array_equal(feat[len(pair["map"]):], inp[keep])  # appended in input order
+
+
+def test_create_map_on_empty(gpu, pair):
+    added, keep = gpu.map_insert_point_distance(pair["reading"], 0.15, want_keep=True)
+    assert added == len(pair["reading"]) and keep.all()  # createMap copies the input
+    gpu.map_commit()
+    assert gpu.has_map()
+    ids, d2 = gpu.match(pair["reading"][:100])
+    assert np.all(d2 == 0) and np.array_equal(ids[:, 0], np.arange(100))
+
+
+def test_surface_normals_match_oracle(gpu, oracle, pair):
+    sub = pair["map"][:60_000]
+    gpu.set_map(sub, None)
+    gpu.map_surface_normals(10)
+    _, nrm = gpu.map_download()
+    rc, onrm = oracle.surface_normals(sub, 10)
+    assert rc == 0 and nrm is not None
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
+    cosang = np.abs(np.einsum("ij,ij->i", nrm, onrm))
+    # identical neighbour sets; the eigenvector differs only where the two smallest eigenvalues are nearly equal
+    assert np.median(cosang) > 0.999999 and (cosang > 0.9999).mean() > 0.99, (np.median(cosang), (cosang > 0.9999).mean())
+    # and they are real surface normals: close to the analytic ones of the synthetic world
+    truth = np.abs(np.einsum("ij,ij->i", nrm, pair["normals"][:60_000]))
+    assert np.median(truth) > 0.95
+
+
+def test_icp_after_update_uses_new_normals(gpu, oracle, pair):
+    """Full Map::updateLocalPointCloud sequence on the device, then icp(): same pose as the oracle
+    run on the downloaded map."""
+    gpu.set_map(pair["map"][:100_000], None)
+    extra = pair["map"][100_000:]
+    added, _ = gpu.map_insert_point_distance(extra, 0.05)
+    gpu.map_commit()
+    gpu.map_surface_normals(10)
+    feat, nrm = gpu.map_download()
+    assert len(feat) == 100_000 + added and nrm is not None
+    T_g = gpu(pair["reading"])
+    cfg = gpu.cfg
+    o = oracle.OracleICP(cfg)
+    o.set_map(feat, nrm)
+    rc, T_o, res, _, _ = o.register(pair["reading"])
+    er, et = synth.pose_error(T_g, T_o)
+    assert rc == 0 and er <= 1e-4 and et <= 1e-3, (er, et)
+
+
+def test_cell_window_load_unload(gpu, pair):
+    m = pair["map"]
+    gpu.set_map(m, pair["normals"])
+    cell = np.floor(m[:, :3] / 20.0).astype(int)
+    # unload the slab rows [-5, -2] (x in [-100, -20)), everything in y / z
+    big = 10 ** 6
+    changed = gpu.map_window(False, [-5, -2, -big, big, -big, big])
+    inside = (m[:, 0] >= -100.0) & (m[:, 0] < -20.0)
+    assert changed == inside.sum()
+    n_local, n_global = gpu.map_counts()
+    assert n_local == len(m) - inside.sum() and n_global == len(m)
+    gpu.map_commit()
+    feat, nrm = gpu.map_download()
+    assert np.array_equal(feat, m[~inside]) and np.array_equal(nrm, pair["normals"][~inside])
+    gfeat, _ = gpu.map_download(global_map=True)
+    assert np.array_equal(gfeat, m)
+    # queries in the unloaded region no longer find neighbours within maxDist; others are untouched
+    q = m[inside][:2000]
+    ids, d2 = gpu.match(q)
+    assert (ids[:, 0] == -1).mean() > 0.9
+    # load back two of the four rows
+    changed = gpu.map_window(True, [-4, -3, -big, big, -big, big])
+    back = inside & (cell[:, 0] >= -4) & (cell[:, 0] <= -3)
+    assert changed == back.sum()
+    gpu.map_commit()
+    ids, d2 = gpu.match(m[back][:2000])
+    assert np.all(d2[:, 0] == 0)
+    assert gpu.map_counts()[0] == len(m) - inside.sum() + back.sum()
