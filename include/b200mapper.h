@@ -1,0 +1,63 @@
+/*
+ * b200mapper.h -- C face of the host-side mirror of norlab_icp_mapper::Mapper
+ * (norlab_icp_mapper_b200/host/, libb200mapper.so).  It exists so that non-C++ callers (the ctypes
+ * tests, a cgo/JNI binding) can drive the same Mapper::processInput sequence the reference exposes
+ * through pybind11 (python/src/mapper.cpp:11-25).  Matrices are column-major fp32 like b200icp.h.
+ */
+#ifndef B200MAPPER_H
+#define B200MAPPER_H
+
+#include <stdint.h>
+#include "b200icp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200mapper b200mapper;
+
+typedef struct b200mapper_config {
+    b200icp_config icp;        /* YAML `icp:`                                                        */
+    int32_t update_condition;  /* mapper.updateCondition.type: 0 distance, 1 delay, 2 overlap        */
+    float update_value;        /* mapper.updateCondition.value                                       */
+    float sensor_max_range;    /* mapper.sensorMaxRange (default 200)                                */
+    float min_dist_new_point;  /* PointDistanceMapperModule{minDistNewPoint}; < 0: the default 0.15  */
+    int32_t surface_normal_knn;/* post: SurfaceNormalDataPointsFilter{knn}; 0 = absent               */
+    int32_t is_3d, is_online, is_mapping;
+    int32_t reserved[4];
+} b200mapper_config;
+
+typedef struct b200mapper_stats {
+    float overlap;             /* icp.errorMinimizer->getOverlap() of the last processInput          */
+    int32_t iterations;
+    int32_t map_updated;       /* the last processInput called updateMap                             */
+    int32_t n_window_updates;  /* slabs loaded/unloaded by the last Map::updatePose                  */
+    int64_t n_local, n_global; /* points in Map::localPointCloud / in the whole map                  */
+} b200mapper_stats;
+
+/* Mapper::Mapper(config, is3D, isOnline, isMapping, saveMapCellsOnHardDrive) -- Mapper.cpp:15-33 */
+int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapper** out);
+void b200mapper_destroy(b200mapper* m);
+const char* b200mapper_last_error(const b200mapper* m);
+/* Mapper::applyInputFilters -- Mapper.cpp:187-191; in place, returns the new point count in *n */
+int32_t b200mapper_apply_input_filters(b200mapper* m, float* features, int32_t feature_rows, int64_t* n);
+/* Mapper::processInput -- Mapper.cpp:194-238; status codes of b200icp.h (exceptions of the C++ class) */
+int32_t b200mapper_process_input(b200mapper* m, const float* features_sensor_frame, int32_t feature_rows, int64_t n,
+                                 const float* estimated_pose, double time_stamp_seconds);
+int32_t b200mapper_get_pose(b200mapper* m, float* pose);                       /* Mapper::getPose        */
+int32_t b200mapper_get_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n); /* getMap */
+int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n,
+                                     int32_t* available);                      /* Mapper::getNewLocalMap */
+int32_t b200mapper_set_map(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, int64_t n);
+int32_t b200mapper_get_is_mapping(const b200mapper* m);
+int32_t b200mapper_set_is_mapping(b200mapper* m, int32_t is_mapping);
+int64_t b200mapper_trajectory_size(b200mapper* m);                             /* Mapper::getTrajectory  */
+int32_t b200mapper_get_trajectory(b200mapper* m, float* poses, double* stamps, int64_t capacity);
+int32_t b200mapper_get_stats(b200mapper* m, b200mapper_stats* out);
+/* slabs applied by the last Map::updatePose, 7 ints each (see Map::lastUpdates) */
+int32_t b200mapper_get_window_updates(b200mapper* m, int32_t* out7, int32_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

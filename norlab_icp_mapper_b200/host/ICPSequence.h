@@ -1,0 +1,62 @@
+// ICPSequence.h -- `PM::ICPSequence icp` (reference Mapper.h:23) over the C-ABI of libb200icp.so.
+// Same methods the reference calls: setMap (Map.cpp:111,178,528,581), operator() (Mapper.cpp:213),
+// getOverlap (Mapper.cpp:219); libpointmatcher's exceptions are re-thrown from the status codes.
+#pragma once
+#include "DataPoints.h"
+#include "b200icp.h"
+
+namespace norlab_icp_mapper_b200 {
+
+class ICPSequence {
+    b200icp_ctx* ctx = nullptr;
+    b200icp_result last{};
+    int dim;
+
+   public:
+    static void check(b200icp_ctx* c, int32_t rc) {
+        switch (rc) {
+            case B200ICP_OK:
+                return;
+            case B200ICP_ERR_CONVERGENCE:
+            case B200ICP_ERR_BOUND:
+            case B200ICP_ERR_NAN:
+                throw ConvergenceError(b200icp_last_error(c));
+            case B200ICP_ERR_TRANSFORM:
+                throw TransformationError(b200icp_last_error(c));
+            case B200ICP_ERR_INVALID_FIELD:
+                throw InvalidField(b200icp_last_error(c));
+            default:
+                throw std::runtime_error(b200icp_last_error(c));
+        }
+    }
+    ICPSequence(const b200icp_config& cfg, int device) : dim(cfg.dim) { check(nullptr, b200icp_create(&cfg, device, &ctx)); }
+    ~ICPSequence() { b200icp_destroy(ctx); }
+    ICPSequence(const ICPSequence&) = delete;
+    ICPSequence& operator=(const ICPSequence&) = delete;
+
+    b200icp_ctx* context() { return ctx; }
+    bool hasMap() const { return b200icp_map_size(ctx) > 0; }
+    bool setMap(const DataPoints& map) {
+        check(ctx, b200icp_set_map(ctx, map.features.data(), dim + 1, map.normals.empty() ? nullptr : map.normals.data(), map.getNbPoints()));
+        return map.getNbPoints() > 0;
+    }
+    TransformationParameters operator()(const DataPoints& cloud) {
+        TransformationParameters T = TransformationParameters::Identity(dim + 1);
+        const int32_t rc = b200icp_register(ctx, cloud.features.data(), dim + 1, cloud.getNbPoints(), nullptr, T.m, &last);
+        if (rc == B200ICP_ERR_NO_MAP) return T;  // LPM: no map -> identity
+        check(ctx, rc);
+        return T;
+    }
+    float getOverlap() const { return last.overlap; }  // errorMinimizer->getOverlap()
+    const b200icp_result& lastResult() const { return last; }
+};
+
+// PM::Transformation("RigidTransformation")::compute (Mapper.cpp:197,221)
+inline DataPoints rigidTransform(ICPSequence& icp, const DataPoints& in, const TransformationParameters& T) {
+    DataPoints out = in;
+    ICPSequence::check(icp.context(), b200icp_transform(icp.context(), out.features.data(), in.dim + 1,
+                                                        out.normals.empty() ? nullptr : out.normals.data(), out.getNbPoints(), T.m));
+    return out;
+}
+
+}  // namespace norlab_icp_mapper_b200

@@ -1,0 +1,64 @@
+// Mapper.h -- host mirror of norlab_icp_mapper::Mapper (reference Mapper.{h,cpp}): same public
+// methods, same processInput / shouldUpdateMap / updateMap sequence, the heavy steps delegated to
+// libb200icp.so.  YAML parsing is out of scope: the configuration arrives as the
+// struct the reference's loadYamlConfig would produce.
+#pragma once
+#include <atomic>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "Map.h"
+
+namespace norlab_icp_mapper_b200 {
+
+struct MapperConfig {
+    b200icp_config icp;                                      // YAML `icp:` (Mapper.cpp:70-78)
+    PostFilters post;                                        // YAML `post:` (Mapper.cpp:90-98)
+    std::string mapUpdateCondition = "distance";            // mapper.updateCondition.type (Mapper.cpp:117-146)
+    float mapUpdateValue = 1.0f;                             // ... .value (DEFAULT_MAP_UPDATE_DISTANCE, Mapper.h:20)
+    float sensorMaxRange = 200.0f;                           // mapper.sensorMaxRange (Mapper.cpp:152-160)
+    std::vector<std::pair<std::string, Parameters>> mapperModules;  // mapper.mapperModule (Mapper.cpp:162-172); empty -> default
+};
+
+class Mapper {
+    ICPSequence icp;
+    PostFilters mapPostFilters;
+    std::string mapUpdateCondition;
+    float mapUpdateOverlap = 0.f, mapUpdateDelay = 0.f, mapUpdateDistance = 1.0f;
+    bool is3D, isOnline;
+    std::atomic_bool isMapping;
+    std::mutex icpMapLock;
+    Map map;
+    TransformationParameters pose;
+    std::vector<std::pair<TransformationParameters, double>> trajectory;
+    double lastTimeMapWasUpdated = 0.0;
+    TransformationParameters lastPoseWhereMapWasUpdated;
+    std::mutex poseLock, trajectoryLock;
+    MapperModuleRegistrar registrar;
+    bool lastInputUpdatedMap = false;
+
+    void fillRegistrar();
+    void updateMap(const DataPoints& currentInput, const TransformationParameters& currentPose, double currentTimeStamp);
+    bool shouldUpdateMap(double currentTime, const TransformationParameters& currentPose, float currentOverlap) const;
+
+   public:
+    Mapper(const MapperConfig& config, bool is3D, bool isOnline, bool isMapping, bool saveMapCellsOnHardDrive, int device = 0);
+    void applyInputFilters(DataPoints& inputInSensorFrame);
+    void processInput(const DataPoints& filteredInputInSensorFrame, const TransformationParameters& estimatedPose, double timeStamp);
+    DataPoints getMap();
+    void setMap(const DataPoints& newMap);
+    bool getNewLocalMap(DataPoints& mapOut);
+    TransformationParameters getPose();
+    bool getIsMapping() const;
+    void setIsMapping(bool newIsMapping);
+    std::vector<std::pair<TransformationParameters, double>> getTrajectory();
+    // introspection for tests / benches
+    Map& getMapObject() { return map; }
+    ICPSequence& getICP() { return icp; }
+    bool lastInputTriggeredMapUpdate() const { return lastInputUpdatedMap; }
+};
+
+}  // namespace norlab_icp_mapper_b200

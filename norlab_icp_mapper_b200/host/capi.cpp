@@ -1,0 +1,182 @@
+// capi.cpp -- extern "C" face of the host mirror (include/b200mapper.h).
+#include <cstring>
+#include <string>
+
+#include "Mapper.h"
+#include "b200mapper.h"
+
+using namespace norlab_icp_mapper_b200;
+
+struct b200mapper {
+    std::unique_ptr<Mapper> mapper;
+    int dim = 3;
+    std::string err;
+};
+
+namespace {
+std::string g_err;
+
+template <typename F>
+int32_t guarded(b200mapper* m, F&& f) {
+    try {
+        f();
+        return B200ICP_OK;
+    } catch (const ConvergenceError& e) {
+        (m ? m->err : g_err) = e.what();
+        return B200ICP_ERR_CONVERGENCE;
+    } catch (const TransformationError& e) {
+        (m ? m->err : g_err) = e.what();
+        return B200ICP_ERR_TRANSFORM;
+    } catch (const InvalidField& e) {
+        (m ? m->err : g_err) = e.what();
+        return B200ICP_ERR_INVALID_FIELD;
+    } catch (const InvalidParameter& e) {
+        (m ? m->err : g_err) = e.what();
+        return B200ICP_ERR_INVALID_ARG;
+    } catch (const std::exception& e) {
+        (m ? m->err : g_err) = e.what();
+        return B200ICP_ERR_CUDA;
+    }
+}
+
+DataPoints wrap(const float* f, int rows, int64_t n, const float* nrm) {
+    DataPoints d;
+    d.dim = rows - 1;
+    d.features.assign(f, f + (size_t)n * rows);
+    if (nrm) d.normals.assign(nrm, nrm + (size_t)n * d.dim);
+    return d;
+}
+TransformationParameters wrapT(const float* T, int n) {
+    TransformationParameters P = TransformationParameters::Identity(n);
+    if (T) std::memcpy(P.m, T, sizeof(float) * (size_t)(n * n));
+    return P;
+}
+int32_t copy_out(const DataPoints& d, float* features, float* normals, int64_t capacity, int64_t* n) {
+    *n = d.getNbPoints();
+    if (!features) return B200ICP_OK;
+    if (capacity < *n) return B200ICP_ERR_INVALID_ARG;
+    std::memcpy(features, d.features.data(), d.features.size() * sizeof(float));
+    if (normals && !d.normals.empty()) std::memcpy(normals, d.normals.data(), d.normals.size() * sizeof(float));
+    return B200ICP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapper** out) {
+    if (!cfg || !out) return B200ICP_ERR_INVALID_ARG;
+    *out = nullptr;
+    b200mapper* m = new b200mapper();
+    const int32_t rc = guarded(nullptr, [&] {
+        MapperConfig mc;
+        mc.icp = cfg->icp;
+        mc.post.surfaceNormalKnn = cfg->surface_normal_knn;
+        mc.mapUpdateCondition = cfg->update_condition == 0 ? "distance" : (cfg->update_condition == 1 ? "delay" : (cfg->update_condition == 2 ? "overlap" : "?"));
+        mc.mapUpdateValue = cfg->update_value;
+        mc.sensorMaxRange = cfg->sensor_max_range;
+        if (cfg->min_dist_new_point >= 0.f)
+            mc.mapperModules.push_back({"PointDistanceMapperModule", Parameters{{"minDistNewPoint", std::to_string(cfg->min_dist_new_point)}}});
+        m->dim = cfg->is_3d ? 3 : 2;
+        m->mapper.reset(new Mapper(mc, cfg->is_3d != 0, cfg->is_online != 0, cfg->is_mapping != 0, false, device));
+    });
+    if (rc != B200ICP_OK) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return B200ICP_OK;
+}
+
+void b200mapper_destroy(b200mapper* m) { delete m; }
+const char* b200mapper_last_error(const b200mapper* m) { return m ? m->err.c_str() : g_err.c_str(); }
+
+int32_t b200mapper_apply_input_filters(b200mapper* m, float* features, int32_t feature_rows, int64_t* n) {
+    if (!m || !features || !n || feature_rows != m->dim + 1) return B200ICP_ERR_INVALID_ARG;
+    return guarded(m, [&] {
+        DataPoints d = wrap(features, feature_rows, *n, nullptr);
+        m->mapper->applyInputFilters(d);
+        *n = d.getNbPoints();
+        std::memcpy(features, d.features.data(), d.features.size() * sizeof(float));
+    });
+}
+
+int32_t b200mapper_process_input(b200mapper* m, const float* features, int32_t feature_rows, int64_t n, const float* estimated_pose,
+                                 double time_stamp_seconds) {
+    if (!m || (n > 0 && !features) || feature_rows != m->dim + 1) return B200ICP_ERR_INVALID_ARG;
+    return guarded(m, [&] {
+        m->mapper->processInput(wrap(features, feature_rows, n, nullptr), wrapT(estimated_pose, m->dim + 1), time_stamp_seconds);
+    });
+}
+
+int32_t b200mapper_get_pose(b200mapper* m, float* pose) {
+    if (!m || !pose) return B200ICP_ERR_INVALID_ARG;
+    const TransformationParameters T = m->mapper->getPose();
+    std::memcpy(pose, T.m, sizeof(float) * (size_t)(T.n * T.n));
+    return B200ICP_OK;
+}
+
+int32_t b200mapper_get_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n) {
+    if (!m || !n) return B200ICP_ERR_INVALID_ARG;
+    int32_t rc2 = B200ICP_OK;
+    const int32_t rc = guarded(m, [&] { rc2 = copy_out(m->mapper->getMap(), features, normals, capacity, n); });
+    return rc != B200ICP_OK ? rc : rc2;
+}
+
+int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n, int32_t* available) {
+    if (!m || !n || !available) return B200ICP_ERR_INVALID_ARG;
+    int32_t rc2 = B200ICP_OK;
+    const int32_t rc = guarded(m, [&] {
+        DataPoints d;
+        d.dim = m->dim;
+        *available = m->mapper->getNewLocalMap(d) ? 1 : 0;
+        *n = 0;
+        if (*available) rc2 = copy_out(d, features, normals, capacity, n);
+    });
+    return rc != B200ICP_OK ? rc : rc2;
+}
+
+int32_t b200mapper_set_map(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, int64_t n) {
+    if (!m || (n > 0 && !features) || feature_rows != m->dim + 1) return B200ICP_ERR_INVALID_ARG;
+    return guarded(m, [&] { m->mapper->setMap(wrap(features, feature_rows, n, normals)); });
+}
+
+int32_t b200mapper_get_is_mapping(const b200mapper* m) { return (m && m->mapper->getIsMapping()) ? 1 : 0; }
+int32_t b200mapper_set_is_mapping(b200mapper* m, int32_t v) {
+    if (!m) return B200ICP_ERR_INVALID_ARG;
+    m->mapper->setIsMapping(v != 0);
+    return B200ICP_OK;
+}
+
+int64_t b200mapper_trajectory_size(b200mapper* m) { return m ? (int64_t)m->mapper->getTrajectory().size() : 0; }
+int32_t b200mapper_get_trajectory(b200mapper* m, float* poses, double* stamps, int64_t capacity) {
+    if (!m || !poses) return B200ICP_ERR_INVALID_ARG;
+    const auto tr = m->mapper->getTrajectory();
+    const int nn = (m->dim + 1) * (m->dim + 1);
+    for (int64_t i = 0; i < (int64_t)tr.size() && i < capacity; ++i) {
+        std::memcpy(poses + i * nn, tr[i].first.m, sizeof(float) * (size_t)nn);
+        if (stamps) stamps[i] = tr[i].second;
+    }
+    return B200ICP_OK;
+}
+
+int32_t b200mapper_get_stats(b200mapper* m, b200mapper_stats* out) {
+    if (!m || !out) return B200ICP_ERR_INVALID_ARG;
+    const b200icp_result& r = m->mapper->getICP().lastResult();
+    out->overlap = r.overlap;
+    out->iterations = r.iterations;
+    out->map_updated = m->mapper->lastInputTriggeredMapUpdate() ? 1 : 0;
+    out->n_window_updates = (int32_t)m->mapper->getMapObject().lastUpdates().size();
+    out->n_local = m->mapper->getMapObject().localSize();
+    out->n_global = m->mapper->getMapObject().globalSize();
+    return B200ICP_OK;
+}
+
+int32_t b200mapper_get_window_updates(b200mapper* m, int32_t* out7, int32_t capacity) {
+    if (!m || !out7) return B200ICP_ERR_INVALID_ARG;
+    const auto u = m->mapper->getMapObject().lastUpdates();
+    for (int i = 0; i < (int)u.size() && i < capacity; ++i)
+        for (int j = 0; j < 7; ++j) out7[i * 7 + j] = u[i][j];
+    return (int32_t)u.size();
+}
+
+}  // extern "C"

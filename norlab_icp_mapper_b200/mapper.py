@@ -1,0 +1,159 @@
+"""Python face of the host-side mirror of `norlab_icp_mapper::Mapper` (libb200mapper.so, C++ in
+norlab_icp_mapper_b200/host/).  Method names follow the reference's pybind11 module
+(/root/reference/python/src/mapper.cpp:11-25): Mapper(config, is3D, isOnline, isMapping,
+saveMapCellsOnHardDrive), applyInputFilters, processInput, getMap, setMap, getNewLocalMap, getPose,
+getIsMapping, setIsMapping, getTrajectory."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._lib import B200ICPError, load as _load_icp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libb200mapper.so")
+SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "b200mapper_apply_input_filters",
+           "b200mapper_process_input", "b200mapper_get_pose", "b200mapper_get_map", "b200mapper_get_new_local_map",
+           "b200mapper_set_map", "b200mapper_get_is_mapping", "b200mapper_set_is_mapping", "b200mapper_trajectory_size",
+           "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates"]
+
+
+class MapperConfig(C.Structure):
+    _fields_ = [("icp", _abi.Config), ("update_condition", C.c_int32), ("update_value", C.c_float),
+                ("sensor_max_range", C.c_float), ("min_dist_new_point", C.c_float), ("surface_normal_knn", C.c_int32),
+                ("is_3d", C.c_int32), ("is_online", C.c_int32), ("is_mapping", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class MapperStats(C.Structure):
+    _fields_ = [("overlap", C.c_float), ("iterations", C.c_int32), ("map_updated", C.c_int32), ("n_window_updates", C.c_int32),
+                ("n_local", C.c_int64), ("n_global", C.c_int64)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    _load_icp()  # libb200icp.so first (also resolved through the rpath)
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing: build it with `make -C norlab_icp_mapper_b200/host`")
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.b200mapper_create.argtypes = [C.POINTER(MapperConfig), i32, C.POINTER(vp)]
+    L.b200mapper_destroy.argtypes = [vp]
+    L.b200mapper_destroy.restype = None
+    L.b200mapper_last_error.argtypes = [vp]
+    L.b200mapper_last_error.restype = C.c_char_p
+    L.b200mapper_apply_input_filters.argtypes = [vp, vp, i32, C.POINTER(i64)]
+    L.b200mapper_process_input.argtypes = [vp, vp, i32, i64, vp, C.c_double]
+    L.b200mapper_get_pose.argtypes = [vp, vp]
+    L.b200mapper_get_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    L.b200mapper_get_new_local_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
+    L.b200mapper_set_map.argtypes = [vp, vp, i32, vp, i64]
+    L.b200mapper_get_is_mapping.argtypes = [vp]
+    L.b200mapper_set_is_mapping.argtypes = [vp, i32]
+    L.b200mapper_trajectory_size.argtypes = [vp]
+    L.b200mapper_trajectory_size.restype = i64
+    L.b200mapper_get_trajectory.argtypes = [vp, vp, vp, i64]
+    L.b200mapper_get_stats.argtypes = [vp, C.POINTER(MapperStats)]
+    L.b200mapper_get_window_updates.argtypes = [vp, vp, i32]
+    _lib = L
+    return L
+
+
+class Mapper:
+    CONDITIONS = {"distance": 0, "delay": 1, "overlap": 2}
+
+    def __init__(self, icp_config, is3D=True, isOnline=False, isMapping=True, saveMapCellsOnHardDrive=False, *,
+                 updateCondition=("distance", 1.0), sensorMaxRange=200.0, minDistNewPoint=0.15, surfaceNormalKnn=0, device=0):
+        self._L = load()
+        cfg = MapperConfig()
+        cfg.icp = icp_config
+        cfg.update_condition = self.CONDITIONS.get(updateCondition[0], 99)
+        cfg.update_value = updateCondition[1]
+        cfg.sensor_max_range = sensorMaxRange
+        cfg.min_dist_new_point = minDistNewPoint
+        cfg.surface_normal_knn = surfaceNormalKnn
+        cfg.is_3d, cfg.is_online, cfg.is_mapping = int(is3D), int(isOnline), int(isMapping)
+        self.dim = 3 if is3D else 2
+        self.n = self.dim + 1
+        h = C.c_void_p()
+        rc = self._L.b200mapper_create(C.byref(cfg), device, C.byref(h))
+        if rc != _abi.OK:
+            raise B200ICPError(rc, self._L.b200mapper_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200mapper_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != _abi.OK:
+            raise B200ICPError(rc, self._L.b200mapper_last_error(self._h).decode())
+
+    def applyInputFilters(self, cloud):
+        cloud = np.ascontiguousarray(cloud, np.float32).copy()
+        n = C.c_int64(len(cloud))
+        self._check(self._L.b200mapper_apply_input_filters(self._h, cloud.ctypes.data, self.n, C.byref(n)))
+        return cloud[:n.value]
+
+    def processInput(self, cloud_sensor_frame, estimatedPose, timeStamp):
+        cloud = np.ascontiguousarray(cloud_sensor_frame, np.float32)
+        T = np.ascontiguousarray(np.asarray(estimatedPose, np.float32).T).ravel()
+        self._check(self._L.b200mapper_process_input(self._h, cloud.ctypes.data, self.n, len(cloud), T.ctypes.data, float(timeStamp)))
+
+    def getPose(self):
+        T = np.zeros(self.n * self.n, np.float32)
+        self._check(self._L.b200mapper_get_pose(self._h, T.ctypes.data))
+        return T.reshape(self.n, self.n).T.copy()
+
+    def getMap(self):
+        n = C.c_int64()
+        self._check(self._L.b200mapper_get_map(self._h, None, None, 0, C.byref(n)))
+        feat = np.zeros((n.value, self.n), np.float32)
+        nrm = np.full((n.value, self.dim), np.nan, np.float32)
+        if n.value:
+            self._check(self._L.b200mapper_get_map(self._h, feat.ctypes.data, nrm.ctypes.data, n.value, C.byref(n)))
+        return feat, (None if np.isnan(nrm).all() else nrm)
+
+    def setMap(self, features, normals=None):
+        features = np.ascontiguousarray(features, np.float32)
+        nptr = None
+        if normals is not None:
+            normals = np.ascontiguousarray(normals, np.float32)
+            nptr = normals.ctypes.data
+        self._check(self._L.b200mapper_set_map(self._h, features.ctypes.data, self.n, nptr, len(features)))
+
+    def getIsMapping(self):
+        return bool(self._L.b200mapper_get_is_mapping(self._h))
+
+    def setIsMapping(self, v):
+        self._check(self._L.b200mapper_set_is_mapping(self._h, int(v)))
+
+    def getTrajectory(self):
+        n = self._L.b200mapper_trajectory_size(self._h)
+        poses = np.zeros((n, self.n * self.n), np.float32)
+        stamps = np.zeros(n, np.float64)
+        if n:
+            self._check(self._L.b200mapper_get_trajectory(self._h, poses.ctypes.data, stamps.ctypes.data, n))
+        return poses.reshape(n, self.n, self.n).transpose(0, 2, 1).copy(), stamps
+
+    def stats(self):
+        s = MapperStats()
+        self._check(self._L.b200mapper_get_stats(self._h, C.byref(s)))
+        return s
+
+    def windowUpdates(self):
+        buf = np.zeros((64, 7), np.int32)
+        n = self._L.b200mapper_get_window_updates(self._h, buf.ctypes.data, 64)
+        return buf[:n].copy()

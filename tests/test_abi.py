@@ -83,3 +83,31 @@ def test_no_cpu_fallback(lib):
     with pytest.raises(B200ICPError):
         ICP(cfg)
     assert lib.b200icp_map_size(None) == 0
+
+
+def test_mapper_library_exports_its_header(lib):
+    """libb200mapper.so (host-side C++ mirror of Mapper/Map/MapperModule) exports include/b200mapper.h."""
+    from norlab_icp_mapper_b200 import mapper
+    if not os.path.exists(mapper.SO_PATH):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "norlab_icp_mapper_b200", "host")], check=True)
+    M = mapper.load()
+    text = open(os.path.join(ROOT, "include", "b200mapper.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200mapper_[a-z0-9_]+)\s*\(", text)))
+    assert declared == sorted(mapper.SYMBOLS)
+    assert not [s for s in declared if not hasattr(M, s)]
+    src = r'''
+#include <stdio.h>
+#include "b200mapper.h"
+int main(void) { printf("%zu %zu\n", sizeof(b200mapper_config), sizeof(b200mapper_stats)); return 0; }'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [C.sizeof(mapper.MapperConfig), C.sizeof(mapper.MapperStats)]
+    import torch
+    if not torch.cuda.is_available():  # no fallback: constructing a Mapper without a GPU fails loudly
+        from norlab_icp_mapper_b200._lib import B200ICPError
+        with pytest.raises(B200ICPError):
+            mapper.Mapper(_abi.make_config(), True, False, True, False)

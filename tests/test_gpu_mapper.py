@@ -1,0 +1,139 @@
+"""The host-side C++ mirror of Mapper::processInput (libb200mapper.so over libb200icp.so) against a
+step-by-step restatement of the reference's sequence on the CPU oracle (tests/reference_mapper.py)."""
+import numpy as np
+import pytest
+
+from norlab_icp_mapper_b200 import synth
+from norlab_icp_mapper_b200._abi import make_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _scans(n_scans=6, n_pts=20_000, step=0.8, seed=77):
+    world = synth.World3D(seed=1234, size=(120.0, 120.0), n_boxes=16)
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_scans):
+        T_true = synth.make_T((-10.0 + step * i, 2.0 + 0.3 * i, 1.5), (0.0, 0.0, 10.0 + 3.0 * i))
+        S, _ = world.sample(n_pts, np.random.default_rng(seed + 100 + i), noise=0.01, center=T_true[:3, 3], radius=40.0)
+        scan = synth.homog(synth.apply_T(np.linalg.inv(T_true), S))
+        noise = synth.make_T(rng.normal(0, 0.05, 3), rng.normal(0, 0.3, 3))
+        out.append((scan, T_true, (T_true @ noise).astype(np.float32)))
+    return out
+
+
+def test_process_input_sequence_matches_reference_sequence(oracle):
+    from norlab_icp_mapper_b200.mapper import Mapper
+    from reference_mapper import RefMapper
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=20)
+    gpu = Mapper(cfg, True, False, True, False, updateCondition=("distance", 1.0), minDistNewPoint=0.15, surfaceNormalKnn=10)
+    ref = RefMapper(cfg, update_distance=1.0, min_dist_new_point=0.15, surface_normal_knn=10)
+    updates = []
+    for i, (scan, T_true, T_est) in enumerate(_scans()):
+        filtered = gpu.applyInputFilters(scan)
+        assert len(filtered) == len(scan)  # everything is within sensorMaxRange (200 m)
+        gpu.processInput(filtered, T_est, 0.1 * i)
+        ref.process_input(scan, T_est, 0.1 * i)
+        er, et = synth.pose_error(gpu.getPose(), ref.pose)
+        assert er <= 1e-4 and et <= 1e-3, (i, er, et)
+        st = gpu.stats()
+        assert bool(st.map_updated) == ref.updated, i
+        assert abs(st.n_local - len(ref.map)) <= max(2, 0.002 * len(ref.map)), (i, st.n_local, len(ref.map))
+        updates.append(ref.updated)
+        if i == 0:
+            pose0, true0 = gpu.getPose().astype(np.float64), T_true
+        else:  # localisation really works: motion relative to the first scan (whose pose defines the map frame)
+            rel_gpu = np.linalg.inv(pose0) @ gpu.getPose().astype(np.float64)
+            rel_true = np.linalg.inv(true0) @ T_true
+            e = synth.pose_error(rel_gpu, rel_true)
+            assert e[0] < 2e-3 and e[1] < 0.03, (i, e)
+    assert updates[0] and any(updates[1:]) and not all(updates[1:])  # the distance condition throttles updates
+    poses, stamps = gpu.getTrajectory()
+    assert len(poses) == 6 and np.allclose(stamps, 0.1 * np.arange(6))
+    feat, nrm = gpu.getMap()
+    assert nrm is not None and len(feat) == gpu.stats().n_global
+    cosang = np.abs(np.einsum("ij,ij->i", nrm[:len(ref.normals)], ref.normals[:len(nrm)]))
+    assert np.median(cosang) > 0.9999
+    gpu.close()
+
+
+def test_is_mapping_false_only_localises(oracle):
+    from norlab_icp_mapper_b200.mapper import Mapper
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=15)
+    m = Mapper(cfg, True, False, True, False, surfaceNormalKnn=10)
+    scans = _scans(4)
+    m.processInput(scans[0][0], scans[0][2], 0.0)
+    n0 = m.stats().n_global
+    m.setIsMapping(False)
+    assert m.getIsMapping() is False
+    for i in (1, 2, 3):
+        m.processInput(scans[i][0], scans[i][2], 0.1 * i)
+        assert m.stats().map_updated == 0 and m.stats().n_global == n0
+    m.close()
+
+
+def test_update_conditions_and_validation():
+    from norlab_icp_mapper_b200.mapper import Mapper
+    from norlab_icp_mapper_b200._lib import B200ICPError
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=10)
+    for bad in (dict(updateCondition=("overlap", 1.5)), dict(updateCondition=("distance", -1.0)), dict(updateCondition=("nope", 1.0)),
+                dict(sensorMaxRange=-5.0)):
+        with pytest.raises(B200ICPError):
+            Mapper(cfg, True, False, True, False, **bad)
+    scans = _scans(3)
+    m = Mapper(cfg, True, False, True, False, updateCondition=("delay", 0.15), surfaceNormalKnn=10)
+    flags = []
+    for i in range(3):
+        m.processInput(scans[i][0], scans[i][2], 0.1 * i)
+        flags.append(m.stats().map_updated)
+    assert flags == [1, 0, 1]  # (t - lastUpdate) > 0.15 s: 0.1 no, 0.2 yes
+    m.close()
+    m = Mapper(cfg, True, False, True, False, updateCondition=("overlap", 0.99), surfaceNormalKnn=10)
+    for i in range(2):
+        m.processInput(scans[i][0], scans[i][2], 0.1 * i)
+    assert m.stats().map_updated == 1 and m.stats().overlap < 0.99  # trimmed ratio 0.85 < 0.99 -> always update
+    m.close()
+
+
+def test_cell_window_follows_reference_state_machine():
+    """sensorMaxRange 30 m and a 400 m drive: the slabs Map::updatePose loads / unloads equal the
+    reference's per-axis code, and the local map is exactly the global points inside the window."""
+    from norlab_icp_mapper_b200.mapper import Mapper
+    from reference_mapper import RefWindow, BUFFER
+    cfg = make_config(dim=3, knn=1, max_dist=2.0, outliers=(("trimmed", 0.85),), minimizer="identity", max_iteration_count=1)
+    m = Mapper(cfg, True, False, False, False, sensorMaxRange=30.0)  # not mapping: the map is what setMap gave
+    rng = np.random.default_rng(3)
+    pts = synth.homog(np.c_[rng.uniform(-250, 250, 200_000), rng.uniform(-250, 250, 200_000), rng.uniform(-30, 30, 200_000)])
+    m.setMap(pts, None)
+    win = RefWindow(30.0)
+    scan = synth.homog(rng.normal(0, 5, (500, 3)))
+    loaded = np.ones(len(pts), bool)
+    cell = np.floor(pts[:, :3] / np.float32(20.0)).astype(int)
+    path = [(-200 + 13.0 * k, -150 + 9.0 * k, 3.0 * np.sin(k)) for k in range(32)] + [(216 - 25.0 * k, 138 - 7.0 * k, -45.0 + 4 * k) for k in range(12)]
+    n_slabs = 0
+    for k, pos in enumerate(path):
+        T = synth.make_T(pos, (0, 0, 5.0 * k)).astype(np.float32)
+        m.processInput(scan, T, 0.1 * k)
+        expect = win.update(np.float32(T[:3, 3]))
+        got = m.windowUpdates()
+        if expect and expect[0] == "unload-all":
+            assert len(got) == 2 and got[0][6] == 0 and tuple(got[1]) == expect[1]
+            loaded[:] = False
+            expect = expect[1:]
+        else:
+            assert [tuple(g) for g in got] == expect, (k, got, expect)
+        for (r0, r1, c0, c1, a0, a1, load) in expect:
+            if load:
+                inside = (cell[:, 0] >= r0) & (cell[:, 0] <= r1) & (cell[:, 1] >= c0) & (cell[:, 1] <= c1) & (cell[:, 2] >= a0) & (cell[:, 2] <= a1)
+                loaded |= inside
+            else:
+                x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+                f = np.float32
+                inside = ((x >= f(r0) * 20) & (x < (f(r1) + 1) * 20) & (y >= f(c0) * 20) & (y < (f(c1) + 1) * 20)
+                          & (z >= f(a0) * 20) & (z < (f(a1) + 1) * 20))
+                loaded &= ~inside
+        n_slabs += len(expect)
+        st = m.stats()
+        assert st.n_local == loaded.sum() and st.n_global == len(pts), (k, st.n_local, loaded.sum())
+    assert n_slabs > 20  # the window really slid
+    m.close()
