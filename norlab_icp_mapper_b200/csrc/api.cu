@@ -34,6 +34,8 @@ struct b200icp_ctx {
     float4* d_q4 = nullptr;
     int64_t cap_out = 0, cap_q4 = 0;
     int* d_scalar_nq = nullptr;
+    unsigned* d_bar_counter = nullptr;
+    int n_sms = 148;
     char* h_pinned = nullptr;  // [0, 1024): state image to upload, [1024, 2048): state read back, [2048..): ints
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_map0 = nullptr, ev_map1 = nullptr;
     std::vector<cudaEvent_t> nn_events;
@@ -333,6 +335,8 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     ok = ok && cudaMallocHost((void**)&ctx->h_pinned, 4096) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_scalar_nq, 64) == cudaSuccess;
     ok = ok && icp_device_setup() == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->d_bar_counter, 64) == cudaSuccess;
+    ctx->n_sms = prop.multiProcessorCount;
     if (!ok) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         b200icp_destroy(ctx);
@@ -366,6 +370,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaFree(ctx->d_out_d2);
     cudaFree(ctx->d_q4);
     cudaFree(ctx->d_scalar_nq);
+    cudaFree(ctx->d_bar_counter);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t ev : ctx->nn_events) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -533,7 +538,20 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     } restore_trace{b, trace_keep};
     IcpState* out_state = reinterpret_cast<IcpState*>(ctx->h_pinned + kStateBytes);
     int issued = 0, nn_timed = 0;
-    while (true) {
+    // k = 1: cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
+    // (Per-kernel profiling and nn_variant bit 2 select the kernel-per-step path below instead.)
+    const bool persistent = p.knn == 1 && !ctx->profiling && !(ctx->cfg.nn_variant & 4);
+    if (persistent) {
+        CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, 1, p.max_r2, b.match_pos, b.match_d2,
+                      /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+        CK(cudaMemsetAsync(ctx->d_bar_counter, 0, sizeof(unsigned), s));
+        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, s));
+        launches += 2;
+        CK(cudaMemcpyAsync(out_state, b.state, kStateBytes, cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->ev_end, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    while (!persistent) {
         const int upto = std::min(hard_cap, issued + chunk);
         for (; issued < upto; ++issued) {
             const bool time_it = ctx->profiling && (size_t)(4 * nn_timed + 3) < ctx->nn_events.size();

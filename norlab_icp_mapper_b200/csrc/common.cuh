@@ -15,7 +15,8 @@ constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
 constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)
 constexpr int kAccBlocks = 128;      // accumulate-kernel grid (one partial each, summed in fixed order)
-constexpr int kMaxAccBlocks = kAccBlocks;
+constexpr int kLoopMaxBlocks = 192;  // persistent loop kernel: one CTA per SM
+constexpr int kMaxAccBlocks = kLoopMaxBlocks;  // partials buffer size
 
 // Uniform grid over a cloud; points sorted by linear cell id (x fastest), so the cells
 // [x0..x1] of one (y, z) row are one contiguous run of `pts`.
@@ -180,6 +181,9 @@ cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const floa
 cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,
                                   cudaStream_t s);
 cudaError_t icp_device_setup();
+// loop.cu: iterations 1.. of a k = 1 registration in one persistent cooperative kernel
+cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
+                            int variant, cudaStream_t s);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
                                   cudaStream_t s, int* launches, cudaEvent_t ev_mid);

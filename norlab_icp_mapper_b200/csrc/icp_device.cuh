@@ -1,0 +1,560 @@
+// icp_device.cuh -- device-side pieces of one ICP iteration shared by icp.cu (one kernel per step)
+// and loop.cu (persistent loop kernel): rigid apply, the one-warp 6x6 solve, AngleAxis / SVD
+// updates, T_iter composition and the transformation checkers.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+struct Mat4 {
+    float m[16];
+};
+
+__device__ __forceinline__ float3 apply_T(const float* __restrict__ T, const float4& r) {
+    float3 o;
+    o.x = __fadd_rn(__fmaf_rn(T[8], r.z, __fmaf_rn(T[4], r.y, __fmul_rn(T[0], r.x))), T[12]);
+    o.y = __fadd_rn(__fmaf_rn(T[9], r.z, __fmaf_rn(T[5], r.y, __fmul_rn(T[1], r.x))), T[13]);
+    o.z = __fadd_rn(__fmaf_rn(T[10], r.z, __fmaf_rn(T[6], r.y, __fmul_rn(T[2], r.x))), T[14]);
+    return o;
+}
+
+// ---- small dense linear algebra on one thread ----------------------------------------------------
+__device__ __noinline__ void jacobi_eig_f64(double* A, int n, double* V, double* w) {
+    for (int i = 0; i < n * n; ++i) V[i] = 0.0;
+    for (int i = 0; i < n; ++i) V[i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) off += A[q * n + p] * A[q * n + p];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = A[q * n + p];
+                if (fabs(apq) < 1e-300) continue;
+                const double app = A[p * n + p], aqq = A[q * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = A[p * n + k], akq = A[q * n + k];
+                    A[p * n + k] = c * akp - s * akq;
+                    A[q * n + k] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = A[k * n + p], aqk = A[k * n + q];
+                    A[k * n + p] = c * apk - s * aqk;
+                    A[k * n + q] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = V[p * n + k], vkq = V[q * n + k];
+                    V[p * n + k] = c * vkp - s * vkq;
+                    V[q * n + k] = s * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < n; ++i) w[i] = A[i * n + i];
+}
+
+// Minimum-norm least-squares fallback (rank-deficient A), kept out of line: it is never on the
+// common path and must not inflate the register allocation of the accumulate kernel.
+__device__ __noinline__ void solve_min_norm(const float* A_in, const float* b, float* x, int n) {
+    double Ad[36], V[36], w[6];
+    for (int i = 0; i < n * n; ++i) Ad[i] = (double)A_in[i];
+    jacobi_eig_f64(Ad, n, V, w);
+    double wmax = 0.0;
+    for (int i = 0; i < n; ++i) wmax = fmax(wmax, fabs(w[i]));
+    double xd[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = 0; e < n; ++e) {
+        if (!(fabs(w[e]) > 1e-6 * wmax)) continue;
+        double proj = 0.0;
+        for (int i = 0; i < n; ++i) proj += V[e * n + i] * (double)b[i];
+        proj /= w[e];
+        for (int i = 0; i < n; ++i) xd[i] += proj * V[e * n + i];
+    }
+    for (int i = 0; i < n; ++i) x[i] = (float)xd[i];
+}
+
+__device__ void quat_from_T(const float* T, float* q /* w x y z */) {
+    float R[3][3];
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) R[r][c] = T[c * 4 + r];
+    float t = R[0][0] + R[1][1] + R[2][2];
+    if (t > 0.f) {
+        t = sqrtf(t + 1.f);
+        q[0] = 0.5f * t;
+        t = 0.5f / t;
+        q[1] = (R[2][1] - R[1][2]) * t;
+        q[2] = (R[0][2] - R[2][0]) * t;
+        q[3] = (R[1][0] - R[0][1]) * t;
+    } else {
+        int i = 0;
+        if (R[1][1] > R[0][0]) i = 1;
+        if (R[2][2] > R[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrtf(R[i][i] - R[j][j] - R[k][k] + 1.f);
+        q[1 + i] = 0.5f * t;
+        t = 0.5f / t;
+        q[0] = (R[k][j] - R[j][k]) * t;
+        q[1 + j] = (R[j][i] + R[i][j]) * t;
+        q[1 + k] = (R[k][i] + R[i][k]) * t;
+    }
+}
+
+__device__ float quat_angular_distance(const float* a, const float* b) {
+    const float bw = b[0], bx = -b[1], by = -b[2], bz = -b[3];
+    const float w = a[0] * bw - a[1] * bx - a[2] * by - a[3] * bz;
+    const float x = a[0] * bx + a[1] * bw + a[2] * bz - a[3] * by;
+    const float y = a[0] * by + a[2] * bw + a[3] * bx - a[1] * bz;
+    const float z = a[0] * bz + a[3] * bw + a[1] * by - a[2] * bx;
+    return 2.f * atan2f(sqrtf(x * x + y * y + z * z), fabsf(w));
+}
+
+// LPM PointToPlaneErrorMinimizer::compute_in_place tail: solve, AngleAxis / Rotation2D.
+// Runs on ONE WARP: lane r < 6 owns row r of [A | b] (entries rounded to fp32 like the reference's
+// float matrices), Gauss-Jordan elimination in fp64 with shuffles, everything in registers.  The
+// pivots of the elimination are the squares of the Cholesky diagonal, so the reference's
+// "is A invertible" decision (LLT succeeds) is the same test; the rank-deficient case falls back
+// to the minimum-norm solution on lane 0.  Result: x[6] identical in every lane.
+__device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/) {
+    const unsigned full = 0xffffffffu;
+    const int r = min(lane, 5);
+    double a[7];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const int lo = min(r, c), hi = max(r, c);
+        a[c] = (double)(float)S[hi * (hi + 1) / 2 + lo];
+    }
+    a[6] = (double)(float)S[21 + r];
+    if (dim == 2) {  // z = 0 embedding: rows/columns 0, 1, 5 are empty -> x = 0 there
+        if (r == 0) a[0] = 1.0;
+        if (r == 1) a[1] = 1.0;
+        if (r == 5) a[5] = 1.0;
+    }
+    double diag = 0.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+        if (c == r) diag = fabs(a[c]);
+    double maxdiag = (lane < 6) ? diag : 0.0;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(full, maxdiag, off));
+    maxdiag = fmax(maxdiag, __shfl_xor_sync(full, maxdiag, 8));  // lanes 0..7 hold the max over lanes 0..5 (6, 7 contribute copies of row 5)
+    maxdiag = __shfl_sync(full, maxdiag, 0);
+    const double thr = 6.0 * 1.1920929e-7 * maxdiag;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        double pk[7];
+#pragma unroll
+        for (int c = k; c < 7; ++c) pk[c] = __shfl_sync(full, a[c], k);
+        const double piv = pk[k];
+        if (!(piv > thr)) ok = false;
+        if (lane != k) {
+            const double f = a[k] / piv;
+#pragma unroll
+            for (int c = k; c < 7; ++c) a[c] -= f * pk[c];
+        }
+    }
+    double arr = 1.0;
+#pragma unroll
+    for (int c = 0; c < 6; ++c)
+        if (c == r) arr = a[c];
+    const double xr = a[6] / arr;  // one division, not one per unrolled candidate
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = (float)__shfl_sync(full, xr, i);
+    bool bad = !ok;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (isnan(x[i])) bad = true;
+    if (bad) {  // rare: rank-deficient normal equations
+        if (lane == 0) {
+            float A6[36], b6[6], xs[6] = {0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < 6; ++c)
+                for (int rr = 0; rr <= c; ++rr) {
+                    const float v = (float)S[c * (c + 1) / 2 + rr];
+                    A6[c * 6 + rr] = v;
+                    A6[rr * 6 + c] = v;
+                }
+            for (int i = 0; i < 6; ++i) b6[i] = (float)S[21 + i];
+            if (dim == 3) {
+                solve_min_norm(A6, b6, xs, 6);
+            } else {
+                float A3[9], b3[3], x3[3];
+                const int id[3] = {2, 3, 4};
+                for (int c = 0; c < 3; ++c) {
+                    for (int rr = 0; rr < 3; ++rr) A3[c * 3 + rr] = A6[id[c] * 6 + id[rr]];
+                    b3[c] = b6[id[c]];
+                }
+                solve_min_norm(A3, b3, x3, 3);
+                xs[2] = x3[0];
+                xs[3] = x3[1];
+                xs[4] = x3[2];
+            }
+            for (int i = 0; i < 6; ++i) s_x[i] = xs[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = s_x[i];
+    }
+}
+
+// x -> dT (R column-major in dT[0..8], t in dT[9..11]); Eigen AngleAxis(|r|, r/|r|) / Rotation2D.
+__device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT) {
+    dT[0] = 1.f; dT[1] = 0.f; dT[2] = 0.f;
+    dT[3] = 0.f; dT[4] = 1.f; dT[5] = 0.f;
+    dT[6] = 0.f; dT[7] = 0.f; dT[8] = 1.f;
+    if (dim == 3) {
+        const float nrm2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+        const float ang = sqrtf(nrm2);
+        float ax0 = x[0], ax1 = x[1], ax2 = x[2];
+        if (nrm2 > 0.f) {
+            ax0 = x[0] / ang;
+            ax1 = x[1] / ang;
+            ax2 = x[2] / ang;
+        }
+        const float s = sinf(ang), c = cosf(ang);
+        const float sx = s * ax0, sy = s * ax1, sz = s * ax2;
+        const float cx = (1.f - c) * ax0, cy = (1.f - c) * ax1, cz = (1.f - c) * ax2;
+        float R[9];  // column-major
+        float tmp = cx * ax1;
+        R[3] = tmp - sz;  // (0,1)
+        R[1] = tmp + sz;  // (1,0)
+        tmp = cx * ax2;
+        R[6] = tmp + sy;  // (0,2)
+        R[2] = tmp - sy;  // (2,0)
+        tmp = cy * ax2;
+        R[7] = tmp - sx;  // (1,2)
+        R[5] = tmp + sx;  // (2,1)
+        R[0] = cx * ax0 + c;
+        R[4] = cy * ax1 + c;
+        R[8] = cz * ax2 + c;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            if (isnan(R[i])) bad = true;
+        if (!bad) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dT[i] = R[i];
+        }
+        dT[9] = x[3];
+        dT[10] = x[4];
+        dT[11] = x[5];
+    } else {  // unknowns of the z = 0 embedding: theta = x[2], t = (x[3], x[4])
+        const float s = sinf(x[2]), c = cosf(x[2]);
+        dT[0] = c;
+        dT[1] = s;
+        dT[3] = -s;
+        dT[4] = c;
+        dT[9] = x[3];
+        dT[10] = x[4];
+        dT[11] = 0.f;
+    }
+}
+
+// LPM PointToPointErrorMinimizer::compute_in_place: weighted centroids, SVD of the cross-covariance.
+__device__ __noinline__ void delta_point_to_point(const double* S, int dim, float* dT) {
+    for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
+    const double sw = S[0];
+    double mp[3], mq[3];
+    for (int d = 0; d < 3; ++d) {
+        mp[d] = S[1 + d] / sw;
+        mq[d] = S[4 + d] / sw;
+    }
+    double M[9];
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) M[c * dim + r] = S[7 + c * 3 + r] - sw * mq[r] * mp[c];
+    double MtM[9], V[9], ev[3];
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+            double a = 0;
+            for (int j = 0; j < dim; ++j) a += M[r * dim + j] * M[c * dim + j];
+            MtM[c * dim + r] = a;
+        }
+    jacobi_eig_f64(MtM, dim, V, ev);
+    int order[3] = {0, 1, 2};
+    for (int a = 0; a < dim; ++a)
+        for (int bb = a + 1; bb < dim; ++bb)
+            if (ev[order[bb]] > ev[order[a]]) {
+                const int tt = order[a];
+                order[a] = order[bb];
+                order[bb] = tt;
+            }
+    double U[9], Vs[9];
+    for (int e = 0; e < dim; ++e)
+        for (int r = 0; r < dim; ++r) Vs[e * dim + r] = V[order[e] * dim + r];
+    for (int e = 0; e < dim; ++e) {
+        double u[3] = {0, 0, 0}, nn = 0;
+        for (int r = 0; r < dim; ++r) {
+            for (int c = 0; c < dim; ++c) u[r] += M[c * dim + r] * Vs[e * dim + c];
+            nn += u[r] * u[r];
+        }
+        nn = sqrt(nn);
+        for (int r = 0; r < dim; ++r) U[e * dim + r] = (nn > 0) ? u[r] / nn : 0.0;
+    }
+    if (dim == 3) {
+        double* u0 = U;
+        double* u1 = U + 3;
+        double* u2 = U + 6;
+        const double cx[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+        const double sgn = (cx[0] * u2[0] + cx[1] * u2[1] + cx[2] * u2[2]) < 0 ? -1.0 : 1.0;
+        for (int r = 0; r < 3; ++r) u2[r] = sgn * cx[r];
+    } else {
+        double* u0 = U;
+        double* u1 = U + 2;
+        const double px[2] = {-u0[1], u0[0]};
+        const double sgn = (px[0] * u1[0] + px[1] * u1[1]) < 0 ? -1.0 : 1.0;
+        u1[0] = sgn * px[0];
+        u1[1] = sgn * px[1];
+    }
+    double R[9];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int r = 0; r < dim; ++r)
+            for (int c = 0; c < dim; ++c) {
+                double a = 0;
+                for (int e = 0; e < dim; ++e) a += U[e * dim + r] * Vs[e * dim + c];
+                R[c * dim + r] = a;
+            }
+        const double det = (dim == 2) ? R[0] * R[3] - R[2] * R[1]
+                                      : R[0] * (R[4] * R[8] - R[7] * R[5]) - R[3] * (R[1] * R[8] - R[7] * R[2]) +
+                                            R[6] * (R[1] * R[5] - R[4] * R[2]);
+        if (det >= 0) break;
+        for (int c = 0; c < dim; ++c) Vs[(dim - 1) * dim + c] = -Vs[(dim - 1) * dim + c];
+    }
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) dT[c * 4 + r] = (float)R[c * dim + r];
+    for (int r = 0; r < dim; ++r) {
+        float a = 0.f;
+        for (int c = 0; c < dim; ++c) a += dT[c * 4 + r] * (float)mp[c];
+        dT[12 + r] = (float)mq[r] - a;
+    }
+}
+
+// Tail of one iteration, run by lane 0: T_iter = dT * T_iter, bookkeeping, then the checkers
+// (LPM TransformationCheckersImpl.cpp: Counter, Differential, Bound).
+__device__ __noinline__ void finish_iteration(const IcpParams& prm, IcpState* st, const float* dT12, double pairs, double wsum,
+                                              float* trace) {
+    const double denom = (double)prm.knn * (double)st->nq;
+    float T[16];
+    {
+        float old[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) old[i] = st->T[i];
+        // T = [R t; 0 1] * old   (same accumulation order as the oracle's 4x4 product)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) acc += dT12[k * 3 + r] * old[c * 4 + k];
+                acc += dT12[9 + r] * old[c * 4 + 3];
+                T[c * 4 + r] = acc;
+            }
+            T[c * 4 + 3] = old[c * 4 + 3];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+    st->pairs = (long long)pairs;
+    st->used_ratio = (float)pairs / (float)denom;
+    st->overlap = (float)wsum / (float)denom;
+    const int it = st->iter;
+    if (trace) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) trace[(size_t)it * 16 + i] = T[i];
+    }
+    st->iter = it + 1;
+
+    bool iterate = true;
+    if (prm.max_iteration_count > 0) {
+        st->counter += 1;
+        if (st->counter >= prm.max_iteration_count) {
+            st->max_iter_reached = 1;
+            st->done = 1;
+            return;
+        }
+    }
+    if (prm.use_differential) {
+        const int smooth = min(max(prm.smooth_length, 1), 7);
+        const int slot = st->dcount % 8;
+        quat_from_T(T, st->dq[slot]);
+        for (int d = 0; d < 3; ++d) st->dt[slot][d] = T[12 + d];
+        st->dcount += 1;
+        float vr = 0.f, vt = 0.f;
+        if (st->dcount > smooth) {
+            for (int j = st->dcount - 1; j >= st->dcount - smooth; --j) {
+                const int a = j % 8, b = (j - 1) % 8;
+                vr += fabsf(quat_angular_distance(st->dq[a], st->dq[b]));
+                const float dx = st->dt[a][0] - st->dt[b][0], dy = st->dt[a][1] - st->dt[b][1], dz = st->dt[a][2] - st->dt[b][2];
+                vt += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+            }
+            vr /= (float)smooth;
+            vt /= (float)smooth;
+            if (vr < prm.min_diff_rot_err && vt < prm.min_diff_trans_err) iterate = false;
+        }
+        if (isnan(vr) || isnan(vt)) {
+            st->status = B200ICP_ERR_NAN;
+            st->done = 1;
+            return;
+        }
+    }
+    if (prm.use_bound) {
+        float qc[4];
+        quat_from_T(T, qc);
+        const float vr = quat_angular_distance(qc, st->bq0);
+        float vt = 0.f;
+        for (int d = 0; d < 3; ++d) vt += (T[12 + d] - st->bt0[d]) * (T[12 + d] - st->bt0[d]);
+        vt = sqrtf(vt);
+        if (isnan(vr) || isnan(vt)) {
+            st->status = B200ICP_ERR_NAN;
+            st->done = 1;
+            return;
+        }
+        if (vr > prm.max_rotation_norm || vt > prm.max_translation_norm) {
+            st->status = B200ICP_ERR_BOUND;
+            st->done = 1;
+            return;
+        }
+    }
+    if (prm.max_iteration_count <= 0 && !prm.use_differential) iterate = false;
+    if (!iterate) {
+        st->done = 1;
+        return;
+    }
+    // the next transformations.apply(stepReading, T_iter) checks orthonormality
+    const float det = T[0] * (T[5] * T[10] - T[9] * T[6]) - T[4] * (T[1] * T[10] - T[9] * T[2]) + T[8] * (T[1] * T[6] - T[5] * T[2]);
+    if (fabsf(1.f - det) > 1e-3f) {
+        st->status = B200ICP_ERR_TRANSFORM;
+        st->done = 1;
+    }
+}
+
+// Everything after the sums, on warp 0 of the last block.
+__device__ __forceinline__ void finish_warp(const IcpParams& prm, IcpState* st, const double* S, int n_sums, float* trace,
+                                            float* s_scratch /* smem[16] */) {
+    const int lane = threadIdx.x & 31;
+    const double pairs = S[n_sums - 1];
+    const double wsum = S[n_sums - 2];
+    if (pairs == 0.0) {  // LPM: ConvergenceError("ErrorMnimizer: no point to minimize")
+        if (lane == 0) {
+            st->status = B200ICP_ERR_CONVERGENCE;
+            st->done = 1;
+        }
+        return;
+    }
+    float dT[12];
+    if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE) {
+        float x[6];
+        solve6_warp(S, prm.dim, lane, x, s_scratch);
+        delta_from_x(x, prm.dim, dT);
+    } else {
+        if (lane == 0) {
+            float d16[16];
+            for (int i = 0; i < 16; ++i) d16[i] = (i % 5 == 0) ? 1.f : 0.f;
+            if (prm.minimizer == B200ICP_MIN_POINT_TO_POINT) delta_point_to_point(S, prm.dim, d16);
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r) s_scratch[c * 3 + r] = d16[c * 4 + r];
+            for (int r = 0; r < 3; ++r) s_scratch[9 + r] = d16[12 + r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 12; ++i) dT[i] = s_scratch[i];
+    }
+    if (lane == 0) finish_iteration(prm, st, dT, pairs, wsum, trace);
+}
+
+// ---- ErrorElements + error minimiser sums --------------------------------------------------------
+// MIN: 0 point-to-plane (29 sums), 1 point-to-point (18 sums), 2 identity (2 sums).
+template <int MIN>
+struct SumLayout;
+template <>
+struct SumLayout<0> {
+    static constexpr int N = 29;
+};
+template <>
+struct SumLayout<1> {
+    static constexpr int N = 18;
+};
+template <>
+struct SumLayout<2> {
+    static constexpr int N = 2;
+};
+
+// Sum 32 per-lane values v[0..31] across the 32 lanes of a warp with 31 shuffles (butterfly
+// transpose): on return every lane holds the warp total of ONE slot, namely slot `lane_slot(lane)`.
+// fp32 pairwise tree over the lanes, deterministic.
+__device__ __forceinline__ float warp_reduce_32slots(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? v[j] : v[j + half];
+            const float keep = upper ? v[j + half] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+// slot held by `lane` after warp_reduce_32slots: bit b of the lane selects the upper half at level b
+__device__ __forceinline__ int lane_slot(int lane) { return lane; }
+
+// One (reading point, neighbour) entry of ErrorElements: outlier weights, then the error-minimiser
+// products.  MIN: 0 point-to-plane (29 sums), 1 point-to-point (18 sums), 2 identity (2 sums).
+template <int MIN>
+__device__ __forceinline__ void accumulate_entry(float* acc, const IcpParams& prm, const float* T, const GridView& g,
+                                                 const float4* __restrict__ nrm, const float4* __restrict__ reading, long long e,
+                                                 int K, int pos, float d, float qlimit) {
+    constexpr int NS = SumLayout<MIN>::N;
+    if (pos < 0) return;
+    if (d == CUDART_INF_F) return;
+    float w = 1.f;
+    for (int f = 0; f < prm.n_outlier; ++f) {
+        const float p = prm.outlier_param[f];
+        bool keep = true;
+        switch (prm.outlier_kind[f]) {
+            case B200ICP_OUTLIER_TRIMMED_DIST: keep = d <= qlimit; break;
+            case B200ICP_OUTLIER_MEDIAN_DIST: keep = d <= p * qlimit; break;
+            case B200ICP_OUTLIER_MAX_DIST: keep = d <= p * p; break;
+            case B200ICP_OUTLIER_MIN_DIST: keep = d >= p * p; break;
+        }
+        w *= keep ? 1.f : 0.f;
+    }
+    if (w == 0.f) return;
+    const long long i = (K == 1) ? e : e / K;
+    const float3 p = apply_T(T, __ldg(reading + i));
+    const float4 q = __ldg(g.pts + pos);
+    if (MIN == 0) {
+        const float4 n = __ldg(nrm + pos);
+        float F[6];
+        F[0] = p.y * n.z - p.z * n.y;
+        F[1] = p.z * n.x - p.x * n.z;
+        F[2] = p.x * n.y - p.y * n.x;
+        F[3] = n.x;
+        F[4] = n.y;
+        F[5] = n.z;
+        const float dot = (p.x - q.x) * n.x + (p.y - q.y) * n.y + (p.z - q.z) * n.z;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const float wf = w * F[c];
+#pragma unroll
+            for (int r = 0; r <= c; ++r) acc[c * (c + 1) / 2 + r] += wf * F[r];
+            acc[21 + c] -= wf * dot;
+        }
+    } else if (MIN == 1) {
+        const float pv[3] = {p.x, p.y, p.z}, qv[3] = {q.x, q.y, q.z};
+        acc[0] += w;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            acc[1 + c] += w * pv[c];
+            acc[4 + c] += w * qv[c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += w * qv[r] * pv[c];
+        }
+    }
+    acc[NS - 2] += w;
+    acc[NS - 1] += 1.f;
+}
+
+}  // namespace
+}  // namespace b200

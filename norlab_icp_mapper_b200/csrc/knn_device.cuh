@@ -1,0 +1,290 @@
+// knn_device.cuh -- device-side building blocks of the exact k-NN search (see knn.cu for the design
+// notes): accumulators, the pruned shell walk (cold search) and the ball search (warm search).
+// Included by knn.cu (stand-alone kernels) and loop.cu (persistent ICP loop kernel).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+namespace {
+
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    if constexpr (G == 32) {
+        return 0xffffffffu;
+    } else {
+        return ((1u << G) - 1u) << (lane & ~(G - 1));
+    }
+}
+
+__device__ __forceinline__ float dist2_exact(float qx, float qy, float qz, const float4& p) {
+    const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ int floor_to_int(float v) {  // v already clamped to a sane range
+    return (int)floorf(v);
+}
+
+// ---- k = 1: per-lane best, shuffle reduction ---------------------------------------------------
+template <int G>
+struct Acc1 {
+    static constexpr bool kPerLaneOutput = false;
+    float d;
+    int pos;
+    __device__ __forceinline__ void init(int) {
+        d = CUDART_INF_F;
+        pos = -1;
+    }
+    __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
+                                         int lig, unsigned, float) {
+        for (uint32_t j = s + lig; j < e; j += G) {
+            const float4 p = __ldg(pts + j);
+            const float dd = dist2_exact(qx, qy, qz, p);
+            if (dd < d || (dd == d && j < (uint32_t)pos)) {  // ties: lowest cell-sorted position wins
+                d = dd;
+                pos = (int)j;
+            }
+        }
+    }
+    // squared radius beyond which nothing can improve the result
+    __device__ __forceinline__ float tau(unsigned gmask, float max_r2) const {
+        float v = d;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
+        return fminf(v, max_r2);
+    }
+    __device__ __forceinline__ void finish(unsigned gmask, int lig, int, float max_r2, float& out_d, int& out_pos) {
+        float bd = d;
+        int bp = pos;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(gmask, bd, o);
+            const int op = __shfl_xor_sync(gmask, bp, o);
+            if (od < bd || (od == bd && (unsigned)op < (unsigned)bp)) {
+                bd = od;
+                bp = op;
+            }
+        }
+        if (!(bd <= max_r2)) {
+            bd = CUDART_INF_F;
+            bp = -1;
+        }
+        out_d = bd;
+        out_pos = bp;
+        (void)lig;
+    }
+};
+
+// ---- k > 1: one sorted list per group, lane j holds the j-th best ------------------------------
+template <int G>
+struct AccK {
+    static constexpr bool kPerLaneOutput = true;
+    float d;      // my entry
+    int pos;
+    float kth;    // group-uniform: current k-th best (inf until k found)
+    int k;
+    __device__ __forceinline__ void init(int k_) {
+        d = CUDART_INF_F;
+        pos = -1;
+        kth = CUDART_INF_F;
+        k = k_;
+    }
+    __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
+                                         int lig, unsigned gmask, float max_r2) {
+        for (uint32_t j0 = s; j0 < e; j0 += G) {
+            const uint32_t j = j0 + lig;
+            float cd = CUDART_INF_F;
+            if (j < e) {
+                const float4 p = __ldg(pts + j);
+                cd = dist2_exact(qx, qy, qz, p);
+            }
+            bool pass = (cd < kth) && (cd <= max_r2);
+            unsigned m = __ballot_sync(gmask, pass) & gmask;
+            while (m) {
+                const int src = __ffs(m) - 1;  // absolute lane
+                const float nd = __shfl_sync(gmask, cd, src);
+                const int np = (int)(j0 + (uint32_t)(src & (G - 1)));
+                // rank of the newcomer = entries <= nd (stable: goes after equal distances)
+                const unsigned le = __ballot_sync(gmask, d <= nd) & gmask;
+                const int r = __popc(le);
+                const float pd = __shfl_up_sync(gmask, d, 1, G);
+                const int pp = __shfl_up_sync(gmask, pos, 1, G);
+                if (lig == r) {
+                    d = nd;
+                    pos = np;
+                } else if (lig > r) {
+                    d = pd;
+                    pos = pp;
+                }
+                if (lig >= k) {
+                    d = CUDART_INF_F;
+                    pos = -1;
+                }
+                kth = __shfl_sync(gmask, d, k - 1, G);
+                m &= m - 1;
+                pass = pass && (cd < kth);
+                m &= __ballot_sync(gmask, pass);
+            }
+        }
+    }
+    __device__ __forceinline__ float tau(unsigned, float max_r2) const { return fminf(kth, max_r2); }
+    __device__ __forceinline__ void finish(unsigned, int, int, float, float& out_d, int& out_pos) {
+        out_d = d;
+        out_pos = pos;
+    }
+};
+
+// One shell of cells with Chebyshev distance in (Rprev, R] around (cx, cy, cz), pruned by tau.
+template <int G, typename Acc>
+__device__ __forceinline__ void visit_shell(const GridView& g, Acc& acc, float qx, float qy, float qz, float ux, float uy,
+                                            float uz, int cx, int cy, int cz, int R, int Rprev, float tau, float slack,
+                                            float max_r2, int lig, unsigned gmask) {
+    const float rt = fminf(sqrtf(tau) * g.inv_h + slack, 3.0e8f);
+    const int ylo = max(max(cy - R, 0), floor_to_int(fmaxf(uy - rt, -1.f)));
+    const int yhi = min(min(cy + R, g.ny - 1), floor_to_int(fminf(uy + rt, (float)g.ny)));
+    const int zlo = max(max(cz - R, 0), floor_to_int(fmaxf(uz - rt, -1.f)));
+    const int zhi = min(min(cz + R, g.nz - 1), floor_to_int(fminf(uz + rt, (float)g.nz)));
+    const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
+    if (wy <= 0 || wz <= 0) return;
+    const int nrows = wy * wz;
+    for (int base = 0; base < nrows; base += G) {
+        const int r = base + lig;
+        uint32_t s1 = 0, e1 = 0, s2 = 0, e2 = 0;
+        if (r < nrows) {
+            const int y = ylo + r % wy, z = zlo + r / wy;
+            const int dy = y - cy, dz = z - cz;
+            float gy = dy == 0 ? 0.f : (dy > 0 ? (float)y - uy : uy - (float)(y + 1));
+            float gz = dz == 0 ? 0.f : (dz > 0 ? (float)z - uz : uz - (float)(z + 1));
+            gy = fmaxf(gy - slack, 0.f) * g.h;
+            gz = fmaxf(gz - slack, 0.f) * g.h;
+            const float gyz2 = gy * gy + gz * gz;
+            if (gyz2 <= tau) {
+                const float rx = fminf(sqrtf(fmaxf(tau - gyz2, 0.f)) * g.inv_h + slack, 3.0e8f);
+                const int xa = max(max(cx - R, 0), floor_to_int(fmaxf(ux - rx, -1.f)));
+                const int xb = min(min(cx + R, g.nx - 1), floor_to_int(fminf(ux + rx, (float)g.nx)));
+                const uint32_t* row = g.cell_start + ((size_t)z * g.ny + y) * (size_t)g.nx;
+                const bool inner = max(abs(dy), abs(dz)) <= Rprev;
+                if (!inner) {
+                    if (xa <= xb) {
+                        s1 = __ldg(row + xa);
+                        e1 = __ldg(row + xb + 1);
+                    }
+                } else {
+                    const int xb1 = min(xb, cx - Rprev - 1);
+                    const int xa2 = max(xa, cx + Rprev + 1);
+                    if (xa <= xb1) {
+                        s1 = __ldg(row + xa);
+                        e1 = __ldg(row + xb1 + 1);
+                    }
+                    if (xa2 <= xb) {
+                        s2 = __ldg(row + xa2);
+                        e2 = __ldg(row + xb + 1);
+                    }
+                }
+            }
+        }
+        unsigned m = __ballot_sync(gmask, (e1 > s1) || (e2 > s2)) & gmask;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t a1 = __shfl_sync(gmask, s1, src), b1 = __shfl_sync(gmask, e1, src);
+            const uint32_t a2 = __shfl_sync(gmask, s2, src), b2 = __shfl_sync(gmask, e2, src);
+            if (b1 > a1) acc.scan(g.pts, a1, b1, qx, qy, qz, lig, gmask, max_r2);
+            if (b2 > a2) acc.scan(g.pts, a2, b2, qx, qy, qz, lig, gmask, max_r2);
+        }
+    }
+}
+
+// Cold search: walk Chebyshev shells around the query's cell until the k-th best is inside the
+// radius the visited block guarantees (or the whole grid has been seen).
+template <int G, typename Acc>
+__device__ __forceinline__ void search_shells(const GridView& g, Acc& acc, float qx, float qy, float qz, float max_r2,
+                                              int variant, int lig, unsigned gmask) {
+    // grid coordinates (same fp32 expression as the builder's cell_coord)
+    const float lim = 1.0e8f;
+    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
+    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
+    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
+    const int cx = floor_to_int(ux), cy = floor_to_int(uy), cz = floor_to_int(uz);
+    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+    // first shell that can touch the grid
+    int R0 = 0;
+    R0 = max(R0, cx < 0 ? -cx : (cx > g.nx - 1 ? cx - (g.nx - 1) : 0));
+    R0 = max(R0, cy < 0 ? -cy : (cy > g.ny - 1 ? cy - (g.ny - 1) : 0));
+    R0 = max(R0, cz < 0 ? -cz : (cz > g.nz - 1 ? cz - (g.nz - 1) : 0));
+    int R = R0, Rprev = R0 - 1;
+    if ((variant & 1) && R0 == 0) R = 1;  // variant bit 0: no own-cell pre-pass
+    const bool finite_q = (fabsf(qx) < 3.0e38f) && (fabsf(qy) < 3.0e38f) && (fabsf(qz) < 3.0e38f);  // false for NaN too
+    if (!finite_q) return;
+    while (true) {
+        const float tau = acc.tau(gmask, max_r2);
+        visit_shell<G, Acc>(g, acc, qx, qy, qz, ux, uy, uz, cx, cy, cz, R, Rprev, tau, slack, max_r2, lig, gmask);
+        // radius guaranteed by the visited block: distance to the nearest face that still has cells behind it
+        float gu = CUDART_INF_F;
+        if (cx - R > 0) gu = fminf(gu, ux - (float)(cx - R));
+        if (cx + R < g.nx - 1) gu = fminf(gu, (float)(cx + R + 1) - ux);
+        if (cy - R > 0) gu = fminf(gu, uy - (float)(cy - R));
+        if (cy + R < g.ny - 1) gu = fminf(gu, (float)(cy + R + 1) - uy);
+        if (cz - R > 0) gu = fminf(gu, uz - (float)(cz - R));
+        if (cz + R < g.nz - 1) gu = fminf(gu, (float)(cz + R + 1) - uz);
+        if (gu == CUDART_INF_F) break;  // whole grid visited
+        const float gm = fmaxf(gu - slack, 0.f) * g.h;
+        if (acc.tau(gmask, max_r2) <= gm * gm) break;
+        Rprev = R;
+        R = R + 1;
+    }
+}
+
+// Warm search (k = 1, ICP iterations >= 1): the previous iteration's match is a real map point, so
+// its distance to the moved query bounds the new nearest distance.  Every cell that intersects the
+// ball of that radius is scanned in ONE pass -- no shell walk, no pre-pass.  Each lane of the group
+// owns whole (y, z) rows of the ball's cover, so the loads of different rows are in flight together
+// and the inner loop has no cross-lane traffic; the result is exact for the same reason the bound
+// is valid, and identical to the cold search thanks to the (dist2, position) tie rule.
+template <int G>
+__device__ __forceinline__ void search_ball(const GridView& g, float qx, float qy, float qz, float tau, float& bd, int& bp,
+                                            int lig) {
+    const float lim = 1.0e8f;
+    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
+    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
+    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
+    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+    const float rt = fminf(sqrtf(tau) * g.inv_h + slack, 3.0e8f);
+    const int ylo = max(0, floor_to_int(fmaxf(uy - rt, -1.f)));
+    const int yhi = min(g.ny - 1, floor_to_int(fminf(uy + rt, (float)g.ny)));
+    const int zlo = max(0, floor_to_int(fmaxf(uz - rt, -1.f)));
+    const int zhi = min(g.nz - 1, floor_to_int(fminf(uz + rt, (float)g.nz)));
+    const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
+    if (wy <= 0 || wz <= 0) return;
+    const int nrows = wy * wz;
+    for (int r = lig; r < nrows; r += G) {
+        const int y = ylo + r % wy, z = zlo + r / wy;
+        // distance from the query to the row's y/z slab (0 when inside it)
+        float gy = fmaxf(fmaxf((float)y - uy, uy - (float)(y + 1)), 0.f);
+        float gz = fmaxf(fmaxf((float)z - uz, uz - (float)(z + 1)), 0.f);
+        gy = fmaxf(gy - slack, 0.f) * g.h;
+        gz = fmaxf(gz - slack, 0.f) * g.h;
+        const float gyz2 = gy * gy + gz * gz;
+        if (gyz2 > tau) continue;
+        const float rx = fminf(sqrtf(fmaxf(tau - gyz2, 0.f)) * g.inv_h + slack, 3.0e8f);
+        const int xa = max(0, floor_to_int(fmaxf(ux - rx, -1.f)));
+        const int xb = min(g.nx - 1, floor_to_int(fminf(ux + rx, (float)g.nx)));
+        if (xa > xb) continue;
+        const uint32_t* row = g.cell_start + ((size_t)z * g.ny + y) * (size_t)g.nx;
+        const uint32_t s = __ldg(row + xa), e = __ldg(row + xb + 1);
+#pragma unroll 4
+        for (uint32_t j = s; j < e; ++j) {
+            const float4 p = __ldg(g.pts + j);
+            const float dd = dist2_exact(qx, qy, qz, p);
+            if (dd < bd || (dd == bd && j < (uint32_t)bp)) {
+                bd = dd;
+                bp = (int)j;
+            }
+        }
+        tau = fminf(tau, bd);
+    }
+}
+
+}  // namespace
+}  // namespace b200

@@ -123,18 +123,23 @@ def test_golden_corrections(golden):
 
 
 def test_run_to_run_determinism(pair3d):
+    """Each execution path is bitwise reproducible; the search strategy (warm ball vs cold shells) does
+    not change the result at all; the persistent-kernel and kernel-per-step paths slice the error
+    sums differently and therefore agree to rounding only."""
     from norlab_icp_mapper_b200.icp import ICP
     cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
-    outs = []
-    for variant in (0, 0, 2):  # 2 = warm-started search disabled: results must not depend on the search strategy
+    outs = {}
+    for variant in (0, 4, 4 | 2):  # 0: persistent loop kernel; 4: kernel per step; 4|2: kernel per step, cold search every iteration
         cfg.nn_variant = variant
         g = ICP(cfg)
         g.set_map(pair3d["map"], pair3d["normals"])
-        outs.append((g(pair3d["reading"]), g(pair3d["reading"])))
+        a, b = g(pair3d["reading"]), g(pair3d["reading"])
         g.close()
-    for a, b in outs:
-        assert np.array_equal(a, b)
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], outs[2][0])
+        assert np.array_equal(a, b), variant
+        outs[variant] = a
+    assert np.array_equal(outs[4], outs[4 | 2])
+    er, et = synth.pose_error(outs[0], outs[4])
+    assert er <= 1e-6 and et <= 1e-5, (er, et)
 
 
 def test_error_behaviour_matches_libpointmatcher(oracle, pair3d):

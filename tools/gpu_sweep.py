@@ -15,7 +15,7 @@ for cpp in cpps:
     for variant in variants:
         cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane",
                           max_iteration_count=30, nn_variant=variant)
-        g = ICP(cfg); g.set_profiling(True); g.set_map(d["map"], d["normals"])
+        g = ICP(cfg); g.set_profiling("--prof" in sys.argv); g.set_map(d["map"], d["normals"])
         ts = []
         for rep in range(4):
             T = g(d["reading"]); tm = g.timing(); ts.append((tm.total_ms, 1e3 * tm.nn_ms_sum / max(tm.nn_launches, 1), 1e3 * tm.select_ms_sum / max(tm.nn_launches, 1), 1e3 * tm.acc_ms_sum / max(tm.nn_launches, 1)))
