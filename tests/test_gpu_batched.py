@@ -1,0 +1,69 @@
+"""Batched mode on the GPU: the product register_fn (libb200icp.so) under register_batch equals the
+oracle pair by pair; with more than one visible GPU the pairs are really sharded over NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from norlab_icp_mapper_b200 import batched, synth
+from norlab_icp_mapper_b200._abi import make_config
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pair(j):
+    return synth.make_pair_3d(n_map=100_000, n_scan=10_000, seed=4000 + j, world_size=(100.0, 100.0), n_boxes=12, scan_radius=45.0)
+
+
+CFG = dict(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=15)
+
+
+def test_batched_single_gpu_matches_oracle(oracle):
+    cfg = make_config(**CFG)
+    fn = batched.gpu_register_fn(cfg, 0)
+    poses, overlaps, iters = batched.register_batch(_pair, 4, fn)
+    fn.close()
+    for j in range(4):
+        p = _pair(j)
+        o = oracle.OracleICP(cfg)
+        o.set_map(p["map"], p["normals"])
+        rc, T, res, _, _ = o.register(p["reading"])
+        er, et = synth.pose_error(poses[j], T)
+        assert rc == 0 and er <= 1e-4 and et <= 1e-3, (j, er, et)
+        assert iters[j] == res.iterations and abs(overlaps[j] - res.overlap) < 2e-3
+
+
+def _worker(rank, world, port, n_pairs, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = make_config(**CFG)
+    fn = batched.gpu_register_fn(cfg, rank)
+    poses, overlaps, iters = batched.register_batch(_pair, n_pairs, fn, rank=rank, world=world, dist=dist, device=f"cuda:{rank}")
+    fn.close()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), poses=poses, overlaps=overlaps, iters=iters)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_batched_multi_gpu_nccl(tmp_path):
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    n_pairs = 6
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, n_pairs, str(tmp_path)), nprocs=world, join=True)
+    cfg = make_config(**CFG)
+    fn = batched.gpu_register_fn(cfg, 0)
+    single = batched.register_batch(_pair, n_pairs, fn)
+    fn.close()
+    for r in range(world):
+        got = np.load(tmp_path / f"rank{r}.npz")
+        assert np.array_equal(got["poses"], single[0]) and np.array_equal(got["iters"], single[2])
