@@ -216,6 +216,40 @@ int32_t b200icp_map_has_normals(const b200icp_ctx* ctx);
 int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, float* normals,
                              int64_t capacity, int64_t* n_out);
 
+/* `probabilityDynamic` descriptor of the map (AddDescriptorDataPointsFilter on a map given by set_map):
+ * per-point values (prob != NULL, one per map point in insertion order) or a constant. */
+int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant);
+int32_t b200icp_map_has_prob(const b200icp_ctx* ctx);
+int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob, int64_t capacity);
+
+/* OctreeMapperModule::inPlaceUpdateMap (MapperModules/OctreeMapperModule.cpp:35-39): map.concatenate(input)
+ * then libpointmatcher's OctreeGridDataPointsFilter{maxPointByNode, maxSizeByNode, samplingMethod}
+ * over the whole local map.  The octree descent is emulated bit for bit (child = p > centre per axis,
+ * centre +- r/2, until 2r <= maxSizeByNode); one survivor per occupied leaf: samplingMethod 0 = the
+ * first point (lowest index), 2 = centroid of features and descriptors.  maxPointByNode must be 1.
+ * input_normals / input_prob may be NULL (concatenate then drops that descriptor from the map). */
+int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                           const float* input_normals, const float* input_prob, float max_size_by_node,
+                           int32_t max_point_by_node, int32_t sampling_method, int64_t* n_after);
+
+/* CutAtDescriptorThresholdDataPointsFilter{descName probabilityDynamic, useLargerThan, threshold}
+ * (examples/config.yaml:29-32) over the local map. */
+int32_t b200icp_map_cut_at_threshold(b200icp_ctx* ctx, float threshold, int32_t use_larger_than, int64_t* n_removed);
+
+/* DynamicPointsMapperModule parameters (MapperModules/DynamicPointsMapperModule.h:33-44). */
+typedef struct b200icp_dynamic_params {
+    float threshold_dynamic, alpha, beta, beam_half_angle, epsilon_a, epsilon_d, sensor_max_range;
+} b200icp_dynamic_params;
+
+/* DynamicPointsMapperModule::inPlaceUpdateMap (MapperModules/DynamicPointsMapperModule.cpp:34-151):
+ * scan and map to the sensor frame (pose^-1), spherical coordinates, 1-NN of every map point within
+ * sensorMaxRange against the scan in (elevation, azimuth) space with radius 2*beamHalfAngle -- on a
+ * 2-D grid index over the scan angles, no kd-tree -- then the Bayesian update of the map's
+ * probabilityDynamic.  Needs map normals and probabilityDynamic and an input probabilityDynamic
+ * (B200ICP_ERR_INVALID_FIELD otherwise, like the reference's InvalidField). */
+int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                                   const float* input_prob, const float* pose, const b200icp_dynamic_params* prm);
+
 /* Device-pointer variant of b200icp_transform (features/normals live on ctx's device). */
 int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows,
                                  float* d_normals, int64_t n, const float* T);

@@ -93,3 +93,12 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
         c.use_bound, c.max_rotation_norm, c.max_translation_norm = 0, 1.0, 1.0
     c.sort_reading, c.use_graph, c.nn_variant = sort_reading, use_graph, nn_variant
     return c
+
+
+class DynamicParams(C.Structure):
+    """DynamicPointsMapperModule parameters with the reference's defaults (DynamicPointsMapperModule.h:33-44)."""
+    _fields_ = [("threshold_dynamic", C.c_float), ("alpha", C.c_float), ("beta", C.c_float), ("beam_half_angle", C.c_float),
+                ("epsilon_a", C.c_float), ("epsilon_d", C.c_float), ("sensor_max_range", C.c_float)]
+
+    def __init__(self, thresholdDynamic=0.6, alpha=0.8, beta=0.99, beamHalfAngle=0.01, epsilonA=0.01, epsilonD=0.01, sensorMaxRange=200.0):
+        super().__init__(thresholdDynamic, alpha, beta, beamHalfAngle, epsilonA, epsilonD, sensorMaxRange)

@@ -911,4 +911,147 @@ int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, 
     return B200ICP_OK;
 }
 
+int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    MapStore& st = ctx->store;
+    if (st.n == 0) return B200ICP_OK;
+    if (prob) {
+        CK(cudaMemcpyAsync(st.prob, prob, (size_t)st.n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        std::vector<float> v((size_t)st.n, constant);
+        CK(cudaMemcpy(st.prob, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    st.has_prob = true;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob, int64_t capacity) {
+    if (!ctx || !prob) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    MapStore& st = ctx->store;
+    if (!st.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map has no probabilityDynamic descriptor");
+    std::vector<float> p((size_t)st.n);
+    std::vector<uint8_t> l((size_t)st.n);
+    CK(cudaMemcpy(p.data(), st.prob, p.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost));
+    int64_t o = 0;
+    for (int64_t i = 0; i < st.n; ++i) {
+        if (!global && !l[i]) continue;
+        if (o >= capacity) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
+        prob[o++] = p[i];
+    }
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_has_prob(const b200icp_ctx* ctx) { return (ctx && ctx->store.has_prob) ? 1 : 0; }
+
+static int32_t upload_input(b200icp_ctx* ctx, const float* input, int rows, int64_t n_in, const float* nrm, const float* prob, float** d_in,
+                            float** d_nrm, float** d_prob) {
+    const int dim = ctx->cfg.dim;
+    const size_t fb = (((size_t)n_in * rows * sizeof(float)) + 255) / 256 * 256;
+    const size_t nb = (((size_t)n_in * dim * sizeof(float)) + 255) / 256 * 256;
+    const size_t pb = (((size_t)n_in * sizeof(float)) + 255) / 256 * 256;
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + pb + 256));
+    char* base = reinterpret_cast<char*>(ctx->d_stage_a);
+    *d_in = reinterpret_cast<float*>(base);
+    *d_nrm = nrm ? reinterpret_cast<float*>(base + fb) : nullptr;
+    *d_prob = prob ? reinterpret_cast<float*>(base + fb + nb) : nullptr;
+    CK(cudaMemcpyAsync(*d_in, input, (size_t)n_in * rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (nrm) CK(cudaMemcpyAsync(*d_nrm, nrm, (size_t)n_in * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (prob) CK(cudaMemcpyAsync(*d_prob, prob, (size_t)n_in * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_normals,
+                           const float* input_prob, float max_size_by_node, int32_t max_point_by_node, int32_t sampling_method,
+                           int64_t* n_after) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+    if (!(max_size_by_node > 0.f)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "maxSizeByNode must be positive");
+    if (max_point_by_node != 1) return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "OctreeGrid: only maxPointByNode = 1 (the LPM default) is implemented");
+    if (sampling_method != 0 && sampling_method != 2)
+        return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "OctreeGrid: samplingMethod 0 (first) and 2 (centroid) are implemented; 1 (random) cannot match a CPU RNG stream, 3 (medoid) is not implemented");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    MapStore& st = ctx->store;
+    if (n_in > 0) {
+        float *d_in, *d_nrm, *d_prob;
+        const int32_t rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &d_in, &d_nrm, &d_prob);
+        if (rc != B200ICP_OK) return rc;
+        CK(store_append_all(st, d_in, feature_rows, dim, d_nrm, d_prob, n_in, s));  // map.concatenate(input)
+    }
+    int64_t removed = 0;
+    CK(store_octree_filter(st, ctx->map, dim, max_size_by_node, sampling_method, &removed, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->index_stale = true;
+    if (n_after) *n_after = st.n_active;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_cut_at_threshold(b200icp_ctx* ctx, float threshold, int32_t use_larger_than, int64_t* n_removed) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (!ctx->store.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "CutAtDescriptorThreshold: descriptor probabilityDynamic not found");
+    CK(cudaSetDevice(ctx->device));
+    int64_t removed = 0;
+    CK(store_cut_prob(ctx->store, ctx->map, ctx->cfg.dim, threshold, use_larger_than, &removed, ctx->stream));
+    if (removed > 0) ctx->index_stale = true;
+    if (n_removed) *n_removed = removed;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_prob,
+                                   const float* pose, const b200icp_dynamic_params* prm) {
+    if (!ctx || !prm || !pose) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+    MapStore& st = ctx->store;
+    if (!input_prob)
+        return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Missing field 'probabilityDynamic' in input point cloud. You can add it with the AddDescriptorDataPointsFilter in your input filters.");
+    if (!st.has_normals)
+        return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Missing field 'normals' in map point cloud. You can add it with the SurfaceNormalDataPointsFilter in your post filters.");
+    if (!st.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Missing field 'probabilityDynamic' in map point cloud.");
+    if (n_in == 0 || st.n_active == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // pose.inverse(): rigid inverse, computed in double
+    float P[16], Tinv[16];
+    embed(pose, dim, P);
+    mat4_identity(Tinv);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) Tinv[c * 4 + r] = P[r * 4 + c];
+    for (int r = 0; r < 3; ++r) {
+        double acc = 0.0;
+        for (int c = 0; c < 3; ++c) acc += (double)P[r * 4 + c] * (double)P[12 + c];
+        Tinv[12 + r] = (float)(-acc);
+    }
+    if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, ctx->map, s));
+    float *d_in, *d_nrm, *d_prob;
+    const int32_t rc = upload_input(ctx, input, feature_rows, n_in, nullptr, nullptr, &d_in, &d_nrm, &d_prob);
+    if (rc != B200ICP_OK) return rc;
+    // scratch: input in the sensor frame (float4) + its angles (2 floats)
+    CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, (size_t)n_in * (sizeof(float4) + 2 * sizeof(float)) + 512));
+    float4* d_in_sensor = reinterpret_cast<float4*>(ctx->d_stage_b);
+    float* d_angles = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->d_stage_b) + (((size_t)n_in * sizeof(float4)) + 255) / 256 * 256);
+    CK(launch_dyn_input(d_in, feature_rows, dim, Tinv, n_in, d_in_sensor, d_angles, s));
+    // Nabo::NNS::create(inputInSensorFrameAngles) + knn(map angles, 1, 0, ALLOW_SELF_MATCH, 2 * beamHalfAngle) -- :75-78
+    CK(grid_build(ctx->aux, d_angles, 2, 2, nullptr, n_in, /*centre=*/false, 0.f, s));
+    const int64_t na = st.n_active;
+    const int32_t eb = ensure_query_buffers(ctx, na, 1);
+    if (eb != B200ICP_OK) return eb;
+    CK(launch_dyn_queries(st, dim, Tinv, prm->sensor_max_range, ctx->d_q4, s));
+    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+    *h_nq = (int)na;
+    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+    const float r = 2.f * prm->beam_half_angle;
+    CK(launch_knn(ctx->aux.view, ctx->d_q4, ctx->d_scalar_nq, (int)na, nullptr, 1, r * r, ctx->d_out_ids, ctx->d_out_d2,
+                  /*want_original_ids=*/1, ctx->cfg.nn_variant, s));
+    DynParams dp{prm->threshold_dynamic, prm->alpha, prm->beta, prm->beam_half_angle, prm->epsilon_a, prm->epsilon_d, prm->sensor_max_range};
+    CK(launch_dyn_update(st, dim, Tinv, dp, d_in_sensor, ctx->d_out_ids, ctx->d_out_d2, s));
+    CK(cudaStreamSynchronize(s));
+    return B200ICP_OK;
+}
+
 }  // extern "C"

@@ -119,6 +119,8 @@ cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, con
                        int64_t n, bool centre, float cell_hint, cudaStream_t s, const uint32_t* d_subset = nullptr);
 void grid_free(GridIndex& g);
 cudaError_t ensure_scratch(GridIndex& g, int64_t n);  // sort scratch for at least n pairs
+cudaError_t cloud_bounds(GridIndex& g, const float* d_feat, int rows, int dim, int64_t n, const uint32_t* d_subset, float* lo3,
+                         float* hi3, cudaStream_t s);
 
 // Stable radix sort of (key, value) pairs on `s` using g's scratch (also used to cell-sort readings).
 cudaError_t sort_pairs(GridIndex& scratch_owner, uint32_t* keys_in, uint32_t* keys_out,
@@ -130,13 +132,23 @@ cudaError_t sort_pairs(GridIndex& scratch_owner, uint32_t* keys_in, uint32_t* ke
 struct MapStore {
     float4* feat = nullptr;      // (x, y, z, 1)
     float* nrm = nullptr;        // dim floats per point
+    float* prob = nullptr;       // `probabilityDynamic` descriptor (DynamicPointsMapperModule), 1 float per point
     uint8_t* loaded = nullptr;
     uint32_t* active = nullptr;  // indices of the loaded points (valid after store_compact_active)
     uint32_t *tmp_u32a = nullptr, *tmp_u32b = nullptr;
     unsigned long long* d_counter = nullptr;
     int64_t n = 0, cap = 0, n_active = 0, cap_tmp = 0;
     bool has_normals = false;
+    bool has_prob = false;
     bool all_loaded = true;
+    // double buffers for compaction
+    float4* feat2 = nullptr;
+    float* nrm2 = nullptr;
+    float* prob2 = nullptr;
+    uint8_t* loaded2 = nullptr;
+    unsigned long long* keys64_a = nullptr;
+    unsigned long long* keys64_b = nullptr;
+    int64_t cap_keys64 = 0;
 };
 void store_free(MapStore& m);
 cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s);
@@ -146,6 +158,24 @@ cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* c
 cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const float* d_in, int rows, int dim,
                                         const float* d_in_nrm, int64_t n_in, const int32_t* d_nn_id, float min_dist,
                                         int64_t* n_kept, uint8_t* d_keep_out, cudaStream_t s);
+// map.concatenate(input): append every input point (descriptors survive only if both clouds have them)
+cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, const float* d_in_nrm, const float* d_in_prob,
+                             int64_t n_in, cudaStream_t s);
+// OctreeGridDataPointsFilter{maxPointByNode 1, maxSizeByNode, samplingMethod 0 (first) | 2 (centroid)} over the loaded points
+cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, int64_t* n_removed,
+                                cudaStream_t s);
+// CutAtDescriptorThresholdDataPointsFilter{probabilityDynamic, useLargerThan, threshold} over the loaded points
+cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s);
+struct DynParams {  // DynamicPointsMapperModule parameters (DynamicPointsMapperModule.h:33-44)
+    float thresholdDynamic, alpha, beta, beamHalfAngle, epsilonA, epsilonD, sensorMaxRange;
+};
+// stage 1: input -> sensor frame (x, y, z, |p|) and (elevation, azimuth); stage 2: angles of the loaded
+// map points within sensorMaxRange as k-NN queries (NaN otherwise); stage 3: the Bayesian update.
+cudaError_t launch_dyn_input(const float* d_in, int rows, int dim, const float* Tinv16, int64_t n_in, float4* d_in_sensor, float* d_in_angles,
+                             cudaStream_t s);
+cudaError_t launch_dyn_queries(const MapStore& m, int dim, const float* Tinv16, float sensor_max_range, float4* d_q4, cudaStream_t s);
+cudaError_t launch_dyn_update(MapStore& m, int dim, const float* Tinv16, const DynParams& prm, const float4* d_in_sensor,
+                              const int32_t* d_ids, const float* d_d2, cudaStream_t s);
 cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d_nn_pos, float4* d_nrm_sorted,
                            float* d_store_nrm, cudaStream_t s);
 

@@ -158,6 +158,24 @@ cudaError_t ensure_scratch(GridIndex& g, int64_t n) {
     return cudaSuccess;
 }
 
+// min / max per axis of a (subset of a) cloud; one streaming pass + a 72-byte read-back
+cudaError_t cloud_bounds(GridIndex& g, const float* d_feat, int rows, int dim, int64_t n, const uint32_t* d_subset, float* lo3, float* hi3,
+                         cudaStream_t s) {
+    cudaError_t e = ensure_scratch(g, 1);
+    if (e != cudaSuccess) return e;
+    unsigned long long h_red[9] = {0, 0, 0, 0xffffffffull, 0xffffffffull, 0xffffffffull, 0, 0, 0};
+    if ((e = cudaMemcpyAsync(g.d_reduce, h_red, sizeof(h_red), cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4 * kSMs);
+    bbox_sum_kernel<<<blocks, 256, 0, s>>>(d_feat, rows, dim, (long long)n, d_subset, g.d_reduce);
+    if ((e = cudaMemcpyAsync(h_red, g.d_reduce, sizeof(h_red), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    for (int d = 0; d < 3; ++d) {
+        lo3[d] = d < dim ? ordered_to_float((unsigned int)h_red[3 + d]) : 0.f;
+        hi3[d] = d < dim ? ordered_to_float((unsigned int)h_red[6 + d]) : 0.f;
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t sort_pairs(GridIndex& g, uint32_t* keys_in, uint32_t* keys_out, uint32_t* vals_in, uint32_t* vals_out,
                        int64_t n, int end_bit, cudaStream_t s) {
     cudaError_t e = ensure_scratch(g, n);

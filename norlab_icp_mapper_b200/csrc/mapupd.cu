@@ -9,6 +9,7 @@
 //        -> 1-NN against the LIVE index (no second kd-tree), keep rule, ordered compaction, append
 //   SurfaceNormalDataPointsFilter{knn} (examples/config.yaml:26-27 via Map.cpp:524)
 //        -> self k-NN on the cell-sorted index + per-point covariance + Jacobi eigenvector
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(256) pd_keep_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) pd_append_kernel(const float* __restrict__ in, int rows, int dim, const float* __restrict__ in_nrm,
                                                         long long n_in, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offs,
                                                         long long base, float4* __restrict__ store, float* __restrict__ store_nrm,
+                                                        const float* __restrict__ in_prob, float* __restrict__ store_prob,
                                                         uint8_t* __restrict__ loaded, uint8_t* __restrict__ keep_out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_in) return;
@@ -58,6 +60,7 @@ __global__ void __launch_bounds__(256) pd_append_kernel(const float* __restrict_
     loaded[dst] = 1;
     if (store_nrm && in_nrm)
         for (int c = 0; c < dim; ++c) store_nrm[dst * dim + c] = in_nrm[i * dim + c];
+    if (store_prob && in_prob) store_prob[dst] = in_prob[i];
 }
 
 // unload: loaded points inside the slab's metric AABB leave the local cloud (Map.cpp:161-174);
@@ -200,7 +203,14 @@ unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 void store_free(MapStore& m) {
     cudaFree(m.feat);
     cudaFree(m.nrm);
+    cudaFree(m.prob);
     cudaFree(m.loaded);
+    cudaFree(m.feat2);
+    cudaFree(m.nrm2);
+    cudaFree(m.prob2);
+    cudaFree(m.loaded2);
+    cudaFree(m.keys64_a);
+    cudaFree(m.keys64_b);
     cudaFree(m.active);
     cudaFree(m.tmp_u32a);
     cudaFree(m.tmp_u32b);
@@ -214,7 +224,19 @@ cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s) {
         const int64_t cap = n + n / 2 + 4096;
         if ((e = regrow(m.feat, m.n, cap, s)) != cudaSuccess) return e;
         if ((e = regrow(m.nrm, m.n * dim, cap * dim, s)) != cudaSuccess) return e;
+        if ((e = regrow(m.prob, m.n, cap, s)) != cudaSuccess) return e;
         if ((e = regrow(m.loaded, m.n, cap, s)) != cudaSuccess) return e;
+        cudaFree(m.feat2);
+        cudaFree(m.nrm2);
+        cudaFree(m.prob2);
+        cudaFree(m.loaded2);
+        m.feat2 = nullptr;
+        m.nrm2 = m.prob2 = nullptr;
+        m.loaded2 = nullptr;
+        if ((e = cudaMalloc((void**)&m.feat2, (size_t)cap * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&m.nrm2, (size_t)cap * dim * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&m.prob2, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&m.loaded2, (size_t)cap)) != cudaSuccess) return e;
         cudaFree(m.active);
         m.active = nullptr;
         if ((e = cudaMalloc((void**)&m.active, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
@@ -262,6 +284,7 @@ cudaError_t store_set(MapStore& m, const float* d_in, int rows, int dim, const f
     m.has_normals = d_normals != nullptr;
     if (d_normals)
         if ((e = cudaMemcpyAsync(m.nrm, d_normals, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    m.has_prob = false;
     m.n = n;
     m.n_active = n;
     m.all_loaded = true;
@@ -318,11 +341,351 @@ cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const f
     // DataPoints::concatenate keeps only descriptors present in both clouds
     const bool keep_normals = m.has_normals && d_in_nrm != nullptr;
     pd_append_kernel<<<blocks_for(n_in), 256, 0, s>>>(d_in, rows, dim, d_in_nrm, (long long)n_in, m.tmp_u32a, m.tmp_u32b, (long long)m.n,
-                                                      m.feat, keep_normals ? m.nrm : nullptr, m.loaded, d_keep_out);
+                                                      m.feat, keep_normals ? m.nrm : nullptr, nullptr, nullptr, m.loaded, d_keep_out);
     m.has_normals = keep_normals;
+    m.has_prob = false;  // the PointDistance entry point carries no probabilityDynamic on the input
     m.n += total;
     m.n_active += total;
     *n_kept = total;
+    return cudaGetLastError();
+}
+
+namespace {
+
+__global__ void __launch_bounds__(256) ones_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ offs, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        a[i] = 1u;
+        offs[i] = (uint32_t)i;
+    }
+}
+
+// Descend the LPM octree (utils/octree: child = (p > centre) per axis, child centre = centre +- r/2,
+// r halves) `depth` levels with the same fp32 operations; the path is the voxel key.
+__global__ void __launch_bounds__(256) octree_key_kernel(const float4* __restrict__ feat, const uint32_t* __restrict__ active, long long n_active,
+                                                         int dim, float cx, float cy, float cz, float radius, int depth,
+                                                         unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n_active) return;
+    const uint32_t i = active ? active[j] : (uint32_t)j;
+    const float4 p = feat[i];
+    float c0 = cx, c1 = cy, c2 = cz, r = radius;
+    unsigned long long key = 0;
+    for (int l = 0; l < depth; ++l) {
+        const float h = r * 0.5f;
+        const unsigned b0 = p.x > c0, b1 = p.y > c1, b2 = (dim == 3) ? (p.z > c2) : 0u;
+        key = (key << 3) | (unsigned long long)(b0 | (b1 << 1) | (b2 << 2));
+        c0 += b0 ? h : -h;
+        c1 += b1 ? h : -h;
+        if (dim == 3) c2 += b2 ? h : -h;
+        r = h;
+    }
+    keys[j] = key;
+    vals[j] = i;
+}
+
+// sorted by key (stable): run heads survive; samplingMethod 2 replaces the head by the run's centroid
+__global__ void __launch_bounds__(256) octree_mark_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                          long long n_active, int dim, int centroid, float4* __restrict__ feat,
+                                                          float* __restrict__ nrm, float* __restrict__ prob, uint32_t* __restrict__ remove) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= n_active) return;
+    const bool head = (j == 0) || (keys[j] != keys[j - 1]);
+    const uint32_t i = vals[j];
+    remove[i] = head ? 0u : 1u;
+    if (head && centroid) {
+        float sx = 0.f, sy = 0.f, sz = 0.f, sp = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
+        int cnt = 0;
+        for (long long t = j; t < n_active && keys[t] == keys[j]; ++t) {
+            const uint32_t q = vals[t];
+            const float4 f = feat[q];
+            sx += f.x;
+            sy += f.y;
+            sz += f.z;
+            if (prob) sp += prob[q];
+            if (nrm) {
+                n0 += nrm[(long long)q * dim + 0];
+                n1 += nrm[(long long)q * dim + 1];
+                if (dim == 3) n2 += nrm[(long long)q * dim + 2];
+            }
+            ++cnt;
+        }
+        const float inv = 1.f / (float)cnt;
+        feat[i] = make_float4(sx * inv, sy * inv, sz * inv, 1.f);
+        if (prob) prob[i] = sp * inv;
+        if (nrm) {
+            nrm[(long long)i * dim + 0] = n0 * inv;
+            nrm[(long long)i * dim + 1] = n1 * inv;
+            if (dim == 3) nrm[(long long)i * dim + 2] = n2 * inv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cut_prob_kernel(const float* __restrict__ prob, const uint8_t* __restrict__ loaded, long long n, float thr,
+                                                       int larger, uint32_t* __restrict__ remove) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = prob[i];
+    remove[i] = (loaded[i] && (larger ? (v > thr) : (v < thr))) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) invert_flags_kernel(uint32_t* __restrict__ f, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) f[i] = f[i] ? 0u : 1u;
+}
+
+__global__ void __launch_bounds__(256) compact_store_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offs, long long n, int dim,
+                                                            const float4* __restrict__ feat, const float* __restrict__ nrm, const float* __restrict__ prob,
+                                                            const uint8_t* __restrict__ loaded, float4* __restrict__ feat2, float* __restrict__ nrm2,
+                                                            float* __restrict__ prob2, uint8_t* __restrict__ loaded2) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const long long d = offs[i];
+    feat2[d] = feat[i];
+    loaded2[d] = loaded[i];
+    if (nrm)
+        for (int c = 0; c < dim; ++c) nrm2[d * dim + c] = nrm[i * dim + c];
+    if (prob) prob2[d] = prob[i];
+}
+
+// remove the store points whose flag in tmp_u32a is 1 (order of the survivors preserved)
+cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64_t* n_removed, cudaStream_t s) {
+    cudaError_t e;
+    const int64_t n = m.n;
+    invert_flags_kernel<<<blocks_for(n), 256, 0, s>>>(m.tmp_u32a, (long long)n);  // now: keep flags
+    if ((e = cudaMemsetAsync(m.tmp_u32a + n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
+    if ((e = exclusive_sum(scratch, m.tmp_u32a, m.tmp_u32b, n + 1, s)) != cudaSuccess) return e;
+    uint32_t kept = 0;
+    if ((e = cudaMemcpyAsync(&kept, m.tmp_u32b + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    compact_store_kernel<<<blocks_for(n), 256, 0, s>>>(m.tmp_u32a, m.tmp_u32b, (long long)n, dim, m.feat, m.has_normals ? m.nrm : nullptr,
+                                                       m.has_prob ? m.prob : nullptr, m.loaded, m.feat2, m.nrm2, m.prob2, m.loaded2);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    std::swap(m.feat, m.feat2);
+    std::swap(m.nrm, m.nrm2);
+    std::swap(m.prob, m.prob2);
+    std::swap(m.loaded, m.loaded2);
+    *n_removed = n - (int64_t)kept;
+    m.n = kept;
+    m.n_active -= *n_removed;  // only loaded points are ever flagged
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, const float* d_in_nrm, const float* d_in_prob,
+                             int64_t n_in, cudaStream_t s) {
+    cudaError_t e;
+    if (n_in == 0) return cudaSuccess;
+    const bool first = m.n == 0;
+    if ((e = store_reserve(m, dim, m.n + n_in, s)) != cudaSuccess) return e;
+    if ((e = ensure_tmp(m, n_in + 1)) != cudaSuccess) return e;
+    // DataPoints::concatenate keeps only descriptors present in both clouds; a first cloud brings its own
+    const bool keep_n = first ? (d_in_nrm != nullptr) : (m.has_normals && d_in_nrm != nullptr);
+    const bool keep_p = first ? (d_in_prob != nullptr) : (m.has_prob && d_in_prob != nullptr);
+    ones_kernel<<<blocks_for(n_in), 256, 0, s>>>(m.tmp_u32a, m.tmp_u32b, (long long)n_in);
+    pd_append_kernel<<<blocks_for(n_in), 256, 0, s>>>(d_in, rows, dim, d_in_nrm, (long long)n_in, m.tmp_u32a, m.tmp_u32b, (long long)m.n,
+                                                      m.feat, keep_n ? m.nrm : nullptr, d_in_prob, keep_p ? m.prob : nullptr, m.loaded,
+                                                      nullptr);
+    m.has_normals = keep_n;
+    m.has_prob = keep_p;
+    m.n += n_in;
+    m.n_active += n_in;
+    return cudaGetLastError();
+}
+
+cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, int64_t* n_removed,
+                                cudaStream_t s) {
+    cudaError_t e;
+    *n_removed = 0;
+    if (m.n_active == 0) return cudaSuccess;
+    if (!m.all_loaded || m.n_active != m.n)
+        if ((e = store_compact_active(m, scratch, s)) != cudaSuccess) return e;
+    const uint32_t* active = m.all_loaded ? nullptr : m.active;
+    const int64_t na = m.n_active;
+    // bounding box of the filtered cloud (LPM Octree::build): centre = min + (max - min) / 2, radius = max extent / 2
+    if ((e = ensure_scratch(scratch, na)) != cudaSuccess) return e;
+    float lo[3], hi[3];
+    if ((e = cloud_bounds(scratch, reinterpret_cast<const float*>(m.feat), 4, dim, na, active, lo, hi, s)) != cudaSuccess) return e;
+    float radii[3] = {0, 0, 0}, centre[3] = {0, 0, 0}, radius = 0.f;
+    for (int d = 0; d < dim; ++d) {
+        radii[d] = hi[d] - lo[d];
+        centre[d] = lo[d] + radii[d] * 0.5f;
+        radius = d == 0 ? radii[0] : (radius < radii[d] ? radii[d] : radius);
+    }
+    radius *= 0.5f;
+    int depth = 0;
+    for (float r = radius; (double)r * 2.0 > (double)max_size_by_node && depth < 22; r *= 0.5f) ++depth;
+    if (depth > 21) return cudaErrorInvalidValue;  // key would not fit 63 bits
+    if (na > m.cap_keys64) {
+        cudaFree(m.keys64_a);
+        cudaFree(m.keys64_b);
+        m.keys64_a = m.keys64_b = nullptr;
+        m.cap_keys64 = 0;
+        const int64_t cap = na + na / 2 + 4096;
+        if ((e = cudaMalloc((void**)&m.keys64_a, (size_t)cap * 8)) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&m.keys64_b, (size_t)cap * 8)) != cudaSuccess) return e;
+        m.cap_keys64 = cap;
+    }
+    if ((e = ensure_tmp(m, std::max<int64_t>(m.n, na) + 1)) != cudaSuccess) return e;
+    octree_key_kernel<<<blocks_for(na), 256, 0, s>>>(m.feat, active, (long long)na, dim, centre[0], centre[1], centre[2], radius, depth,
+                                                     m.keys64_a, scratch.vals_in);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, m.keys64_a, m.keys64_b, scratch.vals_in, scratch.vals_out, (int)na, 0, std::max(1, 3 * depth));
+    if (need > scratch.cub_tmp_bytes) {
+        cudaFree(scratch.cub_tmp);
+        scratch.cub_tmp = nullptr;
+        scratch.cub_tmp_bytes = 0;
+        if ((e = cudaMalloc(&scratch.cub_tmp, need + 256)) != cudaSuccess) return e;
+        scratch.cub_tmp_bytes = need + 256;
+    }
+    size_t bytes = scratch.cub_tmp_bytes;
+    if ((e = cub::DeviceRadixSort::SortPairs(scratch.cub_tmp, bytes, m.keys64_a, m.keys64_b, scratch.vals_in, scratch.vals_out, (int)na, 0,
+                                             std::max(1, 3 * depth), s)) != cudaSuccess)
+        return e;
+    if ((e = cudaMemsetAsync(m.tmp_u32a, 0, (size_t)(m.n + 1) * sizeof(uint32_t), s)) != cudaSuccess) return e;
+    octree_mark_kernel<<<blocks_for(na), 256, 0, s>>>(m.keys64_b, scratch.vals_out, (long long)na, dim, sampling_method == 2 ? 1 : 0, m.feat,
+                                                      m.has_normals ? m.nrm : nullptr, m.has_prob ? m.prob : nullptr, m.tmp_u32a);
+    return store_remove_flagged(m, scratch, dim, n_removed, s);
+}
+
+cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s) {
+    cudaError_t e;
+    *n_removed = 0;
+    if (m.n == 0 || !m.has_prob) return cudaSuccess;
+    if ((e = ensure_tmp(m, m.n + 1)) != cudaSuccess) return e;
+    cut_prob_kernel<<<blocks_for(m.n), 256, 0, s>>>(m.prob, m.loaded, (long long)m.n, threshold, use_larger_than, m.tmp_u32a);
+    return store_remove_flagged(m, scratch, dim, n_removed, s);
+}
+
+namespace {
+
+struct M16 {
+    float m[16];
+};
+
+__device__ __forceinline__ float3 xform(const M16& T, float x, float y, float z) {
+    float3 o;
+    o.x = __fadd_rn(__fmaf_rn(T.m[8], z, __fmaf_rn(T.m[4], y, __fmul_rn(T.m[0], x))), T.m[12]);
+    o.y = __fadd_rn(__fmaf_rn(T.m[9], z, __fmaf_rn(T.m[5], y, __fmul_rn(T.m[1], x))), T.m[13]);
+    o.z = __fadd_rn(__fmaf_rn(T.m[10], z, __fmaf_rn(T.m[6], y, __fmul_rn(T.m[2], x))), T.m[14]);
+    return o;
+}
+
+// convertToSphericalCoordinates (DynamicPointsMapperModule.cpp:156-172)
+__device__ __forceinline__ void spherical(float3 p, int dim, float& r, float& el, float& az) {
+    r = (dim == 3) ? sqrtf(p.x * p.x + p.y * p.y + p.z * p.z) : sqrtf(p.x * p.x + p.y * p.y);
+    el = (dim == 3) ? asinf(p.z / r) : 0.f;
+    az = atan2f(p.y, p.x);
+}
+
+__global__ void __launch_bounds__(256) dyn_input_kernel(const float* __restrict__ in, int rows, int dim, M16 Tinv, long long n_in,
+                                                        float4* __restrict__ in_sensor, float* __restrict__ angles) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_in) return;
+    const float3 p = xform(Tinv, in[i * rows + 0], in[i * rows + 1], dim == 3 ? in[i * rows + 2] : 0.f);
+    float r, el, az;
+    spherical(p, dim, r, el, az);
+    in_sensor[i] = make_float4(p.x, p.y, p.z, r);
+    angles[i * 2 + 0] = el;
+    angles[i * 2 + 1] = az;
+}
+
+__global__ void __launch_bounds__(256) dyn_query_kernel(const float4* __restrict__ feat, const uint32_t* __restrict__ active, long long na, int dim,
+                                                        M16 Tinv, float range, float4* __restrict__ q4) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= na) return;
+    const float4 f = feat[active ? active[j] : (uint32_t)j];
+    const float3 p = xform(Tinv, f.x, f.y, f.z);
+    float r, el, az;
+    spherical(p, dim, r, el, az);
+    const float nanv = __int_as_float(0x7fc00000);
+    q4[j] = (r < range) ? make_float4(el, az, 0.f, 1.f) : make_float4(nanv, nanv, nanv, 1.f);  // NaN -> no neighbours
+}
+
+// DynamicPointsMapperModule.cpp:86-150, same promotion to double where the reference writes `1.`
+__global__ void __launch_bounds__(256) dyn_update_kernel(const float4* __restrict__ feat, const uint32_t* __restrict__ active, long long na, int dim,
+                                                         M16 Tinv, DynParams prm, const float* __restrict__ nrm, float* __restrict__ prob,
+                                                         const float4* __restrict__ in_sensor, const int32_t* __restrict__ ids,
+                                                         const float* __restrict__ d2) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= na) return;
+    const float dist = d2[j];
+    const int id = ids[j];
+    if (id < 0 || dist == CUDART_INF_F) return;
+    const uint32_t i = active ? active[j] : (uint32_t)j;
+    const float eps = 0.0001f;
+    const float4 f = feat[i];
+    const float3 lp = xform(Tinv, f.x, f.y, f.z);
+    const float4 ip = in_sensor[id];
+    const float lpNorm = (dim == 3) ? sqrtf(lp.x * lp.x + lp.y * lp.y + lp.z * lp.z) : sqrtf(lp.x * lp.x + lp.y * lp.y);
+    const float inNorm = ip.w;
+    const float ddx = ip.x - lp.x, ddy = ip.y - lp.y, ddz = ip.z - lp.z;
+    const float delta = (dim == 3) ? sqrtf(ddx * ddx + ddy * ddy + ddz * ddz) : sqrtf(ddx * ddx + ddy * ddy);
+    const float d_max = prm.epsilonA * inNorm;
+    // normal in the sensor frame (rotation part of Tinv)
+    const float n0 = nrm[(long long)i * dim + 0], n1 = nrm[(long long)i * dim + 1], n2 = dim == 3 ? nrm[(long long)i * dim + 2] : 0.f;
+    const float nsx = __fmaf_rn(Tinv.m[8], n2, __fmaf_rn(Tinv.m[4], n1, __fmul_rn(Tinv.m[0], n0)));
+    const float nsy = __fmaf_rn(Tinv.m[9], n2, __fmaf_rn(Tinv.m[5], n1, __fmul_rn(Tinv.m[1], n0)));
+    const float nsz = __fmaf_rn(Tinv.m[10], n2, __fmaf_rn(Tinv.m[6], n1, __fmul_rn(Tinv.m[2], n0)));
+    const float dotn = nsx * (lp.x / lpNorm) + nsy * (lp.y / lpNorm) + nsz * (lp.z / lpNorm);
+    const float w_v = (float)((double)eps + (1. - (double)eps) * fabs((double)dotn));
+    const float w_d1 = (float)((double)eps + (1. - (double)eps) * (1. - (double)sqrtf(dist) / (double)(2 * prm.beamHalfAngle)));
+    const float offset = delta - prm.epsilonD;
+    float w_d2 = 1.f;
+    if (delta < prm.epsilonD || lpNorm > inNorm) {
+        w_d2 = eps;
+    } else if (offset < d_max) {
+        w_d2 = eps + (1 - eps) * offset / d_max;
+    }
+    float w_p2 = eps;
+    if (delta < prm.epsilonD) {
+        w_p2 = 1;
+    } else if (offset < d_max) {
+        w_p2 = (float)((double)eps + (1. - (double)eps) * (1. - (double)(offset / d_max)));
+    }
+    if ((inNorm + prm.epsilonD + d_max) >= lpNorm) {
+        const float lastDyn = prob[i];
+        const float c1 = (1 - (w_v * w_d1));
+        const float c2 = w_v * w_d1;
+        float probDynamic, probStatic;
+        if (lastDyn < prm.thresholdDynamic) {
+            probDynamic = c1 * lastDyn + c2 * w_d2 * ((1 - prm.alpha) * (1 - lastDyn) + prm.beta * lastDyn);
+            probStatic = c1 * (1 - lastDyn) + c2 * w_p2 * (prm.alpha * (1 - lastDyn) + (1 - prm.beta) * lastDyn);
+        } else {
+            probDynamic = 1 - eps;
+            probStatic = eps;
+        }
+        prob[i] = probDynamic / (probDynamic + probStatic);
+    }
+}
+
+M16 to_m16(const float* T) {
+    M16 m;
+    memcpy(m.m, T, sizeof(m.m));
+    return m;
+}
+
+}  // namespace
+
+cudaError_t launch_dyn_input(const float* d_in, int rows, int dim, const float* Tinv16, int64_t n_in, float4* d_in_sensor, float* d_in_angles,
+                             cudaStream_t s) {
+    if (n_in <= 0) return cudaSuccess;
+    dyn_input_kernel<<<blocks_for(n_in), 256, 0, s>>>(d_in, rows, dim, to_m16(Tinv16), (long long)n_in, d_in_sensor, d_in_angles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dyn_queries(const MapStore& m, int dim, const float* Tinv16, float sensor_max_range, float4* d_q4, cudaStream_t s) {
+    if (m.n_active <= 0) return cudaSuccess;
+    dyn_query_kernel<<<blocks_for(m.n_active), 256, 0, s>>>(m.feat, m.all_loaded ? nullptr : m.active, (long long)m.n_active, dim, to_m16(Tinv16),
+                                                            sensor_max_range, d_q4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dyn_update(MapStore& m, int dim, const float* Tinv16, const DynParams& prm, const float4* d_in_sensor, const int32_t* d_ids,
+                              const float* d_d2, cudaStream_t s) {
+    if (m.n_active <= 0) return cudaSuccess;
+    dyn_update_kernel<<<blocks_for(m.n_active), 256, 0, s>>>(m.feat, m.all_loaded ? nullptr : m.active, (long long)m.n_active, dim, to_m16(Tinv16),
+                                                             prm, m.nrm, m.prob, d_in_sensor, d_ids, d_d2);
     return cudaGetLastError();
 }
 

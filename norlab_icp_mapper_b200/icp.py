@@ -192,6 +192,51 @@ class ICP:
                                                      n.value, C.byref(n)))
         return feat[:n.value], (nrm[:n.value] if has_n else None)
 
+    def map_set_prob(self, prob=None, constant=0.6):
+        ptr = None
+        if prob is not None:
+            prob = np.ascontiguousarray(prob, np.float32)
+            ptr = prob.ctypes.data
+        self._check(self._L.b200icp_map_set_prob(self._h, ptr, constant))
+
+    def map_download_prob(self, global_map=False):
+        n = self.map_counts()[1 if global_map else 0]
+        out = np.zeros(n, np.float32)
+        if n:
+            self._check(self._L.b200icp_map_download_prob(self._h, int(global_map), out.ctypes.data, n))
+        return out
+
+    def map_octree(self, input_features, max_size_by_node, sampling_method=0, input_normals=None, input_prob=None, max_point_by_node=1):
+        """OctreeMapperModule::inPlaceUpdateMap.  Returns the local map size afterwards."""
+        inp = _cloud(input_features, self.n)
+        nptr = pptr = None
+        if input_normals is not None:
+            input_normals = _cloud(input_normals, self.dim)
+            nptr = input_normals.ctypes.data
+        if input_prob is not None:
+            input_prob = np.ascontiguousarray(input_prob, np.float32)
+            pptr = input_prob.ctypes.data
+        n_after = C.c_int64()
+        self._check(self._L.b200icp_map_octree(self._h, inp.ctypes.data, self.n, len(inp), nptr, pptr, max_size_by_node,
+                                               max_point_by_node, sampling_method, C.byref(n_after)))
+        return n_after.value
+
+    def map_cut_at_threshold(self, threshold, use_larger_than=True):
+        n = C.c_int64()
+        self._check(self._L.b200icp_map_cut_at_threshold(self._h, threshold, int(use_larger_than), C.byref(n)))
+        return n.value
+
+    def map_dynamic_points(self, input_features, input_prob, pose, params=None):
+        """DynamicPointsMapperModule::inPlaceUpdateMap (input in the map frame)."""
+        inp = _cloud(input_features, self.n)
+        pptr = None
+        if input_prob is not None:
+            input_prob = np.ascontiguousarray(input_prob, np.float32)
+            pptr = input_prob.ctypes.data
+        T = _T_to_colmajor(pose, self.n)
+        params = params or _abi.DynamicParams()
+        self._check(self._L.b200icp_map_dynamic_points(self._h, inp.ctypes.data, self.n, len(inp), pptr, T.ctypes.data, C.byref(params)))
+
     # -- instrumentation ---------------------------------------------------------------------------
     def stream(self):
         return self._L.b200icp_stream(self._h)
