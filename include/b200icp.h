@@ -115,6 +115,20 @@ typedef struct b200icp_timing {
     int32_t reserved[1];
 } b200icp_timing;
 
+/* One entry of the YAML `input:` chain (libpointmatcher DataPointsFilters used on this path,
+ * examples/config.yaml:1-23, Mapper.cpp:27-31). */
+typedef enum b200icp_filter_kind {
+    B200ICP_FILTER_BOUNDING_BOX = 1,   /* BoundingBoxDataPointsFilter{xMin..zMax, removeInside}             */
+    B200ICP_FILTER_DISTANCE_LIMIT = 2  /* DistanceLimitDataPointsFilter{dim (-1 radial), dist, removeInside} */
+} b200icp_filter_kind;
+typedef struct b200icp_filter {
+    int32_t kind;
+    float lo[3], hi[3];    /* bounding box: a point is inside when every coordinate is in [lo, hi]         */
+    int32_t dim;           /* distance limit: -1 = radial, else the axis                                   */
+    float dist;
+    int32_t remove_inside; /* 1: drop the points inside the box / closer than dist; 0: drop the others      */
+} b200icp_filter;
+
 typedef struct b200icp_ctx b200icp_ctx;
 
 int32_t b200icp_abi_version(void);
@@ -222,6 +236,11 @@ int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant
 int32_t b200icp_map_has_prob(const b200icp_ctx* ctx);
 int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob, int64_t capacity);
 
+/* map.concatenate(input) / `DataPoints outputMap(input)` of the modules' createMap: append every input
+ * point; a descriptor survives only if both clouds carry it (an empty map takes the input's). */
+int32_t b200icp_map_append(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                           const float* input_normals, const float* input_prob, int64_t* n_added);
+
 /* OctreeMapperModule::inPlaceUpdateMap (MapperModules/OctreeMapperModule.cpp:35-39): map.concatenate(input)
  * then libpointmatcher's OctreeGridDataPointsFilter{maxPointByNode, maxSizeByNode, samplingMethod}
  * over the whole local map.  The octree descent is emulated bit for bit (child = p > centre per axis,
@@ -249,6 +268,12 @@ typedef struct b200icp_dynamic_params {
  * (B200ICP_ERR_INVALID_FIELD otherwise, like the reference's InvalidField). */
 int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
                                    const float* input_prob, const float* pose, const b200icp_dynamic_params* prm);
+
+/* DataPointsFilters::apply(cloud) for the `input:` chain (Mapper::applyInputFilters, Mapper.cpp:187-191):
+ * one predicate kernel evaluating the whole chain per point + ordered stream compaction on the device.
+ * In place on the host buffer; *n is updated to the surviving count. */
+int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_rows, int64_t* n,
+                             const b200icp_filter* chain, int32_t n_filters);
 
 /* Device-pointer variant of b200icp_transform (features/normals live on ctx's device). */
 int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows,

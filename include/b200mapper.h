@@ -24,6 +24,21 @@ typedef struct b200mapper_config {
     float min_dist_new_point;  /* PointDistanceMapperModule{minDistNewPoint}; < 0: the default 0.15  */
     int32_t surface_normal_knn;/* post: SurfaceNormalDataPointsFilter{knn}; 0 = absent               */
     int32_t is_3d, is_online, is_mapping;
+    /* mapper.mapperModule list, applied in this order when enabled (examples/config.yaml:38-52):
+     * DynamicPointsMapperModule, then OctreeMapperModule or PointDistanceMapperModule */
+    int32_t use_dynamic_points;
+    b200icp_dynamic_params dynamic_points;
+    int32_t use_octree;            /* replaces the PointDistance module */
+    float octree_max_size_by_node;
+    int32_t octree_sampling_method;
+    /* post: CutAtDescriptorThresholdDataPointsFilter{probabilityDynamic} after SurfaceNormal */
+    int32_t use_cut_at_threshold;
+    float cut_threshold;
+    /* input: chain (after Mapper's own radius filter) + AddDescriptor{probabilityDynamic} */
+    int32_t n_input_filters;
+    b200icp_filter input_filters[6];
+    int32_t add_probability_dynamic;
+    float probability_dynamic_value;
     int32_t reserved[4];
 } b200mapper_config;
 

@@ -911,6 +911,31 @@ int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, 
     return B200ICP_OK;
 }
 
+int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_rows, int64_t* n, const b200icp_filter* chain,
+                             int32_t n_filters) {
+    if (!ctx || !n) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || *n < 0 || (*n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
+    if (n_filters < 0 || n_filters > 8 || (n_filters > 0 && !chain)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad filter chain (at most 8 entries)");
+    for (int i = 0; i < n_filters; ++i)
+        if (chain[i].kind != B200ICP_FILTER_BOUNDING_BOX && chain[i].kind != B200ICP_FILTER_DISTANCE_LIMIT)
+            return fail(ctx, B200ICP_ERR_INVALID_ARG, "unknown input filter");
+    if (*n == 0 || n_filters == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t fb = (((size_t)*n * feature_rows * sizeof(float)) + 255) / 256 * 256;
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, 2 * fb + 256));
+    float* d_in = ctx->d_stage_a;
+    float* d_out = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->d_stage_a) + fb);
+    CK(cudaMemcpyAsync(d_in, features, (size_t)*n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, s));
+    int64_t kept = 0;
+    CK(filter_cloud_device(ctx->store, ctx->map, d_in, feature_rows, dim, *n, chain, n_filters, d_out, &kept, s));
+    if (kept > 0) CK(cudaMemcpyAsync(features, d_out, (size_t)kept * feature_rows * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *n = kept;
+    return B200ICP_OK;
+}
+
 int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -961,6 +986,24 @@ static int32_t upload_input(b200icp_ctx* ctx, const float* input, int rows, int6
     CK(cudaMemcpyAsync(*d_in, input, (size_t)n_in * rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     if (nrm) CK(cudaMemcpyAsync(*d_nrm, nrm, (size_t)n_in * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     if (prob) CK(cudaMemcpyAsync(*d_prob, prob, (size_t)n_in * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_append(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_normals,
+                           const float* input_prob, int64_t* n_added) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+    if (n_added) *n_added = 0;
+    if (n_in == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    float *d_in, *d_nrm, *d_prob;
+    const int32_t rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &d_in, &d_nrm, &d_prob);
+    if (rc != B200ICP_OK) return rc;
+    CK(store_append_all(ctx->store, d_in, feature_rows, dim, d_nrm, d_prob, n_in, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->index_stale = true;
+    if (n_added) *n_added = n_in;
     return B200ICP_OK;
 }
 

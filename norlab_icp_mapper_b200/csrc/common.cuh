@@ -166,6 +166,9 @@ cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float 
                                 cudaStream_t s);
 // CutAtDescriptorThresholdDataPointsFilter{probabilityDynamic, useLargerThan, threshold} over the loaded points
 cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s);
+// input filter chain on a device cloud (rows floats per point): keep flags -> ordered compaction
+cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, float* d_feat, int rows, int dim, int64_t n, const b200icp_filter* chain,
+                                int n_filters, float* d_out, int64_t* n_out, cudaStream_t s);
 struct DynParams {  // DynamicPointsMapperModule parameters (DynamicPointsMapperModule.h:33-44)
     float thresholdDynamic, alpha, beta, beamHalfAngle, epsilonA, epsilonD, sensorMaxRange;
 };

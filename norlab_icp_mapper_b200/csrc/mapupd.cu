@@ -472,6 +472,66 @@ cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64
 
 }  // namespace
 
+namespace {
+struct FilterChain {
+    b200icp_filter f[8];
+    int n;
+};
+__global__ void __launch_bounds__(256) filter_flags_kernel(const float* __restrict__ feat, int rows, int dim, long long n, FilterChain ch,
+                                                           uint32_t* __restrict__ keep) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = feat[i * rows + 0], y = feat[i * rows + 1], z = dim == 3 ? feat[i * rows + 2] : 0.f;
+    bool k = true;
+    for (int t = 0; t < ch.n && k; ++t) {
+        const b200icp_filter& f = ch.f[t];
+        if (f.kind == B200ICP_FILTER_BOUNDING_BOX) {
+            bool inside = x >= f.lo[0] && x <= f.hi[0] && y >= f.lo[1] && y <= f.hi[1];
+            if (dim == 3) inside = inside && z >= f.lo[2] && z <= f.hi[2];
+            k = f.remove_inside ? !inside : inside;
+        } else {
+            float v, lim;
+            if (f.dim == -1) {
+                v = dim == 3 ? sqrtf(x * x + y * y + z * z) : sqrtf(x * x + y * y);
+                lim = fabsf(f.dist);
+            } else {
+                v = f.dim == 0 ? x : (f.dim == 1 ? y : z);
+                lim = f.dist;
+            }
+            k = f.remove_inside ? (v > lim) : (v < lim);
+        }
+    }
+    keep[i] = k ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) filter_compact_kernel(const float* __restrict__ in, int rows, long long n, const uint32_t* __restrict__ keep,
+                                                             const uint32_t* __restrict__ offs, float* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    for (int c = 0; c < rows; ++c) out[(long long)offs[i] * rows + c] = in[i * rows + c];
+}
+}  // namespace
+
+cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, float* d_feat, int rows, int dim, int64_t n, const b200icp_filter* chain,
+                                int n_filters, float* d_out, int64_t* n_out, cudaStream_t s) {
+    cudaError_t e;
+    *n_out = 0;
+    if (n == 0) return cudaSuccess;
+    if (n_filters > 8) return cudaErrorInvalidValue;
+    if ((e = ensure_tmp(tmp, n + 1)) != cudaSuccess) return e;
+    FilterChain ch;
+    ch.n = n_filters;
+    for (int i = 0; i < n_filters; ++i) ch.f[i] = chain[i];
+    filter_flags_kernel<<<blocks_for(n), 256, 0, s>>>(d_feat, rows, dim, (long long)n, ch, tmp.tmp_u32a);
+    if ((e = cudaMemsetAsync(tmp.tmp_u32a + n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
+    if ((e = exclusive_sum(scratch, tmp.tmp_u32a, tmp.tmp_u32b, n + 1, s)) != cudaSuccess) return e;
+    filter_compact_kernel<<<blocks_for(n), 256, 0, s>>>(d_feat, rows, (long long)n, tmp.tmp_u32a, tmp.tmp_u32b, d_out);
+    uint32_t total = 0;
+    if ((e = cudaMemcpyAsync(&total, tmp.tmp_u32b + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    *n_out = total;
+    return cudaGetLastError();
+}
+
 cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, const float* d_in_nrm, const float* d_in_prob,
                              int64_t n_in, cudaStream_t s) {
     cudaError_t e;

@@ -14,8 +14,11 @@ struct DataPoints {
     int dim = 3;                  // euclidean dimension (2 or 3); features has dim + 1 rows
     std::vector<float> features;  // (dim + 1) x N, column-major
     std::vector<float> normals;   // dim x N, column-major, or empty (descriptor absent)
+    std::vector<float> probabilityDynamic;  // 1 x N or empty (descriptor absent)
     int64_t getNbPoints() const { return features.empty() ? 0 : (int64_t)features.size() / (dim + 1); }
-    bool descriptorExists(const std::string& name) const { return name == "normals" && !normals.empty(); }
+    bool descriptorExists(const std::string& name) const {
+        return (name == "normals" && !normals.empty()) || (name == "probabilityDynamic" && !probabilityDynamic.empty());
+    }
 };
 
 // (dim + 1) x (dim + 1), column-major -- PM::TransformationParameters

@@ -114,6 +114,12 @@ void Map::updateLocalPointCloud(const DataPoints& input, const TransformationPar
         ICPSequence::check(icp.context(), b200icp_map_commit(icp.context()));
         if (postFilters.surfaceNormalKnn > 0)
             ICPSequence::check(icp.context(), b200icp_map_surface_normals(icp.context(), postFilters.surfaceNormalKnn));
+        if (postFilters.cutAtThreshold) {
+            int64_t removed = 0;
+            ICPSequence::check(icp.context(), b200icp_map_cut_at_threshold(icp.context(), postFilters.cutThreshold,
+                                                                           postFilters.cutUseLargerThan ? 1 : 0, &removed));
+            if (removed > 0) ICPSequence::check(icp.context(), b200icp_map_commit(icp.context()));
+        }
     }
     localPointCloudEmpty.store(localPointCloud.getNbPoints() == 0);
     newLocalPointCloudAvailable = true;

@@ -14,6 +14,9 @@ namespace norlab_icp_mapper_b200 {
 
 struct PostFilters {           // the `post:` chain entries this path implements (examples/config.yaml:25-32)
     int surfaceNormalKnn = 0;  // SurfaceNormalDataPointsFilter{knn}; 0 = absent
+    bool cutAtThreshold = false;       // CutAtDescriptorThresholdDataPointsFilter{descName probabilityDynamic, ...}
+    bool cutUseLargerThan = true;
+    float cutThreshold = 0.65f;
 };
 
 class Map {

@@ -5,13 +5,18 @@
 
 namespace norlab_icp_mapper_b200 {
 
-void Mapper::fillRegistrar() {  // Mapper.cpp:9-13 (Octree / DynamicPoints modules: DESIGN.md section 7, next)
+void Mapper::fillRegistrar() {  // Mapper.cpp:9-13
     registrar.add("PointDistanceMapperModule", [](const Parameters& p) { return std::make_shared<PointDistanceMapperModule>(p); });
+    registrar.add("OctreeMapperModule", [](const Parameters& p) { return std::make_shared<OctreeMapperModule>(p); });
+    registrar.add("DynamicPointsMapperModule", [](const Parameters& p) { return std::make_shared<DynamicPointsMapperModule>(p); });
 }
 
 Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMapping_, bool /*saveMapCellsOnHardDrive*/, int device)
     : icp(config.icp, device),
       mapPostFilters(config.post),
+      inputFilters(config.inputFilters),
+      addProbabilityDynamic(config.addProbabilityDynamic),
+      probabilityDynamicValue(config.probabilityDynamicValue),
       mapUpdateCondition(config.mapUpdateCondition),
       is3D(is3D_),
       isOnline(isOnline_),
@@ -44,29 +49,22 @@ Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMa
 }
 
 // Mapper.cpp:187-191: radiusFilter = DistanceLimitDataPointsFilter{dim -1, dist sensorMaxRange,
-// removeInside 0} (built at Mapper.cpp:27-31) keeps ||p|| < dist; then the YAML `input:` chain.
-// O(N) predicate + compaction on the caller's host buffer before the single upload; the device-side
-// chain is the first "next" row of SURVEY 8f.
+// removeInside 0} (built at Mapper.cpp:27-31), then the YAML `input:` chain -- one predicate kernel +
+// ordered compaction on the device (b200icp_filter_cloud); AddDescriptor attaches a constant.
 void Mapper::applyInputFilters(DataPoints& in) {
-    const int rows = in.dim + 1;
-    const float r = std::fabs(map.getSensorMaxRange());
-    const int64_t n = in.getNbPoints();
-    int64_t o = 0;
-    const bool has_n = !in.normals.empty();
-    for (int64_t i = 0; i < n; ++i) {
-        float d2 = 0.f;
-        for (int c = 0; c < in.dim; ++c) d2 += in.features[i * rows + c] * in.features[i * rows + c];
-        if (std::sqrt(d2) < r) {
-            if (o != i) {
-                for (int c = 0; c < rows; ++c) in.features[o * rows + c] = in.features[i * rows + c];
-                if (has_n)
-                    for (int c = 0; c < in.dim; ++c) in.normals[o * in.dim + c] = in.normals[i * in.dim + c];
-            }
-            ++o;
-        }
-    }
-    in.features.resize((size_t)o * rows);
-    if (has_n) in.normals.resize((size_t)o * in.dim);
+    std::vector<b200icp_filter> chain;
+    b200icp_filter radius{};
+    radius.kind = B200ICP_FILTER_DISTANCE_LIMIT;
+    radius.dim = -1;
+    radius.dist = map.getSensorMaxRange();
+    radius.remove_inside = 0;
+    chain.push_back(radius);
+    chain.insert(chain.end(), inputFilters.begin(), inputFilters.end());
+    if (!in.normals.empty()) throw std::runtime_error("applyInputFilters: descriptors on the raw input are not carried through the device chain");
+    int64_t n = in.getNbPoints();
+    ICPSequence::check(icp.context(), b200icp_filter_cloud(icp.context(), in.features.data(), in.dim + 1, &n, chain.data(), (int32_t)chain.size()));
+    in.features.resize((size_t)n * (in.dim + 1));
+    if (addProbabilityDynamic) in.probabilityDynamic.assign((size_t)n, probabilityDynamicValue);
 }
 
 // Mapper.cpp:194-238

@@ -17,6 +17,9 @@ namespace norlab_icp_mapper_b200 {
 struct MapperConfig {
     b200icp_config icp;                                      // YAML `icp:` (Mapper.cpp:70-78)
     PostFilters post;                                        // YAML `post:` (Mapper.cpp:90-98)
+    std::vector<b200icp_filter> inputFilters;                // YAML `input:` (Mapper.cpp:80-88): BoundingBox / DistanceLimit entries
+    bool addProbabilityDynamic = false;                      // ... AddDescriptorDataPointsFilter{probabilityDynamic, 1, [value]}
+    float probabilityDynamicValue = 0.6f;
     std::string mapUpdateCondition = "distance";            // mapper.updateCondition.type (Mapper.cpp:117-146)
     float mapUpdateValue = 1.0f;                             // ... .value (DEFAULT_MAP_UPDATE_DISTANCE, Mapper.h:20)
     float sensorMaxRange = 200.0f;                           // mapper.sensorMaxRange (Mapper.cpp:152-160)
@@ -26,6 +29,9 @@ struct MapperConfig {
 class Mapper {
     ICPSequence icp;
     PostFilters mapPostFilters;
+    std::vector<b200icp_filter> inputFilters;
+    bool addProbabilityDynamic;
+    float probabilityDynamicValue;
     std::string mapUpdateCondition;
     float mapUpdateOverlap = 0.f, mapUpdateDelay = 0.f, mapUpdateDistance = 1.0f;
     bool is3D, isOnline;
@@ -47,6 +53,9 @@ class Mapper {
    public:
     Mapper(const MapperConfig& config, bool is3D, bool isOnline, bool isMapping, bool saveMapCellsOnHardDrive, int device = 0);
     void applyInputFilters(DataPoints& inputInSensorFrame);
+    void attachInputDescriptors(DataPoints& input) const {  // AddDescriptorDataPointsFilter of the `input:` chain
+        if (addProbabilityDynamic && input.probabilityDynamic.empty()) input.probabilityDynamic.assign((size_t)input.getNbPoints(), probabilityDynamicValue);
+    }
     void processInput(const DataPoints& filteredInputInSensorFrame, const TransformationParameters& estimatedPose, double timeStamp);
     DataPoints getMap();
     void setMap(const DataPoints& newMap);

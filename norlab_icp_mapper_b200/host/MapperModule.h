@@ -44,6 +44,10 @@ class DeviceMap {
         if (n > 0)
             ICPSequence::check(icp.context(), b200icp_map_download(icp.context(), global, out.features.data(),
                                                                    has_n ? out.normals.data() : nullptr, n, &n));
+        if (n > 0 && b200icp_map_has_prob(icp.context())) {
+            out.probabilityDynamic.resize((size_t)n);
+            ICPSequence::check(icp.context(), b200icp_map_download_prob(icp.context(), global, out.probabilityDynamic.data(), n));
+        }
         return out;
     }
 };
@@ -103,6 +107,74 @@ class PointDistanceMapperModule : public MapperModule {
         ICPSequence::check(map.context(), b200icp_map_insert_point_distance(map.context(), input.features.data(), input.dim + 1,
                                                                             input.getNbPoints(), input.normals.empty() ? nullptr : input.normals.data(),
                                                                             minDistNewPoint, &added, nullptr));
+    }
+};
+
+// OctreeMapperModule (MapperModules/OctreeMapperModule.{h,cpp}): map.concatenate(input) then
+// libpointmatcher's OctreeGridDataPointsFilter over the whole map, parameters passed through.
+class OctreeMapperModule : public MapperModule {
+    bool buildParallel = true;
+    int maxPointByNode = 1;
+    float maxSizeByNode = 0.f;
+    int samplingMethod = 0;
+
+   public:
+    explicit OctreeMapperModule(const Parameters& params) {
+        for (const auto& kv : params) {
+            if (kv.first == "buildParallel") buildParallel = std::stoi(kv.second) != 0;
+            else if (kv.first == "maxPointByNode") maxPointByNode = std::stoi(kv.second);
+            else if (kv.first == "maxSizeByNode") maxSizeByNode = std::stof(kv.second);
+            else if (kv.first == "samplingMethod") samplingMethod = std::stoi(kv.second);
+            else throw InvalidParameter("OctreeMapperModule: unknown parameter " + kv.first);
+        }
+        if (maxPointByNode < 1) throw InvalidParameter("OctreeMapperModule: maxPointByNode must be >= 1");
+        if (!(maxSizeByNode > 0.f)) throw InvalidParameter("OctreeMapperModule: maxSizeByNode must be > 0 on this implementation");
+        (void)buildParallel;  // the device build is always parallel
+    }
+    void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
+        inPlaceUpdateMap(input, map, pose);  // inPlaceUpdateMap(emptyMap, input): concatenate into an empty map, then filter
+    }
+    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters&) override {
+        int64_t n_after = 0;
+        ICPSequence::check(map.context(),
+                           b200icp_map_octree(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
+                                              input.normals.empty() ? nullptr : input.normals.data(),
+                                              input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(), maxSizeByNode,
+                                              maxPointByNode, samplingMethod, &n_after));
+    }
+};
+
+// DynamicPointsMapperModule (MapperModules/DynamicPointsMapperModule.{h,cpp}): Bayesian update of the
+// map's probabilityDynamic from the new scan; parameters and defaults of the reference (:33-44).
+class DynamicPointsMapperModule : public MapperModule {
+    b200icp_dynamic_params prm{0.6f, 0.8f, 0.99f, 0.01f, 0.01f, 0.01f, 200.f};
+
+   public:
+    explicit DynamicPointsMapperModule(const Parameters& params) {
+        for (const auto& kv : params) {
+            const float v = std::stof(kv.second);
+            if (kv.first == "thresholdDynamic") prm.threshold_dynamic = v;
+            else if (kv.first == "alpha") prm.alpha = v;
+            else if (kv.first == "beta") prm.beta = v;
+            else if (kv.first == "beamHalfAngle") prm.beam_half_angle = v;
+            else if (kv.first == "epsilonA") prm.epsilon_a = v;
+            else if (kv.first == "epsilonD") prm.epsilon_d = v;
+            else if (kv.first == "sensorMaxRange") prm.sensor_max_range = v;
+            else throw InvalidParameter("DynamicPointsMapperModule: unknown parameter " + kv.first);
+        }
+    }
+    void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters&) override {
+        // createMap copies the input (DynamicPointsMapperModule.cpp:16-25): an unfiltered insert
+        int64_t added = 0;
+        if (map.getNbPoints() != 0) throw std::runtime_error("DynamicPointsMapperModule::createMap on a non-empty map");
+        ICPSequence::check(map.context(), b200icp_map_append(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
+                                                             input.normals.empty() ? nullptr : input.normals.data(),
+                                                             input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(), &added));
+    }
+    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
+        ICPSequence::check(map.context(), b200icp_map_dynamic_points(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
+                                                                     input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(),
+                                                                     pose.m, &prm));
     }
 };
 

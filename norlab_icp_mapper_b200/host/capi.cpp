@@ -74,8 +74,24 @@ int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapp
         mc.mapUpdateCondition = cfg->update_condition == 0 ? "distance" : (cfg->update_condition == 1 ? "delay" : (cfg->update_condition == 2 ? "overlap" : "?"));
         mc.mapUpdateValue = cfg->update_value;
         mc.sensorMaxRange = cfg->sensor_max_range;
-        if (cfg->min_dist_new_point >= 0.f)
+        if (cfg->use_dynamic_points) {
+            const b200icp_dynamic_params& d = cfg->dynamic_points;
+            mc.mapperModules.push_back({"DynamicPointsMapperModule",
+                                        Parameters{{"thresholdDynamic", std::to_string(d.threshold_dynamic)}, {"alpha", std::to_string(d.alpha)},
+                                                   {"beta", std::to_string(d.beta)}, {"beamHalfAngle", std::to_string(d.beam_half_angle)},
+                                                   {"epsilonA", std::to_string(d.epsilon_a)}, {"epsilonD", std::to_string(d.epsilon_d)},
+                                                   {"sensorMaxRange", std::to_string(d.sensor_max_range)}}});
+        }
+        if (cfg->use_octree)
+            mc.mapperModules.push_back({"OctreeMapperModule", Parameters{{"buildParallel", "1"}, {"maxSizeByNode", std::to_string(cfg->octree_max_size_by_node)},
+                                                                         {"samplingMethod", std::to_string(cfg->octree_sampling_method)}}});
+        else if (cfg->min_dist_new_point >= 0.f)
             mc.mapperModules.push_back({"PointDistanceMapperModule", Parameters{{"minDistNewPoint", std::to_string(cfg->min_dist_new_point)}}});
+        mc.post.cutAtThreshold = cfg->use_cut_at_threshold != 0;
+        mc.post.cutThreshold = cfg->cut_threshold;
+        for (int i = 0; i < cfg->n_input_filters && i < 6; ++i) mc.inputFilters.push_back(cfg->input_filters[i]);
+        mc.addProbabilityDynamic = cfg->add_probability_dynamic != 0;
+        mc.probabilityDynamicValue = cfg->probability_dynamic_value;
         m->dim = cfg->is_3d ? 3 : 2;
         m->mapper.reset(new Mapper(mc, cfg->is_3d != 0, cfg->is_online != 0, cfg->is_mapping != 0, false, device));
     });
@@ -104,7 +120,9 @@ int32_t b200mapper_process_input(b200mapper* m, const float* features, int32_t f
                                  double time_stamp_seconds) {
     if (!m || (n > 0 && !features) || feature_rows != m->dim + 1) return B200ICP_ERR_INVALID_ARG;
     return guarded(m, [&] {
-        m->mapper->processInput(wrap(features, feature_rows, n, nullptr), wrapT(estimated_pose, m->dim + 1), time_stamp_seconds);
+        DataPoints in = wrap(features, feature_rows, n, nullptr);
+        m->mapper->attachInputDescriptors(in);  // what AddDescriptor in applyInputFilters attached
+        m->mapper->processInput(in, wrapT(estimated_pose, m->dim + 1), time_stamp_seconds);
     });
 }
 

@@ -19,10 +19,37 @@ SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "
            "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates"]
 
 
+class InputFilter(C.Structure):
+    """b200icp_filter: kind 1 = BoundingBox{lo, hi, removeInside}, 2 = DistanceLimit{dim, dist, removeInside}."""
+    _fields_ = [("kind", C.c_int32), ("lo", C.c_float * 3), ("hi", C.c_float * 3), ("dim", C.c_int32), ("dist", C.c_float),
+                ("remove_inside", C.c_int32)]
+
+
+def bounding_box(lo, hi, removeInside=True):
+    f = InputFilter()
+    f.kind = 1
+    for i in range(3):
+        f.lo[i], f.hi[i] = lo[i], hi[i]
+    f.remove_inside = int(removeInside)
+    return f
+
+
+def distance_limit(dist, dim=-1, removeInside=False):
+    f = InputFilter()
+    f.kind, f.dim, f.dist, f.remove_inside = 2, dim, dist, int(removeInside)
+    return f
+
+
 class MapperConfig(C.Structure):
     _fields_ = [("icp", _abi.Config), ("update_condition", C.c_int32), ("update_value", C.c_float),
                 ("sensor_max_range", C.c_float), ("min_dist_new_point", C.c_float), ("surface_normal_knn", C.c_int32),
-                ("is_3d", C.c_int32), ("is_online", C.c_int32), ("is_mapping", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("is_3d", C.c_int32), ("is_online", C.c_int32), ("is_mapping", C.c_int32),
+                ("use_dynamic_points", C.c_int32), ("dynamic_points", _abi.DynamicParams),
+                ("use_octree", C.c_int32), ("octree_max_size_by_node", C.c_float), ("octree_sampling_method", C.c_int32),
+                ("use_cut_at_threshold", C.c_int32), ("cut_threshold", C.c_float),
+                ("n_input_filters", C.c_int32), ("input_filters", InputFilter * 6),
+                ("add_probability_dynamic", C.c_int32), ("probability_dynamic_value", C.c_float),
+                ("reserved", C.c_int32 * 4)]
 
 
 class MapperStats(C.Structure):
@@ -68,7 +95,10 @@ class Mapper:
     CONDITIONS = {"distance": 0, "delay": 1, "overlap": 2}
 
     def __init__(self, icp_config, is3D=True, isOnline=False, isMapping=True, saveMapCellsOnHardDrive=False, *,
-                 updateCondition=("distance", 1.0), sensorMaxRange=200.0, minDistNewPoint=0.15, surfaceNormalKnn=0, device=0):
+                 updateCondition=("distance", 1.0), sensorMaxRange=200.0, minDistNewPoint=0.15, surfaceNormalKnn=0,
+                 dynamicPoints=None, octree=None, cutAtThreshold=None, inputFilters=(), addProbabilityDynamic=None, device=0):
+        """dynamicPoints: _abi.DynamicParams or None; octree: (maxSizeByNode, samplingMethod) or None (then PointDistance);
+        cutAtThreshold: threshold or None; inputFilters: InputFilter list; addProbabilityDynamic: value or None."""
         self._L = load()
         cfg = MapperConfig()
         cfg.icp = icp_config
@@ -78,6 +108,17 @@ class Mapper:
         cfg.min_dist_new_point = minDistNewPoint
         cfg.surface_normal_knn = surfaceNormalKnn
         cfg.is_3d, cfg.is_online, cfg.is_mapping = int(is3D), int(isOnline), int(isMapping)
+        if dynamicPoints is not None:
+            cfg.use_dynamic_points, cfg.dynamic_points = 1, dynamicPoints
+        if octree is not None:
+            cfg.use_octree, cfg.octree_max_size_by_node, cfg.octree_sampling_method = 1, octree[0], octree[1]
+        if cutAtThreshold is not None:
+            cfg.use_cut_at_threshold, cfg.cut_threshold = 1, cutAtThreshold
+        cfg.n_input_filters = len(inputFilters)
+        for i, f in enumerate(inputFilters):
+            cfg.input_filters[i] = f
+        if addProbabilityDynamic is not None:
+            cfg.add_probability_dynamic, cfg.probability_dynamic_value = 1, addProbabilityDynamic
         self.dim = 3 if is3D else 2
         self.n = self.dim + 1
         h = C.c_void_p()

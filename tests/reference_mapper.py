@@ -6,7 +6,12 @@ import math
 
 import numpy as np
 
+import os
+import sys
+
 import oracle_binding as ob
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 
 CELL, BUFFER = 20.0, 2
 
@@ -145,3 +150,58 @@ class RefWindow:
                     ups.append((i[0] - B, s[0] + B, i[1] - B, s[1] + B, n + B - nb + 1, n + B, 1))
                 s[2] = n
         return ups
+
+
+class RefExampleMapper:
+    """The pipeline of the reference's bundled configuration (examples/config.yaml) restated on the
+    oracle pieces: input BoundingBox x2 + AddDescriptor{probabilityDynamic 0.6}; mapper modules
+    DynamicPoints then Octree; post SurfaceNormal{knn 10} + CutAtDescriptorThreshold{0.65}; delay
+    update condition; Identity error minimiser.  samplingMethod is 0 (first) instead of the shipped 1
+    (random), which no two implementations can reproduce."""
+
+    def __init__(self, max_size=0.15, knn=10, cut=0.65, delay=0.05, dyn=None, boxes=()):
+        import modules_oracle as mo
+        self.mo, self.max_size, self.knn, self.cut, self.delay = mo, max_size, knn, cut, delay
+        self.dyn = dyn or {}
+        self.boxes = boxes
+        self.map = self.normals = self.prob = None
+        self.last_t = 0.0
+        self.updated = False
+
+    def apply_input_filters(self, scan, sensor_max_range=200.0):
+        keep = self.mo.distance_limit_keep(scan, sensor_max_range)
+        for lo, hi in self.boxes:
+            keep &= self.mo.bounding_box_keep(scan, lo, hi, True)
+        return np.ascontiguousarray(scan[keep])
+
+    def _post(self, pose):
+        inv = np.linalg.inv(pose.astype(np.float32)).astype(np.float32)
+        rc, in_sensor, _ = ob.transform(self.map, inv)
+        rc2, nrm = ob.surface_normals(in_sensor, self.knn)
+        rc3, back, nrm_back = ob.transform(in_sensor, pose, nrm)
+        self.map, self.normals = back, nrm_back
+        keep = self.mo.cut_at_descriptor_threshold(self.prob, self.cut, True)
+        self.map, self.normals, self.prob = self.map[keep], self.normals[keep], self.prob[keep]
+
+    def _octree(self, inp, inp_prob):
+        allp = np.r_[self.map, inp] if self.map is not None else inp
+        allq = np.r_[self.prob, inp_prob] if self.prob is not None else inp_prob
+        order, feat, desc = self.mo.octree_grid_filter(allp, self.max_size, 0, descriptors=allq[:, None])
+        self.map, self.prob, self.normals = np.ascontiguousarray(feat), desc[:, 0].copy(), None
+
+    def process_input(self, scan, T_est, stamp):
+        T_est = np.asarray(T_est, np.float32)
+        rc, inp, _ = ob.transform(scan, T_est)
+        inp_prob = np.full(len(inp), 0.6, np.float32)
+        self.updated = False
+        if self.map is None:
+            self.map, self.prob = inp.copy(), inp_prob.copy()  # DynamicPoints::createMap copies the input
+            self._octree(inp, inp_prob)                         # Octree::inPlaceUpdateMap concatenates it again
+            self._post(T_est)
+            self.last_t, self.updated = stamp, True
+        elif (stamp - self.last_t) > self.delay:                # Identity minimiser: correction = I, pose = T_est
+            self.prob, _ = self.mo.dynamic_points_update(inp, self.map, self.normals, self.prob, T_est, **self.dyn)
+            self._octree(inp, inp_prob)
+            self._post(T_est)
+            self.last_t, self.updated = stamp, True
+        self.pose = T_est

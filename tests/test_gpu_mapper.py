@@ -137,3 +137,55 @@ def test_cell_window_follows_reference_state_machine():
         assert st.n_local == loaded.sum() and st.n_global == len(pts), (k, st.n_local, loaded.sum())
     assert n_slabs > 20  # the window really slid
     m.close()
+
+
+def test_input_filter_chain_matches_oracle():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import modules_oracle as mo
+    from norlab_icp_mapper_b200.mapper import Mapper, bounding_box, distance_limit
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(), minimizer="identity", max_iteration_count=1)
+    boxes = [((-1.5, -1, -1), (0.5, 1, 0.5)), ((-6, -2.5, -1), (-1.5, 2.5, 1))]  # examples/config.yaml:1-17
+    m = Mapper(cfg, True, False, True, False, sensorMaxRange=40.0, inputFilters=[bounding_box(lo, hi, True) for lo, hi in boxes] + [distance_limit(0.5, 2, False)])
+    rng = np.random.default_rng(4)
+    scan = synth.homog(rng.normal(0, 15, (50_000, 3)) * [1, 1, 0.1])
+    got = m.applyInputFilters(scan)
+    keep = mo.distance_limit_keep(scan, 40.0)
+    for lo, hi in boxes:
+        keep &= mo.bounding_box_keep(scan, lo, hi, True)
+    keep &= mo.distance_limit_keep(scan, 0.5, dim_index=2)
+    assert 0 < keep.sum() < len(scan) and np.array_equal(got, scan[keep])
+    m.close()
+
+
+def test_example_config_pipeline_matches_reference_sequence(oracle):
+    """DynamicPoints + Octree + SurfaceNormal + CutAtDescriptorThreshold + input boxes, i.e. the
+    reference's examples/config.yaml (with deterministic octree sampling), over a short drive."""
+    from norlab_icp_mapper_b200 import _abi
+    from norlab_icp_mapper_b200.mapper import Mapper, bounding_box
+    from reference_mapper import RefExampleMapper
+    cfg = make_config(dim=3, knn=6, max_dist=2.0, outliers=(), minimizer="identity", max_iteration_count=10)
+    boxes = [((-1.5, -1, -1), (0.5, 1, 0.5)), ((-6, -2.5, -1), (-1.5, 2.5, 1))]
+    dyn = _abi.DynamicParams(thresholdDynamic=0.9, alpha=0.8, beta=0.99, beamHalfAngle=0.01, epsilonA=0.01, epsilonD=0.01)
+    gpu = Mapper(cfg, True, False, True, False, updateCondition=("delay", 0.05), sensorMaxRange=200.0, surfaceNormalKnn=10,
+                 dynamicPoints=dyn, octree=(0.15, 0), cutAtThreshold=0.65, inputFilters=[bounding_box(lo, hi, True) for lo, hi in boxes],
+                 addProbabilityDynamic=0.6)
+    ref = RefExampleMapper(max_size=0.15, knn=10, cut=0.65, delay=0.05, dyn=dict(thresholdDynamic=0.9), boxes=boxes)
+    for i, (scan, T_true, T_est) in enumerate(_scans(n_scans=4, n_pts=15_000)):
+        f_gpu = gpu.applyInputFilters(scan)
+        f_ref = ref.apply_input_filters(scan)
+        assert np.array_equal(f_gpu, f_ref)
+        gpu.processInput(f_gpu, T_true.astype(np.float32), 0.1 * i)   # exact poses: the chain uses the Identity minimiser
+        ref.process_input(f_ref, T_true.astype(np.float32), 0.1 * i)
+        assert np.array_equal(gpu.getPose(), T_true.astype(np.float32))
+        st = gpu.stats()
+        assert bool(st.map_updated) == ref.updated
+        # the reference's sensor-frame round trip moves map coordinates by ulps per update, which can move a
+        # borderline point across an octree face: sizes agree to a fraction of a percent, not exactly
+        assert abs(st.n_local - len(ref.map)) <= 0.005 * len(ref.map) + 5, (i, st.n_local, len(ref.map))
+    feat, nrm = gpu.getMap()
+    assert nrm is not None
+    from scipy.spatial import cKDTree
+    d, _ = cKDTree(ref.map[:, :3]).query(feat[:, :3])
+    assert (d < 1e-4).mean() > 0.995  # same surviving points
+    gpu.close()
