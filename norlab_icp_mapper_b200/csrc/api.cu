@@ -170,7 +170,7 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
         CK(cudaMalloc((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
     }
     if (nq > b.cap_nq) {
-        const int64_t cap = nq + nq / 4 + 1024;
+        const int64_t cap = grow_capacity(nq);
         cudaFree(b.reading_in);
         cudaFree(b.reading);
         cudaFree(b.reading_tmp);
@@ -193,7 +193,7 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
 
 int32_t ensure_query_buffers(b200icp_ctx* ctx, int64_t nq, int k) {
     if (nq * k > ctx->cap_out) {
-        const int64_t cap = nq * k + nq * k / 4 + 1024;
+        const int64_t cap = grow_capacity(nq * k);
         cudaFree(ctx->d_out_ids);
         cudaFree(ctx->d_out_d2);
         ctx->d_out_ids = nullptr;
@@ -204,7 +204,7 @@ int32_t ensure_query_buffers(b200icp_ctx* ctx, int64_t nq, int k) {
         ctx->cap_out = cap;
     }
     if (nq > ctx->cap_q4) {
-        const int64_t cap = nq + nq / 4 + 1024;
+        const int64_t cap = grow_capacity(nq);
         cudaFree(ctx->d_q4);
         ctx->d_q4 = nullptr;
         ctx->cap_q4 = 0;
@@ -844,8 +844,8 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         cudaFree(ctx->map.normals);
         ctx->map.normals = nullptr;
         ctx->map.cap_normals = 0;
-        CK(cudaMalloc((void**)&ctx->map.normals, (size_t)(n + n / 4 + 1024) * sizeof(float4)));
-        ctx->map.cap_normals = n + n / 4 + 1024;
+        CK(cudaMalloc((void**)&ctx->map.normals, (size_t)grow_capacity(n) * sizeof(float4)));
+        ctx->map.cap_normals = grow_capacity(n);
     }
     int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
     *h_nq = (int)n;

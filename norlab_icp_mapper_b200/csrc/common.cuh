@@ -11,6 +11,10 @@
 namespace b200 {
 
 constexpr int kSMs = 148;        // B200
+// Capacity policy of every growing device buffer: double, never below 1 Mi elements.  cudaMalloc /
+// cudaFree of multi-hundred-MB buffers cost 100+ ms and synchronise the device, so a growing online
+// map must hit them O(log N) times, not every few scans.
+inline int64_t grow_capacity(int64_t n) { return n * 2 > (int64_t(1) << 20) ? n * 2 : (int64_t(1) << 20); }
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
 constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)

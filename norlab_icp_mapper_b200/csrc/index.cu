@@ -133,7 +133,7 @@ void grid_free(GridIndex& g) {
 cudaError_t ensure_scratch(GridIndex& g, int64_t n) {
     cudaError_t e;
     if (n > g.cap_scratch) {
-        const int64_t cap = n + n / 4 + 1024;
+        const int64_t cap = grow_capacity(n);
         if ((e = ensure(g.tmp_pts, cap)) != cudaSuccess) return e;
         if ((e = ensure(g.keys_in, cap)) != cudaSuccess) return e;
         if ((e = ensure(g.keys_out, cap)) != cudaSuccess) return e;
@@ -263,16 +263,17 @@ cudaError_t grid_build(GridIndex& g, const float* d_feat, int rows, int dim, con
     v.slack = 1e-6f * (float)(max_n + 8) + 1e-5f;
     const int64_t n_cells = (int64_t)v.nx * v.ny * v.nz;
     if (n_cells + 1 > g.cap_cells) {
-        if ((e = ensure(g.cell_start, n_cells + 1 + n_cells / 8)) != cudaSuccess) return e;
-        g.cap_cells = n_cells + 1 + n_cells / 8;
+        const int64_t cap_c = std::min<int64_t>(grow_capacity(n_cells + 1), (int64_t)kMaxCells + 2);
+        if ((e = ensure(g.cell_start, cap_c)) != cudaSuccess) return e;
+        g.cap_cells = cap_c;
     }
     if (n > g.cap_pts) {
-        const int64_t cap = n + n / 4 + 1024;
+        const int64_t cap = grow_capacity(n);
         if ((e = ensure(g.pts, cap)) != cudaSuccess) return e;
         g.cap_pts = cap;
     }
     if (d_normals && n > g.cap_normals) {
-        const int64_t cap = n + n / 4 + 1024;
+        const int64_t cap = grow_capacity(n);
         if ((e = ensure(g.normals, cap)) != cudaSuccess) return e;
         g.cap_normals = cap;
     }

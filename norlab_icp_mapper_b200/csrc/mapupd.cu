@@ -221,7 +221,7 @@ void store_free(MapStore& m) {
 cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s) {
     cudaError_t e;
     if (n > m.cap) {
-        const int64_t cap = n + n / 2 + 4096;
+        const int64_t cap = grow_capacity(n);
         if ((e = regrow(m.feat, m.n, cap, s)) != cudaSuccess) return e;
         if ((e = regrow(m.nrm, m.n * dim, cap * dim, s)) != cudaSuccess) return e;
         if ((e = regrow(m.prob, m.n, cap, s)) != cudaSuccess) return e;
@@ -253,7 +253,7 @@ static cudaError_t ensure_tmp(MapStore& m, int64_t n) {
     cudaFree(m.tmp_u32b);
     m.tmp_u32a = m.tmp_u32b = nullptr;
     m.cap_tmp = 0;
-    const int64_t cap = n + n / 2 + 4096;
+    const int64_t cap = grow_capacity(n);
     cudaError_t e;
     if ((e = cudaMalloc((void**)&m.tmp_u32a, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void**)&m.tmp_u32b, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
@@ -581,7 +581,7 @@ cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float 
         cudaFree(m.keys64_b);
         m.keys64_a = m.keys64_b = nullptr;
         m.cap_keys64 = 0;
-        const int64_t cap = na + na / 2 + 4096;
+        const int64_t cap = grow_capacity(na);
         if ((e = cudaMalloc((void**)&m.keys64_a, (size_t)cap * 8)) != cudaSuccess) return e;
         if ((e = cudaMalloc((void**)&m.keys64_b, (size_t)cap * 8)) != cudaSuccess) return e;
         m.cap_keys64 = cap;

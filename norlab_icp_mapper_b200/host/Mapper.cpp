@@ -1,7 +1,10 @@
 // Mapper.cpp -- see Mapper.h.  Reference: /root/reference/norlab_icp_mapper/Mapper.cpp.
 #include "Mapper.h"
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 namespace norlab_icp_mapper_b200 {
 
@@ -68,8 +71,23 @@ void Mapper::applyInputFilters(DataPoints& in) {
 }
 
 // Mapper.cpp:194-238
+namespace {
+struct StepTimer {  // B200MAPPER_TIMING=1 prints the wall time of each step of processInput (development aid)
+    bool on = std::getenv("B200MAPPER_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "  [mapper] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+}  // namespace
+
 void Mapper::processInput(const DataPoints& filteredInputInSensorFrame, const TransformationParameters& estimatedPose, double timeStamp) {
+    StepTimer timer;
     DataPoints input = rigidTransform(icp, filteredInputInSensorFrame, estimatedPose);
+    timer.lap("transform(input, T_est)");
     lastInputUpdatedMap = false;
 
     TransformationParameters correctedPose;
@@ -83,10 +101,15 @@ void Mapper::processInput(const DataPoints& filteredInputInSensorFrame, const Tr
             std::lock_guard<std::mutex> icpMapLockGuard(icpMapLock);
             correction = icp(input);
         }
+        timer.lap("icp(input)");
         correctedPose = correction * estimatedPose;
         map.updatePose(correctedPose);
+        timer.lap("map.updatePose");
         if (shouldUpdateMap(timeStamp, correctedPose, icp.getOverlap())) {
-            updateMap(rigidTransform(icp, input, correction), correctedPose, timeStamp);
+            DataPoints corrected = rigidTransform(icp, input, correction);
+            timer.lap("transform(input, correction)");
+            updateMap(corrected, correctedPose, timeStamp);
+            timer.lap("updateMap");
         }
     }
     {
