@@ -259,6 +259,10 @@ def run_b200(args):
         e2e_ms = float(t.item())
     clocks = sampler.finish() if sampler else None
 
+    # ---- in-kernel timing of the search phase of the persistent loop (from the timed `value` steps) ---
+    tm = icp.timing()
+    loop_iters, loop_search_ms, loop_total_ms = tm.loop_iterations, tm.loop_search_ms_sum, tm.loop_total_ms
+
     # ---- roofline of the k-NN kernel: separate pass with per-launch events --------------------------
     icp.set_profiling(True)
     nn_ms, nn_n = 0.0, 0
@@ -304,9 +308,16 @@ def run_b200(args):
             "device_ms_per_step": dev_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "knn_kernel<G, Acc1> (k = 1 correspondence search)", "algorithmic_bytes": b_nn,
+                         "kernel": "nn1_warm_kernel<4> (k = 1 correspondence search, iterations >= 1; iteration 0 is knn_kernel<8, Acc1>)", "algorithmic_bytes": b_nn,
                          "avg_launch_us": nn_avg_ms * 1e3, "launches_timed": nn_n, "peak_source": peak_src,
-                         "how": "separate pass of %d steps with cudaEvents around every k-NN launch on the library's stream" % args.steps},
+                         "how": "separate pass of %d steps through the kernel-per-step path with cudaEvents around every k-NN "
+                                "launch on the library's stream (event-to-event, so it includes the launch gap)" % args.steps,
+                         "in_loop": {"what": "the same search as a phase of the persistent loop kernel the timed steps use, "
+                                             "%globaltimer on CTA 0, last timed step", "iterations": loop_iters,
+                                     "avg_phase_us": (1e3 * loop_search_ms / loop_iters) if loop_iters else None,
+                                     "achieved": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9) if loop_iters else None,
+                                     "frac": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9 / peak) if loop_iters else None,
+                                     "loop_kernel_ms": loop_total_ms}},
             "clocks": clocks,
             "setmap_ms": setmap_ms,
             "pose_error_vs_truth": {"rad": err[0], "m": err[1]},

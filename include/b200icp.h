@@ -112,7 +112,9 @@ typedef struct b200icp_timing {
     float setmap_ms;      /* last b200icp_set_map*: mean-centre + index build                      */
     float select_ms_sum;  /* sum over iterations of the quantile-select kernel (profiling on)      */
     float acc_ms_sum;     /* sum over iterations of the accumulate/solve kernel (profiling on)     */
-    int32_t reserved[1];
+    int32_t loop_iterations; /* persistent loop kernel: iterations whose search phase was timed    */
+    float loop_search_ms_sum; /* ... sum of the in-kernel correspondence-search phase (%globaltimer, CTA 0) */
+    float loop_total_ms;      /* ... first iteration start to last iteration end (%globaltimer)        */
 } b200icp_timing;
 
 /* One entry of the YAML `input:` chain (libpointmatcher DataPointsFilters used on this path,
@@ -215,6 +217,10 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn);
  * leave HBM: unloading clears their `loaded` flag (the reference moves them to the CellManager),
  * loading sets it again.  Does not rebuild the index (call b200icp_map_commit). */
 int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed);
+
+/* Pre-size the device buffers for a map of n_points (and, if normals_knn > 0, the self-k-NN scratch of
+ * b200icp_map_surface_normals): an online map then grows without cudaMalloc stalls.  Optional. */
+int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_knn);
 
 /* icp.setMap(localPointCloud): rebuild the index over the loaded points.  An empty local cloud is
  * ignored like LPM does (the previous index stays). */

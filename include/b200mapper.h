@@ -39,7 +39,8 @@ typedef struct b200mapper_config {
     b200icp_filter input_filters[6];
     int32_t add_probability_dynamic;
     float probability_dynamic_value;
-    int32_t reserved[4];
+    int32_t reserve_points;    /* > 0: pre-size the device map for this many points (no reference counterpart) */
+    int32_t reserved[3];
 } b200mapper_config;
 
 typedef struct b200mapper_stats {

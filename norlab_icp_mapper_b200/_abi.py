@@ -58,7 +58,9 @@ class Timing(C.Structure):
         ("setmap_ms", C.c_float),
         ("select_ms_sum", C.c_float),
         ("acc_ms_sum", C.c_float),
-        ("reserved", C.c_int32 * 1),
+        ("loop_iterations", C.c_int32),
+        ("loop_search_ms_sum", C.c_float),
+        ("loop_total_ms", C.c_float),
     ]
 
 

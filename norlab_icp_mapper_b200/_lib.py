@@ -22,7 +22,7 @@ SYMBOLS = [
     "b200icp_set_trace", "b200icp_get_trace", "b200icp_map_insert_point_distance",
     "b200icp_map_surface_normals", "b200icp_map_window", "b200icp_map_commit", "b200icp_map_counts",
     "b200icp_map_has_normals", "b200icp_map_download", "b200icp_map_set_prob", "b200icp_map_has_prob",
-    "b200icp_map_download_prob", "b200icp_map_append", "b200icp_filter_cloud", "b200icp_map_octree", "b200icp_map_cut_at_threshold", "b200icp_map_dynamic_points",
+    "b200icp_map_download_prob", "b200icp_map_append", "b200icp_map_reserve", "b200icp_filter_cloud", "b200icp_map_octree", "b200icp_map_cut_at_threshold", "b200icp_map_dynamic_points",
 ]
 
 _lib = None
@@ -80,6 +80,7 @@ def load():
     L.b200icp_map_set_prob.argtypes = [vp, vp, f32]
     L.b200icp_map_has_prob.argtypes = [vp]
     L.b200icp_map_download_prob.argtypes = [vp, i32, vp, i64]
+    L.b200icp_map_reserve.argtypes = [vp, i64, i32]
     L.b200icp_map_append.argtypes = [vp, vp, i32, i64, vp, vp, C.POINTER(i64)]
     L.b200icp_filter_cloud.argtypes = [vp, vp, i32, C.POINTER(i64), vp, i32]
     L.b200icp_map_octree.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, i32, C.POINTER(i64)]

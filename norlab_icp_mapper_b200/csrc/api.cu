@@ -165,8 +165,8 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
     const int K = ctx->cfg.knn;
     if (!b.state) {
         CK(cudaMalloc((void**)&b.state, kStateBytes));
-        CK(cudaMalloc((void**)&b.hist, 3 * kHistBins * sizeof(uint32_t)));
-        CK(cudaMemset(b.hist, 0, 3 * kHistBins * sizeof(uint32_t)));
+        CK(cudaMalloc((void**)&b.hist, kHistWords * sizeof(uint32_t)));
+        CK(cudaMemset(b.hist, 0, kHistWords * sizeof(uint32_t)));
         CK(cudaMalloc((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
     }
     if (nq > b.cap_nq) {
@@ -559,9 +559,9 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
             if (time_it) CK(cudaEventRecord(ev[0], s));
             if (issued > 0 && p.knn == 1 && !(ctx->cfg.nn_variant & 2))  // warm: previous matches bound the search
                 CK(launch_nn1_warm(ctx->map.view, b.reading, (int)nq, b.state, p.max_r2, b.match_pos, b.match_d2, ctx->cfg.nn_variant, s));
-            else
+            else  // k > 1 from iteration 1 on: the previous matches bound the search (variant bit 16)
                 CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
-                              /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+                              /*want_original_ids=*/0, (ctx->cfg.nn_variant & 0xffff) | ((issued > 0 && !(ctx->cfg.nn_variant & 2)) ? 0x10000 : 0), s));
             if (time_it) CK(cudaEventRecord(ev[1], s));
             ++launches;
             CK(launch_iteration_tail(p, ctx->map, b, issued, s, &launches, time_it ? ev[2] : nullptr));
@@ -581,6 +581,9 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     ctx->timing.total_ms = ms;
     ctx->timing.kernel_launches = launches;
     ctx->timing.nn_ms_sum = ctx->timing.select_ms_sum = ctx->timing.acc_ms_sum = 0.f;
+    ctx->timing.loop_iterations = persistent ? out_state->loop_iters_timed : 0;
+    ctx->timing.loop_search_ms_sum = persistent ? (float)(1e-6 * (double)out_state->loop_search_ns) : 0.f;
+    ctx->timing.loop_total_ms = persistent ? (float)(1e-6 * (double)out_state->loop_total_ns) : 0.f;
     ctx->timing.nn_launches = 0;
     const int executed = out_state->iter;
     for (int i = 0; i < nn_timed && i < std::max(executed, 1); ++i) {
@@ -752,6 +755,33 @@ int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t fe
 }
 
 /* ---- device-resident map: Map::updateLocalPointCloud / updatePose pieces -------------------------- */
+
+int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_knn) {
+    if (!ctx || n_points < 0 || n_points > (int64_t)INT32_MAX / 2) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int dim = ctx->cfg.dim;
+    CK(store_reserve(ctx->store, dim, n_points, ctx->stream));
+    CK(ensure_scratch(ctx->map, n_points));
+    if (n_points > ctx->map.cap_pts) {
+        cudaFree(ctx->map.pts);
+        ctx->map.pts = nullptr;
+        ctx->map.cap_pts = 0;
+        CK(cudaMalloc((void**)&ctx->map.pts, (size_t)grow_capacity(n_points) * sizeof(float4)));
+        ctx->map.cap_pts = grow_capacity(n_points);
+    }
+    if (n_points > ctx->map.cap_normals) {
+        cudaFree(ctx->map.normals);
+        ctx->map.normals = nullptr;
+        ctx->map.cap_normals = 0;
+        CK(cudaMalloc((void**)&ctx->map.normals, (size_t)grow_capacity(n_points) * sizeof(float4)));
+        ctx->map.cap_normals = grow_capacity(n_points);
+    }
+    if (normals_knn > 0) {
+        const int32_t eb = ensure_query_buffers(ctx, n_points, normals_knn);
+        if (eb != B200ICP_OK) return eb;
+    }
+    return B200ICP_OK;
+}
 
 int32_t b200icp_map_commit(b200icp_ctx* ctx) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;

@@ -17,6 +17,7 @@ constexpr int kSMs = 148;        // B200
 inline int64_t grow_capacity(int64_t n) { return n * 2 > (int64_t(1) << 20) ? n * 2 : (int64_t(1) << 20); }
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
+constexpr int kHistWords = 16384; // uint32 words of the histogram / candidate-list buffer (layout in loop.cu)
 constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)
 constexpr int kAccBlocks = 128;      // accumulate-kernel grid (one partial each, summed in fixed order)
 constexpr int kLoopMaxBlocks = 192;  // persistent loop kernel: one CTA per SM
@@ -53,6 +54,11 @@ struct IcpState {
     float dt[8][3];
     float bq0[4];
     float bt0[3];
+    // instrumentation of the persistent loop kernel (CTA 0's view, %globaltimer ns)
+    unsigned long long loop_search_ns;  // sum over iterations of the correspondence-search phase
+    unsigned long long loop_total_ns;   // first iteration start -> last iteration end
+    int loop_iters_timed;
+    int pad_;
 };
 
 static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");

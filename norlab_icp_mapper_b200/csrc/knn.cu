@@ -26,7 +26,7 @@ template <int G, typename Acc>
 __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __restrict__ queries, const int* __restrict__ d_nq,
                                                   const IcpState* __restrict__ state, int k, float max_r2,
                                                   int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
-                                                  int want_original_ids, int variant) {
+                                                  int want_original_ids, int variant, int warm) {
     if (state && state->done) return;
     const int nq = *d_nq;
     const int lane = threadIdx.x & 31;
@@ -44,7 +44,21 @@ __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __re
         qz = __fadd_rn(__fmaf_rn(T[10], q4.z, __fmaf_rn(T[6], q4.y, __fmul_rn(T[2], q4.x))), T[14]);
     }
     Acc acc;
-    acc.init(k);
+    float bound = CUDART_INF_F;
+    if (Acc::kPerLaneOutput && warm) {
+        // warm start for k > 1 (ICP iterations >= 1): out_ids still holds the previous iteration's k
+        // matches -- k distinct real map points -- so the largest of their distances to the moved query
+        // bounds the new k-th distance.  The bound only prunes; the result stays exact.
+        float dj = 0.f;
+        if (lig < k) {
+            const int pj = out_ids[qi * k + lig];
+            dj = (pj >= 0) ? dist2_exact(qx, qy, qz, __ldg(g.pts + pj)) : CUDART_INF_F;
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) dj = fmaxf(dj, __shfl_xor_sync(gmask, dj, o));
+        if (dj < CUDART_INF_F) bound = __uint_as_float(__float_as_uint(dj) + 1u);  // next float up: ties with the bound stay accepted
+    }
+    acc.init(k, bound);
     search_shells<G, Acc>(g, acc, qx, qy, qz, max_r2, variant, lig, gmask);
     float od;
     int op;
@@ -127,11 +141,11 @@ cudaError_t launch_warm_one(const GridView& g, const float4* reading, int cap, c
 
 template <int G, typename Acc>
 cudaError_t launch_one(const GridView& g, const float4* q, const int* d_nq, int cap, const IcpState* st, int k, float max_r2,
-                       int32_t* ids, float* d2, int want_orig, int variant, cudaStream_t s) {
+                       int32_t* ids, float* d2, int want_orig, int variant, cudaStream_t s, int warm = 0) {
     const int per_block = 256 / G;
     const int blocks = (cap + per_block - 1) / per_block;
     if (blocks <= 0) return cudaSuccess;
-    knn_kernel<G, Acc><<<blocks, 256, 0, s>>>(g, q, d_nq, st, k, max_r2, ids, d2, want_orig, variant);
+    knn_kernel<G, Acc><<<blocks, 256, 0, s>>>(g, q, d_nq, st, k, max_r2, ids, d2, want_orig, variant, warm);
     return cudaGetLastError();
 }
 
@@ -151,9 +165,10 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
             default: return launch_one<8, Acc1<8>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
         }
     }
-    if (k <= 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-    if (k <= 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-    return launch_one<32, AccK<32>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s);
+    const int warm = (variant & 0x10000) ? 1 : 0;  // set by the ICP loop from iteration 1 on (out_ids = previous matches, positions)
+    if (k <= 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
+    if (k <= 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
+    return launch_one<32, AccK<32>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
 }
 
 cudaError_t launch_nn1_warm(const GridView& g, const float4* d_reading, int nq_capacity, const IcpState* st, float max_r2,

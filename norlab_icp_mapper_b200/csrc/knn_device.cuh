@@ -32,7 +32,7 @@ struct Acc1 {
     static constexpr bool kPerLaneOutput = false;
     float d;
     int pos;
-    __device__ __forceinline__ void init(int) {
+    __device__ __forceinline__ void init(int, float) {
         d = CUDART_INF_F;
         pos = -1;
     }
@@ -82,12 +82,14 @@ struct AccK {
     static constexpr bool kPerLaneOutput = true;
     float d;      // my entry
     int pos;
-    float kth;    // group-uniform: current k-th best (inf until k found)
+    float kth;    // group-uniform: current k-th best (inf until k found), never above `bound`
+    float bound;  // group-uniform: a proven upper bound of the final k-th distance (warm start) or inf
     int k;
-    __device__ __forceinline__ void init(int k_) {
+    __device__ __forceinline__ void init(int k_, float bound_) {
         d = CUDART_INF_F;
         pos = -1;
-        kth = CUDART_INF_F;
+        bound = bound_;
+        kth = bound_;
         k = k_;
     }
     __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
@@ -121,7 +123,7 @@ struct AccK {
                     d = CUDART_INF_F;
                     pos = -1;
                 }
-                kth = __shfl_sync(gmask, d, k - 1, G);
+                kth = fminf(bound, __shfl_sync(gmask, d, k - 1, G));
                 m &= m - 1;
                 pass = pass && (cd < kth);
                 m &= __ballot_sync(gmask, pass);

@@ -94,6 +94,8 @@ int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapp
         mc.probabilityDynamicValue = cfg->probability_dynamic_value;
         m->dim = cfg->is_3d ? 3 : 2;
         m->mapper.reset(new Mapper(mc, cfg->is_3d != 0, cfg->is_online != 0, cfg->is_mapping != 0, false, device));
+        if (cfg->reserve_points > 0)
+            ICPSequence::check(m->mapper->getICP().context(), b200icp_map_reserve(m->mapper->getICP().context(), cfg->reserve_points, cfg->surface_normal_knn));
     });
     if (rc != B200ICP_OK) {
         delete m;

@@ -49,7 +49,7 @@ class MapperConfig(C.Structure):
                 ("use_cut_at_threshold", C.c_int32), ("cut_threshold", C.c_float),
                 ("n_input_filters", C.c_int32), ("input_filters", InputFilter * 6),
                 ("add_probability_dynamic", C.c_int32), ("probability_dynamic_value", C.c_float),
-                ("reserved", C.c_int32 * 4)]
+                ("reserve_points", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class MapperStats(C.Structure):
@@ -96,7 +96,7 @@ class Mapper:
 
     def __init__(self, icp_config, is3D=True, isOnline=False, isMapping=True, saveMapCellsOnHardDrive=False, *,
                  updateCondition=("distance", 1.0), sensorMaxRange=200.0, minDistNewPoint=0.15, surfaceNormalKnn=0,
-                 dynamicPoints=None, octree=None, cutAtThreshold=None, inputFilters=(), addProbabilityDynamic=None, device=0):
+                 dynamicPoints=None, octree=None, cutAtThreshold=None, inputFilters=(), addProbabilityDynamic=None, reservePoints=0, device=0):
         """dynamicPoints: _abi.DynamicParams or None; octree: (maxSizeByNode, samplingMethod) or None (then PointDistance);
         cutAtThreshold: threshold or None; inputFilters: InputFilter list; addProbabilityDynamic: value or None."""
         self._L = load()
@@ -119,6 +119,7 @@ class Mapper:
             cfg.input_filters[i] = f
         if addProbabilityDynamic is not None:
             cfg.add_probability_dynamic, cfg.probability_dynamic_value = 1, addProbabilityDynamic
+        cfg.reserve_points = int(reservePoints)
         self.dim = 3 if is3D else 2
         self.n = self.dim + 1
         h = C.c_void_p()

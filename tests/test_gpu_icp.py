@@ -142,6 +142,22 @@ def test_run_to_run_determinism(pair3d):
     assert er <= 1e-6 and et <= 1e-5, (er, et)
 
 
+def test_quantile_fallback_path_is_identical(pair3d):
+    """nn_variant bit 3 forces the loop kernel's global-pass fallback of the quantile select (used when
+    the quantile's bucket is larger than the candidate list); the limit, hence the pose, is the same."""
+    from norlab_icp_mapper_b200.icp import ICP
+    outs = []
+    for variant in (0, 8):
+        for chain in ((("trimmed", 0.85),), (("median", 3.0),)):
+            cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=chain, minimizer="point_to_plane", max_iteration_count=12, nn_variant=variant)
+            g = ICP(cfg)
+            g.set_map(pair3d["map"], pair3d["normals"])
+            outs.append((g(pair3d["reading"]), g.last_result.pairs_last_iter))
+            g.close()
+    assert np.array_equal(outs[0][0], outs[2][0]) and outs[0][1] == outs[2][1]
+    assert np.array_equal(outs[1][0], outs[3][0]) and outs[1][1] == outs[3][1]
+
+
 def test_error_behaviour_matches_libpointmatcher(oracle, pair3d):
     from norlab_icp_mapper_b200.icp import ICP, B200ICPError
     cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=5)

@@ -68,7 +68,7 @@ print("cfg5", json.dumps(out["cfg5_batched"]), flush=True)
 n_scans = 30 if quick else 120
 world = synth.World3D(seed=2000, size=(1000.0, 200.0), n_boxes=200)
 cfg3 = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30, differential=(1e-3, 1e-3, 3))
-m = Mapper(cfg3, True, False, True, False, updateCondition=("distance", 1.0), sensorMaxRange=80.0, minDistNewPoint=0.05, surfaceNormalKnn=10)
+m = Mapper(cfg3, True, False, True, False, updateCondition=("distance", 1.0), sensorMaxRange=80.0, minDistNewPoint=0.05, surfaceNormalKnn=10, reservePoints=12_000_000)
 rng = np.random.default_rng(5)
 times, sizes, upd = [], [], []
 T_prev_true = None

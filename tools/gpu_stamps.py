@@ -12,9 +12,8 @@ names = {0: "sel start", 1: "sel p0 hist", 2: "sel p0 sync", 3: "sel p0 pick", 4
          7: "sel p2 hist", 8: "sel p2 sync", 9: "sel p2 pick", 10: "sel end", 11: "acc start(b0)", 12: "acc loop done(b0)",
          13: "acc last-block ticket", 14: "acc reduced", 15: "acc finished", 16: "nn start(b0)", 17: "nn end(last block)"}
 if "--loop" in sys.argv:
-    names = {20: "iter start", 21: "nn done", 22: "p0 hist flushed", 23: "p0 barrier", 24: "p0 pick", 25: "p1 hist flushed", 26: "p1 barrier",
-             27: "p1 pick", 28: "p2 hist flushed", 29: "p2 barrier", 30: "p2 pick", 31: "acc partial written", 12: "acc barrier",
-             13: "reduced", 14: "finished"}
+    names = {20: "iter start", 21: "nn done", 22: "level-0 hist flushed", 23: "barrier 1", 24: "pick 0", 25: "candidates gathered", 26: "barrier 2",
+             27: "local select done", 31: "acc partial written", 12: "acc barrier", 13: "reduced", 14: "finished"}
 for rep in range(3):
     g(d["reading"])
     st = np.zeros(32, np.uint64)

@@ -14,7 +14,7 @@ for cpp in cpps:
     os.environ["B200ICP_CELLS_PER_POINT"] = str(cpp)
     for variant in variants:
         cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane",
-                          max_iteration_count=30, nn_variant=variant)
+                          max_iteration_count=30, nn_variant=variant & 0xffff, sort_reading=0 if (variant & 0x100000) else 1)
         g = ICP(cfg); g.set_profiling("--prof" in sys.argv); g.set_map(d["map"], d["normals"])
         ts = []
         for rep in range(4):
