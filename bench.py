@@ -262,6 +262,7 @@ def run_b200(args):
     # ---- in-kernel timing of the search phase of the persistent loop (from the timed `value` steps) ---
     tm = icp.timing()
     loop_iters, loop_search_ms, loop_total_ms = tm.loop_iterations, tm.loop_search_ms_sum, tm.loop_total_ms
+    loop_fast_iters = tm.loop_fast_iterations
 
     # ---- roofline of the k-NN kernel: separate pass with per-launch events --------------------------
     icp.set_profiling(True)
@@ -317,7 +318,7 @@ def run_b200(args):
                                      "avg_phase_us": (1e3 * loop_search_ms / loop_iters) if loop_iters else None,
                                      "achieved": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9) if loop_iters else None,
                                      "frac": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9 / peak) if loop_iters else None,
-                                     "loop_kernel_ms": loop_total_ms}},
+                                     "loop_kernel_ms": loop_total_ms, "one_barrier_iterations": loop_fast_iters}},
             "clocks": clocks,
             "setmap_ms": setmap_ms,
             "pose_error_vs_truth": {"rad": err[0], "m": err[1]},

@@ -115,6 +115,8 @@ typedef struct b200icp_timing {
     int32_t loop_iterations; /* persistent loop kernel: iterations whose search phase was timed    */
     float loop_search_ms_sum; /* ... sum of the in-kernel correspondence-search phase (%globaltimer, CTA 0) */
     float loop_total_ms;      /* ... first iteration start to last iteration end (%globaltimer)        */
+    int32_t loop_fast_iterations; /* ... iterations that ran with ONE device-wide barrier (predicted quantile window) */
+    int32_t loop_searched_queries; /* ... queries (summed over the iterations) that needed a search; the others were proven unchanged */
 } b200icp_timing;
 
 /* One entry of the YAML `input:` chain (libpointmatcher DataPointsFilters used on this path,

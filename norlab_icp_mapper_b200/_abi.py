@@ -61,6 +61,8 @@ class Timing(C.Structure):
         ("loop_iterations", C.c_int32),
         ("loop_search_ms_sum", C.c_float),
         ("loop_total_ms", C.c_float),
+        ("loop_fast_iterations", C.c_int32),
+        ("loop_searched_queries", C.c_int32),
     ]
 
 

@@ -36,6 +36,8 @@ struct b200icp_ctx {
     int* d_scalar_nq = nullptr;
     unsigned* d_bar_counter = nullptr;
     int n_sms = 148;
+    float margin3[3] = {3.0f, 0.002f, 0.25f};  // search margin of the loop kernel's match cache; B200ICP_MARGIN="gain,min[m],max[cells]"
+    float win3[3] = {2.0f, 0.0015f, 0.12f};  // quantile-window policy of the one-barrier iteration (loop.cu); B200ICP_WINDOW="gain,floor,max"
     char* h_pinned = nullptr;  // [0, 1024): state image to upload, [1024, 2048): state read back, [2048..): ints
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_map0 = nullptr, ev_map1 = nullptr;
     std::vector<cudaEvent_t> nn_events;
@@ -168,6 +170,8 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
         CK(cudaMalloc((void**)&b.hist, kHistWords * sizeof(uint32_t)));
         CK(cudaMemset(b.hist, 0, kHistWords * sizeof(uint32_t)));
         CK(cudaMalloc((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
+        CK(cudaMalloc((void**)&b.fastws, icp_loop_workspace_bytes()));
+        CK(cudaMemset(b.fastws, 0, icp_loop_workspace_bytes()));
     }
     if (nq > b.cap_nq) {
         const int64_t cap = grow_capacity(nq);
@@ -176,6 +180,9 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
         cudaFree(b.reading_tmp);
         cudaFree(b.match_pos);
         cudaFree(b.match_d2);
+        cudaFree(b.spill_pp);
+        cudaFree(b.spill_nv);
+        b.spill_pp = b.spill_nv = nullptr;
         b.reading_in = nullptr;
         b.reading = b.reading_tmp = nullptr;
         b.match_pos = nullptr;
@@ -186,6 +193,10 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
         CK(cudaMalloc((void**)&b.reading_tmp, (size_t)cap * sizeof(float4)));
         CK(cudaMalloc((void**)&b.match_pos, (size_t)cap * K * sizeof(int32_t)));
         CK(cudaMalloc((void**)&b.match_d2, (size_t)cap * K * sizeof(float)));
+        if (K == 1) {
+            CK(cudaMalloc((void**)&b.spill_pp, (size_t)cap * sizeof(float4)));
+            CK(cudaMalloc((void**)&b.spill_nv, (size_t)cap * sizeof(float4)));
+        }
         b.cap_nq = cap;
     }
     return B200ICP_OK;
@@ -337,6 +348,22 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     ok = ok && icp_device_setup() == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_bar_counter, 64) == cudaSuccess;
     ctx->n_sms = prop.multiProcessorCount;
+    if (const char* env = getenv("B200ICP_MARGIN")) {
+        float a, f, m;
+        if (sscanf(env, "%f,%f,%f", &a, &f, &m) == 3 && a >= 0.f && f >= 0.f && m >= 0.f) {
+            ctx->margin3[0] = a;
+            ctx->margin3[1] = f;
+            ctx->margin3[2] = m;
+        }
+    }
+    if (const char* env = getenv("B200ICP_WINDOW")) {
+        float a, f, m;
+        if (sscanf(env, "%f,%f,%f", &a, &f, &m) == 3 && a >= 0.f && f > 0.f && m >= f) {
+            ctx->win3[0] = a;
+            ctx->win3[1] = f;
+            ctx->win3[2] = m;
+        }
+    }
     if (!ok) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
         b200icp_destroy(ctx);
@@ -364,6 +391,9 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaFree(b.partials);
     cudaFree(b.state);
     cudaFree(b.trace);
+    cudaFree(b.fastws);
+    cudaFree(b.spill_pp);
+    cudaFree(b.spill_nv);
     cudaFree(ctx->d_stage_a);
     cudaFree(ctx->d_stage_b);
     cudaFree(ctx->d_out_ids);
@@ -414,6 +444,16 @@ int32_t b200icp_get_trace(const b200icp_ctx* ctx, float* out, int32_t max_iterat
 int32_t b200icp_debug_stamps(const b200icp_ctx* ctx, unsigned long long* out32) {
     if (!ctx || !out32) return B200ICP_ERR_INVALID_ARG;
     memcpy(out32, ctx->h_pinned + kStateBytes + kDebugOffset, 32 * sizeof(unsigned long long));
+    return B200ICP_OK;
+}
+
+/* development aid (not in the public header): the loop kernel's per-iteration record of the last registration,
+ * 8 words per iteration: {path 0 general / 1 one-barrier / 2 failed attempt, limit bits, candidates, pairs below the
+ * window, queries searched so far (all CTAs), next window lo, hi, iteration time in ns on CTA 0} */
+int32_t b200icp_debug_loop_record(b200icp_ctx* ctx, uint32_t* out, int32_t iterations) {
+    if (!ctx || !out || iterations < 0 || iterations > 256 || !ctx->buf.hist) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(out, ctx->buf.hist + 12288, (size_t)iterations * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return B200ICP_OK;
 }
 
@@ -545,7 +585,7 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, 1, p.max_r2, b.match_pos, b.match_d2,
                       /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
         CK(cudaMemsetAsync(ctx->d_bar_counter, 0, sizeof(unsigned), s));
-        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, s));
+        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, ctx->win3, ctx->margin3, s));
         launches += 2;
         CK(cudaMemcpyAsync(out_state, b.state, kStateBytes, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(ctx->ev_end, s));
@@ -584,6 +624,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     ctx->timing.loop_iterations = persistent ? out_state->loop_iters_timed : 0;
     ctx->timing.loop_search_ms_sum = persistent ? (float)(1e-6 * (double)out_state->loop_search_ns) : 0.f;
     ctx->timing.loop_total_ms = persistent ? (float)(1e-6 * (double)out_state->loop_total_ns) : 0.f;
+    ctx->timing.loop_fast_iterations = persistent ? out_state->fast_iters : 0;
+    ctx->timing.loop_searched_queries = persistent ? out_state->searched_queries : 0;
     ctx->timing.nn_launches = 0;
     const int executed = out_state->iter;
     for (int i = 0; i < nn_timed && i < std::max(executed, 1); ++i) {

@@ -58,7 +58,12 @@ struct IcpState {
     unsigned long long loop_search_ns;  // sum over iterations of the correspondence-search phase
     unsigned long long loop_total_ns;   // first iteration start -> last iteration end
     int loop_iters_timed;
-    int pad_;
+    int fast_iters;  // iterations that took the one-barrier path
+    // one-barrier iteration (loop.cu): window [win_lo, win_hi] of dist2 bit patterns predicted to hold the next quantile limit
+    uint32_t win_lo, win_hi;
+    int win_valid, have_limit;
+    int searched_queries;  // queries that went through the search phase (the rest were verified against their bound)
+    int pad2_;
 };
 
 static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");
@@ -214,6 +219,9 @@ struct IcpBuffers {
     double* partials = nullptr;    // kMaxAccBlocks x kAccSlots
     IcpState* state = nullptr;
     float* trace = nullptr;        // max_iter x 16
+    char* fastws = nullptr;        // loop.cu one-barrier iteration workspace (icp_loop_workspace_bytes())
+    float4* spill_pp = nullptr;    // loop.cu match cache for the queries beyond the shared-memory capacity (cap_nq each)
+    float4* spill_nv = nullptr;
     int64_t cap_nq = 0;
     int cap_iter = 0;
 };
@@ -225,8 +233,11 @@ cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, fl
                                   cudaStream_t s);
 cudaError_t icp_device_setup();
 // loop.cu: iterations 1.. of a k = 1 registration in one persistent cooperative kernel
+// win3 = {gain, floor, max}: half-width of the quantile window = max(gain * |limit - previous limit|, floor * limit), tried when <= max * limit
+size_t icp_loop_workspace_bytes();
+// margin3 = {gain, min [m], max [cell edges]}: extra search radius = clamp(gain * the query's last motion, min, max * h)
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                            int variant, cudaStream_t s);
+                            int variant, const float* win3, const float* margin3, cudaStream_t s);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
                                   cudaStream_t s, int* launches, cudaEvent_t ev_mid);

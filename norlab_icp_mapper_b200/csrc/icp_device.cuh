@@ -116,6 +116,15 @@ __device__ float quat_angular_distance(const float* a, const float* b) {
 // pivots of the elimination are the squares of the Cholesky diagonal, so the reference's
 // "is A invertible" decision (LLT succeeds) is the same test; the rank-deficient case falls back
 // to the minimum-norm solution on lane 0.  Result: x[6] identical in every lane.
+// 1 / x for a pivot: fp32 reciprocal + one Newton step in fp64 (relative error ~4e-15) -- the full-precision
+// fp64 division is a long dependent sequence and the elimination below needs one per pivot, serially.
+__device__ __forceinline__ double pivot_rcp(double x) {
+    if (!(x > 1e-30 && x < 1e30)) return 1.0 / x;
+    double r = (double)__frcp_rn((float)x);
+    r = fma(r, fma(-x, r, 1.0), r);  // 2^-24 -> 2^-48: far below what the fp32 inputs carry
+    return r;
+}
+
 __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/) {
     const unsigned full = 0xffffffffu;
     const int r = min(lane, 5);
@@ -149,8 +158,9 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
         for (int c = k; c < 7; ++c) pk[c] = __shfl_sync(full, a[c], k);
         const double piv = pk[k];
         if (!(piv > thr)) ok = false;
+        const double inv = pivot_rcp(piv);
         if (lane != k) {
-            const double f = a[k] / piv;
+            const double f = a[k] * inv;
 #pragma unroll
             for (int c = k; c < 7; ++c) a[c] -= f * pk[c];
         }
@@ -159,7 +169,7 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
 #pragma unroll
     for (int c = 0; c < 6; ++c)
         if (c == r) arr = a[c];
-    const double xr = a[6] / arr;  // one division, not one per unrolled candidate
+    const double xr = a[6] * pivot_rcp(arr);
 #pragma unroll
     for (int i = 0; i < 6; ++i) x[i] = (float)__shfl_sync(full, xr, i);
     bool bad = !ok;
@@ -431,7 +441,7 @@ __device__ __noinline__ void finish_iteration(const IcpParams& prm, IcpState* st
 
 // Everything after the sums, on warp 0 of the last block.
 __device__ __forceinline__ void finish_warp(const IcpParams& prm, IcpState* st, const double* S, int n_sums, float* trace,
-                                            float* s_scratch /* smem[16] */) {
+                                            float* s_scratch /* smem[16] */, IcpState* stamp_to = nullptr) {
     const int lane = threadIdx.x & 31;
     const double pairs = S[n_sums - 1];
     const double wsum = S[n_sums - 2];
@@ -446,7 +456,9 @@ __device__ __forceinline__ void finish_warp(const IcpParams& prm, IcpState* st, 
     if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE) {
         float x[6];
         solve6_warp(S, prm.dim, lane, x, s_scratch);
+        if (stamp_to && lane == 0) B200_STAMP(stamp_to, 15);
         delta_from_x(x, prm.dim, dT);
+        if (stamp_to && lane == 0) B200_STAMP(stamp_to, 16);
     } else {
         if (lane == 0) {
             float d16[16];

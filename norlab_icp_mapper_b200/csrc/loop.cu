@@ -1,18 +1,30 @@
 // loop.cu -- the whole ICP loop of one registration as ONE persistent cooperative kernel (k = 1).
 //
-// Same steps as the kernel-per-step path (knn.cu / icp.cu) -- warm ball search, exact radix-select
-// of the distance quantile, gather + error sums, fixed-order reduction, one-warp solve, checkers --
-// but the grid stays resident (one 1024-thread CTA per SM) and the steps are separated by a
-// device-wide barrier (one atomic + acquire spin, ~1 us) instead of a kernel boundary (~4 us of
-// launch gap each on B200).  Each CTA owns a fixed slice of the reading for the whole registration;
-// every CTA reduces the per-CTA partial sums in the same fixed order and runs the 6x6 solve and the
-// checkers redundantly, so T_iter and the stop decision are bit-identical everywhere and nothing has
-// to be broadcast.  (The slices differ from the kernel-per-step path's, so the error sums -- and
-// therefore the pose -- agree with that path to rounding, not bit for bit; each path is run-to-run
-// deterministic.)
-//
 // Replaces the body of PM::ICPSequence::operator() (/root/reference/norlab_icp_mapper/Mapper.cpp:213)
 // from the second iteration on; iteration 0's cold search is the stand-alone knn_kernel.
+//
+// The grid stays resident (one 1024-thread CTA per SM); each CTA owns a fixed slice of the reading for
+// the whole registration and keeps that slice's MATCH STATE IN SHARED MEMORY across iterations:
+// reading point, matched map point (+ its position), its normal, the squared distance, and a proven
+// lower bound L on the distance from the query to every OTHER map point.  One iteration is
+//
+//   V  verify   (thread per query, shared memory only): the query moved by delta since the bound was
+//               established; if dist(q, match) + delta < L the old match is still the exact nearest
+//               neighbour (triangle inequality) -- no search.  Otherwise the query goes on a work list.
+//   S  search   (4 lanes per listed query): exact ball search on the cell-sorted grid, bounded by the old
+//               match, widened by a small margin m so that it also yields the 2nd-nearest distance / the
+//               covered radius = the next bound L.  After ICP's first iterations only a few percent of
+//               the queries need this.
+//   C  classify (thread per query): outlier weights, error-minimiser sums, quantile bookkeeping.
+//   one device-wide barrier, then every CTA finishes the iteration redundantly and bit-identically:
+//   exact quantile limit, fixed-order reduction, 6x6 solve, checkers ("one-barrier iteration" below).
+//
+// Results are the same as an exhaustive search every iteration: the verification only ever skips work
+// whose outcome is proven (nn_variant bit 5 disables it; tests compare).  The general quantile path
+// (3 barriers, level-0 histogram through global memory) remains for iterations whose quantile window
+// cannot be predicted.  Every CTA reduces the per-CTA partial sums in the same fixed order and runs the
+// solve and the checkers redundantly, so T_iter and the stop decision are bit-identical everywhere and
+// nothing has to be broadcast; each path is run-to-run deterministic.
 #include <cooperative_groups.h>
 
 #include "icp_device.cuh"
@@ -23,6 +35,11 @@ namespace {
 
 constexpr int kLoopThreads = 1024;
 constexpr int kLoopWarps = kLoopThreads / 32;
+constexpr int kLoopG = 4;                       // lanes per query in the search phase
+constexpr int kChunk = 32;                      // reading points are dealt to the CTAs in chunks of 32 consecutive points (balance)
+constexpr int kCacheCap = 2048;                 // queries per CTA whose match state lives in shared memory (the rest spills to global)
+// dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[cap]
+constexpr size_t kLoopDynSmem = (size_t)kCacheCap * (3 * sizeof(float4) + sizeof(float) + sizeof(uint32_t));
 // Exact quantile inside the loop kernel: level 0 = 12 bits [30:19] of the float pattern (4096 bins,
 // histogrammed while searching, merged through global memory); the bucket that holds the quantile
 // then contains ~1 % of the distances, which every CTA pulls into shared memory as a candidate list
@@ -34,6 +51,29 @@ constexpr int kSelListCap = 4096;
 // layout of the `hist` buffer (uint32): [0, 4096) level 0 | [4096, 6144) fallback level 1 | [6144, 6400) fallback level 2 |
 // [6400] list counter | [8192, 8192 + kSelListCap) candidate list
 constexpr int kHistL1 = 4096, kHistL2 = 6144, kHistCount = 6400, kHistList = 8192;
+constexpr int kHistDebug = 12288;  // 8 words per iteration (first 256 iterations): development record written by CTA 0
+constexpr int kHistStat = 16000;   // [0] queries that went through the search phase (all CTAs, whole registration)
+
+// ---- one-barrier iteration ("fast path") --------------------------------------------------------------
+// Once ICP settles the Trimmed/quantile limit moves by a few percent per iteration, so the limit of the
+// previous iteration predicts a narrow WINDOW [win_lo, win_hi] (float bit patterns of dist2) that will
+// contain the new limit.  Each CTA then classifies its pairs while it still has them at hand:
+//   dist2 <  win_lo : certainly kept    -> error sums accumulated right away (per-CTA partial)
+//   dist2 in window : candidate         -> (p, n, dot | q) tuple + dist2 bits appended to the CTA's segment
+//   dist2 >  win_hi : certainly dropped -> counted only
+// and publishes {counts, partial sums, candidate segment}.  After ONE device-wide barrier every CTA reads
+// the 148 counts, checks that the quantile's rank really falls among the candidates, pulls the candidate
+// list (~1 % of the pairs) into shared memory, finds the exact limit there (same value the 3-level radix
+// select returns), adds the candidates below the limit in a fixed order, reduces the per-CTA partials in a
+// fixed order and solves -- redundantly and bit-identically in every CTA.  If the prediction fails (rank
+// outside the window, or a segment overflows) all CTAs take the general path below for that iteration.
+// Buffers are double-buffered on the iteration's parity: a CTA can only be one barrier ahead of another.
+constexpr int kSegCap = 64;     // candidate tuples per CTA
+constexpr int kCandCap = 2048;  // candidates in total (2 per thread after the barrier)
+constexpr size_t kFastCountsOff = 0;                                                        // uint4 [2][kLoopMaxBlocks]
+constexpr size_t kFastPartialsOff = kFastCountsOff + 2 * kLoopMaxBlocks * sizeof(uint4);    // double [2][kLoopMaxBlocks][kAccSlots]
+constexpr size_t kFastCandOff = kFastPartialsOff + 2 * (size_t)kLoopMaxBlocks * kAccSlots * sizeof(double);  // float4 [2][kLoopMaxBlocks][kSegCap][2]
+constexpr size_t kFastBytes = kFastCandOff + 2 * (size_t)kLoopMaxBlocks * kSegCap * 2 * sizeof(float4);
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -54,6 +94,20 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch)
         __threadfence();
     }
     __syncthreads();
+}
+
+// s_cnt32[w] = count of warp w (written before the preceding __syncthreads): returns the sum over the warps before `warp`
+// and the block total.  One shared load + a 5-step shuffle scan per thread.
+__device__ __forceinline__ void block_prefix32(const uint32_t* s_cnt32, int lane, int warp, uint32_t& before, uint32_t& total) {
+    const uint32_t v = s_cnt32[lane];
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += u;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    before = __shfl_sync(0xffffffffu, incl - v, warp);
 }
 
 // Block-wide (kLoopThreads threads): smallest bin with cumulative count > rank (see icp.cu select_pick).
@@ -80,12 +134,7 @@ __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bo
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kLoopWarps; ++w) {
-        const uint32_t v = s_warp[w];
-        if (w < warp) before += v;
-        total += v;
-    }
+    block_prefix32(s_warp, lane, warp, before, total);
     incl += before;
     if (rank_is_fraction) {
         rank = (q == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * q);
@@ -108,12 +157,168 @@ __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bo
     return total;
 }
 
-template <int MIN, int kLoopG /* lanes per query in the warm search */>
+// Product of the weights of every outlier filter EXCEPT the quantile-based one (fast path: that one is
+// decided after the barrier).
+__device__ __forceinline__ float other_filters_weight(const IcpParams& prm, float d) {
+    float w = 1.f;
+    for (int f = 0; f < prm.n_outlier; ++f) {
+        const float p = prm.outlier_param[f];
+        bool keep = true;
+        switch (prm.outlier_kind[f]) {
+            case B200ICP_OUTLIER_MAX_DIST: keep = d <= p * p; break;
+            case B200ICP_OUTLIER_MIN_DIST: keep = d >= p * p; break;
+            default: break;
+        }
+        w *= keep ? 1.f : 0.f;
+    }
+    return w;
+}
+
+// The error-minimiser products of one kept pair (same expressions as accumulate_entry).
+// MIN 0: v = (n.x, n.y, n.z, (p - q).n);  MIN 1: v = (q.x, q.y, q.z, *).
+template <int MIN>
+__device__ __forceinline__ void add_pair(float* acc, float w, const float3& p, const float4& v) {
+    constexpr int NS = SumLayout<MIN>::N;
+    if (MIN == 0) {
+        float F[6];
+        F[0] = p.y * v.z - p.z * v.y;
+        F[1] = p.z * v.x - p.x * v.z;
+        F[2] = p.x * v.y - p.y * v.x;
+        F[3] = v.x;
+        F[4] = v.y;
+        F[5] = v.z;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const float wf = w * F[c];
+#pragma unroll
+            for (int r = 0; r <= c; ++r) acc[c * (c + 1) / 2 + r] += wf * F[r];
+            acc[21 + c] -= wf * v.w;
+        }
+    } else if (MIN == 1) {
+        const float pv[3] = {p.x, p.y, p.z}, qv[3] = {v.x, v.y, v.z};
+        acc[0] += w;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            acc[1 + c] += w * pv[c];
+            acc[4 + c] += w * qv[c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) acc[7 + c * 3 + r] += w * qv[r] * pv[c];
+        }
+    }
+    acc[NS - 2] += w;
+    acc[NS - 1] += 1.f;
+}
+
+// Ball search of the loop kernel's S phase (4 lanes per query).
+//  phase 1: the 2 x 2 block of (y, z) cell rows nearest to the query, one row per lane -- two cell-table
+//           loads give the row's contiguous run of points -- then a group-wide minimum: this usually
+//           finds the nearest neighbour and tightens the bound a loose previous match gave;
+//  phase 2: whatever other rows the tightened ball still touches (usually none), lane-strided.
+// Unlike search_ball (knn_device.cuh) the covered radius is sqrt(min(best, tau0)) + m instead of
+// sqrt(best): on return every map point within that radius of the query has been looked at, so besides
+// the exact nearest neighbour (bd, bp per lane; ties: lowest position) the lanes also know sd = the
+// smallest squared distance to any OTHER point seen.  bp / bd come in as the previous match (or -1 / inf)
+// in every lane.
+__device__ __forceinline__ void test_point(float qx, float qy, float qz, const float4& p, uint32_t j, float& bd, int& bp, float& sd) {
+    const float dd = dist2_exact(qx, qy, qz, p);
+    if (dd < bd || (dd == bd && j < (uint32_t)bp)) {
+        sd = bd;  // sd >= bd always: the dethroned best becomes the second
+        bd = dd;
+        bp = (int)j;
+    } else {
+        sd = fminf(sd, dd);
+    }
+}
+
+// run of points [s, e) of the cells [xa, xb] of row (y, z) that a ball of squared radius cov2 around the query can touch
+__device__ __forceinline__ void row_run(const GridView& g, float ux, float slack, int y, int z, float gyz2, float cov2, uint32_t& s, uint32_t& e) {
+    const float rx = fminf(sqrtf(fmaxf(cov2 - gyz2, 0.f)) * g.inv_h + slack, 3.0e8f);
+    const int xa = max(0, floor_to_int(fmaxf(ux - rx, -1.f)));
+    const int xb = min(g.nx - 1, floor_to_int(fminf(ux + rx, (float)g.nx)));
+    if (xa > xb) return;
+    const uint32_t* row = g.cell_start + ((size_t)z * g.ny + y) * (size_t)g.nx;
+    s = __ldg(row + xa);
+    e = __ldg(row + xb + 1);
+}
+
+__device__ __forceinline__ float row_gap2(const GridView& g, float uy, float uz, float slack, int y, int z) {
+    float gy = fmaxf(fmaxf((float)y - uy, uy - (float)(y + 1)), 0.f);
+    float gz = fmaxf(fmaxf((float)z - uz, uz - (float)(z + 1)), 0.f);
+    gy = fmaxf(gy - slack, 0.f) * g.h;
+    gz = fmaxf(gz - slack, 0.f) * g.h;
+    return gy * gy + gz * gz;
+}
+
+// bd / bp / sd start at inf / -1 / inf in every lane: the previous match only bounds the ball (tau0) and is found
+// again by the scan like any other point.
+__device__ __forceinline__ void search_ball4(const GridView& g, float qx, float qy, float qz, float tau0, float m, float& bd, int& bp,
+                                             float& sd, int lig, unsigned gmask) {
+    constexpr int G = 4;
+    const float lim = 1.0e8f;
+    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
+    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
+    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
+    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+    // phase 1: own row, the nearer y neighbour, the nearer z neighbour, and the diagonal
+    const int cy = floor_to_int(uy), cz = floor_to_int(uz);
+    const int y1 = (uy - (float)cy >= 0.5f) ? cy + 1 : cy - 1;
+    const int z1 = (uz - (float)cz >= 0.5f) ? cz + 1 : cz - 1;
+    float gb = tau0;  // group-uniform bound on the final best distance
+    {
+        const int y = (lig & 1) ? y1 : cy, z = (lig & 2) ? z1 : cz;
+        uint32_t s = 0, e = 0;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+            const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
+            const float cov = sqrtf(gb) + m;
+            if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
+        }
+        // the four runs, concatenated, are scanned by the four lanes together (balanced, 64-byte coalesced)
+        const uint32_t n = e - s;
+        const uint32_t n0 = __shfl_sync(gmask, n, 0, G), n1 = __shfl_sync(gmask, n, 1, G), n2 = __shfl_sync(gmask, n, 2, G),
+                       n3 = __shfl_sync(gmask, n, 3, G);
+        const uint32_t p1 = n0, p2 = p1 + n1, p3 = p2 + n2, N = p3 + n3;
+        const uint32_t o0 = __shfl_sync(gmask, s, 0, G), o1 = __shfl_sync(gmask, s, 1, G) - p1, o2 = __shfl_sync(gmask, s, 2, G) - p2,
+                       o3 = __shfl_sync(gmask, s, 3, G) - p3;
+#pragma unroll 2
+        for (uint32_t k = (uint32_t)lig; k < N; k += G) {
+            const uint32_t j = k + (k >= p2 ? (k >= p3 ? o3 : o2) : (k >= p1 ? o1 : o0));
+            test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
+        }
+        float v = bd;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
+        gb = fminf(v, tau0);
+    }
+    // phase 2: the rest of the (tightened) ball's cover -- usually nothing
+    const float rt = fminf((sqrtf(gb) + m) * g.inv_h + slack, 3.0e8f);
+    const int ylo = max(0, floor_to_int(fmaxf(uy - rt, -1.f)));
+    const int yhi = min(g.ny - 1, floor_to_int(fminf(uy + rt, (float)g.ny)));
+    const int zlo = max(0, floor_to_int(fmaxf(uz - rt, -1.f)));
+    const int zhi = min(g.nz - 1, floor_to_int(fminf(uz + rt, (float)g.nz)));
+    const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
+    if (wy <= 0 || wz <= 0) return;
+    if (ylo >= min(cy, y1) && yhi <= max(cy, y1) && zlo >= min(cz, z1) && zhi <= max(cz, z1)) return;  // inside the 2 x 2 block
+    const int nrows = wy * wz;
+    for (int r = lig; r < nrows; r += G) {
+        const int y = ylo + r % wy, z = zlo + r / wy;
+        if ((y == cy || y == y1) && (z == cz || z == z1)) continue;  // done in phase 1
+        const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
+        const float cov = sqrtf(fminf(bd, gb)) + m;  // this lane's covered radius from here on (never below the final one)
+        if (gyz2 > cov * cov) continue;
+        uint32_t s = 0, e = 0;
+        row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
+#pragma unroll 4
+        for (uint32_t j = s; j < e; ++j) test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
+    }
+}
+
+template <int MIN>
 __global__ void __launch_bounds__(kLoopThreads, 1)
     icp_loop_kernel(IcpParams prm, GridView g, const float4* __restrict__ nrm, const float4* __restrict__ reading,
                     int32_t* __restrict__ mpos, float* __restrict__ md2, IcpState* __restrict__ gst, uint32_t* __restrict__ hist,
                     double* __restrict__ partials, unsigned* __restrict__ bar_counter, float* __restrict__ trace, int max_iters,
-                    int variant_flags) {
+                    int variant_flags, char* __restrict__ fastws, float win_gain, float win_floor, float win_max,
+                    float4* __restrict__ sp_pp, float4* __restrict__ sp_nv, float margin_gain, float margin_min, float margin_max) {
     constexpr int NS = SumLayout<MIN>::N;
     __shared__ IcpState st;
     __shared__ uint32_t sh[kSel0Bins];   // radix level 0 histogram, then staging / the candidate list
@@ -124,6 +329,16 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     __shared__ double s_red[kLoopWarps][kAccSlots];
     __shared__ double s_sum[kAccSlots];
     __shared__ float s_scratch[16];
+    __shared__ uint32_t s_off[kLoopMaxBlocks + 1];  // fast path: exclusive prefix of the per-CTA candidate counts
+    __shared__ uint32_t s_tot[4];                   // fast path: totals {below, candidates, above, max candidates per CTA}
+    __shared__ float s_Tprev[16];                   // T_iter the bounds L of the match cache refer to
+    __shared__ uint32_t s_nlist;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    float4* const s_r4 = reinterpret_cast<float4*>(dyn_smem);
+    float4* const s_pp = s_r4 + kCacheCap;   // (x, y, z, bit-cast position) of the matched map point
+    float4* const s_nv = s_pp + kCacheCap;   // (normal of the matched point, bound L)
+    float* const s_d2 = reinterpret_cast<float*>(s_nv + kCacheCap);
+    uint32_t* const s_list = reinterpret_cast<uint32_t*>(s_d2 + kCacheCap);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < (int)(sizeof(IcpState) / 4); i += kLoopThreads)
@@ -134,7 +349,41 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const bool use_quantile = prm.quantile_filter >= 0;
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
-    constexpr int kPerSweep = kLoopThreads / kLoopG;  // queries per CTA per sweep
+    constexpr int kPerSweep = kChunk;  // the general path walks this CTA's chunks
+    // entries of this CTA: entry e <-> reading point qi_of(e); contiguous because only the globally last chunk is partial
+    int n_ent = 0;
+    {
+        const long long chunks_total = ((long long)nq + kChunk - 1) / kChunk;
+        if ((long long)blockIdx.x < chunks_total) {
+            const long long mine = (chunks_total - 1 - blockIdx.x) / gridDim.x + 1;
+            n_ent = (int)(mine * kChunk);
+            if ((long long)blockIdx.x + (mine - 1) * gridDim.x == chunks_total - 1) n_ent -= (int)(chunks_total * kChunk - nq);
+        }
+    }
+    auto qi_of = [&](int e) -> long long { return ((long long)(e / kChunk) * gridDim.x + blockIdx.x) * kChunk + (e % kChunk); };
+    // match cache <- the cold search's matches (bound L = 0: nothing proven yet)
+    for (int e = tid; e < n_ent; e += kLoopThreads) {
+        const long long qi = qi_of(e);
+        const int pos = mpos[qi];
+        float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), nn = pt;
+        if (pos >= 0) {
+            pt = __ldg(g.pts + pos);
+            if (MIN == 0) nn = __ldg(nrm + pos);
+        }
+        pt.w = __int_as_float(pos);
+        nn.w = 0.f;
+        if (e < kCacheCap) {
+            s_r4[e] = __ldg(reading + qi);
+            s_pp[e] = pt;
+            s_nv[e] = nn;
+            s_d2[e] = md2[qi];
+        } else {
+            sp_pp[qi] = pt;
+            sp_nv[qi] = nn;
+        }
+    }
+    if (tid < 16) s_Tprev[tid] = st.T[tid];
+    __syncthreads();
 
     for (int it = 0; it < max_iters; ++it) {
         if (st.done) break;  // identical in every CTA
@@ -146,68 +395,463 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_iter0));
             if (it == 0) st.loop_total_ns = t_iter0;  // start mark, turned into a duration at the end
         }
-        if (use_quantile) {
+        // one-barrier iteration possible?  (identical decision in every CTA)
+        const bool attempt_fast = !(variant_flags & 16) && (use_quantile ? (searched && st.win_valid != 0) : true);
+        const bool fuse_hist = use_quantile && !attempt_fast;
+        if (fuse_hist) {
             for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
             __syncthreads();
         }
-        // ---- correspondence search (iteration 0 was done by the cold kernel) ----------------------
-        if (st.iter > 0) {
-            for (long long base = (long long)blockIdx.x * kPerSweep; base < nq; base += (long long)gridDim.x * kPerSweep) {
-                const long long qi = base + tid / kLoopG;
-                if (qi < nq) {
-                    const float4 q4 = __ldg(reading + qi);
-                    const int prev = mpos[qi];
-                    const float3 q = apply_T(st.T, q4);
-                    float bd = CUDART_INF_F;
-                    int bp = -1;
-                    const bool finite_q = (fabsf(q.x) < 3.0e38f) && (fabsf(q.y) < 3.0e38f) && (fabsf(q.z) < 3.0e38f);
-                    if (finite_q) {
-                        float tau = prm.max_r2;
-                        if (prev >= 0) {
-                            const float dprev = dist2_exact(q.x, q.y, q.z, __ldg(g.pts + prev));
-                            if (dprev <= prm.max_r2) {
-                                tau = dprev;
-                                bd = dprev;
-                                bp = prev;
-                            }
+        // ---- V / S / C over this CTA's entries, 1024 at a time (one block unless nq > 148 * 1024) -------------------
+        const int par = it & 1;
+        uint4* my_counts = reinterpret_cast<uint4*>(fastws + kFastCountsOff) + (size_t)par * kLoopMaxBlocks;
+        double* my_partials = reinterpret_cast<double*>(fastws + kFastPartialsOff) + (size_t)par * kLoopMaxBlocks * kAccSlots;
+        float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kLoopMaxBlocks * kSegCap * 2;
+        const uint32_t wlo = use_quantile ? st.win_lo : 0xffffffffu, whi = use_quantile ? st.win_hi : 0xffffffffu;
+        const bool verify = !(variant_flags & 32);
+        uint32_t c_below = 0, c_above = 0;
+        uint32_t seg_count = 0;  // uniform: candidates of this CTA so far
+        if (tid < 4) s_tot[tid] = 0u;
+        if (attempt_fast && lane < NS) s_part[warp][lane] = 0.0;
+        unsigned long long t_search = 0;  // CTA 0, thread 0: time spent in V + S
+        for (int e0 = 0; e0 < n_ent; e0 += kLoopThreads) {
+            const int e = e0 + tid;
+            const bool have = e < n_ent;
+            const bool cached = e < kCacheCap;
+            const long long qi = have ? qi_of(e) : 0;
+            bool listed = false;
+            unsigned long long t_s0 = 0;
+            if (searched) {
+                if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_s0));
+                // V: is the previous match still provably the nearest neighbour?  (shared memory only)
+                if (have) {
+                    const float4 r4 = cached ? s_r4[e] : __ldg(reading + qi);
+                    float4* ppp = cached ? s_pp + e : sp_pp + qi;
+                    float4* pnv = cached ? s_nv + e : sp_nv + qi;
+                    float* pd2 = cached ? s_d2 + e : md2 + qi;
+                    const float3 qn = apply_T(st.T, r4), qo = apply_T(s_Tprev, r4);
+                    const float4 pp = *ppp;
+                    const int pos = __float_as_int(pp.w);
+                    const float L = pnv->w;
+                    const bool finite_q = (fabsf(qn.x) < 3.0e38f) && (fabsf(qn.y) < 3.0e38f) && (fabsf(qn.z) < 3.0e38f);
+                    if (!finite_q) {  // NaN / inf reading point: never matched
+                        ppp->w = __int_as_float(-1);
+                        *pd2 = CUDART_INF_F;
+                    } else if (!(pos < 0 && prm.max_r2 == CUDART_INF_F)) {  // (unbounded search that found nothing: the map is empty)
+                        const float ddx = qn.x - qo.x, ddy = qn.y - qo.y, ddz = qn.z - qo.z;
+                        const float delta = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+                        const float d2n = pos >= 0 ? dist2_exact(qn.x, qn.y, qn.z, pp) : CUDART_INF_F;
+                        const float dn = pos >= 0 ? sqrtf(d2n) : sqrtf(prm.max_r2);
+                        const float slack = 2e-6f * (dn + delta + L);
+                        const float Lnew = L - delta - slack;  // still a lower bound for every other point, now around the moved query
+                        if (verify && (pos < 0 || d2n <= prm.max_r2) && dn + slack < Lnew) {
+                            pnv->w = Lnew;
+                            *pd2 = d2n;  // inf when there is (still) no neighbour within maxDist
+                        } else {
+                            listed = true;
                         }
-                        if (tau < CUDART_INF_F) search_ball<kLoopG>(g, q.x, q.y, q.z, tau, bd, bp, lig);
-                    }
-#pragma unroll
-                    for (int o = kLoopG / 2; o > 0; o >>= 1) {
-                        const float od = __shfl_xor_sync(gmask, bd, o);
-                        const int op = __shfl_xor_sync(gmask, bp, o);
-                        if (od < bd || (od == bd && (unsigned)op < (unsigned)bp)) {
-                            bd = od;
-                            bp = op;
-                        }
-                    }
-                    if (!(bd <= prm.max_r2)) {
-                        bd = CUDART_INF_F;
-                        bp = -1;
-                    }
-                    if (lig == 0) {
-                        mpos[qi] = bp;
-                        md2[qi] = bd;
-                        if (use_quantile && bd < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(bd) >> kSel0Shift], 1u);  // radix level 0
                     }
                 }
+                // ordered work list (neighbouring groups get neighbouring queries)
+                const unsigned bal = __ballot_sync(0xffffffffu, listed);
+                if (lane == 0) s_warp[warp] = __popc(bal);
+                if (tid == 0) s_nlist = 0u;  // cursor of the S phase
+                __syncthreads();
+                uint32_t before = 0, n_list = 0;
+                block_prefix32(s_warp, lane, warp, before, n_list);
+                if (listed) s_list[before + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
+                __syncthreads();
+                if (tid == 0 && n_list) atomicAdd(&hist[kHistStat], n_list);
+                if (stamper) B200_STAMP(gst, 17);
+                // S: exact ball search for the listed queries, kLoopG lanes each.  The 8 groups of a warp walk the list in
+                // lockstep (warp-uniform trip count, reconvergence every round): a warp then issues the LONGEST of its
+                // groups' instruction paths per round, not their sum -- this phase is issue-bound, not memory-bound.
+                // Batches of 8 consecutive list entries are handed to whole warps dynamically (difficulty is spatially
+                // coherent, a static deal leaves the CTA waiting for its unluckiest warp).
+                while (true) {
+                    uint32_t i0 = 0;
+                    if (lane == 0) i0 = atomicAdd(&s_nlist, 32u / kLoopG);
+                    i0 = __shfl_sync(0xffffffffu, i0, 0);
+                    if (i0 >= n_list) break;  // warp-uniform
+                    const uint32_t i = i0 + (uint32_t)(lane / kLoopG);
+                    if (i < n_list) {
+                    const int es = (int)s_list[i];
+                    const bool cs = es < kCacheCap;
+                    const long long qs = qi_of(es);
+                    const float4 r4 = cs ? s_r4[es] : __ldg(reading + qs);
+                    float4* ppp = cs ? s_pp + es : sp_pp + qs;
+                    float4* pnv = cs ? s_nv + es : sp_nv + qs;
+                    float* pd2 = cs ? s_d2 + es : md2 + qs;
+                    const float3 qn = apply_T(st.T, r4), qo = apply_T(s_Tprev, r4);
+                    const float4 pp = *ppp;
+                    const int pos = __float_as_int(pp.w);
+                    const float ddx = qn.x - qo.x, ddy = qn.y - qo.y, ddz = qn.z - qo.z;
+                    const float delta = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+                    const float d2n = pos >= 0 ? dist2_exact(qn.x, qn.y, qn.z, pp) : CUDART_INF_F;
+                    const bool valid_prev = pos >= 0 && d2n <= prm.max_r2;
+                    const float tau0 = valid_prev ? d2n : prm.max_r2;  // finite: V never lists (no previous match, unbounded maxDist)
+                    // margin: worth paying only when the next motion is likely to stay inside it
+                    const float want = margin_gain * delta;
+                    const float m = want <= margin_max ? fmaxf(want, margin_min) : 0.f;
+                    float bd = CUDART_INF_F, sd = CUDART_INF_F;
+                    int bp = -1;
+                    search_ball4(g, qn.x, qn.y, qn.z, tau0, m, bd, bp, sd, lig, gmask);
+                    float gbd = bd;
+                    int gbp = bp;
+#pragma unroll
+                    for (int o = kLoopG / 2; o > 0; o >>= 1) {
+                        const float od = __shfl_xor_sync(gmask, gbd, o);
+                        const int op = __shfl_xor_sync(gmask, gbp, o);
+                        if (od < gbd || (od == gbd && (unsigned)op < (unsigned)gbp)) {
+                            gbd = od;
+                            gbp = op;
+                        }
+                    }
+                    float gsd = (bp != gbp) ? bd : sd;  // a lane whose best lost is looking at another point (and bd <= sd)
+#pragma unroll
+                    for (int o = kLoopG / 2; o > 0; o >>= 1) gsd = fminf(gsd, __shfl_xor_sync(gmask, gsd, o));
+                    const float cover = sqrtf(fminf(gbd, tau0)) + m;  // every lane covered at least this radius
+                    if (!(gbd <= prm.max_r2)) {  // nothing within maxDist: whatever was seen beyond it is an "other" point
+                        gsd = fminf(gsd, gbd);
+                        gbd = CUDART_INF_F;
+                        gbp = -1;
+                    }
+                    if (lig == 0) {
+                        float L = fminf(sqrtf(gsd), cover);
+                        L -= 2e-6f * L;
+                        // position only: coordinates and normal of a NEW match are fetched by the classify pass
+                        // (thread per entry, one round trip for all of them); -(pos + 2) marks them stale
+                        ppp->w = __int_as_float((gbp >= 0 && gbp != pos) ? -(gbp + 2) : gbp);
+                        pnv->w = L;
+                        *pd2 = gbd;
+                    }
+                    }
+                    __syncwarp();
+                }
+                if (stamper) B200_STAMP(gst, 18);
+                if (blockIdx.x == 0 && tid == 0) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    t_search += t1 - t_s0;
+                }
+            }
+            if (attempt_fast) {
+                // C: outlier weights + error sums of what is certain + candidate tuples.  Entries that did not need a
+                // search go first (their warps do not wait for the searching warps), the searched ones after the sync.
+                float acc[NS];
+#pragma unroll
+                for (int i = 0; i < NS; ++i) acc[i] = 0.f;
+                bool is_cand = false;
+                float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+                auto classify = [&]() {
+                    float4 pp = cached ? s_pp[e] : sp_pp[qi];
+                    float4 nv = cached ? s_nv[e] : sp_nv[qi];
+                    const float d = cached ? s_d2[e] : md2[qi];
+                    int pos = __float_as_int(pp.w);
+                    if (pos <= -2) {  // new match from the search phase: fetch its coordinates and normal
+                        pos = -(pos + 2);
+                        pp = __ldg(g.pts + pos);
+                        pp.w = __int_as_float(pos);
+                        if (MIN == 0) {
+                            const float4 nn = __ldg(nrm + pos);
+                            nv = make_float4(nn.x, nn.y, nn.z, nv.w);
+                        }
+                        if (cached) {
+                            s_pp[e] = pp;
+                            s_nv[e] = nv;
+                        } else {
+                            sp_pp[qi] = pp;
+                            sp_nv[qi] = nv;
+                        }
+                    }
+                    if (pos >= 0 && d < CUDART_INF_F) {
+                        const uint32_t bits = __float_as_uint(d);
+                        const int cls = bits < wlo ? 0 : (bits <= whi ? 1 : 2);
+                        c_below += cls == 0;
+                        c_above += cls == 2;
+                        if (cls != 2) {
+                            const float wo = other_filters_weight(prm, d);
+                            float3 p = make_float3(CUDART_NAN_F, 0.f, 0.f);
+                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (wo != 0.f) {
+                                p = apply_T(st.T, cached ? s_r4[e] : __ldg(reading + qi));
+                                if (MIN == 0)
+                                    v = make_float4(nv.x, nv.y, nv.z, (p.x - pp.x) * nv.x + (p.y - pp.y) * nv.y + (p.z - pp.z) * nv.z);
+                                else
+                                    v = pp;
+                                if (cls == 0) add_pair<MIN>(acc, wo, p, v);
+                            }
+                            if (cls == 1) {  // a candidate dropped by another filter still takes part in the quantile: p.x = NaN marks it
+                                is_cand = true;
+                                ta = make_float4(p.x, p.y, p.z, __uint_as_float(bits));
+                                tb = v;
+                            }
+                        }
+                    }
+                };
+                if (have && !listed) classify();
+                if (searched) __syncthreads();  // the search results of this block are in the cache
+                if (have && listed) classify();
+                if (use_quantile) {  // ordered (deterministic) compaction of this block's candidates into the CTA's segment
+                    const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
+                    if (lane == 0) s_warp[warp] = __popc(bal);
+                    __syncthreads();
+                    uint32_t before = 0, total = 0;
+                    block_prefix32(s_warp, lane, warp, before, total);
+                    if (is_cand) {
+                        const uint32_t slot = seg_count + before + __popc(bal & ((1u << lane) - 1u));
+                        if (slot < (uint32_t)kSegCap) {
+                            float4* dst = my_cand + ((size_t)blockIdx.x * kSegCap + slot) * 2;
+                            __stcg(dst, ta);
+                            __stcg(dst + 1, tb);
+                        }
+                    }
+                    seg_count += total;
+                    __syncthreads();
+                }
+                // this block's sums -> the warp's running partial (fp64 from here on)
+                float v32[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc[i] : 0.f;
+                const float tot = warp_reduce_32slots(v32, lane);
+                if (lane < NS) s_part[warp][lane] += (double)tot;
+            } else if (searched) {
+                __syncthreads();
+                if (stamper) B200_STAMP(gst, 19);
             }
         }
-        __syncthreads();  // this CTA's matches are written before any of its threads reads them
+        if (searched && tid < 16) s_Tprev[tid] = st.T[tid];  // the bounds now refer to this iteration's query positions
+        __syncthreads();
         if (blockIdx.x == 0 && tid == 0 && searched) {
-            unsigned long long t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            st.loop_search_ns += t1 - t_iter0;
+            st.loop_search_ns += t_search;
             st.loop_iters_timed += 1;
         }
         if (stamper) B200_STAMP(gst, 21);
-        // ---- exact quantile of the finite distances (LPM Matches::getDistsQuantile) -------------------
         float qlimit = 0.f;
+        bool fast_done = false;
+        uint32_t dbg_path = 0, dbg_ncand = 0, dbg_nbelow = 0;  // development record (CTA 0)
+        bool hist_ready = fuse_hist;  // level-0 histogram filled by the pre-pass below
+        if (!attempt_fast) {
+            // general path: matches -> global memory (it walks mpos / md2), level-0 histogram of the quantile on the way
+            for (int e = tid; e < n_ent; e += kLoopThreads) {
+                const long long qi = qi_of(e);
+                const bool cached = e < kCacheCap;
+                float4* ppp = cached ? s_pp + e : sp_pp + qi;
+                int pos = __float_as_int(ppp->w);
+                if (pos <= -2) {  // new match from the search phase: fetch its coordinates and normal
+                    pos = -(pos + 2);
+                    float4 pt = __ldg(g.pts + pos);
+                    pt.w = __int_as_float(pos);
+                    *ppp = pt;
+                    if (MIN == 0) {
+                        float4* pnv = cached ? s_nv + e : sp_nv + qi;
+                        const float4 nn = __ldg(nrm + pos);
+                        *pnv = make_float4(nn.x, nn.y, nn.z, pnv->w);
+                    }
+                }
+                const float d = cached ? s_d2[e] : md2[qi];
+                mpos[qi] = pos;
+                md2[qi] = d;
+                if (fuse_hist && pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
+            }
+            __syncthreads();
+        }
+        if (attempt_fast) {
+            // ---- publish, ONE barrier, finish redundantly ---------------------------------------------
+            if (stamper) B200_STAMP(gst, 28);
+            {
+                uint32_t a = c_below, c = c_above;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                }
+                if (lane == 0) {
+                    if (a) atomicAdd(&s_tot[0], a);
+                    if (c) atomicAdd(&s_tot[2], c);
+                }
+            }
+            __syncthreads();
+            if (tid < kAccSlots) {
+                double v = 0.0;
+                if (tid < NS) {
+#pragma unroll
+                    for (int wv = 0; wv < kLoopWarps; ++wv) v += s_part[wv][tid];
+                }
+                __stcg(my_partials + (size_t)blockIdx.x * kAccSlots + tid, v);
+            }
+            if (tid == 0) __stcg(my_counts + blockIdx.x, make_uint4(s_tot[0], seg_count, s_tot[2], 0u));
+            if (stamper) B200_STAMP(gst, 22);
+            grid_barrier(bar_counter, epoch);
+            if (stamper) B200_STAMP(gst, 23);
+            // ---- after the barrier: identical work in every CTA ---------------------------------------
+            const int nblk = (int)gridDim.x;
+            {
+                uint4 c = make_uint4(0u, 0u, 0u, 0u);
+                if (tid < nblk) c = __ldcg(my_counts + tid);
+                uint32_t incl = c.y, sb = c.x, sa = c.z, mx = c.y;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += v;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                if (tid < 4) s_tot[tid] = 0u;
+                if (lane == 31) s_warp[warp] = incl;
+                __syncthreads();
+                uint32_t before = 0;
+                for (int w = 0; w < warp; ++w) before += s_warp[w];
+                if (tid < nblk) s_off[tid] = before + incl - c.y;
+                if (tid == nblk - 1) s_off[nblk] = before + incl;
+                if (lane == 0 && warp * 32 < nblk) {
+                    atomicAdd(&s_tot[0], sb);
+                    atomicAdd(&s_tot[2], sa);
+                    atomicMax(&s_tot[3], mx);
+                }
+                __syncthreads();
+            }
+            if (stamper) B200_STAMP(gst, 29);
+            const uint32_t n_below = s_tot[0], n_cand = s_off[nblk], n_above = s_tot[2], seg_max = s_tot[3];
+            const uint32_t total = n_below + n_cand + n_above;
+            uint32_t rank = 0;
+            bool ok = true;
+            if (use_quantile) {
+                rank = (prm.quantile == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * prm.quantile);
+                if (total && rank >= total) rank = total - 1u;
+                ok = total > 0 && seg_max <= (uint32_t)kSegCap && n_cand <= (uint32_t)kCandCap && rank >= n_below && rank < n_below + n_cand;
+            }
+            dbg_path = ok ? 1u : 2u;
+            dbg_ncand = n_cand;
+            dbg_nbelow = n_below;
+            if (ok) {
+                // the per-CTA partial sums do not depend on the select: fetch them now, add them after it
+                double pv[(kLoopMaxBlocks + kLoopWarps - 1) / kLoopWarps];
+#pragma unroll
+                for (int j = 0; j < (kLoopMaxBlocks + kLoopWarps - 1) / kLoopWarps; ++j) {
+                    const int bq = warp + j * kLoopWarps;
+                    pv[j] = bq < nblk ? __ldcg(my_partials + (size_t)bq * kAccSlots + lane) : 0.0;
+                }
+                float acc2[NS];
+#pragma unroll
+                for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
+                if (use_quantile) {
+                    // candidates -> registers (<= 2 tuples per thread; .w of the first half = dist2 bits)
+                    float4 ca[2], cb[2];
+                    bool have[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t pos = (uint32_t)tid + (uint32_t)j * kLoopThreads;
+                        have[j] = pos < n_cand;
+                        ca[j] = cb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (have[j]) {
+                            int lo = 0, hi = nblk;  // segment with s_off[seg] <= pos < s_off[seg + 1]
+                            while (hi - lo > 1) {
+                                const int mid = (lo + hi) >> 1;
+                                if (s_off[mid] <= pos) lo = mid; else hi = mid;
+                            }
+                            const float4* src = my_cand + ((size_t)lo * kSegCap + (pos - s_off[lo])) * 2;
+                            ca[j] = __ldcg(src);
+                            cb[j] = __ldcg(src + 1);
+                        }
+                    }
+                    const uint32_t W = whi - wlo;  // < 2^30 (window construction)
+                    uint32_t r = rank - n_below, prefix = 0;
+                    const bool small_set = n_cand <= 128u;
+                    if (small_set) {
+                        // few candidates: every candidate counts how many precede it (ties: list order); the one whose
+                        // count equals the rank is the quantile.  Two block syncs instead of five per radix level.
+                        if (have[0]) sh2[tid] = __float_as_uint(ca[0].w);
+                        __syncthreads();
+                        if (have[0]) {
+                            const uint32_t mine = __float_as_uint(ca[0].w);
+                            uint32_t less = 0;
+                            for (uint32_t i = 0; i < n_cand; ++i) {
+                                const uint32_t o = sh2[i];
+                                less += (o < mine) || (o == mine && i < (uint32_t)tid);
+                            }
+                            if (less == r) s_bin = mine - wlo;
+                        }
+                        __syncthreads();
+                        prefix = s_bin;
+                        __syncthreads();
+                    }
+#pragma unroll 1
+                    for (int shift = small_set ? -1 : 20; shift >= 0; shift -= 10) {
+                        if (shift > 0 && (W >> shift) == 0u) continue;
+                        sh2[tid] = 0u;
+                        if (tid == 0) {
+                            s_bin = 0;
+                            s_res = 0;
+                        }
+                        __syncthreads();
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            if (have[j]) {
+                                const uint32_t o = __float_as_uint(ca[j].w) - wlo;
+                                if (((o ^ prefix) >> (shift + 10)) == 0u) atomicAdd(&sh2[(o >> shift) & 1023u], 1u);
+                            }
+                        }
+                        __syncthreads();
+                        loop_pick<true>(sh2, 1024, r, false, 0.f, &s_bin, &s_res, &s_cnt, s_warp);
+                        r = s_res;
+                        prefix |= s_bin << shift;
+                        __syncthreads();
+                    }
+                    const uint32_t limit_bits = wlo + prefix;
+                    qlimit = __uint_as_float(limit_bits);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (have[j] && __float_as_uint(ca[j].w) <= limit_bits && ca[j].x == ca[j].x)
+                            add_pair<MIN>(acc2, 1.f, make_float3(ca[j].x, ca[j].y, ca[j].z), cb[j]);
+                    }
+                }
+                if (stamper) B200_STAMP(gst, 27);
+                // fixed-order reduction: candidates' warp totals + the per-CTA partials, identical in every CTA
+                {
+                    float v32[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc2[i] : 0.f;
+                    const float tot = use_quantile ? warp_reduce_32slots(v32, lane) : 0.f;
+                    const int slot = lane, part = warp;
+                    double v = (double)tot;
+#pragma unroll
+                    for (int j = 0; j < (kLoopMaxBlocks + kLoopWarps - 1) / kLoopWarps; ++j) v += pv[j];
+                    s_red[part][slot] = v;
+                }
+                __syncthreads();
+                if (tid < kAccSlots) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int part = 0; part < kLoopWarps; ++part) v += s_red[part][tid];
+                    s_sum[tid] = v;
+                }
+                __syncthreads();
+                if (stamper) B200_STAMP(gst, 13);
+                fast_done = true;
+                if (tid == 0) st.fast_iters += 1;
+            } else if (use_quantile) {
+                // prediction failed: general path; it walks mpos / md2 in global memory
+                for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
+                for (int e = tid; e < n_ent; e += kLoopThreads) {
+                    const long long qi = qi_of(e);
+                    const bool cached = e < kCacheCap;
+                    mpos[qi] = __float_as_int(cached ? s_pp[e].w : sp_pp[qi].w);
+                    if (cached) md2[qi] = s_d2[e];
+                }
+                __syncthreads();
+                hist_ready = false;
+            }
+        }
+        // ---- exact quantile of the finite distances (LPM Matches::getDistsQuantile) -------------------
         bool fallback_used = false;
-        if (use_quantile) {
+        if (use_quantile && !fast_done) {
             // level 0: histogram of bits [30:19] over this CTA's slice (already done while searching)
-            if (!searched) {
+            if (!hist_ready) {
                 for (long long sweep = tid / kPerSweep;; sweep += kLoopThreads / kPerSweep) {
                     const long long base = (sweep * gridDim.x + blockIdx.x) * kPerSweep;
                     if (base >= nq) break;
@@ -344,6 +988,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             qlimit = __uint_as_float((b1 << kSel0Shift) | low);
         }
         // ---- ErrorElements + error sums over this CTA's slice ----------------------------------------
+        if (!fast_done) {
         float acc[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) acc[i] = 0.f;
@@ -395,9 +1040,39 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         }
         __syncthreads();
         if (stamper) B200_STAMP(gst, 13);
+        }  // !fast_done
         if (tid < 32) {
-            if (tid == 0) st.limit = qlimit;
-            finish_warp(prm, &st, s_sum, NS, blockIdx.x == 0 ? trace : nullptr, s_scratch);
+            if (tid == 0) {
+                // window for the next iteration's one-barrier attempt: centred on this limit, half-width from
+                // the last change of the limit (Trimmed only: Median scales the limit by a factor)
+                const float prev = st.limit;
+                st.win_valid = 0;
+                if (use_quantile && prm.outlier_kind[prm.quantile_filter] == B200ICP_OUTLIER_TRIMMED_DIST && st.have_limit &&
+                    qlimit > 0.f && qlimit < 1.0e30f) {
+                    const float a = fmaxf(win_gain * fabsf(qlimit - prev), win_floor * qlimit);
+                    if (a <= win_max * qlimit) {
+                        st.win_lo = __float_as_uint(fmaxf(qlimit - a, 0.f));
+                        st.win_hi = __float_as_uint(qlimit + a);
+                        st.win_valid = (st.win_hi - st.win_lo) < (1u << 30);
+                    }
+                }
+                st.have_limit = use_quantile ? 1 : 0;
+                st.limit = qlimit;
+            }
+            finish_warp(prm, &st, s_sum, NS, blockIdx.x == 0 ? trace : nullptr, s_scratch, stamper ? gst : nullptr);
+        }
+        if (stamper && it < 256) {  // {path 0 general / 1 one-barrier / 2 failed attempt, limit, candidates, below, searched so far, next window}
+            uint32_t* rec = hist + kHistDebug + it * 8;
+            rec[0] = dbg_path;
+            rec[1] = __float_as_uint(qlimit);
+            rec[2] = dbg_ncand;
+            rec[3] = dbg_nbelow;
+            rec[4] = __ldcg(hist + kHistStat);
+            rec[5] = st.win_valid ? st.win_lo : 0u;
+            rec[6] = st.win_valid ? st.win_hi : 0u;
+            unsigned long long tn;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
+            rec[7] = (uint32_t)(tn - t_iter0);
         }
         __syncthreads();
         if (stamper) B200_STAMP(gst, 14);
@@ -407,6 +1082,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             st.loop_total_ns = t1 - st.loop_total_ns;
+            st.searched_queries = (int)__ldcg(hist + kHistStat);  // every CTA added its share before its last barrier
+            hist[kHistStat] = 0u;
         }
         __syncthreads();
         for (int i = tid; i < (int)(sizeof(IcpState) / 4); i += kLoopThreads)
@@ -414,11 +1091,17 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     }
 }
 
-template <int MIN, int G>
+template <int MIN>
 cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                          int variant_flags, cudaStream_t s) {
+                          int variant_flags, const float* win3, const float* margin3, cudaStream_t s) {
+    static bool attr_set = false;  // per process and instantiation; harmless if repeated
+    if (!attr_set) {
+        cudaError_t ea = cudaFuncSetAttribute(icp_loop_kernel<MIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoopDynSmem);
+        if (ea != cudaSuccess) return ea;
+        attr_set = true;
+    }
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_loop_kernel<MIN, G>, kLoopThreads, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_loop_kernel<MIN>, kLoopThreads, kLoopDynSmem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     const int blocks = std::min(n_sms, kLoopMaxBlocks);
@@ -432,29 +1115,26 @@ cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
     uint32_t* hist = b.hist;
     double* partials = b.partials;
     float* trace = b.trace;
-    void* args[] = {&prm, &view, &nrm, &reading, &mpos, &md2, &st, &hist, &partials, &bar_counter, &trace, &max_iters, &variant_flags};
-    return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN, G>, dim3(blocks), dim3(kLoopThreads), args, 0, s);
-}
-
-template <int MIN>
-cudaError_t launch_loop_g(int variant, const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters,
-                          int n_sms, cudaStream_t s) {
-    switch ((variant >> 8) & 0xf) {  // experimental: lanes per query in the warm search
-        case 1: return launch_loop_t<MIN, 1>(p, g, b, bar_counter, max_iters, n_sms, variant, s);
-        case 2: return launch_loop_t<MIN, 2>(p, g, b, bar_counter, max_iters, n_sms, variant, s);
-        case 8: return launch_loop_t<MIN, 8>(p, g, b, bar_counter, max_iters, n_sms, variant, s);
-        default: return launch_loop_t<MIN, 4>(p, g, b, bar_counter, max_iters, n_sms, variant, s);
-    }
+    char* fastws = b.fastws;
+    float win_gain = win3[0], win_floor = win3[1], win_max = win3[2];
+    float4* sp_pp = b.spill_pp;
+    float4* sp_nv = b.spill_nv;
+    float margin_gain = margin3[0], margin_min = margin3[1], margin_max = margin3[2] * g.view.h;
+    void* args[] = {&prm, &view, &nrm, &reading, &mpos, &md2, &st, &hist, &partials, &bar_counter, &trace, &max_iters, &variant_flags,
+                    &fastws, &win_gain, &win_floor, &win_max, &sp_pp, &sp_nv, &margin_gain, &margin_min, &margin_max};
+    return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN>, dim3(blocks), dim3(kLoopThreads), args, kLoopDynSmem, s);
 }
 
 }  // namespace
 
+size_t icp_loop_workspace_bytes() { return kFastBytes; }
+
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                            int variant, cudaStream_t s) {
-    if (p.knn != 1) return cudaErrorInvalidValue;
-    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE) return launch_loop_g<0>(variant, p, g, b, bar_counter, max_iters, n_sms, s);
-    if (p.minimizer == B200ICP_MIN_POINT_TO_POINT) return launch_loop_g<1>(variant, p, g, b, bar_counter, max_iters, n_sms, s);
-    return launch_loop_g<2>(variant, p, g, b, bar_counter, max_iters, n_sms, s);
+                            int variant, const float* win3, const float* margin3, cudaStream_t s) {
+    if (p.knn != 1 || !b.fastws || !b.spill_pp || !b.spill_nv) return cudaErrorInvalidValue;
+    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE) return launch_loop_t<0>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    if (p.minimizer == B200ICP_MIN_POINT_TO_POINT) return launch_loop_t<1>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    return launch_loop_t<2>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
 }
 
 }  // namespace b200

@@ -6,14 +6,14 @@ import numpy as np
 from norlab_icp_mapper_b200 import synth
 from norlab_icp_mapper_b200.icp import ICP, make_config
 d = synth.make_pair_3d()
-cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
+cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=int(os.environ.get("ITERS", "30")))
 g = ICP(cfg); g.set_map(d["map"], d["normals"])
 names = {0: "sel start", 1: "sel p0 hist", 2: "sel p0 sync", 3: "sel p0 pick", 4: "sel p1 hist", 5: "sel p1 sync", 6: "sel p1 pick",
          7: "sel p2 hist", 8: "sel p2 sync", 9: "sel p2 pick", 10: "sel end", 11: "acc start(b0)", 12: "acc loop done(b0)",
          13: "acc last-block ticket", 14: "acc reduced", 15: "acc finished", 16: "nn start(b0)", 17: "nn end(last block)"}
 if "--loop" in sys.argv:
-    names = {20: "iter start", 21: "nn done", 22: "level-0 hist flushed", 23: "barrier 1", 24: "pick 0", 25: "candidates gathered", 26: "barrier 2",
-             27: "local select done", 31: "acc partial written", 12: "acc barrier", 13: "reduced", 14: "finished"}
+    names = {20: "iter start", 21: "nn done", 22: "published / level-0 hist flushed", 23: "barrier 1", 24: "pick 0", 25: "candidates gathered", 26: "barrier 2",
+             27: "select done", 31: "acc partial written", 12: "acc barrier", 13: "reduced", 14: "finished", 28: "classified", 29: "counts read", 15: "solved", 16: "delta built", 17: "V + list done", 18: "S done (warp 0)", 19: "S done (CTA 0)"}
 for rep in range(3):
     g(d["reading"])
     st = np.zeros(32, np.uint64)
