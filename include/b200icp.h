@@ -117,6 +117,7 @@ typedef struct b200icp_timing {
     float loop_total_ms;      /* ... first iteration start to last iteration end (%globaltimer)        */
     int32_t loop_fast_iterations; /* ... iterations that ran with ONE device-wide barrier (predicted quantile window) */
     int32_t loop_searched_queries; /* ... queries (summed over the iterations) that needed a search; the others were proven unchanged */
+    int32_t loop_two_barrier_iterations; /* ... iterations that ran with TWO barriers (quantile bucket found by a histogram pass) */
 } b200icp_timing;
 
 /* One entry of the YAML `input:` chain (libpointmatcher DataPointsFilters used on this path,

@@ -63,6 +63,7 @@ class Timing(C.Structure):
         ("loop_total_ms", C.c_float),
         ("loop_fast_iterations", C.c_int32),
         ("loop_searched_queries", C.c_int32),
+        ("loop_two_barrier_iterations", C.c_int32),
     ]
 
 

@@ -626,6 +626,7 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     ctx->timing.loop_total_ms = persistent ? (float)(1e-6 * (double)out_state->loop_total_ns) : 0.f;
     ctx->timing.loop_fast_iterations = persistent ? out_state->fast_iters : 0;
     ctx->timing.loop_searched_queries = persistent ? out_state->searched_queries : 0;
+    ctx->timing.loop_two_barrier_iterations = persistent ? out_state->hist_iters : 0;
     ctx->timing.nn_launches = 0;
     const int executed = out_state->iter;
     for (int i = 0; i < nn_timed && i < std::max(executed, 1); ++i) {

@@ -17,7 +17,7 @@ constexpr int kSMs = 148;        // B200
 inline int64_t grow_capacity(int64_t n) { return n * 2 > (int64_t(1) << 20) ? n * 2 : (int64_t(1) << 20); }
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
-constexpr int kHistWords = 16384; // uint32 words of the histogram / candidate-list buffer (layout in loop.cu)
+constexpr int kHistWords = 24576; // uint32 words of the histogram / candidate-list buffer (layout in loop.cu)
 constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)
 constexpr int kAccBlocks = 128;      // accumulate-kernel grid (one partial each, summed in fixed order)
 constexpr int kLoopMaxBlocks = 192;  // persistent loop kernel: one CTA per SM
@@ -63,7 +63,7 @@ struct IcpState {
     uint32_t win_lo, win_hi;
     int win_valid, have_limit;
     int searched_queries;  // queries that went through the search phase (the rest were verified against their bound)
-    int pad2_;
+    int hist_iters;        // iterations that took the two-barrier path (window from a level-0 histogram)
 };
 
 static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");

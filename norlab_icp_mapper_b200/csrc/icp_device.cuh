@@ -111,67 +111,61 @@ __device__ float quat_angular_distance(const float* a, const float* b) {
 }
 
 // LPM PointToPlaneErrorMinimizer::compute_in_place tail: solve, AngleAxis / Rotation2D.
-// Runs on ONE WARP: lane r < 6 owns row r of [A | b] (entries rounded to fp32 like the reference's
-// float matrices), Gauss-Jordan elimination in fp64 with shuffles, everything in registers.  The
-// pivots of the elimination are the squares of the Cholesky diagonal, so the reference's
-// "is A invertible" decision (LLT succeeds) is the same test; the rank-deficient case falls back
-// to the minimum-norm solution on lane 0.  Result: x[6] identical in every lane.
-// 1 / x for a pivot: fp32 reciprocal + one Newton step in fp64 (relative error ~4e-15) -- the full-precision
-// fp64 division is a long dependent sequence and the elimination below needs one per pivot, serially.
-__device__ __forceinline__ double pivot_rcp(double x) {
-    if (!(x > 1e-30 && x < 1e30)) return 1.0 / x;
-    double r = (double)__frcp_rn((float)x);
-    r = fma(r, fma(-x, r, 1.0), r);  // 2^-24 -> 2^-48: far below what the fp32 inputs carry
-    return r;
-}
-
+// A (entries rounded to fp32 like the reference's float matrices) is factored and solved in fp32 the way
+// upstream does it -- Eigen's unblocked LLT, then the two triangular solves -- by every lane of the warp
+// redundantly (no communication; x ends up identical in all lanes).  "A is invertible" is restated as "every
+// pivot of the factorisation exceeds 6 eps max|diag|"; the rank-deficient case falls back to the minimum-norm
+// solution on lane 0.  (An fp64 Gauss-Jordan was measured at 2.2 us per iteration on this dependent chain;
+// the 6x6 system does not need it: upstream itself solves in fp32.)
 __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/) {
-    const unsigned full = 0xffffffffu;
-    const int r = min(lane, 5);
-    double a[7];
+    float L[21], bv[6];  // lower triangle, L[i * (i + 1) / 2 + j] = (i, j), j <= i
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        const int lo = min(r, c), hi = max(r, c);
-        a[c] = (double)(float)S[hi * (hi + 1) / 2 + lo];
-    }
-    a[6] = (double)(float)S[21 + r];
+    for (int i = 0; i < 21; ++i) L[i] = (float)S[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) bv[i] = (float)S[21 + i];
     if (dim == 2) {  // z = 0 embedding: rows/columns 0, 1, 5 are empty -> x = 0 there
-        if (r == 0) a[0] = 1.0;
-        if (r == 1) a[1] = 1.0;
-        if (r == 5) a[5] = 1.0;
+        L[0] = 1.f;
+        L[2] = 1.f;
+        L[20] = 1.f;
     }
-    double diag = 0.0;
+    float maxdiag = 0.f;
 #pragma unroll
-    for (int c = 0; c < 6; ++c)
-        if (c == r) diag = fabs(a[c]);
-    double maxdiag = (lane < 6) ? diag : 0.0;
-#pragma unroll
-    for (int off = 4; off > 0; off >>= 1) maxdiag = fmax(maxdiag, __shfl_xor_sync(full, maxdiag, off));
-    maxdiag = fmax(maxdiag, __shfl_xor_sync(full, maxdiag, 8));  // lanes 0..7 hold the max over lanes 0..5 (6, 7 contribute copies of row 5)
-    maxdiag = __shfl_sync(full, maxdiag, 0);
-    const double thr = 6.0 * 1.1920929e-7 * maxdiag;
+    for (int i = 0; i < 6; ++i) maxdiag = fmaxf(maxdiag, fabsf(L[i * (i + 1) / 2 + i]));
+    const float thr = 6.0f * 1.1920929e-7f * maxdiag;
     bool ok = true;
+    float invd[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        double pk[7];
+        float d = L[k * (k + 1) / 2 + k];
 #pragma unroll
-        for (int c = k; c < 7; ++c) pk[c] = __shfl_sync(full, a[c], k);
-        const double piv = pk[k];
-        if (!(piv > thr)) ok = false;
-        const double inv = pivot_rcp(piv);
-        if (lane != k) {
-            const double f = a[k] * inv;
+        for (int j = 0; j < k; ++j) d -= L[k * (k + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
+        if (!(d > thr)) ok = false;
+        const float sq = sqrtf(d);
+        invd[k] = 1.0f / sq;
+        L[k * (k + 1) / 2 + k] = sq;
 #pragma unroll
-            for (int c = k; c < 7; ++c) a[c] -= f * pk[c];
+        for (int i = k + 1; i < 6; ++i) {
+            float v = L[i * (i + 1) / 2 + k];
+#pragma unroll
+            for (int j = 0; j < k; ++j) v -= L[i * (i + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
+            L[i * (i + 1) / 2 + k] = v * invd[k];
         }
     }
-    double arr = 1.0;
+    float y[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c)
-        if (c == r) arr = a[c];
-    const double xr = a[6] * pivot_rcp(arr);
+    for (int i = 0; i < 6; ++i) {  // L y = b
+        float v = bv[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) x[i] = (float)__shfl_sync(full, xr, i);
+        for (int j = 0; j < i; ++j) v -= L[i * (i + 1) / 2 + j] * y[j];
+        y[i] = v * invd[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {  // L^T x = y
+        float v = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) v -= L[j * (j + 1) / 2 + i] * x[j];
+        x[i] = v * invd[i];
+    }
     bool bad = !ok;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
@@ -341,7 +335,7 @@ __device__ __noinline__ void delta_point_to_point(const double* S, int dim, floa
 
 // Tail of one iteration, run by lane 0: T_iter = dT * T_iter, bookkeeping, then the checkers
 // (LPM TransformationCheckersImpl.cpp: Counter, Differential, Bound).
-__device__ __noinline__ void finish_iteration(const IcpParams& prm, IcpState* st, const float* dT12, double pairs, double wsum,
+__device__ __forceinline__ void finish_iteration(const IcpParams& prm, IcpState* st, const float* dT12, double pairs, double wsum,
                                               float* trace) {
     const double denom = (double)prm.knn * (double)st->nq;
     float T[16];

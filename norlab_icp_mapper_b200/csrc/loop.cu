@@ -52,6 +52,7 @@ constexpr int kSelListCap = 4096;
 // [6400] list counter | [8192, 8192 + kSelListCap) candidate list
 constexpr int kHistL1 = 4096, kHistL2 = 6144, kHistCount = 6400, kHistList = 8192;
 constexpr int kHistDebug = 12288;  // 8 words per iteration (first 256 iterations): development record written by CTA 0
+constexpr int kHistStage1 = 16384;  // two more level-0 histograms (4096 words each), used alternately by the two-barrier iteration
 constexpr int kHistStat = 16000;   // [0] queries that went through the search phase (all CTAs, whole registration)
 
 // ---- one-barrier iteration ("fast path") --------------------------------------------------------------
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     __syncthreads();
     const int nq = st.nq;
     unsigned epoch = 0;
+    uint32_t n_runs = 0, n_hist = 0;  // publish/finish rounds (stage-1 histograms) so far: parity selects the double buffer
     const bool use_quantile = prm.quantile_filter >= 0;
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
@@ -395,24 +397,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_iter0));
             if (it == 0) st.loop_total_ns = t_iter0;  // start mark, turned into a duration at the end
         }
-        // one-barrier iteration possible?  (identical decision in every CTA)
-        const bool attempt_fast = !(variant_flags & 16) && (use_quantile ? (searched && st.win_valid != 0) : true);
-        const bool fuse_hist = use_quantile && !attempt_fast;
-        if (fuse_hist) {
-            for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
-            __syncthreads();
-        }
-        // ---- V / S / C over this CTA's entries, 1024 at a time (one block unless nq > 148 * 1024) -------------------
-        const int par = it & 1;
-        uint4* my_counts = reinterpret_cast<uint4*>(fastws + kFastCountsOff) + (size_t)par * kLoopMaxBlocks;
-        double* my_partials = reinterpret_cast<double*>(fastws + kFastPartialsOff) + (size_t)par * kLoopMaxBlocks * kAccSlots;
-        float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kLoopMaxBlocks * kSegCap * 2;
-        const uint32_t wlo = use_quantile ? st.win_lo : 0xffffffffu, whi = use_quantile ? st.win_hi : 0xffffffffu;
+        // ---- V / S over this CTA's entries, 1024 at a time (one block unless nq > 148 * 1024) ------------------------
         const bool verify = !(variant_flags & 32);
-        uint32_t c_below = 0, c_above = 0;
-        uint32_t seg_count = 0;  // uniform: candidates of this CTA so far
-        if (tid < 4) s_tot[tid] = 0u;
-        if (attempt_fast && lane < NS) s_part[warp][lane] = 0.0;
         unsigned long long t_search = 0;  // CTA 0, thread 0: time spent in V + S
         for (int e0 = 0; e0 < n_ent; e0 += kLoopThreads) {
             const int e = e0 + tid;
@@ -535,35 +521,122 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     t_search += t1 - t_s0;
                 }
             }
-            if (attempt_fast) {
-                // C: outlier weights + error sums of what is certain + candidate tuples.  Entries that did not need a
-                // search go first (their warps do not wait for the searching warps), the searched ones after the sync.
+            if (searched) {
+                __syncthreads();  // the search results of this block are in the cache
+                if (stamper) B200_STAMP(gst, 19);
+                // new matches: fetch coordinates and normal (thread per entry: one round trip for all of them)
+                if (have) {
+                    float4* ppp = cached ? s_pp + e : sp_pp + qi;
+                    int pos = __float_as_int(ppp->w);
+                    if (pos <= -2) {
+                        pos = -(pos + 2);
+                        float4 pt = __ldg(g.pts + pos);
+                        pt.w = __int_as_float(pos);
+                        *ppp = pt;
+                        if (MIN == 0) {
+                            float4* pnv = cached ? s_nv + e : sp_nv + qi;
+                            const float4 nn = __ldg(nrm + pos);
+                            *pnv = make_float4(nn.x, nn.y, nn.z, pnv->w);
+                        }
+                    }
+                }
+            }
+        }
+        if (searched && tid < 16) s_Tprev[tid] = st.T[tid];  // the bounds now refer to this iteration's query positions
+        __syncthreads();
+        if (blockIdx.x == 0 && tid == 0 && searched) {
+            st.loop_search_ns += t_search;
+            st.loop_iters_timed += 1;
+        }
+        if (stamper) B200_STAMP(gst, 21);
+        float qlimit = 0.f;
+        bool fast_done = false;
+        bool fatal = false;
+        uint32_t dbg_path = 0, dbg_ncand = 0, dbg_nbelow = 0;  // development record (CTA 0)
+        // ---- the rest of the iteration in ONE barrier (stage 0: quantile window predicted from the last limits) or
+        //      TWO (stage 1: window = the level-0 radix bucket that holds the quantile, found with a histogram pass);
+        //      both decisions are identical in every CTA
+        for (int stage = 0; stage < 2 && !fast_done; ++stage) {
+            uint32_t wlo = 0xffffffffu, whi = 0xffffffffu;
+            uint32_t* h1 = nullptr;
+            if (use_quantile) {
+                if (stage == 0) {
+                    if (!searched || !st.win_valid || (variant_flags & (16 | 8))) continue;
+                    wlo = st.win_lo;
+                    whi = st.win_hi;
+                } else {
+                    // (Median scales the limit by a factor: the uncertain pairs are not the quantile's bucket -> general path)
+                    if ((variant_flags & (64 | 8)) || prm.outlier_kind[prm.quantile_filter] != B200ICP_OUTLIER_TRIMMED_DIST) continue;
+                    // level-0 histogram (bits [30:19] of dist2) of this CTA's slice -> global -> barrier -> bucket of the quantile
+                    for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
+                    __syncthreads();
+                    for (int e = tid; e < n_ent; e += kLoopThreads) {
+                        const bool cached = e < kCacheCap;
+                        const long long qi = qi_of(e);
+                        const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[qi].w);
+                        const float d = cached ? s_d2[e] : md2[qi];
+                        if (pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
+                    }
+                    __syncthreads();
+                    h1 = hist + kHistStage1 + (n_hist & 1u) * kSel0Bins;  // zeroed again by CTA 0 after this stage's second barrier
+                    n_hist += 1;
+                    for (int i = tid; i < kSel0Bins; i += kLoopThreads)
+                        if (sh[i]) atomicAdd(&h1[i], sh[i]);
+                    if (tid == 0) {
+                        s_bin = 0;
+                        s_res = 0;
+                        s_cnt = 0;
+                    }
+                    if (stamper) B200_STAMP(gst, 24);
+                    grid_barrier(bar_counter, epoch);
+                    if (stamper) B200_STAMP(gst, 25);
+                    const uint32_t total = loop_pick<false>(h1, kSel0Bins, 0u, true, prm.quantile, &s_bin, &s_res, &s_cnt, s_warp);
+                    const uint32_t b1 = s_bin;
+                    __syncthreads();
+                    if (total == 0) {
+                        // LPM: ConvergenceError("no outlier to filter"); leave the buffers clean and stop everywhere
+                        grid_barrier(bar_counter, epoch);
+                        if (blockIdx.x == 0)
+                            for (int i = tid; i < kSel0Bins; i += kLoopThreads) h1[i] = 0u;
+                        if (tid == 0) {
+                            st.status = B200ICP_ERR_CONVERGENCE;
+                            st.done = 1;
+                        }
+                        __syncthreads();
+                        fatal = true;
+                        break;
+                    }
+                    wlo = b1 << kSel0Shift;
+                    whi = wlo | ((1u << kSel0Shift) - 1u);
+                }
+            } else if (stage == 1 || (variant_flags & 16)) {
+                continue;
+            }
+            const int par = (int)(n_runs & 1u);
+            n_runs += 1;
+            uint4* my_counts = reinterpret_cast<uint4*>(fastws + kFastCountsOff) + (size_t)par * kLoopMaxBlocks;
+            double* my_partials = reinterpret_cast<double*>(fastws + kFastPartialsOff) + (size_t)par * kLoopMaxBlocks * kAccSlots;
+            float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kLoopMaxBlocks * kSegCap * 2;
+            uint32_t c_below = 0, c_above = 0;
+            uint32_t seg_count = 0;  // uniform: candidates of this CTA so far
+            if (tid < 4) s_tot[tid] = 0u;
+            if (lane < NS) s_part[warp][lane] = 0.0;
+            // C: outlier weights + error sums of what is certain + candidate tuples (thread per entry, from the cache)
+            for (int e0 = 0; e0 < n_ent; e0 += kLoopThreads) {
+                const int e = e0 + tid;
+                const bool have = e < n_ent;
+                const bool cached = e < kCacheCap;
+                const long long qi = have ? qi_of(e) : 0;
                 float acc[NS];
 #pragma unroll
                 for (int i = 0; i < NS; ++i) acc[i] = 0.f;
                 bool is_cand = false;
                 float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
-                auto classify = [&]() {
-                    float4 pp = cached ? s_pp[e] : sp_pp[qi];
-                    float4 nv = cached ? s_nv[e] : sp_nv[qi];
+                if (have) {
+                    const float4 pp = cached ? s_pp[e] : sp_pp[qi];
+                    const float4 nv = cached ? s_nv[e] : sp_nv[qi];
                     const float d = cached ? s_d2[e] : md2[qi];
-                    int pos = __float_as_int(pp.w);
-                    if (pos <= -2) {  // new match from the search phase: fetch its coordinates and normal
-                        pos = -(pos + 2);
-                        pp = __ldg(g.pts + pos);
-                        pp.w = __int_as_float(pos);
-                        if (MIN == 0) {
-                            const float4 nn = __ldg(nrm + pos);
-                            nv = make_float4(nn.x, nn.y, nn.z, nv.w);
-                        }
-                        if (cached) {
-                            s_pp[e] = pp;
-                            s_nv[e] = nv;
-                        } else {
-                            sp_pp[qi] = pp;
-                            sp_nv[qi] = nv;
-                        }
-                    }
+                    const int pos = __float_as_int(pp.w);
                     if (pos >= 0 && d < CUDART_INF_F) {
                         const uint32_t bits = __float_as_uint(d);
                         const int cls = bits < wlo ? 0 : (bits <= whi ? 1 : 2);
@@ -588,10 +661,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             }
                         }
                     }
-                };
-                if (have && !listed) classify();
-                if (searched) __syncthreads();  // the search results of this block are in the cache
-                if (have && listed) classify();
+                }
                 if (use_quantile) {  // ordered (deterministic) compaction of this block's candidates into the CTA's segment
                     const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
                     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -615,48 +685,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc[i] : 0.f;
                 const float tot = warp_reduce_32slots(v32, lane);
                 if (lane < NS) s_part[warp][lane] += (double)tot;
-            } else if (searched) {
-                __syncthreads();
-                if (stamper) B200_STAMP(gst, 19);
             }
-        }
-        if (searched && tid < 16) s_Tprev[tid] = st.T[tid];  // the bounds now refer to this iteration's query positions
-        __syncthreads();
-        if (blockIdx.x == 0 && tid == 0 && searched) {
-            st.loop_search_ns += t_search;
-            st.loop_iters_timed += 1;
-        }
-        if (stamper) B200_STAMP(gst, 21);
-        float qlimit = 0.f;
-        bool fast_done = false;
-        uint32_t dbg_path = 0, dbg_ncand = 0, dbg_nbelow = 0;  // development record (CTA 0)
-        bool hist_ready = fuse_hist;  // level-0 histogram filled by the pre-pass below
-        if (!attempt_fast) {
-            // general path: matches -> global memory (it walks mpos / md2), level-0 histogram of the quantile on the way
-            for (int e = tid; e < n_ent; e += kLoopThreads) {
-                const long long qi = qi_of(e);
-                const bool cached = e < kCacheCap;
-                float4* ppp = cached ? s_pp + e : sp_pp + qi;
-                int pos = __float_as_int(ppp->w);
-                if (pos <= -2) {  // new match from the search phase: fetch its coordinates and normal
-                    pos = -(pos + 2);
-                    float4 pt = __ldg(g.pts + pos);
-                    pt.w = __int_as_float(pos);
-                    *ppp = pt;
-                    if (MIN == 0) {
-                        float4* pnv = cached ? s_nv + e : sp_nv + qi;
-                        const float4 nn = __ldg(nrm + pos);
-                        *pnv = make_float4(nn.x, nn.y, nn.z, pnv->w);
-                    }
-                }
-                const float d = cached ? s_d2[e] : md2[qi];
-                mpos[qi] = pos;
-                md2[qi] = d;
-                if (fuse_hist && pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
-            }
-            __syncthreads();
-        }
-        if (attempt_fast) {
             // ---- publish, ONE barrier, finish redundantly ---------------------------------------------
             if (stamper) B200_STAMP(gst, 28);
             {
@@ -725,7 +754,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 if (total && rank >= total) rank = total - 1u;
                 ok = total > 0 && seg_max <= (uint32_t)kSegCap && n_cand <= (uint32_t)kCandCap && rank >= n_below && rank < n_below + n_cand;
             }
-            dbg_path = ok ? 1u : 2u;
+            dbg_path = dbg_path * 10u + (ok ? (stage == 0 ? 1u : 3u) : (stage == 0 ? 2u : 4u));
             dbg_ncand = n_cand;
             dbg_nbelow = n_below;
             if (ok) {
@@ -833,19 +862,31 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 __syncthreads();
                 if (stamper) B200_STAMP(gst, 13);
                 fast_done = true;
-                if (tid == 0) st.fast_iters += 1;
-            } else if (use_quantile) {
-                // prediction failed: general path; it walks mpos / md2 in global memory
-                for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
-                for (int e = tid; e < n_ent; e += kLoopThreads) {
-                    const long long qi = qi_of(e);
-                    const bool cached = e < kCacheCap;
-                    mpos[qi] = __float_as_int(cached ? s_pp[e].w : sp_pp[qi].w);
-                    if (cached) md2[qi] = s_d2[e];
+                if (tid == 0) {
+                    if (stage == 0) st.fast_iters += 1;
+                    else st.hist_iters += 1;
                 }
-                __syncthreads();
-                hist_ready = false;
             }
+            if (h1 && blockIdx.x == 0)  // the level-0 histogram was read by every CTA before the barrier above
+                for (int i = tid; i < kSel0Bins; i += kLoopThreads) h1[i] = 0u;
+        }
+        if (fatal) break;
+        bool hist_ready = false;
+        if (!fast_done) {
+            // general path (window overflow, or forced by nn_variant): it walks mpos / md2 in global memory
+            for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
+            __syncthreads();
+            for (int e = tid; e < n_ent; e += kLoopThreads) {
+                const long long qi = qi_of(e);
+                const bool cached = e < kCacheCap;
+                const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[qi].w);
+                const float d = cached ? s_d2[e] : md2[qi];
+                mpos[qi] = pos;
+                md2[qi] = d;
+                if (use_quantile && pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
+            }
+            __syncthreads();
+            hist_ready = true;
         }
         // ---- exact quantile of the finite distances (LPM Matches::getDistsQuantile) -------------------
         bool fallback_used = false;

@@ -166,15 +166,16 @@ def test_quantile_fallback_path_is_identical(pair3d):
     dict(outliers=(), minimizer="point_to_point", max_iteration_count=15),
 ])
 def test_one_barrier_iterations(pair3d, chain, monkeypatch):
-    """The loop kernel's one-barrier iteration (quantile window predicted from the previous limit) must
-    give the same quantile limit -- hence exactly the same kept pairs -- as the general three-barrier
-    iteration (nn_variant bit 4 disables it), also when the window policy is made so narrow that most
-    predictions fail and the kernel falls back mid-iteration; poses agree to summation-order rounding."""
+    """The loop kernel's one-barrier iteration (quantile window predicted from the previous limit), its
+    two-barrier iteration (window = the quantile's radix bucket, nn_variant bit 4 forces it) and the general
+    three-barrier iteration (bits 4 + 6) must find the same quantile limit -- hence exactly the same kept
+    pairs -- also when the window policy is made so narrow that most predictions fail and the kernel falls
+    back mid-iteration; poses agree to summation-order rounding."""
     from norlab_icp_mapper_b200.icp import ICP
     has_quantile = any(k == "trimmed" for k, _ in chain["outliers"])
     outs = {}
     for name, variant, window in (("fast", 0, None), ("general", 16, None), ("narrow", 0, "0.0,0.00001,1.0"), ("wide", 0, "8.0,0.05,0.5"),
-                                  ("always_search", 32, None)):
+                                  ("always_search", 32, None), ("three_barrier", 16 | 64, None)):
         if window is None:
             monkeypatch.delenv("B200ICP_WINDOW", raising=False)
         else:
@@ -185,15 +186,17 @@ def test_one_barrier_iterations(pair3d, chain, monkeypatch):
         T = g(pair3d["reading"])
         T2 = g(pair3d["reading"])
         outs[name] = (T, g.last_result.pairs_last_iter, g.last_result.overlap, g.timing().loop_fast_iterations, g.last_result.iterations,
-                      g.timing().loop_searched_queries)
+                      g.timing().loop_searched_queries, g.timing().loop_two_barrier_iterations)
         g.close()
         assert np.array_equal(T, T2), name  # each policy is run-to-run deterministic
-    assert outs["general"][3] == 0
+    assert outs["general"][3] == 0 and outs["three_barrier"][3] == 0 and outs["three_barrier"][6] == 0
+    if has_quantile:  # without the prediction every iteration finds the quantile's bucket with a histogram pass: two barriers
+        assert outs["general"][6] == outs["general"][4], outs["general"]
     # the match cache only skips searches whose outcome is proven: with it disabled (bit 5) every bit is the same
     assert np.array_equal(outs["fast"][0], outs["always_search"][0]) and outs["fast"][1:5] == outs["always_search"][1:5]
     assert outs["always_search"][5] >= (outs["fast"][4] - 1) * len(pair3d["reading"]) > outs["fast"][5] > 0
     assert outs["fast"][3] > (5 if has_quantile else 0), outs["fast"]
-    for name in ("fast", "narrow", "wide"):
+    for name in ("fast", "narrow", "wide", "three_barrier"):
         er, et = synth.pose_error(outs[name][0], outs["general"][0])
         assert er <= 1e-6 and et <= 1e-5, (name, er, et)
         assert outs[name][1] == outs["general"][1] and outs[name][2] == outs["general"][2], (name, outs[name], outs["general"])

@@ -16,10 +16,10 @@ rec = np.zeros((30, 8), np.uint32)
 g._L.b200icp_debug_loop_record.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
 g._L.b200icp_debug_loop_record(g._h, rec.ctypes.data, 30)
 tm = g.timing()
-print(f"total {tm.total_ms:.3f} ms loop {tm.loop_total_ms:.3f} ms fast {tm.loop_fast_iterations} searched {tm.loop_searched_queries}")
+print(f"total {tm.total_ms:.3f} ms loop {tm.loop_total_ms:.3f} ms one-barrier {tm.loop_fast_iterations} two-barrier {tm.loop_two_barrier_iterations} searched {tm.loop_searched_queries}")
 prev = 0
 for i, r in enumerate(rec):
     lim = np.array([r[1]], np.uint32).view(np.float32)[0]
     lo, hi = np.array([r[5], r[6]], np.uint32).view(np.float32)
-    print(f"it {i:2d} path {r[0]} limit {lim:.6f} cand {r[2]:6d} below {r[3]:6d} searched {int(r[4]) - prev:7d}  next window [{lo:.6f}, {hi:.6f}]  {r[7] / 1e3:7.2f} us")
+    print(f"it {i:2d} path {r[0]:2d} limit {lim:.6f} cand {r[2]:6d} below {r[3]:6d} searched {int(r[4]) - prev:7d}  next window [{lo:.6f}, {hi:.6f}]  {r[7] / 1e3:7.2f} us")
     prev = int(r[4])
