@@ -259,10 +259,20 @@ def run_b200(args):
         e2e_ms = float(t.item())
     clocks = sampler.finish() if sampler else None
 
-    # ---- in-kernel timing of the search phase of the persistent loop (from the timed `value` steps) ---
-    tm = icp.timing()
+    # ---- the persistent loop kernel (what the timed steps run): CUDA events around its launch, averaged over a
+    #      separate pass of L2-flushed steps; the in-kernel %globaltimer figures come from the last of them ---
+    loop_ms_sum, loop_n = 0.0, 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        step_device()
+        tm = icp.timing()
+        loop_ms_sum += tm.loop_kernel_ms
+        loop_n += 1
+    loop_kernel_ms = loop_ms_sum / max(loop_n, 1)
     loop_iters, loop_search_ms, loop_total_ms = tm.loop_iterations, tm.loop_search_ms_sum, tm.loop_total_ms
-    loop_fast_iters = tm.loop_fast_iterations
+    loop_fast_iters, loop_two_iters, loop_searched = tm.loop_fast_iterations, tm.loop_two_barrier_iterations, tm.loop_searched_queries
+    iterations_run = icp.last_result.iterations
 
     # ---- roofline of the k-NN kernel: separate pass with per-launch events --------------------------
     icp.set_profiling(True)
@@ -288,12 +298,23 @@ def run_b200(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic = None
+        try:  # DRAM bytes of one loop-kernel launch from the committed ncu capture (not measured by this run)
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["icp_loop_kernel"]
+            if args.n_map == 2_000_000 and args.n_scan == 100_000 and args.iters == 30:
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         k = 1
-        b_nn = 16 * args.n_scan + 16 * args.n_map + 8 * k * args.n_scan
+        b_nn = 16 * args.n_scan + 16 * args.n_map + 8 * k * args.n_scan   # one correspondence search
+        b_acc = 48 * k * args.n_scan                                      # one pair accumulation
         nn_avg_ms = nn_ms / max(nn_n, 1)
-        achieved = b_nn / (nn_avg_ms * 1e-3) / 1e9 if nn_n else None
+        warm_achieved = b_nn / (nn_avg_ms * 1e-3) / 1e9 if nn_n else None
+        # the dominant kernel is the loop kernel: one launch = (iterations - 1) searches + `iterations` accumulations
+        b_loop = (iterations_run - 1) * b_nn + iterations_run * b_acc
+        achieved = b_loop / (loop_kernel_ms * 1e-3) / 1e9 if loop_kernel_ms > 0 else None
         from norlab_icp_mapper_b200 import synth
         err = synth.pose_error(T, data["correction_true"])
         line = {
@@ -308,17 +329,28 @@ def run_b200(args):
             "gpu_launches": int(launches_per_step) * args.steps,
             "device_ms_per_step": dev_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "nn1_warm_kernel<4> (k = 1 correspondence search, iterations >= 1; iteration 0 is knn_kernel<8, Acc1>)", "algorithmic_bytes": b_nn,
-                         "avg_launch_us": nn_avg_ms * 1e3, "launches_timed": nn_n, "peak_source": peak_src,
-                         "how": "separate pass of %d steps through the kernel-per-step path with cudaEvents around every k-NN "
-                                "launch on the library's stream (event-to-event, so it includes the launch gap)" % args.steps,
-                         "in_loop": {"what": "the same search as a phase of the persistent loop kernel the timed steps use, "
-                                             "%globaltimer on CTA 0, last timed step", "iterations": loop_iters,
-                                     "avg_phase_us": (1e3 * loop_search_ms / loop_iters) if loop_iters else None,
-                                     "achieved": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9) if loop_iters else None,
-                                     "frac": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9 / peak) if loop_iters else None,
-                                     "loop_kernel_ms": loop_total_ms, "one_barrier_iterations": loop_fast_iters}},
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "kernel": "icp_loop_kernel<0> (persistent cooperative kernel, one launch per registration: iterations 1..%d "
+                                   "of search + outlier quantile + error sums + solve)" % (iterations_run - 1),
+                         "algorithmic_bytes": b_loop, "avg_launch_us": loop_kernel_ms * 1e3, "launches_timed": loop_n,
+                         "peak_source": peak_src,
+                         "how": "cudaEvents around the loop kernel's launch on the library's stream, mean over a separate pass of %d "
+                                "L2-flushed steps; algorithmic bytes = (iterations - 1) x B_nn + iterations x B_acc with B_nn = 16 Nq + "
+                                "16 Nm + 8 k Nq, B_acc = 48 k Nq (SURVEY 8d).  The kernel is latency/issue-bound, not HBM-bound: the index "
+                                "stays L2-resident across iterations and most searches are skipped by proof (see search_phase)" % args.steps,
+                         "search_phase": {"what": "verify + search phases of the loop kernel, %globaltimer on CTA 0, last step of that pass",
+                                          "iterations": loop_iters,
+                                          "avg_phase_us": (1e3 * loop_search_ms / loop_iters) if loop_iters else None,
+                                          "achieved": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9) if loop_iters else None,
+                                          "frac": (b_nn / (1e-3 * loop_search_ms / loop_iters) / 1e9 / peak) if loop_iters else None,
+                                          "queries_searched": loop_searched, "queries_total": (iterations_run - 1) * args.n_scan,
+                                          "one_barrier_iterations": loop_fast_iters, "two_barrier_iterations": loop_two_iters,
+                                          "loop_kernel_ms_globaltimer": loop_total_ms},
+                         "standalone_search_kernel": {"kernel": "nn1_warm_kernel<4> (kernel-per-step path, exhaustive warm ball search)",
+                                                      "avg_launch_us": nn_avg_ms * 1e3, "launches_timed": nn_n, "achieved": warm_achieved,
+                                                      "frac": (warm_achieved / peak) if warm_achieved else None,
+                                                      "how": "separate pass through the kernel-per-step path, cudaEvents around every "
+                                                             "k-NN launch (event-to-event, includes the launch gap)"}},
             "clocks": clocks,
             "setmap_ms": setmap_ms,
             "pose_error_vs_truth": {"rad": err[0], "m": err[1]},

@@ -64,6 +64,7 @@ class Timing(C.Structure):
         ("loop_fast_iterations", C.c_int32),
         ("loop_searched_queries", C.c_int32),
         ("loop_two_barrier_iterations", C.c_int32),
+        ("loop_kernel_ms", C.c_float),
     ]
 
 

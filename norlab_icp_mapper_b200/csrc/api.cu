@@ -39,7 +39,7 @@ struct b200icp_ctx {
     float margin3[3] = {3.0f, 0.002f, 0.25f};  // search margin of the loop kernel's match cache; B200ICP_MARGIN="gain,min[m],max[cells]"
     float win3[3] = {2.0f, 0.0015f, 0.12f};  // quantile-window policy of the one-barrier iteration (loop.cu); B200ICP_WINDOW="gain,floor,max"
     char* h_pinned = nullptr;  // [0, 1024): state image to upload, [1024, 2048): state read back, [2048..): ints
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_map0 = nullptr, ev_map1 = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_map0 = nullptr, ev_map1 = nullptr, ev_loop0 = nullptr, ev_loop1 = nullptr;
     std::vector<cudaEvent_t> nn_events;
     bool profiling = false;
     bool want_trace = false;
@@ -343,6 +343,7 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_map0) == cudaSuccess && cudaEventCreate(&ctx->ev_map1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev_loop0) == cudaSuccess && cudaEventCreate(&ctx->ev_loop1) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_pinned, 4096) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->d_scalar_nq, 64) == cudaSuccess;
     ok = ok && icp_device_setup() == cudaSuccess;
@@ -407,6 +408,8 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_map0) cudaEventDestroy(ctx->ev_map0);
     if (ctx->ev_map1) cudaEventDestroy(ctx->ev_map1);
+    if (ctx->ev_loop0) cudaEventDestroy(ctx->ev_loop0);
+    if (ctx->ev_loop1) cudaEventDestroy(ctx->ev_loop1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -585,7 +588,9 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, 1, p.max_r2, b.match_pos, b.match_d2,
                       /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
         CK(cudaMemsetAsync(ctx->d_bar_counter, 0, sizeof(unsigned), s));
+        CK(cudaEventRecord(ctx->ev_loop0, s));
         CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, ctx->win3, ctx->margin3, s));
+        CK(cudaEventRecord(ctx->ev_loop1, s));
         launches += 2;
         CK(cudaMemcpyAsync(out_state, b.state, kStateBytes, cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(ctx->ev_end, s));
@@ -624,6 +629,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     ctx->timing.loop_iterations = persistent ? out_state->loop_iters_timed : 0;
     ctx->timing.loop_search_ms_sum = persistent ? (float)(1e-6 * (double)out_state->loop_search_ns) : 0.f;
     ctx->timing.loop_total_ms = persistent ? (float)(1e-6 * (double)out_state->loop_total_ns) : 0.f;
+    ctx->timing.loop_kernel_ms = 0.f;
+    if (persistent) cudaEventElapsedTime(&ctx->timing.loop_kernel_ms, ctx->ev_loop0, ctx->ev_loop1);
     ctx->timing.loop_fast_iterations = persistent ? out_state->fast_iters : 0;
     ctx->timing.loop_searched_queries = persistent ? out_state->searched_queries : 0;
     ctx->timing.loop_two_barrier_iterations = persistent ? out_state->hist_iters : 0;
