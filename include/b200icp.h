@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200ICP_ABI_VERSION 1
+#define B200ICP_ABI_VERSION 2
 
 typedef enum b200icp_status {
     B200ICP_OK = 0,
@@ -50,7 +50,10 @@ typedef enum b200icp_outlier_kind {
     B200ICP_OUTLIER_TRIMMED_DIST = 1, /* param = ratio;   w = dist2 <= quantile(finite dist2, ratio)  */
     B200ICP_OUTLIER_MAX_DIST = 2,     /* param = maxDist; w = dist2 <= maxDist^2                      */
     B200ICP_OUTLIER_MIN_DIST = 3,     /* param = minDist; w = dist2 >= minDist^2                      */
-    B200ICP_OUTLIER_MEDIAN_DIST = 4   /* param = factor;  w = dist2 <= factor * median(finite dist2)  */
+    B200ICP_OUTLIER_MEDIAN_DIST = 4,  /* param = factor;  w = dist2 <= factor * median(finite dist2)  */
+    B200ICP_OUTLIER_VAR_TRIMMED_DIST = 5 /* VarTrimmedDistOutlierFilter{minRatio = param, maxRatio = param2, lambda = param3}:
+                                            ratio = argmin FRMS over the sorted finite positive dist2 (optimizeInlierRatio),
+                                            then w = dist2 <= quantile(finite dist2, ratio)                               */
 } b200icp_outlier_kind;
 
 /* icp.errorMinimizer */
@@ -76,6 +79,8 @@ typedef struct b200icp_config {
     int32_t n_outlier;
     int32_t outlier_kind[B200ICP_MAX_OUTLIER_FILTERS];
     float outlier_param[B200ICP_MAX_OUTLIER_FILTERS];
+    float outlier_param2[B200ICP_MAX_OUTLIER_FILTERS]; /* second / third parameter of filters that have them (VarTrimmed) */
+    float outlier_param3[B200ICP_MAX_OUTLIER_FILTERS];
     /* errorMinimizer */
     int32_t minimizer;
     /* transformationCheckers */
@@ -125,7 +130,10 @@ typedef struct b200icp_timing {
  * examples/config.yaml:1-23, Mapper.cpp:27-31). */
 typedef enum b200icp_filter_kind {
     B200ICP_FILTER_BOUNDING_BOX = 1,   /* BoundingBoxDataPointsFilter{xMin..zMax, removeInside}             */
-    B200ICP_FILTER_DISTANCE_LIMIT = 2  /* DistanceLimitDataPointsFilter{dim (-1 radial), dist, removeInside} */
+    B200ICP_FILTER_DISTANCE_LIMIT = 2, /* DistanceLimitDataPointsFilter{dim (-1 radial), dist, removeInside} */
+    B200ICP_FILTER_RANDOM_SAMPLING = 3 /* RandomSamplingDataPointsFilter{prob}: `dist` = prob, `dim` = seed.  A point survives
+                                          when u(seed, chain slot, point index) < prob, u from a counter-based generator:
+                                          reproducible; upstream draws from rand(), so only the distribution can agree      */
 } b200icp_filter_kind;
 typedef struct b200icp_filter {
     int32_t kind;
@@ -255,7 +263,10 @@ int32_t b200icp_map_append(b200icp_ctx* ctx, const float* input, int32_t feature
  * then libpointmatcher's OctreeGridDataPointsFilter{maxPointByNode, maxSizeByNode, samplingMethod}
  * over the whole local map.  The octree descent is emulated bit for bit (child = p > centre per axis,
  * centre +- r/2, until 2r <= maxSizeByNode); one survivor per occupied leaf: samplingMethod 0 = the
- * first point (lowest index), 2 = centroid of features and descriptors.  maxPointByNode must be 1.
+ * first point (lowest index), 1 = a uniformly random member (counter-based generator keyed by the leaf:
+ * reproducible, base seed from B200ICP_OCTREE_SEED; upstream draws from its own unseeded generator, so only the
+ * distribution can agree), 2 = centroid of features and descriptors, 3 = medoid (the member closest to the
+ * leaf's centroid).  maxPointByNode must be 1 (the value OctreeMapperModule.cpp hard-codes).
  * input_normals / input_prob may be NULL (concatenate then drops that descriptor from the map). */
 int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
                            const float* input_normals, const float* input_prob, float max_size_by_node,

@@ -2,14 +2,14 @@
 product binding (icp.py) and by the tests' oracle binding so both speak the same config."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_OUTLIER_FILTERS = 4
 
 # b200icp_status
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_MAP, ERR_CONVERGENCE, ERR_BOUND, ERR_NAN, ERR_TRANSFORM, \
     ERR_INVALID_FIELD, ERR_NOT_IMPLEMENTED = range(10)
 # b200icp_outlier_kind
-OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST = 1, 2, 3, 4
+OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST, OUTLIER_VAR_TRIMMED_DIST = 1, 2, 3, 4, 5
 # b200icp_minimizer_kind
 MIN_POINT_TO_PLANE, MIN_POINT_TO_POINT, MIN_IDENTITY = 0, 1, 2
 
@@ -23,6 +23,8 @@ class Config(C.Structure):
         ("n_outlier", C.c_int32),
         ("outlier_kind", C.c_int32 * MAX_OUTLIER_FILTERS),
         ("outlier_param", C.c_float * MAX_OUTLIER_FILTERS),
+        ("outlier_param2", C.c_float * MAX_OUTLIER_FILTERS),
+        ("outlier_param3", C.c_float * MAX_OUTLIER_FILTERS),
         ("minimizer", C.c_int32),
         ("max_iteration_count", C.c_int32),
         ("use_differential", C.c_int32),
@@ -74,7 +76,7 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
     """Build a Config from the names used in the reference's `icp:` YAML node
     (docs/MapperConfiguration.md:172-189)."""
     kinds = {"trimmed": OUTLIER_TRIMMED_DIST, "max_dist": OUTLIER_MAX_DIST,
-             "min_dist": OUTLIER_MIN_DIST, "median": OUTLIER_MEDIAN_DIST}
+             "min_dist": OUTLIER_MIN_DIST, "median": OUTLIER_MEDIAN_DIST, "var_trimmed": OUTLIER_VAR_TRIMMED_DIST}
     mins = {"point_to_plane": MIN_POINT_TO_PLANE, "point_to_point": MIN_POINT_TO_POINT,
             "identity": MIN_IDENTITY}
     c = Config()
@@ -82,9 +84,11 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
     if len(outliers) > MAX_OUTLIER_FILTERS:
         raise ValueError("too many outlier filters")
     c.n_outlier = len(outliers)
-    for i, (name, param) in enumerate(outliers):
+    for i, (name, *params) in enumerate(outliers):  # ("var_trimmed", minRatio, maxRatio, lambda); one parameter otherwise
         c.outlier_kind[i] = kinds[name]
-        c.outlier_param[i] = param
+        c.outlier_param[i] = params[0]
+        c.outlier_param2[i] = params[1] if len(params) > 1 else 0.0
+        c.outlier_param3[i] = params[2] if len(params) > 2 else 0.0
     c.minimizer = mins[minimizer]
     c.max_iteration_count = max_iteration_count
     if differential is not None:

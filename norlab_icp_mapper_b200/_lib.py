@@ -7,6 +7,7 @@ There is NO fallback: if the shared object is missing this raises, and if no B20
 import ctypes as C
 import os
 
+from . import _abi
 from ._abi import Config, Result, Timing
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -86,7 +87,7 @@ def load():
     L.b200icp_map_octree.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, i32, C.POINTER(i64)]
     L.b200icp_map_cut_at_threshold.argtypes = [vp, f32, i32, C.POINTER(i64)]
     L.b200icp_map_dynamic_points.argtypes = [vp, vp, i32, i64, vp, vp, vp]
-    if L.b200icp_abi_version() != 1:
+    if L.b200icp_abi_version() != _abi.ABI_VERSION:
         raise ImportError("libb200icp.so ABI version mismatch")
     _lib = L
     return L

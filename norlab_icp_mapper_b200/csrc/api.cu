@@ -26,6 +26,7 @@ struct b200icp_ctx {
     int64_t cap_keep = 0;
     GridIndex aux;  // index for b200icp_knn on arbitrary clouds
     IcpBuffers buf;
+    VarTrimScratch var_scratch;
     float* d_stage_a = nullptr;  // uploads: features
     float* d_stage_b = nullptr;  // uploads: normals / queries
     size_t stage_a_bytes = 0, stage_b_bytes = 0;
@@ -36,6 +37,7 @@ struct b200icp_ctx {
     int* d_scalar_nq = nullptr;
     unsigned* d_bar_counter = nullptr;
     int n_sms = 148;
+    uint64_t octree_calls = 0;  // advances the random sampler's seed from one b200icp_map_octree call to the next
     float margin3[3] = {3.0f, 0.002f, 0.25f};  // search margin of the loop kernel's match cache; B200ICP_MARGIN="gain,min[m],max[cells]"
     float win3[3] = {2.0f, 0.0015f, 0.12f};  // quantile-window policy of the one-barrier iteration (loop.cu); B200ICP_WINDOW="gain,floor,max"
     char* h_pinned = nullptr;  // [0, 1024): state image to upload, [1024, 2048): state read back, [2048..): ints
@@ -150,12 +152,15 @@ int32_t validate_config(const b200icp_config* c, std::string& why) {
     int quant = 0;
     for (int f = 0; f < c->n_outlier; ++f) {
         const int kd = c->outlier_kind[f];
-        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_MEDIAN_DIST) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
-        if (kd == B200ICP_OUTLIER_TRIMMED_DIST || kd == B200ICP_OUTLIER_MEDIAN_DIST) ++quant;
+        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_VAR_TRIMMED_DIST) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
+        if (kd == B200ICP_OUTLIER_TRIMMED_DIST || kd == B200ICP_OUTLIER_MEDIAN_DIST || kd == B200ICP_OUTLIER_VAR_TRIMMED_DIST) ++quant;
+        if (kd == B200ICP_OUTLIER_VAR_TRIMMED_DIST &&
+            !(c->outlier_param[f] >= 0.f && c->outlier_param[f] < c->outlier_param2[f] && c->outlier_param2[f] <= 1.f && c->outlier_param3[f] > 0.f))
+            return why = "VarTrimmedDist: need 0 <= minRatio < maxRatio <= 1 and lambda > 0", B200ICP_ERR_INVALID_ARG;
         if (kd == B200ICP_OUTLIER_TRIMMED_DIST && !(c->outlier_param[f] >= 0.f && c->outlier_param[f] <= 1.f))
             return why = "quantile must be between 0 and 1", B200ICP_ERR_INVALID_ARG;
     }
-    if (quant > 1) return why = "at most one quantile-based outlier filter (Trimmed or Median) per chain", B200ICP_ERR_NOT_IMPLEMENTED;
+    if (quant > 1) return why = "at most one quantile-based outlier filter (Trimmed, VarTrimmed or Median) per chain", B200ICP_ERR_NOT_IMPLEMENTED;
     if (c->minimizer < B200ICP_MIN_POINT_TO_PLANE || c->minimizer > B200ICP_MIN_IDENTITY) return why = "unknown error minimizer", B200ICP_ERR_INVALID_ARG;
     if (c->use_differential && (c->smooth_length < 1 || c->smooth_length > 7)) return why = "smoothLength must be in [1, 7]", B200ICP_ERR_INVALID_ARG;
     return B200ICP_OK;
@@ -323,6 +328,12 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     for (int f = 0; f < cfg->n_outlier; ++f) {
         p.outlier_kind[f] = cfg->outlier_kind[f];
         p.outlier_param[f] = cfg->outlier_param[f];
+        p.outlier_param2[f] = cfg->outlier_param2[f];
+        p.outlier_param3[f] = cfg->outlier_param3[f];
+        if (cfg->outlier_kind[f] == B200ICP_OUTLIER_VAR_TRIMMED_DIST) {
+            p.quantile_filter = f;
+            p.quantile = -1.f;  // tuned per iteration on the device (outlier.cu)
+        }
         if (cfg->outlier_kind[f] == B200ICP_OUTLIER_TRIMMED_DIST) {
             p.quantile_filter = f;
             p.quantile = cfg->outlier_param[f];
@@ -392,6 +403,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaFree(b.partials);
     cudaFree(b.state);
     cudaFree(b.trace);
+    var_trimmed_free(ctx->var_scratch);
     cudaFree(b.fastws);
     cudaFree(b.spill_pp);
     cudaFree(b.spill_nv);
@@ -583,7 +595,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     int issued = 0, nn_timed = 0;
     // k = 1: cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
     // (Per-kernel profiling and nn_variant bit 2 select the kernel-per-step path below instead.)
-    const bool persistent = p.knn == 1 && !ctx->profiling && !(ctx->cfg.nn_variant & 4);
+    const bool var_trimmed = p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST;
+    const bool persistent = p.knn == 1 && !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed;
     if (persistent) {
         CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, 1, p.max_r2, b.match_pos, b.match_d2,
                       /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
@@ -609,7 +622,7 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
                               /*want_original_ids=*/0, (ctx->cfg.nn_variant & 0xffff) | ((issued > 0 && !(ctx->cfg.nn_variant & 2)) ? 0x10000 : 0), s));
             if (time_it) CK(cudaEventRecord(ev[1], s));
             ++launches;
-            CK(launch_iteration_tail(p, ctx->map, b, issued, s, &launches, time_it ? ev[2] : nullptr));
+            CK(launch_iteration_tail(p, ctx->map, b, issued, s, &launches, time_it ? ev[2] : nullptr, &ctx->var_scratch));
             if (time_it) {
                 CK(cudaEventRecord(ev[3], s));
                 ++nn_timed;
@@ -998,7 +1011,8 @@ int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_
     if (feature_rows != dim + 1 || *n < 0 || (*n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
     if (n_filters < 0 || n_filters > 8 || (n_filters > 0 && !chain)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad filter chain (at most 8 entries)");
     for (int i = 0; i < n_filters; ++i)
-        if (chain[i].kind != B200ICP_FILTER_BOUNDING_BOX && chain[i].kind != B200ICP_FILTER_DISTANCE_LIMIT)
+        if (chain[i].kind != B200ICP_FILTER_BOUNDING_BOX && chain[i].kind != B200ICP_FILTER_DISTANCE_LIMIT &&
+            chain[i].kind != B200ICP_FILTER_RANDOM_SAMPLING)
             return fail(ctx, B200ICP_ERR_INVALID_ARG, "unknown input filter");
     if (*n == 0 || n_filters == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
@@ -1095,8 +1109,8 @@ int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature
     if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
     if (!(max_size_by_node > 0.f)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "maxSizeByNode must be positive");
     if (max_point_by_node != 1) return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "OctreeGrid: only maxPointByNode = 1 (the LPM default) is implemented");
-    if (sampling_method != 0 && sampling_method != 2)
-        return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "OctreeGrid: samplingMethod 0 (first) and 2 (centroid) are implemented; 1 (random) cannot match a CPU RNG stream, 3 (medoid) is not implemented");
+    if (sampling_method < 0 || sampling_method > 3)
+        return fail(ctx, B200ICP_ERR_INVALID_ARG, "OctreeGrid: samplingMethod must be 0 (first), 1 (random), 2 (centroid) or 3 (medoid)");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     MapStore& st = ctx->store;
@@ -1107,7 +1121,11 @@ int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature
         CK(store_append_all(st, d_in, feature_rows, dim, d_nrm, d_prob, n_in, s));  // map.concatenate(input)
     }
     int64_t removed = 0;
-    CK(store_octree_filter(st, ctx->map, dim, max_size_by_node, sampling_method, &removed, s));
+    // the random sampler is reproducible: same base seed + same call count -> same survivors (B200ICP_OCTREE_SEED sets the base)
+    uint64_t seed = 0x0c7ee5eedull;
+    if (const char* env = getenv("B200ICP_OCTREE_SEED")) seed = strtoull(env, nullptr, 0);
+    seed += ctx->octree_calls++;
+    CK(store_octree_filter(st, ctx->map, dim, max_size_by_node, sampling_method, seed, &removed, s));
     CK(cudaStreamSynchronize(s));
     ctx->index_stale = true;
     if (n_after) *n_after = st.n_active;

@@ -64,6 +64,8 @@ struct IcpState {
     int win_valid, have_limit;
     int searched_queries;  // queries that went through the search phase (the rest were verified against their bound)
     int hist_iters;        // iterations that took the two-barrier path (window from a level-0 histogram)
+    float dyn_quantile;    // VarTrimmedDist: the ratio tuned for this iteration (outlier.cu)
+    int pad3_;
 };
 
 static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");
@@ -96,8 +98,10 @@ struct IcpParams {  // by-value kernel argument, constant for the life of a cont
     int n_outlier;
     int outlier_kind[B200ICP_MAX_OUTLIER_FILTERS];
     float outlier_param[B200ICP_MAX_OUTLIER_FILTERS];
+    float outlier_param2[B200ICP_MAX_OUTLIER_FILTERS];
+    float outlier_param3[B200ICP_MAX_OUTLIER_FILTERS];
     int quantile_filter;  // index of the Trimmed/Median filter or -1
-    float quantile;       // ratio (Trimmed) or 0.5 (Median)
+    float quantile;       // ratio (Trimmed), 0.5 (Median), or < 0: read IcpState::dyn_quantile (VarTrimmed)
     int minimizer;
     int max_iteration_count;
     int use_differential;
@@ -176,9 +180,9 @@ cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const f
 // map.concatenate(input): append every input point (descriptors survive only if both clouds have them)
 cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, const float* d_in_nrm, const float* d_in_prob,
                              int64_t n_in, cudaStream_t s);
-// OctreeGridDataPointsFilter{maxPointByNode 1, maxSizeByNode, samplingMethod 0 (first) | 2 (centroid)} over the loaded points
-cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, int64_t* n_removed,
-                                cudaStream_t s);
+// OctreeGridDataPointsFilter{maxPointByNode 1, maxSizeByNode, samplingMethod 0 first | 1 random | 2 centroid | 3 medoid} over the loaded points
+cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, uint64_t seed,
+                                int64_t* n_removed, cudaStream_t s);
 // CutAtDescriptorThresholdDataPointsFilter{probabilityDynamic, useLargerThan, threshold} over the loaded points
 cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s);
 // input filter chain on a device cloud (rows floats per point): keep flags -> ordered compaction
@@ -226,6 +230,18 @@ struct IcpBuffers {
     int cap_iter = 0;
 };
 
+// outlier.cu: VarTrimmedDist's tuned ratio -> IcpState::dyn_quantile (sort + fp64 scan + argmin, all on the device)
+struct VarTrimScratch {
+    float *keys_in = nullptr, *keys_out = nullptr;
+    double* cums = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    unsigned int* d_count = nullptr;
+    long long cap = 0;
+};
+void var_trimmed_free(VarTrimScratch& v);
+cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int filter_index, IcpBuffers& b, cudaStream_t s, int* launches);
+
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
                                 float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,
                                 uint32_t* d_vals, int64_t nq, cudaStream_t s);
@@ -240,7 +256,7 @@ cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& 
                             int variant, const float* win3, const float* margin3, cudaStream_t s);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
-                                  cudaStream_t s, int* launches, cudaEvent_t ev_mid);
+                                  cudaStream_t s, int* launches, cudaEvent_t ev_mid, VarTrimScratch* var_scratch);
 cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals, int64_t n,
                              const float* T16 /*host, 4x4*/, cudaStream_t s);
 

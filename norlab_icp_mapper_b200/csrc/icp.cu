@@ -202,7 +202,7 @@ __global__ void __cluster_dims__(kSelCtas, 1, 1) __launch_bounds__(kSelThreads)
         __threadfence();
         cluster_sync_all();
         if (stamper) B200_STAMP(st, 2 + pass * 3);
-        const uint32_t tot = select_pick(gh, nbins, rank, pass == 0, quantile, &s_bin, &s_res, s_scan);
+        const uint32_t tot = select_pick(gh, nbins, rank, pass == 0, quantile < 0.f ? st->dyn_quantile : quantile, &s_bin, &s_res, s_scan);
         if (pass == 0) total = tot;
         rank = s_res;
         prefix = (pass == 0) ? s_bin : ((prefix << (pass == 1 ? 11 : 10)) | s_bin);
@@ -346,9 +346,14 @@ cudaError_t icp_device_setup() {  // once per device (context creation)
 }
 
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it, cudaStream_t s, int* launches,
-                                  cudaEvent_t ev_mid) {
+                                  cudaEvent_t ev_mid, VarTrimScratch* var_scratch) {
     (void)it;
     const long long m = (long long)b.cap_nq * p.knn;
+    if (p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST) {
+        if (!var_scratch) return cudaErrorInvalidValue;
+        cudaError_t e = launch_var_trimmed_ratio(*var_scratch, p, p.quantile_filter, b, s, launches);
+        if (e != cudaSuccess) return e;
+    }
     if (p.quantile_filter >= 0) {
         const size_t dyn = (size_t)kSelCache * sizeof(uint32_t);
         select_kernel<<<kSelCtas, kSelThreads, dyn, s>>>(b.state, b.match_d2, p.knn, b.hist, p.quantile);

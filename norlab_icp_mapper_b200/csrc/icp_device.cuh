@@ -519,7 +519,8 @@ __device__ __forceinline__ void accumulate_entry(float* acc, const IcpParams& pr
         const float p = prm.outlier_param[f];
         bool keep = true;
         switch (prm.outlier_kind[f]) {
-            case B200ICP_OUTLIER_TRIMMED_DIST: keep = d <= qlimit; break;
+            case B200ICP_OUTLIER_TRIMMED_DIST:
+            case B200ICP_OUTLIER_VAR_TRIMMED_DIST: keep = d <= qlimit; break;
             case B200ICP_OUTLIER_MEDIAN_DIST: keep = d <= p * qlimit; break;
             case B200ICP_OUTLIER_MAX_DIST: keep = d <= p * p; break;
             case B200ICP_OUTLIER_MIN_DIST: keep = d >= p * p; break;

@@ -384,15 +384,59 @@ __global__ void __launch_bounds__(256) octree_key_kernel(const float4* __restric
     vals[j] = i;
 }
 
-// sorted by key (stable): run heads survive; samplingMethod 2 replaces the head by the run's centroid
+// counter-based generator of the random sampler: which member of the leaf `key` survives (deterministic per seed)
+__device__ __forceinline__ unsigned long long octree_mix64(unsigned long long x) {  // splitmix64 finaliser
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+// sorted by key (stable: a leaf's members are in insertion order).  One survivor per leaf (LPM OctreeGrid samplers):
+//   0 first point; 2 centroid (written over the first point); 1 random member (uniform; upstream draws from its own
+//   generator, here hash(leaf key, seed) -- same distribution, reproducible); 3 medoid = the member closest to the
+//   leaf's centroid (first one on ties).  In modes 1 and 3 the head thread of a run flags the whole run.
 __global__ void __launch_bounds__(256) octree_mark_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                          long long n_active, int dim, int centroid, float4* __restrict__ feat,
+                                                          long long n_active, int dim, int mode, unsigned long long seed, float4* __restrict__ feat,
                                                           float* __restrict__ nrm, float* __restrict__ prob, uint32_t* __restrict__ remove) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n_active) return;
     const bool head = (j == 0) || (keys[j] != keys[j - 1]);
     const uint32_t i = vals[j];
-    remove[i] = head ? 0u : 1u;
+    const bool centroid = mode == 2;
+    if (mode == 0 || mode == 2) remove[i] = head ? 0u : 1u;
+    if (head && (mode == 1 || mode == 3)) {
+        long long end = j;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        while (end < n_active && keys[end] == keys[j]) {
+            if (mode == 3) {
+                const float4 f = feat[vals[end]];
+                sx += f.x;
+                sy += f.y;
+                sz += f.z;
+            }
+            ++end;
+        }
+        const long long cnt = end - j;
+        long long pick = j;
+        if (mode == 1) {
+            pick = j + (long long)(octree_mix64(keys[j] ^ octree_mix64(seed)) % (unsigned long long)cnt);
+        } else {
+            const float inv = 1.f / (float)cnt;
+            const float mx = sx * inv, my = sy * inv, mz = sz * inv;
+            float best = CUDART_INF_F;
+            for (long long t = j; t < end; ++t) {
+                const float4 f = feat[vals[t]];
+                const float dx = f.x - mx, dy = f.y - my, dz = (dim == 3) ? f.z - mz : 0.f;
+                const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+                if (d < best) {
+                    best = d;
+                    pick = t;
+                }
+            }
+        }
+        for (long long t = j; t < end; ++t) remove[vals[t]] = (t == pick) ? 0u : 1u;
+    }
     if (head && centroid) {
         float sx = 0.f, sy = 0.f, sz = 0.f, sp = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f;
         int cnt = 0;
@@ -489,6 +533,14 @@ __global__ void __launch_bounds__(256) filter_flags_kernel(const float* __restri
             bool inside = x >= f.lo[0] && x <= f.hi[0] && y >= f.lo[1] && y <= f.hi[1];
             if (dim == 3) inside = inside && z >= f.lo[2] && z <= f.hi[2];
             k = f.remove_inside ? !inside : inside;
+        } else if (f.kind == B200ICP_FILTER_RANDOM_SAMPLING) {
+            // keep with probability `dist`: uniform in [0, 1) from a counter-based generator keyed by (seed = dim, chain slot, point index)
+            unsigned long long x = ((unsigned long long)(uint32_t)f.dim << 40) ^ ((unsigned long long)t << 36) ^ (unsigned long long)i;
+            x += 0x9e3779b97f4a7c15ull;
+            x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+            x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+            x ^= x >> 31;
+            k = (float)(x >> 40) * (1.0f / 16777216.0f) < f.dist;
         } else {
             float v, lim;
             if (f.dim == -1) {
@@ -553,8 +605,8 @@ cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, 
     return cudaGetLastError();
 }
 
-cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, int64_t* n_removed,
-                                cudaStream_t s) {
+cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, uint64_t seed,
+                                int64_t* n_removed, cudaStream_t s) {
     cudaError_t e;
     *n_removed = 0;
     if (m.n_active == 0) return cudaSuccess;
@@ -603,7 +655,7 @@ cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float 
                                              std::max(1, 3 * depth), s)) != cudaSuccess)
         return e;
     if ((e = cudaMemsetAsync(m.tmp_u32a, 0, (size_t)(m.n + 1) * sizeof(uint32_t), s)) != cudaSuccess) return e;
-    octree_mark_kernel<<<blocks_for(na), 256, 0, s>>>(m.keys64_b, scratch.vals_out, (long long)na, dim, sampling_method == 2 ? 1 : 0, m.feat,
+    octree_mark_kernel<<<blocks_for(na), 256, 0, s>>>(m.keys64_b, scratch.vals_out, (long long)na, dim, sampling_method, (unsigned long long)seed, m.feat,
                                                       m.has_normals ? m.nrm : nullptr, m.has_prob ? m.prob : nullptr, m.tmp_u32a);
     return store_remove_flagged(m, scratch, dim, n_removed, s);
 }

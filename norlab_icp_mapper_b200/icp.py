@@ -221,6 +221,15 @@ class ICP:
                                                max_point_by_node, sampling_method, C.byref(n_after)))
         return n_after.value
 
+    def filter_cloud(self, features, filters):
+        """DataPointsFilters::apply for the `input:` chain (Mapper.cpp:187-191); filters: mapper.InputFilter entries.
+        Returns the surviving points in input order."""
+        pts = _cloud(features, self.n).copy()
+        n = C.c_int64(len(pts))
+        arr = (type(filters[0]) * len(filters))(*filters) if len(filters) else None
+        self._check(self._L.b200icp_filter_cloud(self._h, pts.ctypes.data, self.n, C.byref(n), arr, len(filters)))
+        return pts[:n.value]
+
     def map_cut_at_threshold(self, threshold, use_larger_than=True):
         n = C.c_int64()
         self._check(self._L.b200icp_map_cut_at_threshold(self._h, threshold, int(use_larger_than), C.byref(n)))

@@ -20,7 +20,8 @@ SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "
 
 
 class InputFilter(C.Structure):
-    """b200icp_filter: kind 1 = BoundingBox{lo, hi, removeInside}, 2 = DistanceLimit{dim, dist, removeInside}."""
+    """b200icp_filter: kind 1 = BoundingBox{lo, hi, removeInside}, 2 = DistanceLimit{dim, dist, removeInside},
+    3 = RandomSampling{prob = dist, seed = dim}."""
     _fields_ = [("kind", C.c_int32), ("lo", C.c_float * 3), ("hi", C.c_float * 3), ("dim", C.c_int32), ("dist", C.c_float),
                 ("remove_inside", C.c_int32)]
 
@@ -37,6 +38,13 @@ def bounding_box(lo, hi, removeInside=True):
 def distance_limit(dist, dim=-1, removeInside=False):
     f = InputFilter()
     f.kind, f.dim, f.dist, f.remove_inside = 2, dim, dist, int(removeInside)
+    return f
+
+
+def random_sampling(prob, seed=0):
+    """RandomSamplingDataPointsFilter{prob}: keep each point with probability prob (reproducible counter-based generator)."""
+    f = InputFilter()
+    f.kind, f.dim, f.dist = 3, int(seed), float(prob)
     return f
 
 

@@ -475,6 +475,7 @@ struct orc_icp {
     float* normals; /* 3 floats per point, or NULL */
     float mean[3];
     orc_kdtree* tree;
+    float last_var_ratio; /* VarTrimmed: the tuned ratio of the last iteration (diagnostic) */
     char err[256];
 };
 
@@ -493,6 +494,7 @@ void orc_icp_destroy(orc_icp* o) {
     free(o);
 }
 const char* orc_icp_last_error(const orc_icp* o) { return o ? o->err : "null oracle"; }
+float orc_icp_last_var_ratio(const orc_icp* o) { return o ? o->last_var_ratio : 0.f; }
 void orc_icp_get_mean(const orc_icp* o, float mean[3]) {
     for (int d = 0; d < 3; ++d) mean[d] = o->mean[d];
 }
@@ -571,6 +573,47 @@ static int dists_quantile(const float* d2, int64_t m, float quantile, float* out
     int64_t idx = (int64_t)((float)cnt * quantile);
     if (idx >= cnt) idx = cnt - 1;
     *out = nth_element_f32(scratch, cnt, idx);
+    return 0;
+}
+
+static int cmp_f32(const void* a, const void* b) {
+    const float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* LPM OutlierFiltersImpl.cpp VarTrimmedDistOutlierFilter::optimizeInlierRatio: the finite, positive squared
+ * distances sorted ascending, their running sum (std::partial_sum in T = float), then over the indices
+ * [floor(minRatio n), floor(maxRatio n)) -- n = rows * cols of the match matrix -- the minimum of
+ * FRMS_i = (1 / (id_i / n)^lambda)^2 * cumsum_i / id_i, id_i = i + 1; returns (argmin + minEl) / n.
+ * Upstream maps n entries of the running-sum vector even when fewer distances qualified (reading past its end);
+ * here the range is clipped to the entries that exist. */
+static int var_trimmed_ratio(const float* d2, int64_t m, float min_ratio, float max_ratio, float lambda, float* ratio, float* scratch) {
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < m; ++i)
+        if (d2[i] != INFINITY && d2[i] > 0.f) scratch[cnt++] = d2[i];
+    if (cnt == 0) return -1;
+    qsort(scratch, (size_t)cnt, sizeof(float), cmp_f32);
+    float run = 0.f;
+    for (int64_t i = 0; i < cnt; ++i) {
+        run += scratch[i];
+        scratch[i] = run;
+    }
+    int64_t min_el = (int64_t)floorf(min_ratio * (float)m), max_el = (int64_t)floorf(max_ratio * (float)m);
+    if (max_el > cnt) max_el = cnt;
+    if (min_el >= max_el) min_el = max_el > 0 ? max_el - 1 : 0;
+    float best = INFINITY;
+    int64_t best_i = 0;
+    for (int64_t i = min_el; i < max_el; ++i) {
+        const float id = (float)(i + 1);
+        const float deno = powf(id / (float)m, lambda);
+        const float inv = 1.f / deno;
+        const float frms = inv * inv * scratch[i] * (1.f / id);
+        if (frms < best) {
+            best = frms;
+            best_i = i - min_el;
+        }
+    }
+    *ratio = (float)(best_i + min_el) / (float)m;
     return 0;
 }
 
@@ -685,6 +728,15 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
                     limit = prm * limit;
                     for (int64_t i = 0; i < m; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;
                     break;
+                case B200ICP_OUTLIER_VAR_TRIMMED_DIST: {
+                    float ratio = 0.f;
+                    if (var_trimmed_ratio(d2, m, prm, cfg->outlier_param2[f], cfg->outlier_param3[f], &ratio, scratch))
+                        FAIL(o, B200ICP_ERR_CONVERGENCE, "Inlier ratio optimization failed: no finite distances");
+                    if (dists_quantile(d2, m, ratio, &limit, scratch)) FAIL(o, B200ICP_ERR_CONVERGENCE, "no outlier to filter");
+                    for (int64_t i = 0; i < m; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;
+                    o->last_var_ratio = ratio;
+                    break;
+                }
                 case B200ICP_OUTLIER_MAX_DIST:
                     limit = prm * prm;
                     for (int64_t i = 0; i < m; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;

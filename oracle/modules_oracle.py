@@ -39,14 +39,51 @@ def octree_leaf_keys(xyz, max_size_by_node):
     return keys, depth
 
 
-def octree_grid_filter(features, max_size_by_node, sampling_method=0, descriptors=None):
+def _mix64(x):
+    """splitmix64 finaliser on Python ints (the random sampler's counter-based generator)."""
+    m = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & m
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & m
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & m
+    return x ^ (x >> 31)
+
+
+def octree_grid_filter(features, max_size_by_node, sampling_method=0, descriptors=None, seed=0x0c7ee5eed):
     """LPM DataPointsFilters/OctreeGrid.cpp with maxPointByNode 1 (ref: OctreeMapperModule.cpp:35-39 after
-    map.concatenate).  One survivor per leaf: method 0 = first point (lowest index), 2 = centroid.
+    map.concatenate).  One survivor per leaf: method 0 = first point (lowest index), 2 = centroid, 1 = random
+    member (upstream: its own generator; here member hash(leaf key, seed) mod count of the leaf, members in
+    input order), 3 = medoid (member closest to the leaf's centroid, first one on ties).
     Returns (indices of the leaf representatives in input order, survivor features, survivor descriptors)."""
     feat = np.asarray(features, f32)
     dim = feat.shape[1] - 1
     keys, depth = octree_leaf_keys(feat[:, :dim], max_size_by_node)
     uniq, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
+    if sampling_method in (1, 3):
+        members = {}
+        for i, k in enumerate(keys):
+            members.setdefault(int(k), []).append(i)
+        picks = []
+        for k, idx in members.items():
+            if sampling_method == 1:
+                picks.append(idx[_mix64(k ^ _mix64(seed)) % len(idx)])
+            else:
+                acc = np.zeros(dim, f32)
+                for i in idx:  # sequential fp32 sums in index order, like the device's run walk
+                    acc = (acc + feat[i, :dim]).astype(f32)
+                mean = (acc * f32(f32(1.0) / f32(len(idx)))).astype(f32)
+                best, pick = np.inf, idx[0]
+                for i in idx:
+                    dlt = (feat[i, :dim] - mean).astype(f32)
+                    sq = f32(0)
+                    for c in range(dim):
+                        sq = f32(sq + f32(dlt[c] * dlt[c]))
+                    d = np.sqrt(sq, dtype=f32)
+                    if d < best:
+                        best, pick = d, i
+                picks.append(pick)
+        order = np.sort(np.array(picks, np.int64))
+        out_desc = None if descriptors is None else np.asarray(descriptors, f32)[order].copy()
+        return order, feat[order].copy(), out_desc
     order = np.sort(first)
     out_feat = feat[order].copy()
     out_desc = None if descriptors is None else np.asarray(descriptors, f32)[order].copy()
@@ -161,3 +198,15 @@ def distance_limit_keep(features, dist, dim_index=-1, remove_inside=False, n_dim
         v = p[:, dim_index]
         lim = f32(dist)
     return (v > lim) if remove_inside else (v < lim)
+
+
+def random_sampling_keep(n, prob, seed=0, slot=0):
+    """RandomSamplingDataPointsFilter{prob} as this project defines its generator (upstream: rand() < prob * RAND_MAX, any
+    stream): point i of the cloud entering the chain survives when u < prob, u = top 24 bits of
+    splitmix64((seed << 40) ^ (chain slot << 36) ^ i) / 2^24."""
+    keep = np.zeros(n, bool)
+    p = f32(prob)
+    for i in range(n):
+        x = _mix64(((seed & 0xFFFFFFFF) << 40) ^ (slot << 36) ^ i)
+        keep[i] = f32(x >> 40) * f32(1.0 / 16777216.0) < p
+    return keep

@@ -203,6 +203,21 @@ def test_one_barrier_iterations(pair3d, chain, monkeypatch):
         assert outs[name][4] == outs["general"][4]
 
 
+def test_var_trimmed_dist_outlier_filter(oracle, pair3d):
+    """VarTrimmedDistOutlierFilter (LPM defaults minRatio 0.05, maxRatio 0.99, lambda 0.95): the ratio is tuned every
+    iteration from the sorted distances.  The device sums in fp64 where upstream (and the oracle) sum sequentially in
+    fp32, so the tuned ratio may differ in its last digits: poses must agree to the BASELINE tolerance, the kept
+    pairs to a fraction of a percent."""
+    for k, minimizer in ((1, "point_to_plane"), (3, "point_to_point")):
+        cfg = make_config(dim=3, knn=k, max_dist=1.0, outliers=(("var_trimmed", 0.05, 0.99, 0.95),), minimizer=minimizer, max_iteration_count=15)
+        T_g, res_g, tr_g, T_o, res_o, tr_o = _both(oracle, cfg, pair3d)
+        er, et = synth.pose_error(T_g, T_o)
+        assert er <= TOL_RAD and et <= TOL_M, (k, er, et)
+        assert res_g.iterations == res_o.iterations == 15
+        assert abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.01 * res_o.pairs_last_iter, (res_g.pairs_last_iter, res_o.pairs_last_iter)
+        assert 0.3 * k * len(pair3d["reading"]) < res_g.pairs_last_iter < 0.995 * k * len(pair3d["reading"])
+
+
 def test_error_behaviour_matches_libpointmatcher(oracle, pair3d):
     from norlab_icp_mapper_b200.icp import ICP, B200ICPError
     cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=5)

@@ -65,13 +65,39 @@ def test_octree_centroid_sampling_with_descriptors(gpu, pair):
     np.testing.assert_allclose(prob, odesc[:, 0], rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("method", [1, 3])
+def test_octree_random_and_medoid_sampling(gpu, pair, method):
+    """samplingMethod 1 (the one examples/config.yaml:48-51 uses) and 3: one survivor per leaf, a member of that leaf;
+    the random pick follows the documented counter-based generator, the medoid is the member closest to the centroid."""
+    m, inp = pair["map"][:60_000], pair["reading"]
+    gpu.set_map(m, None)
+    n_after = gpu.map_octree(inp, 0.5, sampling_method=method)
+    feat, _ = gpu.map_download()
+    allpts = np.r_[m, inp]
+    order, ofeat, _ = mo.octree_grid_filter(allpts, 0.5, method)
+    assert n_after == len(feat) == len(order)
+    keys_all, _ = mo.octree_leaf_keys(allpts[:, :3], 0.5)
+    assert len(np.unique(keys_all)) == n_after
+    assert _rows(feat) <= _rows(allpts)  # survivors are input points, untouched
+    if method == 3:  # fp32 ties between equidistant members may resolve differently under FMA contraction: allow a few
+        assert len(_rows(feat) ^ _rows(ofeat)) <= 2 * max(1, n_after // 2000)
+    else:
+        assert np.array_equal(feat, ofeat)
+    # a second call draws with the next seed: still one member per leaf
+    if method == 1:
+        n2 = gpu.map_octree(inp[:0], 0.5, sampling_method=1)
+        assert n2 == n_after
+
+
 def test_octree_rejects_what_is_not_implemented(gpu, pair):
     from norlab_icp_mapper_b200._lib import B200ICPError
     gpu.set_map(pair["map"][:1000], None)
-    for kw in (dict(sampling_method=1), dict(sampling_method=3), dict(max_point_by_node=4)):
-        with pytest.raises(B200ICPError) as e:
-            gpu.map_octree(pair["reading"][:100], 0.15, **kw)
-        assert e.value.status == _abi.ERR_NOT_IMPLEMENTED
+    with pytest.raises(B200ICPError) as e:
+        gpu.map_octree(pair["reading"][:100], 0.15, max_point_by_node=4)
+    assert e.value.status == _abi.ERR_NOT_IMPLEMENTED
+    with pytest.raises(B200ICPError) as e:
+        gpu.map_octree(pair["reading"][:100], 0.15, sampling_method=7)
+    assert e.value.status == _abi.ERR_INVALID_ARG
 
 
 def test_cut_at_descriptor_threshold(gpu, pair):
@@ -127,3 +153,19 @@ def test_dynamic_points_missing_fields(gpu, pair):
     with pytest.raises(B200ICPError) as e:  # input without probabilityDynamic
         gpu.map_dynamic_points(pair["reading"][:100], None, pose)
     assert e.value.status == _abi.ERR_INVALID_FIELD and "probabilityDynamic" in str(e.value)
+
+
+def test_input_filter_chain_with_random_sampling(gpu, pair):
+    """BoundingBox + DistanceLimit + RandomSampling (docs/MapperConfiguration.md input chain) in one predicate pass:
+    same survivors, same order as the oracle predicates; the sampling rate is what was asked for."""
+    from norlab_icp_mapper_b200.mapper import bounding_box, distance_limit, random_sampling
+    pts = pair["reading"]
+    chain = [bounding_box((-1.5, -1.0, -1.0), (0.5, 1.0, 0.5), True), random_sampling(0.3, seed=7), distance_limit(60.0, -1, False)]
+    out = gpu.filter_cloud(pts, chain)
+    keep = mo.bounding_box_keep(pts, (-1.5, -1.0, -1.0), (0.5, 1.0, 0.5), True)
+    keep &= mo.random_sampling_keep(len(pts), 0.3, seed=7, slot=1)
+    keep &= mo.distance_limit_keep(pts, 60.0, -1, False)
+    assert np.array_equal(out, pts[keep])
+    rate = mo.random_sampling_keep(len(pts), 0.3, seed=7, slot=1).mean()
+    assert abs(rate - 0.3) < 0.02
+    assert len(gpu.filter_cloud(pts, [random_sampling(1.0)])) == len(pts) and len(gpu.filter_cloud(pts, [random_sampling(0.0)])) == 0

@@ -48,3 +48,24 @@ def test_filters():
     assert mo.bounding_box_keep(p, [-1.5, -1, -1], [0.5, 1, 0.5], True).tolist() == [False, True, True, True]
     assert mo.distance_limit_keep(p, 3.5).tolist() == [True, True, True, False]
     assert mo.cut_at_descriptor_threshold([0.1, 0.65, 0.7], 0.65).tolist() == [True, True, False]
+
+
+def test_octree_random_and_medoid_oracle():
+    rng = np.random.default_rng(5)
+    p = np.c_[rng.uniform(-5, 5, (4000, 3)), np.ones(4000)].astype(np.float32)
+    keys, _ = mo.octree_leaf_keys(p[:, :3], 1.0)
+    for method in (1, 3):
+        order, feat, _ = mo.octree_grid_filter(p, 1.0, method)
+        assert len(order) == len(np.unique(keys)) and len(np.unique(keys[order])) == len(order)  # one member per leaf
+    a = mo.octree_grid_filter(p, 1.0, 1, seed=1)[0]
+    b = mo.octree_grid_filter(p, 1.0, 1, seed=2)[0]
+    assert not np.array_equal(a, b) and np.array_equal(a, mo.octree_grid_filter(p, 1.0, 1, seed=1)[0])
+    # medoid of a leaf with a clear centre: the centre point wins
+    q = np.array([[0.1, 0.1, 0.1, 1], [0.2, 0.2, 0.2, 1], [0.3, 0.3, 0.3, 1], [5, 5, 5, 1]], np.float32)
+    order, _, _ = mo.octree_grid_filter(q, 3.0, 3)
+    assert 1 in order.tolist()
+
+
+def test_random_sampling_oracle_rate():
+    k = mo.random_sampling_keep(20000, 0.25, seed=3)
+    assert abs(k.mean() - 0.25) < 0.01 and not np.array_equal(k, mo.random_sampling_keep(20000, 0.25, seed=4))
