@@ -255,6 +255,45 @@ __device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT)
     }
 }
 
+// Symmetric 3x3 eigen-decomposition for the point-to-point SVD: cyclic Jacobi in fp64 like jacobi_eig_f64, but the
+// sweep stops at a RELATIVE off-diagonal level (1e-30 of the squared diagonal: far below fp64 resolution) instead of
+// running on until the off-diagonals underflow, and a rotation costs one sqrt, one division and one rsqrt.  This
+// serial chain runs once per ICP iteration on one thread: it was ~20 us of every point-to-point iteration.
+__device__ __noinline__ void jacobi_eig3_f64(double* A, double* V, double* w) {
+    for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        const double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+        const double dia = A[0] * A[0] + A[4] * A[4] + A[8] * A[8];
+        if (!(off > 1e-30 * dia) || off < 1e-300) break;
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                const double apq = A[q * 3 + p];
+                if (fabs(apq) < 1e-300) continue;
+                const double app = A[p * 3 + p], aqq = A[q * 3 + q];
+                const double d = aqq - app;
+                // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)), theta = d / (2 apq), without forming theta
+                const double t = (d >= 0 ? 2.0 : -2.0) * apq / (fabs(d) + sqrt(d * d + 4.0 * apq * apq));
+                const double c = rsqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = A[p * 3 + k], akq = A[q * 3 + k];
+                    A[p * 3 + k] = c * akp - sn * akq;
+                    A[q * 3 + k] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = A[k * 3 + p], aqk = A[k * 3 + q];
+                    A[k * 3 + p] = c * apk - sn * aqk;
+                    A[k * 3 + q] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[p * 3 + k], vkq = V[q * 3 + k];
+                    V[p * 3 + k] = c * vkp - sn * vkq;
+                    V[q * 3 + k] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = A[i * 3 + i];
+}
+
 // LPM PointToPointErrorMinimizer::compute_in_place: weighted centroids, SVD of the cross-covariance.
 __device__ __noinline__ void delta_point_to_point(const double* S, int dim, float* dT) {
     for (int i = 0; i < 16; ++i) dT[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -267,6 +306,27 @@ __device__ __noinline__ void delta_point_to_point(const double* S, int dim, floa
     double M[9];
     for (int r = 0; r < dim; ++r)
         for (int c = 0; c < dim; ++c) M[c * dim + r] = S[7 + c * 3 + r] - sw * mq[r] * mp[c];
+    if (dim == 2) {
+        // R = U diag(1, det(U V^T)) V^T of a 2x2 M in closed form: the rotation that maximises tr(R^T M),
+        // (cos, sin) parallel to (M00 + M11, M10 - M01).  Degenerate M (both zero): identity, like a zero SVD.
+        const double a = M[0] + M[3], b = M[1] - M[2];  // M[c * 2 + r]
+        const double hyp = sqrt(a * a + b * b);
+        double cs = 1.0, sn = 0.0;
+        if (hyp > 0.0) {
+            cs = a / hyp;
+            sn = b / hyp;
+        }
+        dT[0] = (float)cs;
+        dT[1] = (float)sn;
+        dT[4] = (float)-sn;
+        dT[5] = (float)cs;
+        for (int r = 0; r < 2; ++r) {
+            float acc = 0.f;
+            for (int c = 0; c < 2; ++c) acc += dT[c * 4 + r] * (float)mp[c];
+            dT[12 + r] = (float)mq[r] - acc;
+        }
+        return;
+    }
     double MtM[9], V[9], ev[3];
     for (int r = 0; r < dim; ++r)
         for (int c = 0; c < dim; ++c) {
@@ -274,7 +334,7 @@ __device__ __noinline__ void delta_point_to_point(const double* S, int dim, floa
             for (int j = 0; j < dim; ++j) a += M[r * dim + j] * M[c * dim + j];
             MtM[c * dim + r] = a;
         }
-    jacobi_eig_f64(MtM, dim, V, ev);
+    jacobi_eig3_f64(MtM, V, ev);
     int order[3] = {0, 1, 2};
     for (int a = 0; a < dim; ++a)
         for (int bb = a + 1; bb < dim; ++bb)

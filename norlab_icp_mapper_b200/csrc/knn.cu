@@ -166,8 +166,12 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
         }
     }
     const int warm = (variant & 0x10000) ? 1 : 0;  // set by the ICP loop from iteration 1 on (out_ids = previous matches, positions)
-    if (k <= 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
-    if (k <= 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
+    // lanes per query: at least k (lane j holds the j-th best); few queries get more lanes each -- a query's latency is what
+    // is left to cut when the whole batch does not even fill the SMs (10 k queries x 8 lanes = a quarter of the B200)
+    int lanes = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
+    while (lanes < 32 && (long long)nq_capacity * lanes * 2 <= (long long)kSMs * 2048) lanes *= 2;
+    if (lanes == 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
+    if (lanes == 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
     return launch_one<32, AccK<32>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
 }
 
