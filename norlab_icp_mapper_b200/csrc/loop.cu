@@ -250,6 +250,27 @@ __device__ __forceinline__ float row_gap2(const GridView& g, float uy, float uz,
     return gy * gy + gz * gz;
 }
 
+// The runs [s, e) the four lanes of a group hold (one cell row each, possibly empty), concatenated, are scanned by the
+// four lanes together: balanced, and a lane quartet reads 64 contiguous bytes.  Returns the group-wide best distance.
+__device__ __forceinline__ float scan_runs4(const GridView& g, float qx, float qy, float qz, uint32_t s, uint32_t e, float& bd, int& bp, float& sd,
+                                            int lig, unsigned gmask) {
+    constexpr int G = 4;
+    const uint32_t n = e - s;
+    const uint32_t n0 = __shfl_sync(gmask, n, 0, G), n1 = __shfl_sync(gmask, n, 1, G), n2 = __shfl_sync(gmask, n, 2, G), n3 = __shfl_sync(gmask, n, 3, G);
+    const uint32_t p1 = n0, p2 = p1 + n1, p3 = p2 + n2, N = p3 + n3;
+    const uint32_t o0 = __shfl_sync(gmask, s, 0, G), o1 = __shfl_sync(gmask, s, 1, G) - p1, o2 = __shfl_sync(gmask, s, 2, G) - p2,
+                   o3 = __shfl_sync(gmask, s, 3, G) - p3;
+#pragma unroll 2
+    for (uint32_t k = (uint32_t)lig; k < N; k += G) {
+        const uint32_t j = k + (k >= p2 ? (k >= p3 ? o3 : o2) : (k >= p1 ? o1 : o0));
+        test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
+    }
+    float v = bd;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
+    return v;
+}
+
 // bd / bp / sd start at inf / -1 / inf in every lane: the previous match only bounds the ball (tau0) and is found
 // again by the scan like any other point.
 __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float qy, float qz, float tau0, float m, float& bd, int& bp,
@@ -273,24 +294,9 @@ __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float 
             const float cov = sqrtf(gb) + m;
             if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
         }
-        // the four runs, concatenated, are scanned by the four lanes together (balanced, 64-byte coalesced)
-        const uint32_t n = e - s;
-        const uint32_t n0 = __shfl_sync(gmask, n, 0, G), n1 = __shfl_sync(gmask, n, 1, G), n2 = __shfl_sync(gmask, n, 2, G),
-                       n3 = __shfl_sync(gmask, n, 3, G);
-        const uint32_t p1 = n0, p2 = p1 + n1, p3 = p2 + n2, N = p3 + n3;
-        const uint32_t o0 = __shfl_sync(gmask, s, 0, G), o1 = __shfl_sync(gmask, s, 1, G) - p1, o2 = __shfl_sync(gmask, s, 2, G) - p2,
-                       o3 = __shfl_sync(gmask, s, 3, G) - p3;
-#pragma unroll 2
-        for (uint32_t k = (uint32_t)lig; k < N; k += G) {
-            const uint32_t j = k + (k >= p2 ? (k >= p3 ? o3 : o2) : (k >= p1 ? o1 : o0));
-            test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
-        }
-        float v = bd;
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
-        gb = fminf(v, tau0);
+        gb = fminf(scan_runs4(g, qx, qy, qz, s, e, bd, bp, sd, lig, gmask), tau0);
     }
-    // phase 2: the rest of the (tightened) ball's cover -- usually nothing
+    // phase 2: the rest of the (tightened) ball's cover -- usually nothing; four rows at a time, same scan
     const float rt = fminf((sqrtf(gb) + m) * g.inv_h + slack, 3.0e8f);
     const int ylo = max(0, floor_to_int(fmaxf(uy - rt, -1.f)));
     const int yhi = min(g.ny - 1, floor_to_int(fminf(uy + rt, (float)g.ny)));
@@ -300,16 +306,18 @@ __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float 
     if (wy <= 0 || wz <= 0) return;
     if (ylo >= min(cy, y1) && yhi <= max(cy, y1) && zlo >= min(cz, z1) && zhi <= max(cz, z1)) return;  // inside the 2 x 2 block
     const int nrows = wy * wz;
-    for (int r = lig; r < nrows; r += G) {
-        const int y = ylo + r % wy, z = zlo + r / wy;
-        if ((y == cy || y == y1) && (z == cz || z == z1)) continue;  // done in phase 1
-        const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
-        const float cov = sqrtf(fminf(bd, gb)) + m;  // this lane's covered radius from here on (never below the final one)
-        if (gyz2 > cov * cov) continue;
+    for (int base = 0; base < nrows; base += G) {  // group-uniform trip count
+        const int r = base + lig;
         uint32_t s = 0, e = 0;
-        row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
-#pragma unroll 4
-        for (uint32_t j = s; j < e; ++j) test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
+        if (r < nrows) {
+            const int y = ylo + r % wy, z = zlo + r / wy;
+            if (!((y == cy || y == y1) && (z == cz || z == z1))) {  // (those were phase 1)
+                const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
+                const float cov = sqrtf(gb) + m;  // covered radius from here on (never below the final one)
+                if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
+            }
+        }
+        gb = fminf(scan_runs4(g, qx, qy, qz, s, e, bd, bp, sd, lig, gmask), tau0);
     }
 }
 
@@ -505,10 +513,19 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     if (lig == 0) {
                         float L = fminf(sqrtf(gsd), cover);
                         L -= 2e-6f * L;
-                        // position only: coordinates and normal of a NEW match are fetched by the classify pass
-                        // (thread per entry, one round trip for all of them); -(pos + 2) marks them stale
-                        ppp->w = __int_as_float((gbp >= 0 && gbp != pos) ? -(gbp + 2) : gbp);
-                        pnv->w = L;
+                        if ((variant_flags & 128) || gbp < 0 || gbp == pos) {
+                            // (bit 7: defer) position only: coordinates and normal of a NEW match are fetched after the
+                            // search phase, thread per entry; -(pos + 2) marks them stale
+                            ppp->w = __int_as_float((gbp >= 0 && gbp != pos) ? -(gbp + 2) : gbp);
+                            pnv->w = L;
+                        } else {  // new match: its coordinates and normal go into the cache now
+                            float4 pt = __ldg(g.pts + gbp), nn = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (MIN == 0) nn = __ldg(nrm + gbp);
+                            pt.w = __int_as_float(gbp);
+                            nn.w = L;
+                            *ppp = pt;
+                            *pnv = nn;
+                        }
                         *pd2 = gbd;
                     }
                     }
@@ -542,6 +559,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 }
             }
         }
+        if (stamper) B200_STAMP(gst, 30);
         if (searched && tid < 16) s_Tprev[tid] = st.T[tid];  // the bounds now refer to this iteration's query positions
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0 && searched) {
