@@ -203,6 +203,32 @@ def test_one_barrier_iterations(pair3d, chain, monkeypatch):
         assert outs[name][4] == outs["general"][4]
 
 
+def test_large_reading_spills_the_match_cache(oracle):
+    """A CTA of the loop kernel keeps 2048 queries in shared memory and walks its slice 1024 at a time: a 360 k-point
+    reading (2433 per CTA) exercises the multi-block walk and the global-memory spill of the cache.  Same pose as the
+    oracle, identical to the general path and to the exhaustive search."""
+    from norlab_icp_mapper_b200.icp import ICP
+    d = synth.make_pair_3d(n_map=300_000, n_scan=360_000, seed=77)
+    outs = {}
+    for variant in (0, 32, 16 | 64):
+        cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.8),), minimizer="point_to_plane", max_iteration_count=12, nn_variant=variant)
+        g = ICP(cfg)
+        g.set_map(d["map"], d["normals"])
+        outs[variant] = (g(d["reading"]), g.last_result.pairs_last_iter, g.last_result.overlap)
+        g.close()
+    assert np.array_equal(outs[0][0], outs[32][0]) and outs[0][1:] == outs[32][1:]
+    assert outs[0][1:] == outs[16 | 64][1:]
+    er, et = synth.pose_error(outs[0][0], outs[16 | 64][0])
+    assert er <= 1e-6 and et <= 1e-5, (er, et)
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.8),), minimizer="point_to_plane", max_iteration_count=12)
+    o = oracle.OracleICP(cfg)
+    o.set_map(d["map"], d["normals"])
+    rc, T_o, res_o, _, _ = o.register(d["reading"])
+    er, et = synth.pose_error(outs[0][0], T_o)
+    assert rc == _abi.OK and er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert outs[0][1] == res_o.pairs_last_iter
+
+
 def test_var_trimmed_dist_outlier_filter(oracle, pair3d):
     """VarTrimmedDistOutlierFilter (LPM defaults minRatio 0.05, maxRatio 0.99, lambda 0.95): the ratio is tuned every
     iteration from the sorted distances.  The device sums in fp64 where upstream (and the oracle) sum sequentially in
