@@ -8,6 +8,9 @@
 #include <string>
 #include <vector>
 
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
 #include "common.cuh"
 
 using namespace b200;
@@ -37,6 +40,12 @@ struct b200icp_ctx {
     int* d_scalar_nq = nullptr;
     unsigned* d_bar_counter = nullptr;
     int n_sms = 148;
+    float* d_kth = nullptr;      // incremental SurfaceNormal: squared k-th neighbour distance per store point
+    int64_t cap_kth = 0;
+    uint8_t* d_dirty = nullptr;  // ... dirty flags (store order, then index order)
+    uint32_t* d_list = nullptr;  // ... index positions to recompute
+    int64_t cap_dirty = 0;
+    int64_t last_normals_recomputed = 0;
     uint64_t octree_calls = 0;  // advances the random sampler's seed from one b200icp_map_octree call to the next
     float margin3[3] = {3.0f, 0.002f, 0.25f};  // search margin of the loop kernel's match cache; B200ICP_MARGIN="gain,min[m],max[cells]"
     float win3[3] = {2.0f, 0.0015f, 0.12f};  // quantile-window policy of the one-barrier iteration (loop.cu); B200ICP_WINDOW="gain,floor,max"
@@ -246,8 +255,12 @@ int32_t commit_index(b200icp_ctx* ctx) {
     float cell_hint = 0.f;
     if (const char* env = getenv("B200ICP_CELL_EDGE")) cell_hint = (float)atof(env);
     CK(cudaEventRecord(ctx->ev_map0, s));
-    CK(grid_build(ctx->map, reinterpret_cast<const float*>(st.feat), 4, ctx->cfg.dim, st.has_normals ? st.nrm : nullptr, st.n_active,
+    // (normals of the points that already had some are carried along even when the cloud formally lost the descriptor to a
+    //  concatenate: the incremental SurfaceNormal pass reuses them; has_normals below keeps the formal truth)
+    const bool carry_normals = st.has_normals || (st.nrm_epoch_ok && st.nrm != nullptr);
+    CK(grid_build(ctx->map, reinterpret_cast<const float*>(st.feat), 4, ctx->cfg.dim, carry_normals ? st.nrm : nullptr, st.n_active,
                   /*centre=*/true, cell_hint, s, st.all_loaded ? nullptr : st.active));
+    ctx->map.has_normals = st.has_normals;
     CK(cudaEventRecord(ctx->ev_map1, s));
     CK(cudaStreamSynchronize(s));
     float ms = 0.f;
@@ -404,6 +417,9 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaFree(b.state);
     cudaFree(b.trace);
     var_trimmed_free(ctx->var_scratch);
+    cudaFree(ctx->d_kth);
+    cudaFree(ctx->d_dirty);
+    cudaFree(ctx->d_list);
     cudaFree(b.fastws);
     cudaFree(b.spill_pp);
     cudaFree(b.spill_nv);
@@ -931,27 +947,105 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
     }
     cudaStream_t s = ctx->stream;
     const int64_t n = ctx->map.view.n;
-    const int32_t eb = ensure_query_buffers(ctx, n, knn);
-    if (eb != B200ICP_OK) return eb;
     if (n > ctx->map.cap_normals) {
+        // (the index was built without normals: nothing to preserve)
         cudaFree(ctx->map.normals);
         ctx->map.normals = nullptr;
         ctx->map.cap_normals = 0;
         CK(cudaMalloc((void**)&ctx->map.normals, (size_t)grow_capacity(n) * sizeof(float4)));
         ctx->map.cap_normals = grow_capacity(n);
     }
+    // k-th neighbour distance per store point (incremental bookkeeping); grows with the store, content preserved
+    if (st.n > ctx->cap_kth) {
+        const int64_t cap = grow_capacity(st.n);
+        float* nk = nullptr;
+        CK(cudaMalloc((void**)&nk, (size_t)cap * sizeof(float)));
+        if (ctx->d_kth && st.nrm_epoch_ok && st.nrm_epoch_n > 0)
+            CK(cudaMemcpyAsync(nk, ctx->d_kth, (size_t)std::min<int64_t>(st.nrm_epoch_n, ctx->cap_kth) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        cudaFree(ctx->d_kth);
+        ctx->d_kth = nk;
+        ctx->cap_kth = cap;
+    }
     int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
-    *h_nq = (int)n;
-    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-    // self k-NN: the queries are the cell-sorted map points themselves (neighbouring threads share cells)
-    CK(launch_knn(ctx->map.view, ctx->map.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
-                  /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
-    CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->map.normals, st.nrm, s));
+
+    // ---- incremental pass: only appends since the last pass -> recompute the new points and the old points that have a new
+    //      point within their k-th neighbour distance; every other point keeps the neighbours, hence the normal, it had ----
+    const int64_t n_new = st.n - st.nrm_epoch_n;
+    const bool incremental = st.nrm_epoch_ok && st.nrm_epoch_k == knn && n_new >= 0 && st.nrm_epoch_n > 0 && n_new * 4 <= st.n &&
+                             !getenv("B200ICP_FULL_NORMALS");
+    ctx->last_normals_recomputed = n;
+    if (incremental && n_new == 0) {
+        ctx->last_normals_recomputed = 0;
+    } else if (incremental) {
+        // grid over the new points alone (map frame, not centred)
+        CK(grid_build(ctx->aux, reinterpret_cast<const float*>(st.feat + st.nrm_epoch_n), 4, ctx->cfg.dim, nullptr, n_new, /*centre=*/false, 0.f, s));
+        if (st.n + n > ctx->cap_dirty) {
+            cudaFree(ctx->d_dirty);
+            cudaFree(ctx->d_list);
+            ctx->d_dirty = nullptr;
+            ctx->d_list = nullptr;
+            ctx->cap_dirty = 0;
+            const int64_t cap = grow_capacity(st.n + n);
+            CK(cudaMalloc((void**)&ctx->d_dirty, (size_t)cap));
+            CK(cudaMalloc((void**)&ctx->d_list, (size_t)cap * sizeof(uint32_t)));
+            ctx->cap_dirty = cap;
+        }
+        uint8_t* d_dirty = ctx->d_dirty;         // per store index
+        uint8_t* d_flag = ctx->d_dirty + st.n;   // per cell-sorted position of the live index
+        CK(launch_normals_dirty(ctx->aux.view, st, ctx->d_kth, st.nrm_epoch_n, d_dirty, s));
+        CK(launch_normals_positions(ctx->map.view, d_dirty, d_flag, s));
+        unsigned int* d_count = reinterpret_cast<unsigned int*>(ctx->d_scalar_nq) + 4;
+        size_t need = 0;
+        thrust::counting_iterator<uint32_t> counting(0u);
+        cub::DeviceSelect::Flagged(nullptr, need, counting, d_flag, ctx->d_list, d_count, (int)n);
+        if (need > ctx->map.cub_tmp_bytes) {
+            cudaFree(ctx->map.cub_tmp);
+            ctx->map.cub_tmp = nullptr;
+            ctx->map.cub_tmp_bytes = 0;
+            CK(cudaMalloc(&ctx->map.cub_tmp, need + 256));
+            ctx->map.cub_tmp_bytes = need + 256;
+        }
+        size_t bytes = ctx->map.cub_tmp_bytes;
+        CK(cub::DeviceSelect::Flagged(ctx->map.cub_tmp, bytes, counting, d_flag, ctx->d_list, d_count, (int)n, s));
+        unsigned int m = 0;
+        CK(cudaMemcpyAsync(&m, d_count, sizeof(m), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->last_normals_recomputed = m;
+        if (m > 0) {
+            const int32_t eb = ensure_query_buffers(ctx, m, knn);
+            if (eb != B200ICP_OK) return eb;
+            CK(launch_normals_gather(ctx->map.view, ctx->d_list, d_count, m, ctx->d_q4, s));
+            *h_nq = (int)m;
+            CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(launch_knn(ctx->map.view, ctx->d_q4, ctx->d_scalar_nq, (int)m, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+                          /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+            CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, ctx->d_list, d_count, m, ctx->map.normals, st.nrm,
+                              ctx->d_kth, s));
+        }
+    } else {
+        const int32_t eb = ensure_query_buffers(ctx, n, knn);
+        if (eb != B200ICP_OK) return eb;
+        *h_nq = (int)n;
+        CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+        // self k-NN: the queries are the cell-sorted map points themselves (neighbouring threads share cells)
+        CK(launch_knn(ctx->map.view, ctx->map.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+                      /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+        CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->map.normals, st.nrm, ctx->d_kth, s));
+    }
     CK(cudaStreamSynchronize(s));
     ctx->map.has_normals = true;
     st.has_normals = true;
+    // bookkeeping valid when every store point is in the index (parked points keep what they had and are recomputed
+    // wholesale when the window moves: store_window invalidates)
+    st.nrm_epoch_ok = true;
+    st.nrm_epoch_n = st.n;
+    st.nrm_epoch_k = knn;
     return B200ICP_OK;
 }
+
+/* development aid / tests (not in the public header): points whose normal the last b200icp_map_surface_normals recomputed */
+int64_t b200icp_debug_normals_recomputed(const b200icp_ctx* ctx) { return ctx ? ctx->last_normals_recomputed : -1; }
 
 int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed) {
     if (!ctx || !slab6) return B200ICP_ERR_INVALID_ARG;

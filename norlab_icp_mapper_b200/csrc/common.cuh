@@ -160,6 +160,11 @@ struct MapStore {
     bool has_normals = false;
     bool has_prob = false;
     bool all_loaded = true;
+    // incremental SurfaceNormal: store points [0, nrm_epoch_n) carry normals (+ k-th neighbour distances) computed with
+    // knn = nrm_epoch_k and nothing but appends happened since
+    bool nrm_epoch_ok = false;
+    int64_t nrm_epoch_n = 0;
+    int nrm_epoch_k = 0;
     // double buffers for compaction
     float4* feat2 = nullptr;
     float* nrm2 = nullptr;
@@ -198,8 +203,12 @@ cudaError_t launch_dyn_input(const float* d_in, int rows, int dim, const float* 
 cudaError_t launch_dyn_queries(const MapStore& m, int dim, const float* Tinv16, float sensor_max_range, float4* d_q4, cudaStream_t s);
 cudaError_t launch_dyn_update(MapStore& m, int dim, const float* Tinv16, const DynParams& prm, const float4* d_in_sensor,
                               const int32_t* d_ids, const float* d_d2, cudaStream_t s);
-cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d_nn_pos, float4* d_nrm_sorted,
-                           float* d_store_nrm, cudaStream_t s);
+cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d_nn_pos, const float* d_nn_d2, const uint32_t* d_list,
+                           const unsigned int* d_n_list, long long list_capacity, float4* d_nrm_sorted, float* d_store_nrm, float* d_kth,
+                           cudaStream_t s);
+cudaError_t launch_normals_dirty(const GridView& new_points, const MapStore& m, const float* d_kth, int64_t n_old, uint8_t* d_dirty, cudaStream_t s);
+cudaError_t launch_normals_positions(const GridView& g, const uint8_t* d_dirty, uint8_t* d_flag, cudaStream_t s);
+cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s);
 
 // ---- knn.cu --------------------------------------------------------------------------------
 // queries: float4 (x, y, z, *) in the grid's frame, optionally moved by state->T first.

@@ -119,12 +119,19 @@ __global__ void __launch_bounds__(256) scatter_active_kernel(const uint8_t* __re
 
 // LPM SurfaceNormalDataPointsFilter: over the finite neighbours (the point itself included): mean,
 // centred covariance, eigenvector of the smallest eigenvalue (unit, sign arbitrary).
+// list (optional): the cell-sorted positions to (re)compute, n_list of them; row i of nn_pos / nn_d2 then belongs to
+// position list[i].  kth (optional, per STORE index): squared distance to the k-th neighbour (+inf when fewer than k
+// exist) -- what the incremental update compares new points against.
 __global__ void __launch_bounds__(128) normals_kernel(GridView g, int dim, int knn, const int32_t* __restrict__ nn_pos,
-                                                      float4* __restrict__ nrm_sorted, float* __restrict__ store_nrm) {
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j >= g.n) return;
+                                                      const float* __restrict__ nn_d2, const uint32_t* __restrict__ list,
+                                                      const unsigned int* __restrict__ n_list, float4* __restrict__ nrm_sorted,
+                                                      float* __restrict__ store_nrm, float* __restrict__ kth) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (list ? (long long)*n_list : (long long)g.n)) return;
+    const long long j = list ? (long long)list[i] : i;
     float mx = 0.f, my = 0.f, mz = 0.f;
     int cnt = 0;
+    nn_pos += (i - j) * knn;  // rows are indexed by i, the code below by j
     for (int c = 0; c < knn; ++c) {
         const int p = nn_pos[j * knn + c];
         if (p < 0) continue;
@@ -178,6 +185,68 @@ __global__ void __launch_bounds__(128) normals_kernel(GridView g, int dim, int k
     store_nrm[orig * dim + 0] = (float)nx;
     store_nrm[orig * dim + 1] = (float)ny;
     if (dim == 3) store_nrm[orig * dim + 2] = (float)nz;
+    if (kth) kth[orig] = nn_d2[i * knn + (knn - 1)];  // ascending; +inf when the k-th neighbour does not exist
+}
+
+// Incremental SurfaceNormal, step 1: which OLD points (store index < n_old, loaded) have a NEW point within their k-th
+// neighbour distance?  Their k-NN set -- hence their normal -- changes; everybody else's does not.  `nw` is a grid over
+// the new points only (map frame, not centred); one thread per old point scans the cells its ball touches, first hit wins.
+__global__ void __launch_bounds__(256) normals_dirty_kernel(GridView nw, const float4* __restrict__ feat, const uint8_t* __restrict__ loaded,
+                                                            const float* __restrict__ kth, long long n_old, long long n_all,
+                                                            uint8_t* __restrict__ dirty) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_all) return;
+    if (i >= n_old) {  // a new point: always computed
+        dirty[i] = loaded[i] ? 1 : 0;
+        return;
+    }
+    uint8_t d = 0;
+    if (loaded[i]) {
+        const float4 q = feat[i];
+        const float r2 = kth[i];
+        if (!(r2 < 3.0e38f)) {
+            d = 1;  // fewer than k neighbours so far (or unknown): any new point changes the set
+        } else {
+            const float r = sqrtf(r2);
+            const float ux = (q.x - nw.ox) * nw.inv_h, uy = (q.y - nw.oy) * nw.inv_h, uz = (q.z - nw.oz) * nw.inv_h;
+            const float slack = nw.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+            const float rt = r * nw.inv_h + slack;
+            // reject early when the ball misses the new points' bounding box altogether
+            if (ux + rt >= 0.f && uy + rt >= 0.f && uz + rt >= 0.f && ux - rt <= (float)nw.nx && uy - rt <= (float)nw.ny && uz - rt <= (float)nw.nz) {
+                const int xa = max(0, (int)floorf(ux - rt)), xb = min(nw.nx - 1, (int)floorf(ux + rt));
+                const int ylo = max(0, (int)floorf(uy - rt)), yhi = min(nw.ny - 1, (int)floorf(uy + rt));
+                const int zlo = max(0, (int)floorf(uz - rt)), zhi = min(nw.nz - 1, (int)floorf(uz + rt));
+                for (int z = zlo; z <= zhi && !d; ++z)
+                    for (int y = ylo; y <= yhi && !d; ++y) {
+                        if (xa > xb) continue;
+                        const uint32_t* row = nw.cell_start + ((size_t)z * nw.ny + y) * (size_t)nw.nx;
+                        const uint32_t s = __ldg(row + xa), e = __ldg(row + xb + 1);
+                        for (uint32_t j = s; j < e; ++j) {
+                            const float4 p = __ldg(nw.pts + j);
+                            const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+                            if (dx * dx + dy * dy + dz * dz <= r2 * 1.000001f + 1e-12f) {  // ties and rounding count as changes
+                                d = 1;
+                                break;
+                            }
+                        }
+                    }
+            }
+        }
+    }
+    dirty[i] = d;
+}
+
+// step 2: dirty flags per store index -> flags per cell-sorted position of the live index
+__global__ void __launch_bounds__(256) normals_flag_positions_kernel(GridView g, const uint8_t* __restrict__ dirty, uint8_t* __restrict__ flag) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= g.n) return;
+    flag[j] = dirty[__float_as_int(__ldg(g.pts + j).w)];
+}
+
+__global__ void __launch_bounds__(256) normals_gather_queries_kernel(GridView g, const uint32_t* __restrict__ list, const unsigned int* __restrict__ n_list,
+                                                                     float4* __restrict__ q) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < (long long)*n_list) q[i] = __ldg(g.pts + list[i]);
 }
 
 template <typename T>
@@ -282,6 +351,7 @@ cudaError_t store_set(MapStore& m, const float* d_in, int rows, int dim, const f
     if ((e = store_reserve(m, dim, n, s)) != cudaSuccess) return e;
     to_store_kernel<<<blocks_for(n), 256, 0, s>>>(d_in, rows, dim, (long long)n, m.feat, m.loaded);
     m.has_normals = d_normals != nullptr;
+    m.nrm_epoch_ok = false;
     if (d_normals)
         if ((e = cudaMemcpyAsync(m.nrm, d_normals, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     m.has_prob = false;
@@ -321,6 +391,7 @@ cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* c
     if ((e = cudaMemcpyAsync(&c, m.d_counter, sizeof(c), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     *changed = (int64_t)c;
+    if (c) m.nrm_epoch_ok = false;  // neighbourhoods at the window's edge changed
     return cudaGetLastError();
 }
 
@@ -509,6 +580,7 @@ cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64
     std::swap(m.prob, m.prob2);
     std::swap(m.loaded, m.loaded2);
     *n_removed = n - (int64_t)kept;
+    m.nrm_epoch_ok = false;  // points moved / vanished: the incremental normals bookkeeping starts over
     m.n = kept;
     m.n_active -= *n_removed;  // only loaded points are ever flagged
     return cudaGetLastError();
@@ -801,10 +873,30 @@ cudaError_t launch_dyn_update(MapStore& m, int dim, const float* Tinv16, const D
     return cudaGetLastError();
 }
 
-cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d_nn_pos, float4* d_nrm_sorted, float* d_store_nrm,
+cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d_nn_pos, const float* d_nn_d2, const uint32_t* d_list,
+                           const unsigned int* d_n_list, long long list_capacity, float4* d_nrm_sorted, float* d_store_nrm, float* d_kth,
                            cudaStream_t s) {
+    const long long n = d_list ? list_capacity : (long long)g.n;
+    if (n <= 0) return cudaSuccess;
+    normals_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(g, dim, knn, d_nn_pos, d_nn_d2, d_list, d_n_list, d_nrm_sorted, d_store_nrm, d_kth);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normals_dirty(const GridView& new_points, const MapStore& m, const float* d_kth, int64_t n_old, uint8_t* d_dirty, cudaStream_t s) {
+    if (m.n <= 0) return cudaSuccess;
+    normals_dirty_kernel<<<blocks_for(m.n), 256, 0, s>>>(new_points, m.feat, m.loaded, d_kth, (long long)n_old, (long long)m.n, d_dirty);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normals_positions(const GridView& g, const uint8_t* d_dirty, uint8_t* d_flag, cudaStream_t s) {
     if (g.n <= 0) return cudaSuccess;
-    normals_kernel<<<(unsigned)((g.n + 127) / 128), 128, 0, s>>>(g, dim, knn, d_nn_pos, d_nrm_sorted, d_store_nrm);
+    normals_flag_positions_kernel<<<blocks_for(g.n), 256, 0, s>>>(g, d_dirty, d_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s) {
+    if (capacity <= 0) return cudaSuccess;
+    normals_gather_queries_kernel<<<blocks_for(capacity), 256, 0, s>>>(g, d_list, d_n_list, d_q);
     return cudaGetLastError();
 }
 

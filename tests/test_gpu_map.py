@@ -113,3 +113,46 @@ def test_cell_window_load_unload(gpu, pair):
     ids, d2 = gpu.match(m[back][:2000])
     assert np.all(d2[:, 0] == 0)
     assert gpu.map_counts()[0] == len(m) - inside.sum() + back.sum()
+
+
+def test_incremental_surface_normals_match_a_full_recompute(monkeypatch):
+    """After an append-only map update the SurfaceNormal pass recomputes only the new points and the old points that got
+    a new point within their k-th neighbour distance; everybody else keeps neighbours and normal.  Same normals as a
+    full recompute (up to the arbitrary sign and fp32 noise from the moved mean-centring), far fewer points touched."""
+    import ctypes
+    from norlab_icp_mapper_b200 import synth
+    from norlab_icp_mapper_b200.icp import ICP, make_config
+    d = synth.make_pair_3d(n_map=300_000, n_scan=40_000, seed=5)
+    inp = synth.homog(synth.apply_T(d["correction_true"], d["reading"]))
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=5)
+    out = {}
+    for mode in ("incremental", "full"):
+        if mode == "full":
+            monkeypatch.setenv("B200ICP_FULL_NORMALS", "1")
+        else:
+            monkeypatch.delenv("B200ICP_FULL_NORMALS", raising=False)
+        g = ICP(cfg)
+        g._L.b200icp_debug_normals_recomputed.restype = ctypes.c_int64
+        g._L.b200icp_debug_normals_recomputed.argtypes = [ctypes.c_void_p]
+        g.set_map(d["map"], None)
+        g.map_surface_normals(10)
+        first = g._L.b200icp_debug_normals_recomputed(g._h)
+        added, _ = g.map_insert_point_distance(inp, 0.05)
+        assert not g._L.b200icp_map_has_normals(g._h)  # concatenate with a scan that has none: formally gone until the post filter runs
+        g.map_surface_normals(10)
+        second = g._L.b200icp_debug_normals_recomputed(g._h)
+        feat, nrm = g.map_download()
+        T = g(d["reading"])  # point-to-plane on the refreshed normals
+        g.map_surface_normals(10)  # nothing changed since: nothing to do
+        third = g._L.b200icp_debug_normals_recomputed(g._h)
+        out[mode] = (feat, nrm, first, second, third, added, T)
+        g.close()
+    fi, ni, first_i, second_i, third_i, added_i, Ti = out["incremental"]
+    ff, nf, first_f, second_f, third_f, added_f, Tf = out["full"]
+    assert added_i == added_f > 1000 and np.array_equal(fi, ff)
+    assert first_i == first_f == len(d["map"]) and second_f == len(ff) and third_f == len(ff)
+    assert added_i < second_i < 0.6 * len(fi) and third_i == 0  # new points + their neighbourhoods only
+    dots = np.abs((ni * nf).sum(axis=1))
+    assert np.isfinite(ni).all() and (dots > 0.9999).mean() > 0.999, (dots > 0.9999).mean()
+    er, et = synth.pose_error(Ti, Tf)
+    assert er <= 1e-5 and et <= 1e-4, (er, et)
