@@ -296,6 +296,17 @@ int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t
 int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_rows, int64_t* n,
                              const b200icp_filter* chain, int32_t n_filters);
 
+/* ---- the device-resident scan slot (no reference counterpart: it removes the host round trips between the steps of
+ * Mapper::processInput, Mapper.cpp:194-238).  The scan is uploaded once; RigidTransformation (Mapper.cpp:197,221),
+ * icp(input) (:213) and PointDistanceMapperModule::inPlaceUpdateMap (via Map.cpp:502-534) then run on that copy,
+ * stream-ordered.  The slot holds features only (the reference's raw scans carry no normals). */
+int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n);
+int64_t b200icp_scan_size(const b200icp_ctx* ctx);
+int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T);
+int32_t b200icp_scan_register(b200icp_ctx* ctx, const float* T_init, float* T_out, b200icp_result* result);
+int32_t b200icp_scan_insert_point_distance(b200icp_ctx* ctx, float min_dist_new_point, int64_t* n_added);
+int32_t b200icp_scan_download(b200icp_ctx* ctx, float* features, int64_t capacity, int64_t* n_out);
+
 /* Device-pointer variant of b200icp_transform (features/normals live on ctx's device). */
 int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows,
                                  float* d_normals, int64_t n, const float* T);

@@ -40,6 +40,8 @@ struct b200icp_ctx {
     int* d_scalar_nq = nullptr;
     unsigned* d_bar_counter = nullptr;
     int n_sms = 148;
+    float* d_scan = nullptr;     // the device-resident scan slot (b200icp_scan_*)
+    int64_t cap_scan = 0, n_scan = 0;
     float* d_kth = nullptr;      // incremental SurfaceNormal: squared k-th neighbour distance per store point
     int64_t cap_kth = 0;
     uint8_t* d_dirty = nullptr;  // ... dirty flags (store order, then index order)
@@ -417,6 +419,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaFree(b.state);
     cudaFree(b.trace);
     var_trimmed_free(ctx->var_scratch);
+    cudaFree(ctx->d_scan);
     cudaFree(ctx->d_kth);
     cudaFree(ctx->d_dirty);
     cudaFree(ctx->d_list);
@@ -877,27 +880,13 @@ int32_t b200icp_map_counts(const b200icp_ctx* ctx, int64_t* n_local, int64_t* n_
 
 int32_t b200icp_map_has_normals(const b200icp_ctx* ctx) { return (ctx && ctx->store.has_normals) ? 1 : 0; }
 
-int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
-                                          const float* input_normals, float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
-    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+// PointDistance insert of a cloud that is already on the device (map frame)
+static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, const float* d_in_nrm, int32_t feature_rows, int64_t n_in,
+                                         float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
     const int dim = ctx->cfg.dim;
-    if (feature_rows != dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
-    if (n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
-    if (n_added) *n_added = 0;
-    if (n_in == 0) return B200ICP_OK;
-    CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     MapStore& st = ctx->store;
-    if (st.n_active > 0 && ctx->index_stale) {
-        const int32_t rc = commit_index(ctx);
-        if (rc != B200ICP_OK) return rc;
-    }
-    const size_t fb = (size_t)n_in * feature_rows * sizeof(float), nb = (size_t)n_in * dim * sizeof(float);
-    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + 256));
-    float* d_in = ctx->d_stage_a;
-    float* d_in_nrm = input_normals ? ctx->d_stage_a + ((fb + 255) / 256) * 64 : nullptr;
-    CK(cudaMemcpyAsync(d_in, input, fb, cudaMemcpyHostToDevice, s));
-    if (input_normals) CK(cudaMemcpyAsync(d_in_nrm, input_normals, nb, cudaMemcpyHostToDevice, s));
+    const float* input_normals = d_in_nrm;  // (only its presence matters below)
     const int32_t eb = ensure_query_buffers(ctx, n_in, 1);
     if (eb != B200ICP_OK) return eb;
     if (st.n_active > 0) {
@@ -932,6 +921,91 @@ int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, 
     CK(cudaStreamSynchronize(s));
     if (kept > 0) ctx->index_stale = true;
     if (n_added) *n_added = kept;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                                          const float* input_normals, float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
+    if (n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+    if (n_added) *n_added = 0;
+    if (n_in == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (ctx->store.n_active > 0 && ctx->index_stale) {
+        const int32_t rc = commit_index(ctx);
+        if (rc != B200ICP_OK) return rc;
+    }
+    const size_t fb = (size_t)n_in * feature_rows * sizeof(float), nb = (size_t)n_in * dim * sizeof(float);
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + 256));
+    float* d_in = ctx->d_stage_a;
+    float* d_in_nrm = input_normals ? ctx->d_stage_a + ((fb + 255) / 256) * 64 : nullptr;
+    CK(cudaMemcpyAsync(d_in, input, fb, cudaMemcpyHostToDevice, s));
+    if (input_normals) CK(cudaMemcpyAsync(d_in_nrm, input_normals, nb, cudaMemcpyHostToDevice, s));
+    return insert_point_distance_dev(ctx, d_in, d_in_nrm, feature_rows, n_in, min_dist_new_point, n_added, keep_out);
+}
+
+/* ---- the device-resident scan slot: Mapper::processInput uploads the scan ONCE; the rigid transforms
+ * (Mapper.cpp:197,221), icp(input) (:213) and the PointDistance insert (Map.cpp:502-534) then run on that copy ---- */
+int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (feature_rows != ctx->cfg.dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad scan");
+    CK(cudaSetDevice(ctx->device));
+    if (n > ctx->cap_scan) {
+        cudaFree(ctx->d_scan);
+        ctx->d_scan = nullptr;
+        ctx->cap_scan = 0;
+        CK(cudaMalloc((void**)&ctx->d_scan, (size_t)grow_capacity(n) * feature_rows * sizeof(float)));
+        ctx->cap_scan = grow_capacity(n);
+    }
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d_scan, features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_scan = n;
+    return B200ICP_OK;
+}
+
+int64_t b200icp_scan_size(const b200icp_ctx* ctx) { return ctx ? ctx->n_scan : 0; }
+
+int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T) {
+    if (!ctx || !T) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    float M[16];
+    embed(T, dim, M);
+    if (std::fabs(1.f - det3(M)) > 1e-3f)
+        return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
+    if (ctx->n_scan == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_transform(ctx->d_scan, dim + 1, dim, nullptr, ctx->n_scan, M, ctx->stream));  // stream-ordered: no sync needed here
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_register(b200icp_ctx* ctx, const float* T_init, float* T_out, b200icp_result* result) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    return b200icp_register_device(ctx, ctx->d_scan, ctx->cfg.dim + 1, ctx->n_scan, T_init, T_out, result);
+}
+
+int32_t b200icp_scan_insert_point_distance(b200icp_ctx* ctx, float min_dist_new_point, int64_t* n_added) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (n_added) *n_added = 0;
+    if (ctx->n_scan == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->store.n_active > 0 && ctx->index_stale) {
+        const int32_t rc = commit_index(ctx);
+        if (rc != B200ICP_OK) return rc;
+    }
+    return insert_point_distance_dev(ctx, ctx->d_scan, nullptr, ctx->cfg.dim + 1, ctx->n_scan, min_dist_new_point, n_added, nullptr);
+}
+
+int32_t b200icp_scan_download(b200icp_ctx* ctx, float* features, int64_t capacity, int64_t* n_out) {
+    if (!ctx || !n_out) return B200ICP_ERR_INVALID_ARG;
+    *n_out = ctx->n_scan;
+    if (!features) return B200ICP_OK;
+    if (capacity < ctx->n_scan) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_scan > 0)
+        CK(cudaMemcpyAsync(features, ctx->d_scan, (size_t)ctx->n_scan * (ctx->cfg.dim + 1) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return B200ICP_OK;
 }
 

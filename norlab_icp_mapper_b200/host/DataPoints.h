@@ -15,7 +15,12 @@ struct DataPoints {
     std::vector<float> features;  // (dim + 1) x N, column-major
     std::vector<float> normals;   // dim x N, column-major, or empty (descriptor absent)
     std::vector<float> probabilityDynamic;  // 1 x N or empty (descriptor absent)
-    int64_t getNbPoints() const { return features.empty() ? 0 : (int64_t)features.size() / (dim + 1); }
+    // Device-resident scan: `features` is empty and the (dim + 1) x deviceCount matrix lives in the ICP context's scan
+    // slot (b200icp_scan_*).  Set by Mapper::processInput for its temporaries so that the transforms, icp(input) and the
+    // map insert work on ONE upload; anything that needs the numbers on the host calls ICPSequence::materialize().
+    bool onDevice = false;
+    int64_t deviceCount = 0;
+    int64_t getNbPoints() const { return onDevice ? deviceCount : (features.empty() ? 0 : (int64_t)features.size() / (dim + 1)); }
     bool descriptorExists(const std::string& name) const {
         return (name == "normals" && !normals.empty()) || (name == "probabilityDynamic" && !probabilityDynamic.empty());
     }

@@ -40,9 +40,31 @@ class ICPSequence {
         check(ctx, b200icp_set_map(ctx, map.features.data(), dim + 1, map.normals.empty() ? nullptr : map.normals.data(), map.getNbPoints()));
         return map.getNbPoints() > 0;
     }
+    // host copy of a device-resident scan (modules without a device entry point use it)
+    DataPoints materialize(const DataPoints& cloud) {
+        if (!cloud.onDevice) return cloud;
+        DataPoints out = cloud;
+        out.onDevice = false;
+        out.deviceCount = 0;
+        int64_t n = 0;
+        out.features.resize((size_t)cloud.deviceCount * (dim + 1));
+        check(ctx, b200icp_scan_download(ctx, out.features.data(), cloud.deviceCount, &n));
+        return out;
+    }
+    // upload once; the returned cloud refers to the context's scan slot
+    DataPoints toDevice(const DataPoints& cloud) {
+        check(ctx, b200icp_scan_upload(ctx, cloud.features.data(), dim + 1, cloud.getNbPoints()));
+        DataPoints out;
+        out.dim = cloud.dim;
+        out.probabilityDynamic = cloud.probabilityDynamic;
+        out.onDevice = true;
+        out.deviceCount = cloud.getNbPoints();
+        return out;
+    }
     TransformationParameters operator()(const DataPoints& cloud) {
         TransformationParameters T = TransformationParameters::Identity(dim + 1);
-        const int32_t rc = b200icp_register(ctx, cloud.features.data(), dim + 1, cloud.getNbPoints(), nullptr, T.m, &last);
+        const int32_t rc = cloud.onDevice ? b200icp_scan_register(ctx, nullptr, T.m, &last)
+                                          : b200icp_register(ctx, cloud.features.data(), dim + 1, cloud.getNbPoints(), nullptr, T.m, &last);
         if (rc == B200ICP_ERR_NO_MAP) return T;  // LPM: no map -> identity
         check(ctx, rc);
         return T;
@@ -53,6 +75,10 @@ class ICPSequence {
 
 // PM::Transformation("RigidTransformation")::compute (Mapper.cpp:197,221)
 inline DataPoints rigidTransform(ICPSequence& icp, const DataPoints& in, const TransformationParameters& T) {
+    if (in.onDevice) {  // the slot is transformed in place: `in` and the result are the same device cloud
+        ICPSequence::check(icp.context(), b200icp_scan_transform(icp.context(), T.m));
+        return in;
+    }
     DataPoints out = in;
     ICPSequence::check(icp.context(), b200icp_transform(icp.context(), out.features.data(), in.dim + 1,
                                                         out.normals.empty() ? nullptr : out.normals.data(), out.getNbPoints(), T.m));

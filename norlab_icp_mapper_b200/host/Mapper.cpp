@@ -86,7 +86,12 @@ struct StepTimer {  // B200MAPPER_TIMING=1 prints the wall time of each step of 
 
 void Mapper::processInput(const DataPoints& filteredInputInSensorFrame, const TransformationParameters& estimatedPose, double timeStamp) {
     StepTimer timer;
-    DataPoints input = rigidTransform(icp, filteredInputInSensorFrame, estimatedPose);
+    // One upload: the scan goes to the context's device slot and the steps below (two rigid transforms, icp(input), the
+    // map insert) work on that copy.  Scans that carry normals, or B200MAPPER_HOST_SCAN=1, take the host path.
+    static const bool hostScan = std::getenv("B200MAPPER_HOST_SCAN") != nullptr;
+    const bool deviceScan = !hostScan && filteredInputInSensorFrame.normals.empty() && filteredInputInSensorFrame.getNbPoints() > 0;
+    DataPoints input = deviceScan ? rigidTransform(icp, icp.toDevice(filteredInputInSensorFrame), estimatedPose)
+                                  : rigidTransform(icp, filteredInputInSensorFrame, estimatedPose);
     timer.lap("transform(input, T_est)");
     lastInputUpdatedMap = false;
 

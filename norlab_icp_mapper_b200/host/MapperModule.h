@@ -23,6 +23,8 @@ class DeviceMap {
    public:
     explicit DeviceMap(ICPSequence& icp_) : icp(icp_) {}
     b200icp_ctx* context() { return icp.context(); }
+    //! host copy of an input that lives in the device scan slot (no-op for host inputs)
+    DataPoints host(const DataPoints& in) { return icp.materialize(in); }
     int64_t getNbPoints() {
         int64_t nl = 0, ng = 0;
         b200icp_map_counts(icp.context(), &nl, &ng);
@@ -104,6 +106,10 @@ class PointDistanceMapperModule : public MapperModule {
    private:
     void insert(const DataPoints& input, DeviceMap& map) {
         int64_t added = 0;
+        if (input.onDevice) {  // the scan is already on the device (Mapper::processInput uploaded it once)
+            ICPSequence::check(map.context(), b200icp_scan_insert_point_distance(map.context(), minDistNewPoint, &added));
+            return;
+        }
         ICPSequence::check(map.context(), b200icp_map_insert_point_distance(map.context(), input.features.data(), input.dim + 1,
                                                                             input.getNbPoints(), input.normals.empty() ? nullptr : input.normals.data(),
                                                                             minDistNewPoint, &added, nullptr));
@@ -134,7 +140,9 @@ class OctreeMapperModule : public MapperModule {
     void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
         inPlaceUpdateMap(input, map, pose);  // inPlaceUpdateMap(emptyMap, input): concatenate into an empty map, then filter
     }
-    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters&) override {
+    void inPlaceUpdateMap(const DataPoints& input_, DeviceMap& map, const TransformationParameters&) override {
+        const DataPoints hostCopy = input_.onDevice ? map.host(input_) : DataPoints();  // (no device entry point for this module yet)
+        const DataPoints& input = input_.onDevice ? hostCopy : input_;
         int64_t n_after = 0;
         ICPSequence::check(map.context(),
                            b200icp_map_octree(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
@@ -163,7 +171,9 @@ class DynamicPointsMapperModule : public MapperModule {
             else throw InvalidParameter("DynamicPointsMapperModule: unknown parameter " + kv.first);
         }
     }
-    void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters&) override {
+    void inPlaceCreateMap(const DataPoints& input_, DeviceMap& map, const TransformationParameters&) override {
+        const DataPoints hostCopy = input_.onDevice ? map.host(input_) : DataPoints();
+        const DataPoints& input = input_.onDevice ? hostCopy : input_;
         // createMap copies the input (DynamicPointsMapperModule.cpp:16-25): an unfiltered insert
         int64_t added = 0;
         if (map.getNbPoints() != 0) throw std::runtime_error("DynamicPointsMapperModule::createMap on a non-empty map");
@@ -171,7 +181,9 @@ class DynamicPointsMapperModule : public MapperModule {
                                                              input.normals.empty() ? nullptr : input.normals.data(),
                                                              input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(), &added));
     }
-    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
+    void inPlaceUpdateMap(const DataPoints& input_, DeviceMap& map, const TransformationParameters& pose) override {
+        const DataPoints hostCopy = input_.onDevice ? map.host(input_) : DataPoints();
+        const DataPoints& input = input_.onDevice ? hostCopy : input_;
         ICPSequence::check(map.context(), b200icp_map_dynamic_points(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
                                                                      input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(),
                                                                      pose.m, &prm));
