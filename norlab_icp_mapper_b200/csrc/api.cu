@@ -1046,30 +1046,58 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
     // ---- incremental pass: only appends since the last pass -> recompute the new points and the old points that have a new
     //      point within their k-th neighbour distance; every other point keeps the neighbours, hence the normal, it had ----
     const int64_t n_new = st.n - st.nrm_epoch_n;
-    const bool incremental = st.nrm_epoch_ok && st.nrm_epoch_k == knn && n_new >= 0 && st.nrm_epoch_n > 0 && n_new * 4 <= st.n &&
-                             !getenv("B200ICP_FULL_NORMALS");
+    bool incremental = st.nrm_epoch_ok && st.nrm_epoch_k == knn && n_new >= 0 && st.nrm_epoch_n > 0 && n_new * 4 <= st.n &&
+                       !getenv("B200ICP_FULL_NORMALS");
     ctx->last_normals_recomputed = n;
-    if (incremental && n_new == 0) {
+    if (incremental && (n_new > 0 || st.nrm_touched) && st.n + n > ctx->cap_dirty) {
+        cudaFree(ctx->d_dirty);
+        cudaFree(ctx->d_list);
+        ctx->d_dirty = nullptr;
+        ctx->d_list = nullptr;
+        ctx->cap_dirty = 0;
+        const int64_t cap = grow_capacity(st.n + n);
+        CK(cudaMalloc((void**)&ctx->d_dirty, (size_t)cap));
+        CK(cudaMalloc((void**)&ctx->d_list, (size_t)cap * sizeof(uint32_t)));
+        ctx->cap_dirty = cap;
+    }
+    unsigned int* d_count = reinterpret_cast<unsigned int*>(ctx->d_scalar_nq) + 4;
+    int64_t n_changed = n_new;
+    if (incremental && st.nrm_touched) {
+        // the window moved since the last pass: the changed set = appended points + points whose loaded flag flipped
+        CK(launch_normals_changed(st, st.nrm_epoch_n, ctx->d_dirty, s));
+        size_t need = 0;
+        thrust::counting_iterator<uint32_t> counting(0u);
+        cub::DeviceSelect::Flagged(nullptr, need, counting, ctx->d_dirty, ctx->d_list, d_count, (int)st.n);
+        if (need > ctx->map.cub_tmp_bytes) {
+            cudaFree(ctx->map.cub_tmp);
+            ctx->map.cub_tmp = nullptr;
+            ctx->map.cub_tmp_bytes = 0;
+            CK(cudaMalloc(&ctx->map.cub_tmp, need + 256));
+            ctx->map.cub_tmp_bytes = need + 256;
+        }
+        size_t bytes = ctx->map.cub_tmp_bytes;
+        CK(cub::DeviceSelect::Flagged(ctx->map.cub_tmp, bytes, counting, ctx->d_dirty, ctx->d_list, d_count, (int)st.n, s));
+        unsigned int c = 0;
+        CK(cudaMemcpyAsync(&c, d_count, sizeof(c), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        n_changed = c;
+        if (n_changed * 4 > st.n) incremental = false;  // too much changed: the full pass is cheaper
+    }
+    if (incremental && n_changed == 0) {
         ctx->last_normals_recomputed = 0;
     } else if (incremental) {
-        // grid over the new points alone (map frame, not centred)
-        CK(grid_build(ctx->aux, reinterpret_cast<const float*>(st.feat + st.nrm_epoch_n), 4, ctx->cfg.dim, nullptr, n_new, /*centre=*/false, 0.f, s));
-        if (st.n + n > ctx->cap_dirty) {
-            cudaFree(ctx->d_dirty);
-            cudaFree(ctx->d_list);
-            ctx->d_dirty = nullptr;
-            ctx->d_list = nullptr;
-            ctx->cap_dirty = 0;
-            const int64_t cap = grow_capacity(st.n + n);
-            CK(cudaMalloc((void**)&ctx->d_dirty, (size_t)cap));
-            CK(cudaMalloc((void**)&ctx->d_list, (size_t)cap * sizeof(uint32_t)));
-            ctx->cap_dirty = cap;
+        // grid over the changed points alone (map frame, not centred)
+        if (st.nrm_touched) {
+            // (d_list holds the subset for the duration of the build only; it is reused for the index positions below)
+            CK(grid_build(ctx->aux, reinterpret_cast<const float*>(st.feat), 4, ctx->cfg.dim, nullptr, n_changed, /*centre=*/false, 0.f, s,
+                          ctx->d_list));
+        } else {
+            CK(grid_build(ctx->aux, reinterpret_cast<const float*>(st.feat + st.nrm_epoch_n), 4, ctx->cfg.dim, nullptr, n_new, /*centre=*/false, 0.f, s));
         }
         uint8_t* d_dirty = ctx->d_dirty;         // per store index
         uint8_t* d_flag = ctx->d_dirty + st.n;   // per cell-sorted position of the live index
         CK(launch_normals_dirty(ctx->aux.view, st, ctx->d_kth, st.nrm_epoch_n, d_dirty, s));
         CK(launch_normals_positions(ctx->map.view, d_dirty, d_flag, s));
-        unsigned int* d_count = reinterpret_cast<unsigned int*>(ctx->d_scalar_nq) + 4;
         size_t need = 0;
         thrust::counting_iterator<uint32_t> counting(0u);
         cub::DeviceSelect::Flagged(nullptr, need, counting, d_flag, ctx->d_list, d_count, (int)n);
@@ -1107,6 +1135,7 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
                       /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
         CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->map.normals, st.nrm, ctx->d_kth, s));
     }
+    CK(store_clear_touched(st, s));
     CK(cudaStreamSynchronize(s));
     ctx->map.has_normals = true;
     st.has_normals = true;

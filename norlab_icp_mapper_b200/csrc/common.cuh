@@ -153,6 +153,7 @@ struct MapStore {
     float* nrm = nullptr;        // dim floats per point
     float* prob = nullptr;       // `probabilityDynamic` descriptor (DynamicPointsMapperModule), 1 float per point
     uint8_t* loaded = nullptr;
+    uint8_t* touched = nullptr;  // loaded flag flipped since the last SurfaceNormal pass (incremental normals)
     uint32_t* active = nullptr;  // indices of the loaded points (valid after store_compact_active)
     uint32_t *tmp_u32a = nullptr, *tmp_u32b = nullptr;
     unsigned long long* d_counter = nullptr;
@@ -163,6 +164,7 @@ struct MapStore {
     // incremental SurfaceNormal: store points [0, nrm_epoch_n) carry normals (+ k-th neighbour distances) computed with
     // knn = nrm_epoch_k and nothing but appends happened since
     bool nrm_epoch_ok = false;
+    bool nrm_touched = false;  // some `touched` flags are set
     int64_t nrm_epoch_n = 0;
     int nrm_epoch_k = 0;
     // double buffers for compaction
@@ -207,6 +209,8 @@ cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d
                            const unsigned int* d_n_list, long long list_capacity, float4* d_nrm_sorted, float* d_store_nrm, float* d_kth,
                            cudaStream_t s);
 cudaError_t launch_normals_dirty(const GridView& new_points, const MapStore& m, const float* d_kth, int64_t n_old, uint8_t* d_dirty, cudaStream_t s);
+cudaError_t launch_normals_changed(const MapStore& m, int64_t n_old, uint8_t* d_flag, cudaStream_t s);
+cudaError_t store_clear_touched(MapStore& m, cudaStream_t s);
 cudaError_t launch_normals_positions(const GridView& g, const uint8_t* d_dirty, uint8_t* d_flag, cudaStream_t s);
 cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s);
 

@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) pd_append_kernel(const float* __restrict_
 // load: parked points whose 20 m grid coordinate lies in the slab come back (Map.cpp:79-99, cell ids
 // are floor(x / CELL_SIZE), Map.cpp:232-235).
 __global__ void __launch_bounds__(256) window_kernel(const float4* __restrict__ store, long long n, uint8_t* __restrict__ loaded,
-                                                     int load, float cell, int r0, int r1, int c0, int c1, int a0, int a1,
-                                                     unsigned long long* __restrict__ changed) {
+                                                     uint8_t* __restrict__ touched, int load, float cell, int r0, int r1, int c0, int c1,
+                                                     int a0, int a1, unsigned long long* __restrict__ changed) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = store[i];
@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) window_kernel(const float4* __restrict__ 
         const int gx = (int)floorf(p.x / cell), gy = (int)floorf(p.y / cell), gz = (int)floorf(p.z / cell);
         if (gx >= r0 && gx <= r1 && gy >= c0 && gy <= c1 && gz >= a0 && gz <= a1) {
             loaded[i] = 1;
+            touched[i] = 1;
             atomicAdd(changed, 1ull);
         }
     } else {
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(256) window_kernel(const float4* __restrict__ 
         const float sz = (float)a0 * cell, ez = ((float)a1 + 1.f) * cell;
         if (p.x >= sx && p.x < ex && p.y >= sy && p.y < ey && p.z >= sz && p.z < ez) {
             loaded[i] = 0;
+            touched[i] = 1;
             atomicAdd(changed, 1ull);
         }
     }
@@ -188,15 +190,16 @@ __global__ void __launch_bounds__(128) normals_kernel(GridView g, int dim, int k
     if (kth) kth[orig] = nn_d2[i * knn + (knn - 1)];  // ascending; +inf when the k-th neighbour does not exist
 }
 
-// Incremental SurfaceNormal, step 1: which OLD points (store index < n_old, loaded) have a NEW point within their k-th
-// neighbour distance?  Their k-NN set -- hence their normal -- changes; everybody else's does not.  `nw` is a grid over
-// the new points only (map frame, not centred); one thread per old point scans the cells its ball touches, first hit wins.
+// Incremental SurfaceNormal, step 1: which OLD points (store index < n_old, loaded) have a CHANGED point -- appended, or
+// moved into / out of the window -- within their k-th neighbour distance?  Their k-NN set, hence their normal, changes;
+// everybody else's does not.  `nw` is a grid over the changed points only (map frame, not centred); one thread per old
+// point scans the cells its ball touches, first hit wins.
 __global__ void __launch_bounds__(256) normals_dirty_kernel(GridView nw, const float4* __restrict__ feat, const uint8_t* __restrict__ loaded,
-                                                            const float* __restrict__ kth, long long n_old, long long n_all,
-                                                            uint8_t* __restrict__ dirty) {
+                                                            const uint8_t* __restrict__ touched, const float* __restrict__ kth, long long n_old,
+                                                            long long n_all, uint8_t* __restrict__ dirty) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_all) return;
-    if (i >= n_old) {  // a new point: always computed
+    if (i >= n_old || touched[i]) {  // a new point, or one that came back into the window: always computed (if loaded)
         dirty[i] = loaded[i] ? 1 : 0;
         return;
     }
@@ -274,6 +277,7 @@ void store_free(MapStore& m) {
     cudaFree(m.nrm);
     cudaFree(m.prob);
     cudaFree(m.loaded);
+    cudaFree(m.touched);
     cudaFree(m.feat2);
     cudaFree(m.nrm2);
     cudaFree(m.prob2);
@@ -295,6 +299,11 @@ cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s) {
         if ((e = regrow(m.nrm, m.n * dim, cap * dim, s)) != cudaSuccess) return e;
         if ((e = regrow(m.prob, m.n, cap, s)) != cudaSuccess) return e;
         if ((e = regrow(m.loaded, m.n, cap, s)) != cudaSuccess) return e;
+        {   // "loaded flag flipped since the last SurfaceNormal pass" (incremental normals); new tail zeroed
+            const int64_t old_cap = m.cap;
+            if ((e = regrow(m.touched, m.touched ? old_cap : 0, cap, s)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(m.touched + old_cap, 0, (size_t)(cap - old_cap), s)) != cudaSuccess) return e;
+        }
         cudaFree(m.feat2);
         cudaFree(m.nrm2);
         cudaFree(m.prob2);
@@ -385,13 +394,13 @@ cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* c
     if (m.n == 0) return cudaSuccess;
     cudaError_t e;
     if ((e = cudaMemsetAsync(m.d_counter, 0, sizeof(unsigned long long), s)) != cudaSuccess) return e;
-    window_kernel<<<blocks_for(m.n), 256, 0, s>>>(m.feat, (long long)m.n, m.loaded, load, 20.0f, slab6[0], slab6[1], slab6[2], slab6[3],
-                                                  slab6[4], slab6[5], m.d_counter);
+    window_kernel<<<blocks_for(m.n), 256, 0, s>>>(m.feat, (long long)m.n, m.loaded, m.touched, load, 20.0f, slab6[0], slab6[1], slab6[2],
+                                                  slab6[3], slab6[4], slab6[5], m.d_counter);
     unsigned long long c = 0;
     if ((e = cudaMemcpyAsync(&c, m.d_counter, sizeof(c), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     *changed = (int64_t)c;
-    if (c) m.nrm_epoch_ok = false;  // neighbourhoods at the window's edge changed
+    if (c) m.nrm_touched = true;  // neighbourhoods at the window's edge changed: those points are marked in `touched`
     return cudaGetLastError();
 }
 
@@ -884,8 +893,24 @@ cudaError_t launch_normals(const GridView& g, int dim, int knn, const int32_t* d
 
 cudaError_t launch_normals_dirty(const GridView& new_points, const MapStore& m, const float* d_kth, int64_t n_old, uint8_t* d_dirty, cudaStream_t s) {
     if (m.n <= 0) return cudaSuccess;
-    normals_dirty_kernel<<<blocks_for(m.n), 256, 0, s>>>(new_points, m.feat, m.loaded, d_kth, (long long)n_old, (long long)m.n, d_dirty);
+    normals_dirty_kernel<<<blocks_for(m.n), 256, 0, s>>>(new_points, m.feat, m.loaded, m.touched, d_kth, (long long)n_old, (long long)m.n, d_dirty);
     return cudaGetLastError();
+}
+
+// flag[i] = 1 for the points that changed since the last pass: appended (i >= n_old) or flipped by the window
+__global__ void __launch_bounds__(256) normals_changed_kernel(const uint8_t* __restrict__ touched, long long n_old, long long n_all, uint8_t* __restrict__ flag) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_all) flag[i] = (i >= n_old || touched[i]) ? 1 : 0;
+}
+cudaError_t launch_normals_changed(const MapStore& m, int64_t n_old, uint8_t* d_flag, cudaStream_t s) {
+    if (m.n <= 0) return cudaSuccess;
+    normals_changed_kernel<<<blocks_for(m.n), 256, 0, s>>>(m.touched, (long long)n_old, (long long)m.n, d_flag);
+    return cudaGetLastError();
+}
+cudaError_t store_clear_touched(MapStore& m, cudaStream_t s) {
+    m.nrm_touched = false;
+    if (!m.touched || m.n <= 0) return cudaSuccess;
+    return cudaMemsetAsync(m.touched, 0, (size_t)m.n, s);
 }
 
 cudaError_t launch_normals_positions(const GridView& g, const uint8_t* d_dirty, uint8_t* d_flag, cudaStream_t s) {

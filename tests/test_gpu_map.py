@@ -156,3 +156,45 @@ def test_incremental_surface_normals_match_a_full_recompute(monkeypatch):
     assert np.isfinite(ni).all() and (dots > 0.9999).mean() > 0.999, (dots > 0.9999).mean()
     er, et = synth.pose_error(Ti, Tf)
     assert er <= 1e-5 and et <= 1e-4, (er, et)
+
+
+def test_incremental_normals_across_a_window_move(monkeypatch):
+    """Unloading / loading 20 m cells (Map::updatePose) changes neighbourhoods at the window's edge: the points whose
+    loaded flag flipped are treated like appended / removed points, the pass stays incremental and agrees with a full
+    recompute."""
+    import ctypes
+    from norlab_icp_mapper_b200 import synth
+    from norlab_icp_mapper_b200.icp import ICP, make_config
+    d = synth.make_pair_3d(n_map=300_000, n_scan=10_000, seed=9)
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(), minimizer="point_to_plane", max_iteration_count=3)
+    out = {}
+    for mode in ("incremental", "full"):
+        if mode == "full":
+            monkeypatch.setenv("B200ICP_FULL_NORMALS", "1")
+        else:
+            monkeypatch.delenv("B200ICP_FULL_NORMALS", raising=False)
+        g = ICP(cfg)
+        g._L.b200icp_debug_normals_recomputed.restype = ctypes.c_int64
+        g._L.b200icp_debug_normals_recomputed.argtypes = [ctypes.c_void_p]
+        g.set_map(d["map"], None)
+        g.map_surface_normals(8)
+        slab = (-2, -2, -10, 10, -10, 10)  # rows -2..-2 (x in [-40, -20)): a 20 m wide strip of the 200 m world
+        changed = g.map_window(False, slab)
+        g.map_commit()
+        g.map_surface_normals(8)
+        n_after_unload = g._L.b200icp_debug_normals_recomputed(g._h)
+        local1, _ = g.map_counts()
+        changed2 = g.map_window(True, slab)
+        g.map_commit()
+        g.map_surface_normals(8)
+        n_after_load = g._L.b200icp_debug_normals_recomputed(g._h)
+        feat, nrm = g.map_download()
+        out[mode] = (changed, changed2, n_after_unload, n_after_load, local1, feat, nrm)
+        g.close()
+    ci, ci2, a_i, b_i, l1_i, fi, ni = out["incremental"]
+    cf, cf2, a_f, b_f, l1_f, ff, nf = out["full"]
+    assert ci == cf == ci2 == cf2 > 1000 and l1_i == l1_f == len(d["map"]) - ci and np.array_equal(fi, ff)
+    assert 0 < a_i < 0.2 * l1_i and a_f == l1_f            # only the strip's neighbours
+    assert ci <= b_i < ci + 0.2 * len(fi) and b_f == len(ff)  # the strip itself + its neighbours
+    dots = np.abs((ni * nf).sum(axis=1))
+    assert np.isfinite(ni).all() and (dots > 0.9999).mean() > 0.999, (dots > 0.9999).mean()
