@@ -71,7 +71,7 @@ for a in sys.argv:
         n_scans = int(a.split("=")[1])
 world = synth.World3D(seed=2000, size=(1000.0, 200.0), n_boxes=200)
 cfg3 = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30, differential=(1e-3, 1e-3, 3))
-m = Mapper(cfg3, True, False, True, False, updateCondition=("distance", 1.0), sensorMaxRange=80.0, minDistNewPoint=0.05, surfaceNormalKnn=10, reservePoints=12_000_000)
+m = Mapper(cfg3, True, False, True, False, updateCondition=("distance", 1.0), sensorMaxRange=80.0, minDistNewPoint=0.05, surfaceNormalKnn=10, reservePoints=int(os.environ.get("CFG3_RESERVE", "32000000")))
 rng = np.random.default_rng(5)
 times, sizes, upd = [], [], []
 T_prev_true = None
@@ -98,7 +98,8 @@ for i in range(n_scans):
 err = synth.pose_error(pose_est, T_true)
 out["cfg3_online"] = dict(scans=n_scans, scans_per_s=n_scans / sum(times), ms_per_scan_median=1e3 * float(np.median(times)),
                           ms_per_update_scan=1e3 * float(np.mean([t for t, u in zip(times, upd) if u])), updates=int(sum(upd)),
-                          ms_per_scan_p95=1e3 * float(np.percentile(times, 95)), ms_per_scan_last50=1e3 * float(np.mean(times[-50:])),
+                          ms_per_scan_p95=1e3 * float(np.percentile(times, 95)), ms_per_scan_mean=1e3 * float(np.mean(times)),
+                          ms_slowest_scans=[round(1e3 * t, 1) for t in sorted(times)[-5:]], ms_per_scan_last50=1e3 * float(np.mean(times[-50:])),
                           final_local=sizes[-1][0], final_global=sizes[-1][1], drift_rad=err[0], drift_m=err[1],
                           note="whole Mapper::processInput per scan through the host mirror (upload, input filters, ICP with Counter{30} + "
                                "Differential, PointDistance insert, SurfaceNormal knn 10 over the local map, index rebuild); every scan updates the map")
