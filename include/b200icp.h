@@ -94,8 +94,14 @@ typedef struct b200icp_config {
     float max_translation_norm;
     /* implementation knobs (no reference counterpart) */
     int32_t sort_reading; /* 1: Morton-sort the reading once per registration (default)          */
-    int32_t use_graph;    /* 1: replay the iteration as a CUDA graph when the chain allows it    */
-    int32_t nn_variant;   /* 0: default kernel; other values select experimental variants        */
+    int32_t use_graph;    /* reserved, ignored: the persistent loop kernel made graph replay pointless */
+    int32_t nn_variant;   /* 0: default.  Test / development switches, results never change beyond summation order:
+                             bit 1 (2)   kernel-per-step path: cold search every iteration (no warm bound)
+                             bit 2 (4)   kernel-per-step path instead of the persistent loop kernel
+                             bit 3 (8)   loop kernel: general three-barrier quantile with global radix passes
+                             bit 4 (16)  loop kernel: no predicted quantile window (two barriers per iteration)
+                             bit 5 (32)  loop kernel: no match-cache verification (every query searched every iteration)
+                             bit 6 (64)  loop kernel: no histogram-derived window (with bit 4: three barriers)      */
     int32_t reserved[5];
 } b200icp_config;
 

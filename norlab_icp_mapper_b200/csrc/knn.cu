@@ -155,16 +155,7 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
                        const IcpState* st, int k, float max_r2, int32_t* out_ids, float* out_d2, int want_original_ids,
                        int variant, cudaStream_t s) {
     if (k < 1 || k > 32) return cudaErrorInvalidValue;
-    if (k == 1) {
-        switch ((variant >> 4) & 0xf) {  // experimental: lanes per query for k = 1
-            case 5: return launch_one<1, Acc1<1>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-            case 6: return launch_one<2, Acc1<2>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-            case 4: return launch_one<4, Acc1<4>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-            case 1: return launch_one<16, Acc1<16>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-            case 2: return launch_one<32, Acc1<32>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-            default: return launch_one<8, Acc1<8>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
-        }
-    }
+    if (k == 1) return launch_one<8, Acc1<8>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
     const int warm = (variant & 0x10000) ? 1 : 0;  // set by the ICP loop from iteration 1 on (out_ids = previous matches, positions)
     // lanes per query: at least k (lane j holds the j-th best); few queries get more lanes each -- a query's latency is what
     // is left to cut when the whole batch does not even fill the SMs (10 k queries x 8 lanes = a quarter of the B200)
@@ -177,12 +168,7 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
 
 cudaError_t launch_nn1_warm(const GridView& g, const float4* d_reading, int nq_capacity, const IcpState* st, float max_r2,
                             int32_t* match_pos, float* match_d2, int variant, cudaStream_t s) {
-    switch ((variant >> 8) & 0xf) {  // experimental: lanes per query in the warm search
-        case 1: return launch_warm_one<1>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
-        case 2: return launch_warm_one<2>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
-        case 8: return launch_warm_one<8>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
-        default: return launch_warm_one<4>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
-    }
+    return launch_warm_one<4>(g, d_reading, nq_capacity, st, max_r2, match_pos, match_d2, variant, s);
 }
 
 }  // namespace b200

@@ -513,10 +513,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     if (lig == 0) {
                         float L = fminf(sqrtf(gsd), cover);
                         L -= 2e-6f * L;
-                        if ((variant_flags & 128) || gbp < 0 || gbp == pos) {
-                            // (bit 7: defer) position only: coordinates and normal of a NEW match are fetched after the
-                            // search phase, thread per entry; -(pos + 2) marks them stale
-                            ppp->w = __int_as_float((gbp >= 0 && gbp != pos) ? -(gbp + 2) : gbp);
+                        if (gbp < 0 || gbp == pos) {
+                            ppp->w = __int_as_float(gbp);
                             pnv->w = L;
                         } else {  // new match: its coordinates and normal go into the cache now
                             float4 pt = __ldg(g.pts + gbp), nn = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -541,22 +539,6 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             if (searched) {
                 __syncthreads();  // the search results of this block are in the cache
                 if (stamper) B200_STAMP(gst, 19);
-                // new matches: fetch coordinates and normal (thread per entry: one round trip for all of them)
-                if (have) {
-                    float4* ppp = cached ? s_pp + e : sp_pp + qi;
-                    int pos = __float_as_int(ppp->w);
-                    if (pos <= -2) {
-                        pos = -(pos + 2);
-                        float4 pt = __ldg(g.pts + pos);
-                        pt.w = __int_as_float(pos);
-                        *ppp = pt;
-                        if (MIN == 0) {
-                            float4* pnv = cached ? s_nv + e : sp_nv + qi;
-                            const float4 nn = __ldg(nrm + pos);
-                            *pnv = make_float4(nn.x, nn.y, nn.z, pnv->w);
-                        }
-                    }
-                }
             }
         }
         if (stamper) B200_STAMP(gst, 30);

@@ -37,32 +37,34 @@ def time_pair(label, d, cfg, reps=10, oracle_reps=2):
     print(label, json.dumps(out[label]), flush=True)
 
 
+only3 = "--only-cfg3" in sys.argv
 # config 1-like: 41k scan vs 41k map, knn 6, maxDist 2, point-to-plane, 10 iterations (docs/MapperConfiguration.md:172-189)
-d = synth.make_pair_3d(n_map=41_400, n_scan=41_339, world_size=(120.0, 120.0), n_boxes=14, scan_radius=60.0, dt=(0.10, -0.05, 0.02), drpy_deg=(0, 0, 1.0))
-time_pair("cfg1_knn6_41k", d, make_config(dim=3, knn=6, max_dist=2.0, outliers=(), minimizer="point_to_plane", max_iteration_count=10))
+d = None if only3 else synth.make_pair_3d(n_map=41_400, n_scan=41_339, world_size=(120.0, 120.0), n_boxes=14, scan_radius=60.0, dt=(0.10, -0.05, 0.02), drpy_deg=(0, 0, 1.0))
+if not only3: time_pair("cfg1_knn6_41k", d, make_config(dim=3, knn=6, max_dist=2.0, outliers=(), minimizer="point_to_plane", max_iteration_count=10))
 # config 4: 2-D, 10k-pt scans, point-to-point, dense k = 8
-d2 = synth.make_pair_2d()
-time_pair("cfg4_2d_knn8", d2, make_config(dim=2, knn=8, max_dist=0.5, outliers=(), minimizer="point_to_point", max_iteration_count=30))
+d2 = None if only3 else synth.make_pair_2d()
+if not only3: time_pair("cfg4_2d_knn8", d2, make_config(dim=2, knn=8, max_dist=0.5, outliers=(), minimizer="point_to_point", max_iteration_count=30))
 # config 2 for reference
-if not quick:
+if not quick and not only3:
     time_pair("cfg2", synth.make_pair_3d(), make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30))
 
 # config 5: batched pairs (200k scan vs 1M submap) on this GPU; 8 pairs = one GPU's share of the 64
-n_pairs = 4 if quick else 8
+n_pairs = 0 if only3 else (4 if quick else 8)
 cfg5 = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
 pairs = [synth.make_pair_3d(n_map=1_000_000, n_scan=200_000, seed=4000 + j) for j in range(n_pairs)]
-fn = batched.gpu_register_fn(cfg5, 0)
-batched.register_batch(lambda j: pairs[j], 1, fn)
-t0 = time.perf_counter()
-poses, ov, it = batched.register_batch(lambda j: pairs[j], n_pairs, fn)
-t_gpu = time.perf_counter() - t0
-fn.close()
-o = ob.OracleICP(cfg5)
-t0 = time.perf_counter(); o.set_map(pairs[0]["map"], pairs[0]["normals"]); rc, To, res, _, _ = o.register(pairs[0]["reading"]); t_cpu = time.perf_counter() - t0
-e = synth.pose_error(poses[0], To)
-out["cfg5_batched"] = dict(pairs=n_pairs, gpu_pairs_per_s=n_pairs / t_gpu, gpu_ms_per_pair=1e3 * t_gpu / n_pairs, cpu_ms_per_pair=1e3 * t_cpu,
+if n_pairs:
+  fn = batched.gpu_register_fn(cfg5, 0)
+  batched.register_batch(lambda j: pairs[j], 1, fn)
+  t0 = time.perf_counter()
+  poses, ov, it = batched.register_batch(lambda j: pairs[j], n_pairs, fn)
+  t_gpu = time.perf_counter() - t0
+  fn.close()
+  o = ob.OracleICP(cfg5)
+  t0 = time.perf_counter(); o.set_map(pairs[0]["map"], pairs[0]["normals"]); rc, To, res, _, _ = o.register(pairs[0]["reading"]); t_cpu = time.perf_counter() - t0
+  e = synth.pose_error(poses[0], To)
+  out["cfg5_batched"] = dict(pairs=n_pairs, gpu_pairs_per_s=n_pairs / t_gpu, gpu_ms_per_pair=1e3 * t_gpu / n_pairs, cpu_ms_per_pair=1e3 * t_cpu,
                            speedup=t_cpu / (t_gpu / n_pairs), pose_diff_rad=e[0], pose_diff_m=e[1], note="per pair: set_map (index build) + 30-iteration ICP; CPU: kd-tree build + ICP")
-print("cfg5", json.dumps(out["cfg5_batched"]), flush=True)
+if n_pairs: print("cfg5", json.dumps(out["cfg5_batched"]), flush=True)
 
 # config 3: online mapping through the host mirror of Mapper::processInput
 n_scans = 30 if quick else 120

@@ -11,10 +11,7 @@ from norlab_icp_mapper_b200.icp import ICP, make_config
 d = synth.make_pair_3d()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ref = None
-cases = [("general (variant 16)", 16, None), ("default", 0, None)]
-for w in ("1.5,0.01,0.1", "2,0.02,0.12", "2,0.03,0.2", "3,0.02,0.3", "2,0.05,0.3", "4,0.04,0.5", "1,0.005,0.1"):
-    cases.append(("window " + w, 0, w))
-cases = [("general (variant 16)", 16, None, None), ("always search (variant 32)", 32, None, None), ("default", 0, None, None)]
+cases = [("two barriers (variant 16)", 16, None, None), ("three barriers (variant 80)", 80, None, None), ("always search (variant 32)", 32, None, None), ("default", 0, None, None)]
 for w in ("2,0.02,0.12", "2,0.005,0.12", "2,0.0005,0.12", "3,0.0015,0.2", "1.5,0.001,0.08"):
     cases.append(("window " + w, 0, w, None))
 for mg in ("2,0.001,0.25", "3,0.005,0.25", "4,0.002,0.5", "3,0.002,0.1", "1.5,0.002,0.25", "3,0.02,0.5"):
