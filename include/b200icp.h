@@ -51,9 +51,13 @@ typedef enum b200icp_outlier_kind {
     B200ICP_OUTLIER_MAX_DIST = 2,     /* param = maxDist; w = dist2 <= maxDist^2                      */
     B200ICP_OUTLIER_MIN_DIST = 3,     /* param = minDist; w = dist2 >= minDist^2                      */
     B200ICP_OUTLIER_MEDIAN_DIST = 4,  /* param = factor;  w = dist2 <= factor * median(finite dist2)  */
-    B200ICP_OUTLIER_VAR_TRIMMED_DIST = 5 /* VarTrimmedDistOutlierFilter{minRatio = param, maxRatio = param2, lambda = param3}:
+    B200ICP_OUTLIER_VAR_TRIMMED_DIST = 5, /* VarTrimmedDistOutlierFilter{minRatio = param, maxRatio = param2, lambda = param3}:
                                             ratio = argmin FRMS over the sorted finite positive dist2 (optimizeInlierRatio),
                                             then w = dist2 <= quantile(finite dist2, ratio)                               */
+    B200ICP_OUTLIER_SURFACE_NORMAL = 6  /* SurfaceNormalOutlierFilter{maxAngle = param, rad}: w = 0 when the reading's normal (moved
+                                           with the reading) and the matched map point's normal, both normalised, have a dot
+                                           product below cos(maxAngle); all ones when either cloud has no normals (LPM: "Skipping
+                                           filtering").  The reading's normals come in through b200icp_register_normals.        */
 } b200icp_outlier_kind;
 
 /* icp.errorMinimizer */
@@ -186,6 +190,12 @@ int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature
 int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_t feature_rows,
                                 int64_t nq, const float* T_init, float* T_out,
                                 b200icp_result* result);
+
+/* icp(input) for a reading that carries the `normals` descriptor (dim x nq, column-major; e.g. from a
+ * SurfaceNormalDataPointsFilter in the `input:` chain): needed by SurfaceNormalOutlierFilter only.  reading_normals may be NULL
+ * (then identical to b200icp_register).  Host pointers. */
+int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq,
+                                 const float* reading_normals, const float* T_init, float* T_out, b200icp_result* result);
 
 /* matcher->findClosests(cloud) against the current map -- the KDTreeMatcher step of the loop and
  * the direct Nabo::NNS::knn call sites (PointDistanceMapperModule.cpp:36).  `queries` are in the

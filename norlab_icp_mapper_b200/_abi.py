@@ -9,7 +9,7 @@ MAX_OUTLIER_FILTERS = 4
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_MAP, ERR_CONVERGENCE, ERR_BOUND, ERR_NAN, ERR_TRANSFORM, \
     ERR_INVALID_FIELD, ERR_NOT_IMPLEMENTED = range(10)
 # b200icp_outlier_kind
-OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST, OUTLIER_VAR_TRIMMED_DIST = 1, 2, 3, 4, 5
+OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST, OUTLIER_VAR_TRIMMED_DIST, OUTLIER_SURFACE_NORMAL = 1, 2, 3, 4, 5, 6
 # b200icp_minimizer_kind
 MIN_POINT_TO_PLANE, MIN_POINT_TO_POINT, MIN_IDENTITY = 0, 1, 2
 
@@ -76,7 +76,8 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
     """Build a Config from the names used in the reference's `icp:` YAML node
     (docs/MapperConfiguration.md:172-189)."""
     kinds = {"trimmed": OUTLIER_TRIMMED_DIST, "max_dist": OUTLIER_MAX_DIST,
-             "min_dist": OUTLIER_MIN_DIST, "median": OUTLIER_MEDIAN_DIST, "var_trimmed": OUTLIER_VAR_TRIMMED_DIST}
+             "min_dist": OUTLIER_MIN_DIST, "median": OUTLIER_MEDIAN_DIST, "var_trimmed": OUTLIER_VAR_TRIMMED_DIST,
+             "surface_normal": OUTLIER_SURFACE_NORMAL}
     mins = {"point_to_plane": MIN_POINT_TO_PLANE, "point_to_point": MIN_POINT_TO_POINT,
             "identity": MIN_IDENTITY}
     c = Config()

@@ -163,7 +163,7 @@ int32_t validate_config(const b200icp_config* c, std::string& why) {
     int quant = 0;
     for (int f = 0; f < c->n_outlier; ++f) {
         const int kd = c->outlier_kind[f];
-        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_VAR_TRIMMED_DIST) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
+        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_SURFACE_NORMAL) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
         if (kd == B200ICP_OUTLIER_TRIMMED_DIST || kd == B200ICP_OUTLIER_MEDIAN_DIST || kd == B200ICP_OUTLIER_VAR_TRIMMED_DIST) ++quant;
         if (kd == B200ICP_OUTLIER_VAR_TRIMMED_DIST &&
             !(c->outlier_param[f] >= 0.f && c->outlier_param[f] < c->outlier_param2[f] && c->outlier_param2[f] <= 1.f && c->outlier_param3[f] > 0.f))
@@ -414,6 +414,9 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaFree(b.reading_tmp);
     cudaFree(b.match_pos);
     cudaFree(b.match_d2);
+    cudaFree(b.rnrm_in);
+    cudaFree(b.rnrm);
+    cudaFree(b.rnrm_tmp);
     cudaFree(b.hist);
     cudaFree(b.partials);
     cudaFree(b.state);
@@ -542,8 +545,9 @@ int32_t b200icp_set_map(b200icp_ctx* ctx, const float* features, int32_t feature
 
 // The ICP loop on device-resident reading points.
 static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int32_t rows, int64_t nq, const float* T_init,
-                                  float* T_out, b200icp_result* result) {
+                                  float* T_out, b200icp_result* result, const float* d_reading_normals = nullptr) {
     const int dim = ctx->cfg.dim;
+    ctx->prm.rnrm = nullptr;
     const IcpParams& p = ctx->prm;
     IcpBuffers& b = ctx->buf;
     cudaStream_t s = ctx->stream;
@@ -588,6 +592,12 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     } else {
         CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading, nullptr, nullptr, nullptr, nq, s));
         launches += 1;
+    }
+    if (d_reading_normals) {  // the reading's `normals` descriptor follows the reading: same rotation, same order
+        CK(launch_prep_normals(d_reading_normals, dim, Tpre, do_sort ? b.rnrm_tmp : b.rnrm, nq, s));
+        if (do_sort) CK(launch_gather_reading(b.rnrm_tmp, ctx->map.vals_out, b.rnrm, nq, s));
+        launches += do_sort ? 2 : 1;
+        ctx->prm.rnrm = b.rnrm;
     }
 
     const bool fixed_count = p.max_iteration_count > 0 && !p.use_differential && !p.use_bound;
@@ -730,6 +740,35 @@ int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_
     const int32_t eb = ensure_icp_buffers(ctx, nq);
     if (eb != B200ICP_OK) return eb;
     return register_on_device(ctx, d_reading, feature_rows, nq, T_init, T_out, result);
+}
+
+int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq, const float* reading_normals,
+                                 const float* T_init, float* T_out, b200icp_result* result) {
+    if (!reading_normals) return b200icp_register(ctx, reading, feature_rows, nq, T_init, T_out, result);
+    if (result) memset(result, 0, sizeof(*result));
+    const int32_t rc = register_checks(ctx, reading, feature_rows, nq, T_out);
+    if (rc != B200ICP_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int32_t eb = ensure_icp_buffers(ctx, nq);
+    if (eb != B200ICP_OK) return eb;
+    IcpBuffers& b = ctx->buf;
+    const int dim = ctx->cfg.dim;
+    if (nq > b.cap_rnrm) {
+        cudaFree(b.rnrm_in);
+        cudaFree(b.rnrm);
+        cudaFree(b.rnrm_tmp);
+        b.rnrm_in = nullptr;
+        b.rnrm = b.rnrm_tmp = nullptr;
+        b.cap_rnrm = 0;
+        const int64_t cap = grow_capacity(nq);
+        CK(cudaMalloc((void**)&b.rnrm_in, (size_t)cap * dim * sizeof(float)));
+        CK(cudaMalloc((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
+        CK(cudaMalloc((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
+        b.cap_rnrm = cap;
+    }
+    CK(cudaMemcpyAsync(b.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b.rnrm_in, reading_normals, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return register_on_device(ctx, b.reading_in, feature_rows, nq, T_init, T_out, result, b.rnrm_in);
 }
 
 int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq, const float* T_init,

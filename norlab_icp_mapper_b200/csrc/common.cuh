@@ -100,6 +100,8 @@ struct IcpParams {  // by-value kernel argument, constant for the life of a cont
     float outlier_param[B200ICP_MAX_OUTLIER_FILTERS];
     float outlier_param2[B200ICP_MAX_OUTLIER_FILTERS];
     float outlier_param3[B200ICP_MAX_OUTLIER_FILTERS];
+    const float4* rnrm;   // reading normals (refMean frame, same order as the reading) for SurfaceNormalOutlierFilter, or null:
+                          // set per registration, the only field that is not constant for the life of a context
     int quantile_filter;  // index of the Trimmed/Median filter or -1
     float quantile;       // ratio (Trimmed), 0.5 (Median), or < 0: read IcpState::dyn_quantile (VarTrimmed)
     int minimizer;
@@ -230,6 +232,10 @@ struct IcpBuffers {
     float* reading_in = nullptr;   // raw (dim+1) x N upload
     float4* reading = nullptr;     // reading in the refMean frame (T_refMean_dataIn applied)
     float4* reading_tmp = nullptr; // pre-sort
+    float* rnrm_in = nullptr;      // raw dim x N upload of the reading's normals (b200icp_register_normals)
+    float4* rnrm = nullptr;        // ... rotated into the refMean frame, same order as `reading`
+    float4* rnrm_tmp = nullptr;    // ... pre-sort
+    int64_t cap_rnrm = 0;
     int32_t* match_pos = nullptr;  // knn x N
     float* match_d2 = nullptr;
     uint32_t* hist = nullptr;      // max_iter x 3 x kHistBins
@@ -258,6 +264,8 @@ cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int 
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
                                 float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,
                                 uint32_t* d_vals, int64_t nq, cudaStream_t s);
+// dim x N column-major normals -> float4, rotated by the rotation block of Tpre16 (descriptors named `normals` rotate with the cloud)
+cudaError_t launch_prep_normals(const float* d_in, int dim, const float* Tpre16 /*host*/, float4* d_out, int64_t nq, cudaStream_t s);
 cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,
                                   cudaStream_t s);
 cudaError_t icp_device_setup();

@@ -43,6 +43,15 @@ __global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restri
     }
 }
 
+__global__ void __launch_bounds__(256) prep_normals_kernel(const float* __restrict__ in, int dim, Mat4 Tpre, float4* __restrict__ out, long long nq) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float x = in[i * dim + 0], y = in[i * dim + 1], z = (dim == 3) ? in[i * dim + 2] : 0.f;
+    const float* T = Tpre.m;
+    out[i] = make_float4(__fmaf_rn(T[8], z, __fmaf_rn(T[4], y, __fmul_rn(T[0], x))), __fmaf_rn(T[9], z, __fmaf_rn(T[5], y, __fmul_rn(T[1], x))),
+                         __fmaf_rn(T[10], z, __fmaf_rn(T[6], y, __fmul_rn(T[2], x))), 0.f);
+}
+
 __global__ void __launch_bounds__(256) gather_reading_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ perm,
                                                              float4* __restrict__ out, long long nq) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -324,6 +333,14 @@ cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const floa
     if (g_for_keys) g = *g_for_keys;
     prep_reading_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, rows, dim, T, d_out, g, g_for_keys ? d_keys : nullptr,
                                                                       d_vals, (long long)nq);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_normals(const float* d_in, int dim, const float* Tpre16, float4* d_out, int64_t nq, cudaStream_t s) {
+    if (nq <= 0) return cudaSuccess;
+    Mat4 T;
+    memcpy(T.m, Tpre16, sizeof(T.m));
+    prep_normals_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, dim, T, d_out, (long long)nq);
     return cudaGetLastError();
 }
 

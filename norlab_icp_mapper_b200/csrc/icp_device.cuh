@@ -565,6 +565,17 @@ __device__ __forceinline__ float warp_reduce_32slots(float (&v)[32], int lane) {
 // slot held by `lane` after warp_reduce_32slots: bit b of the lane selects the upper half at level b
 __device__ __forceinline__ int lane_slot(int lane) { return lane; }
 
+// LPM SurfaceNormalOutlierFilter: keep when the reading normal (rotated by T_iter like the reading) and the reference normal,
+// both normalised, have a dot product >= eps = cos(maxAngle).
+__device__ __forceinline__ bool surface_normal_keep(const float* T, const float4& rn, const float4& fn, float eps) {
+    const float rx = __fmaf_rn(T[8], rn.z, __fmaf_rn(T[4], rn.y, __fmul_rn(T[0], rn.x)));
+    const float ry = __fmaf_rn(T[9], rn.z, __fmaf_rn(T[5], rn.y, __fmul_rn(T[1], rn.x)));
+    const float rz = __fmaf_rn(T[10], rn.z, __fmaf_rn(T[6], rn.y, __fmul_rn(T[2], rn.x)));
+    const float lr = sqrtf(rx * rx + ry * ry + rz * rz), lf = sqrtf(fn.x * fn.x + fn.y * fn.y + fn.z * fn.z);
+    const float dot = (rx / lr) * (fn.x / lf) + (ry / lr) * (fn.y / lf) + (rz / lr) * (fn.z / lf);
+    return !(dot < eps);
+}
+
 // One (reading point, neighbour) entry of ErrorElements: outlier weights, then the error-minimiser
 // products.  MIN: 0 point-to-plane (29 sums), 1 point-to-point (18 sums), 2 identity (2 sums).
 template <int MIN>
@@ -584,6 +595,9 @@ __device__ __forceinline__ void accumulate_entry(float* acc, const IcpParams& pr
             case B200ICP_OUTLIER_MEDIAN_DIST: keep = d <= p * qlimit; break;
             case B200ICP_OUTLIER_MAX_DIST: keep = d <= p * p; break;
             case B200ICP_OUTLIER_MIN_DIST: keep = d >= p * p; break;
+            case B200ICP_OUTLIER_SURFACE_NORMAL:
+                if (prm.rnrm && nrm) keep = surface_normal_keep(T, __ldg(prm.rnrm + ((K == 1) ? e : e / K)), __ldg(nrm + pos), cosf(p));
+                break;
         }
         w *= keep ? 1.f : 0.f;
     }

@@ -160,7 +160,7 @@ __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bo
 
 // Product of the weights of every outlier filter EXCEPT the quantile-based one (fast path: that one is
 // decided after the barrier).
-__device__ __forceinline__ float other_filters_weight(const IcpParams& prm, float d) {
+__device__ __forceinline__ float other_filters_weight(const IcpParams& prm, float d, const float* T, const float4* rn, const float4& fn) {
     float w = 1.f;
     for (int f = 0; f < prm.n_outlier; ++f) {
         const float p = prm.outlier_param[f];
@@ -168,6 +168,9 @@ __device__ __forceinline__ float other_filters_weight(const IcpParams& prm, floa
         switch (prm.outlier_kind[f]) {
             case B200ICP_OUTLIER_MAX_DIST: keep = d <= p * p; break;
             case B200ICP_OUTLIER_MIN_DIST: keep = d >= p * p; break;
+            case B200ICP_OUTLIER_SURFACE_NORMAL:
+                if (rn) keep = surface_normal_keep(T, __ldg(rn), fn, cosf(p));  // (rn is null when either cloud has no normals)
+                break;
             default: break;
         }
         w *= keep ? 1.f : 0.f;
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     unsigned epoch = 0;
     uint32_t n_runs = 0, n_hist = 0;  // publish/finish rounds (stage-1 histograms) so far: parity selects the double buffer
     const bool use_quantile = prm.quantile_filter >= 0;
+    const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
     constexpr int kPerSweep = kChunk;  // the general path walks this CTA's chunks
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), nn = pt;
         if (pos >= 0) {
             pt = __ldg(g.pts + pos);
-            if (MIN == 0) nn = __ldg(nrm + pos);
+            if (MIN == 0 || sn_active) nn = __ldg(nrm + pos);
         }
         pt.w = __int_as_float(pos);
         nn.w = 0.f;
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             pnv->w = L;
                         } else {  // new match: its coordinates and normal go into the cache now
                             float4 pt = __ldg(g.pts + gbp), nn = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (MIN == 0) nn = __ldg(nrm + gbp);
+                            if (MIN == 0 || sn_active) nn = __ldg(nrm + gbp);
                             pt.w = __int_as_float(gbp);
                             nn.w = L;
                             *ppp = pt;
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         c_below += cls == 0;
                         c_above += cls == 2;
                         if (cls != 2) {
-                            const float wo = other_filters_weight(prm, d);
+                            const float wo = other_filters_weight(prm, d, st.T, sn_active ? prm.rnrm + qi : nullptr, nv);
                             float3 p = make_float3(CUDART_NAN_F, 0.f, 0.f);
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (wo != 0.f) {

@@ -63,8 +63,10 @@ class ICPSequence {
     }
     TransformationParameters operator()(const DataPoints& cloud) {
         TransformationParameters T = TransformationParameters::Identity(dim + 1);
+        // (a reading that carries `normals` hands them over: SurfaceNormalOutlierFilter compares them with the map's)
         const int32_t rc = cloud.onDevice ? b200icp_scan_register(ctx, nullptr, T.m, &last)
-                                          : b200icp_register(ctx, cloud.features.data(), dim + 1, cloud.getNbPoints(), nullptr, T.m, &last);
+                                          : b200icp_register_normals(ctx, cloud.features.data(), dim + 1, cloud.getNbPoints(),
+                                                                     cloud.normals.empty() ? nullptr : cloud.normals.data(), nullptr, T.m, &last);
         if (rc == B200ICP_ERR_NO_MAP) return T;  // LPM: no map -> identity
         check(ctx, rc);
         return T;

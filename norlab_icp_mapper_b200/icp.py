@@ -90,7 +90,8 @@ class ICP:
         return h.value, tuple(int(x) for x in dims)
 
     # -- correction = icp(input) ---------------------------------------------------------------
-    def __call__(self, reading, T_init=None):
+    def __call__(self, reading, T_init=None, reading_normals=None):
+        """reading_normals: the reading's `normals` descriptor (N x dim), needed by SurfaceNormalOutlierFilter only."""
         reading = _cloud(reading, self.n)
         tptr = None
         if T_init is not None:
@@ -98,7 +99,13 @@ class ICP:
             tptr = T_cm.ctypes.data
         T_out = np.zeros(self.n * self.n, np.float32)
         res = Result()
-        rc = self._L.b200icp_register(self._h, reading.ctypes.data, self.n, len(reading), tptr, T_out.ctypes.data, C.byref(res))
+        if reading_normals is not None:
+            rn = _cloud(reading_normals, self.dim)
+            assert len(rn) == len(reading)
+            rc = self._L.b200icp_register_normals(self._h, reading.ctypes.data, self.n, len(reading), rn.ctypes.data, tptr, T_out.ctypes.data,
+                                                  C.byref(res))
+        else:
+            rc = self._L.b200icp_register(self._h, reading.ctypes.data, self.n, len(reading), tptr, T_out.ctypes.data, C.byref(res))
         self.last_result = res
         self._check(rc)
         return T_out.reshape(self.n, self.n).T.copy()

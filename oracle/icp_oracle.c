@@ -476,6 +476,8 @@ struct orc_icp {
     float mean[3];
     orc_kdtree* tree;
     float last_var_ratio; /* VarTrimmed: the tuned ratio of the last iteration (diagnostic) */
+    float* reading_normals; /* dim floats per reading point for the NEXT register call (SurfaceNormalOutlierFilter), or NULL */
+    int64_t n_reading_normals;
     char err[256];
 };
 
@@ -490,11 +492,25 @@ void orc_icp_destroy(orc_icp* o) {
     if (!o) return;
     free(o->map);
     free(o->normals);
+    free(o->reading_normals);
     orc_kdtree_free(o->tree);
     free(o);
 }
 const char* orc_icp_last_error(const orc_icp* o) { return o ? o->err : "null oracle"; }
 float orc_icp_last_var_ratio(const orc_icp* o) { return o ? o->last_var_ratio : 0.f; }
+/* the `normals` descriptor of the reading handed to the next orc_icp_register (dim x n, column-major); NULL clears it */
+int32_t orc_icp_set_reading_normals(orc_icp* o, const float* normals, int64_t n) {
+    if (!o || n < 0) return B200ICP_ERR_INVALID_ARG;
+    free(o->reading_normals);
+    o->reading_normals = NULL;
+    o->n_reading_normals = 0;
+    if (normals && n > 0) {
+        o->reading_normals = (float*)malloc((size_t)n * o->dim * sizeof(float));
+        memcpy(o->reading_normals, normals, (size_t)n * o->dim * sizeof(float));
+        o->n_reading_normals = n;
+    }
+    return B200ICP_OK;
+}
 void orc_icp_get_mean(const orc_icp* o, float mean[3]) {
     for (int d = 0; d < 3; ++d) mean[d] = o->mean[d];
 }
@@ -660,7 +676,7 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
         if (result) memset(result, 0, sizeof(*result));
         return B200ICP_ERR_NO_MAP;
     }
-    float *reading = NULL, *step = NULL, *d2 = NULL, *w = NULL, *scratch = NULL;
+    float *reading = NULL, *step = NULL, *d2 = NULL, *w = NULL, *scratch = NULL, *rnrm = NULL;
     int32_t* ids = NULL;
     reading = (float*)calloc((size_t)nq * 4 + 4, sizeof(float));
     step = (float*)calloc((size_t)nq * 4 + 4, sizeof(float));
@@ -682,6 +698,16 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
     for (int64_t i = 0; i < nq; ++i) {
         apply_T_point(Tpre, dim, reading_in + i * rows, reading + i * 4);
         reading[i * 4 + 3] = 1.f;
+    }
+
+    /* descriptors named `normals` rotate with the cloud (LPM TransformationsImpl.cpp) */
+    if (o->reading_normals && o->n_reading_normals == nq) {
+        rnrm = (float*)malloc((size_t)nq * 3 * sizeof(float));
+        for (int64_t i = 0; i < nq; ++i) {
+            float out3[3] = {0, 0, 0};
+            apply_R_vec(Tpre, dim, o->reading_normals + i * dim, out3);
+            for (int d = 0; d < 3; ++d) rnrm[i * 3 + d] = d < dim ? out3[d] : 0.f;
+        }
     }
 
     float T_iter[16];
@@ -735,6 +761,34 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
                     if (dists_quantile(d2, m, ratio, &limit, scratch)) FAIL(o, B200ICP_ERR_CONVERGENCE, "no outlier to filter");
                     for (int64_t i = 0; i < m; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;
                     o->last_var_ratio = ratio;
+                    break;
+                }
+                case B200ICP_OUTLIER_SURFACE_NORMAL: {
+                    /* LPM SurfaceNormalOutlierFilter{maxAngle}: eps = cos(maxAngle); w = 0 when the (normalised) reading normal,
+                     * moved by T_iter, and the (normalised) reference normal of the match have dot < eps, or there is no match;
+                     * all ones when either cloud lacks normals ("Skipping filtering") */
+                    if (!rnrm || !o->normals) break;
+                    const float eps = cosf(prm);
+                    for (int64_t i = 0; i < nq; ++i) {
+                        float nr[3] = {0, 0, 0};
+                        apply_R_vec(T_iter, dim, rnrm + i * 3, nr);
+                        float ln = 0.f;
+                        for (int d = 0; d < dim; ++d) ln += nr[d] * nr[d];
+                        ln = sqrtf(ln);
+                        for (int j = 0; j < k; ++j) {
+                            const int32_t id = ids[i * k + j];
+                            if (id < 0) {
+                                w[i * k + j] = 0.f;
+                                continue;
+                            }
+                            const float* nf = o->normals + (int64_t)id * 3;
+                            float lf = 0.f, dot = 0.f;
+                            for (int d = 0; d < dim; ++d) lf += nf[d] * nf[d];
+                            lf = sqrtf(lf);
+                            for (int d = 0; d < dim; ++d) dot += (nr[d] / ln) * (nf[d] / lf);
+                            w[i * k + j] *= (dot < eps) ? 0.f : 1.f;
+                        }
+                    }
                     break;
                 }
                 case B200ICP_OUTLIER_MAX_DIST:
@@ -1030,6 +1084,7 @@ done:
     free(d2);
     free(w);
     free(scratch);
+    free(rnrm);
     return rc;
 }
 

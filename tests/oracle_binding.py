@@ -112,9 +112,17 @@ class OracleICP:
         rc = lib().orc_icp_match(self._h, queries, queries.shape[1], queries.shape[0], ids, d2, nthreads)
         return rc, ids, d2
 
-    def register(self, reading, T_init=None, nthreads=0, want_trace=False):
+    def register(self, reading, T_init=None, nthreads=0, want_trace=False, reading_normals=None):
         """Returns (status, T (n x n, row-major numpy view of the math matrix), Result, trace, secs)."""
         reading = _cloud(reading)
+        L = lib()
+        L.orc_icp_set_reading_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        if reading_normals is not None:
+            rn = np.ascontiguousarray(reading_normals, np.float32)
+            assert rn.shape == (reading.shape[0], self.n - 1)
+            L.orc_icp_set_reading_normals(self._h, rn.ctypes.data_as(C.c_void_p), rn.shape[0])
+        else:
+            L.orc_icp_set_reading_normals(self._h, None, 0)
         n = self.n
         T_out = np.zeros(n * n, np.float32)
         res = Result()

@@ -229,6 +229,48 @@ def test_large_reading_spills_the_match_cache(oracle):
     assert outs[0][1] == res_o.pairs_last_iter
 
 
+def test_surface_normal_outlier_filter(oracle, pair3d):
+    """SurfaceNormalOutlierFilter{maxAngle} (a staple of norlab's configurations, next to TrimmedDist): pairs whose
+    reading normal -- carried through icp(input) and rotated with the reading -- and map normal disagree by more than
+    maxAngle get weight 0.  Reading normals: the true surface normals plus noise, sign made consistent with the map's;
+    the filter must actually drop pairs, and poses / kept pairs must match the oracle on the persistent loop (k = 1,
+    one- and two-barrier iterations), the general path and the kernel-per-step path (k = 3)."""
+    from norlab_icp_mapper_b200.icp import ICP
+    d = pair3d
+    rng = np.random.default_rng(11)
+    # reading normals: normal of the nearest map point (after the true correction), perturbed, expressed in the reading's frame
+    o0 = oracle.OracleICP(make_config(dim=3, knn=1, max_dist=5.0, outliers=(), minimizer="point_to_point", max_iteration_count=1))
+    o0.set_map(d["map"], d["normals"])
+    truth = synth.homog(synth.apply_T(d["correction_true"], d["reading"]))
+    _, ids, _ = o0.match(truth)
+    R = np.asarray(d["correction_true"], np.float64)[:3, :3]
+    rn = d["normals"][np.maximum(ids[:, 0], 0)].astype(np.float64) + rng.normal(0, 0.25, (len(truth), 3))
+    rn = (rn / np.linalg.norm(rn, axis=1, keepdims=True)) @ R  # map frame -> reading frame (R^T applied to rows)
+    rn = rn.astype(np.float32)
+    for k, minimizer, variants in ((1, "point_to_plane", (0, 16 | 64, 4)), (3, "point_to_point", (0,))):
+        chain = (("trimmed", 0.9), ("surface_normal", 0.35))
+        cfg = make_config(dim=3, knn=k, max_dist=1.0, outliers=chain, minimizer=minimizer, max_iteration_count=12)
+        o = oracle.OracleICP(cfg)
+        o.set_map(d["map"], d["normals"])
+        rc, T_o, res_o, _, _ = o.register(d["reading"], reading_normals=rn)
+        assert rc == _abi.OK
+        rc, T_plain, res_plain, _, _ = o.register(d["reading"])
+        assert res_o.pairs_last_iter < 0.9 * res_plain.pairs_last_iter  # the filter bites
+        for variant in variants:
+            cfg.nn_variant = variant
+            g = ICP(cfg)
+            g.set_map(d["map"], d["normals"])
+            T_g = g(d["reading"], reading_normals=rn)
+            res_g = g.last_result
+            T_non = g(d["reading"])  # without reading normals the filter is skipped, like upstream
+            res_non = g.last_result
+            g.close()
+            er, et = synth.pose_error(T_g, T_o)
+            assert er <= TOL_RAD and et <= TOL_M, (k, variant, er, et)
+            assert abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.002 * res_o.pairs_last_iter + 2, (k, variant)
+            assert res_non.pairs_last_iter == res_plain.pairs_last_iter
+
+
 def test_var_trimmed_dist_outlier_filter(oracle, pair3d):
     """VarTrimmedDistOutlierFilter (LPM defaults minRatio 0.05, maxRatio 0.99, lambda 0.95): the ratio is tuned every
     iteration from the sorted distances.  The device sums in fp64 where upstream (and the oracle) sum sequentially in
