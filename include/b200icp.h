@@ -240,6 +240,11 @@ int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, 
  * reference wraps around the filter, so the two whole-map transforms are not needed. */
 int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn);
 
+/* The same filter on an arbitrary host cloud -- a SurfaceNormalDataPointsFilter in the `input:` chain (Mapper.cpp:187-191), which
+ * configurations that use SurfaceNormalOutlierFilter need on the reading.  normals_out: dim x n, column-major. */
+int32_t b200icp_cloud_surface_normals(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, int32_t knn,
+                                      float* normals_out);
+
 /* Map::loadCells (load = 1, Map.cpp:71-128) / Map::unloadCells (load = 0, Map.cpp:140-230) for the
  * slab {startRow, endRow, startColumn, endColumn, startAisle, endAisle} of 20 m cells.  Points never
  * leave HBM: unloading clears their `loaded` flag (the reference moves them to the CellManager),

@@ -40,7 +40,8 @@ typedef struct b200mapper_config {
     int32_t add_probability_dynamic;
     float probability_dynamic_value;
     int32_t reserve_points;    /* > 0: pre-size the device map for this many points (no reference counterpart) */
-    int32_t reserved[3];
+    int32_t input_surface_normal_knn; /* input: SurfaceNormalDataPointsFilter{knn} on the reading (for SurfaceNormalOutlierFilter); 0 = absent */
+    int32_t reserved[2];
 } b200mapper_config;
 
 typedef struct b200mapper_stats {

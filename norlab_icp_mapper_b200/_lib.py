@@ -21,7 +21,7 @@ SYMBOLS = [
     "b200icp_register_device", "b200icp_register_normals", "b200icp_match", "b200icp_knn", "b200icp_transform",
     "b200icp_transform_device", "b200icp_get_map_mean", "b200icp_get_grid_info",
     "b200icp_set_trace", "b200icp_get_trace", "b200icp_map_insert_point_distance",
-    "b200icp_map_surface_normals", "b200icp_map_window", "b200icp_map_commit", "b200icp_map_counts",
+    "b200icp_map_surface_normals", "b200icp_cloud_surface_normals", "b200icp_map_window", "b200icp_map_commit", "b200icp_map_counts",
     "b200icp_map_has_normals", "b200icp_map_download", "b200icp_map_set_prob", "b200icp_map_has_prob",
     "b200icp_map_download_prob", "b200icp_map_append", "b200icp_map_reserve", "b200icp_filter_cloud", "b200icp_scan_upload", "b200icp_scan_size", "b200icp_scan_transform", "b200icp_scan_register",
     "b200icp_scan_insert_point_distance", "b200icp_scan_download", "b200icp_map_octree", "b200icp_map_cut_at_threshold", "b200icp_map_dynamic_points",

@@ -1186,6 +1186,36 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
     return B200ICP_OK;
 }
 
+/* SurfaceNormalDataPointsFilter{knn} on an arbitrary host cloud (the `input:` chain of a configuration that wants normals on
+ * the reading, e.g. for SurfaceNormalOutlierFilter): grid over the cloud, self k-NN, covariance, smallest eigenvector. */
+int32_t b200icp_cloud_surface_normals(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, int32_t knn, float* normals_out) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n < 0 || (n > 0 && (!features || !normals_out))) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
+    if (knn < 1 || knn > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "knn must be in [1, 32]");
+    if (n == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t fb = (((size_t)n * feature_rows * sizeof(float)) + 255) / 256 * 256, nb = (size_t)n * dim * sizeof(float);
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + 256));
+    float* d_in = ctx->d_stage_a;
+    float* d_nrm = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->d_stage_a) + fb);
+    CK(cudaMemcpyAsync(d_in, features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, s));
+    CK(grid_build(ctx->aux, d_in, feature_rows, dim, nullptr, n, /*centre=*/false, 0.f, s));
+    const int32_t eb = ensure_query_buffers(ctx, n, knn);
+    if (eb != B200ICP_OK) return eb;
+    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+    *h_nq = (int)n;
+    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(launch_knn(ctx->aux.view, ctx->aux.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+                  /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+    // d_q4 (n float4, sized by ensure_query_buffers) receives the cell-sorted copy nobody needs; d_nrm the cloud-order normals
+    CK(launch_normals(ctx->aux.view, dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->d_q4, d_nrm, nullptr, s));
+    CK(cudaMemcpyAsync(normals_out, d_nrm, nb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return B200ICP_OK;
+}
+
 /* development aid / tests (not in the public header): points whose normal the last b200icp_map_surface_normals recomputed */
 int64_t b200icp_debug_normals_recomputed(const b200icp_ctx* ctx) { return ctx ? ctx->last_normals_recomputed : -1; }
 

@@ -20,6 +20,7 @@ Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMa
       inputFilters(config.inputFilters),
       addProbabilityDynamic(config.addProbabilityDynamic),
       probabilityDynamicValue(config.probabilityDynamicValue),
+      inputSurfaceNormalKnn(config.inputSurfaceNormalKnn),
       mapUpdateCondition(config.mapUpdateCondition),
       is3D(is3D_),
       isOnline(isOnline_),
@@ -67,7 +68,7 @@ void Mapper::applyInputFilters(DataPoints& in) {
     int64_t n = in.getNbPoints();
     ICPSequence::check(icp.context(), b200icp_filter_cloud(icp.context(), in.features.data(), in.dim + 1, &n, chain.data(), (int32_t)chain.size()));
     in.features.resize((size_t)n * (in.dim + 1));
-    if (addProbabilityDynamic) in.probabilityDynamic.assign((size_t)n, probabilityDynamicValue);
+    attachInputDescriptors(in);
 }
 
 // Mapper.cpp:194-238

@@ -20,6 +20,7 @@ struct MapperConfig {
     std::vector<b200icp_filter> inputFilters;                // YAML `input:` (Mapper.cpp:80-88): BoundingBox / DistanceLimit entries
     bool addProbabilityDynamic = false;                      // ... AddDescriptorDataPointsFilter{probabilityDynamic, 1, [value]}
     float probabilityDynamicValue = 0.6f;
+    int inputSurfaceNormalKnn = 0;                           // ... SurfaceNormalDataPointsFilter{knn} on the reading; 0 = absent
     std::string mapUpdateCondition = "distance";            // mapper.updateCondition.type (Mapper.cpp:117-146)
     float mapUpdateValue = 1.0f;                             // ... .value (DEFAULT_MAP_UPDATE_DISTANCE, Mapper.h:20)
     float sensorMaxRange = 200.0f;                           // mapper.sensorMaxRange (Mapper.cpp:152-160)
@@ -32,6 +33,7 @@ class Mapper {
     std::vector<b200icp_filter> inputFilters;
     bool addProbabilityDynamic;
     float probabilityDynamicValue;
+    int inputSurfaceNormalKnn;
     std::string mapUpdateCondition;
     float mapUpdateOverlap = 0.f, mapUpdateDelay = 0.f, mapUpdateDistance = 1.0f;
     bool is3D, isOnline;
@@ -53,8 +55,15 @@ class Mapper {
    public:
     Mapper(const MapperConfig& config, bool is3D, bool isOnline, bool isMapping, bool saveMapCellsOnHardDrive, int device = 0);
     void applyInputFilters(DataPoints& inputInSensorFrame);
-    void attachInputDescriptors(DataPoints& input) const {  // AddDescriptorDataPointsFilter of the `input:` chain
+    // the descriptor-producing entries of the `input:` chain: AddDescriptorDataPointsFilter{probabilityDynamic} and
+    // SurfaceNormalDataPointsFilter{knn} (normals on the reading, for SurfaceNormalOutlierFilter)
+    void attachInputDescriptors(DataPoints& input) {
         if (addProbabilityDynamic && input.probabilityDynamic.empty()) input.probabilityDynamic.assign((size_t)input.getNbPoints(), probabilityDynamicValue);
+        if (inputSurfaceNormalKnn > 0 && input.normals.empty() && input.getNbPoints() > 0) {
+            input.normals.resize((size_t)input.getNbPoints() * input.dim);
+            ICPSequence::check(icp.context(), b200icp_cloud_surface_normals(icp.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
+                                                                            inputSurfaceNormalKnn, input.normals.data()));
+        }
     }
     void processInput(const DataPoints& filteredInputInSensorFrame, const TransformationParameters& estimatedPose, double timeStamp);
     DataPoints getMap();

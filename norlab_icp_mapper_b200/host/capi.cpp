@@ -92,6 +92,7 @@ int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapp
         for (int i = 0; i < cfg->n_input_filters && i < 6; ++i) mc.inputFilters.push_back(cfg->input_filters[i]);
         mc.addProbabilityDynamic = cfg->add_probability_dynamic != 0;
         mc.probabilityDynamicValue = cfg->probability_dynamic_value;
+        mc.inputSurfaceNormalKnn = cfg->input_surface_normal_knn;
         m->dim = cfg->is_3d ? 3 : 2;
         m->mapper.reset(new Mapper(mc, cfg->is_3d != 0, cfg->is_online != 0, cfg->is_mapping != 0, false, device));
         if (cfg->reserve_points > 0)

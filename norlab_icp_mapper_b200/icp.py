@@ -173,6 +173,14 @@ class ICP:
     def map_surface_normals(self, knn):
         self._check(self._L.b200icp_map_surface_normals(self._h, knn))
 
+    def cloud_surface_normals(self, features, knn):
+        """SurfaceNormalDataPointsFilter{knn} on a host cloud (N x (dim + 1)); returns N x dim normals."""
+        pts = _cloud(features, self.n)
+        out = np.zeros((len(pts), self.dim), np.float32)
+        self._L.b200icp_cloud_surface_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]
+        self._check(self._L.b200icp_cloud_surface_normals(self._h, pts.ctypes.data, self.n, len(pts), knn, out.ctypes.data))
+        return out
+
     def map_window(self, load, slab):
         slab = np.ascontiguousarray(slab, np.int32)
         assert slab.shape == (6,)

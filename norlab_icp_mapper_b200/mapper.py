@@ -57,7 +57,7 @@ class MapperConfig(C.Structure):
                 ("use_cut_at_threshold", C.c_int32), ("cut_threshold", C.c_float),
                 ("n_input_filters", C.c_int32), ("input_filters", InputFilter * 6),
                 ("add_probability_dynamic", C.c_int32), ("probability_dynamic_value", C.c_float),
-                ("reserve_points", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("reserve_points", C.c_int32), ("input_surface_normal_knn", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class MapperStats(C.Structure):
@@ -104,7 +104,8 @@ class Mapper:
 
     def __init__(self, icp_config, is3D=True, isOnline=False, isMapping=True, saveMapCellsOnHardDrive=False, *,
                  updateCondition=("distance", 1.0), sensorMaxRange=200.0, minDistNewPoint=0.15, surfaceNormalKnn=0,
-                 dynamicPoints=None, octree=None, cutAtThreshold=None, inputFilters=(), addProbabilityDynamic=None, reservePoints=0, device=0):
+                 dynamicPoints=None, octree=None, cutAtThreshold=None, inputFilters=(), addProbabilityDynamic=None, reservePoints=0,
+                 inputSurfaceNormalKnn=0, device=0):
         """dynamicPoints: _abi.DynamicParams or None; octree: (maxSizeByNode, samplingMethod) or None (then PointDistance);
         cutAtThreshold: threshold or None; inputFilters: InputFilter list; addProbabilityDynamic: value or None."""
         self._L = load()
@@ -128,6 +129,7 @@ class Mapper:
         if addProbabilityDynamic is not None:
             cfg.add_probability_dynamic, cfg.probability_dynamic_value = 1, addProbabilityDynamic
         cfg.reserve_points = int(reservePoints)
+        cfg.input_surface_normal_knn = int(inputSurfaceNormalKnn)  # input: SurfaceNormalDataPointsFilter{knn} on the reading
         self.dim = 3 if is3D else 2
         self.n = self.dim + 1
         h = C.c_void_p()

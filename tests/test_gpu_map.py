@@ -198,3 +198,18 @@ def test_incremental_normals_across_a_window_move(monkeypatch):
     assert ci <= b_i < ci + 0.2 * len(fi) and b_f == len(ff)  # the strip itself + its neighbours
     dots = np.abs((ni * nf).sum(axis=1))
     assert np.isfinite(ni).all() and (dots > 0.9999).mean() > 0.999, (dots > 0.9999).mean()
+
+
+def test_cloud_surface_normals_for_the_input_chain(gpu, oracle, pair):
+    """SurfaceNormalDataPointsFilter on a reading (input chain): same normals as the oracle's filter, in the cloud's order,
+    and the map held by the context is left alone."""
+    gpu.set_map(pair["map"][:30_000], None)
+    before = gpu.map_counts()
+    scan = pair["reading"]
+    nrm = gpu.cloud_surface_normals(scan, 12)
+    rc, onrm = oracle.surface_normals(scan, 12)
+    assert rc == 0 and nrm.shape == (len(scan), 3)
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
+    cosang = np.abs(np.einsum("ij,ij->i", nrm, onrm))
+    assert np.median(cosang) > 0.999999 and (cosang > 0.9999).mean() > 0.99, (np.median(cosang), (cosang > 0.9999).mean())
+    assert gpu.map_counts() == before

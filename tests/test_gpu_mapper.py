@@ -189,3 +189,35 @@ def test_example_config_pipeline_matches_reference_sequence(oracle):
     d, _ = cKDTree(ref.map[:, :3]).query(feat[:, :3])
     assert (d < 1e-4).mean() > 0.995  # same surviving points
     gpu.close()
+
+
+def test_mapper_with_reading_normals_and_surface_normal_outlier_filter():
+    """A configuration in norlab's usual style: SurfaceNormalDataPointsFilter on the reading (`input:`), TrimmedDist +
+    SurfaceNormalOutlierFilter in `icp.outlierFilters`, PointDistance module, SurfaceNormal post filter.  The reading's
+    normals travel through processInput (transform, icp(input), insert); the filter drops pairs; poses stay on the truth."""
+    from norlab_icp_mapper_b200.mapper import Mapper
+    world = synth.World3D(seed=21, size=(80.0, 80.0), n_boxes=10)
+    outs = {}
+    for name, chain in (("with", (("trimmed", 0.9), ("surface_normal", 0.3))), ("without", (("trimmed", 0.9),))):
+        cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=chain, minimizer="point_to_plane", max_iteration_count=25, differential=(1e-3, 1e-3, 3))
+        m = Mapper(cfg, True, False, True, False, updateCondition=("distance", 0.5), sensorMaxRange=60.0, minDistNewPoint=0.1, surfaceNormalKnn=10,
+                   inputSurfaceNormalKnn=10)
+        rng = np.random.default_rng(3)
+        errs, overlaps = [], []
+        for i in range(5):
+            T_true = synth.make_T((1.0 * i, 0.3 * i, 1.5), (0, 0, 2.0 * i))
+            S, _ = world.sample(30_000, np.random.default_rng(100 + i), noise=0.01, center=T_true[:3, 3], radius=50.0)
+            scan = synth.homog(synth.apply_T(np.linalg.inv(T_true), S))
+            T_est = T_true @ synth.make_T(rng.normal(0, 0.03, 3), rng.normal(0, 0.3, 3)) if i else T_true
+            m.processInput(scan, T_est.astype(np.float32), 0.1 * i)
+            errs.append(synth.pose_error(m.getPose(), T_true))
+            overlaps.append(m.stats().overlap)
+        feat, nrm = m.getMap()
+        outs[name] = (errs, overlaps, len(feat), nrm)
+        m.close()
+    for name in outs:
+        errs, overlaps, n, nrm = outs[name]
+        assert max(e[0] for e in errs) < 2e-3 and max(e[1] for e in errs) < 0.03, (name, errs)
+        assert n > 30_000 and np.isfinite(nrm).all()
+    # the overlap (weighted ratio of used pairs) is lower with the normal filter: it really rejects pairs
+    assert np.mean(outs["with"][1][1:]) < np.mean(outs["without"][1][1:]) - 0.01, (outs["with"][1], outs["without"][1])
