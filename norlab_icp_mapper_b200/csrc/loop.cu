@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     __shared__ IcpState st;
     __shared__ uint32_t sh[kSel0Bins];   // radix level 0 histogram, then staging / the candidate list
     __shared__ uint32_t sh2[1024];       // local radix levels
-    __shared__ uint32_t s_warp[kLoopWarps + 1];
+    __shared__ uint32_t s_warp[kLoopWarps + 1], s_warp2[kLoopWarps];
     __shared__ uint32_t s_bin, s_res, s_cnt, s_stage, s_base;
     __shared__ double s_part[kLoopWarps][NS];
     __shared__ double s_red[kLoopWarps][kAccSlots];
@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             const bool cached = e < kCacheCap;
             const long long qi = have ? qi_of(e) : 0;
             bool listed = false;
+            int cls = 0;
             unsigned long long t_s0 = 0;
             if (searched) {
                 if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_s0));
@@ -447,17 +448,38 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             *pd2 = d2n;  // inf when there is (still) no neighbour within maxDist
                         } else {
                             listed = true;
+                            // cost class by ball radius in cells: beyond the 2 x 2 rows of the search's first phase (> 0.5) the
+                            // search gets long; 0 = cheapest
+                            const float rc = dn * g.inv_h;
+                            cls = (variant_flags & 128) ? 0 : (!(rc <= 1.0f) ? 3 : (rc > 0.5f ? 2 : (rc > 0.3f ? 1 : 0)));
                         }
                     }
                 }
-                // ordered work list (neighbouring groups get neighbouring queries)
-                const unsigned bal = __ballot_sync(0xffffffffu, listed);
-                if (lane == 0) s_warp[warp] = __popc(bal);
+                // ordered work list (neighbouring groups get neighbouring queries), longest searches first (four cost classes by
+                // ball radius): warps take batches dynamically, so the expensive ones must not be the last to start
+                unsigned bal[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) bal[c] = __ballot_sync(0xffffffffu, listed && cls == c);
+                if (lane == 0) {  // two packed prefix sums: (class 3 | class 2 << 16), (class 1 | class 0 << 16); <= 1024 entries in all
+                    s_warp[warp] = (uint32_t)__popc(bal[3]) | ((uint32_t)__popc(bal[2]) << 16);
+                    s_warp2[warp] = (uint32_t)__popc(bal[1]) | ((uint32_t)__popc(bal[0]) << 16);
+                }
                 if (tid == 0) s_nlist = 0u;  // cursor of the S phase
                 __syncthreads();
-                uint32_t before = 0, n_list = 0;
-                block_prefix32(s_warp, lane, warp, before, n_list);
-                if (listed) s_list[before + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)e;
+                uint32_t before_hi = 0, total_hi = 0, before_lo = 0, total_lo = 0;
+                block_prefix32(s_warp, lane, warp, before_hi, total_hi);
+                block_prefix32(s_warp2, lane, warp, before_lo, total_lo);
+                const uint32_t n3 = total_hi & 0xffffu, n2 = total_hi >> 16, n1 = total_lo & 0xffffu, n0 = total_lo >> 16;
+                const uint32_t n_list = n3 + n2 + n1 + n0;
+                if (listed) {
+                    const unsigned lt = (1u << lane) - 1u;
+                    uint32_t slot;
+                    if (cls == 3) slot = (before_hi & 0xffffu) + __popc(bal[3] & lt);
+                    else if (cls == 2) slot = n3 + (before_hi >> 16) + __popc(bal[2] & lt);
+                    else if (cls == 1) slot = n3 + n2 + (before_lo & 0xffffu) + __popc(bal[1] & lt);
+                    else slot = n3 + n2 + n1 + (before_lo >> 16) + __popc(bal[0] & lt);
+                    s_list[slot] = (uint32_t)e;
+                }
                 __syncthreads();
                 if (tid == 0 && n_list) atomicAdd(&hist[kHistStat], n_list);
                 if (stamper) B200_STAMP(gst, 17);
