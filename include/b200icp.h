@@ -105,7 +105,10 @@ typedef struct b200icp_config {
                              bit 3 (8)   loop kernel: general three-barrier quantile with global radix passes
                              bit 4 (16)  loop kernel: no predicted quantile window (two barriers per iteration)
                              bit 5 (32)  loop kernel: no match-cache verification (every query searched every iteration)
-                             bit 6 (64)  loop kernel: no histogram-derived window (with bit 4: three barriers)      */
+                             bit 6 (64)  loop kernel: no histogram-derived window (with bit 4: three barriers)
+                             bit 7 (128) loop kernel: work list in plain entry order (no cost classes)
+                             bit 8 (256) cold k = 1 search: shell-walk kernel even when maxDist is small
+                             bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3) */
     int32_t reserved[5];
 } b200icp_config;
 

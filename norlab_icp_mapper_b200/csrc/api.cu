@@ -583,10 +583,15 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     const bool do_sort = ctx->cfg.sort_reading != 0 && nq > 1024;
     if (do_sort) {
         CK(ensure_scratch(ctx->map, nq));
-        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s));
         const GridView& v = ctx->map.view;
-        CK(sort_pairs(ctx->map, ctx->map.keys_in, ctx->map.keys_out, ctx->map.vals_in, ctx->map.vals_out, nq,
-                      bits_for((uint64_t)v.nx * v.ny * v.nz), s));
+        // sort key: blocks of 8 x 8 x 4 cells (shift 3) -- half the radix passes of the full cell id and the loop is no
+        // slower for it; nn_variant bits 12..14 = shift + 1 override it (1 = the full cell id)
+        const int cs_bits = (ctx->cfg.nn_variant >> 12) & 7;
+        const int cs = cs_bits ? cs_bits - 1 : 3;
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s, cs));
+        const uint64_t n_keys = cs ? (uint64_t)(((v.nx - 1) >> cs) + 1) * (((v.ny - 1) >> cs) + 1) * (((v.nz - 1) >> std::max(cs - 1, 0)) + 1)
+                                   : (uint64_t)v.nx * v.ny * v.nz;
+        CK(sort_pairs(ctx->map, ctx->map.keys_in, ctx->map.keys_out, ctx->map.vals_in, ctx->map.vals_out, nq, bits_for(n_keys), s));
         CK(launch_gather_reading(b.reading_tmp, ctx->map.vals_out, b.reading, nq, s));
         launches += 4;
     } else {

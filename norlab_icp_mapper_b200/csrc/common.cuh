@@ -263,7 +263,7 @@ cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int 
 
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
                                 float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,
-                                uint32_t* d_vals, int64_t nq, cudaStream_t s);
+                                uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift = 0);
 // dim x N column-major normals -> float4, rotated by the rotation block of Tpre16 (descriptors named `normals` rotate with the cloud)
 cudaError_t launch_prep_normals(const float* d_in, int dim, const float* Tpre16 /*host*/, float4* d_out, int64_t nq, cudaStream_t s);
 cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,

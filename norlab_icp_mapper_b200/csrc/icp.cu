@@ -23,7 +23,7 @@ namespace {
 // ---- reading preparation: (dim+1) x N upload -> float4 in the refMean frame ---------------------
 __global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restrict__ in, int rows, int dim, Mat4 Tpre,
                                                            float4* __restrict__ out, GridView g, uint32_t* __restrict__ keys,
-                                                           uint32_t* __restrict__ vals, long long nq) {
+                                                           uint32_t* __restrict__ vals, long long nq, int coarse_shift) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nq) return;
     float4 r;
@@ -38,7 +38,14 @@ __global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restri
         const int cx = min((int)floorf(fminf(fmaxf((p.x - g.ox) * g.inv_h, 0.f), lim)), g.nx - 1);
         const int cy = min((int)floorf(fminf(fmaxf((p.y - g.oy) * g.inv_h, 0.f), lim)), g.ny - 1);
         const int cz = min((int)floorf(fminf(fmaxf((p.z - g.oz) * g.inv_h, 0.f), lim)), g.nz - 1);
-        keys[i] = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+        if (coarse_shift > 0) {
+            // locality is all the sort is for: blocks of 2^s x 2^s x 2^(s-1) cells need half the radix passes of the full cell id
+            const int sz = max(coarse_shift - 1, 0);
+            const uint32_t nxb = (uint32_t)((g.nx - 1) >> coarse_shift) + 1u, nyb = (uint32_t)((g.ny - 1) >> coarse_shift) + 1u;
+            keys[i] = ((uint32_t)(cz >> sz) * nyb + (uint32_t)(cy >> coarse_shift)) * nxb + (uint32_t)(cx >> coarse_shift);
+        } else {
+            keys[i] = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+        }
         vals[i] = (uint32_t)i;
     }
 }
@@ -325,14 +332,14 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
 
 // ---- host launchers -------------------------------------------------------------------------------
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16, float4* d_out,
-                                const GridView* g_for_keys, uint32_t* d_keys, uint32_t* d_vals, int64_t nq, cudaStream_t s) {
+                                const GridView* g_for_keys, uint32_t* d_keys, uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift) {
     if (nq <= 0) return cudaSuccess;
     Mat4 T;
     memcpy(T.m, Tpre16, sizeof(T.m));
     GridView g{};
     if (g_for_keys) g = *g_for_keys;
     prep_reading_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, rows, dim, T, d_out, g, g_for_keys ? d_keys : nullptr,
-                                                                      d_vals, (long long)nq);
+                                                                      d_vals, (long long)nq, coarse_shift);
     return cudaGetLastError();
 }
 

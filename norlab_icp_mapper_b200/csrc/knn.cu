@@ -129,6 +129,50 @@ __global__ void __launch_bounds__(256) nn1_warm_kernel(GridView g, const float4*
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) B200_STAMP(const_cast<IcpState*>(state), 17);
 }
 
+// Cold k = 1 search with a finite maxDist (iteration 0 of a registration): the bounded ball search of the loop kernel with
+// tau0 = maxDist^2 -- the 2 x 2 nearest cell rows first, balanced 4-lane scan, then whatever the tightened ball still touches.
+// Same exact result and tie rule as knn_kernel<8, Acc1>; about half its time at maxDist ~ 2-3 cell edges.
+__global__ void __launch_bounds__(256) nn1_cold_kernel(GridView g, const float4* __restrict__ queries, const int* __restrict__ d_nq,
+                                                       const IcpState* __restrict__ state, float max_r2, int32_t* __restrict__ out_ids,
+                                                       float* __restrict__ out_d2, int want_original_ids) {
+    if (state && state->done) return;
+    const int nq = *d_nq;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane & 3;
+    const unsigned gmask = group_mask<4>(lane);
+    const long long qi = (long long)blockIdx.x * 64 + threadIdx.x / 4;
+    if (qi >= nq) return;  // whole group leaves together
+    const float4 q4 = __ldg(queries + qi);
+    float qx = q4.x, qy = q4.y, qz = q4.z;
+    if (state) {
+        const float* T = state->T;
+        qx = __fadd_rn(__fmaf_rn(T[8], q4.z, __fmaf_rn(T[4], q4.y, __fmul_rn(T[0], q4.x))), T[12]);
+        qy = __fadd_rn(__fmaf_rn(T[9], q4.z, __fmaf_rn(T[5], q4.y, __fmul_rn(T[1], q4.x))), T[13]);
+        qz = __fadd_rn(__fmaf_rn(T[10], q4.z, __fmaf_rn(T[6], q4.y, __fmul_rn(T[2], q4.x))), T[14]);
+    }
+    float bd = CUDART_INF_F, sd = CUDART_INF_F;
+    int bp = -1;
+    const bool finite_q = (fabsf(qx) < 3.0e38f) && (fabsf(qy) < 3.0e38f) && (fabsf(qz) < 3.0e38f);
+    if (finite_q) search_ball4(g, qx, qy, qz, max_r2, 0.f, bd, bp, sd, lig, gmask);
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(gmask, bd, o);
+        const int op = __shfl_xor_sync(gmask, bp, o);
+        if (od < bd || (od == bd && (unsigned)op < (unsigned)bp)) {
+            bd = od;
+            bp = op;
+        }
+    }
+    if (!(bd <= max_r2)) {
+        bd = CUDART_INF_F;
+        bp = -1;
+    }
+    if (lig == 0) {
+        out_ids[qi] = (want_original_ids && bp >= 0) ? __float_as_int(__ldg(g.pts + bp).w) : bp;
+        out_d2[qi] = bd;
+    }
+}
+
 template <int G>
 cudaError_t launch_warm_one(const GridView& g, const float4* reading, int cap, const IcpState* st, float max_r2,
                             int32_t* pos, float* d2, int variant, cudaStream_t s) {
@@ -155,6 +199,12 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
                        const IcpState* st, int k, float max_r2, int32_t* out_ids, float* out_d2, int want_original_ids,
                        int variant, cudaStream_t s) {
     if (k < 1 || k > 32) return cudaErrorInvalidValue;
+    if (k == 1 && max_r2 < 3.0e38f && !(variant & 256) && sqrtf(max_r2) * g.inv_h <= 4.0f) {  // (bit 8: the shell-walk kernel instead)
+        const int blocks = (nq_capacity + 63) / 64;
+        if (blocks <= 0) return cudaSuccess;
+        nn1_cold_kernel<<<blocks, 256, 0, s>>>(g, d_queries, d_nq, st, max_r2, out_ids, out_d2, want_original_ids);
+        return cudaGetLastError();
+    }
     if (k == 1) return launch_one<8, Acc1<8>>(g, d_queries, d_nq, nq_capacity, st, 1, max_r2, out_ids, out_d2, want_original_ids, variant, s);
     const int warm = (variant & 0x10000) ? 1 : 0;  // set by the ICP loop from iteration 1 on (out_ids = previous matches, positions)
     // lanes per query: at least k (lane j holds the j-th best); few queries get more lanes each -- a query's latency is what

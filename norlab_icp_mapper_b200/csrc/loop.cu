@@ -213,117 +213,6 @@ __device__ __forceinline__ void add_pair(float* acc, float w, const float3& p, c
     acc[NS - 1] += 1.f;
 }
 
-// Ball search of the loop kernel's S phase (4 lanes per query).
-//  phase 1: the 2 x 2 block of (y, z) cell rows nearest to the query, one row per lane -- two cell-table
-//           loads give the row's contiguous run of points -- then a group-wide minimum: this usually
-//           finds the nearest neighbour and tightens the bound a loose previous match gave;
-//  phase 2: whatever other rows the tightened ball still touches (usually none), lane-strided.
-// Unlike search_ball (knn_device.cuh) the covered radius is sqrt(min(best, tau0)) + m instead of
-// sqrt(best): on return every map point within that radius of the query has been looked at, so besides
-// the exact nearest neighbour (bd, bp per lane; ties: lowest position) the lanes also know sd = the
-// smallest squared distance to any OTHER point seen.  bp / bd come in as the previous match (or -1 / inf)
-// in every lane.
-__device__ __forceinline__ void test_point(float qx, float qy, float qz, const float4& p, uint32_t j, float& bd, int& bp, float& sd) {
-    const float dd = dist2_exact(qx, qy, qz, p);
-    if (dd < bd || (dd == bd && j < (uint32_t)bp)) {
-        sd = bd;  // sd >= bd always: the dethroned best becomes the second
-        bd = dd;
-        bp = (int)j;
-    } else {
-        sd = fminf(sd, dd);
-    }
-}
-
-// run of points [s, e) of the cells [xa, xb] of row (y, z) that a ball of squared radius cov2 around the query can touch
-__device__ __forceinline__ void row_run(const GridView& g, float ux, float slack, int y, int z, float gyz2, float cov2, uint32_t& s, uint32_t& e) {
-    const float rx = fminf(sqrtf(fmaxf(cov2 - gyz2, 0.f)) * g.inv_h + slack, 3.0e8f);
-    const int xa = max(0, floor_to_int(fmaxf(ux - rx, -1.f)));
-    const int xb = min(g.nx - 1, floor_to_int(fminf(ux + rx, (float)g.nx)));
-    if (xa > xb) return;
-    const uint32_t* row = g.cell_start + ((size_t)z * g.ny + y) * (size_t)g.nx;
-    s = __ldg(row + xa);
-    e = __ldg(row + xb + 1);
-}
-
-__device__ __forceinline__ float row_gap2(const GridView& g, float uy, float uz, float slack, int y, int z) {
-    float gy = fmaxf(fmaxf((float)y - uy, uy - (float)(y + 1)), 0.f);
-    float gz = fmaxf(fmaxf((float)z - uz, uz - (float)(z + 1)), 0.f);
-    gy = fmaxf(gy - slack, 0.f) * g.h;
-    gz = fmaxf(gz - slack, 0.f) * g.h;
-    return gy * gy + gz * gz;
-}
-
-// The runs [s, e) the four lanes of a group hold (one cell row each, possibly empty), concatenated, are scanned by the
-// four lanes together: balanced, and a lane quartet reads 64 contiguous bytes.  Returns the group-wide best distance.
-__device__ __forceinline__ float scan_runs4(const GridView& g, float qx, float qy, float qz, uint32_t s, uint32_t e, float& bd, int& bp, float& sd,
-                                            int lig, unsigned gmask) {
-    constexpr int G = 4;
-    const uint32_t n = e - s;
-    const uint32_t n0 = __shfl_sync(gmask, n, 0, G), n1 = __shfl_sync(gmask, n, 1, G), n2 = __shfl_sync(gmask, n, 2, G), n3 = __shfl_sync(gmask, n, 3, G);
-    const uint32_t p1 = n0, p2 = p1 + n1, p3 = p2 + n2, N = p3 + n3;
-    const uint32_t o0 = __shfl_sync(gmask, s, 0, G), o1 = __shfl_sync(gmask, s, 1, G) - p1, o2 = __shfl_sync(gmask, s, 2, G) - p2,
-                   o3 = __shfl_sync(gmask, s, 3, G) - p3;
-#pragma unroll 2
-    for (uint32_t k = (uint32_t)lig; k < N; k += G) {
-        const uint32_t j = k + (k >= p2 ? (k >= p3 ? o3 : o2) : (k >= p1 ? o1 : o0));
-        test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
-    }
-    float v = bd;
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
-    return v;
-}
-
-// bd / bp / sd start at inf / -1 / inf in every lane: the previous match only bounds the ball (tau0) and is found
-// again by the scan like any other point.
-__device__ __forceinline__ void search_ball4(const GridView& g, float qx, float qy, float qz, float tau0, float m, float& bd, int& bp,
-                                             float& sd, int lig, unsigned gmask) {
-    constexpr int G = 4;
-    const float lim = 1.0e8f;
-    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
-    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
-    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
-    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
-    // phase 1: own row, the nearer y neighbour, the nearer z neighbour, and the diagonal
-    const int cy = floor_to_int(uy), cz = floor_to_int(uz);
-    const int y1 = (uy - (float)cy >= 0.5f) ? cy + 1 : cy - 1;
-    const int z1 = (uz - (float)cz >= 0.5f) ? cz + 1 : cz - 1;
-    float gb = tau0;  // group-uniform bound on the final best distance
-    {
-        const int y = (lig & 1) ? y1 : cy, z = (lig & 2) ? z1 : cz;
-        uint32_t s = 0, e = 0;
-        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
-            const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
-            const float cov = sqrtf(gb) + m;
-            if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
-        }
-        gb = fminf(scan_runs4(g, qx, qy, qz, s, e, bd, bp, sd, lig, gmask), tau0);
-    }
-    // phase 2: the rest of the (tightened) ball's cover -- usually nothing; four rows at a time, same scan
-    const float rt = fminf((sqrtf(gb) + m) * g.inv_h + slack, 3.0e8f);
-    const int ylo = max(0, floor_to_int(fmaxf(uy - rt, -1.f)));
-    const int yhi = min(g.ny - 1, floor_to_int(fminf(uy + rt, (float)g.ny)));
-    const int zlo = max(0, floor_to_int(fmaxf(uz - rt, -1.f)));
-    const int zhi = min(g.nz - 1, floor_to_int(fminf(uz + rt, (float)g.nz)));
-    const int wy = yhi - ylo + 1, wz = zhi - zlo + 1;
-    if (wy <= 0 || wz <= 0) return;
-    if (ylo >= min(cy, y1) && yhi <= max(cy, y1) && zlo >= min(cz, z1) && zhi <= max(cz, z1)) return;  // inside the 2 x 2 block
-    const int nrows = wy * wz;
-    for (int base = 0; base < nrows; base += G) {  // group-uniform trip count
-        const int r = base + lig;
-        uint32_t s = 0, e = 0;
-        if (r < nrows) {
-            const int y = ylo + r % wy, z = zlo + r / wy;
-            if (!((y == cy || y == y1) && (z == cz || z == z1))) {  // (those were phase 1)
-                const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
-                const float cov = sqrtf(gb) + m;  // covered radius from here on (never below the final one)
-                if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
-            }
-        }
-        gb = fminf(scan_runs4(g, qx, qy, qz, s, e, bd, bp, sd, lig, gmask), tau0);
-    }
-}
-
 template <int MIN>
 __global__ void __launch_bounds__(kLoopThreads, 1)
     icp_loop_kernel(IcpParams prm, GridView g, const float4* __restrict__ nrm, const float4* __restrict__ reading,
