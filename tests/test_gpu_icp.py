@@ -325,6 +325,44 @@ def test_error_behaviour_matches_libpointmatcher(oracle, pair3d):
     g.close()
 
 
+def test_ragged_readings_match_the_oracle(oracle, pair3d):
+    """Edge cases of the reading the loop kernel's match cache has to survive: points with no map neighbour within
+    maxDist (id -1 from iteration 0 on, some of them drifting into range later), NaN / inf coordinates (never matched),
+    readings far smaller than the grid of CTAs.  Poses, iteration counts and kept pairs as the oracle."""
+    from norlab_icp_mapper_b200.icp import ICP
+    rng = np.random.default_rng(17)
+    base = pair3d["reading"]
+    cases = {}
+    r = base.copy()
+    r[::7, :3] += rng.normal(0, 1.0, (len(r[::7]), 3)).astype(np.float32)      # a seventh of the points 1 m off: mostly unmatched
+    r[::31, 2] += 50.0                                                           # hopeless ones
+    cases["unmatched"] = r
+    r = base.copy()
+    r[5, 0] = np.nan
+    r[77, 1] = np.inf
+    r[1234, :3] = np.nan
+    cases["nan"] = r
+    cases["tiny"] = base[:37].copy()
+    cases["one_chunk"] = base[:1000].copy()
+    for name, reading in cases.items():
+        for chain in ((("trimmed", 0.8),), ()):
+            cfg = make_config(dim=3, knn=1, max_dist=0.7, outliers=chain, minimizer="point_to_plane", max_iteration_count=14)
+            o = oracle.OracleICP(cfg)
+            o.set_map(pair3d["map"], pair3d["normals"])
+            rc, T_o, res_o, _, _ = o.register(reading)
+            g = ICP(cfg)
+            g.set_map(pair3d["map"], pair3d["normals"])
+            T_g = g(reading)
+            T_g2 = g(reading)
+            res_g = g.last_result
+            g.close()
+            assert rc == _abi.OK and np.array_equal(T_g, T_g2)
+            er, et = synth.pose_error(T_g, T_o)
+            assert er <= TOL_RAD and et <= TOL_M, (name, chain, er, et)
+            assert res_g.iterations == res_o.iterations
+            assert abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.002 * res_o.pairs_last_iter + 2, (name, chain, res_g.pairs_last_iter, res_o.pairs_last_iter)
+
+
 def test_rigid_transform_bit_exact(oracle):
     from norlab_icp_mapper_b200.icp import ICP, B200ICPError
     rng = np.random.default_rng(2)
