@@ -598,8 +598,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 float v32[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc[i] : 0.f;
-                const float tot = warp_reduce_32slots(v32, lane);
-                if (lane < NS) s_part[warp][lane] += (double)tot;
+                if (e0 + warp * 32 < n_ent) {  // (warp-uniform: warps past the end of the slice have nothing to add)
+                    const float tot = warp_reduce_32slots(v32, lane);
+                    if (lane < NS) s_part[warp][lane] += (double)tot;
+                }
             }
             // ---- publish, ONE barrier, finish redundantly ---------------------------------------------
             if (stamper) B200_STAMP(gst, 28);
@@ -760,7 +762,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     float v32[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc2[i] : 0.f;
-                    const float tot = use_quantile ? warp_reduce_32slots(v32, lane) : 0.f;
+                    // (only the warps that hold candidates have anything to add: warp-uniform skip of the 31-shuffle reduction)
+                    const float tot = (use_quantile && (uint32_t)(warp * 32) < n_cand) ? warp_reduce_32slots(v32, lane) : 0.f;
                     const int slot = lane, part = warp;
                     double v = (double)tot;
 #pragma unroll
@@ -1056,9 +1059,13 @@ cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
         if (ea != cudaSuccess) return ea;
         attr_set = true;
     }
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_loop_kernel<MIN>, kLoopThreads, kLoopDynSmem);
-    if (e != cudaSuccess) return e;
+    static int per_sm = -1;  // (queried once per instantiation: the answer does not change)
+    if (per_sm < 0) {
+        int q = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_loop_kernel<MIN>, kLoopThreads, kLoopDynSmem);
+        if (e != cudaSuccess) return e;
+        per_sm = q;
+    }
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     const int blocks = std::min(n_sms, kLoopMaxBlocks);
     IcpParams prm = p;
