@@ -209,10 +209,8 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
         CK(cudaMalloc((void**)&b.reading_tmp, (size_t)cap * sizeof(float4)));
         CK(cudaMalloc((void**)&b.match_pos, (size_t)cap * K * sizeof(int32_t)));
         CK(cudaMalloc((void**)&b.match_d2, (size_t)cap * K * sizeof(float)));
-        if (K == 1) {
-            CK(cudaMalloc((void**)&b.spill_pp, (size_t)cap * sizeof(float4)));
-            CK(cudaMalloc((void**)&b.spill_nv, (size_t)cap * sizeof(float4)));
-        }
+        CK(cudaMalloc((void**)&b.spill_pp, (size_t)cap * K * sizeof(float4)));  // one row per (reading point, neighbour) pair
+        CK(cudaMalloc((void**)&b.spill_nv, (size_t)cap * K * sizeof(float4)));
         b.cap_nq = cap;
     }
     return B200ICP_OK;
@@ -627,16 +625,16 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     } restore_trace{b, trace_keep};
     IcpState* out_state = reinterpret_cast<IcpState*>(ctx->h_pinned + kStateBytes);
     int issued = 0, nn_timed = 0;
-    // k = 1: cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
+    // Cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
     // (Per-kernel profiling and nn_variant bit 2 select the kernel-per-step path below instead.)
     const bool var_trimmed = p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST;
-    const bool persistent = p.knn == 1 && !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed;
+    const bool persistent = !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed;
     if (persistent) {
-        CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, 1, p.max_r2, b.match_pos, b.match_d2,
-                      /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+        CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
+                      /*want_original_ids=*/0, ctx->cfg.nn_variant & 0xffff, s));
         CK(cudaMemsetAsync(ctx->d_bar_counter, 0, sizeof(unsigned), s));
         CK(cudaEventRecord(ctx->ev_loop0, s));
-        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, ctx->win3, ctx->margin3, s));
+        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, ctx->win3, ctx->margin3, nq, s));
         CK(cudaEventRecord(ctx->ev_loop1, s));
         launches += 2;
         CK(cudaMemcpyAsync(out_state, b.state, kStateBytes, cudaMemcpyDeviceToHost, s));

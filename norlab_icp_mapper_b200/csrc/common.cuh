@@ -274,7 +274,7 @@ cudaError_t icp_device_setup();
 size_t icp_loop_workspace_bytes();
 // margin3 = {gain, min [m], max [cell edges]}: extra search radius = clamp(gain * the query's last motion, min, max * h)
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                            int variant, const float* win3, const float* margin3, cudaStream_t s);
+                            int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
                                   cudaStream_t s, int* launches, cudaEvent_t ev_mid, VarTrimScratch* var_scratch);

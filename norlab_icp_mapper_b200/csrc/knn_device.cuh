@@ -77,7 +77,9 @@ struct Acc1 {
 };
 
 // ---- k > 1: one sorted list per group, lane j holds the j-th best ------------------------------
-template <int G>
+// TRACK (loop.cu): the search also covers `margin` beyond the k-th distance and remembers, per lane, the smallest
+// distance among the points it tested and did not keep -- together a lower bound for every point NOT in the result.
+template <int G, bool TRACK = false>
 struct AccK {
     static constexpr bool kPerLaneOutput = true;
     float d;      // my entry
@@ -85,12 +87,16 @@ struct AccK {
     float kth;    // group-uniform: current k-th best (inf until k found), never above `bound`
     float bound;  // group-uniform: a proven upper bound of the final k-th distance (warm start) or inf
     int k;
-    __device__ __forceinline__ void init(int k_, float bound_) {
+    float margin;  // TRACK: extra radius covered around the ball of the k-th distance
+    float sd;      // TRACK, per lane: smallest dist2 tested and refused, or pushed out of the list
+    __device__ __forceinline__ void init(int k_, float bound_, float margin_ = 0.f) {
         d = CUDART_INF_F;
         pos = -1;
         bound = bound_;
         kth = bound_;
         k = k_;
+        margin = margin_;
+        sd = CUDART_INF_F;
     }
     __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
                                          int lig, unsigned gmask, float max_r2) {
@@ -102,11 +108,13 @@ struct AccK {
                 cd = dist2_exact(qx, qy, qz, p);
             }
             bool pass = (cd < kth) && (cd <= max_r2);
+            if (TRACK && !pass) sd = fminf(sd, cd);
             unsigned m = __ballot_sync(gmask, pass) & gmask;
             while (m) {
                 const int src = __ffs(m) - 1;  // absolute lane
                 const float nd = __shfl_sync(gmask, cd, src);
                 const int np = (int)(j0 + (uint32_t)(src & (G - 1)));
+                if (TRACK) sd = fminf(sd, __shfl_sync(gmask, d, k - 1, G));  // the entry this insertion pushes out (inf: list not full)
                 // rank of the newcomer = entries <= nd (stable: goes after equal distances)
                 const unsigned le = __ballot_sync(gmask, d <= nd) & gmask;
                 const int r = __popc(le);
@@ -125,12 +133,20 @@ struct AccK {
                 }
                 kth = fminf(bound, __shfl_sync(gmask, d, k - 1, G));
                 m &= m - 1;
-                pass = pass && (cd < kth);
+                const bool still = pass && (cd < kth);
+                if (TRACK && pass && !still && lig != (src & (G - 1))) sd = fminf(sd, cd);  // overtaken before its turn came
+                pass = still;
                 m &= __ballot_sync(gmask, pass);
             }
         }
     }
-    __device__ __forceinline__ float tau(unsigned, float max_r2) const { return fminf(kth, max_r2); }
+    __device__ __forceinline__ float tau(unsigned, float max_r2) const {
+        if (TRACK) {
+            const float r = sqrtf(fminf(kth, max_r2)) + margin;
+            return r * r;
+        }
+        return fminf(kth, max_r2);
+    }
     __device__ __forceinline__ void finish(unsigned, int, int, float, float& out_d, int& out_pos) {
         out_d = d;
         out_pos = pos;

@@ -213,7 +213,7 @@ __device__ __forceinline__ void add_pair(float* acc, float w, const float3& p, c
     acc[NS - 1] += 1.f;
 }
 
-template <int MIN>
+template <int MIN, int GK /* lanes per query of the k > 1 search (8, 16, 32); 4 stands for k = 1 */>
 __global__ void __launch_bounds__(kLoopThreads, 1)
     icp_loop_kernel(IcpParams prm, GridView g, const float4* __restrict__ nrm, const float4* __restrict__ reading,
                     int32_t* __restrict__ mpos, float* __restrict__ md2, IcpState* __restrict__ gst, uint32_t* __restrict__ hist,
@@ -252,22 +252,26 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
-    constexpr int kPerSweep = kChunk;  // the general path walks this CTA's chunks
-    // entries of this CTA: entry e <-> reading point qi_of(e); contiguous because only the globally last chunk is partial
-    int n_ent = 0;
+    // This CTA's slice: n_ql reading points (chunks of kChunk consecutive points, dealt round-robin: only the globally last
+    // chunk is partial, so local query ql <-> reading point qi_of(ql) is contiguous) and K entries each -- one per neighbour.
+    // Entry e = ql * K + j <-> row `pair_of(e)` of the match arrays (ids[i * knn + j] layout).  K = 1: entries are the points.
+    const int K = prm.knn;
+    int n_ql = 0;
     {
         const long long chunks_total = ((long long)nq + kChunk - 1) / kChunk;
         if ((long long)blockIdx.x < chunks_total) {
             const long long mine = (chunks_total - 1 - blockIdx.x) / gridDim.x + 1;
-            n_ent = (int)(mine * kChunk);
-            if ((long long)blockIdx.x + (mine - 1) * gridDim.x == chunks_total - 1) n_ent -= (int)(chunks_total * kChunk - nq);
+            n_ql = (int)(mine * kChunk);
+            if ((long long)blockIdx.x + (mine - 1) * gridDim.x == chunks_total - 1) n_ql -= (int)(chunks_total * kChunk - nq);
         }
     }
-    auto qi_of = [&](int e) -> long long { return ((long long)(e / kChunk) * gridDim.x + blockIdx.x) * kChunk + (e % kChunk); };
+    const int n_ent = n_ql * K;
+    auto qi_of = [&](int ql) -> long long { return ((long long)(ql / kChunk) * gridDim.x + blockIdx.x) * kChunk + (ql % kChunk); };
+    auto pair_of = [&](int e) -> long long { return K == 1 ? qi_of(e) : qi_of(e / K) * K + (e % K); };
     // match cache <- the cold search's matches (bound L = 0: nothing proven yet)
     for (int e = tid; e < n_ent; e += kLoopThreads) {
-        const long long qi = qi_of(e);
-        const int pos = mpos[qi];
+        const long long pi = pair_of(e);
+        const int pos = mpos[pi];
         float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), nn = pt;
         if (pos >= 0) {
             pt = __ldg(g.pts + pos);
@@ -276,15 +280,15 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         pt.w = __int_as_float(pos);
         nn.w = 0.f;
         if (e < kCacheCap) {
-            s_r4[e] = __ldg(reading + qi);
             s_pp[e] = pt;
             s_nv[e] = nn;
-            s_d2[e] = md2[qi];
+            s_d2[e] = md2[pi];
         } else {
-            sp_pp[qi] = pt;
-            sp_nv[qi] = nn;
+            sp_pp[pi] = pt;
+            sp_nv[pi] = nn;
         }
     }
+    for (int ql = tid; ql < n_ql && ql < kCacheCap; ql += kLoopThreads) s_r4[ql] = __ldg(reading + qi_of(ql));
     if (tid < 16) s_Tprev[tid] = st.T[tid];
     __syncthreads();
 
@@ -301,6 +305,129 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         // ---- V / S over this CTA's entries, 1024 at a time (one block unless nq > 148 * 1024) ------------------------
         const bool verify = !(variant_flags & 32);
         unsigned long long t_search = 0;  // CTA 0, thread 0: time spent in V + S
+        if (GK > 4) {
+            // k > 1, by blocks of 1024 reading points.  V (thread per point): the cached k matches are still THE k nearest
+            // when the farthest of them is closer to the moved query than the bound L (kept in the first entry's s_nv.w)
+            // allows any other map point to be.  S (GK lanes per listed point): shell search with one sorted list per group
+            // (AccK, knn_device.cuh), pruned from the start by the largest distance to the cached matches -- k distinct
+            // real map points -- and widened by the margin so that the new bound L leaves room for the next motions.
+            const int ligk = lane & (GK - 1);
+            const unsigned gmaskk = group_mask<GK>(lane);
+            for (int q0 = 0; searched && q0 < n_ql; q0 += kLoopThreads) {
+                unsigned long long t_s0 = 0;
+                if (blockIdx.x == 0 && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_s0));
+                const int ql = q0 + tid;
+                bool listed = false;
+                if (ql < n_ql) {
+                    const long long qq = qi_of(ql);
+                    const float4 r4 = ql < kCacheCap ? s_r4[ql] : __ldg(reading + qq);
+                    const float3 qn = apply_T(st.T, r4), qo = apply_T(s_Tprev, r4);
+                    const float ddx = qn.x - qo.x, ddy = qn.y - qo.y, ddz = qn.z - qo.z;
+                    const float delta = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+                    const int e0 = ql * K;
+                    float maxd = 0.f;
+                    int cnt = 0;
+                    bool inside = true;
+                    for (int j = 0; j < K; ++j) {
+                        const int e = e0 + j;
+                        const bool cs = e < kCacheCap;
+                        const float4 pp = cs ? s_pp[e] : sp_pp[qq * K + j];
+                        const int pos = __float_as_int(pp.w);
+                        float d2n = CUDART_INF_F;
+                        if (pos >= 0) {
+                            d2n = dist2_exact(qn.x, qn.y, qn.z, pp);
+                            inside = inside && (d2n <= prm.max_r2);  // (false for a NaN query too)
+                            maxd = fmaxf(maxd, d2n);
+                            cnt += 1;
+                        }
+                        if (cs) s_d2[e] = d2n;
+                        else md2[qq * K + j] = d2n;
+                    }
+                    float* pL = e0 < kCacheCap ? &s_nv[e0].w : &sp_nv[qq * K].w;
+                    const float L = *pL;
+                    // fewer than k matches: every other map point was beyond maxDist and has to stay there
+                    const float need = cnt == K ? sqrtf(maxd) : sqrtf(prm.max_r2);
+                    const float slack = 2e-6f * (need + delta + L);
+                    const float Lnew = L - delta - slack;
+                    if (verify && inside && need + slack < Lnew) *pL = Lnew;
+                    else listed = true;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, listed);
+                if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
+                if (tid == 0) s_nlist = 0u;  // cursor of the S phase
+                __syncthreads();
+                uint32_t before = 0, n_list = 0;
+                block_prefix32(s_warp, lane, warp, before, n_list);
+                if (listed) s_list[before + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)ql;
+                __syncthreads();
+                if (tid == 0 && n_list) atomicAdd(&hist[kHistStat], n_list);
+                while (true) {  // batches of 32 / GK consecutive list entries, handed to whole warps dynamically
+                    uint32_t i0 = 0;
+                    if (lane == 0) i0 = atomicAdd(&s_nlist, 32u / GK);
+                    i0 = __shfl_sync(0xffffffffu, i0, 0);
+                    if (i0 >= n_list) break;  // warp-uniform
+                    const uint32_t i = i0 + (uint32_t)(lane / GK);
+                    if (i < n_list) {
+                        const int qs = (int)s_list[i];
+                        const long long qq = qi_of(qs);
+                        const float4 r4 = qs < kCacheCap ? s_r4[qs] : __ldg(reading + qq);
+                        const float3 qn = apply_T(st.T, r4), qo = apply_T(s_Tprev, r4);
+                        const float ddx = qn.x - qo.x, ddy = qn.y - qo.y, ddz = qn.z - qo.z;
+                        const float delta = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+                        const float want = margin_gain * delta;
+                        const float m = want <= margin_max ? fmaxf(want, margin_min) : 0.f;
+                        const int e = qs * K + ligk;
+                        const bool mine = ligk < K, cs = e < kCacheCap;
+                        const long long pi = qq * K + ligk;
+                        float dj = 0.f;
+                        if (mine) {
+                            const float4 pp = cs ? s_pp[e] : sp_pp[pi];
+                            dj = __float_as_int(pp.w) >= 0 ? dist2_exact(qn.x, qn.y, qn.z, pp) : CUDART_INF_F;
+                        }
+#pragma unroll
+                        for (int o = GK / 2; o > 0; o >>= 1) dj = fmaxf(dj, __shfl_xor_sync(gmaskk, dj, o));
+                        float bound = CUDART_INF_F;
+                        if (dj < CUDART_INF_F) bound = __uint_as_float(__float_as_uint(dj) + 1u);  // next float up: ties with the bound stay accepted
+                        AccK<GK, true> acc;
+                        acc.init(K, bound, m);
+                        search_shells<GK, AccK<GK, true>>(g, acc, qn.x, qn.y, qn.z, prm.max_r2, 0, ligk, gmaskk);
+                        float gsd = acc.sd;
+#pragma unroll
+                        for (int o = GK / 2; o > 0; o >>= 1) gsd = fminf(gsd, __shfl_xor_sync(gmaskk, gsd, o));
+                        if (mine) {
+                            const float od = acc.d;
+                            const int op = acc.pos;
+                            float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), nn = pt;
+                            if (op >= 0) {
+                                pt = __ldg(g.pts + op);
+                                if (MIN == 0 || sn_active) nn = __ldg(nrm + op);
+                            }
+                            pt.w = __int_as_float(op);
+                            // every point within sqrt(min(k-th, maxDist^2)) + m was tested: the others are at least L away
+                            float L = fminf(sqrtf(gsd), sqrtf(fminf(acc.kth, prm.max_r2)) + m);
+                            L = fminf(L - 2e-6f * L, 1.0e18f);
+                            nn.w = L;  // (read from the first entry only)
+                            if (cs) {
+                                s_pp[e] = pt;
+                                s_nv[e] = nn;
+                                s_d2[e] = od;
+                            } else {
+                                sp_pp[pi] = pt;
+                                sp_nv[pi] = nn;
+                                md2[pi] = od;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();  // the search results of this block are in the cache (and s_list is free again)
+                if (blockIdx.x == 0 && tid == 0) {
+                    unsigned long long t1;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    t_search += t1 - t_s0;
+                }
+            }
+        } else
         for (int e0 = 0; e0 < n_ent; e0 += kLoopThreads) {
             const int e = e0 + tid;
             const bool have = e < n_ent;
@@ -487,9 +614,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     __syncthreads();
                     for (int e = tid; e < n_ent; e += kLoopThreads) {
                         const bool cached = e < kCacheCap;
-                        const long long qi = qi_of(e);
-                        const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[qi].w);
-                        const float d = cached ? s_d2[e] : md2[qi];
+                        const long long pi = pair_of(e);
+                        const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[pi].w);
+                        const float d = cached ? s_d2[e] : md2[pi];
                         if (pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
                     }
                     __syncthreads();
@@ -541,16 +668,18 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 const int e = e0 + tid;
                 const bool have = e < n_ent;
                 const bool cached = e < kCacheCap;
-                const long long qi = have ? qi_of(e) : 0;
+                const int ql = (GK > 4) ? e / K : e;  // the entry's reading point (k = 1: the entry itself)
+                const long long qi = have ? qi_of(ql) : 0;
+                const long long pi = (GK > 4) ? qi * K + (e - ql * K) : qi;
                 float acc[NS];
 #pragma unroll
                 for (int i = 0; i < NS; ++i) acc[i] = 0.f;
                 bool is_cand = false;
                 float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
                 if (have) {
-                    const float4 pp = cached ? s_pp[e] : sp_pp[qi];
-                    const float4 nv = cached ? s_nv[e] : sp_nv[qi];
-                    const float d = cached ? s_d2[e] : md2[qi];
+                    const float4 pp = cached ? s_pp[e] : sp_pp[pi];
+                    const float4 nv = cached ? s_nv[e] : sp_nv[pi];
+                    const float d = cached ? s_d2[e] : md2[pi];
                     const int pos = __float_as_int(pp.w);
                     if (pos >= 0 && d < CUDART_INF_F) {
                         const uint32_t bits = __float_as_uint(d);
@@ -562,7 +691,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             float3 p = make_float3(CUDART_NAN_F, 0.f, 0.f);
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (wo != 0.f) {
-                                p = apply_T(st.T, cached ? s_r4[e] : __ldg(reading + qi));
+                                p = apply_T(st.T, ql < kCacheCap ? s_r4[ql] : __ldg(reading + qi));
                                 if (MIN == 0)
                                     v = make_float4(nv.x, nv.y, nv.z, (p.x - pp.x) * nv.x + (p.y - pp.y) * nv.y + (p.z - pp.z) * nv.z);
                                 else
@@ -789,39 +918,25 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 for (int i = tid; i < kSel0Bins; i += kLoopThreads) h1[i] = 0u;
         }
         if (fatal) break;
-        bool hist_ready = false;
         if (!fast_done) {
             // general path (window overflow, or forced by nn_variant): it walks mpos / md2 in global memory
             for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
             __syncthreads();
             for (int e = tid; e < n_ent; e += kLoopThreads) {
-                const long long qi = qi_of(e);
+                const long long pi = pair_of(e);
                 const bool cached = e < kCacheCap;
-                const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[qi].w);
-                const float d = cached ? s_d2[e] : md2[qi];
-                mpos[qi] = pos;
-                md2[qi] = d;
+                const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[pi].w);
+                const float d = cached ? s_d2[e] : md2[pi];
+                mpos[pi] = pos;
+                md2[pi] = d;
                 if (use_quantile && pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
             }
             __syncthreads();
-            hist_ready = true;
         }
         // ---- exact quantile of the finite distances (LPM Matches::getDistsQuantile) -------------------
         bool fallback_used = false;
         if (use_quantile && !fast_done) {
-            // level 0: histogram of bits [30:19] over this CTA's slice (already done while searching)
-            if (!hist_ready) {
-                for (long long sweep = tid / kPerSweep;; sweep += kLoopThreads / kPerSweep) {
-                    const long long base = (sweep * gridDim.x + blockIdx.x) * kPerSweep;
-                    if (base >= nq) break;
-                    const long long qi = base + (tid % kPerSweep);
-                    if (qi < nq) {
-                        const uint32_t bits = __float_as_uint(md2[qi]);
-                        if (bits < 0x7f800000u) atomicAdd(&sh[bits >> kSel0Shift], 1u);
-                    }
-                }
-                __syncthreads();
-            }
+            // level 0: histogram of bits [30:19] over this CTA's slice: built by the pre-pass above
             for (int i = tid; i < kSel0Bins; i += kLoopThreads)
                 if (sh[i]) atomicAdd(&hist[i], sh[i]);
             if (tid == 0) {
@@ -853,14 +968,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             if (c1 <= (uint32_t)kSelListCap && !(variant_flags & 8)) {
                 // candidate list: this CTA's distances that fall in bucket b1 -> staged in shared memory,
                 // one global atomic per CTA reserves their place in the list
-                for (long long sweep = tid / kPerSweep;; sweep += kLoopThreads / kPerSweep) {
-                    const long long base = (sweep * gridDim.x + blockIdx.x) * kPerSweep;
-                    if (base >= nq) break;
-                    const long long qi = base + (tid % kPerSweep);
-                    if (qi < nq) {
-                        const uint32_t bits = __float_as_uint(md2[qi]);
-                        if (bits < 0x7f800000u && (bits >> kSel0Shift) == b1) sh[atomicAdd(&s_stage, 1u)] = bits;
-                    }
+                for (int e = tid; e < n_ent; e += kLoopThreads) {
+                    const uint32_t bits = __float_as_uint(md2[pair_of(e)]);
+                    if (bits < 0x7f800000u && (bits >> kSel0Shift) == b1) sh[atomicAdd(&s_stage, 1u)] = bits;
                 }
                 __syncthreads();
                 if (tid == 0) s_base = s_stage ? atomicAdd(&hist[kHistCount], s_stage) : 0u;
@@ -913,18 +1023,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         s_res = 0;
                     }
                     __syncthreads();
-                    for (long long sweep = tid / kPerSweep;; sweep += kLoopThreads / kPerSweep) {
-                        const long long base = (sweep * gridDim.x + blockIdx.x) * kPerSweep;
-                        if (base >= nq) break;
-                        const long long qi = base + (tid % kPerSweep);
-                        if (qi < nq) {
-                            const uint32_t bits = __float_as_uint(md2[qi]);
-                            if (bits >= 0x7f800000u) continue;
-                            if (pass == 1) {
-                                if ((bits >> kSel0Shift) == pre) atomicAdd(&sh[(bits >> 8) & 2047u], 1u);
-                            } else {
-                                if ((bits >> 8) == pre) atomicAdd(&sh[bits & 255u], 1u);
-                            }
+                    for (int e = tid; e < n_ent; e += kLoopThreads) {
+                        const uint32_t bits = __float_as_uint(md2[pair_of(e)]);
+                        if (bits >= 0x7f800000u) continue;
+                        if (pass == 1) {
+                            if ((bits >> kSel0Shift) == pre) atomicAdd(&sh[(bits >> 8) & 2047u], 1u);
+                        } else {
+                            if ((bits >> 8) == pre) atomicAdd(&sh[bits & 255u], 1u);
                         }
                     }
                     __syncthreads();
@@ -955,11 +1060,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             float T[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) T[i] = st.T[i];
-            for (long long sweep = tid / kPerSweep;; sweep += kLoopThreads / kPerSweep) {
-                const long long base = (sweep * gridDim.x + blockIdx.x) * kPerSweep;
-                if (base >= nq) break;
-                const long long qi = base + (tid % kPerSweep);
-                if (qi < nq) accumulate_entry<MIN>(acc, prm, T, g, nrm, reading, qi, 1, mpos[qi], md2[qi], qlimit);
+            for (int e = tid; e < n_ent; e += kLoopThreads) {
+                const long long pi = pair_of(e);
+                accumulate_entry<MIN>(acc, prm, T, g, nrm, reading, pi, K, mpos[pi], md2[pi], qlimit);
             }
         }
         {
@@ -1050,19 +1153,19 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     }
 }
 
-template <int MIN>
+template <int MIN, int GK>
 cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
                           int variant_flags, const float* win3, const float* margin3, cudaStream_t s) {
     static bool attr_set = false;  // per process and instantiation; harmless if repeated
     if (!attr_set) {
-        cudaError_t ea = cudaFuncSetAttribute(icp_loop_kernel<MIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoopDynSmem);
+        cudaError_t ea = cudaFuncSetAttribute(icp_loop_kernel<MIN, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoopDynSmem);
         if (ea != cudaSuccess) return ea;
         attr_set = true;
     }
     static int per_sm = -1;  // (queried once per instantiation: the answer does not change)
     if (per_sm < 0) {
         int q = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_loop_kernel<MIN>, kLoopThreads, kLoopDynSmem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_loop_kernel<MIN, GK>, kLoopThreads, kLoopDynSmem);
         if (e != cudaSuccess) return e;
         per_sm = q;
     }
@@ -1085,19 +1188,31 @@ cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
     float margin_gain = margin3[0], margin_min = margin3[1], margin_max = margin3[2] * g.view.h;
     void* args[] = {&prm, &view, &nrm, &reading, &mpos, &md2, &st, &hist, &partials, &bar_counter, &trace, &max_iters, &variant_flags,
                     &fastws, &win_gain, &win_floor, &win_max, &sp_pp, &sp_nv, &margin_gain, &margin_min, &margin_max};
-    return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN>, dim3(blocks), dim3(kLoopThreads), args, kLoopDynSmem, s);
+    return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN, GK>, dim3(blocks), dim3(kLoopThreads), args, kLoopDynSmem, s);
 }
 
 }  // namespace
 
 size_t icp_loop_workspace_bytes() { return kFastBytes; }
 
+template <int GK>
+cudaError_t launch_loop_g(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
+                          int variant, const float* win3, const float* margin3, cudaStream_t s) {
+    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE) return launch_loop_t<0, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    if (p.minimizer == B200ICP_MIN_POINT_TO_POINT) return launch_loop_t<1, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    return launch_loop_t<2, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+}
+
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                            int variant, const float* win3, const float* margin3, cudaStream_t s) {
-    if (p.knn != 1 || !b.fastws || !b.spill_pp || !b.spill_nv) return cudaErrorInvalidValue;
-    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE) return launch_loop_t<0>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
-    if (p.minimizer == B200ICP_MIN_POINT_TO_POINT) return launch_loop_t<1>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
-    return launch_loop_t<2>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+                            int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s) {
+    if (p.knn < 1 || p.knn > 32 || !b.fastws || !b.spill_pp || !b.spill_nv) return cudaErrorInvalidValue;
+    if (p.knn == 1) return launch_loop_g<4>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    // k > 1: lanes per query >= k (lane j holds the j-th best); a reading too small to fill the SMs gets more lanes per query
+    int lanes = p.knn <= 8 ? 8 : (p.knn <= 16 ? 16 : 32);
+    while (lanes < 32 && nq * lanes <= (int64_t)n_sms * kLoopThreads) lanes *= 2;
+    if (lanes == 8) return launch_loop_g<8>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    if (lanes == 16) return launch_loop_g<16>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    return launch_loop_g<32>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
 }
 
 }  // namespace b200
