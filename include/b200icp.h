@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200ICP_ABI_VERSION 2
+#define B200ICP_ABI_VERSION 3
 
 typedef enum b200icp_status {
     B200ICP_OK = 0,
@@ -54,11 +54,38 @@ typedef enum b200icp_outlier_kind {
     B200ICP_OUTLIER_VAR_TRIMMED_DIST = 5, /* VarTrimmedDistOutlierFilter{minRatio = param, maxRatio = param2, lambda = param3}:
                                             ratio = argmin FRMS over the sorted finite positive dist2 (optimizeInlierRatio),
                                             then w = dist2 <= quantile(finite dist2, ratio)                               */
-    B200ICP_OUTLIER_SURFACE_NORMAL = 6  /* SurfaceNormalOutlierFilter{maxAngle = param, rad}: w = 0 when the reading's normal (moved
+    B200ICP_OUTLIER_SURFACE_NORMAL = 6, /* SurfaceNormalOutlierFilter{maxAngle = param, rad}: w = 0 when the reading's normal (moved
                                            with the reading) and the matched map point's normal, both normalised, have a dot
                                            product below cos(maxAngle); all ones when either cloud has no normals (LPM: "Skipping
                                            filtering").  The reading's normals come in through b200icp_register_normals.        */
+    B200ICP_OUTLIER_ROBUST = 7          /* RobustOutlierFilter{tuning = param, approximation = param2 (+inf: none), robustFct /
+                                           scaleEstimator / distanceType / nbIterationForScale = outlier_mode, see
+                                           B200ICP_ROBUST_MODE}: M-estimator weights w(e2), e2 = dist / scale^2 with dist the
+                                           match's squared distance (point2point) or (n . (p - q))^2 with the map point's unit
+                                           normal (point2plane); scale = 1 (none), sqrt(median |d2 - median d2|) (mad),
+                                           sqrt(std d2) (std), or Bergstrom's schedule (berg: 1.9 sqrt(median d2) at the first
+                                           iteration, then 0.85 (scale - tuning) + tuning; the weight function's constant becomes
+                                           4.3040 / 7.0589 / 2.0138 for cauchy / tukey / huber).  The scale is re-estimated while
+                                           iteration <= nbIterationForScale, or always when that is 0; the iteration count
+                                           restarts at 1 with every registration.  w = 0 where e2 >= approximation^2.             */
 } b200icp_outlier_kind;
+
+/* RobustOutlierFilter: robustFct, scaleEstimator and distanceType names (libpointmatcher's parameter values) */
+typedef enum b200icp_robust_fct {
+    B200ICP_ROBUST_CAUCHY = 0, /* 1 / (1 + e2 / k^2)                          k = tuning */
+    B200ICP_ROBUST_WELSCH = 1, /* exp(-e2 / k^2)                                          */
+    B200ICP_ROBUST_SC = 2,     /* e2 >= k ? 4 k^2 / (k + e2)^2 : 1    (switchable constraint) */
+    B200ICP_ROBUST_GM = 3,     /* k^2 / (k + e2)^2                       (Geman-McClure)  */
+    B200ICP_ROBUST_TUKEY = 4,  /* e2 >= k^2 ? 0 : (1 - e2 / k^2)^2                       */
+    B200ICP_ROBUST_HUBER = 5,  /* e2 >= k^2 ? k / sqrt(e2) : 1                           */
+    B200ICP_ROBUST_L1 = 6,     /* 1 / sqrt(e2)                                            */
+    B200ICP_ROBUST_STUDENT = 7 /* (k + 3) (1 + e2 / k)^(-(k + 3) / 2) / (k + e2)          */
+} b200icp_robust_fct;
+typedef enum b200icp_robust_scale { B200ICP_SCALE_NONE = 0, B200ICP_SCALE_MAD = 1, B200ICP_SCALE_BERG = 2, B200ICP_SCALE_STD = 3 } b200icp_robust_scale;
+typedef enum b200icp_robust_dist { B200ICP_DIST_POINT2POINT = 0, B200ICP_DIST_POINT2PLANE = 1 } b200icp_robust_dist;
+/* outlier_mode of a RobustOutlierFilter entry: bits 0..7 robustFct, 8..11 scaleEstimator, 12 distanceType, 16..30 nbIterationForScale */
+#define B200ICP_ROBUST_MODE(fct, scale, dist, nb_iteration_for_scale) \
+    ((int32_t)(fct) | ((int32_t)(scale) << 8) | ((int32_t)(dist) << 12) | ((int32_t)(nb_iteration_for_scale) << 16))
 
 /* icp.errorMinimizer */
 typedef enum b200icp_minimizer_kind {
@@ -109,7 +136,8 @@ typedef struct b200icp_config {
                              bit 7 (128) loop kernel: work list in plain entry order (no cost classes)
                              bit 8 (256) cold k = 1 search: shell-walk kernel even when maxDist is small
                              bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3) */
-    int32_t reserved[5];
+    int32_t outlier_mode[B200ICP_MAX_OUTLIER_FILTERS]; /* per filter: B200ICP_ROBUST_MODE(...) for RobustOutlierFilter, else 0 */
+    int32_t reserved[1];
 } b200icp_config;
 
 /* What `icp(input)` leaves behind for the caller (Mapper.cpp:213,219). */

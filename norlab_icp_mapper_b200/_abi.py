@@ -2,14 +2,19 @@
 product binding (icp.py) and by the tests' oracle binding so both speak the same config."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_OUTLIER_FILTERS = 4
 
 # b200icp_status
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_MAP, ERR_CONVERGENCE, ERR_BOUND, ERR_NAN, ERR_TRANSFORM, \
     ERR_INVALID_FIELD, ERR_NOT_IMPLEMENTED = range(10)
 # b200icp_outlier_kind
-OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST, OUTLIER_VAR_TRIMMED_DIST, OUTLIER_SURFACE_NORMAL = 1, 2, 3, 4, 5, 6
+OUTLIER_TRIMMED_DIST, OUTLIER_MAX_DIST, OUTLIER_MIN_DIST, OUTLIER_MEDIAN_DIST, OUTLIER_VAR_TRIMMED_DIST, OUTLIER_SURFACE_NORMAL, \
+    OUTLIER_ROBUST = 1, 2, 3, 4, 5, 6, 7
+# b200icp_robust_fct / b200icp_robust_scale / b200icp_robust_dist (libpointmatcher parameter values)
+ROBUST_FCTS = {"cauchy": 0, "welsch": 1, "sc": 2, "gm": 3, "tukey": 4, "huber": 5, "L1": 6, "student": 7}
+ROBUST_SCALES = {"none": 0, "mad": 1, "berg": 2, "std": 3}
+ROBUST_DISTS = {"point2point": 0, "point2plane": 1}
 # b200icp_minimizer_kind
 MIN_POINT_TO_PLANE, MIN_POINT_TO_POINT, MIN_IDENTITY = 0, 1, 2
 
@@ -37,7 +42,8 @@ class Config(C.Structure):
         ("sort_reading", C.c_int32),
         ("use_graph", C.c_int32),
         ("nn_variant", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("outlier_mode", C.c_int32 * MAX_OUTLIER_FILTERS),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -77,7 +83,7 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
     (docs/MapperConfiguration.md:172-189)."""
     kinds = {"trimmed": OUTLIER_TRIMMED_DIST, "max_dist": OUTLIER_MAX_DIST,
              "min_dist": OUTLIER_MIN_DIST, "median": OUTLIER_MEDIAN_DIST, "var_trimmed": OUTLIER_VAR_TRIMMED_DIST,
-             "surface_normal": OUTLIER_SURFACE_NORMAL}
+             "surface_normal": OUTLIER_SURFACE_NORMAL, "robust": OUTLIER_ROBUST}
     mins = {"point_to_plane": MIN_POINT_TO_PLANE, "point_to_point": MIN_POINT_TO_POINT,
             "identity": MIN_IDENTITY}
     c = Config()
@@ -87,6 +93,14 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
     c.n_outlier = len(outliers)
     for i, (name, *params) in enumerate(outliers):  # ("var_trimmed", minRatio, maxRatio, lambda); one parameter otherwise
         c.outlier_kind[i] = kinds[name]
+        if name == "robust":  # ("robust", {robustFct, tuning, scaleEstimator, nbIterationForScale, distanceType, approximation})
+            rp = dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad", nbIterationForScale=0, distanceType="point2point",
+                      approximation=float("inf"))  # libpointmatcher's defaults
+            rp.update(params[0] if params else {})
+            c.outlier_param[i], c.outlier_param2[i], c.outlier_param3[i] = rp["tuning"], rp["approximation"], 0.0
+            c.outlier_mode[i] = (ROBUST_FCTS[rp["robustFct"]] | (ROBUST_SCALES[rp["scaleEstimator"]] << 8) |
+                                 (ROBUST_DISTS[rp["distanceType"]] << 12) | (int(rp["nbIterationForScale"]) << 16))
+            continue
         c.outlier_param[i] = params[0]
         c.outlier_param2[i] = params[1] if len(params) > 1 else 0.0
         c.outlier_param3[i] = params[2] if len(params) > 2 else 0.0

@@ -160,10 +160,17 @@ int32_t validate_config(const b200icp_config* c, std::string& why) {
     if (c->knn < 1 || c->knn > 32) return why = "knn must be in [1, 32]", B200ICP_ERR_INVALID_ARG;
     if (!(c->max_dist > 0.f)) return why = "maxDist must be positive", B200ICP_ERR_INVALID_ARG;
     if (c->n_outlier < 0 || c->n_outlier > B200ICP_MAX_OUTLIER_FILTERS) return why = "too many outlier filters", B200ICP_ERR_INVALID_ARG;
-    int quant = 0;
+    int quant = 0, n_robust = 0;
     for (int f = 0; f < c->n_outlier; ++f) {
         const int kd = c->outlier_kind[f];
-        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_SURFACE_NORMAL) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
+        if (kd == B200ICP_OUTLIER_ROBUST && ++n_robust > 1) return why = "at most one RobustOutlierFilter per chain", B200ICP_ERR_NOT_IMPLEMENTED;
+        if (kd < B200ICP_OUTLIER_TRIMMED_DIST || kd > B200ICP_OUTLIER_ROBUST) return why = "unknown outlier filter", B200ICP_ERR_INVALID_ARG;
+        if (kd == B200ICP_OUTLIER_ROBUST) {
+            const int mode = c->outlier_mode[f];
+            if ((mode & 255) > B200ICP_ROBUST_STUDENT) return why = "RobustOutlierFilter: invalid robust function name", B200ICP_ERR_INVALID_ARG;
+            if (((mode >> 8) & 15) > B200ICP_SCALE_STD) return why = "RobustOutlierFilter: invalid scale estimator name", B200ICP_ERR_INVALID_ARG;
+            if (mode < 0) return why = "RobustOutlierFilter: invalid mode bits", B200ICP_ERR_INVALID_ARG;
+        }
         if (kd == B200ICP_OUTLIER_TRIMMED_DIST || kd == B200ICP_OUTLIER_MEDIAN_DIST || kd == B200ICP_OUTLIER_VAR_TRIMMED_DIST) ++quant;
         if (kd == B200ICP_OUTLIER_VAR_TRIMMED_DIST &&
             !(c->outlier_param[f] >= 0.f && c->outlier_param[f] < c->outlier_param2[f] && c->outlier_param2[f] <= 1.f && c->outlier_param3[f] > 0.f))
@@ -343,6 +350,7 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
         p.outlier_param[f] = cfg->outlier_param[f];
         p.outlier_param2[f] = cfg->outlier_param2[f];
         p.outlier_param3[f] = cfg->outlier_param3[f];
+        p.outlier_mode[f] = cfg->outlier_mode[f];
         if (cfg->outlier_kind[f] == B200ICP_OUTLIER_VAR_TRIMMED_DIST) {
             p.quantile_filter = f;
             p.quantile = -1.f;  // tuned per iteration on the device (outlier.cu)
@@ -563,6 +571,9 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
     if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE && !ctx->map.has_normals)
         return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Cannot find descriptor normals in reference (PointToPlaneErrorMinimizer)");
+    for (int f = 0; f < p.n_outlier; ++f)
+        if (p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST && ((p.outlier_mode[f] >> 12) & 1) && !ctx->map.has_normals)
+            return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Cannot find descriptor normals in reference (RobustOutlierFilter, distanceType point2plane)");
 
     // state image
     IcpState* hs = reinterpret_cast<IcpState*>(ctx->h_pinned);
@@ -628,7 +639,10 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     // Cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
     // (Per-kernel profiling and nn_variant bit 2 select the kernel-per-step path below instead.)
     const bool var_trimmed = p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST;
-    const bool persistent = !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed;
+    bool robust = false;
+    for (int f = 0; f < p.n_outlier; ++f) robust = robust || p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST;
+    // (VarTrimmed and Robust estimate their ratio / scale with device-wide sorts between the steps: kernel-per-step path)
+    const bool persistent = !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed && !robust;
     if (persistent) {
         CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
                       /*want_original_ids=*/0, ctx->cfg.nn_variant & 0xffff, s));

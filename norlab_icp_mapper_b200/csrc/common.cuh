@@ -65,7 +65,7 @@ struct IcpState {
     int searched_queries;  // queries that went through the search phase (the rest were verified against their bound)
     int hist_iters;        // iterations that took the two-barrier path (window from a level-0 histogram)
     float dyn_quantile;    // VarTrimmedDist: the ratio tuned for this iteration (outlier.cu)
-    int pad3_;
+    float robust_scale;    // RobustOutlierFilter: the current scale estimate (outlier.cu); kept across iterations
 };
 
 static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");
@@ -100,6 +100,7 @@ struct IcpParams {  // by-value kernel argument, constant for the life of a cont
     float outlier_param[B200ICP_MAX_OUTLIER_FILTERS];
     float outlier_param2[B200ICP_MAX_OUTLIER_FILTERS];
     float outlier_param3[B200ICP_MAX_OUTLIER_FILTERS];
+    int outlier_mode[B200ICP_MAX_OUTLIER_FILTERS];  // RobustOutlierFilter: B200ICP_ROBUST_MODE bits
     const float4* rnrm;   // reading normals (refMean frame, same order as the reading) for SurfaceNormalOutlierFilter, or null:
                           // set per registration, the only field that is not constant for the life of a context
     int quantile_filter;  // index of the Trimmed/Median filter or -1
@@ -260,6 +261,8 @@ struct VarTrimScratch {
 };
 void var_trimmed_free(VarTrimScratch& v);
 cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int filter_index, IcpBuffers& b, cudaStream_t s, int* launches);
+// RobustOutlierFilter's scale estimate for iteration `it` (0-based) -> IcpState::robust_scale
+cudaError_t launch_robust_scale(VarTrimScratch& v, const IcpParams& p, int filter_index, IcpBuffers& b, int it, cudaStream_t s, int* launches);
 
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
                                 float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,

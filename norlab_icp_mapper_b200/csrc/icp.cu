@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
 #pragma unroll
     for (int i = 0; i < 16; ++i) T[i] = st->T[i];
     const float qlimit = st->limit;
+    const float rscale = st->robust_scale;
 
     // per-thread sums stay in fp32 (a thread sees only a handful of pairs); everything above the
     // thread level is accumulated in fp64 in a fixed order
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
     for (int i = 0; i < NS; ++i) acc[i] = 0.f;
 
     for (long long e = blockIdx.x * 256ll + threadIdx.x; e < m; e += (long long)gridDim.x * 256ll) {
-        accumulate_entry<MIN>(acc, prm, T, g, nrm, reading, e, K, mpos[e], md2[e], qlimit);
+        accumulate_entry<MIN>(acc, prm, T, g, nrm, reading, e, K, mpos[e], md2[e], qlimit, rscale);
     }
 
     if (blockIdx.x == 0 && threadIdx.x == 0) B200_STAMP(st, 12);
@@ -371,8 +372,13 @@ cudaError_t icp_device_setup() {  // once per device (context creation)
 
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it, cudaStream_t s, int* launches,
                                   cudaEvent_t ev_mid, VarTrimScratch* var_scratch) {
-    (void)it;
     const long long m = (long long)b.cap_nq * p.knn;
+    for (int f = 0; f < p.n_outlier; ++f)
+        if (p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST) {
+            if (!var_scratch) return cudaErrorInvalidValue;
+            cudaError_t e = launch_robust_scale(*var_scratch, p, f, b, it, s, launches);
+            if (e != cudaSuccess) return e;
+        }
     if (p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST) {
         if (!var_scratch) return cudaErrorInvalidValue;
         cudaError_t e = launch_var_trimmed_ratio(*var_scratch, p, p.quantile_filter, b, s, launches);

@@ -578,10 +578,38 @@ __device__ __forceinline__ bool surface_normal_keep(const float* T, const float4
 
 // One (reading point, neighbour) entry of ErrorElements: outlier weights, then the error-minimiser
 // products.  MIN: 0 point-to-plane (29 sums), 1 point-to-point (18 sums), 2 identity (2 sums).
+// LPM RobustOutlierFilter::robustFiltering: the M-estimator weight of one match.  dist = squared distance (point2point) or
+// squared distance along the map point's unit normal (point2plane); e2 = dist / scale^2; k = tuning (berg: the constant of
+// Bergstrom & Edlund 2014 for cauchy / tukey / huber, the tuning parameter being the target scale there).
+__device__ __forceinline__ float robust_weight(int mode, float tuning, float approximation, float scale, float dist) {
+    const int fct = mode & 255, est = (mode >> 8) & 15;
+    float k = tuning;
+    if (est == B200ICP_SCALE_BERG) k = fct == B200ICP_ROBUST_CAUCHY ? 4.3040f : (fct == B200ICP_ROBUST_TUKEY ? 7.0589f : (fct == B200ICP_ROBUST_HUBER ? 2.0138f : tuning));
+    const float s = est == B200ICP_SCALE_NONE ? 1.f : scale;
+    const float e2 = dist / (s * s);
+    const float k2 = k * k;
+    float w = 1.f;
+    switch (fct) {
+        case B200ICP_ROBUST_CAUCHY: w = 1.f / (1.f + e2 / k2); break;
+        case B200ICP_ROBUST_WELSCH: w = expf(-e2 / k2); break;
+        case B200ICP_ROBUST_SC: w = e2 >= k ? 4.f * k2 / ((k + e2) * (k + e2)) : 1.f; break;
+        case B200ICP_ROBUST_GM: w = k2 / ((k + e2) * (k + e2)); break;
+        case B200ICP_ROBUST_TUKEY: w = e2 >= k2 ? 0.f : (1.f - e2 / k2) * (1.f - e2 / k2); break;
+        case B200ICP_ROBUST_HUBER: w = e2 >= k2 ? k / sqrtf(e2) : 1.f; break;
+        case B200ICP_ROBUST_L1: w = 1.f / sqrtf(e2); break;
+        case B200ICP_ROBUST_STUDENT: w = powf(1.f + e2 / k, -(k + 3.f) * 0.5f) * (k + 3.f) / (k + e2); break;
+        default: break;
+    }
+    if (w <= 0.f) w = 0.f;  // (upstream's 1e-50 floor is 0 in fp32)
+    const float a2 = approximation * approximation;
+    if (a2 != CUDART_INF_F && e2 >= a2) w = 0.f;
+    return w;
+}
+
 template <int MIN>
 __device__ __forceinline__ void accumulate_entry(float* acc, const IcpParams& prm, const float* T, const GridView& g,
                                                  const float4* __restrict__ nrm, const float4* __restrict__ reading, long long e,
-                                                 int K, int pos, float d, float qlimit) {
+                                                 int K, int pos, float d, float qlimit, float robust_scale = 1.f) {
     constexpr int NS = SumLayout<MIN>::N;
     if (pos < 0) return;
     if (d == CUDART_INF_F) return;
@@ -600,6 +628,17 @@ __device__ __forceinline__ void accumulate_entry(float* acc, const IcpParams& pr
                 break;
         }
         w *= keep ? 1.f : 0.f;
+        if (prm.outlier_kind[f] == B200ICP_OUTLIER_ROBUST) {
+            float dist = d;
+            if ((prm.outlier_mode[f] >> 12) & 1) {  // point2plane: (n . (p - q))^2, n normalised (nrm is there: checked by the host)
+                const float3 pr = apply_T(T, __ldg(reading + ((K == 1) ? e : e / K)));
+                const float4 qm = __ldg(g.pts + pos), nm = __ldg(nrm + pos);
+                const float inv = 1.f / sqrtf(nm.x * nm.x + nm.y * nm.y + nm.z * nm.z);
+                const float dot = (nm.x * inv) * (pr.x - qm.x) + (nm.y * inv) * (pr.y - qm.y) + (nm.z * inv) * (pr.z - qm.z);
+                dist = dot * dot;
+            }
+            w *= robust_weight(prm.outlier_mode[f], p, prm.outlier_param2[f], robust_scale, dist);
+        }
     }
     if (w == 0.f) return;
     const long long i = (K == 1) ? e : e / K;

@@ -80,6 +80,89 @@ __global__ void __launch_bounds__(1024) var_argmin_kernel(IcpState* __restrict__
     }
 }
 
+// ---- RobustOutlierFilter: the scale estimate (LPM OutlierFiltersImpl.cpp RobustOutlierFilter::robustFiltering) ----
+// mad:  scale = sqrt(median |d - median d|) over the finite squared distances d (Matches::getMedianAbsDeviation: both medians
+//       are the element at index n / 2 of the sorted values);
+// berg: first iteration 1.9 sqrt(median d) (Matches::getDistsQuantile(0.5)), afterwards scale <- 0.85 (scale - target) + target;
+// std:  scale = sqrt(std d) over ALL entries, n - 1 in the denominator (Matches::getStandardDeviation; an unmatched entry's
+//       +inf makes it NaN, as upstream).
+__global__ void __launch_bounds__(256) robust_keys_kernel(const IcpState* __restrict__ st, const float* __restrict__ d2, int knn, long long cap,
+                                                          float* __restrict__ keys, unsigned int* __restrict__ count) {
+    if (st->done) return;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long m = (long long)st->nq * knn;
+    float v = CUDART_INF_F;
+    if (i < m && i < cap) v = d2[i];
+    if (i < cap) keys[i] = v;
+    const unsigned bal = __ballot_sync(0xffffffffu, v != CUDART_INF_F);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, (unsigned)__popc(bal));
+}
+
+// stage 0: median of the sorted finite distances -> scratch[0]; berg's first iteration ends here.
+// stage 1: median of the sorted absolute deviations -> the mad scale.
+__global__ void robust_median_kernel(IcpState* __restrict__ st, const float* __restrict__ sorted, unsigned int* __restrict__ count,
+                                     float* __restrict__ scratch, int stage, int estimator) {
+    if (st->done) return;
+    const unsigned n = *count;
+    if (n == 0) {  // LPM: ConvergenceError("no outlier to filter")
+        st->status = B200ICP_ERR_CONVERGENCE;
+        st->done = 1;
+        return;
+    }
+    const float med = sorted[n / 2];
+    if (stage == 0) {
+        scratch[0] = med;
+        if (estimator == B200ICP_SCALE_BERG) {
+            st->robust_scale = 1.9f * sqrtf(med);
+            *count = 0u;
+        }
+    } else {
+        st->robust_scale = sqrtf(med);
+        *count = 0u;  // ready for the next iteration
+    }
+}
+
+__global__ void __launch_bounds__(256) robust_absdev_kernel(const IcpState* __restrict__ st, const float* __restrict__ sorted,
+                                                            const unsigned int* __restrict__ count, const float* __restrict__ scratch,
+                                                            float* __restrict__ keys, long long cap) {
+    if (st->done) return;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= cap) return;
+    keys[i] = (i < (long long)*count) ? fabsf(sorted[i] - scratch[0]) : CUDART_INF_F;
+}
+
+__global__ void robust_berg_step_kernel(IcpState* __restrict__ st, float target) {
+    if (st->done) return;
+    st->robust_scale = 0.85f * (st->robust_scale - target) + target;
+}
+
+__global__ void __launch_bounds__(1024) robust_std_kernel(IcpState* __restrict__ st, const float* __restrict__ d2, int knn) {
+    if (st->done) return;
+    __shared__ double s_red[32];
+    __shared__ double s_mean;
+    const long long m = (long long)st->nq * knn;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int pass = 0; pass < 2; ++pass) {
+        double acc = 0.0;
+        const double mean = pass ? s_mean : 0.0;
+        for (long long i = threadIdx.x; i < m; i += 1024) {
+            const double v = (double)d2[i];
+            acc += pass ? (v - mean) * (v - mean) : v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < 32; ++w) tot += s_red[w];
+            if (pass == 0) s_mean = tot / (double)m;
+            else st->robust_scale = sqrtf((float)sqrt(tot / (double)(m - 1)));
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 void var_trimmed_free(VarTrimScratch& v) {
@@ -91,8 +174,43 @@ void var_trimmed_free(VarTrimScratch& v) {
     v = VarTrimScratch{};
 }
 
-cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int f, IcpBuffers& b, cudaStream_t s, int* launches) {
+static cudaError_t ensure_sort_scratch(VarTrimScratch& v, long long cap, cudaStream_t s);
+
+cudaError_t launch_robust_scale(VarTrimScratch& v, const IcpParams& p, int f, IcpBuffers& b, int it, cudaStream_t s, int* launches) {
+    const int mode = p.outlier_mode[f];
+    const int estimator = (mode >> 8) & 15, nb = (mode >> 16) & 0x7fff;
+    const int iteration = it + 1;  // LPM counts from 1; here it restarts with every registration
+    if (estimator == B200ICP_SCALE_NONE || !(iteration <= nb || nb == 0)) return cudaSuccess;
+    if (estimator == B200ICP_SCALE_STD) {
+        robust_std_kernel<<<1, 1024, 0, s>>>(b.state, b.match_d2, p.knn);
+        *launches += 1;
+        return cudaGetLastError();
+    }
+    if (estimator == B200ICP_SCALE_BERG && iteration > 1) {
+        robust_berg_step_kernel<<<1, 1, 0, s>>>(b.state, p.outlier_param[f]);
+        *launches += 1;
+        return cudaGetLastError();
+    }
     const long long cap = (long long)b.cap_nq * p.knn;
+    cudaError_t e = ensure_sort_scratch(v, cap, s);
+    if (e != cudaSuccess) return e;
+    float* scratch = reinterpret_cast<float*>(v.d_count) + 4;
+    robust_keys_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(b.state, b.match_d2, p.knn, cap, v.keys_in, v.d_count);
+    size_t bytes = v.cub_bytes;
+    if ((e = cub::DeviceRadixSort::SortKeys(v.cub_tmp, bytes, v.keys_in, v.keys_out, (int)cap, 0, 32, s)) != cudaSuccess) return e;
+    robust_median_kernel<<<1, 1, 0, s>>>(b.state, v.keys_out, v.d_count, scratch, 0, estimator);
+    *launches += 4;
+    if (estimator == B200ICP_SCALE_MAD) {
+        robust_absdev_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(b.state, v.keys_out, v.d_count, scratch, v.keys_in, cap);
+        bytes = v.cub_bytes;
+        if ((e = cub::DeviceRadixSort::SortKeys(v.cub_tmp, bytes, v.keys_in, v.keys_out, (int)cap, 0, 32, s)) != cudaSuccess) return e;
+        robust_median_kernel<<<1, 1, 0, s>>>(b.state, v.keys_out, v.d_count, scratch, 1, estimator);
+        *launches += 4;
+    }
+    return cudaGetLastError();
+}
+
+static cudaError_t ensure_sort_scratch(VarTrimScratch& v, long long cap, cudaStream_t s) {
     cudaError_t e;
     if (cap > v.cap) {
         var_trimmed_free(v);
@@ -109,6 +227,13 @@ cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int 
         if ((e = cudaMalloc(&v.cub_tmp, v.cub_bytes)) != cudaSuccess) return e;
         v.cap = cap;
     }
+    return cudaSuccess;
+}
+
+cudaError_t launch_var_trimmed_ratio(VarTrimScratch& v, const IcpParams& p, int f, IcpBuffers& b, cudaStream_t s, int* launches) {
+    const long long cap = (long long)b.cap_nq * p.knn;
+    cudaError_t e = ensure_sort_scratch(v, cap, s);
+    if (e != cudaSuccess) return e;
     var_keys_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, s>>>(b.state, b.match_d2, p.knn, cap, v.keys_in, v.d_count);
     size_t bytes = v.cub_bytes;
     if ((e = cub::DeviceRadixSort::SortKeys(v.cub_tmp, bytes, v.keys_in, v.keys_out, (int)cap, 0, 32, s)) != cudaSuccess) return e;

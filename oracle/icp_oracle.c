@@ -476,6 +476,7 @@ struct orc_icp {
     float mean[3];
     orc_kdtree* tree;
     float last_var_ratio; /* VarTrimmed: the tuned ratio of the last iteration (diagnostic) */
+    float last_robust_scale; /* RobustOutlierFilter: the scale used by the last iteration (diagnostic) */
     float* reading_normals; /* dim floats per reading point for the NEXT register call (SurfaceNormalOutlierFilter), or NULL */
     int64_t n_reading_normals;
     char err[256];
@@ -498,6 +499,7 @@ void orc_icp_destroy(orc_icp* o) {
 }
 const char* orc_icp_last_error(const orc_icp* o) { return o ? o->err : "null oracle"; }
 float orc_icp_last_var_ratio(const orc_icp* o) { return o ? o->last_var_ratio : 0.f; }
+float orc_icp_last_robust_scale(const orc_icp* o) { return o ? o->last_robust_scale : 0.f; }
 /* the `normals` descriptor of the reading handed to the next orc_icp_register (dim x n, column-major); NULL clears it */
 int32_t orc_icp_set_reading_normals(orc_icp* o, const float* normals, int64_t n) {
     if (!o || n < 0) return B200ICP_ERR_INVALID_ARG;
@@ -595,6 +597,50 @@ static int dists_quantile(const float* d2, int64_t m, float quantile, float* out
 static int cmp_f32(const void* a, const void* b) {
     const float x = *(const float*)a, y = *(const float*)b;
     return (x > y) - (x < y);
+}
+
+/* LPM Matches::getMedianAbsDeviation: median (element n / 2 after nth_element) of the finite squared distances, then the
+ * median of their absolute deviations from it. */
+static int median_abs_deviation(const float* d2, int64_t m, float* out, float* scratch) {
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < m; ++i)
+        if (d2[i] != INFINITY) scratch[cnt++] = d2[i];
+    if (cnt == 0) return -1;
+    const float median = nth_element_f32(scratch, cnt, cnt / 2);
+    for (int64_t i = 0; i < cnt; ++i) scratch[i] = fabsf(scratch[i] - median);
+    *out = nth_element_f32(scratch, cnt, cnt / 2);
+    return 0;
+}
+
+/* LPM Matches::getStandardDeviation: sqrt(sum (d - mean)^2 / (size - 1)) over ALL entries of the dists matrix (an
+ * unmatched entry's +inf turns it into NaN, as upstream). */
+static float dists_standard_deviation(const float* d2, int64_t m) {
+    double sum = 0.0, sq = 0.0;
+    for (int64_t i = 0; i < m; ++i) sum += d2[i];
+    const double mean = sum / (double)m;
+    for (int64_t i = 0; i < m; ++i) sq += ((double)d2[i] - mean) * ((double)d2[i] - mean);
+    return (float)sqrt(sq / (double)(m - 1));
+}
+
+/* LPM OutlierFiltersImpl.cpp RobustOutlierFilter::robustFiltering, weight of one match: e2 = dist / scale^2, k = tuning */
+static float robust_weight(int fct, float k, float approximation, float scale, float dist) {
+    const float e2 = dist / (scale * scale);
+    const float k2 = k * k;
+    float w = 1.f;
+    switch (fct) {
+        case B200ICP_ROBUST_CAUCHY: w = 1.f / (1.f + e2 / k2); break;
+        case B200ICP_ROBUST_WELSCH: w = expf(-e2 / k2); break;
+        case B200ICP_ROBUST_SC: w = e2 >= k ? 4.f * k2 / ((k + e2) * (k + e2)) : 1.f; break;
+        case B200ICP_ROBUST_GM: w = k2 / ((k + e2) * (k + e2)); break;
+        case B200ICP_ROBUST_TUKEY: w = e2 >= k2 ? 0.f : (1.f - e2 / k2) * (1.f - e2 / k2); break;
+        case B200ICP_ROBUST_HUBER: w = e2 >= k2 ? k / sqrtf(e2) : 1.f; break;
+        case B200ICP_ROBUST_L1: w = 1.f / sqrtf(e2); break;
+        case B200ICP_ROBUST_STUDENT: w = powf(1.f + e2 / k, -(k + 3.f) / 2.f) * (k + 3.f) / (k + e2); break;
+        default: break;
+    }
+    if (w <= 0.f) w = 0.f; /* upstream floors at 1e-50, which is 0 in T = float */
+    if (approximation * approximation != INFINITY && e2 >= approximation * approximation) w = 0.f;
+    return w;
 }
 
 /* LPM OutlierFiltersImpl.cpp VarTrimmedDistOutlierFilter::optimizeInlierRatio: the finite, positive squared
@@ -723,6 +769,7 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
     quat_from_R(T_iter, dim, bound_q0);
 
     int iterate = 1, iterations = 0, max_iter_reached = 0;
+    float robust_scale[B200ICP_MAX_OUTLIER_FILTERS] = {0.f, 0.f, 0.f, 0.f}; /* RobustOutlierFilter::scale, per filter */
     float overlap = 0.f, used_ratio = 0.f;
     int64_t pairs = 0;
     const int smooth = cfg->smooth_length > 7 ? 7 : (cfg->smooth_length < 1 ? 1 : cfg->smooth_length);
@@ -789,6 +836,59 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
                             w[i * k + j] *= (dot < eps) ? 0.f : 1.f;
                         }
                     }
+                    break;
+                }
+                case B200ICP_OUTLIER_ROBUST: {
+                    /* LPM RobustOutlierFilter{robustFct, tuning, scaleEstimator, nbIterationForScale, distanceType, approximation}.
+                     * `iteration` counts this filter's calls from 1 (restarted per registration here); the scale is re-estimated
+                     * while iteration <= nbIterationForScale, or always when that is 0. */
+                    const int mode = cfg->outlier_mode[f];
+                    const int fct = mode & 255, est = (mode >> 8) & 15, p2plane = (mode >> 12) & 1, nb = (mode >> 16) & 0x7fff;
+                    const int iteration = iterations + 1;
+                    float tuning = prm;
+                    if (est == B200ICP_SCALE_BERG) { /* Bergstrom & Edlund 2014: tuning is the target scale, k comes from the paper */
+                        if (fct == B200ICP_ROBUST_CAUCHY) tuning = 4.3040f;
+                        else if (fct == B200ICP_ROBUST_TUKEY) tuning = 7.0589f;
+                        else if (fct == B200ICP_ROBUST_HUBER) tuning = 2.0138f;
+                    }
+                    if (iteration <= nb || nb == 0) {
+                        float v = 0.f;
+                        if (est == B200ICP_SCALE_MAD) {
+                            if (median_abs_deviation(d2, m, &v, scratch)) FAIL(o, B200ICP_ERR_CONVERGENCE, "no outlier to filter");
+                            robust_scale[f] = sqrtf(v);
+                        } else if (est == B200ICP_SCALE_STD) {
+                            robust_scale[f] = sqrtf(dists_standard_deviation(d2, m));
+                        } else if (est == B200ICP_SCALE_BERG) {
+                            if (iteration == 1) {
+                                if (dists_quantile(d2, m, 0.5f, &v, scratch)) FAIL(o, B200ICP_ERR_CONVERGENCE, "no outlier to filter");
+                                robust_scale[f] = 1.9f * sqrtf(v);
+                            } else {
+                                robust_scale[f] = 0.85f * (robust_scale[f] - prm) + prm;
+                            }
+                        }
+                    }
+                    const float scale = est == B200ICP_SCALE_NONE ? 1.f : robust_scale[f];
+                    o->last_robust_scale = scale;
+                    if (p2plane && !o->normals) FAIL(o, B200ICP_ERR_INVALID_FIELD, "Cannot find descriptor normals in reference");
+                    for (int64_t i = 0; i < nq; ++i)
+                        for (int j = 0; j < k; ++j) {
+                            const int32_t id = ids[i * k + j];
+                            float dist = d2[i * k + j];
+                            if (p2plane) { /* computePointToPlaneDistance: (n . (p - q))^2 with n normalised; 0 where unmatched */
+                                dist = 0.f;
+                                if (id >= 0) {
+                                    const float* nf = o->normals + (int64_t)id * 3;
+                                    const float* q = o->map + (int64_t)id * 4;
+                                    const float* pp = step + i * 4;
+                                    float ln = 0.f, dot = 0.f;
+                                    for (int d = 0; d < dim; ++d) ln += nf[d] * nf[d];
+                                    ln = sqrtf(ln);
+                                    for (int d = 0; d < dim; ++d) dot += (nf[d] / ln) * (pp[d] - q[d]);
+                                    dist = dot * dot;
+                                }
+                            }
+                            w[i * k + j] *= robust_weight(fct, tuning, cfg->outlier_param2[f], scale, dist);
+                        }
                     break;
                 }
                 case B200ICP_OUTLIER_MAX_DIST:

@@ -43,6 +43,7 @@ orc_icp* orc_icp_create(const b200icp_config* cfg);
 void orc_icp_destroy(orc_icp* o);
 const char* orc_icp_last_error(const orc_icp* o);
 float orc_icp_last_var_ratio(const orc_icp* o); /* VarTrimmed: tuned ratio of the last iteration */
+float orc_icp_last_robust_scale(const orc_icp* o); /* RobustOutlierFilter: scale used by the last iteration */
 /* `normals` descriptor of the reading for the next orc_icp_register (dim x n column-major; NULL clears): SurfaceNormalOutlierFilter */
 int32_t orc_icp_set_reading_normals(orc_icp* o, const float* normals, int64_t n);
 /* icp.setMap(cloud) -- Map.cpp:111,178,528,581. Returns b200icp_status. */

@@ -33,6 +33,59 @@ def rodrigues(r):
     return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
 
 
+def robust_weights(prm, iteration, scale, d2, ids, p_all, ref, map_normals):
+    """RobustOutlierFilter (libpointmatcher OutlierFiltersImpl.cpp) written from its documentation in fp64: returns
+    (scale, weights).  prm: dict with libpointmatcher's parameter names."""
+    prm = dict(dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad", nbIterationForScale=0, distanceType="point2point",
+                    approximation=np.inf), **prm)
+    k, est, nb = prm["tuning"], prm["scaleEstimator"], prm["nbIterationForScale"]
+    if est == "berg":
+        k = {"cauchy": 4.3040, "tukey": 7.0589, "huber": 2.0138}.get(prm["robustFct"], k)
+    if iteration <= nb or nb == 0:
+        fin = np.sort(d2[np.isfinite(d2)])
+        if est == "mad":
+            med = fin[len(fin) // 2]
+            scale = np.sqrt(np.sort(np.abs(fin - med))[len(fin) // 2])
+        elif est == "std":
+            scale = np.sqrt(np.std(d2, ddof=1))
+        elif est == "berg":
+            scale = 1.9 * np.sqrt(fin[int(len(fin) * 0.5)]) if iteration == 1 else 0.85 * (scale - prm["tuning"]) + prm["tuning"]
+    s = 1.0 if est == "none" else scale
+    dist = d2
+    if prm["distanceType"] == "point2plane":
+        n = np.asarray(map_normals, np.float64)
+        n = n / np.linalg.norm(n, axis=1, keepdims=True)
+        safe = np.where(np.isfinite(d2), ids, 0)
+        diff = p_all[:, None, :] - ref[safe]
+        dist = np.einsum("ijk,ijk->ij", n[safe], diff) ** 2
+    with np.errstate(all="ignore"):
+        e2 = dist / (s * s)
+        k2 = k * k
+        fct = prm["robustFct"]
+        if fct == "cauchy":
+            w = 1.0 / (1.0 + e2 / k2)
+        elif fct == "welsch":
+            w = np.exp(-e2 / k2)
+        elif fct == "sc":
+            w = np.where(e2 >= k, 4.0 * k2 / (k + e2) ** 2, 1.0)
+        elif fct == "gm":
+            w = k2 / (k + e2) ** 2
+        elif fct == "tukey":
+            w = np.where(e2 >= k2, 0.0, (1.0 - e2 / k2) ** 2)
+        elif fct == "huber":
+            w = np.where(e2 >= k2, k / np.sqrt(e2), 1.0)
+        elif fct == "L1":
+            w = 1.0 / np.sqrt(e2)
+        elif fct == "student":
+            w = (1.0 + e2 / k) ** (-(k + 3.0) / 2.0) * (k + 3.0) / (k + e2)
+        else:
+            raise ValueError(fct)
+    w = np.where(w <= 0.0, 0.0, w)
+    if np.isfinite(prm["approximation"]):
+        w = np.where(e2 >= prm["approximation"] ** 2, 0.0, w)
+    return scale, w
+
+
 def icp(map_xyz, map_normals, reading_xyz, knn_k=1, max_dist=np.inf, outliers=(("trimmed", 0.85),),
         minimizer="point_to_plane", iterations=30):
     """Counter-checker-only ICP in the mean-centred frame; returns the (dim+1)x(dim+1) correction."""
@@ -43,7 +96,8 @@ def icp(map_xyz, map_normals, reading_xyz, knn_k=1, max_dist=np.inf, outliers=((
     tree = cKDTree(ref)
     reading = np.asarray(reading_xyz, np.float64) - mean
     T = np.eye(dim + 1)
-    for _ in range(iterations):
+    robust_scale = 0.0
+    for it in range(iterations):
         p_all = reading @ T[:dim, :dim].T + T[:dim, dim]
         d, ids = tree.query(p_all, k=knn_k, distance_upper_bound=max_dist if np.isfinite(max_dist) else np.inf)
         d = d.reshape(len(p_all), knn_k)
@@ -59,6 +113,9 @@ def icp(map_xyz, map_normals, reading_xyz, knn_k=1, max_dist=np.inf, outliers=((
                 w *= d2 <= prm * prm
             elif name == "min_dist":
                 w *= d2 >= prm * prm
+            elif name == "robust":
+                robust_scale, wr = robust_weights(prm, it + 1, robust_scale, d2, ids, p_all, ref, map_normals)
+                w *= wr
         keep = np.isfinite(d2) & (w != 0)
         qi, kk = np.nonzero(keep)
         p = p_all[qi]

@@ -91,6 +91,12 @@ class OracleICP:
     def last_error(self):
         return lib().orc_icp_last_error(self._h).decode()
 
+    def last_robust_scale(self):
+        L = lib()
+        L.orc_icp_last_robust_scale.restype = C.c_float
+        L.orc_icp_last_robust_scale.argtypes = [C.c_void_p]
+        return float(L.orc_icp_last_robust_scale(self._h))
+
     def set_map(self, features, normals=None):
         features = _cloud(features)
         nptr = None

@@ -286,6 +286,49 @@ def test_var_trimmed_dist_outlier_filter(oracle, pair3d):
         assert 0.3 * k * len(pair3d["reading"]) < res_g.pairs_last_iter < 0.995 * k * len(pair3d["reading"])
 
 
+ROBUST_CASES = [
+    ("point_to_plane", 1, 1.0, dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),  # libpointmatcher's defaults
+    ("point_to_plane", 2, 1.0, dict(robustFct="huber", tuning=1.5, scaleEstimator="mad", nbIterationForScale=3)),
+    ("point_to_point", 1, 1.0, dict(robustFct="tukey", tuning=3.0, scaleEstimator="none", approximation=0.9)),
+    ("point_to_plane", 1, 1.0, dict(robustFct="cauchy", tuning=0.05, scaleEstimator="berg")),
+    ("point_to_plane", 1, 1.0, dict(robustFct="welsch", tuning=2.0, scaleEstimator="mad", distanceType="point2plane")),
+    ("point_to_point", 3, 1.0, dict(robustFct="gm", tuning=1.0, scaleEstimator="mad")),
+    ("point_to_plane", 1, 1.0, dict(robustFct="sc", tuning=1.0, scaleEstimator="mad", distanceType="point2plane")),
+    ("point_to_plane", 1, 1.0, dict(robustFct="student", tuning=2.0, scaleEstimator="mad")),
+    ("point_to_plane", 1, 1.0, dict(robustFct="L1", tuning=1.0, scaleEstimator="none")),
+    ("point_to_plane", 1, float("inf"), dict(robustFct="cauchy", tuning=2.0, scaleEstimator="std")),  # (std needs every point matched)
+]
+
+
+@pytest.mark.parametrize("minimizer,knn,max_dist,rp", ROBUST_CASES)
+def test_robust_outlier_filter(oracle, pair3d, minimizer, knn, max_dist, rp):
+    """RobustOutlierFilter: soft M-estimator weights with a per-iteration scale estimate (two device sorts for mad).
+    Same pose, same kept pairs and the same weighted ratio (getOverlap) as the oracle."""
+    cfg = make_config(dim=3, knn=knn, max_dist=max_dist, outliers=(("robust", rp), ("max_dist", 0.9)), minimizer=minimizer,
+                      max_iteration_count=10)
+    T_g, res_g, tr_g, T_o, res_o, tr_o = _both(oracle, cfg, pair3d)
+    er, et = synth.pose_error(T_g, T_o)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res_g.iterations == res_o.iterations == 10
+    assert abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.001 * res_o.pairs_last_iter + 2
+    assert res_g.overlap == pytest.approx(res_o.overlap, rel=2e-3)
+
+
+def test_robust_point2plane_needs_reference_normals(pair3d):
+    from norlab_icp_mapper_b200.icp import ICP, B200ICPError
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("robust", dict(distanceType="point2plane")),), minimizer="point_to_point",
+                      max_iteration_count=3)
+    g = ICP(cfg)
+    g.set_map(pair3d["map"], None)
+    with pytest.raises(B200ICPError) as e:
+        g(pair3d["reading"])
+    assert e.value.status == _abi.ERR_INVALID_FIELD
+    g.close()
+    with pytest.raises(B200ICPError) as e:  # one scale estimate per chain
+        ICP(make_config(dim=3, outliers=(("robust", {}), ("robust", {}))))
+    assert e.value.status == _abi.ERR_NOT_IMPLEMENTED
+
+
 def test_error_behaviour_matches_libpointmatcher(oracle, pair3d):
     from norlab_icp_mapper_b200.icp import ICP, B200ICPError
     cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=5)

@@ -152,3 +152,65 @@ def test_point_distance_and_normals(oracle, golden):
     g = golden["normals"]
     cosang = np.abs(np.einsum("ij,ij->i", nrm, g))
     assert rc == _abi.OK and np.median(cosang) > 0.9999 and (cosang > 0.999).mean() > 0.97
+
+
+ROBUST_CASES = [
+    ("point_to_plane", 1, dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),                      # libpointmatcher's defaults
+    ("point_to_plane", 2, dict(robustFct="huber", tuning=1.5, scaleEstimator="mad", nbIterationForScale=3)),
+    ("point_to_point", 1, dict(robustFct="tukey", tuning=3.0, scaleEstimator="none", approximation=0.9)),
+    ("point_to_plane", 1, dict(robustFct="cauchy", tuning=0.05, scaleEstimator="berg")),
+    ("point_to_plane", 1, dict(robustFct="welsch", tuning=2.0, scaleEstimator="mad", distanceType="point2plane")),
+    ("point_to_point", 3, dict(robustFct="gm", tuning=1.0, scaleEstimator="mad")),
+    ("point_to_plane", 1, dict(robustFct="sc", tuning=1.0, scaleEstimator="mad", distanceType="point2plane")),
+    ("point_to_plane", 1, dict(robustFct="student", tuning=2.0, scaleEstimator="mad")),
+    ("point_to_plane", 1, dict(robustFct="L1", tuning=1.0, scaleEstimator="none")),  # (1 / |e| is unbounded: point2plane would hinge on near-zero residuals)
+]
+
+
+@pytest.mark.parametrize("minimizer,knn,rp", ROBUST_CASES)
+def test_robust_outlier_filter_agrees_with_numpy_second_opinion(oracle, pair3d, minimizer, knn, rp):
+    """RobustOutlierFilter: every weight function, scale estimator and distance type against the fp64 numpy statement."""
+    outliers = (("robust", rp),)
+    cfg = make_config(dim=3, knn=knn, max_dist=1.0, outliers=outliers, minimizer=minimizer, max_iteration_count=10)
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair3d)
+    assert rc == _abi.OK
+    T_np = numpy_icp.icp(pair3d["map"][:, :3], pair3d["normals"], pair3d["reading"][:, :3], knn_k=knn, max_dist=1.0,
+                         outliers=outliers, minimizer=minimizer, iterations=10)
+    er, et = synth.pose_error(T, T_np)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    if rp["robustFct"] != "L1":  # weights <= 1 for the others: the weighted ratio is below the kept ratio
+        assert 0.0 < res.overlap < res.point_used_ratio <= 1.0
+
+
+def test_robust_scale_estimators(oracle, pair3d):
+    """mad / std / berg scales of the first iteration against numpy on the oracle's own first matches."""
+    base = dict(dim=3, knn=2, max_dist=float("inf"), minimizer="point_to_plane", max_iteration_count=1)
+    o = oracle.OracleICP(make_config(outliers=(), **base))
+    o.set_map(pair3d["map"], pair3d["normals"])
+    rc, ids, d2 = o.match(pair3d["reading"])
+    fin = np.sort(d2[np.isfinite(d2)].astype(np.float64))
+    med = fin[len(fin) // 2]
+    want = {"mad": np.sqrt(np.sort(np.abs(fin - med))[len(fin) // 2]), "std": np.sqrt(np.std(d2.astype(np.float64), ddof=1)),
+            "berg": 1.9 * np.sqrt(med), "none": 1.0}
+    for est, expect in want.items():
+        o = oracle.OracleICP(make_config(outliers=(("robust", dict(scaleEstimator=est, tuning=0.05)),), **base))
+        o.set_map(pair3d["map"], pair3d["normals"])
+        rc = o.register(pair3d["reading"])[0]
+        assert rc == _abi.OK
+        assert o.last_robust_scale() == pytest.approx(expect, rel=2e-5), est
+    # berg from the second iteration on: scale <- 0.85 (scale - target) + target
+    o = oracle.OracleICP(make_config(outliers=(("robust", dict(scaleEstimator="berg", tuning=0.05)),), **dict(base, max_iteration_count=3)))
+    o.set_map(pair3d["map"], pair3d["normals"])
+    assert o.register(pair3d["reading"])[0] == _abi.OK
+    s = want["berg"]
+    for _ in range(2):
+        s = 0.85 * (s - 0.05) + 0.05
+    assert o.last_robust_scale() == pytest.approx(s, rel=2e-5)
+
+
+def test_robust_point2plane_needs_reference_normals(oracle, pair3d):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("robust", dict(distanceType="point2plane")),), minimizer="point_to_point",
+                      max_iteration_count=3)
+    o = oracle.OracleICP(cfg)
+    o.set_map(pair3d["map"], None)
+    assert o.register(pair3d["reading"])[0] == _abi.ERR_INVALID_FIELD
