@@ -47,6 +47,13 @@ struct Acc1 {
             }
         }
     }
+    // one candidate per lane (cd = inf: none)
+    __device__ __forceinline__ void consume(float cd, uint32_t j, int, unsigned, float) {
+        if (cd < d || (cd == d && j < (uint32_t)pos)) {
+            d = cd;
+            pos = (int)j;
+        }
+    }
     // squared radius beyond which nothing can improve the result
     __device__ __forceinline__ float tau(unsigned gmask, float max_r2) const {
         float v = d;
@@ -98,46 +105,47 @@ struct AccK {
         margin = margin_;
         sd = CUDART_INF_F;
     }
+    // one candidate per lane (cd = inf: none), taken in lane order: ballot-driven insertion into the group's sorted list
+    __device__ __forceinline__ void consume(float cd, uint32_t j, int lig, unsigned gmask, float max_r2) {
+        bool pass = (cd < kth) && (cd <= max_r2);
+        if (TRACK && !pass) sd = fminf(sd, cd);
+        unsigned m = __ballot_sync(gmask, pass) & gmask;
+        while (m) {
+            const int src = __ffs(m) - 1;  // absolute lane
+            const float nd = __shfl_sync(gmask, cd, src);
+            const int np = (int)__shfl_sync(gmask, j, src);
+            if (TRACK) sd = fminf(sd, __shfl_sync(gmask, d, k - 1, G));  // the entry this insertion pushes out (inf: list not full)
+            // rank of the newcomer = entries <= nd (stable: goes after equal distances)
+            const unsigned le = __ballot_sync(gmask, d <= nd) & gmask;
+            const int r = __popc(le);
+            const float pd = __shfl_up_sync(gmask, d, 1, G);
+            const int pp = __shfl_up_sync(gmask, pos, 1, G);
+            if (lig == r) {
+                d = nd;
+                pos = np;
+            } else if (lig > r) {
+                d = pd;
+                pos = pp;
+            }
+            if (lig >= k) {
+                d = CUDART_INF_F;
+                pos = -1;
+            }
+            kth = fminf(bound, __shfl_sync(gmask, d, k - 1, G));
+            m &= m - 1;
+            const bool still = pass && lig != (src & (G - 1)) && (cd < kth);  // (the lane just served is done: its point is in the list)
+            if (TRACK && pass && !still && lig != (src & (G - 1))) sd = fminf(sd, cd);  // overtaken before its turn came
+            pass = still;
+            m &= __ballot_sync(gmask, pass);
+        }
+    }
     __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz,
                                          int lig, unsigned gmask, float max_r2) {
         for (uint32_t j0 = s; j0 < e; j0 += G) {
             const uint32_t j = j0 + lig;
             float cd = CUDART_INF_F;
-            if (j < e) {
-                const float4 p = __ldg(pts + j);
-                cd = dist2_exact(qx, qy, qz, p);
-            }
-            bool pass = (cd < kth) && (cd <= max_r2);
-            if (TRACK && !pass) sd = fminf(sd, cd);
-            unsigned m = __ballot_sync(gmask, pass) & gmask;
-            while (m) {
-                const int src = __ffs(m) - 1;  // absolute lane
-                const float nd = __shfl_sync(gmask, cd, src);
-                const int np = (int)(j0 + (uint32_t)(src & (G - 1)));
-                if (TRACK) sd = fminf(sd, __shfl_sync(gmask, d, k - 1, G));  // the entry this insertion pushes out (inf: list not full)
-                // rank of the newcomer = entries <= nd (stable: goes after equal distances)
-                const unsigned le = __ballot_sync(gmask, d <= nd) & gmask;
-                const int r = __popc(le);
-                const float pd = __shfl_up_sync(gmask, d, 1, G);
-                const int pp = __shfl_up_sync(gmask, pos, 1, G);
-                if (lig == r) {
-                    d = nd;
-                    pos = np;
-                } else if (lig > r) {
-                    d = pd;
-                    pos = pp;
-                }
-                if (lig >= k) {
-                    d = CUDART_INF_F;
-                    pos = -1;
-                }
-                kth = fminf(bound, __shfl_sync(gmask, d, k - 1, G));
-                m &= m - 1;
-                const bool still = pass && (cd < kth);
-                if (TRACK && pass && !still && lig != (src & (G - 1))) sd = fminf(sd, cd);  // overtaken before its turn came
-                pass = still;
-                m &= __ballot_sync(gmask, pass);
-            }
+            if (j < e) cd = dist2_exact(qx, qy, qz, __ldg(pts + j));
+            consume(cd, j, lig, gmask, max_r2);
         }
     }
     __device__ __forceinline__ float tau(unsigned, float max_r2) const {
@@ -202,14 +210,42 @@ __device__ __forceinline__ void visit_shell(const GridView& g, Acc& acc, float q
                 }
             }
         }
-        unsigned m = __ballot_sync(gmask, (e1 > s1) || (e2 > s2)) & gmask;
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t a1 = __shfl_sync(gmask, s1, src), b1 = __shfl_sync(gmask, e1, src);
-            const uint32_t a2 = __shfl_sync(gmask, s2, src), b2 = __shfl_sync(gmask, e2, src);
-            if (b1 > a1) acc.scan(g.pts, a1, b1, qx, qy, qz, lig, gmask, max_r2);
-            if (b2 > a2) acc.scan(g.pts, a2, b2, qx, qy, qz, lig, gmask, max_r2);
+        // The (up to 2 G) runs of this chunk of rows are consumed as ONE flat sequence, G points at a time in the same order
+        // a run-by-run scan would take them (rows in lane order, x ascending): every batch keeps all G lanes busy whatever
+        // the run lengths, and the next batch's points are already in flight while the current one is inserted -- the
+        // search is a chain of dependent L2 round trips, one per batch instead of one or more per run.
+        const uint32_t len1 = e1 > s1 ? e1 - s1 : 0u, len2 = e2 > s2 ? e2 - s2 : 0u;
+        uint32_t incl = len1 + len2;
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(gmask, incl, o, G);
+            if (lig >= o) incl += v;
+        }
+        const uint32_t excl = incl - (len1 + len2);
+        const uint32_t total = __shfl_sync(gmask, incl, G - 1, G);
+        if (total == 0u) continue;  // group-uniform
+        auto locate = [&](uint32_t t) -> uint32_t {  // flat index -> point position (t clamped by the caller)
+            int r = 0;  // largest lane with excl <= t
+#pragma unroll
+            for (int step = G / 2; step > 0; step >>= 1) {
+                const uint32_t ex = __shfl_sync(gmask, excl, r + step, G);
+                if (ex <= t) r += step;
+            }
+            const uint32_t off = t - __shfl_sync(gmask, excl, r, G);
+            const uint32_t rs1 = __shfl_sync(gmask, s1, r, G), rl1 = __shfl_sync(gmask, len1, r, G), rs2 = __shfl_sync(gmask, s2, r, G);
+            return off < rl1 ? rs1 + off : rs2 + (off - rl1);
+        };
+        uint32_t jn = locate(min((uint32_t)lig, total - 1u));
+        float4 pn = __ldg(g.pts + jn);
+        for (uint32_t t0 = 0; t0 < total; t0 += G) {
+            const float4 pc = pn;
+            const uint32_t jc = jn;
+            const bool valid = t0 + (uint32_t)lig < total;
+            if (t0 + G < total) {  // group-uniform
+                jn = locate(min(t0 + G + (uint32_t)lig, total - 1u));
+                pn = __ldg(g.pts + jn);
+            }
+            acc.consume(valid ? dist2_exact(qx, qy, qz, pc) : CUDART_INF_F, jc, lig, gmask, max_r2);
         }
     }
 }
@@ -252,6 +288,23 @@ __device__ __forceinline__ void search_shells(const GridView& g, Acc& acc, float
         Rprev = R;
         R = R + 1;
     }
+}
+
+// Warm search for k > 1 (loop.cu): k real map points are known to lie within acc.bound of the query, so ONE pass over the
+// cells that intersect the ball of radius sqrt(min(bound, maxDist^2)) + margin sees everything that matters -- no shell walk,
+// no exit test.  On return every map point within that radius has been offered to the accumulator.
+template <int G, typename Acc>
+__device__ __forceinline__ void search_ball_k(const GridView& g, Acc& acc, float qx, float qy, float qz, float max_r2, int lig,
+                                              unsigned gmask) {
+    const float lim = 1.0e8f;
+    const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
+    const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
+    const float uz = fminf(fmaxf((qz - g.oz) * g.inv_h, -lim), lim);
+    const int cx = floor_to_int(ux), cy = floor_to_int(uy), cz = floor_to_int(uz);
+    const float slack = g.slack + 1e-6f * (fabsf(ux) + fabsf(uy) + fabsf(uz));
+    const float tau = acc.tau(gmask, max_r2);
+    const int R = (int)fminf(sqrtf(tau) * g.inv_h + slack + 2.f, 1.0e6f);  // Chebyshev cell radius that contains the ball
+    visit_shell<G, Acc>(g, acc, qx, qy, qz, ux, uy, uz, cx, cy, cz, R, -1, tau, slack, max_r2, lig, gmask);
 }
 
 // Warm search (k = 1, ICP iterations >= 1): the previous iteration's match is a real map point, so

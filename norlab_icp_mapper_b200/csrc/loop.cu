@@ -390,7 +390,11 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         if (dj < CUDART_INF_F) bound = __uint_as_float(__float_as_uint(dj) + 1u);  // next float up: ties with the bound stay accepted
                         AccK<GK, true> acc;
                         acc.init(K, bound, m);
-                        search_shells<GK, AccK<GK, true>>(g, acc, qn.x, qn.y, qn.z, prm.max_r2, 0, ligk, gmaskk);
+                        // all k cached matches still within maxDist: the ball they bound is searched in one pass
+                        if (dj <= prm.max_r2 && !(variant_flags & 128))
+                            search_ball_k<GK, AccK<GK, true>>(g, acc, qn.x, qn.y, qn.z, prm.max_r2, ligk, gmaskk);
+                        else
+                            search_shells<GK, AccK<GK, true>>(g, acc, qn.x, qn.y, qn.z, prm.max_r2, 0, ligk, gmaskk);
                         float gsd = acc.sd;
 #pragma unroll
                         for (int o = GK / 2; o > 0; o >>= 1) gsd = fminf(gsd, __shfl_xor_sync(gmaskk, gsd, o));

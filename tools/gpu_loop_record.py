@@ -6,10 +6,18 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from norlab_icp_mapper_b200 import synth
 from norlab_icp_mapper_b200.icp import ICP, make_config
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-d = synth.make_pair_3d()
-cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30, nn_variant=variant)
-g = ICP(cfg); g.set_map(d["map"], d["normals"])
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+variant = int(args[0]) if args else 0
+if "--cfg1" in sys.argv:
+    d = synth.make_pair_3d(n_map=41_400, n_scan=41_339, world_size=(120.0, 120.0), n_boxes=14, scan_radius=60.0, dt=(0.10, -0.05, 0.02), drpy_deg=(0, 0, 1.0))
+    cfg = make_config(dim=3, knn=6, max_dist=2.0, outliers=(), minimizer="point_to_plane", max_iteration_count=10, nn_variant=variant)
+elif "--cfg4" in sys.argv:
+    d = synth.make_pair_2d()
+    cfg = make_config(dim=2, knn=8, max_dist=0.5, outliers=(), minimizer="point_to_point", max_iteration_count=30, nn_variant=variant)
+else:
+    d = synth.make_pair_3d()
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30, nn_variant=variant)
+g = ICP(cfg); g.set_map(d["map"], d.get("normals"))
 for _ in range(3):
     g(d["reading"])
 rec = np.zeros((30, 8), np.uint32)
