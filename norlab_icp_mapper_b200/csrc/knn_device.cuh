@@ -210,6 +210,20 @@ __device__ __forceinline__ void visit_shell(const GridView& g, Acc& acc, float q
                 }
             }
         }
+        if (g.nz == 1) {
+            // 2-D maps: a shell has few rows and their runs are long -- run by run, G points at a time (flattening them, as
+            // below, costs more in bookkeeping than it saves: cfg 4 + 5 %)
+            unsigned mrun = __ballot_sync(gmask, (e1 > s1) || (e2 > s2)) & gmask;
+            while (mrun) {
+                const int src = __ffs(mrun) - 1;
+                mrun &= mrun - 1;
+                const uint32_t a1 = __shfl_sync(gmask, s1, src), b1 = __shfl_sync(gmask, e1, src);
+                const uint32_t a2 = __shfl_sync(gmask, s2, src), b2 = __shfl_sync(gmask, e2, src);
+                if (b1 > a1) acc.scan(g.pts, a1, b1, qx, qy, qz, lig, gmask, max_r2);
+                if (b2 > a2) acc.scan(g.pts, a2, b2, qx, qy, qz, lig, gmask, max_r2);
+            }
+            continue;
+        }
         // The (up to 2 G) runs of this chunk of rows are consumed as ONE flat sequence, G points at a time in the same order
         // a run-by-run scan would take them (rows in lane order, x ascending): every batch keeps all G lanes busy whatever
         // the run lengths, and the next batch's points are already in flight while the current one is inserted -- the
