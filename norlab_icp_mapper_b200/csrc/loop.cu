@@ -36,7 +36,10 @@ namespace {
 constexpr int kLoopThreads = 1024;
 constexpr int kLoopWarps = kLoopThreads / 32;
 constexpr int kLoopG = 4;                       // lanes per query in the search phase
-constexpr int kChunk = 32;                      // reading points are dealt to the CTAs in chunks of 32 consecutive points (balance)
+// reading points are dealt to the CTAs round-robin in chunks of 32 consecutive points, 8 for small readings (balance: with
+// 32 a 10 k-point reading gives 17 of the 148 CTAs 96 points and the others 64, and everybody waits for those 17)
+constexpr int kChunkShiftLarge = 5, kChunkShiftSmall = 3;
+constexpr int kSmallReading = 64 * 1024;
 constexpr int kCacheCap = 2048;                 // queries per CTA whose match state lives in shared memory (the rest spills to global)
 // dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[cap]
 constexpr size_t kLoopDynSmem = (size_t)kCacheCap * (3 * sizeof(float4) + sizeof(float) + sizeof(uint32_t));
@@ -252,13 +255,15 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
+    const int cshift = (nq <= kSmallReading || (variant_flags & 512)) ? kChunkShiftSmall : kChunkShiftLarge;
+    const int kChunk = 1 << cshift;
     // This CTA's slice: n_ql reading points (chunks of kChunk consecutive points, dealt round-robin: only the globally last
     // chunk is partial, so local query ql <-> reading point qi_of(ql) is contiguous) and K entries each -- one per neighbour.
     // Entry e = ql * K + j <-> row `pair_of(e)` of the match arrays (ids[i * knn + j] layout).  K = 1: entries are the points.
     const int K = prm.knn;
     int n_ql = 0;
     {
-        const long long chunks_total = ((long long)nq + kChunk - 1) / kChunk;
+        const long long chunks_total = ((long long)nq + kChunk - 1) >> cshift;
         if ((long long)blockIdx.x < chunks_total) {
             const long long mine = (chunks_total - 1 - blockIdx.x) / gridDim.x + 1;
             n_ql = (int)(mine * kChunk);
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         }
     }
     const int n_ent = n_ql * K;
-    auto qi_of = [&](int ql) -> long long { return ((long long)(ql / kChunk) * gridDim.x + blockIdx.x) * kChunk + (ql % kChunk); };
+    auto qi_of = [&](int ql) -> long long { return (((long long)(ql >> cshift) * gridDim.x + blockIdx.x) << cshift) + (ql & (kChunk - 1)); };
     auto pair_of = [&](int e) -> long long { return K == 1 ? qi_of(e) : qi_of(e / K) * K + (e % K); };
     // match cache <- the cold search's matches (bound L = 0: nothing proven yet)
     for (int e = tid; e < n_ent; e += kLoopThreads) {
