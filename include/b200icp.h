@@ -136,6 +136,7 @@ typedef struct b200icp_config {
                              bit 7 (128) loop kernel: work list in plain entry order (no cost classes); k > 1: shell walk instead of the ball pass
                              bit 8 (256) cold k = 1 search: shell-walk kernel even when maxDist is small
                              bit 9 (512) loop kernel: deal the reading to the CTAs in chunks of 8 points whatever its size
+                             bits 10..11 loop kernel: value - 1 = log2 of that chunk size (1, 2, 4 points)
                              bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3) */
     int32_t outlier_mode[B200ICP_MAX_OUTLIER_FILTERS]; /* per filter: B200ICP_ROBUST_MODE(...) for RobustOutlierFilter, else 0 */
     int32_t reserved[1];

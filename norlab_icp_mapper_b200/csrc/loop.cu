@@ -39,7 +39,7 @@ constexpr int kLoopG = 4;                       // lanes per query in the search
 // reading points are dealt to the CTAs round-robin in chunks of 32 consecutive points, 8 for small readings (balance: with
 // 32 a 10 k-point reading gives 17 of the 148 CTAs 96 points and the others 64, and everybody waits for those 17)
 constexpr int kChunkShiftLarge = 5, kChunkShiftSmall = 3;
-constexpr int kSmallReading = 64 * 1024;
+constexpr int kSmallReading = 64 * 1024, kTinyReading = 16 * 1024;
 constexpr int kCacheCap = 2048;                 // queries per CTA whose match state lives in shared memory (the rest spills to global)
 // dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[cap]
 constexpr size_t kLoopDynSmem = (size_t)kCacheCap * (3 * sizeof(float4) + sizeof(float) + sizeof(uint32_t));
@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
-    const int cshift = (nq <= kSmallReading || (variant_flags & 512)) ? kChunkShiftSmall : kChunkShiftLarge;
+    int cshift = (nq <= kSmallReading || (variant_flags & 512)) ? kChunkShiftSmall : kChunkShiftLarge;
+    if (nq <= kTinyReading) cshift = 0;  // plain round-robin (cfg 4, 10 k points: another -3.6 %)
+    if ((variant_flags >> 10) & 3) cshift = ((variant_flags >> 10) & 3) - 1;  // development: chunks of 1 / 2 / 4
     const int kChunk = 1 << cshift;
     // This CTA's slice: n_ql reading points (chunks of kChunk consecutive points, dealt round-robin: only the globally last
     // chunk is partial, so local query ql <-> reading point qi_of(ql) is contiguous) and K entries each -- one per neighbour.

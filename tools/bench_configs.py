@@ -11,6 +11,7 @@ from norlab_icp_mapper_b200.mapper import Mapper
 
 out = {}
 quick = "--quick" in sys.argv
+small = "--only-small" in sys.argv  # configs 1 and 4 only
 
 
 def time_pair(label, d, cfg, reps=10, oracle_reps=2):
@@ -45,11 +46,11 @@ if not only3: time_pair("cfg1_knn6_41k", d, make_config(dim=3, knn=6, max_dist=2
 d2 = None if only3 else synth.make_pair_2d()
 if not only3: time_pair("cfg4_2d_knn8", d2, make_config(dim=2, knn=8, max_dist=0.5, outliers=(), minimizer="point_to_point", max_iteration_count=30))
 # config 2 for reference
-if not quick and not only3:
+if not quick and not only3 and not small:
     time_pair("cfg2", synth.make_pair_3d(), make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30))
 
 # config 5: batched pairs (200k scan vs 1M submap) on this GPU; 8 pairs = one GPU's share of the 64
-n_pairs = 0 if only3 else (4 if quick else 8)
+n_pairs = 0 if (only3 or small) else (4 if quick else 8)
 cfg5 = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)
 pairs = [synth.make_pair_3d(n_map=1_000_000, n_scan=200_000, seed=4000 + j) for j in range(n_pairs)]
 if n_pairs:
@@ -67,6 +68,10 @@ if n_pairs:
 if n_pairs: print("cfg5", json.dumps(out["cfg5_batched"]), flush=True)
 
 # config 3: online mapping through the host mirror of Mapper::processInput
+if small:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_small.json"), "w"), indent=1)
+    sys.exit(0)
 n_scans = 30 if quick else 120
 for a in sys.argv:
     if a.startswith("--cfg3-scans="):
@@ -101,7 +106,7 @@ err = synth.pose_error(pose_est, T_true)
 out["cfg3_online"] = dict(scans=n_scans, scans_per_s=n_scans / sum(times), ms_per_scan_median=1e3 * float(np.median(times)),
                           ms_per_update_scan=1e3 * float(np.mean([t for t, u in zip(times, upd) if u])), updates=int(sum(upd)),
                           ms_per_scan_p95=1e3 * float(np.percentile(times, 95)), ms_per_scan_mean=1e3 * float(np.mean(times)),
-                          ms_slowest_scans=[round(1e3 * t, 1) for t in sorted(times)[-5:]], ms_per_scan_last50=1e3 * float(np.mean(times[-50:])),
+                          ms_slowest_scans=[round(1e3 * t, 1) for t in sorted(times)[-5:]], slowest_scan_indices=[int(i) for i in np.argsort(times)[-5:]], ms_per_scan_last50=1e3 * float(np.mean(times[-50:])),
                           final_local=sizes[-1][0], final_global=sizes[-1][1], drift_rad=err[0], drift_m=err[1],
                           note="whole Mapper::processInput per scan through the host mirror (upload, input filters, ICP with Counter{30} + "
                                "Differential, PointDistance insert, SurfaceNormal knn 10 over the local map, index rebuild); every scan updates the map")
