@@ -284,8 +284,11 @@ int32_t b200icp_cloud_surface_normals(b200icp_ctx* ctx, const float* features, i
  * loading sets it again.  Does not rebuild the index (call b200icp_map_commit). */
 int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed);
 
-/* Pre-size the device buffers for a map of n_points (and, if normals_knn > 0, the self-k-NN scratch of
- * b200icp_map_surface_normals): an online map then grows without cudaMalloc stalls.  Optional. */
+/* Pre-size the device buffers for a map of n_points: the point store and its compaction scratch, the index (points,
+ * normals, cell table, sort scratch), the auxiliary index the update steps build over the changed points and, if
+ * normals_knn > 0, the self-k-NN scratch and bookkeeping of b200icp_map_surface_normals.  An online map then grows
+ * without cudaMalloc / cudaFree on the update path (a cudaFree next to gigabytes of live buffers was measured at
+ * 70-870 ms; B200ICP_TRACE_ALLOC=1 reports every allocation and release on stderr).  Optional. */
 int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_knn);
 
 /* icp.setMap(localPointCloud): rebuild the index over the loaded points.  An empty local cloud is

@@ -899,24 +899,53 @@ int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_
     CK(cudaSetDevice(ctx->device));
     const int dim = ctx->cfg.dim;
     CK(store_reserve(ctx->store, dim, n_points, ctx->stream));
-    CK(ensure_scratch(ctx->map, n_points));
-    if (n_points > ctx->map.cap_pts) {
-        cudaFree(ctx->map.pts);
-        ctx->map.pts = nullptr;
-        ctx->map.cap_pts = 0;
-        CK(cudaMalloc((void**)&ctx->map.pts, (size_t)grow_capacity(n_points) * sizeof(float4)));
-        ctx->map.cap_pts = grow_capacity(n_points);
-    }
-    if (n_points > ctx->map.cap_normals) {
-        cudaFree(ctx->map.normals);
-        ctx->map.normals = nullptr;
-        ctx->map.cap_normals = 0;
-        CK(cudaMalloc((void**)&ctx->map.normals, (size_t)grow_capacity(n_points) * sizeof(float4)));
-        ctx->map.cap_normals = grow_capacity(n_points);
-    }
+    CK(store_reserve_scratch(ctx->store, n_points));
+    // Index buffers: the map's own grid, and the auxiliary grid the update steps build over the changed points (a window move
+    // changes up to a quarter of the local map at once).  Releasing any of them later is a cudaFree on the update path, and
+    // a cudaFree next to gigabytes of reserved buffers was measured at 70-870 ms (B200ICP_TRACE_ALLOC=1).
+    auto reserve_grid = [&](GridIndex& g, int64_t n, bool with_normals) -> int32_t {
+        CK(ensure_scratch(g, n));
+        if (n > g.cap_pts) {
+            cudaFree(g.pts);
+            g.pts = nullptr;
+            g.cap_pts = 0;
+            CK(cudaMalloc((void**)&g.pts, (size_t)grow_capacity(n) * sizeof(float4)));
+            g.cap_pts = grow_capacity(n);
+        }
+        if (with_normals && n > g.cap_normals) {
+            cudaFree(g.normals);
+            g.normals = nullptr;
+            g.cap_normals = 0;
+            CK(cudaMalloc((void**)&g.normals, (size_t)grow_capacity(n) * sizeof(float4)));
+            g.cap_normals = grow_capacity(n);
+        }
+        const int64_t want_cells = std::min<int64_t>(4 * n + 2, (int64_t)kMaxCells + 2);  // about 4 cells per point, capped
+        if (want_cells > g.cap_cells) {
+            cudaFree(g.cell_start);
+            g.cell_start = nullptr;
+            g.cap_cells = 0;
+            CK(cudaMalloc((void**)&g.cell_start, (size_t)want_cells * sizeof(uint32_t)));
+            g.cap_cells = want_cells;
+        }
+        return B200ICP_OK;
+    };
+    int32_t rg = reserve_grid(ctx->map, n_points, true);
+    if (rg != B200ICP_OK) return rg;
+    rg = reserve_grid(ctx->aux, std::max<int64_t>(n_points / 4, 1), false);
+    if (rg != B200ICP_OK) return rg;
     if (normals_knn > 0) {
         const int32_t eb = ensure_query_buffers(ctx, n_points, normals_knn);
         if (eb != B200ICP_OK) return eb;
+        // bookkeeping of the incremental SurfaceNormal pass (b200icp_map_surface_normals)
+        if (n_points > ctx->cap_kth && !ctx->d_kth) {
+            CK(cudaMalloc((void**)&ctx->d_kth, (size_t)n_points * sizeof(float)));
+            ctx->cap_kth = n_points;
+        }
+        if (2 * n_points > ctx->cap_dirty && !ctx->d_dirty && !ctx->d_list) {
+            CK(cudaMalloc((void**)&ctx->d_dirty, (size_t)(2 * n_points)));
+            CK(cudaMalloc((void**)&ctx->d_list, (size_t)(2 * n_points) * sizeof(uint32_t)));
+            ctx->cap_dirty = 2 * n_points;
+        }
     }
     return B200ICP_OK;
 }

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <chrono>
 
 #include "b200icp.h"
 
@@ -14,6 +16,31 @@ constexpr int kSMs = 148;        // B200
 // Capacity policy of every growing device buffer: double, never below 1 Mi elements.  cudaMalloc /
 // cudaFree of multi-hundred-MB buffers cost 100+ ms and synchronise the device, so a growing online
 // map must hit them O(log N) times, not every few scans.
+// B200ICP_TRACE_ALLOC=1: every device allocation / release of the library is reported on stderr with its size, call site
+// and host time (development aid: where an online map update stalls).
+inline bool trace_alloc_enabled() {
+    static const bool on = [] { const char* e = getenv("B200ICP_TRACE_ALLOC"); return e && e[0] == '1'; }();
+    return on;
+}
+inline cudaError_t traced_malloc(void** p, size_t bytes, const char* file, int line) {
+    if (!trace_alloc_enabled()) return cudaMalloc(p, bytes);
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaMalloc(p, bytes);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[b200icp alloc] cudaMalloc %10.2f MB %8.3f ms  %s:%d\n", bytes / 1048576.0, ms, file, line);
+    return e;
+}
+inline cudaError_t traced_free(void* p, const char* file, int line) {
+    if (!trace_alloc_enabled() || !p) return cudaFree(p);
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = cudaFree(p);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[b200icp alloc] cudaFree                 %8.3f ms  %s:%d\n", ms, file, line);
+    return e;
+}
+#define cudaMalloc(p, bytes) ::b200::traced_malloc((void**)(p), (bytes), __FILE__, __LINE__)
+#define cudaFree(p) ::b200::traced_free((void*)(p), __FILE__, __LINE__)
+
 inline int64_t grow_capacity(int64_t n) { return n * 2 > (int64_t(1) << 20) ? n * 2 : (int64_t(1) << 20); }
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
@@ -181,6 +208,7 @@ struct MapStore {
 };
 void store_free(MapStore& m);
 cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s);
+cudaError_t store_reserve_scratch(MapStore& m, int64_t n);
 cudaError_t store_set(MapStore& m, const float* d_in, int rows, int dim, const float* d_normals, int64_t n, cudaStream_t s);
 cudaError_t store_compact_active(MapStore& m, GridIndex& scratch, cudaStream_t s);
 cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* changed, cudaStream_t s);

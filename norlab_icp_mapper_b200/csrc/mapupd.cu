@@ -339,6 +339,9 @@ static cudaError_t ensure_tmp(MapStore& m, int64_t n) {
     return cudaSuccess;
 }
 
+// b200icp_map_reserve: the compaction scratch of the update steps, sized once (its regrowth cudaFree stalls the update path)
+cudaError_t store_reserve_scratch(MapStore& m, int64_t n) { return ensure_tmp(m, n + 1); }
+
 static cudaError_t exclusive_sum(GridIndex& scratch, const uint32_t* in, uint32_t* out, int64_t n, cudaStream_t s) {
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n);

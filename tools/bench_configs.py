@@ -96,6 +96,8 @@ for i in range(n_scans):
     t0 = time.perf_counter()
     m.processInput(scan, T_est.astype(np.float32), 0.1 * i)
     times.append(time.perf_counter() - t0)
+    if os.environ.get("B200ICP_TRACE_ALLOC"):
+        print(f"[scan {i}] {1e3 * times[-1]:.1f} ms", file=sys.stderr, flush=True)
     pose_est = m.getPose().astype(np.float64)
     T_prev_true = T_true
     st = m.stats()
@@ -106,7 +108,7 @@ err = synth.pose_error(pose_est, T_true)
 out["cfg3_online"] = dict(scans=n_scans, scans_per_s=n_scans / sum(times), ms_per_scan_median=1e3 * float(np.median(times)),
                           ms_per_update_scan=1e3 * float(np.mean([t for t, u in zip(times, upd) if u])), updates=int(sum(upd)),
                           ms_per_scan_p95=1e3 * float(np.percentile(times, 95)), ms_per_scan_mean=1e3 * float(np.mean(times)),
-                          ms_slowest_scans=[round(1e3 * t, 1) for t in sorted(times)[-5:]], slowest_scan_indices=[int(i) for i in np.argsort(times)[-5:]], ms_per_scan_last50=1e3 * float(np.mean(times[-50:])),
+                          ms_slowest_scans=[round(1e3 * t, 1) for t in sorted(times)[-5:]], slowest_scan_indices=[int(i) for i in np.argsort(times)[-5:]], ms_first_scans=[round(1e3 * t, 1) for t in times[:12]], ms_per_scan_last50=1e3 * float(np.mean(times[-50:])),
                           final_local=sizes[-1][0], final_global=sizes[-1][1], drift_rad=err[0], drift_m=err[1],
                           note="whole Mapper::processInput per scan through the host mirror (upload, input filters, ICP with Counter{30} + "
                                "Differential, PointDistance insert, SurfaceNormal knn 10 over the local map, index rebuild); every scan updates the map")
