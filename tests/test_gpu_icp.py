@@ -229,6 +229,32 @@ def test_large_reading_spills_the_match_cache(oracle):
     assert outs[0][1] == res_o.pairs_last_iter
 
 
+def test_k_gt_1_spills_the_match_cache(oracle):
+    """k > 1 in the loop kernel keeps one cache entry per (reading point, neighbour) pair: 130 k points x knn 3 are
+    2 637 entries per CTA, beyond the 2 048 that fit in shared memory, so entries (and some points' k entries only in
+    part) live in the global spill arrays.  Same pose and kept pairs as the kernel-per-step path and as the oracle;
+    disabling the verification changes nothing."""
+    from norlab_icp_mapper_b200.icp import ICP
+    d = synth.make_pair_3d(n_map=200_000, n_scan=130_000, seed=78)
+    base = dict(dim=3, knn=3, max_dist=1.0, outliers=(("trimmed", 0.8),), minimizer="point_to_plane", max_iteration_count=8)
+    outs = {}
+    for variant in (0, 32, 4):
+        g = ICP(make_config(nn_variant=variant, **base))
+        g.set_map(d["map"], d["normals"])
+        outs[variant] = (g(d["reading"]), g.last_result.pairs_last_iter, g.last_result.overlap)
+        g.close()
+    assert outs[0][1:] == outs[32][1:] == outs[4][1:]
+    for v in (32, 4):
+        er, et = synth.pose_error(outs[0][0], outs[v][0])
+        assert er <= 1e-6 and et <= 1e-5, (v, er, et)
+    o = oracle.OracleICP(make_config(**base))
+    o.set_map(d["map"], d["normals"])
+    rc, T_o, res_o, _, _ = o.register(d["reading"])
+    er, et = synth.pose_error(outs[0][0], T_o)
+    assert rc == _abi.OK and er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert abs(outs[0][1] - res_o.pairs_last_iter) <= 2
+
+
 def test_surface_normal_outlier_filter(oracle, pair3d):
     """SurfaceNormalOutlierFilter{maxAngle} (a staple of norlab's configurations, next to TrimmedDist): pairs whose
     reading normal -- carried through icp(input) and rotated with the reading -- and map normal disagree by more than
