@@ -330,7 +330,7 @@ def run_b200(args):
             "device_ms_per_step": dev_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "icp_loop_kernel<0> (persistent cooperative kernel, one launch per registration: iterations 1..%d "
+                         "kernel": "icp_loop_kernel<0, 4> (persistent cooperative kernel, one launch per registration: iterations 1..%d "
                                    "of search + outlier quantile + error sums + solve)" % (iterations_run - 1),
                          "algorithmic_bytes": b_loop, "avg_launch_us": loop_kernel_ms * 1e3, "launches_timed": loop_n,
                          "peak_source": peak_src,
