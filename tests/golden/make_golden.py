@@ -85,10 +85,15 @@ def main():
                          minimizer="point_to_plane", iterations=30)
     T_p2p = numpy_icp.icp(map_pts, normals, reading, knn_k=1, max_dist=2.0, outliers=(("trimmed", 0.85),),
                           minimizer="point_to_point", iterations=30)
+    # (the clouds go through float32 in the file: the robust correction is computed from what the file holds)
+    m32, r32 = synth.homog(map_pts)[:, :3].astype(np.float64), synth.homog(reading)[:, :3].astype(np.float64)
+    T_rob = numpy_icp.icp(m32, normals.astype(np.float32), r32, knn_k=1, max_dist=2.0,
+                          outliers=(("robust", dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),),
+                          minimizer="point_to_plane", iterations=10)
     out = os.path.join(HERE, "example_pair.npz")
     np.savez_compressed(out, map=synth.homog(map_pts), normals=normals.astype(np.float32), reading=synth.homog(reading),
                         knn6_ids=ids6.astype(np.int32), knn6_d2=d6, knn1_ids=ids1.astype(np.int32), knn1_d2=d1,
-                        T_plane_k6_it10=T_k6, T_plane_trim_it30=T_k1, T_point_trim_it30=T_p2p,
+                        T_plane_k6_it10=T_k6, T_plane_trim_it30=T_k1, T_point_trim_it30=T_p2p, T_plane_robust_cauchy_mad_it10=T_rob,
                         scan_files=np.array(files[:2]))
     print("wrote", out, os.path.getsize(out), "bytes")
     print("correction k6:\n", T_k6)

@@ -65,7 +65,9 @@ def test_golden_corrections(oracle, golden):
     d = dict(map=golden["map"], normals=golden["normals"], reading=golden["reading"])
     for key, kw in (("T_plane_k6_it10", dict(knn=6, outliers=(), minimizer="point_to_plane", max_iteration_count=10)),
                     ("T_plane_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)),
-                    ("T_point_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=30))):
+                    ("T_point_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=30)),
+                    ("T_plane_robust_cauchy_mad_it10", dict(knn=1, outliers=(("robust", dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),),
+                                                            minimizer="point_to_plane", max_iteration_count=10))):
         cfg = make_config(dim=3, max_dist=2.0, **kw)
         _, (rc, T, res, _, _) = _run(oracle, cfg, d)
         assert rc == _abi.OK
