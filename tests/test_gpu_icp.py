@@ -107,7 +107,9 @@ def test_golden_corrections(golden):
     from norlab_icp_mapper_b200.icp import ICP
     for key, kw in (("T_plane_k6_it10", dict(knn=6, outliers=(), minimizer="point_to_plane", max_iteration_count=10)),
                     ("T_plane_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=30)),
-                    ("T_point_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=30))):
+                    ("T_point_trim_it30", dict(knn=1, outliers=(("trimmed", 0.85),), minimizer="point_to_point", max_iteration_count=30)),
+                    ("T_plane_robust_cauchy_mad_it10", dict(knn=1, outliers=(("robust", dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),),
+                                                            minimizer="point_to_plane", max_iteration_count=10))):
         g = ICP(make_config(dim=3, max_dist=2.0, **kw))
         g.set_map(golden["map"], golden["normals"])
         T = g(golden["reading"])
