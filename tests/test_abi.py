@@ -36,9 +36,10 @@ def test_struct_layout_matches_c(lib):
 #include <stddef.h>
 #include "b200icp.h"
 int main(void) {
-    printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(b200icp_config), offsetof(b200icp_config, outlier_param),
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %d\n", sizeof(b200icp_config), offsetof(b200icp_config, outlier_param),
            offsetof(b200icp_config, minimizer), offsetof(b200icp_config, sort_reading), sizeof(b200icp_result),
-           offsetof(b200icp_result, pairs_last_iter), sizeof(b200icp_timing));
+           offsetof(b200icp_result, pairs_last_iter), sizeof(b200icp_timing), offsetof(b200icp_config, outlier_mode),
+           (int)B200ICP_OUTLIER_ROBUST, (int)B200ICP_ROBUST_MODE(B200ICP_ROBUST_HUBER, B200ICP_SCALE_BERG, B200ICP_DIST_POINT2PLANE, 3));
     return 0;
 }'''
     with tempfile.TemporaryDirectory() as td:
@@ -47,8 +48,10 @@ int main(void) {
         exe = os.path.join(td, "t")
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    robust = _abi.make_config(outliers=(("robust", dict(robustFct="huber", scaleEstimator="berg", distanceType="point2plane", nbIterationForScale=3)),))
     want = [C.sizeof(_abi.Config), _abi.Config.outlier_param.offset, _abi.Config.minimizer.offset, _abi.Config.sort_reading.offset,
-            C.sizeof(_abi.Result), _abi.Result.pairs_last_iter.offset, C.sizeof(_abi.Timing)]
+            C.sizeof(_abi.Result), _abi.Result.pairs_last_iter.offset, C.sizeof(_abi.Timing), _abi.Config.outlier_mode.offset,
+            _abi.OUTLIER_ROBUST, robust.outlier_mode[0]]
     assert got == want
 
 
