@@ -84,11 +84,11 @@ int32_t fail_cuda(b200icp_ctx* ctx, cudaError_t e, const char* what) {
 template <typename T>
 cudaError_t grow(T*& p, size_t& have_bytes, size_t need_bytes) {
     if (need_bytes <= have_bytes && p) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) B200_CUDA_FREE(p);
     p = nullptr;
     have_bytes = 0;
     const size_t cap = need_bytes + need_bytes / 4 + 4096;
-    cudaError_t e = cudaMalloc((void**)&p, cap);
+    cudaError_t e = B200_CUDA_MALLOC((void**)&p, cap);
     if (e == cudaSuccess) have_bytes = cap;
     return e;
 }
@@ -189,35 +189,35 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
     const int rows = ctx->cfg.dim + 1;
     const int K = ctx->cfg.knn;
     if (!b.state) {
-        CK(cudaMalloc((void**)&b.state, kStateBytes));
-        CK(cudaMalloc((void**)&b.hist, kHistWords * sizeof(uint32_t)));
+        CK(B200_CUDA_MALLOC((void**)&b.state, kStateBytes));
+        CK(B200_CUDA_MALLOC((void**)&b.hist, kHistWords * sizeof(uint32_t)));
         CK(cudaMemset(b.hist, 0, kHistWords * sizeof(uint32_t)));
-        CK(cudaMalloc((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
-        CK(cudaMalloc((void**)&b.fastws, icp_loop_workspace_bytes()));
+        CK(B200_CUDA_MALLOC((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
+        CK(B200_CUDA_MALLOC((void**)&b.fastws, icp_loop_workspace_bytes()));
         CK(cudaMemset(b.fastws, 0, icp_loop_workspace_bytes()));
     }
     if (nq > b.cap_nq) {
         const int64_t cap = grow_capacity(nq);
-        cudaFree(b.reading_in);
-        cudaFree(b.reading);
-        cudaFree(b.reading_tmp);
-        cudaFree(b.match_pos);
-        cudaFree(b.match_d2);
-        cudaFree(b.spill_pp);
-        cudaFree(b.spill_nv);
+        B200_CUDA_FREE(b.reading_in);
+        B200_CUDA_FREE(b.reading);
+        B200_CUDA_FREE(b.reading_tmp);
+        B200_CUDA_FREE(b.match_pos);
+        B200_CUDA_FREE(b.match_d2);
+        B200_CUDA_FREE(b.spill_pp);
+        B200_CUDA_FREE(b.spill_nv);
         b.spill_pp = b.spill_nv = nullptr;
         b.reading_in = nullptr;
         b.reading = b.reading_tmp = nullptr;
         b.match_pos = nullptr;
         b.match_d2 = nullptr;
         b.cap_nq = 0;
-        CK(cudaMalloc((void**)&b.reading_in, (size_t)cap * rows * sizeof(float)));
-        CK(cudaMalloc((void**)&b.reading, (size_t)cap * sizeof(float4)));
-        CK(cudaMalloc((void**)&b.reading_tmp, (size_t)cap * sizeof(float4)));
-        CK(cudaMalloc((void**)&b.match_pos, (size_t)cap * K * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&b.match_d2, (size_t)cap * K * sizeof(float)));
-        CK(cudaMalloc((void**)&b.spill_pp, (size_t)cap * K * sizeof(float4)));  // one row per (reading point, neighbour) pair
-        CK(cudaMalloc((void**)&b.spill_nv, (size_t)cap * K * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&b.reading_in, (size_t)cap * rows * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&b.reading, (size_t)cap * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&b.reading_tmp, (size_t)cap * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&b.match_pos, (size_t)cap * K * sizeof(int32_t)));
+        CK(B200_CUDA_MALLOC((void**)&b.match_d2, (size_t)cap * K * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&b.spill_pp, (size_t)cap * K * sizeof(float4)));  // one row per (reading point, neighbour) pair
+        CK(B200_CUDA_MALLOC((void**)&b.spill_nv, (size_t)cap * K * sizeof(float4)));
         b.cap_nq = cap;
     }
     return B200ICP_OK;
@@ -226,21 +226,21 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
 int32_t ensure_query_buffers(b200icp_ctx* ctx, int64_t nq, int k) {
     if (nq * k > ctx->cap_out) {
         const int64_t cap = grow_capacity(nq * k);
-        cudaFree(ctx->d_out_ids);
-        cudaFree(ctx->d_out_d2);
+        B200_CUDA_FREE(ctx->d_out_ids);
+        B200_CUDA_FREE(ctx->d_out_d2);
         ctx->d_out_ids = nullptr;
         ctx->d_out_d2 = nullptr;
         ctx->cap_out = 0;
-        CK(cudaMalloc((void**)&ctx->d_out_ids, (size_t)cap * sizeof(int32_t)));
-        CK(cudaMalloc((void**)&ctx->d_out_d2, (size_t)cap * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_out_ids, (size_t)cap * sizeof(int32_t)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_out_d2, (size_t)cap * sizeof(float)));
         ctx->cap_out = cap;
     }
     if (nq > ctx->cap_q4) {
         const int64_t cap = grow_capacity(nq);
-        cudaFree(ctx->d_q4);
+        B200_CUDA_FREE(ctx->d_q4);
         ctx->d_q4 = nullptr;
         ctx->cap_q4 = 0;
-        CK(cudaMalloc((void**)&ctx->d_q4, (size_t)cap * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_q4, (size_t)cap * sizeof(float4)));
         ctx->cap_q4 = cap;
     }
     return B200ICP_OK;
@@ -377,9 +377,9 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     ok = ok && cudaEventCreate(&ctx->ev_map0) == cudaSuccess && cudaEventCreate(&ctx->ev_map1) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_loop0) == cudaSuccess && cudaEventCreate(&ctx->ev_loop1) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->h_pinned, 4096) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&ctx->d_scalar_nq, 64) == cudaSuccess;
+    ok = ok && B200_CUDA_MALLOC((void**)&ctx->d_scalar_nq, 64) == cudaSuccess;
     ok = ok && icp_device_setup() == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&ctx->d_bar_counter, 64) == cudaSuccess;
+    ok = ok && B200_CUDA_MALLOC((void**)&ctx->d_bar_counter, 64) == cudaSuccess;
     ctx->n_sms = prop.multiProcessorCount;
     if (const char* env = getenv("B200ICP_MARGIN")) {
         float a, f, m;
@@ -413,35 +413,35 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     grid_free(ctx->map);
     grid_free(ctx->aux);
     store_free(ctx->store);
-    cudaFree(ctx->d_keep);
+    B200_CUDA_FREE(ctx->d_keep);
     IcpBuffers& b = ctx->buf;
-    cudaFree(b.reading_in);
-    cudaFree(b.reading);
-    cudaFree(b.reading_tmp);
-    cudaFree(b.match_pos);
-    cudaFree(b.match_d2);
-    cudaFree(b.rnrm_in);
-    cudaFree(b.rnrm);
-    cudaFree(b.rnrm_tmp);
-    cudaFree(b.hist);
-    cudaFree(b.partials);
-    cudaFree(b.state);
-    cudaFree(b.trace);
+    B200_CUDA_FREE(b.reading_in);
+    B200_CUDA_FREE(b.reading);
+    B200_CUDA_FREE(b.reading_tmp);
+    B200_CUDA_FREE(b.match_pos);
+    B200_CUDA_FREE(b.match_d2);
+    B200_CUDA_FREE(b.rnrm_in);
+    B200_CUDA_FREE(b.rnrm);
+    B200_CUDA_FREE(b.rnrm_tmp);
+    B200_CUDA_FREE(b.hist);
+    B200_CUDA_FREE(b.partials);
+    B200_CUDA_FREE(b.state);
+    B200_CUDA_FREE(b.trace);
     var_trimmed_free(ctx->var_scratch);
-    cudaFree(ctx->d_scan);
-    cudaFree(ctx->d_kth);
-    cudaFree(ctx->d_dirty);
-    cudaFree(ctx->d_list);
-    cudaFree(b.fastws);
-    cudaFree(b.spill_pp);
-    cudaFree(b.spill_nv);
-    cudaFree(ctx->d_stage_a);
-    cudaFree(ctx->d_stage_b);
-    cudaFree(ctx->d_out_ids);
-    cudaFree(ctx->d_out_d2);
-    cudaFree(ctx->d_q4);
-    cudaFree(ctx->d_scalar_nq);
-    cudaFree(ctx->d_bar_counter);
+    B200_CUDA_FREE(ctx->d_scan);
+    B200_CUDA_FREE(ctx->d_kth);
+    B200_CUDA_FREE(ctx->d_dirty);
+    B200_CUDA_FREE(ctx->d_list);
+    B200_CUDA_FREE(b.fastws);
+    B200_CUDA_FREE(b.spill_pp);
+    B200_CUDA_FREE(b.spill_nv);
+    B200_CUDA_FREE(ctx->d_stage_a);
+    B200_CUDA_FREE(ctx->d_stage_b);
+    B200_CUDA_FREE(ctx->d_out_ids);
+    B200_CUDA_FREE(ctx->d_out_d2);
+    B200_CUDA_FREE(ctx->d_q4);
+    B200_CUDA_FREE(ctx->d_scalar_nq);
+    B200_CUDA_FREE(ctx->d_bar_counter);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (cudaEvent_t ev : ctx->nn_events) cudaEventDestroy(ev);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -626,7 +626,7 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         }
     }
     constexpr int kTraceCap = 512;
-    if (ctx->want_trace && !b.trace) CK(cudaMalloc((void**)&b.trace, (size_t)kTraceCap * 16 * sizeof(float)));
+    if (ctx->want_trace && !b.trace) CK(B200_CUDA_MALLOC((void**)&b.trace, (size_t)kTraceCap * 16 * sizeof(float)));
     float* const trace_keep = b.trace;
     if (!ctx->want_trace || hard_cap > kTraceCap) b.trace = nullptr;  // kernels see null -> no trace writes
     struct RestoreTrace {
@@ -771,16 +771,16 @@ int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t
     IcpBuffers& b = ctx->buf;
     const int dim = ctx->cfg.dim;
     if (nq > b.cap_rnrm) {
-        cudaFree(b.rnrm_in);
-        cudaFree(b.rnrm);
-        cudaFree(b.rnrm_tmp);
+        B200_CUDA_FREE(b.rnrm_in);
+        B200_CUDA_FREE(b.rnrm);
+        B200_CUDA_FREE(b.rnrm_tmp);
         b.rnrm_in = nullptr;
         b.rnrm = b.rnrm_tmp = nullptr;
         b.cap_rnrm = 0;
         const int64_t cap = grow_capacity(nq);
-        CK(cudaMalloc((void**)&b.rnrm_in, (size_t)cap * dim * sizeof(float)));
-        CK(cudaMalloc((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
-        CK(cudaMalloc((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&b.rnrm_in, (size_t)cap * dim * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
         b.cap_rnrm = cap;
     }
     CK(cudaMemcpyAsync(b.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -906,25 +906,25 @@ int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_
     auto reserve_grid = [&](GridIndex& g, int64_t n, bool with_normals) -> int32_t {
         CK(ensure_scratch(g, n));
         if (n > g.cap_pts) {
-            cudaFree(g.pts);
+            B200_CUDA_FREE(g.pts);
             g.pts = nullptr;
             g.cap_pts = 0;
-            CK(cudaMalloc((void**)&g.pts, (size_t)grow_capacity(n) * sizeof(float4)));
+            CK(B200_CUDA_MALLOC((void**)&g.pts, (size_t)grow_capacity(n) * sizeof(float4)));
             g.cap_pts = grow_capacity(n);
         }
         if (with_normals && n > g.cap_normals) {
-            cudaFree(g.normals);
+            B200_CUDA_FREE(g.normals);
             g.normals = nullptr;
             g.cap_normals = 0;
-            CK(cudaMalloc((void**)&g.normals, (size_t)grow_capacity(n) * sizeof(float4)));
+            CK(B200_CUDA_MALLOC((void**)&g.normals, (size_t)grow_capacity(n) * sizeof(float4)));
             g.cap_normals = grow_capacity(n);
         }
         const int64_t want_cells = std::min<int64_t>(4 * n + 2, (int64_t)kMaxCells + 2);  // about 4 cells per point, capped
         if (want_cells > g.cap_cells) {
-            cudaFree(g.cell_start);
+            B200_CUDA_FREE(g.cell_start);
             g.cell_start = nullptr;
             g.cap_cells = 0;
-            CK(cudaMalloc((void**)&g.cell_start, (size_t)want_cells * sizeof(uint32_t)));
+            CK(B200_CUDA_MALLOC((void**)&g.cell_start, (size_t)want_cells * sizeof(uint32_t)));
             g.cap_cells = want_cells;
         }
         return B200ICP_OK;
@@ -938,12 +938,12 @@ int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_
         if (eb != B200ICP_OK) return eb;
         // bookkeeping of the incremental SurfaceNormal pass (b200icp_map_surface_normals)
         if (n_points > ctx->cap_kth && !ctx->d_kth) {
-            CK(cudaMalloc((void**)&ctx->d_kth, (size_t)n_points * sizeof(float)));
+            CK(B200_CUDA_MALLOC((void**)&ctx->d_kth, (size_t)n_points * sizeof(float)));
             ctx->cap_kth = n_points;
         }
         if (2 * n_points > ctx->cap_dirty && !ctx->d_dirty && !ctx->d_list) {
-            CK(cudaMalloc((void**)&ctx->d_dirty, (size_t)(2 * n_points)));
-            CK(cudaMalloc((void**)&ctx->d_list, (size_t)(2 * n_points) * sizeof(uint32_t)));
+            CK(B200_CUDA_MALLOC((void**)&ctx->d_dirty, (size_t)(2 * n_points)));
+            CK(B200_CUDA_MALLOC((void**)&ctx->d_list, (size_t)(2 * n_points) * sizeof(uint32_t)));
             ctx->cap_dirty = 2 * n_points;
         }
     }
@@ -990,10 +990,10 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, co
         if (st.n == 0) st.has_normals = input_normals != nullptr;
     }
     if (keep_out && n_in > ctx->cap_keep) {
-        cudaFree(ctx->d_keep);
+        B200_CUDA_FREE(ctx->d_keep);
         ctx->d_keep = nullptr;
         ctx->cap_keep = 0;
-        CK(cudaMalloc((void**)&ctx->d_keep, (size_t)(n_in + n_in / 4 + 1024)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_keep, (size_t)(n_in + n_in / 4 + 1024)));
         ctx->cap_keep = n_in + n_in / 4 + 1024;
     }
     int64_t kept = 0;
@@ -1039,10 +1039,10 @@ int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t fea
     if (feature_rows != ctx->cfg.dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad scan");
     CK(cudaSetDevice(ctx->device));
     if (n > ctx->cap_scan) {
-        cudaFree(ctx->d_scan);
+        B200_CUDA_FREE(ctx->d_scan);
         ctx->d_scan = nullptr;
         ctx->cap_scan = 0;
-        CK(cudaMalloc((void**)&ctx->d_scan, (size_t)grow_capacity(n) * feature_rows * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_scan, (size_t)grow_capacity(n) * feature_rows * sizeof(float)));
         ctx->cap_scan = grow_capacity(n);
     }
     if (n > 0) CK(cudaMemcpyAsync(ctx->d_scan, features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1108,21 +1108,21 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
     const int64_t n = ctx->map.view.n;
     if (n > ctx->map.cap_normals) {
         // (the index was built without normals: nothing to preserve)
-        cudaFree(ctx->map.normals);
+        B200_CUDA_FREE(ctx->map.normals);
         ctx->map.normals = nullptr;
         ctx->map.cap_normals = 0;
-        CK(cudaMalloc((void**)&ctx->map.normals, (size_t)grow_capacity(n) * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->map.normals, (size_t)grow_capacity(n) * sizeof(float4)));
         ctx->map.cap_normals = grow_capacity(n);
     }
     // k-th neighbour distance per store point (incremental bookkeeping); grows with the store, content preserved
     if (st.n > ctx->cap_kth) {
         const int64_t cap = grow_capacity(st.n);
         float* nk = nullptr;
-        CK(cudaMalloc((void**)&nk, (size_t)cap * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&nk, (size_t)cap * sizeof(float)));
         if (ctx->d_kth && st.nrm_epoch_ok && st.nrm_epoch_n > 0)
             CK(cudaMemcpyAsync(nk, ctx->d_kth, (size_t)std::min<int64_t>(st.nrm_epoch_n, ctx->cap_kth) * sizeof(float), cudaMemcpyDeviceToDevice, s));
         CK(cudaStreamSynchronize(s));
-        cudaFree(ctx->d_kth);
+        B200_CUDA_FREE(ctx->d_kth);
         ctx->d_kth = nk;
         ctx->cap_kth = cap;
     }
@@ -1135,14 +1135,14 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
                        !getenv("B200ICP_FULL_NORMALS");
     ctx->last_normals_recomputed = n;
     if (incremental && (n_new > 0 || st.nrm_touched) && st.n + n > ctx->cap_dirty) {
-        cudaFree(ctx->d_dirty);
-        cudaFree(ctx->d_list);
+        B200_CUDA_FREE(ctx->d_dirty);
+        B200_CUDA_FREE(ctx->d_list);
         ctx->d_dirty = nullptr;
         ctx->d_list = nullptr;
         ctx->cap_dirty = 0;
         const int64_t cap = grow_capacity(st.n + n);
-        CK(cudaMalloc((void**)&ctx->d_dirty, (size_t)cap));
-        CK(cudaMalloc((void**)&ctx->d_list, (size_t)cap * sizeof(uint32_t)));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_dirty, (size_t)cap));
+        CK(B200_CUDA_MALLOC((void**)&ctx->d_list, (size_t)cap * sizeof(uint32_t)));
         ctx->cap_dirty = cap;
     }
     unsigned int* d_count = reinterpret_cast<unsigned int*>(ctx->d_scalar_nq) + 4;
@@ -1154,10 +1154,10 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         thrust::counting_iterator<uint32_t> counting(0u);
         cub::DeviceSelect::Flagged(nullptr, need, counting, ctx->d_dirty, ctx->d_list, d_count, (int)st.n);
         if (need > ctx->map.cub_tmp_bytes) {
-            cudaFree(ctx->map.cub_tmp);
+            B200_CUDA_FREE(ctx->map.cub_tmp);
             ctx->map.cub_tmp = nullptr;
             ctx->map.cub_tmp_bytes = 0;
-            CK(cudaMalloc(&ctx->map.cub_tmp, need + 256));
+            CK(B200_CUDA_MALLOC(&ctx->map.cub_tmp, need + 256));
             ctx->map.cub_tmp_bytes = need + 256;
         }
         size_t bytes = ctx->map.cub_tmp_bytes;
@@ -1187,10 +1187,10 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         thrust::counting_iterator<uint32_t> counting(0u);
         cub::DeviceSelect::Flagged(nullptr, need, counting, d_flag, ctx->d_list, d_count, (int)n);
         if (need > ctx->map.cub_tmp_bytes) {
-            cudaFree(ctx->map.cub_tmp);
+            B200_CUDA_FREE(ctx->map.cub_tmp);
             ctx->map.cub_tmp = nullptr;
             ctx->map.cub_tmp_bytes = 0;
-            CK(cudaMalloc(&ctx->map.cub_tmp, need + 256));
+            CK(B200_CUDA_MALLOC(&ctx->map.cub_tmp, need + 256));
             ctx->map.cub_tmp_bytes = need + 256;
         }
         size_t bytes = ctx->map.cub_tmp_bytes;

@@ -38,8 +38,9 @@ inline cudaError_t traced_free(void* p, const char* file, int line) {
     fprintf(stderr, "[b200icp alloc] cudaFree                 %8.3f ms  %s:%d\n", ms, file, line);
     return e;
 }
-#define cudaMalloc(p, bytes) ::b200::traced_malloc((void**)(p), (bytes), __FILE__, __LINE__)
-#define cudaFree(p) ::b200::traced_free((void*)(p), __FILE__, __LINE__)
+// every device allocation / release of the library goes through these two (call site recorded for the trace)
+#define B200_CUDA_MALLOC(p, bytes) ::b200::traced_malloc((void**)(p), (bytes), __FILE__, __LINE__)
+#define B200_CUDA_FREE(p) ::b200::traced_free((void*)(p), __FILE__, __LINE__)
 
 inline int64_t grow_capacity(int64_t n) { return n * 2 > (int64_t(1) << 20) ? n * 2 : (int64_t(1) << 20); }
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)

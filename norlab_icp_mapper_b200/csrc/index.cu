@@ -109,24 +109,24 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const float4* __rest
 
 template <typename T>
 cudaError_t ensure(T*& p, int64_t count) {
-    if (p) cudaFree(p);
+    if (p) B200_CUDA_FREE(p);
     p = nullptr;
-    return cudaMalloc((void**)&p, (size_t)std::max<int64_t>(count, 1) * sizeof(T));
+    return B200_CUDA_MALLOC((void**)&p, (size_t)std::max<int64_t>(count, 1) * sizeof(T));
 }
 
 }  // namespace
 
 void grid_free(GridIndex& g) {
-    cudaFree(g.pts);
-    cudaFree(g.normals);
-    cudaFree(g.cell_start);
-    cudaFree(g.tmp_pts);
-    cudaFree(g.keys_in);
-    cudaFree(g.keys_out);
-    cudaFree(g.vals_in);
-    cudaFree(g.vals_out);
-    cudaFree(g.cub_tmp);
-    cudaFree(g.d_reduce);
+    B200_CUDA_FREE(g.pts);
+    B200_CUDA_FREE(g.normals);
+    B200_CUDA_FREE(g.cell_start);
+    B200_CUDA_FREE(g.tmp_pts);
+    B200_CUDA_FREE(g.keys_in);
+    B200_CUDA_FREE(g.keys_out);
+    B200_CUDA_FREE(g.vals_in);
+    B200_CUDA_FREE(g.vals_out);
+    B200_CUDA_FREE(g.cub_tmp);
+    B200_CUDA_FREE(g.d_reduce);
     g = GridIndex{};
 }
 
@@ -146,15 +146,15 @@ cudaError_t ensure_scratch(GridIndex& g, int64_t n) {
         cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, kMaxCells + 1);
         bytes = std::max(bytes, scan_bytes) + 256;
         if (bytes > g.cub_tmp_bytes) {
-            if (g.cub_tmp) cudaFree(g.cub_tmp);
+            if (g.cub_tmp) B200_CUDA_FREE(g.cub_tmp);
             g.cub_tmp = nullptr;
-            if ((e = cudaMalloc(&g.cub_tmp, bytes)) != cudaSuccess) return e;
+            if ((e = B200_CUDA_MALLOC(&g.cub_tmp, bytes)) != cudaSuccess) return e;
             g.cub_tmp_bytes = bytes;
         }
         g.cap_scratch = cap;
     }
     if (!g.d_reduce)
-        if ((e = cudaMalloc((void**)&g.d_reduce, 16 * sizeof(unsigned long long))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&g.d_reduce, 16 * sizeof(unsigned long long))) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) normals_gather_queries_kernel(GridView g,
 template <typename T>
 cudaError_t regrow(T*& p, int64_t old_count, int64_t new_cap, cudaStream_t s) {
     T* np = nullptr;
-    cudaError_t e = cudaMalloc((void**)&np, (size_t)std::max<int64_t>(new_cap, 1) * sizeof(T));
+    cudaError_t e = B200_CUDA_MALLOC((void**)&np, (size_t)std::max<int64_t>(new_cap, 1) * sizeof(T));
     if (e != cudaSuccess) return e;
     if (p && old_count > 0) {
         e = cudaMemcpyAsync(np, p, (size_t)old_count * sizeof(T), cudaMemcpyDeviceToDevice, s);
@@ -263,7 +263,7 @@ cudaError_t regrow(T*& p, int64_t old_count, int64_t new_cap, cudaStream_t s) {
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return e;
     }
-    if (p) cudaFree(p);
+    if (p) B200_CUDA_FREE(p);
     p = np;
     return cudaSuccess;
 }
@@ -273,21 +273,21 @@ unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 }  // namespace
 
 void store_free(MapStore& m) {
-    cudaFree(m.feat);
-    cudaFree(m.nrm);
-    cudaFree(m.prob);
-    cudaFree(m.loaded);
-    cudaFree(m.touched);
-    cudaFree(m.feat2);
-    cudaFree(m.nrm2);
-    cudaFree(m.prob2);
-    cudaFree(m.loaded2);
-    cudaFree(m.keys64_a);
-    cudaFree(m.keys64_b);
-    cudaFree(m.active);
-    cudaFree(m.tmp_u32a);
-    cudaFree(m.tmp_u32b);
-    cudaFree(m.d_counter);
+    B200_CUDA_FREE(m.feat);
+    B200_CUDA_FREE(m.nrm);
+    B200_CUDA_FREE(m.prob);
+    B200_CUDA_FREE(m.loaded);
+    B200_CUDA_FREE(m.touched);
+    B200_CUDA_FREE(m.feat2);
+    B200_CUDA_FREE(m.nrm2);
+    B200_CUDA_FREE(m.prob2);
+    B200_CUDA_FREE(m.loaded2);
+    B200_CUDA_FREE(m.keys64_a);
+    B200_CUDA_FREE(m.keys64_b);
+    B200_CUDA_FREE(m.active);
+    B200_CUDA_FREE(m.tmp_u32a);
+    B200_CUDA_FREE(m.tmp_u32b);
+    B200_CUDA_FREE(m.d_counter);
     m = MapStore{};
 }
 
@@ -304,37 +304,37 @@ cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s) {
             if ((e = regrow(m.touched, m.touched ? old_cap : 0, cap, s)) != cudaSuccess) return e;
             if ((e = cudaMemsetAsync(m.touched + old_cap, 0, (size_t)(cap - old_cap), s)) != cudaSuccess) return e;
         }
-        cudaFree(m.feat2);
-        cudaFree(m.nrm2);
-        cudaFree(m.prob2);
-        cudaFree(m.loaded2);
+        B200_CUDA_FREE(m.feat2);
+        B200_CUDA_FREE(m.nrm2);
+        B200_CUDA_FREE(m.prob2);
+        B200_CUDA_FREE(m.loaded2);
         m.feat2 = nullptr;
         m.nrm2 = m.prob2 = nullptr;
         m.loaded2 = nullptr;
-        if ((e = cudaMalloc((void**)&m.feat2, (size_t)cap * sizeof(float4))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&m.nrm2, (size_t)cap * dim * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&m.prob2, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&m.loaded2, (size_t)cap)) != cudaSuccess) return e;
-        cudaFree(m.active);
+        if ((e = B200_CUDA_MALLOC((void**)&m.feat2, (size_t)cap * sizeof(float4))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.nrm2, (size_t)cap * dim * sizeof(float))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.prob2, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.loaded2, (size_t)cap)) != cudaSuccess) return e;
+        B200_CUDA_FREE(m.active);
         m.active = nullptr;
-        if ((e = cudaMalloc((void**)&m.active, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.active, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
         m.cap = cap;
     }
     if (!m.d_counter)
-        if ((e = cudaMalloc((void**)&m.d_counter, 64)) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.d_counter, 64)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 static cudaError_t ensure_tmp(MapStore& m, int64_t n) {
     if (n <= m.cap_tmp) return cudaSuccess;
-    cudaFree(m.tmp_u32a);
-    cudaFree(m.tmp_u32b);
+    B200_CUDA_FREE(m.tmp_u32a);
+    B200_CUDA_FREE(m.tmp_u32b);
     m.tmp_u32a = m.tmp_u32b = nullptr;
     m.cap_tmp = 0;
     const int64_t cap = grow_capacity(n);
     cudaError_t e;
-    if ((e = cudaMalloc((void**)&m.tmp_u32a, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void**)&m.tmp_u32b, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = B200_CUDA_MALLOC((void**)&m.tmp_u32a, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = B200_CUDA_MALLOC((void**)&m.tmp_u32b, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
     m.cap_tmp = cap;
     return cudaSuccess;
 }
@@ -346,10 +346,10 @@ static cudaError_t exclusive_sum(GridIndex& scratch, const uint32_t* in, uint32_
     size_t need = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, (int)n);
     if (need > scratch.cub_tmp_bytes) {
-        cudaFree(scratch.cub_tmp);
+        B200_CUDA_FREE(scratch.cub_tmp);
         scratch.cub_tmp = nullptr;
         scratch.cub_tmp_bytes = 0;
-        cudaError_t e = cudaMalloc(&scratch.cub_tmp, need + 256);
+        cudaError_t e = B200_CUDA_MALLOC(&scratch.cub_tmp, need + 256);
         if (e != cudaSuccess) return e;
         scratch.cub_tmp_bytes = need + 256;
     }
@@ -713,13 +713,13 @@ cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float 
     for (float r = radius; (double)r * 2.0 > (double)max_size_by_node && depth < 22; r *= 0.5f) ++depth;
     if (depth > 21) return cudaErrorInvalidValue;  // key would not fit 63 bits
     if (na > m.cap_keys64) {
-        cudaFree(m.keys64_a);
-        cudaFree(m.keys64_b);
+        B200_CUDA_FREE(m.keys64_a);
+        B200_CUDA_FREE(m.keys64_b);
         m.keys64_a = m.keys64_b = nullptr;
         m.cap_keys64 = 0;
         const int64_t cap = grow_capacity(na);
-        if ((e = cudaMalloc((void**)&m.keys64_a, (size_t)cap * 8)) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&m.keys64_b, (size_t)cap * 8)) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.keys64_a, (size_t)cap * 8)) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.keys64_b, (size_t)cap * 8)) != cudaSuccess) return e;
         m.cap_keys64 = cap;
     }
     if ((e = ensure_tmp(m, std::max<int64_t>(m.n, na) + 1)) != cudaSuccess) return e;
@@ -728,10 +728,10 @@ cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float 
     size_t need = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, need, m.keys64_a, m.keys64_b, scratch.vals_in, scratch.vals_out, (int)na, 0, std::max(1, 3 * depth));
     if (need > scratch.cub_tmp_bytes) {
-        cudaFree(scratch.cub_tmp);
+        B200_CUDA_FREE(scratch.cub_tmp);
         scratch.cub_tmp = nullptr;
         scratch.cub_tmp_bytes = 0;
-        if ((e = cudaMalloc(&scratch.cub_tmp, need + 256)) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC(&scratch.cub_tmp, need + 256)) != cudaSuccess) return e;
         scratch.cub_tmp_bytes = need + 256;
     }
     size_t bytes = scratch.cub_tmp_bytes;

@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(1024) robust_std_kernel(IcpState* __restrict__
 }  // namespace
 
 void var_trimmed_free(VarTrimScratch& v) {
-    cudaFree(v.keys_in);
-    cudaFree(v.keys_out);
-    cudaFree(v.cums);
-    cudaFree(v.cub_tmp);
-    cudaFree(v.d_count);
+    B200_CUDA_FREE(v.keys_in);
+    B200_CUDA_FREE(v.keys_out);
+    B200_CUDA_FREE(v.cums);
+    B200_CUDA_FREE(v.cub_tmp);
+    B200_CUDA_FREE(v.d_count);
     v = VarTrimScratch{};
 }
 
@@ -214,17 +214,17 @@ static cudaError_t ensure_sort_scratch(VarTrimScratch& v, long long cap, cudaStr
     cudaError_t e;
     if (cap > v.cap) {
         var_trimmed_free(v);
-        if ((e = cudaMalloc((void**)&v.keys_in, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&v.keys_out, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&v.cums, (size_t)cap * sizeof(double))) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&v.d_count, 64)) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&v.keys_in, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&v.keys_out, (size_t)cap * sizeof(float))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&v.cums, (size_t)cap * sizeof(double))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&v.d_count, 64)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(v.d_count, 0, 64, s)) != cudaSuccess) return e;
         size_t need_sort = 0, need_scan = 0;
         cub::DeviceRadixSort::SortKeys(nullptr, need_sort, v.keys_in, v.keys_out, (int)cap, 0, 32);
         auto it = thrust::make_transform_iterator((const float*)v.keys_out, FiniteToDouble());
         cub::DeviceScan::InclusiveSum(nullptr, need_scan, it, v.cums, (int)cap);
         v.cub_bytes = (need_sort > need_scan ? need_sort : need_scan) + 256;
-        if ((e = cudaMalloc(&v.cub_tmp, v.cub_bytes)) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC(&v.cub_tmp, v.cub_bytes)) != cudaSuccess) return e;
         v.cap = cap;
     }
     return cudaSuccess;
