@@ -216,3 +216,16 @@ def test_robust_point2plane_needs_reference_normals(oracle, pair3d):
     o = oracle.OracleICP(cfg)
     o.set_map(pair3d["map"], None)
     assert o.register(pair3d["reading"])[0] == _abi.ERR_INVALID_FIELD
+
+
+@pytest.mark.parametrize("minimizer,knn,rp", [("point_to_point", 4, dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),
+                                              ("point_to_plane", 1, dict(robustFct="huber", tuning=1.5, scaleEstimator="mad", distanceType="point2plane"))])
+def test_robust_outlier_filter_2d(oracle, pair2d, minimizer, knn, rp):
+    outliers = (("robust", rp),)
+    cfg = make_config(dim=2, knn=knn, max_dist=0.5, outliers=outliers, minimizer=minimizer, max_iteration_count=12)
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair2d)
+    assert rc == _abi.OK and T.shape == (3, 3)
+    T_np = numpy_icp.icp(pair2d["map"][:, :2], pair2d["normals"], pair2d["reading"][:, :2], knn_k=knn, max_dist=0.5,
+                         outliers=outliers, minimizer=minimizer, iterations=12)
+    er, et = synth.pose_error(T, T_np)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
