@@ -355,7 +355,9 @@ def run_b200(args):
             "setmap_ms": setmap_ms,
             "pose_error_vs_truth": {"rad": err[0], "m": err[1]},
         }
-        if not args.no_cpu_baseline:
+        if world > 1:  # the CPU baseline is a single-GPU-run figure (rank 0 would keep the other ranks waiting for it)
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "timed at N=1 only"}
+        elif not args.no_cpu_baseline:
             n_cpu = 30  # about 10 s of CPU work on a 16-core host: a bounded sample, long enough to average out scheduling noise
             r = time_oracle(args, data, n_cpu, 2)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
