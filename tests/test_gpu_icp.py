@@ -245,7 +245,8 @@ def test_k_gt_1_spills_the_match_cache(oracle):
         g.set_map(d["map"], d["normals"])
         outs[variant] = (g(d["reading"]), g.last_result.pairs_last_iter, g.last_result.overlap)
         g.close()
-    assert outs[0][1:] == outs[32][1:] == outs[4][1:]
+    assert outs[0][1:] == outs[32][1:]  # same path with and without the verification: identical
+    assert abs(outs[0][1] - outs[4][1]) <= 2 and abs(outs[0][2] - outs[4][2]) <= 1e-5  # other summation order: a boundary pair may flip
     for v in (32, 4):
         er, et = synth.pose_error(outs[0][0], outs[v][0])
         assert er <= 1e-6 and et <= 1e-5, (v, er, et)
