@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200ICP_ABI_VERSION 3
+#define B200ICP_ABI_VERSION 4
 
 typedef enum b200icp_status {
     B200ICP_OK = 0,
@@ -139,7 +139,18 @@ typedef struct b200icp_config {
                              bits 10..11 loop kernel: value - 1 = log2 of that chunk size (1, 2, 4 points)
                              bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3) */
     int32_t outlier_mode[B200ICP_MAX_OUTLIER_FILTERS]; /* per filter: B200ICP_ROBUST_MODE(...) for RobustOutlierFilter, else 0 */
-    int32_t reserved[1];
+    int32_t checker_order; /* position of the Counter in the transformationCheckers list.  libpointmatcher runs the checkers in YAML
+                              order and the Counter reports its limit by throwing MaxNumIterationsReached, which skips the checkers
+                              listed after it for that iteration: bit 0 = Differential is listed BEFORE the Counter, bit 1 = Bound is.
+                              0 = Counter first (the order of PM::ICPSequence::setDefault)                                         */
+    int32_t minimizer_flags; /* PointToPlaneErrorMinimizer options (LPM ErrorMinimizers/PointToPlane.cpp): bit 0 = force2D (3-D clouds:
+                                solve for yaw + x, y only, z / roll / pitch untouched), bit 1 = force4DOF (yaw + x, y, z)           */
+    int32_t conventions;     /* choices between two readings of upstream behaviour that cannot be settled without its source here
+                                (SURVEY App. A items marked "(?)"); 0 = the reading the oracle is written to:
+                                bit 0  matcher accepts a neighbour when dist2 <  maxDist^2   (default: <=)
+                                bit 1  MedianDistOutlierFilter: limit = factor^2 * median(dist2), i.e. the factor scales the
+                                       distance, not its square                               (default: factor * median(dist2)) */
+    int32_t reserved2[5];
 } b200icp_config;
 
 /* What `icp(input)` leaves behind for the caller (Mapper.cpp:213,219). */
@@ -229,6 +240,35 @@ int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_
  * (then identical to b200icp_register).  Host pointers. */
 int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq,
                                  const float* reading_normals, const float* T_init, float* T_out, b200icp_result* result);
+
+/* ---- batched registration (BASELINE.json config 5; no reference counterpart: the reference aligns one scan at a time) ----
+ * Independent scan <-> submap alignments.  One pair = `icp.setMap(submap)` (Map.cpp:111) followed by `icp(reading)`
+ * (Mapper.cpp:213) on the same ICP object; pairs do not interact. */
+typedef struct b200icp_pair {
+    const float* map_features; /* (dim+1) x n_map, column-major, host.  NULL: keep the map the context already holds
+                                  (the previous pair's submap, or one installed by b200icp_set_map) -- scans against one map */
+    const float* map_normals;  /* dim x n_map or NULL (then point-to-plane fails with B200ICP_ERR_INVALID_FIELD)          */
+    int64_t n_map;
+    const float* reading;      /* (dim+1) x n_reading, column-major, host                                                   */
+    int64_t n_reading;
+    const float* T_init;       /* (dim+1) x (dim+1) or NULL = identity                                                      */
+} b200icp_pair;
+
+typedef struct b200icp_pair_result {
+    float T[16];              /* the (dim+1) x (dim+1) correction, column-major, in the first (dim+1)^2 entries           */
+    b200icp_result result;
+    int32_t status;           /* b200icp_status of this pair (a failed pair does not stop the batch)                      */
+    float setmap_ms, register_ms; /* device time of the two steps (CUDA events on the context's stream)                   */
+} b200icp_pair_result;
+
+/* Registers pairs[0 .. n_pairs): pair j runs on ctxs[j % n_ctx], each context working through its share in order on its
+ * own host thread and CUDA stream.  Contexts may live on different devices (one process driving several GPUs) and / or
+ * share a device: two contexts on one GPU overlap pair j+1's submap upload (copy engine) with pair j's ICP loop (SMs).
+ * All contexts must have the same `dim`.  Returns B200ICP_OK when every pair succeeded, else the status of the first
+ * failed pair (per-pair statuses in out[]).  Blocks until the whole batch is done.  The contexts must not be used by
+ * other threads meanwhile. */
+int32_t b200icp_register_batch(b200icp_ctx* const* ctxs, int32_t n_ctx, const b200icp_pair* pairs, int64_t n_pairs,
+                               b200icp_pair_result* out);
 
 /* matcher->findClosests(cloud) against the current map -- the KDTreeMatcher step of the loop and
  * the direct Nabo::NNS::knn call sites (PointDistanceMapperModule.cpp:36).  `queries` are in the

@@ -2,7 +2,7 @@
 product binding (icp.py) and by the tests' oracle binding so both speak the same config."""
 import ctypes as C
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_OUTLIER_FILTERS = 4
 
 # b200icp_status
@@ -43,7 +43,10 @@ class Config(C.Structure):
         ("use_graph", C.c_int32),
         ("nn_variant", C.c_int32),
         ("outlier_mode", C.c_int32 * MAX_OUTLIER_FILTERS),
-        ("reserved", C.c_int32 * 1),
+        ("checker_order", C.c_int32),
+        ("minimizer_flags", C.c_int32),
+        ("conventions", C.c_int32),
+        ("reserved2", C.c_int32 * 5),
     ]
 
 
@@ -76,9 +79,20 @@ class Timing(C.Structure):
     ]
 
 
+class Pair(C.Structure):
+    """b200icp_pair: one scan <-> submap alignment of b200icp_register_batch (host pointers)."""
+    _fields_ = [("map_features", C.c_void_p), ("map_normals", C.c_void_p), ("n_map", C.c_int64),
+                ("reading", C.c_void_p), ("n_reading", C.c_int64), ("T_init", C.c_void_p)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("result", Result), ("status", C.c_int32), ("setmap_ms", C.c_float),
+                ("register_ms", C.c_float)]
+
+
 def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("trimmed", 0.85),),
                 minimizer="point_to_plane", max_iteration_count=40, differential=None, bound=None,
-                sort_reading=1, use_graph=1, nn_variant=0):
+                sort_reading=1, use_graph=1, nn_variant=0, checker_order=0, force2D=False, force4DOF=False, conventions=0):
     """Build a Config from the names used in the reference's `icp:` YAML node
     (docs/MapperConfiguration.md:172-189)."""
     kinds = {"trimmed": OUTLIER_TRIMMED_DIST, "max_dist": OUTLIER_MAX_DIST,
@@ -117,6 +131,9 @@ def make_config(dim=3, knn=1, max_dist=float("inf"), epsilon=0.0, outliers=(("tr
     else:
         c.use_bound, c.max_rotation_norm, c.max_translation_norm = 0, 1.0, 1.0
     c.sort_reading, c.use_graph, c.nn_variant = sort_reading, use_graph, nn_variant
+    c.checker_order = checker_order
+    c.minimizer_flags = (1 if force2D else 0) | (2 if force4DOF else 0)
+    c.conventions = conventions
     return c
 
 

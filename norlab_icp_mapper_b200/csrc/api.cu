@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -191,10 +192,10 @@ int32_t ensure_icp_buffers(b200icp_ctx* ctx, int64_t nq) {
     if (!b.state) {
         CK(B200_CUDA_MALLOC((void**)&b.state, kStateBytes));
         CK(B200_CUDA_MALLOC((void**)&b.hist, kHistWords * sizeof(uint32_t)));
-        CK(cudaMemset(b.hist, 0, kHistWords * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(b.hist, 0, kHistWords * sizeof(uint32_t), ctx->stream));
         CK(B200_CUDA_MALLOC((void**)&b.partials, (size_t)kMaxAccBlocks * kAccSlots * sizeof(double)));
         CK(B200_CUDA_MALLOC((void**)&b.fastws, icp_loop_workspace_bytes()));
-        CK(cudaMemset(b.fastws, 0, icp_loop_workspace_bytes()));
+        CK(cudaMemsetAsync(b.fastws, 0, icp_loop_workspace_bytes(), ctx->stream));
     }
     if (nq > b.cap_nq) {
         const int64_t cap = grow_capacity(nq);
@@ -372,6 +373,7 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     p.use_bound = cfg->use_bound;
     p.max_rotation_norm = cfg->max_rotation_norm;
     p.max_translation_norm = cfg->max_translation_norm;
+    p.counter_after = cfg->checker_order & 3;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_map0) == cudaSuccess && cudaEventCreate(&ctx->ev_map1) == cudaSuccess;
@@ -496,7 +498,8 @@ int32_t b200icp_debug_stamps(const b200icp_ctx* ctx, unsigned long long* out32) 
 int32_t b200icp_debug_loop_record(b200icp_ctx* ctx, uint32_t* out, int32_t iterations) {
     if (!ctx || !out || iterations < 0 || iterations > 256 || !ctx->buf.hist) return B200ICP_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpy(out, ctx->buf.hist + 12288, (size_t)iterations * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(out, ctx->buf.hist + 12288, (size_t)iterations * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return B200ICP_OK;
 }
 
@@ -708,7 +711,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     ctx->h_trace.clear();
     if (b.trace && executed > 0) {
         ctx->h_trace.resize((size_t)executed * 16);
-        CK(cudaMemcpy(ctx->h_trace.data(), b.trace, ctx->h_trace.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(ctx->h_trace.data(), b.trace, ctx->h_trace.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
     }
     if (result) {
         result->overlap = out_state->overlap;
@@ -798,6 +802,48 @@ int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature
     if (eb != B200ICP_OK) return eb;
     CK(cudaMemcpyAsync(ctx->buf.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     return register_on_device(ctx, ctx->buf.reading_in, feature_rows, nq, T_init, T_out, result);
+}
+
+int32_t b200icp_register_batch(b200icp_ctx* const* ctxs, int32_t n_ctx, const b200icp_pair* pairs, int64_t n_pairs,
+                               b200icp_pair_result* out) {
+    if (!ctxs || n_ctx < 1 || n_pairs < 0 || (n_pairs > 0 && (!pairs || !out))) return B200ICP_ERR_INVALID_ARG;
+    for (int c = 0; c < n_ctx; ++c) {
+        if (!ctxs[c]) return B200ICP_ERR_INVALID_ARG;
+        if (ctxs[c]->cfg.dim != ctxs[0]->cfg.dim) return fail(ctxs[0], B200ICP_ERR_INVALID_ARG, "register_batch: contexts differ in dim");
+        for (int d = 0; d < c; ++d)
+            if (ctxs[d] == ctxs[c]) return fail(ctxs[0], B200ICP_ERR_INVALID_ARG, "register_batch: the same context listed twice");
+    }
+    const int dim = ctxs[0]->cfg.dim, rows = dim + 1;
+    auto work = [&](int c) {
+        b200icp_ctx* ctx = ctxs[c];
+        for (int64_t j = c; j < n_pairs; j += n_ctx) {
+            const b200icp_pair& pr = pairs[j];
+            b200icp_pair_result& r = out[j];
+            memset(&r, 0, sizeof(r));
+            int32_t rc = B200ICP_OK;
+            if (pr.map_features) {
+                rc = b200icp_set_map(ctx, pr.map_features, rows, pr.map_normals, pr.n_map);
+                r.setmap_ms = ctx->timing.setmap_ms;
+            }
+            if (rc == B200ICP_OK) {
+                rc = b200icp_register(ctx, pr.reading, rows, pr.n_reading, pr.T_init, r.T, &r.result);
+                r.register_ms = ctx->timing.total_ms;
+            }
+            r.status = rc;
+        }
+    };
+    if (n_ctx == 1 || n_pairs <= 1) {
+        for (int c = 0; c < n_ctx; ++c) work(c);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(n_ctx - 1);
+        for (int c = 1; c < n_ctx; ++c) th.emplace_back(work, c);
+        work(0);
+        for (auto& t : th) t.join();
+    }
+    for (int64_t j = 0; j < n_pairs; ++j)
+        if (out[j].status != B200ICP_OK) return out[j].status;
+    return B200ICP_OK;
 }
 
 static int32_t run_queries(b200icp_ctx* ctx, GridIndex& g, const float* queries, int32_t rows, int64_t nq, int dim, int k,
@@ -1294,13 +1340,15 @@ int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, 
     std::vector<float4> f((size_t)st.n);
     std::vector<uint8_t> l((size_t)st.n);
     std::vector<float> nr;
-    CK(cudaMemcpy(f.data(), st.feat, f.size() * sizeof(float4), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost));
+    // (copies on the context's own non-blocking stream: the legacy default stream does not order against it)
+    CK(cudaMemcpyAsync(f.data(), st.feat, f.size() * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost, ctx->stream));
     const bool want_n = normals && st.has_normals;
     if (want_n) {
         nr.resize((size_t)st.n * dim);
-        CK(cudaMemcpy(nr.data(), st.nrm, nr.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(nr.data(), st.nrm, nr.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    CK(cudaStreamSynchronize(ctx->stream));
     int64_t o = 0;
     for (int64_t i = 0; i < st.n; ++i) {
         if (!global && !l[i]) continue;
@@ -1351,7 +1399,8 @@ int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant
         CK(cudaMemcpyAsync(st.prob, prob, (size_t)st.n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     } else {
         std::vector<float> v((size_t)st.n, constant);
-        CK(cudaMemcpy(st.prob, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(st.prob, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // (v goes out of scope)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     st.has_prob = true;
@@ -1365,8 +1414,9 @@ int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob,
     if (!st.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map has no probabilityDynamic descriptor");
     std::vector<float> p((size_t)st.n);
     std::vector<uint8_t> l((size_t)st.n);
-    CK(cudaMemcpy(p.data(), st.prob, p.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(p.data(), st.prob, p.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     int64_t o = 0;
     for (int64_t i = 0; i < st.n; ++i) {
         if (!global && !l[i]) continue;

@@ -140,6 +140,7 @@ struct IcpParams {  // by-value kernel argument, constant for the life of a cont
     int smooth_length;
     int use_bound;
     float max_rotation_norm, max_translation_norm;
+    int counter_after;  // b200icp_config::checker_order
 };
 
 // ---- index.cu ------------------------------------------------------------------------------

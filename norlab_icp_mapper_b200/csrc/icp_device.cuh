@@ -429,55 +429,60 @@ __device__ __forceinline__ void finish_iteration(const IcpParams& prm, IcpState*
     }
     st->iter = it + 1;
 
+    // LPM TransformationCheckers::check runs the checkers in their YAML order; the Counter signals its limit by THROWING
+    // MaxNumIterationsReached (caught by ICP.cpp), which skips the checkers listed after it for that iteration.  counter_after:
+    // bit 0 = Differential is listed before the Counter, bit 1 = Bound is (0 = LPM's setDefault order: Counter first).
     bool iterate = true;
-    if (prm.max_iteration_count > 0) {
-        st->counter += 1;
-        if (st->counter >= prm.max_iteration_count) {
-            st->max_iter_reached = 1;
-            st->done = 1;
-            return;
-        }
-    }
-    if (prm.use_differential) {
-        const int smooth = min(max(prm.smooth_length, 1), 7);
-        const int slot = st->dcount % 8;
-        quat_from_T(T, st->dq[slot]);
-        for (int d = 0; d < 3; ++d) st->dt[slot][d] = T[12 + d];
-        st->dcount += 1;
-        float vr = 0.f, vt = 0.f;
-        if (st->dcount > smooth) {
-            for (int j = st->dcount - 1; j >= st->dcount - smooth; --j) {
-                const int a = j % 8, b = (j - 1) % 8;
-                vr += fabsf(quat_angular_distance(st->dq[a], st->dq[b]));
-                const float dx = st->dt[a][0] - st->dt[b][0], dy = st->dt[a][1] - st->dt[b][1], dz = st->dt[a][2] - st->dt[b][2];
-                vt += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1 && prm.max_iteration_count > 0) {
+            st->counter += 1;
+            if (st->counter >= prm.max_iteration_count) {
+                st->max_iter_reached = 1;
+                st->done = 1;
+                return;
             }
-            vr /= (float)smooth;
-            vt /= (float)smooth;
-            if (vr < prm.min_diff_rot_err && vt < prm.min_diff_trans_err) iterate = false;
         }
-        if (isnan(vr) || isnan(vt)) {
-            st->status = B200ICP_ERR_NAN;
-            st->done = 1;
-            return;
+        if (prm.use_differential && (((prm.counter_after & 1) != 0) == (phase == 0))) {
+            const int smooth = min(max(prm.smooth_length, 1), 7);
+            const int slot = st->dcount % 8;
+            quat_from_T(T, st->dq[slot]);
+            for (int d = 0; d < 3; ++d) st->dt[slot][d] = T[12 + d];
+            st->dcount += 1;
+            float vr = 0.f, vt = 0.f;
+            if (st->dcount > smooth) {
+                for (int j = st->dcount - 1; j >= st->dcount - smooth; --j) {
+                    const int a = j % 8, b = (j - 1) % 8;
+                    vr += fabsf(quat_angular_distance(st->dq[a], st->dq[b]));
+                    const float dx = st->dt[a][0] - st->dt[b][0], dy = st->dt[a][1] - st->dt[b][1], dz = st->dt[a][2] - st->dt[b][2];
+                    vt += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+                }
+                vr /= (float)smooth;
+                vt /= (float)smooth;
+                if (vr < prm.min_diff_rot_err && vt < prm.min_diff_trans_err) iterate = false;
+            }
+            if (isnan(vr) || isnan(vt)) {
+                st->status = B200ICP_ERR_NAN;
+                st->done = 1;
+                return;
+            }
         }
-    }
-    if (prm.use_bound) {
-        float qc[4];
-        quat_from_T(T, qc);
-        const float vr = quat_angular_distance(qc, st->bq0);
-        float vt = 0.f;
-        for (int d = 0; d < 3; ++d) vt += (T[12 + d] - st->bt0[d]) * (T[12 + d] - st->bt0[d]);
-        vt = sqrtf(vt);
-        if (isnan(vr) || isnan(vt)) {
-            st->status = B200ICP_ERR_NAN;
-            st->done = 1;
-            return;
-        }
-        if (vr > prm.max_rotation_norm || vt > prm.max_translation_norm) {
-            st->status = B200ICP_ERR_BOUND;
-            st->done = 1;
-            return;
+        if (prm.use_bound && (((prm.counter_after & 2) != 0) == (phase == 0))) {
+            float qc[4];
+            quat_from_T(T, qc);
+            const float vr = quat_angular_distance(qc, st->bq0);
+            float vt = 0.f;
+            for (int d = 0; d < 3; ++d) vt += (T[12 + d] - st->bt0[d]) * (T[12 + d] - st->bt0[d]);
+            vt = sqrtf(vt);
+            if (isnan(vr) || isnan(vt)) {
+                st->status = B200ICP_ERR_NAN;
+                st->done = 1;
+                return;
+            }
+            if (vr > prm.max_rotation_norm || vt > prm.max_translation_norm) {
+                st->status = B200ICP_ERR_BOUND;
+                st->done = 1;
+                return;
+            }
         }
     }
     if (prm.max_iteration_count <= 0 && !prm.use_differential) iterate = false;

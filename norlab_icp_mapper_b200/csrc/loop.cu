@@ -27,6 +27,8 @@
 // nothing has to be broadcast; each path is run-to-run deterministic.
 #include <cooperative_groups.h>
 
+#include <atomic>
+
 #include "icp_device.cuh"
 #include "knn_device.cuh"
 
@@ -1167,18 +1169,24 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
 template <int MIN, int GK>
 cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
                           int variant_flags, const float* win3, const float* margin3, cudaStream_t s) {
-    static bool attr_set = false;  // per process and instantiation; harmless if repeated
-    if (!attr_set) {
+    // Function attributes are PER DEVICE: one flag per (instantiation, device ordinal).  Contexts on different GPUs of one
+    // process (b200icp_register_batch) each need the opt-in; concurrent contexts may race to set it, which is harmless
+    // (same value, idempotent call), hence atomics only to keep the flags themselves well-defined.
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> per_sm_of[kMaxDevices];  // 0 = not queried yet, else occupancy + 1
+    int dev = 0;
+    cudaError_t ed = cudaGetDevice(&dev);
+    if (ed != cudaSuccess) return ed;
+    const bool cacheable = dev >= 0 && dev < kMaxDevices;
+    int per_sm = cacheable ? per_sm_of[dev].load(std::memory_order_acquire) - 1 : -1;
+    if (per_sm < 0) {
         cudaError_t ea = cudaFuncSetAttribute(icp_loop_kernel<MIN, GK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLoopDynSmem);
         if (ea != cudaSuccess) return ea;
-        attr_set = true;
-    }
-    static int per_sm = -1;  // (queried once per instantiation: the answer does not change)
-    if (per_sm < 0) {
         int q = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, icp_loop_kernel<MIN, GK>, kLoopThreads, kLoopDynSmem);
         if (e != cudaSuccess) return e;
         per_sm = q;
+        if (cacheable) per_sm_of[dev].store(q + 1, std::memory_order_release);
     }
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     const int blocks = std::min(n_sms, kLoopMaxBlocks);

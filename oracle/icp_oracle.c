@@ -1114,45 +1114,52 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
 
         /* LPM TransformationCheckersImpl.cpp: checkers run in YAML order; Counter throws
          * MaxNumIterationsReached which the loop catches (iterate = false). */
-        int all_ok = 1;
-        if (cfg->max_iteration_count > 0) {
-            ++counter;
-            if (counter >= cfg->max_iteration_count) {
-                max_iter_reached = 1;
-                iterate = 0;
-                break;
-            }
-        }
-        if (cfg->use_differential) {
-            const int slot = ds.count % 8;
-            quat_from_R(T_iter, dim, ds.q[slot]);
-            for (int d = 0; d < 3; ++d) ds.t[slot][d] = (d < dim) ? T_iter[dim * n + d] : 0.f;
-            ds.count++;
-            float vr = 0.f, vt = 0.f;
-            if (ds.count > smooth) {
-                for (int j = ds.count - 1; j >= ds.count - smooth; --j) {
-                    const int a = j % 8, bq = (j - 1) % 8;
-                    vr += fabsf(quat_angular_distance(ds.q[a], ds.q[bq]));
-                    const float dx = ds.t[a][0] - ds.t[bq][0], dy = ds.t[a][1] - ds.t[bq][1], dz = ds.t[a][2] - ds.t[bq][2];
-                    vt += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+        int all_ok = 1, counter_fired = 0;
+        for (int phase = 0; phase < 2 && !counter_fired; ++phase) {
+            /* phase 0: the checkers listed before the Counter (cfg->checker_order bits), then the Counter, phase 1: the rest */
+            if (phase == 1 && cfg->max_iteration_count > 0) {
+                ++counter;
+                if (counter >= cfg->max_iteration_count) {
+                    max_iter_reached = 1;
+                    counter_fired = 1;
+                    break;
                 }
-                vr /= (float)smooth;
-                vt /= (float)smooth;
-                if (vr < cfg->min_diff_rot_err && vt < cfg->min_diff_trans_err) all_ok = 0;
             }
-            if (isnan(vr)) FAIL(o, B200ICP_ERR_NAN, "abs rotation norm not a number");
-            if (isnan(vt)) FAIL(o, B200ICP_ERR_NAN, "abs translation norm not a number");
+            if (cfg->use_differential && (((cfg->checker_order & 1) != 0) == (phase == 0))) {
+                const int slot = ds.count % 8;
+                quat_from_R(T_iter, dim, ds.q[slot]);
+                for (int d = 0; d < 3; ++d) ds.t[slot][d] = (d < dim) ? T_iter[dim * n + d] : 0.f;
+                ds.count++;
+                float vr = 0.f, vt = 0.f;
+                if (ds.count > smooth) {
+                    for (int j = ds.count - 1; j >= ds.count - smooth; --j) {
+                        const int a = j % 8, bq = (j - 1) % 8;
+                        vr += fabsf(quat_angular_distance(ds.q[a], ds.q[bq]));
+                        const float dx = ds.t[a][0] - ds.t[bq][0], dy = ds.t[a][1] - ds.t[bq][1], dz = ds.t[a][2] - ds.t[bq][2];
+                        vt += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+                    }
+                    vr /= (float)smooth;
+                    vt /= (float)smooth;
+                    if (vr < cfg->min_diff_rot_err && vt < cfg->min_diff_trans_err) all_ok = 0;
+                }
+                if (isnan(vr)) FAIL(o, B200ICP_ERR_NAN, "abs rotation norm not a number");
+                if (isnan(vt)) FAIL(o, B200ICP_ERR_NAN, "abs translation norm not a number");
+            }
+            if (cfg->use_bound && (((cfg->checker_order & 2) != 0) == (phase == 0))) {
+                float qc[4];
+                quat_from_R(T_iter, dim, qc);
+                const float vr = quat_angular_distance(qc, bound_q0);
+                float vt = 0.f;
+                for (int d = 0; d < dim; ++d) vt += (T_iter[dim * n + d] - bound_t0[d]) * (T_iter[dim * n + d] - bound_t0[d]);
+                vt = sqrtf(vt);
+                if (isnan(vr)) FAIL(o, B200ICP_ERR_NAN, "abs rotation norm not a number");
+                if (isnan(vt)) FAIL(o, B200ICP_ERR_NAN, "abs translation norm not a number");
+                if (vr > cfg->max_rotation_norm || vt > cfg->max_translation_norm) FAIL(o, B200ICP_ERR_BOUND, "limit out of bounds");
+            }
         }
-        if (cfg->use_bound) {
-            float qc[4];
-            quat_from_R(T_iter, dim, qc);
-            const float vr = quat_angular_distance(qc, bound_q0);
-            float vt = 0.f;
-            for (int d = 0; d < dim; ++d) vt += (T_iter[dim * n + d] - bound_t0[d]) * (T_iter[dim * n + d] - bound_t0[d]);
-            vt = sqrtf(vt);
-            if (isnan(vr)) FAIL(o, B200ICP_ERR_NAN, "abs rotation norm not a number");
-            if (isnan(vt)) FAIL(o, B200ICP_ERR_NAN, "abs translation norm not a number");
-            if (vr > cfg->max_rotation_norm || vt > cfg->max_translation_norm) FAIL(o, B200ICP_ERR_BOUND, "limit out of bounds");
+        if (counter_fired) {
+            iterate = 0;
+            break;
         }
         iterate = all_ok;
         if (cfg->max_iteration_count <= 0 && !cfg->use_differential) iterate = 0; /* no checker: LPM would loop forever */

@@ -67,3 +67,31 @@ def test_batched_multi_gpu_nccl(tmp_path):
     for r in range(world):
         got = np.load(tmp_path / f"rank{r}.npz")
         assert np.array_equal(got["poses"], single[0]) and np.array_equal(got["iters"], single[2])
+
+
+def test_register_batch_c_abi_two_contexts_and_map_reuse(oracle):
+    """b200icp_register_batch: pairs dealt over two contexts of one GPU give the poses of one-at-a-time registration bit for
+    bit; a pair without a map registers against the map its context already holds."""
+    cfg = make_config(**CFG)
+    pairs = [_pair(j) for j in range(5)]
+    one = batched.BatchEngine(cfg, devices=(0,), contexts_per_device=1)
+    ref = one.register_many(pairs)
+    one.close()
+    two = batched.BatchEngine(cfg, devices=(0,), contexts_per_device=2)
+    got = two.register_many(pairs)
+    for (Ta, oa, ia, sa), (Tb, ob_, ib, sb) in zip(ref, got):
+        assert sa == sb == 0 and ia == ib and oa == ob_ and np.array_equal(Ta, Tb)
+    # map reuse: contexts 0 / 1 hold the maps of pairs 4 / 3; a map-less pair j goes to context j % 2
+    reuse = two.register_many([dict(reading=pairs[4]["reading"]), dict(reading=pairs[3]["reading"])])
+    assert np.array_equal(reuse[0][0], got[4][0]) and np.array_equal(reuse[1][0], got[3][0])
+    # a failing pair (no normals for point-to-plane) reports its own status and does not stop the others
+    bad = dict(pairs[0], normals=None)
+    mixed = two.register_many([pairs[1], bad, pairs[2]])
+    assert mixed[0][3] == 0 and mixed[2][3] == 0 and mixed[1][3] == 8  # B200ICP_ERR_INVALID_FIELD
+    assert np.array_equal(mixed[0][0], got[1][0]) and np.array_equal(mixed[2][0], got[2][0])
+    two.close()
+    o = oracle.OracleICP(cfg)
+    o.set_map(pairs[2]["map"], pairs[2]["normals"])
+    rc, T, res, _, _ = o.register(pairs[2]["reading"])
+    er, et = synth.pose_error(got[2][0], T)
+    assert rc == 0 and er <= 1e-4 and et <= 1e-3
