@@ -11,7 +11,8 @@ from . import _abi
 from ._abi import Config, Result, Timing
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libb200icp.so")
+# B200ICP_LIB: another build of the same library next to this file (development: the stamped build of tools/gpu_stamps.py)
+SO_PATH = os.path.join(_HERE, os.environ.get("B200ICP_LIB", "libb200icp.so"))
 
 # every symbol include/b200icp.h declares (tests check the export list against the header)
 SYMBOLS = [
