@@ -600,14 +600,14 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         // slower for it; nn_variant bits 12..14 = shift + 1 override it (1 = the full cell id)
         const int cs_bits = (ctx->cfg.nn_variant >> 12) & 7;
         const int cs = cs_bits ? cs_bits - 1 : 3;
-        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s, cs));
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s, cs, &b.state->pmax2_bits));
         const uint64_t n_keys = cs ? (uint64_t)(((v.nx - 1) >> cs) + 1) * (((v.ny - 1) >> cs) + 1) * (((v.nz - 1) >> std::max(cs - 1, 0)) + 1)
                                    : (uint64_t)v.nx * v.ny * v.nz;
         CK(sort_pairs(ctx->map, ctx->map.keys_in, ctx->map.keys_out, ctx->map.vals_in, ctx->map.vals_out, nq, bits_for(n_keys), s));
         CK(launch_gather_reading(b.reading_tmp, ctx->map.vals_out, b.reading, nq, s));
         launches += 4;
     } else {
-        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading, nullptr, nullptr, nullptr, nq, s));
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading, nullptr, nullptr, nullptr, nq, s, 0, &b.state->pmax2_bits));
         launches += 1;
     }
     if (d_reading_normals) {  // the reading's `normals` descriptor follows the reading: same rotation, same order
@@ -650,6 +650,11 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
                       /*want_original_ids=*/0, ctx->cfg.nn_variant & 0xffff, s));
         CK(cudaMemsetAsync(ctx->d_bar_counter, 0, sizeof(unsigned), s));
+        {
+            size_t zoff = 0, zbytes = 0;
+            icp_loop_workspace_zero_range(&zoff, &zbytes);  // the fixed-point accumulators start from zero
+            CK(cudaMemsetAsync(b.fastws + zoff, 0, zbytes, s));
+        }
         CK(cudaEventRecord(ctx->ev_loop0, s));
         CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, ctx->win3, ctx->margin3, nq, s));
         CK(cudaEventRecord(ctx->ev_loop1, s));
@@ -732,6 +737,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         case B200ICP_ERR_BOUND: return fail(ctx, B200ICP_ERR_BOUND, "ConvergenceError: limit out of bounds");
         case B200ICP_ERR_NAN: return fail(ctx, B200ICP_ERR_NAN, "ConvergenceError: abs rotation/translation norm not a number");
         case B200ICP_ERR_TRANSFORM: return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
+        case B200ICP_ERR_NOT_IMPLEMENTED:
+            return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "the error sums left the fixed-point range of the loop kernel (coordinates or normals of absurd magnitude)");
         default: return fail(ctx, out_state->status, "device reported an error");
     }
 }

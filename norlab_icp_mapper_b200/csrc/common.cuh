@@ -94,6 +94,9 @@ struct IcpState {
     int hist_iters;        // iterations that took the two-barrier path (window from a level-0 histogram)
     float dyn_quantile;    // VarTrimmedDist: the ratio tuned for this iteration (outlier.cu)
     float robust_scale;    // RobustOutlierFilter: the current scale estimate (outlier.cu); kept across iterations
+    unsigned int pmax2_bits;  // float bits of max |p|^2 over the finite reading points (refMean frame; prep_reading_kernel): scales the
+                              // loop kernel's fixed-point error sums
+    int sum_overflow;         // loop kernel: a partial sum left the fixed-point range (the registration then fails loudly)
 };
 
 static_assert(sizeof(IcpState) <= 512, "IcpState must fit its 512-byte slot");
@@ -296,7 +299,7 @@ cudaError_t launch_robust_scale(VarTrimScratch& v, const IcpParams& p, int filte
 
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
                                 float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,
-                                uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift = 0);
+                                uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift = 0, unsigned int* d_pmax2_bits = nullptr);
 // dim x N column-major normals -> float4, rotated by the rotation block of Tpre16 (descriptors named `normals` rotate with the cloud)
 cudaError_t launch_prep_normals(const float* d_in, int dim, const float* Tpre16 /*host*/, float4* d_out, int64_t nq, cudaStream_t s);
 cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,
@@ -308,6 +311,8 @@ size_t icp_loop_workspace_bytes();
 // margin3 = {gain, min [m], max [cell edges]}: extra search radius = clamp(gain * the query's last motion, min, max * h)
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
                             int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s);
+// the part of the loop workspace that must be zero when the kernel starts (offset, bytes): cudaMemsetAsync before every launch
+void icp_loop_workspace_zero_range(size_t* offset, size_t* bytes);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
                                   cudaStream_t s, int* launches, cudaEvent_t ev_mid, VarTrimScratch* var_scratch);

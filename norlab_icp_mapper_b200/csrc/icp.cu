@@ -23,16 +23,28 @@ namespace {
 // ---- reading preparation: (dim+1) x N upload -> float4 in the refMean frame ---------------------
 __global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restrict__ in, int rows, int dim, Mat4 Tpre,
                                                            float4* __restrict__ out, GridView g, uint32_t* __restrict__ keys,
-                                                           uint32_t* __restrict__ vals, long long nq, int coarse_shift) {
+                                                           uint32_t* __restrict__ vals, long long nq, int coarse_shift,
+                                                           unsigned int* __restrict__ pmax2_bits) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float n2 = 0.f;
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    if (i < nq) {
+        float4 r;
+        r.x = in[i * rows + 0];
+        r.y = in[i * rows + 1];
+        r.z = (dim == 3) ? in[i * rows + 2] : 0.f;
+        r.w = 1.f;
+        p = apply_T(Tpre.m, r);
+        out[i] = make_float4(p.x, p.y, p.z, 1.f);
+        n2 = p.x * p.x + p.y * p.y + p.z * p.z;
+        if (!(n2 < 3.0e38f)) n2 = 0.f;  // NaN / inf points never pair: they do not count
+    }
+    if (pmax2_bits) {  // (whole warps reach this point: the early exit comes after it)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n2 = fmaxf(n2, __shfl_xor_sync(0xffffffffu, n2, o));
+        if ((threadIdx.x & 31) == 0 && n2 > 0.f) atomicMax(pmax2_bits, __float_as_uint(n2));  // non-negative floats order like their bits
+    }
     if (i >= nq) return;
-    float4 r;
-    r.x = in[i * rows + 0];
-    r.y = in[i * rows + 1];
-    r.z = (dim == 3) ? in[i * rows + 2] : 0.f;
-    r.w = 1.f;
-    const float3 p = apply_T(Tpre.m, r);
-    out[i] = make_float4(p.x, p.y, p.z, 1.f);
     if (keys) {
         const float lim = 16777216.f;
         const int cx = min((int)floorf(fminf(fmaxf((p.x - g.ox) * g.inv_h, 0.f), lim)), g.nx - 1);
@@ -333,14 +345,15 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
 
 // ---- host launchers -------------------------------------------------------------------------------
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16, float4* d_out,
-                                const GridView* g_for_keys, uint32_t* d_keys, uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift) {
+                                const GridView* g_for_keys, uint32_t* d_keys, uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift,
+                                unsigned int* d_pmax2_bits) {
     if (nq <= 0) return cudaSuccess;
     Mat4 T;
     memcpy(T.m, Tpre16, sizeof(T.m));
     GridView g{};
     if (g_for_keys) g = *g_for_keys;
     prep_reading_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, rows, dim, T, d_out, g, g_for_keys ? d_keys : nullptr,
-                                                                      d_vals, (long long)nq, coarse_shift);
+                                                                      d_vals, (long long)nq, coarse_shift, d_pmax2_bits);
     return cudaGetLastError();
 }
 

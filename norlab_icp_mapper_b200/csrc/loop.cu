@@ -27,7 +27,9 @@
 // nothing has to be broadcast; each path is run-to-run deterministic.
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 
 #include "icp_device.cuh"
 #include "knn_device.cuh"
@@ -79,7 +81,16 @@ constexpr int kCandCap = 2048;  // candidates in total (2 per thread after the b
 constexpr size_t kFastCountsOff = 0;                                                        // uint4 [2][kLoopMaxBlocks]
 constexpr size_t kFastPartialsOff = kFastCountsOff + 2 * kLoopMaxBlocks * sizeof(uint4);    // double [2][kLoopMaxBlocks][kAccSlots]
 constexpr size_t kFastCandOff = kFastPartialsOff + 2 * (size_t)kLoopMaxBlocks * kAccSlots * sizeof(double);  // float4 [2][kLoopMaxBlocks][kSegCap][2]
-constexpr size_t kFastBytes = kFastCandOff + 2 * (size_t)kLoopMaxBlocks * kSegCap * 2 * sizeof(float4);
+constexpr size_t kFastCandEnd = kFastCandOff + 2 * (size_t)kLoopMaxBlocks * kSegCap * 2 * sizeof(float4);
+// Error sums of the pairs whose fate is certain before the barrier: ONE set of 64-bit fixed-point accumulators in global
+// memory, added to with integer atomics (associative: the result does not depend on the arrival order, so poses stay
+// run-to-run bitwise deterministic) instead of 148 per-CTA records that every CTA had to read back and reduce.  One slot
+// per 128-byte line (the atomics and the read-back of different slots go to different L2 slices), three buffers used
+// round-robin (see the zeroing protocol at the barrier).
+constexpr int kIsumStride = 16;  // unsigned long long per slot line
+constexpr int kIsumBufs = 3;
+constexpr size_t kFastIsumOff = (kFastCandEnd + 127) / 128 * 128;                           // unsigned long long [3][kAccSlots][16]
+constexpr size_t kFastBytes = kFastIsumOff + (size_t)kIsumBufs * kAccSlots * kIsumStride * sizeof(unsigned long long);
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -87,17 +98,17 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     return v;
 }
 
-// Monotonic counter barrier: the k-th barrier completes when the counter reaches k * gridDim.x.
+// Monotonic counter barrier: the k-th barrier completes when the counter reaches k * gridDim.x.  Arrival is one
+// release-reduction (no round trip for a returned value; cumulativity orders the CTA's earlier writes and atomics, which
+// thread 0 observed through the __syncthreads, before it), the wait polls with acquire loads.
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
     __syncthreads();
     if (threadIdx.x == 0) {
         epoch += 1;
-        __threadfence();
-        atomicAdd(counter, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
         const unsigned target = epoch * gridDim.x;
         while (ld_acquire_u32(counter) < target) {
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     int32_t* __restrict__ mpos, float* __restrict__ md2, IcpState* __restrict__ gst, uint32_t* __restrict__ hist,
                     double* __restrict__ partials, unsigned* __restrict__ bar_counter, float* __restrict__ trace, int max_iters,
                     int variant_flags, char* __restrict__ fastws, float win_gain, float win_floor, float win_max,
-                    float4* __restrict__ sp_pp, float4* __restrict__ sp_nv, float margin_gain, float margin_min, float margin_max) {
+                    float4* __restrict__ sp_pp, float4* __restrict__ sp_nv, float margin_gain, float margin_min, float margin_max, float q_bound) {
     constexpr int NS = SumLayout<MIN>::N;
     __shared__ IcpState st;
     __shared__ uint32_t sh[kSel0Bins];   // radix level 0 histogram, then staging / the candidate list
@@ -239,6 +250,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     __shared__ uint32_t s_tot[4];                   // fast path: totals {below, candidates, above, max candidates per CTA}
     __shared__ float s_Tprev[16];                   // T_iter the bounds L of the match cache refer to
     __shared__ uint32_t s_nlist;
+    __shared__ double s_scale[kAccSlots], s_inv_scale[kAccSlots];  // fixed-point scale of each error sum (see kFastIsumOff)
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* const s_r4 = reinterpret_cast<float4*>(dyn_smem);
     float4* const s_pp = s_r4 + kCacheCap;   // (x, y, z, bit-cast position) of the matched map point
@@ -251,6 +263,35 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         reinterpret_cast<uint32_t*>(&st)[i] = reinterpret_cast<const uint32_t*>(gst)[i];
     __syncthreads();
     const int nq = st.nq;
+    if (tid < kAccSlots) {
+        // A-priori magnitude of every sum: |reading point| <= Pb, |map point| <= Qb, |p - q| <= Db, normals nominally unit.  The
+        // scale puts (pairs x bound) at 2^50 of the 2^63 range: 4096 x headroom for motion and non-unit normals, and a
+        // resolution of 2^-50 of the worst case -- far below the fp32 rounding of the per-warp sums that are added.
+        float Db = sqrtf(prm.max_r2);  // inf when the matcher is unbounded
+        float Pb = sqrtf(__uint_as_float(st.pmax2_bits)) + 1.f;
+        if (Db < 3.0e38f) Pb = fminf(Pb, q_bound + Db);  // a PAIRED reading point lies within maxDist of a map point
+        else Db = Pb + q_bound;
+        float bound = 1.f;
+        if (MIN == 0) {
+            if (tid < 21) {
+                int c = 0;
+                while ((c + 1) * (c + 2) / 2 <= tid) ++c;
+                const int r = tid - c * (c + 1) / 2;
+                bound = (c < 3 ? Pb : 1.f) * (r < 3 ? Pb : 1.f);
+            } else if (tid < 27) {
+                bound = (tid - 21 < 3 ? Pb : 1.f) * Db;
+            }
+        } else if (MIN == 1) {
+            if (tid >= 1 && tid <= 3) bound = Pb;
+            else if (tid >= 4 && tid <= 6) bound = q_bound;
+            else if (tid >= 7 && tid <= 15) bound = Pb * q_bound;
+        }
+        int e2 = 0;
+        frexp((double)nq * (double)prm.knn * fmax((double)bound, 1e-30), &e2);
+        const int shift = max(-60, min(60, 50 - e2));
+        s_scale[tid] = ldexp(1.0, shift);
+        s_inv_scale[tid] = ldexp(1.0, -shift);
+    }
     unsigned epoch = 0;
     uint32_t n_runs = 0, n_hist = 0;  // publish/finish rounds (stage-1 histograms) so far: parity selects the double buffer
     const bool use_quantile = prm.quantile_filter >= 0;
@@ -668,9 +709,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 continue;
             }
             const int par = (int)(n_runs & 1u);
+            unsigned long long* const isum_base = reinterpret_cast<unsigned long long*>(fastws + kFastIsumOff);
+            unsigned long long* const my_isum = isum_base + (size_t)(n_runs % kIsumBufs) * kAccSlots * kIsumStride;
+            // (used again in two rounds: every CTA finished reading it before it arrived at THIS round's barrier, and the next
+            //  additions to it come after the NEXT round's barrier, which CTA 0 only reaches after this zeroing)
+            unsigned long long* const stale_isum = isum_base + (size_t)((n_runs + 2) % kIsumBufs) * kAccSlots * kIsumStride;
             n_runs += 1;
             uint4* my_counts = reinterpret_cast<uint4*>(fastws + kFastCountsOff) + (size_t)par * kLoopMaxBlocks;
-            double* my_partials = reinterpret_cast<double*>(fastws + kFastPartialsOff) + (size_t)par * kLoopMaxBlocks * kAccSlots;
             float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kLoopMaxBlocks * kSegCap * 2;
             uint32_t c_below = 0, c_above = 0;
             uint32_t seg_count = 0;  // uniform: candidates of this CTA so far
@@ -760,13 +805,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 }
             }
             __syncthreads();
-            if (tid < kAccSlots) {
+            if (tid < NS) {
                 double v = 0.0;
-                if (tid < NS) {
 #pragma unroll
-                    for (int wv = 0; wv < kLoopWarps; ++wv) v += s_part[wv][tid];
-                }
-                __stcg(my_partials + (size_t)blockIdx.x * kAccSlots + tid, v);
+                for (int wv = 0; wv < kLoopWarps; ++wv) v += s_part[wv][tid];
+                const double sv = v * s_scale[tid];
+                if (!(fabs(sv) < 4.0e18)) atomicAdd(my_isum + (kAccSlots - 1) * kIsumStride, 1ull);  // out of range (or NaN): flagged for everyone
+                else if (v != 0.0) atomicAdd(my_isum + tid * kIsumStride, (unsigned long long)__double2ll_rn(sv));
             }
             if (tid == 0) __stcg(my_counts + blockIdx.x, make_uint4(s_tot[0], seg_count, s_tot[2], 0u));
             if (stamper) B200_STAMP(gst, 22);
@@ -774,6 +819,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             if (stamper) B200_STAMP(gst, 23);
             // ---- after the barrier: identical work in every CTA ---------------------------------------
             const int nblk = (int)gridDim.x;
+            if (blockIdx.x == 0 && tid < kAccSlots) stale_isum[tid * kIsumStride] = 0ull;
+            // the certain pairs' sums (one line per slot; consumed after the select, the load is in flight meanwhile)
+            const unsigned long long isum_mine = tid < kAccSlots ? __ldcg(my_isum + tid * kIsumStride) : 0ull;
             {
                 uint4 c = make_uint4(0u, 0u, 0u, 0u);
                 if (tid < nblk) c = __ldcg(my_counts + tid);
@@ -817,13 +865,6 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             dbg_ncand = n_cand;
             dbg_nbelow = n_below;
             if (ok) {
-                // the per-CTA partial sums do not depend on the select: fetch them now, add them after it
-                double pv[(kLoopMaxBlocks + kLoopWarps - 1) / kLoopWarps];
-#pragma unroll
-                for (int j = 0; j < (kLoopMaxBlocks + kLoopWarps - 1) / kLoopWarps; ++j) {
-                    const int bq = warp + j * kLoopWarps;
-                    pv[j] = bq < nblk ? __ldcg(my_partials + (size_t)bq * kAccSlots + lane) : 0.0;
-                }
                 float acc2[NS];
 #pragma unroll
                 for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
@@ -906,20 +947,28 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc2[i] : 0.f;
                     // (only the warps that hold candidates have anything to add: warp-uniform skip of the 31-shuffle reduction)
                     const float tot = (use_quantile && (uint32_t)(warp * 32) < n_cand) ? warp_reduce_32slots(v32, lane) : 0.f;
-                    const int slot = lane, part = warp;
-                    double v = (double)tot;
-#pragma unroll
-                    for (int j = 0; j < (kLoopMaxBlocks + kLoopWarps - 1) / kLoopWarps; ++j) v += pv[j];
-                    s_red[part][slot] = v;
+                    s_red[warp][lane] = (double)tot;
                 }
                 __syncthreads();
                 if (tid < kAccSlots) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int part = 0; part < kLoopWarps; ++part) v += s_red[part][tid];
+                    // certain pairs (exact integer total, order-free) + the candidates at or below the limit (fixed order)
+                    double v = (double)(long long)isum_mine * s_inv_scale[tid];
+                    if (use_quantile) {
+                        const int nparts = min(kLoopWarps, (int)((n_cand + 31u) >> 5));
+                        for (int part = 0; part < nparts; ++part) v += s_red[part][tid];
+                    }
                     s_sum[tid] = v;
                 }
                 __syncthreads();
+                if (s_sum[kAccSlots - 1] != 0.0) {  // a sum left the fixed-point range somewhere: same verdict in every CTA
+                    if (tid == 0) {
+                        st.status = B200ICP_ERR_NOT_IMPLEMENTED;
+                        st.done = 1;
+                    }
+                    __syncthreads();
+                    fatal = true;
+                    break;
+                }
                 if (stamper) B200_STAMP(gst, 13);
                 fast_done = true;
                 if (tid == 0) {
@@ -1205,14 +1254,30 @@ cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
     float4* sp_pp = b.spill_pp;
     float4* sp_nv = b.spill_nv;
     float margin_gain = margin3[0], margin_min = margin3[1], margin_max = margin3[2] * g.view.h;
+    // largest norm a map point can have in the (mean-centred) frame of the index: the far corner of the grid's box
+    float q_bound = 0.f;
+    {
+        const float lo[3] = {view.ox, view.oy, view.oz};
+        const float ext[3] = {view.nx * view.h, view.ny * view.h, view.nz * view.h};
+        double q2 = 0.0;
+        for (int d = 0; d < 3; ++d) {
+            const double m = std::max(std::fabs((double)lo[d]), std::fabs((double)lo[d] + ext[d]));
+            q2 += m * m;
+        }
+        q_bound = (float)std::sqrt(q2) + 1.f;
+    }
     void* args[] = {&prm, &view, &nrm, &reading, &mpos, &md2, &st, &hist, &partials, &bar_counter, &trace, &max_iters, &variant_flags,
-                    &fastws, &win_gain, &win_floor, &win_max, &sp_pp, &sp_nv, &margin_gain, &margin_min, &margin_max};
+                    &fastws, &win_gain, &win_floor, &win_max, &sp_pp, &sp_nv, &margin_gain, &margin_min, &margin_max, &q_bound};
     return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN, GK>, dim3(blocks), dim3(kLoopThreads), args, kLoopDynSmem, s);
 }
 
 }  // namespace
 
 size_t icp_loop_workspace_bytes() { return kFastBytes; }
+void icp_loop_workspace_zero_range(size_t* offset, size_t* bytes) {
+    *offset = kFastIsumOff;
+    *bytes = kFastBytes - kFastIsumOff;
+}
 
 template <int GK>
 cudaError_t launch_loop_g(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
