@@ -503,6 +503,16 @@ int32_t b200icp_debug_loop_record(b200icp_ctx* ctx, uint32_t* out, int32_t itera
     return B200ICP_OK;
 }
 
+/* development aid (not in the public header; meaningful in the stamped build only): 32 x uint64 %globaltimer stamps per CTA of
+ * the loop kernel's last iteration */
+int32_t b200icp_debug_cta_stamps(b200icp_ctx* ctx, unsigned long long* out, int32_t n_ctas) {
+    if (!ctx || !out || n_ctas < 0 || n_ctas > kMaxAccBlocks || !ctx->buf.partials) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->buf.partials, (size_t)n_ctas * kAccSlots * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ICP_OK;
+}
+
 int64_t b200icp_map_size(const b200icp_ctx* ctx) { return (ctx && ctx->has_map) ? ctx->map_n : 0; }
 
 int32_t b200icp_get_map_mean(const b200icp_ctx* ctx, float* mean3) {

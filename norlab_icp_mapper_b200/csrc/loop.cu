@@ -37,6 +37,21 @@
 namespace b200 {
 namespace {
 
+// development (stamped build only): per-CTA %globaltimer stamps of the LAST iteration, 32 slots per CTA in the `partials`
+// buffer (idle on the paths that are being looked at); read back with b200icp_debug_cta_stamps
+#ifdef B200ICP_STAMPS
+#define B200_CTA_STAMP(buf, k)                                                                   \
+    do {                                                                                         \
+        if (threadIdx.x == 0) {                                                                  \
+            unsigned long long t_;                                                               \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                               \
+            reinterpret_cast<unsigned long long*>(buf)[(size_t)blockIdx.x * kAccSlots + (k)] = t_; \
+        }                                                                                        \
+    } while (0)
+#else
+#define B200_CTA_STAMP(buf, k) do { } while (0)
+#endif
+
 constexpr int kLoopThreads = 1024;
 constexpr int kLoopWarps = kLoopThreads / 32;
 constexpr int kLoopG = 4;                       // lanes per query in the search phase
@@ -346,6 +361,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         if (st.done) break;  // identical in every CTA
         const bool stamper = blockIdx.x == 0 && tid == 0;
         if (stamper) B200_STAMP(gst, 20);
+        B200_CTA_STAMP(partials, 0);
         const bool searched = st.iter > 0;  // iteration 0's matches come from the cold kernel
         unsigned long long t_iter0 = 0;
         if (blockIdx.x == 0 && tid == 0) {
@@ -638,6 +654,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             }
         }
         if (stamper) B200_STAMP(gst, 30);
+        B200_CTA_STAMP(partials, 1);
         if (searched && tid < 16) s_Tprev[tid] = st.T[tid];  // the bounds now refer to this iteration's query positions
         __syncthreads();
         if (blockIdx.x == 0 && tid == 0 && searched) {
@@ -684,7 +701,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         s_cnt = 0;
                     }
                     if (stamper) B200_STAMP(gst, 24);
+                    B200_CTA_STAMP(partials, 2);
                     grid_barrier(bar_counter, epoch);
+                    B200_CTA_STAMP(partials, 3);
                     if (stamper) B200_STAMP(gst, 25);
                     const uint32_t total = loop_pick<false>(h1, kSel0Bins, 0u, true, prm.quantile, &s_bin, &s_res, &s_cnt, s_warp);
                     const uint32_t b1 = s_bin;
@@ -815,7 +834,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             }
             if (tid == 0) __stcg(my_counts + blockIdx.x, make_uint4(s_tot[0], seg_count, s_tot[2], 0u));
             if (stamper) B200_STAMP(gst, 22);
+            B200_CTA_STAMP(partials, 4);
             grid_barrier(bar_counter, epoch);
+            B200_CTA_STAMP(partials, 5);
             if (stamper) B200_STAMP(gst, 23);
             // ---- after the barrier: identical work in every CTA ---------------------------------------
             const int nblk = (int)gridDim.x;
@@ -1200,6 +1221,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         }
         __syncthreads();
         if (stamper) B200_STAMP(gst, 14);
+        B200_CTA_STAMP(partials, 6);
     }
     if (blockIdx.x == 0) {
         if (tid == 0) {
