@@ -501,7 +501,10 @@ def bench_batched(env, pairs_host, n_pairs_total, passes=3):
     assert len(idx) == len(mine)
     by_j = dict(zip(idx, mine))
     results = {}
-    for n_ctx in (2, 1):
+    default_ctx = int(os.environ.get("B200ICP_BATCH_CONTEXTS", "2"))
+    for n_ctx in (default_ctx, 1, 3, 4):
+        if n_ctx in results:
+            continue
         eng = batched.BatchEngine(cfg, devices=(env.local_rank,), contexts_per_device=n_ctx)
         batched.register_batch(lambda j: by_j[j], n_pairs_total, eng, rank=env.rank, world=env.world, dist=env.dist, device=env.device)
         env.barrier()
@@ -520,8 +523,8 @@ def bench_batched(env, pairs_host, n_pairs_total, passes=3):
         results[n_ctx] = dict(ms=ms, poses=poses, setmap_ms=float(np.mean([lr[i].setmap_ms for i in range(len(mine))])),
                               register_ms=float(np.mean([lr[i].register_ms for i in range(len(mine))])))
         eng.close()
-        if n_ctx == 1 or env.world > 1:
-            break  # the single-context figure is an N = 1 explanation of the overlap, not part of the scaling series
+        if env.world > 1:
+            break  # the other context counts are an N = 1 explanation of the overlap, not part of the scaling series
     # pinned H2D rate of this GPU (explains the upload share)
     buf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
     dst = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
@@ -535,7 +538,7 @@ def bench_batched(env, pairs_host, n_pairs_total, passes=3):
     b.synchronize()
     h2d_gbs = 4 * (64 << 20) / (a.elapsed_time(b) * 1e-3) / 1e9
     bytes_per_pair = 1_000_000 * (16 + 12) + 200_000 * 16
-    r2 = results[2]
+    r2 = results[default_ctx]
     per_pair_ms = r2["ms"] / passes / max(len(mine), 1)
     upload_ms = bytes_per_pair / (h2d_gbs * 1e9) * 1e3
     gpu_ms = r2["setmap_ms"] + r2["register_ms"]
@@ -544,8 +547,8 @@ def bench_batched(env, pairs_host, n_pairs_total, passes=3):
     out = {"metric": "pairs/sec (200k-pt scan vs 1M-pt submap: setMap + 30-iteration ICP per pair), %d pairs sharded over the GPUs" % n_pairs_total,
            "value": n_pairs_total * passes / (r2["ms"] * 1e-3), "unit": "pairs/s", "n_gpus": env.world, "scaling": "strong",
            "pairs": n_pairs_total, "pairs_this_rank": len(mine), "passes_timed": passes, "ms_per_batch": r2["ms"] / passes,
-           "entry_point": "b200icp_register_batch (2 contexts per GPU; pair j -> rank j mod N; NCCL all_gather of the poses inside the "
-                          "timed region; pinned host submaps)",
+           "entry_point": "b200icp_register_batch (%d contexts per GPU, each registration loop on its share of the SMs; pair j -> rank j "
+                          "mod N; NCCL all_gather of the poses inside the timed region; pinned host submaps)" % default_ctx,
            "per_pair_ms_this_rank": per_pair_ms,
            "breakdown_ms_per_pair": {"h2d_upload_at_measured_rate": upload_ms, "setmap_device": r2["setmap_ms"],
                                      "register_device": r2["register_ms"], "h2d_bytes": bytes_per_pair, "h2d_gbs_pinned": h2d_gbs},
@@ -555,9 +558,12 @@ def bench_batched(env, pairs_host, n_pairs_total, passes=3):
                       "host-side serialisation (synchronous set_map / register calls per context): per-pair time exceeds both the "
                       "upload and the GPU work",
            "max_pose_error_vs_truth": {"rad": max(e[0] for e in errs), "m": max(e[1] for e in errs)}}
-    if 1 in results:
-        out["one_context_per_gpu"] = {"value": n_pairs_total * passes / (results[1]["ms"] * 1e-3),
-                                      "per_pair_ms": results[1]["ms"] / passes / max(len(mine), 1)}
+    out["contexts_per_gpu"] = default_ctx
+    if len(results) > 1:
+        out["contexts_per_gpu_sweep"] = {str(k): {"value": n_pairs_total * passes / (v["ms"] * 1e-3),
+                                                  "per_pair_ms": v["ms"] / passes / max(len(mine), 1),
+                                                  "setmap_device_ms": v["setmap_ms"], "register_device_ms": v["register_ms"]}
+                                         for k, v in sorted(results.items())}
     return out
 
 

@@ -214,6 +214,10 @@ const char* b200icp_last_error(const b200icp_ctx* ctx); /* ctx may be NULL: crea
 void* b200icp_stream(b200icp_ctx* ctx);                 /* the cudaStream_t all work is issued on */
 int32_t b200icp_set_profiling(b200icp_ctx* ctx, int32_t on); /* per-kernel event timing (adds syncs) */
 int32_t b200icp_get_timing(const b200icp_ctx* ctx, b200icp_timing* out);
+/* How many SMs the registration loop of this context may occupy (it is a persistent kernel with one CTA per SM); 0 = all
+ * (default).  Contexts that work side by side on one GPU -- b200icp_register_batch does this by itself -- or a registration
+ * that should leave room for a map update running on another context (Mapper isOnline, Mapper.cpp:280-283) take a share. */
+int32_t b200icp_set_sm_share(b200icp_ctx* ctx, int32_t n_sms);
 
 /* icp.setMap(cloud) -- Map.cpp:111,178,528,581.  Copies the cloud, mean-centres it
  * (T_refIn_refMean) and builds the spatial index that replaces libnabo's kd-tree.

@@ -17,7 +17,7 @@ SO_PATH = os.path.join(_HERE, os.environ.get("B200ICP_LIB", "libb200icp.so"))
 # every symbol include/b200icp.h declares (tests check the export list against the header)
 SYMBOLS = [
     "b200icp_abi_version", "b200icp_config_default", "b200icp_create", "b200icp_destroy",
-    "b200icp_last_error", "b200icp_stream", "b200icp_set_profiling", "b200icp_get_timing",
+    "b200icp_last_error", "b200icp_stream", "b200icp_set_profiling", "b200icp_get_timing", "b200icp_set_sm_share",
     "b200icp_set_map", "b200icp_set_map_device", "b200icp_map_size", "b200icp_register",
     "b200icp_register_device", "b200icp_register_normals", "b200icp_register_batch", "b200icp_match", "b200icp_knn", "b200icp_transform",
     "b200icp_transform_device", "b200icp_get_map_mean", "b200icp_get_grid_info",
@@ -59,6 +59,7 @@ def load():
     L.b200icp_stream.restype = vp
     L.b200icp_set_profiling.argtypes = [vp, i32]
     L.b200icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.b200icp_set_sm_share.argtypes = [vp, i32]
     L.b200icp_set_map.argtypes = [vp, vp, i32, vp, i64]
     L.b200icp_set_map_device.argtypes = [vp, vp, i32, vp, i64]
     L.b200icp_map_size.argtypes = [vp]

@@ -41,6 +41,7 @@ struct b200icp_ctx {
     int* d_scalar_nq = nullptr;
     unsigned* d_bar_counter = nullptr;
     int n_sms = 148;
+    int sm_share = 0;  // b200icp_set_sm_share: CTAs (= SMs) the persistent loop kernel may occupy; 0 = all of them
     float* d_scan = nullptr;     // the device-resident scan slot (b200icp_scan_*)
     int64_t cap_scan = 0, n_scan = 0;
     float* d_kth = nullptr;      // incremental SurfaceNormal: squared k-th neighbour distance per store point
@@ -464,6 +465,12 @@ int32_t b200icp_set_profiling(b200icp_ctx* ctx, int32_t on) {
     return B200ICP_OK;
 }
 
+int32_t b200icp_set_sm_share(b200icp_ctx* ctx, int32_t n_sms) {
+    if (!ctx || n_sms < 0) return B200ICP_ERR_INVALID_ARG;
+    ctx->sm_share = n_sms;
+    return B200ICP_OK;
+}
+
 int32_t b200icp_get_timing(const b200icp_ctx* ctx, b200icp_timing* out) {
     if (!ctx || !out) return B200ICP_ERR_INVALID_ARG;
     *out = ctx->timing;
@@ -666,7 +673,8 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
             CK(cudaMemsetAsync(b.fastws + zoff, 0, zbytes, s));
         }
         CK(cudaEventRecord(ctx->ev_loop0, s));
-        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->n_sms, ctx->cfg.nn_variant, ctx->win3, ctx->margin3, nq, s));
+        CK(launch_icp_loop(p, ctx->map, b, ctx->d_bar_counter, hard_cap, ctx->sm_share > 0 ? std::min(ctx->sm_share, ctx->n_sms) : ctx->n_sms,
+                           ctx->cfg.nn_variant, ctx->win3, ctx->margin3, nq, s));
         CK(cudaEventRecord(ctx->ev_loop1, s));
         launches += 2;
         CK(cudaMemcpyAsync(out_state, b.state, kStateBytes, cudaMemcpyDeviceToHost, s));
@@ -831,6 +839,15 @@ int32_t b200icp_register_batch(b200icp_ctx* const* ctxs, int32_t n_ctx, const b2
             if (ctxs[d] == ctxs[c]) return fail(ctxs[0], B200ICP_ERR_INVALID_ARG, "register_batch: the same context listed twice");
     }
     const int dim = ctxs[0]->cfg.dim, rows = dim + 1;
+    // Contexts that share a GPU split its SMs: each registration loop is a persistent kernel with one CTA per SM it may use, so
+    // two half-size loops run side by side (their barrier waits and serial phases overlap) instead of one after the other.
+    std::vector<int> saved_share(n_ctx);
+    for (int c = 0; c < n_ctx; ++c) {
+        saved_share[c] = ctxs[c]->sm_share;
+        int on_device = 0;
+        for (int d = 0; d < n_ctx; ++d) on_device += ctxs[d]->device == ctxs[c]->device;
+        if (on_device > 1 && n_pairs > 1 && saved_share[c] == 0) ctxs[c]->sm_share = std::max(1, ctxs[c]->n_sms / on_device);
+    }
     auto work = [&](int c) {
         b200icp_ctx* ctx = ctxs[c];
         for (int64_t j = c; j < n_pairs; j += n_ctx) {
@@ -858,6 +875,7 @@ int32_t b200icp_register_batch(b200icp_ctx* const* ctxs, int32_t n_ctx, const b2
         work(0);
         for (auto& t : th) t.join();
     }
+    for (int c = 0; c < n_ctx; ++c) ctxs[c]->sm_share = saved_share[c];
     for (int64_t j = 0; j < n_pairs; ++j)
         if (out[j].status != B200ICP_OK) return out[j].status;
     return B200ICP_OK;

@@ -265,6 +265,10 @@ class ICP:
     def stream(self):
         return self._L.b200icp_stream(self._h)
 
+    def set_sm_share(self, n_sms):
+        """SMs the registration loop may occupy (0 = all): contexts working side by side on one GPU each take a share."""
+        self._check(self._L.b200icp_set_sm_share(self._h, int(n_sms)))
+
     def set_profiling(self, on=True):
         self._check(self._L.b200icp_set_profiling(self._h, int(on)))
 

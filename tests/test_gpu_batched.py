@@ -64,14 +64,18 @@ def test_batched_multi_gpu_nccl(tmp_path):
     fn = batched.gpu_register_fn(cfg, 0)
     single = batched.register_batch(_pair, n_pairs, fn)
     fn.close()
+    first = np.load(tmp_path / "rank0.npz")
     for r in range(world):
         got = np.load(tmp_path / f"rank{r}.npz")
-        assert np.array_equal(got["poses"], single[0]) and np.array_equal(got["iters"], single[2])
+        assert np.array_equal(got["poses"], first["poses"]) and np.array_equal(got["iters"], single[2])  # every rank holds the same gathered result
+    for j in range(n_pairs):  # (a rank's contexts split the SMs only when it has several pairs: sums sliced differently -> rounding)
+        er, et = synth.pose_error(first["poses"][j], single[0][j])
+        assert er <= 1e-6 and et <= 1e-5, (j, er, et)
 
 
 def test_register_batch_c_abi_two_contexts_and_map_reuse(oracle):
-    """b200icp_register_batch: pairs dealt over two contexts of one GPU give the poses of one-at-a-time registration bit for
-    bit; a pair without a map registers against the map its context already holds."""
+    """b200icp_register_batch: pairs dealt over two contexts of one GPU give the poses of one-at-a-time registration; a pair
+    without a map registers against the map its context already holds."""
     cfg = make_config(**CFG)
     pairs = [_pair(j) for j in range(5)]
     one = batched.BatchEngine(cfg, devices=(0,), contexts_per_device=1)
@@ -80,7 +84,11 @@ def test_register_batch_c_abi_two_contexts_and_map_reuse(oracle):
     two = batched.BatchEngine(cfg, devices=(0,), contexts_per_device=2)
     got = two.register_many(pairs)
     for (Ta, oa, ia, sa), (Tb, ob_, ib, sb) in zip(ref, got):
-        assert sa == sb == 0 and ia == ib and oa == ob_ and np.array_equal(Ta, Tb)
+        # two contexts on one GPU split its SMs: the error sums are sliced differently, poses agree to rounding
+        er, et = synth.pose_error(Ta, Tb)
+        assert sa == sb == 0 and ia == ib and abs(oa - ob_) < 1e-5 and er <= 1e-6 and et <= 1e-5
+    again = two.register_many(pairs)
+    assert all(np.array_equal(a[0], b[0]) for a, b in zip(got, again))  # run-to-run deterministic
     # map reuse: contexts 0 / 1 hold the maps of pairs 4 / 3; a map-less pair j goes to context j % 2
     reuse = two.register_many([dict(reading=pairs[4]["reading"]), dict(reading=pairs[3]["reading"])])
     assert np.array_equal(reuse[0][0], got[4][0]) and np.array_equal(reuse[1][0], got[3][0])
