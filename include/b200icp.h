@@ -245,6 +245,12 @@ int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_
 int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq,
                                  const float* reading_normals, const float* T_init, float* T_out, b200icp_result* result);
 
+/* icp(input) for a reading that carries descriptors the ICP chain reads: `normals` (see above) and / or `maxSearchDist` (1 x nq):
+ * libpointmatcher's KDTreeMatcher searches every reading point within its own radius when the reading has that descriptor, and
+ * the matcher's maxDist is then not used (libnabo's knn overload with a vector of radii).  Either pointer may be NULL. */
+int32_t b200icp_register_descriptors(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq, const float* reading_normals,
+                                     const float* reading_max_search_dist, const float* T_init, float* T_out, b200icp_result* result);
+
 /* ---- batched registration (BASELINE.json config 5; no reference counterpart: the reference aligns one scan at a time) ----
  * Independent scan <-> submap alignments.  One pair = `icp.setMap(submap)` (Map.cpp:111) followed by `icp(reading)`
  * (Mapper.cpp:213) on the same ICP object; pairs do not interact. */

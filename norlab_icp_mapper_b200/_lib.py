@@ -19,7 +19,7 @@ SYMBOLS = [
     "b200icp_abi_version", "b200icp_config_default", "b200icp_create", "b200icp_destroy",
     "b200icp_last_error", "b200icp_stream", "b200icp_set_profiling", "b200icp_get_timing", "b200icp_set_sm_share",
     "b200icp_set_map", "b200icp_set_map_device", "b200icp_map_size", "b200icp_register",
-    "b200icp_register_device", "b200icp_register_normals", "b200icp_register_batch", "b200icp_match", "b200icp_knn", "b200icp_transform",
+    "b200icp_register_device", "b200icp_register_normals", "b200icp_register_descriptors", "b200icp_register_batch", "b200icp_match", "b200icp_knn", "b200icp_transform",
     "b200icp_transform_device", "b200icp_get_map_mean", "b200icp_get_grid_info",
     "b200icp_set_trace", "b200icp_get_trace", "b200icp_map_insert_point_distance",
     "b200icp_map_surface_normals", "b200icp_cloud_surface_normals", "b200icp_map_window", "b200icp_map_commit", "b200icp_map_counts",
@@ -67,6 +67,7 @@ def load():
     L.b200icp_register.argtypes = [vp, vp, i32, i64, vp, vp, C.POINTER(Result)]
     L.b200icp_register_device.argtypes = [vp, vp, i32, i64, vp, vp, C.POINTER(Result)]
     L.b200icp_register_normals.argtypes = [vp, vp, i32, i64, vp, vp, vp, C.POINTER(Result)]
+    L.b200icp_register_descriptors.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp, C.POINTER(Result)]
     L.b200icp_register_batch.argtypes = [C.POINTER(vp), i32, C.POINTER(_abi.Pair), i64, C.POINTER(_abi.PairResult)]
     L.b200icp_match.argtypes = [vp, vp, i32, i64, vp, vp]
     L.b200icp_knn.argtypes = [vp, vp, i32, i64, vp, i32, i64, i32, i32, f32, vp, vp]

@@ -183,6 +183,9 @@ int32_t validate_config(const b200icp_config* c, std::string& why) {
     if (quant > 1) return why = "at most one quantile-based outlier filter (Trimmed, VarTrimmed or Median) per chain", B200ICP_ERR_NOT_IMPLEMENTED;
     if (c->minimizer < B200ICP_MIN_POINT_TO_PLANE || c->minimizer > B200ICP_MIN_IDENTITY) return why = "unknown error minimizer", B200ICP_ERR_INVALID_ARG;
     if (c->use_differential && (c->smooth_length < 1 || c->smooth_length > 7)) return why = "smoothLength must be in [1, 7]", B200ICP_ERR_INVALID_ARG;
+    if ((c->minimizer_flags & 3) == 3) return why = "Force 2D cannot be used together with force4DOF.", B200ICP_ERR_INVALID_ARG;  // LPM ConfigurationError
+    if (c->minimizer_flags & ~3) return why = "unknown minimizer flag", B200ICP_ERR_INVALID_ARG;
+    if (c->conventions & ~3) return why = "unknown conventions bit", B200ICP_ERR_INVALID_ARG;
     return B200ICP_OK;
 }
 
@@ -375,6 +378,12 @@ int32_t b200icp_create(const b200icp_config* cfg, int32_t device, b200icp_ctx** 
     p.max_rotation_norm = cfg->max_rotation_norm;
     p.max_translation_norm = cfg->max_translation_norm;
     p.counter_after = cfg->checker_order & 3;
+    p.min_flags = (cfg->dim == 3 && cfg->minimizer == B200ICP_MIN_POINT_TO_PLANE) ? (cfg->minimizer_flags & 3) : 0;
+    // conventions (SURVEY App. A "(?)" items): strict '<' at maxDist == '<=' at the next float below; Median factor on the distance
+    if ((cfg->conventions & 1) && !std::isinf(cfg->max_dist)) p.max_r2 = std::nextafterf(p.max_r2, 0.f);
+    if (cfg->conventions & 2)
+        for (int f = 0; f < cfg->n_outlier; ++f)
+            if (cfg->outlier_kind[f] == B200ICP_OUTLIER_MEDIAN_DIST) p.outlier_param[f] = cfg->outlier_param[f] * cfg->outlier_param[f];
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_begin) == cudaSuccess && cudaEventCreate(&ctx->ev_end) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev_map0) == cudaSuccess && cudaEventCreate(&ctx->ev_map1) == cudaSuccess;
@@ -426,6 +435,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     B200_CUDA_FREE(b.rnrm_in);
     B200_CUDA_FREE(b.rnrm);
     B200_CUDA_FREE(b.rnrm_tmp);
+    B200_CUDA_FREE(b.rmax_in);
     B200_CUDA_FREE(b.hist);
     B200_CUDA_FREE(b.partials);
     B200_CUDA_FREE(b.state);
@@ -571,7 +581,8 @@ int32_t b200icp_set_map(b200icp_ctx* ctx, const float* features, int32_t feature
 
 // The ICP loop on device-resident reading points.
 static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int32_t rows, int64_t nq, const float* T_init,
-                                  float* T_out, b200icp_result* result, const float* d_reading_normals = nullptr) {
+                                  float* T_out, b200icp_result* result, const float* d_reading_normals = nullptr,
+                                  const float* d_reading_max_dist = nullptr) {
     const int dim = ctx->cfg.dim;
     ctx->prm.rnrm = nullptr;
     const IcpParams& p = ctx->prm;
@@ -617,14 +628,16 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
         // slower for it; nn_variant bits 12..14 = shift + 1 override it (1 = the full cell id)
         const int cs_bits = (ctx->cfg.nn_variant >> 12) & 7;
         const int cs = cs_bits ? cs_bits - 1 : 3;
-        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s, cs, &b.state->pmax2_bits));
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading_tmp, &ctx->map.view, ctx->map.keys_in, ctx->map.vals_in, nq, s, cs, &b.state->pmax2_bits,
+                               d_reading_max_dist, ctx->cfg.conventions & 1));
         const uint64_t n_keys = cs ? (uint64_t)(((v.nx - 1) >> cs) + 1) * (((v.ny - 1) >> cs) + 1) * (((v.nz - 1) >> std::max(cs - 1, 0)) + 1)
                                    : (uint64_t)v.nx * v.ny * v.nz;
         CK(sort_pairs(ctx->map, ctx->map.keys_in, ctx->map.keys_out, ctx->map.vals_in, ctx->map.vals_out, nq, bits_for(n_keys), s));
         CK(launch_gather_reading(b.reading_tmp, ctx->map.vals_out, b.reading, nq, s));
         launches += 4;
     } else {
-        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading, nullptr, nullptr, nullptr, nq, s, 0, &b.state->pmax2_bits));
+        CK(launch_prep_reading(d_reading, rows, dim, Tpre, b.reading, nullptr, nullptr, nullptr, nq, s, 0, &b.state->pmax2_bits, d_reading_max_dist,
+                               ctx->cfg.conventions & 1));
         launches += 1;
     }
     if (d_reading_normals) {  // the reading's `normals` descriptor follows the reading: same rotation, same order
@@ -662,7 +675,10 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     bool robust = false;
     for (int f = 0; f < p.n_outlier; ++f) robust = robust || p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST;
     // (VarTrimmed and Robust estimate their ratio / scale with device-wide sorts between the steps: kernel-per-step path)
-    const bool persistent = !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed && !robust;
+    // (a reading with a `maxSearchDist` descriptor: per-point radii ride in the reading's .w, which only the stand-alone search
+    //  kernels read -- the sentinel max_r2 = -1 tells them to)
+    const float search_r2 = d_reading_max_dist ? -1.f : p.max_r2;
+    const bool persistent = !ctx->profiling && !(ctx->cfg.nn_variant & 4) && !var_trimmed && !robust && !d_reading_max_dist;
     if (persistent) {
         CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
                       /*want_original_ids=*/0, ctx->cfg.nn_variant & 0xffff, s));
@@ -688,9 +704,9 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
             cudaEvent_t* ev = time_it ? &ctx->nn_events[4 * nn_timed] : nullptr;
             if (time_it) CK(cudaEventRecord(ev[0], s));
             if (issued > 0 && p.knn == 1 && !(ctx->cfg.nn_variant & 2))  // warm: previous matches bound the search
-                CK(launch_nn1_warm(ctx->map.view, b.reading, (int)nq, b.state, p.max_r2, b.match_pos, b.match_d2, ctx->cfg.nn_variant, s));
+                CK(launch_nn1_warm(ctx->map.view, b.reading, (int)nq, b.state, search_r2, b.match_pos, b.match_d2, ctx->cfg.nn_variant, s));
             else  // k > 1 from iteration 1 on: the previous matches bound the search (variant bit 16)
-                CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, p.max_r2, b.match_pos, b.match_d2,
+                CK(launch_knn(ctx->map.view, b.reading, &b.state->nq, (int)nq, b.state, p.knn, search_r2, b.match_pos, b.match_d2,
                               /*want_original_ids=*/0, (ctx->cfg.nn_variant & 0xffff) | ((issued > 0 && !(ctx->cfg.nn_variant & 2)) ? 0x10000 : 0), s));
             if (time_it) CK(cudaEventRecord(ev[1], s));
             ++launches;
@@ -815,6 +831,43 @@ int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t
     CK(cudaMemcpyAsync(b.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(b.rnrm_in, reading_normals, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     return register_on_device(ctx, b.reading_in, feature_rows, nq, T_init, T_out, result, b.rnrm_in);
+}
+
+int32_t b200icp_register_descriptors(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq, const float* reading_normals,
+                                     const float* reading_max_search_dist, const float* T_init, float* T_out, b200icp_result* result) {
+    if (!reading_max_search_dist) return b200icp_register_normals(ctx, reading, feature_rows, nq, reading_normals, T_init, T_out, result);
+    if (result) memset(result, 0, sizeof(*result));
+    const int32_t rc = register_checks(ctx, reading, feature_rows, nq, T_out);
+    if (rc != B200ICP_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int32_t eb = ensure_icp_buffers(ctx, nq);
+    if (eb != B200ICP_OK) return eb;
+    IcpBuffers& b = ctx->buf;
+    const int dim = ctx->cfg.dim;
+    if (nq > b.cap_rmax) {
+        B200_CUDA_FREE(b.rmax_in);
+        b.rmax_in = nullptr;
+        b.cap_rmax = 0;
+        CK(B200_CUDA_MALLOC((void**)&b.rmax_in, (size_t)grow_capacity(nq) * sizeof(float)));
+        b.cap_rmax = grow_capacity(nq);
+    }
+    if (reading_normals && nq > b.cap_rnrm) {
+        B200_CUDA_FREE(b.rnrm_in);
+        B200_CUDA_FREE(b.rnrm);
+        B200_CUDA_FREE(b.rnrm_tmp);
+        b.rnrm_in = nullptr;
+        b.rnrm = b.rnrm_tmp = nullptr;
+        b.cap_rnrm = 0;
+        const int64_t cap = grow_capacity(nq);
+        CK(B200_CUDA_MALLOC((void**)&b.rnrm_in, (size_t)cap * dim * sizeof(float)));
+        CK(B200_CUDA_MALLOC((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
+        CK(B200_CUDA_MALLOC((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
+        b.cap_rnrm = cap;
+    }
+    CK(cudaMemcpyAsync(b.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(b.rmax_in, reading_max_search_dist, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (reading_normals) CK(cudaMemcpyAsync(b.rnrm_in, reading_normals, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    return register_on_device(ctx, b.reading_in, feature_rows, nq, T_init, T_out, result, reading_normals ? b.rnrm_in : nullptr, b.rmax_in);
 }
 
 int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature_rows, int64_t nq, const float* T_init,

@@ -144,6 +144,7 @@ struct IcpParams {  // by-value kernel argument, constant for the life of a cont
     int use_bound;
     float max_rotation_norm, max_translation_norm;
     int counter_after;  // b200icp_config::checker_order
+    int min_flags;      // b200icp_config::minimizer_flags: bit 0 force2D, bit 1 force4DOF (PointToPlaneErrorMinimizer, 3-D clouds)
 };
 
 // ---- index.cu ------------------------------------------------------------------------------
@@ -270,6 +271,8 @@ struct IcpBuffers {
     float4* rnrm = nullptr;        // ... rotated into the refMean frame, same order as `reading`
     float4* rnrm_tmp = nullptr;    // ... pre-sort
     int64_t cap_rnrm = 0;
+    float* rmax_in = nullptr;      // raw upload of the reading's `maxSearchDist` descriptor (b200icp_register_descriptors)
+    int64_t cap_rmax = 0;
     int32_t* match_pos = nullptr;  // knn x N
     float* match_d2 = nullptr;
     uint32_t* hist = nullptr;      // max_iter x 3 x kHistBins
@@ -299,7 +302,8 @@ cudaError_t launch_robust_scale(VarTrimScratch& v, const IcpParams& p, int filte
 
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16 /*host*/,
                                 float4* d_out, const GridView* g_for_keys, uint32_t* d_keys,
-                                uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift = 0, unsigned int* d_pmax2_bits = nullptr);
+                                uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift = 0, unsigned int* d_pmax2_bits = nullptr,
+                                const float* d_max_dist_desc = nullptr /* nq radii -> .w = r^2 */, int strict = 0);
 // dim x N column-major normals -> float4, rotated by the rotation block of Tpre16 (descriptors named `normals` rotate with the cloud)
 cudaError_t launch_prep_normals(const float* d_in, int dim, const float* Tpre16 /*host*/, float4* d_out, int64_t nq, cudaStream_t s);
 cudaError_t launch_gather_reading(const float4* d_in, const uint32_t* d_perm, float4* d_out, int64_t nq,

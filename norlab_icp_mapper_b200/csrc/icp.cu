@@ -24,7 +24,8 @@ namespace {
 __global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restrict__ in, int rows, int dim, Mat4 Tpre,
                                                            float4* __restrict__ out, GridView g, uint32_t* __restrict__ keys,
                                                            uint32_t* __restrict__ vals, long long nq, int coarse_shift,
-                                                           unsigned int* __restrict__ pmax2_bits) {
+                                                           unsigned int* __restrict__ pmax2_bits, const float* __restrict__ max_dist_desc,
+                                                           int strict) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     float n2 = 0.f;
     float3 p = make_float3(0.f, 0.f, 0.f);
@@ -35,7 +36,13 @@ __global__ void __launch_bounds__(256) prep_reading_kernel(const float* __restri
         r.z = (dim == 3) ? in[i * rows + 2] : 0.f;
         r.w = 1.f;
         p = apply_T(Tpre.m, r);
-        out[i] = make_float4(p.x, p.y, p.z, 1.f);
+        float w = 1.f;
+        if (max_dist_desc) {  // the reading's `maxSearchDist` descriptor: this point's squared search radius rides in .w
+            const float r = max_dist_desc[i];
+            w = r * r;
+            if (strict && w < CUDART_INF_F) w = __uint_as_float(__float_as_uint(w) - (w > 0.f ? 1u : 0u));  // '<' == '<=' the float below
+        }
+        out[i] = make_float4(p.x, p.y, p.z, w);
         n2 = p.x * p.x + p.y * p.y + p.z * p.z;
         if (!(n2 < 3.0e38f)) n2 = 0.f;  // NaN / inf points never pair: they do not count
     }
@@ -346,14 +353,14 @@ __global__ void __launch_bounds__(256) accumulate_kernel(IcpParams prm, GridView
 // ---- host launchers -------------------------------------------------------------------------------
 cudaError_t launch_prep_reading(const float* d_in, int rows, int dim, const float* Tpre16, float4* d_out,
                                 const GridView* g_for_keys, uint32_t* d_keys, uint32_t* d_vals, int64_t nq, cudaStream_t s, int coarse_shift,
-                                unsigned int* d_pmax2_bits) {
+                                unsigned int* d_pmax2_bits, const float* d_max_dist_desc, int strict) {
     if (nq <= 0) return cudaSuccess;
     Mat4 T;
     memcpy(T.m, Tpre16, sizeof(T.m));
     GridView g{};
     if (g_for_keys) g = *g_for_keys;
     prep_reading_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(d_in, rows, dim, T, d_out, g, g_for_keys ? d_keys : nullptr,
-                                                                      d_vals, (long long)nq, coarse_shift, d_pmax2_bits);
+                                                                      d_vals, (long long)nq, coarse_shift, d_pmax2_bits, d_max_dist_desc, strict);
     return cudaGetLastError();
 }
 

@@ -117,16 +117,28 @@ __device__ float quat_angular_distance(const float* a, const float* b) {
 // pivot of the factorisation exceeds 6 eps max|diag|"; the rank-deficient case falls back to the minimum-norm
 // solution on lane 0.  (An fp64 Gauss-Jordan was measured at 2.2 us per iteration on this dependent chain;
 // the 6x6 system does not need it: upstream itself solves in fp32.)
-__device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/) {
+// Unknowns that are NOT solved for (bit i = unknown i of [alpha, beta, gamma, tx, ty, tz]): a 2-D cloud (z = 0 embedding: their
+// rows are empty anyway) and force2D leave roll, pitch and tz out -- LPM solves the 3 x 3 system of [cross_z; n_x; n_y] --,
+// force4DOF leaves roll and pitch out (4 x 4 system of [cross_z; n_x; n_y; n_z]).  LPM ErrorMinimizers/PointToPlane.cpp.
+__device__ __forceinline__ int solve_mask(int dim, int min_flags) {
+    return (dim == 2 || (min_flags & 1)) ? 0x23 : ((min_flags & 2) ? 0x03 : 0);
+}
+
+__device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/, int min_flags = 0) {
     float L[21], bv[6];  // lower triangle, L[i * (i + 1) / 2 + j] = (i, j), j <= i
 #pragma unroll
     for (int i = 0; i < 21; ++i) L[i] = (float)S[i];
 #pragma unroll
     for (int i = 0; i < 6; ++i) bv[i] = (float)S[21 + i];
-    if (dim == 2) {  // z = 0 embedding: rows/columns 0, 1, 5 are empty -> x = 0 there
-        L[0] = 1.f;
-        L[2] = 1.f;
-        L[20] = 1.f;
+    const int mask = solve_mask(dim, min_flags);
+    if (mask) {  // excluded unknowns: decoupled rows / columns with a unit diagonal and a zero right-hand side -> x = 0 there
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j)
+                if (((mask >> i) | (mask >> j)) & 1) L[i * (i + 1) / 2 + j] = (i == j) ? 1.f : 0.f;
+            if ((mask >> i) & 1) bv[i] = 0.f;
+        }
     }
     float maxdiag = 0.f;
 #pragma unroll
@@ -180,19 +192,19 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
                     A6[rr * 6 + c] = v;
                 }
             for (int i = 0; i < 6; ++i) b6[i] = (float)S[21 + i];
-            if (dim == 3) {
+            if (!mask) {
                 solve_min_norm(A6, b6, xs, 6);
-            } else {
-                float A3[9], b3[3], x3[3];
-                const int id[3] = {2, 3, 4};
-                for (int c = 0; c < 3; ++c) {
-                    for (int rr = 0; rr < 3; ++rr) A3[c * 3 + rr] = A6[id[c] * 6 + id[rr]];
-                    b3[c] = b6[id[c]];
+            } else {  // the sub-system of the unknowns that are solved for
+                float As[36], bs[6], xr[6];
+                int id[6], n = 0;
+                for (int i = 0; i < 6; ++i)
+                    if (!((mask >> i) & 1)) id[n++] = i;
+                for (int c = 0; c < n; ++c) {
+                    for (int rr = 0; rr < n; ++rr) As[c * n + rr] = A6[id[c] * 6 + id[rr]];
+                    bs[c] = b6[id[c]];
                 }
-                solve_min_norm(A3, b3, x3, 3);
-                xs[2] = x3[0];
-                xs[3] = x3[1];
-                xs[4] = x3[2];
+                solve_min_norm(As, bs, xr, n);
+                for (int c = 0; c < n; ++c) xs[id[c]] = xr[c];
             }
             for (int i = 0; i < 6; ++i) s_x[i] = xs[i];
         }
@@ -203,11 +215,11 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
 }
 
 // x -> dT (R column-major in dT[0..8], t in dT[9..11]); Eigen AngleAxis(|r|, r/|r|) / Rotation2D.
-__device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT) {
+__device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT, int min_flags = 0) {
     dT[0] = 1.f; dT[1] = 0.f; dT[2] = 0.f;
     dT[3] = 0.f; dT[4] = 1.f; dT[5] = 0.f;
     dT[6] = 0.f; dT[7] = 0.f; dT[8] = 1.f;
-    if (dim == 3) {
+    if (dim == 3 && !(min_flags & 3)) {
         const float nrm2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
         const float ang = sqrtf(nrm2);
         float ax0 = x[0], ax1 = x[1], ax2 = x[2];
@@ -243,7 +255,8 @@ __device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT)
         dT[9] = x[3];
         dT[10] = x[4];
         dT[11] = x[5];
-    } else {  // unknowns of the z = 0 embedding: theta = x[2], t = (x[3], x[4])
+    } else {  // rotation about z only: theta = x[2], t = (x[3], x[4], x[5]) -- 2-D clouds and force2D (x[5] = 0: Rotation2D
+              // written into the top-left corner of an identity), force4DOF (AngleAxis(x[2], unitZ) + the full translation)
         const float s = sinf(x[2]), c = cosf(x[2]);
         dT[0] = c;
         dT[1] = s;
@@ -251,7 +264,7 @@ __device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT)
         dT[4] = c;
         dT[9] = x[3];
         dT[10] = x[4];
-        dT[11] = 0.f;
+        dT[11] = x[5];
     }
 }
 
@@ -514,9 +527,9 @@ __device__ __forceinline__ void finish_warp(const IcpParams& prm, IcpState* st, 
     float dT[12];
     if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE) {
         float x[6];
-        solve6_warp(S, prm.dim, lane, x, s_scratch);
+        solve6_warp(S, prm.dim, lane, x, s_scratch, prm.min_flags);
         if (stamp_to && lane == 0) B200_STAMP(stamp_to, 15);
-        delta_from_x(x, prm.dim, dT);
+        delta_from_x(x, prm.dim, dT, prm.min_flags);
         if (stamp_to && lane == 0) B200_STAMP(stamp_to, 16);
     } else {
         if (lane == 0) {
@@ -658,7 +671,8 @@ __device__ __forceinline__ void accumulate_entry(float* acc, const IcpParams& pr
         F[3] = n.x;
         F[4] = n.y;
         F[5] = n.z;
-        const float dot = (p.x - q.x) * n.x + (p.y - q.y) * n.y + (p.z - q.z) * n.z;
+        // force2D: the clouds are cut down to x, y before the residual is formed (LPM PointToPlane.cpp), z does not count
+        const float dot = (prm.min_flags & 1) ? (p.x - q.x) * n.x + (p.y - q.y) * n.y : (p.x - q.x) * n.x + (p.y - q.y) * n.y + (p.z - q.z) * n.z;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             const float wf = w * F[c];

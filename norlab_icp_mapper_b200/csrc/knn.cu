@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __re
         qy = __fadd_rn(__fmaf_rn(T[9], q4.z, __fmaf_rn(T[5], q4.y, __fmul_rn(T[1], q4.x))), T[13]);
         qz = __fadd_rn(__fmaf_rn(T[10], q4.z, __fmaf_rn(T[6], q4.y, __fmul_rn(T[2], q4.x))), T[14]);
     }
+    if (max_r2 < 0.f) max_r2 = q4.w;  // per-point search radius (the reading's `maxSearchDist` descriptor, squared by the prep kernel)
     Acc acc;
     float bound = CUDART_INF_F;
     if (Acc::kPerLaneOutput && warm) {
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) nn1_warm_kernel(GridView g, const float4*
     const long long qi = (long long)blockIdx.x * (256 / G) + threadIdx.x / G;
     if (qi >= nq) return;
     const float4 q4 = __ldg(reading + qi);
+    if (max_r2 < 0.f) max_r2 = q4.w;  // per-point search radius
     const int prev = match_pos[qi];
     const float* T = state->T;
     const float qx = __fadd_rn(__fmaf_rn(T[8], q4.z, __fmaf_rn(T[4], q4.y, __fmul_rn(T[0], q4.x))), T[12]);
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256) nn1_cold_kernel(GridView g, const float4*
     const long long qi = (long long)blockIdx.x * 64 + threadIdx.x / 4;
     if (qi >= nq) return;  // whole group leaves together
     const float4 q4 = __ldg(queries + qi);
+    if (max_r2 < 0.f) max_r2 = q4.w;  // per-point search radius
     float qx = q4.x, qy = q4.y, qz = q4.z;
     if (state) {
         const float* T = state->T;

@@ -770,7 +770,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             if (wo != 0.f) {
                                 p = apply_T(st.T, ql < kCacheCap ? s_r4[ql] : __ldg(reading + qi));
                                 if (MIN == 0)
-                                    v = make_float4(nv.x, nv.y, nv.z, (p.x - pp.x) * nv.x + (p.y - pp.y) * nv.y + (p.z - pp.z) * nv.z);
+                                    v = make_float4(nv.x, nv.y, nv.z, (prm.min_flags & 1) ? (p.x - pp.x) * nv.x + (p.y - pp.y) * nv.y
+                                                                                          : (p.x - pp.x) * nv.x + (p.y - pp.y) * nv.y + (p.z - pp.z) * nv.z);
                                 else
                                     v = pp;
                                 if (cls == 0) add_pair<MIN>(acc, wo, p, v);

@@ -90,8 +90,9 @@ class ICP:
         return h.value, tuple(int(x) for x in dims)
 
     # -- correction = icp(input) ---------------------------------------------------------------
-    def __call__(self, reading, T_init=None, reading_normals=None):
-        """reading_normals: the reading's `normals` descriptor (N x dim), needed by SurfaceNormalOutlierFilter only."""
+    def __call__(self, reading, T_init=None, reading_normals=None, reading_max_search_dist=None):
+        """reading_normals: the reading's `normals` descriptor (N x dim), needed by SurfaceNormalOutlierFilter only.
+        reading_max_search_dist: the reading's `maxSearchDist` descriptor (N radii): per-point search radius instead of maxDist."""
         reading = _cloud(reading, self.n)
         tptr = None
         if T_init is not None:
@@ -99,7 +100,13 @@ class ICP:
             tptr = T_cm.ctypes.data
         T_out = np.zeros(self.n * self.n, np.float32)
         res = Result()
-        if reading_normals is not None:
+        if reading_max_search_dist is not None:
+            rm = np.ascontiguousarray(reading_max_search_dist, np.float32)
+            assert rm.shape == (len(reading),)
+            rn = None if reading_normals is None else _cloud(reading_normals, self.dim)
+            rc = self._L.b200icp_register_descriptors(self._h, reading.ctypes.data, self.n, len(reading), None if rn is None else rn.ctypes.data,
+                                                      rm.ctypes.data, tptr, T_out.ctypes.data, C.byref(res))
+        elif reading_normals is not None:
             rn = _cloud(reading_normals, self.dim)
             assert len(rn) == len(reading)
             rc = self._L.b200icp_register_normals(self._h, reading.ctypes.data, self.n, len(reading), rn.ctypes.data, tptr, T_out.ctypes.data,

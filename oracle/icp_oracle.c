@@ -230,8 +230,15 @@ static void search_rec(search_ctx* s, int32_t ni, float rd) {
 
 void orc_kdtree_knn(const orc_kdtree* t, const float* q, int32_t qstride, int64_t nq, int32_t k,
                     float max_radius, int32_t* ids, float* d2, int32_t nthreads) {
+    orc_kdtree_knn_ex(t, q, qstride, nq, k, max_radius, NULL, 0, ids, d2, nthreads);
+}
+
+/* max_radii (optional, one per query): LPM KDTreeMatcher with a `maxSearchDist` descriptor on the reading -- libnabo's knn
+ * overload with a vector of radii; replaces max_radius.  strict: accept dist2 < r^2 instead of <= (b200icp_config::conventions bit 0). */
+void orc_kdtree_knn_ex(const orc_kdtree* t, const float* q, int32_t qstride, int64_t nq, int32_t k, float max_radius,
+                       const float* max_radii, int32_t strict, int32_t* ids, float* d2, int32_t nthreads) {
     if (!t || k < 1 || k > ORC_MAXK) return;
-    const float max_r2 = isinf(max_radius) ? INFINITY : max_radius * max_radius;
+    const float max_r2_all = isinf(max_radius) ? INFINITY : max_radius * max_radius;
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
@@ -240,6 +247,9 @@ void orc_kdtree_knn(const orc_kdtree* t, const float* q, int32_t qstride, int64_
         search_ctx s;
         s.t = t;
         s.k = k;
+        float max_r2 = max_r2_all;
+        if (max_radii) max_r2 = isinf(max_radii[i]) ? INFINITY : max_radii[i] * max_radii[i];
+        if (strict && !isinf(max_r2)) max_r2 = nextafterf(max_r2, 0.f); /* d < r2  <=>  d <= the next float below r2 */
         s.max_r2 = max_r2;
         s.q[0] = s.q[1] = s.q[2] = s.q[3] = 0.f;
         for (int d = 0; d < t->dim; ++d) s.q[d] = q[i * qstride + d];
@@ -479,11 +489,14 @@ struct orc_icp {
     float last_robust_scale; /* RobustOutlierFilter: the scale used by the last iteration (diagnostic) */
     float* reading_normals; /* dim floats per reading point for the NEXT register call (SurfaceNormalOutlierFilter), or NULL */
     int64_t n_reading_normals;
+    float* reading_max_dist; /* `maxSearchDist` descriptor of the reading for the NEXT register call (one radius per point), or NULL */
+    int64_t n_reading_max_dist;
     char err[256];
 };
 
 orc_icp* orc_icp_create(const b200icp_config* cfg) {
     if (!cfg || (cfg->dim != 2 && cfg->dim != 3) || cfg->knn < 1 || cfg->knn > ORC_MAXK) return NULL;
+    if ((cfg->minimizer_flags & 3) == 3) return NULL; /* LPM ConfigurationError: force2D together with force4DOF */
     orc_icp* o = (orc_icp*)calloc(1, sizeof(orc_icp));
     o->cfg = *cfg;
     o->dim = cfg->dim;
@@ -494,6 +507,7 @@ void orc_icp_destroy(orc_icp* o) {
     free(o->map);
     free(o->normals);
     free(o->reading_normals);
+    free(o->reading_max_dist);
     orc_kdtree_free(o->tree);
     free(o);
 }
@@ -510,6 +524,20 @@ int32_t orc_icp_set_reading_normals(orc_icp* o, const float* normals, int64_t n)
         o->reading_normals = (float*)malloc((size_t)n * o->dim * sizeof(float));
         memcpy(o->reading_normals, normals, (size_t)n * o->dim * sizeof(float));
         o->n_reading_normals = n;
+    }
+    return B200ICP_OK;
+}
+/* the `maxSearchDist` descriptor of the reading handed to the next orc_icp_register / orc_icp_match (LPM KDTreeMatcher: when the
+ * reading carries it, every point is searched within its own radius and the matcher's maxDist is not used); NULL clears it */
+int32_t orc_icp_set_reading_max_search_dist(orc_icp* o, const float* radii, int64_t n) {
+    if (!o || n < 0) return B200ICP_ERR_INVALID_ARG;
+    free(o->reading_max_dist);
+    o->reading_max_dist = NULL;
+    o->n_reading_max_dist = 0;
+    if (radii && n > 0) {
+        o->reading_max_dist = (float*)malloc((size_t)n * sizeof(float));
+        memcpy(o->reading_max_dist, radii, (size_t)n * sizeof(float));
+        o->n_reading_max_dist = n;
     }
     return B200ICP_OK;
 }
@@ -692,7 +720,8 @@ int32_t orc_icp_match(orc_icp* o, const float* queries, int32_t rows, int64_t nq
     float* c = (float*)calloc((size_t)nq * 4 + 4, sizeof(float));
     for (int64_t i = 0; i < nq; ++i)
         for (int d = 0; d < o->dim; ++d) c[i * 4 + d] = queries[i * rows + d] - o->mean[d];
-    orc_kdtree_knn(o->tree, c, 4, nq, o->cfg.knn, o->cfg.max_dist, ids, d2, nthreads);
+    orc_kdtree_knn_ex(o->tree, c, 4, nq, o->cfg.knn, o->cfg.max_dist, (o->reading_max_dist && o->n_reading_max_dist == nq) ? o->reading_max_dist : NULL,
+                      o->cfg.conventions & 1, ids, d2, nthreads);
     free(c);
     return B200ICP_OK;
 }
@@ -781,7 +810,8 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
 
         /* LPM MatchersImpl.cpp KDTreeMatcher::findClosests */
         double t0 = now_s();
-        orc_kdtree_knn(o->tree, step, 4, nq, k, cfg->max_dist, ids, d2, nthreads);
+        orc_kdtree_knn_ex(o->tree, step, 4, nq, k, cfg->max_dist, (o->reading_max_dist && o->n_reading_max_dist == nq) ? o->reading_max_dist : NULL,
+                          cfg->conventions & 1, ids, d2, nthreads);
         t_match += now_s() - t0;
 
         /* LPM OutlierFiltersImpl.cpp: product of all configured filters; none -> ones */
@@ -798,7 +828,8 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
                     break;
                 case B200ICP_OUTLIER_MEDIAN_DIST:
                     if (dists_quantile(d2, m, 0.5f, &limit, scratch)) FAIL(o, B200ICP_ERR_CONVERGENCE, "no outlier to filter");
-                    limit = prm * limit;
+                    /* conventions bit 1: the factor scales the distance, i.e. factor^2 on the squared distances compared here */
+                    limit = ((cfg->conventions & 2) ? prm * prm : prm) * limit;
                     for (int64_t i = 0; i < m; ++i) w[i] *= (d2[i] <= limit) ? 1.f : 0.f;
                     break;
                 case B200ICP_OUTLIER_VAR_TRIMMED_DIST: {
@@ -915,7 +946,11 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
         if (cfg->minimizer == B200ICP_MIN_POINT_TO_PLANE) {
             if (!o->normals) FAIL(o, B200ICP_ERR_INVALID_FIELD, "Cannot find descriptor normals in reference");
             /* LPM ErrorMinimizers/PointToPlane.cpp compute_in_place */
-            const int ns = (dim == 3) ? 6 : 3;
+            /* options force2D / force4DOF (3-D clouds only; mutually exclusive, checked at creation): force2D cuts both clouds
+             * down to x, y (cross = p_x n_y - p_y n_x, F = [cross; n_x; n_y], residual without z), force4DOF keeps 3-D points but
+             * only rotates about z (cross = ((Gamma p)^T n), Gamma = [0 -1 0; 1 0 0; 0 0 0], F = [cross; n_x; n_y; n_z]) */
+            const int force2d = dim == 3 && (cfg->minimizer_flags & 1), force4dof = dim == 3 && (cfg->minimizer_flags & 2);
+            const int ns = force2d ? 3 : (force4dof ? 4 : ((dim == 3) ? 6 : 3));
             float A[36], b[6], x[6];
             memset(A, 0, sizeof(A));
             memset(b, 0, sizeof(b));
@@ -928,7 +963,18 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
                     const float* nr = o->normals + (int64_t)ids[i * k + kk] * 3;
                     float F[6];
                     float dot;
-                    if (dim == 3) {
+                    if (force2d) {
+                        F[0] = p[0] * nr[1] - p[1] * nr[0];
+                        F[1] = nr[0];
+                        F[2] = nr[1];
+                        dot = (p[0] - q[0]) * nr[0] + (p[1] - q[1]) * nr[1];
+                    } else if (force4dof) {
+                        F[0] = p[0] * nr[1] - p[1] * nr[0];
+                        F[1] = nr[0];
+                        F[2] = nr[1];
+                        F[3] = nr[2];
+                        dot = (p[0] - q[0]) * nr[0] + (p[1] - q[1]) * nr[1] + (p[2] - q[2]) * nr[2];
+                    } else if (dim == 3) {
                         F[0] = p[1] * nr[2] - p[2] * nr[1];
                         F[1] = p[2] * nr[0] - p[0] * nr[2];
                         F[2] = p[0] * nr[1] - p[1] * nr[0];
@@ -952,7 +998,17 @@ int32_t orc_icp_register(orc_icp* o, const float* reading_in, int32_t rows, int6
                 }
             if (pairs == 0) FAIL(o, B200ICP_ERR_CONVERGENCE, "ErrorMnimizer: no point to minimize");
             solve_normal_eq(A, b, x, ns);
-            if (dim == 3) {
+            if (force2d || force4dof) {
+                /* Rotation2D(x0) in the top-left corner of an identity (force2D) / AngleAxis(x0, unitZ) (force4DOF) */
+                const float sn = sinf(x[0]), cs = cosf(x[0]);
+                dT[0] = cs;
+                dT[1] = sn;
+                dT[4] = -sn;
+                dT[5] = cs;
+                dT[12] = x[1];
+                dT[13] = x[2];
+                if (force4dof) dT[14] = x[3];
+            } else if (dim == 3) {
                 /* Eigen AngleAxis(|x|, x/|x|).toRotationMatrix(); NaN -> identity */
                 const float nrm2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
                 const float ang = sqrtf(nrm2);

@@ -39,6 +39,9 @@ void orc_kdtree_knn(const orc_kdtree* t, const float* q, int32_t qstride, int64_
 /* ---- PM::ICPSequence ----------------------------------------------------------------------- */
 typedef struct orc_icp orc_icp;
 
+void orc_kdtree_knn_ex(const orc_kdtree* t, const float* q, int32_t qstride, int64_t nq, int32_t k, float max_radius,
+                       const float* max_radii, int32_t strict, int32_t* ids, float* d2, int32_t nthreads);
+
 orc_icp* orc_icp_create(const b200icp_config* cfg);
 void orc_icp_destroy(orc_icp* o);
 const char* orc_icp_last_error(const orc_icp* o);
@@ -46,6 +49,7 @@ float orc_icp_last_var_ratio(const orc_icp* o); /* VarTrimmed: tuned ratio of th
 float orc_icp_last_robust_scale(const orc_icp* o); /* RobustOutlierFilter: scale used by the last iteration */
 /* `normals` descriptor of the reading for the next orc_icp_register (dim x n column-major; NULL clears): SurfaceNormalOutlierFilter */
 int32_t orc_icp_set_reading_normals(orc_icp* o, const float* normals, int64_t n);
+int32_t orc_icp_set_reading_max_search_dist(orc_icp* o, const float* radii, int64_t n);
 /* icp.setMap(cloud) -- Map.cpp:111,178,528,581. Returns b200icp_status. */
 int32_t orc_icp_set_map(orc_icp* o, const float* features, int32_t rows, const float* normals,
                         int64_t n);

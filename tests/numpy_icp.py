@@ -87,7 +87,7 @@ def robust_weights(prm, iteration, scale, d2, ids, p_all, ref, map_normals):
 
 
 def icp(map_xyz, map_normals, reading_xyz, knn_k=1, max_dist=np.inf, outliers=(("trimmed", 0.85),),
-        minimizer="point_to_plane", iterations=30):
+        minimizer="point_to_plane", iterations=30, force2D=False, force4DOF=False):
     """Counter-checker-only ICP in the mean-centred frame; returns the (dim+1)x(dim+1) correction."""
     dim = map_xyz.shape[1]
     map_xyz = np.asarray(map_xyz, np.float64)
@@ -124,14 +124,25 @@ def icp(map_xyz, map_normals, reading_xyz, knn_k=1, max_dist=np.inf, outliers=((
         dT = np.eye(dim + 1)
         if minimizer == "point_to_plane":
             n = np.asarray(map_normals, np.float64)[ids[qi, kk]]
-            if dim == 3:
+            resid = np.einsum("ij,ij->i", p - q, n)
+            if dim == 3 and force2D:      # LPM PointToPlane.cpp: clouds cut down to x, y
+                F = np.c_[p[:, 0] * n[:, 1] - p[:, 1] * n[:, 0], n[:, :2]]
+                resid = np.einsum("ij,ij->i", (p - q)[:, :2], n[:, :2])
+            elif dim == 3 and force4DOF:  # rotation about z only, full translation
+                F = np.c_[p[:, 0] * n[:, 1] - p[:, 1] * n[:, 0], n]
+            elif dim == 3:
                 F = np.c_[np.cross(p, n), n]
             else:
                 F = np.c_[p[:, 0] * n[:, 1] - p[:, 1] * n[:, 0], n]
             A = (F * ww[:, None]).T @ F
-            b = -(F * ww[:, None]).T @ np.einsum("ij,ij->i", p - q, n)
-            x = np.linalg.solve(A, b)
-            if dim == 3:
+            b = -(F * ww[:, None]).T @ resid
+            # solvePossiblyUnderdeterminedLinearSystem: the minimum-norm least-squares solution when A is rank deficient
+            x = np.linalg.solve(A, b) if np.linalg.matrix_rank(A, tol=1e-6 * np.abs(A).max()) == len(A) else np.linalg.pinv(A, rcond=1e-6) @ b
+            if dim == 3 and (force2D or force4DOF):
+                c, s = np.cos(x[0]), np.sin(x[0])
+                dT[:2, :2] = [[c, -s], [s, c]]
+                dT[:len(x) - 1, 3] = x[1:]
+            elif dim == 3:
                 dT[:3, :3] = rodrigues(x[:3])
                 dT[:3, 3] = x[3:]
             else:

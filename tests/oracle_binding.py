@@ -33,6 +33,9 @@ def lib():
     L.orc_kdtree_free.argtypes = [C.c_void_p]
     L.orc_kdtree_knn.argtypes = [C.c_void_p, f32p, C.c_int32, C.c_int64, C.c_int32, C.c_float,
                                  i32p, f32p, C.c_int32]
+    L.orc_kdtree_knn_ex.argtypes = [C.c_void_p, f32p, C.c_int32, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_int32,
+                                    i32p, f32p, C.c_int32]
+    L.orc_icp_set_reading_max_search_dist.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.orc_icp_create.restype = C.c_void_p
     L.orc_icp_create.argtypes = [C.POINTER(Config)]
     L.orc_icp_destroy.argtypes = [C.c_void_p]
@@ -60,7 +63,8 @@ def _cloud(a):
     return a
 
 
-def knn(ref, queries, k, dim=None, max_radius=np.inf, nthreads=0):
+def knn(ref, queries, k, dim=None, max_radius=np.inf, nthreads=0, max_radii=None, strict=False):
+    """max_radii: one search radius per query (libnabo's vector-of-radii overload); strict: dist2 < r^2 instead of <=."""
     ref, queries = _cloud(ref), _cloud(queries)
     dim = dim or min(ref.shape[1], 3)
     L = lib()
@@ -68,7 +72,12 @@ def knn(ref, queries, k, dim=None, max_radius=np.inf, nthreads=0):
     assert t
     ids = np.empty((queries.shape[0], k), np.int32)
     d2 = np.empty((queries.shape[0], k), np.float32)
-    L.orc_kdtree_knn(t, queries, queries.shape[1], queries.shape[0], k, max_radius, ids, d2, nthreads)
+    rptr = None
+    if max_radii is not None:
+        max_radii = np.ascontiguousarray(max_radii, np.float32)
+        assert max_radii.shape == (queries.shape[0],)
+        rptr = max_radii.ctypes.data_as(C.c_void_p)
+    L.orc_kdtree_knn_ex(t, queries, queries.shape[1], queries.shape[0], k, max_radius, rptr, int(strict), ids, d2, nthreads)
     L.orc_kdtree_free(t)
     return ids, d2
 
@@ -117,6 +126,14 @@ class OracleICP:
         d2 = np.empty((queries.shape[0], k), np.float32)
         rc = lib().orc_icp_match(self._h, queries, queries.shape[1], queries.shape[0], ids, d2, nthreads)
         return rc, ids, d2
+
+    def set_reading_max_search_dist(self, radii):
+        """The reading's `maxSearchDist` descriptor for the following register / match calls (None clears it)."""
+        if radii is None:
+            lib().orc_icp_set_reading_max_search_dist(self._h, None, 0)
+        else:
+            r = np.ascontiguousarray(radii, np.float32)
+            lib().orc_icp_set_reading_max_search_dist(self._h, r.ctypes.data_as(C.c_void_p), len(r))
 
     def register(self, reading, T_init=None, nthreads=0, want_trace=False, reading_normals=None):
         """Returns (status, T (n x n, row-major numpy view of the math matrix), Result, trace, secs)."""

@@ -472,3 +472,143 @@ def test_full_size_config2(oracle):
     assert res.iterations == 30 and res.pairs_last_iter == res_o.pairs_last_iter
     er, et = synth.pose_error(T_g, d["correction_true"])
     assert er <= 1e-4 and et <= 1e-3
+
+
+# ---- round 2: solve fallback, minimiser options, checker order, conventions, per-point search radius ---------------------------
+def _planar_pair():
+    import test_oracle_icp
+    return test_oracle_icp.planar_pair()
+
+
+@pytest.mark.parametrize("variant", [0, 4])  # persistent loop kernel / kernel-per-step path: both end in solve6_warp's fallback
+def test_rank_deficient_system_matches_the_oracle(oracle, variant):
+    """A flat map with parallel normals: the 6 x 6 normal matrix has rank 3, LLT fails and the minimum-norm solution is taken
+    (LPM solvePossiblyUnderdeterminedLinearSystem; csrc/icp_device.cuh solve_min_norm)."""
+    d = _planar_pair()
+    cfg = make_config(dim=3, knn=1, max_dist=2.0, outliers=(), minimizer="point_to_plane", max_iteration_count=8, nn_variant=variant)
+    T_g, res_g, tr_g, T_o, res_o, tr_o = _both(oracle, cfg, d)
+    er, et = synth.pose_error(T_g, T_o)
+    assert np.isfinite(T_g).all() and er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res_g.iterations == res_o.iterations == 8
+    fixed = T_g @ d["T_off"]
+    assert abs(fixed[2, 3]) < 1e-4 and abs(fixed[2, 0]) < 1e-5 and abs(fixed[2, 1]) < 1e-5  # z, roll, pitch recovered
+    assert abs(T_g[0, 3]) < 2e-3 and abs(T_g[1, 3]) < 2e-3 and abs(np.arctan2(T_g[1, 0], T_g[0, 0])) < 1e-4  # null space untouched
+    for a, b in zip(tr_g, tr_o):
+        e = synth.pose_error(a, b)
+        assert e[0] <= 5 * TOL_RAD and e[1] <= 5 * TOL_M
+
+
+@pytest.mark.parametrize("opt", ["force2D", "force4DOF"])
+@pytest.mark.parametrize("variant", [0, 4])
+def test_point_to_plane_options(oracle, pair3d, opt, variant):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=12,
+                      nn_variant=variant, **{opt: True})
+    T_g, res_g, tr_g, T_o, res_o, tr_o = _both(oracle, cfg, pair3d)
+    er, et = synth.pose_error(T_g, T_o)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    assert res_g.iterations == res_o.iterations and abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.002 * res_o.pairs_last_iter + 2
+    assert np.allclose(T_g[2, :3], [0, 0, 1], atol=1e-6) and np.allclose(T_g[:3, 2], [0, 0, 1], atol=1e-6)
+    if opt == "force2D":
+        assert abs(T_g[2, 3]) < 1e-5
+
+
+def test_force2d_with_force4dof_is_rejected():
+    from norlab_icp_mapper_b200.icp import ICP, B200ICPError
+    with pytest.raises(B200ICPError) as e:
+        ICP(make_config(dim=3, force2D=True, force4DOF=True))
+    assert e.value.status == _abi.ERR_INVALID_ARG
+
+
+@pytest.mark.parametrize("variant", [0, 4])
+def test_checker_order_counter_throws(oracle, pair3d, variant):
+    """Counter listed first (LPM setDefault order): its MaxNumIterationsReached skips a Bound violation of the last iteration;
+    Bound listed first: the violation is reported."""
+    from norlab_icp_mapper_b200.icp import ICP, B200ICPError
+    kw = dict(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", nn_variant=variant)
+    o = oracle.OracleICP(make_config(max_iteration_count=3, **kw))
+    o.set_map(pair3d["map"], pair3d["normals"])
+    _, _, _, trace, _ = o.register(pair3d["reading"], want_trace=True)
+    t_norms = [float(np.linalg.norm(t[:3, 3])) for t in trace]
+    assert t_norms[2] > max(t_norms[:2])
+    limit = 0.5 * (max(t_norms[:2]) + t_norms[2])
+    for order, want in ((0, _abi.OK), (2, _abi.ERR_BOUND)):
+        cfg = make_config(max_iteration_count=3, bound=(10.0, limit), checker_order=order, **kw)
+        o = oracle.OracleICP(cfg)
+        o.set_map(pair3d["map"], pair3d["normals"])
+        rc_o, T_o, res_o, _, _ = o.register(pair3d["reading"])
+        g = ICP(cfg)
+        g.set_map(pair3d["map"], pair3d["normals"])
+        if want == _abi.OK:
+            T_g = g(pair3d["reading"])
+            assert rc_o == _abi.OK and g.last_result.max_iter_reached == res_o.max_iter_reached == 1 and g.last_result.iterations == 3
+            er, et = synth.pose_error(T_g, T_o)
+            assert er <= TOL_RAD and et <= TOL_M
+        else:
+            with pytest.raises(B200ICPError) as e:
+                g(pair3d["reading"])
+            assert e.value.status == rc_o == _abi.ERR_BOUND
+        g.close()
+
+
+def test_conventions_switches(oracle, pair3d):
+    from norlab_icp_mapper_b200.icp import ICP
+    # bit 0: '<' instead of '<=' at maxDist.  A lattice map whose mean is exactly 0, a query at exactly maxDist from six points.
+    g1 = np.array([-2, -1, 0, 1, 2], np.float32)
+    ref = np.stack(np.meshgrid(g1, g1, g1, indexing="ij"), -1).reshape(-1, 3)
+    ref = ref[np.abs(ref).sum(1) > 0]  # (no point at the origin)
+    ref = np.c_[ref, np.ones(len(ref))].astype(np.float32)
+    q = np.array([[0, 0, 0, 1], [0.25, 0, 0, 1]], np.float32)
+    for conv in (0, 1):
+        cfg = make_config(dim=3, knn=2, max_dist=1.0, outliers=(), minimizer="point_to_point", conventions=conv)
+        g = ICP(cfg)
+        g.set_map(ref)
+        assert np.array_equal(g.map_mean(), [0, 0, 0])
+        ids, d2 = g.match(q)
+        o = oracle.OracleICP(cfg)
+        o.set_map(ref)
+        _, oi, od = o.match(q)
+        g.close()
+        assert np.array_equal(d2, od)
+        if conv == 0:
+            assert np.array_equal(d2[0], [1.0, 1.0])
+        else:
+            assert np.isinf(d2[0]).all() and (ids[0] == -1).all()
+        assert d2[1, 0] == np.float32(0.75) ** 2 and np.isinf(d2[1, 1])  # (1,0,0) at 0.75; everything else beyond 1
+    # bit 1: Median factor on the distance
+    outs = {}
+    for name, factor, conv in (("sq", 1.5, 0), ("root", 1.5, 2), ("sq225", 2.25, 0)):
+        cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("median", factor),), minimizer="point_to_plane", max_iteration_count=6,
+                          conventions=conv)
+        T_g, res_g, _, T_o, res_o, _ = _both(oracle, cfg, pair3d)
+        er, et = synth.pose_error(T_g, T_o)
+        assert er <= TOL_RAD and et <= TOL_M and abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.002 * res_o.pairs_last_iter + 2
+        outs[name] = (T_g, res_g.pairs_last_iter)
+    assert outs["root"][1] > outs["sq"][1] and outs["root"][1] == outs["sq225"][1] and np.array_equal(outs["root"][0], outs["sq225"][0])
+
+
+def test_max_search_dist_descriptor(oracle, pair3d):
+    """A reading with a `maxSearchDist` descriptor: every point is searched within its own radius, the matcher's maxDist is not
+    used (LPM KDTreeMatcher / libnabo's vector-of-radii knn)."""
+    from norlab_icp_mapper_b200.icp import ICP
+    rng = np.random.default_rng(3)
+    radii = rng.choice(np.array([0.05, 0.3, 2.0, np.inf], np.float32), len(pair3d["reading"]))
+    for knn, minimizer in ((1, "point_to_plane"), (4, "point_to_point")):
+        cfg = make_config(dim=3, knn=knn, max_dist=0.01, outliers=(("trimmed", 0.9),), minimizer=minimizer, max_iteration_count=10)
+        o = oracle.OracleICP(cfg)
+        o.set_map(pair3d["map"], pair3d["normals"])
+        o.set_reading_max_search_dist(radii)
+        rc, T_o, res_o, _, _ = o.register(pair3d["reading"])
+        g = ICP(cfg)
+        g.set_map(pair3d["map"], pair3d["normals"])
+        T_g = g(pair3d["reading"], reading_max_search_dist=radii)
+        res_g = g.last_result
+        T_plain_ok = True
+        try:
+            g(pair3d["reading"])  # without the descriptor maxDist 0.01 leaves (almost) nothing to minimise
+        except Exception:
+            T_plain_ok = False
+        g.close()
+        er, et = synth.pose_error(T_g, T_o)
+        assert rc == _abi.OK and er <= TOL_RAD and et <= TOL_M, (knn, er, et)
+        assert res_g.iterations == res_o.iterations and abs(res_g.pairs_last_iter - res_o.pairs_last_iter) <= 0.002 * res_o.pairs_last_iter + 2
+        assert res_g.pairs_last_iter > 0.3 * knn * len(radii) or not T_plain_ok

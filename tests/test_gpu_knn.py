@@ -29,8 +29,14 @@ def _check(gpu, oracle, ref, q, k, dim, r):
                 a = np.sort(ids[i][d2[i] == dval])
                 b = np.sort(oi[i][od[i] == dval])
                 if not np.array_equal(a, b):  # a tie straddling the k-th place: both must be true neighbours at that distance
-                    dd = ((ref[a, :dim].astype(np.float32) - q[i, :dim].astype(np.float32)) ** 2)
                     assert len(a) == len(b)
+                    for cand in (a, b):  # same fp32 expression as both implementations: fma(dz,dz, fma(dy,dy, dx*dx))
+                        assert (cand >= 0).all() and len(np.unique(cand)) == len(cand)
+                        dlt = ref[cand, :dim].astype(np.float32) - q[i, :dim].astype(np.float32)
+                        dd = (dlt[:, 0] * dlt[:, 0]).astype(np.float32)
+                        for c in range(1, dim):
+                            dd = (dlt[:, c].astype(np.float64) * dlt[:, c].astype(np.float64) + dd.astype(np.float64)).astype(np.float32)
+                        assert np.array_equal(dd, np.full(len(cand), dval, np.float32)), (i, dval, cand, dd)
     return ids, d2
 
 
@@ -131,3 +137,15 @@ def test_full_size_properties():
     ids2, d22 = g.match(d["map"][sub])
     assert np.array_equal(ids, ids2) and np.array_equal(d2, d22)
     g.close()
+
+
+def test_knn_ties_straddling_the_kth_place(gpu, oracle):
+    """Points on an integer lattice: many exact ties, also across the k-th place -- whichever member of a tie group an
+    implementation returns must be a true neighbour at exactly that distance (and never twice the same point)."""
+    g = np.arange(-4, 5, dtype=np.float32)
+    ref = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    ref = np.c_[ref, np.ones(len(ref))].astype(np.float32)
+    q = np.c_[np.array([[0, 0, 0], [0.5, 0.5, 0.5], [1, 0.5, 0], [3.5, -2, 1]], np.float32), np.ones(4)].astype(np.float32)
+    for k in (1, 3, 5, 7, 12):
+        _check(gpu, oracle, ref, q, k, 3, np.inf)
+        _check(gpu, oracle, ref, q, k, 3, 1.0)

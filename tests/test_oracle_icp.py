@@ -229,3 +229,95 @@ def test_robust_outlier_filter_2d(oracle, pair2d, minimizer, knn, rp):
                          outliers=outliers, minimizer=minimizer, iterations=12)
     er, et = synth.pose_error(T, T_np)
     assert er <= TOL_RAD and et <= TOL_M, (er, et)
+
+
+# ---- round 2: solve fallback, minimiser options, checker order, conventions ---------------------------------------------------
+def planar_pair(n_map=20_000, n_scan=3_000, seed=7):
+    """A perfectly flat map (all normals = +z): roll, pitch and z are observable, yaw, x and y are not -> the point-to-plane
+    normal matrix has rank 3 and LPM's solvePossiblyUnderdeterminedLinearSystem takes its minimum-norm branch."""
+    rng = np.random.default_rng(seed)
+    P = np.c_[rng.uniform(-20, 20, (n_map, 2)), np.zeros(n_map)]
+    N = np.tile([0.0, 0.0, 1.0], (n_map, 1))
+    S = np.c_[rng.uniform(-15, 15, (n_scan, 2)), np.zeros(n_scan)]
+    T_off = synth.make_T((0.0, 0.0, 0.08), (0.6, -0.4, 0.0))  # what ICP can see: z, roll, pitch
+    reading = synth.apply_T(T_off, S)
+    return dict(map=synth.homog(P), normals=np.ascontiguousarray(N, np.float32), reading=synth.homog(reading), T_off=T_off)
+
+
+def test_rank_deficient_system_takes_the_minimum_norm_solution(oracle):
+    d = planar_pair()
+    cfg = make_config(dim=3, knn=1, max_dist=2.0, outliers=(), minimizer="point_to_plane", max_iteration_count=8)
+    _, (rc, T, res, trace, _) = _run(oracle, cfg, d, want_trace=True)
+    assert rc == _abi.OK and np.isfinite(T).all() and res.iterations == 8
+    T_np = numpy_icp.icp(d["map"][:, :3], d["normals"], d["reading"][:, :3], knn_k=1, max_dist=2.0, outliers=(), iterations=8)
+    er, et = synth.pose_error(T, T_np)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    # the observable part is recovered, the unobservable part (yaw, x, y: the null space) stays where the minimum norm puts it: 0
+    fixed = T @ d["T_off"]
+    assert abs(fixed[2, 3]) < 1e-4 and abs(fixed[2, 0]) < 1e-5 and abs(fixed[2, 1]) < 1e-5
+    assert abs(T[0, 3]) < 2e-3 and abs(T[1, 3]) < 2e-3 and abs(np.arctan2(T[1, 0], T[0, 0])) < 1e-4
+    # the very first step already is the min-norm step of a rank-3 system: no in-plane translation
+    assert abs(trace[0][0, 3]) < 5e-3 and abs(trace[0][1, 3]) < 5e-3
+
+
+@pytest.mark.parametrize("opt", ["force2D", "force4DOF"])
+def test_point_to_plane_options_agree_with_numpy(oracle, pair3d, opt):
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=10,
+                      **{opt: True})
+    _, (rc, T, res, _, _) = _run(oracle, cfg, pair3d)
+    assert rc == _abi.OK
+    T_np = numpy_icp.icp(pair3d["map"][:, :3], pair3d["normals"], pair3d["reading"][:, :3], knn_k=1, max_dist=1.0,
+                         outliers=(("trimmed", 0.85),), iterations=10, **{opt: True})
+    er, et = synth.pose_error(T, T_np)
+    assert er <= TOL_RAD and et <= TOL_M, (er, et)
+    # the correction is a rotation about z (+ x, y[, z]): the third row / column of the rotation block is untouched
+    assert np.allclose(T[2, :3], [0, 0, 1], atol=1e-7) and np.allclose(T[:3, 2], [0, 0, 1], atol=1e-7)
+    if opt == "force2D":
+        assert abs(T[2, 3]) < 1e-6
+    full = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=10)
+    _, (_, T_full, _, _, _) = _run(oracle, full, pair3d)
+    assert synth.pose_error(T, T_full)[0] > 1e-4  # (the option really changes the answer on this pair: roll / pitch errors stay)
+
+
+def test_force2d_with_force4dof_is_a_configuration_error(oracle):
+    with pytest.raises(ValueError):
+        oracle.OracleICP(make_config(dim=3, force2D=True, force4DOF=True))
+
+
+def test_counter_throws_and_skips_the_checkers_listed_after_it(oracle, pair3d):
+    """LPM runs the checkers in YAML order and the Counter reports its limit by throwing: a Bound violation on the last
+    iteration is only seen when the Bound checker is listed BEFORE the Counter (checker_order bit 1)."""
+    kw = dict(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane")
+    free = make_config(max_iteration_count=3, **kw)
+    _, (rc, T, res, trace, _) = _run(oracle, free, pair3d, want_trace=True)
+    t_norms = [float(np.linalg.norm(t[:3, 3])) for t in trace]  # translation of T_iter after each iteration (refMean frame)
+    assert rc == _abi.OK and len(t_norms) == 3
+    limit = 0.5 * (max(t_norms[:2]) + t_norms[2]) if t_norms[2] > max(t_norms[:2]) else None
+    if limit is None:
+        pytest.skip("the translation does not grow on the last iteration for this pair")
+    counter_first = make_config(max_iteration_count=3, bound=(10.0, limit), checker_order=0, **kw)
+    _, (rc, _, res, _, _) = _run(oracle, counter_first, pair3d)
+    assert rc == _abi.OK and res.max_iter_reached == 1 and res.iterations == 3
+    bound_first = make_config(max_iteration_count=3, bound=(10.0, limit), checker_order=2, **kw)
+    _, (rc, _, res, _, _) = _run(oracle, bound_first, pair3d)
+    assert rc == _abi.ERR_BOUND
+
+
+def test_conventions_switches(oracle, pair3d):
+    # bit 0: '<' instead of '<=' at maxDist -- a neighbour at exactly maxDist
+    ref = np.array([[1, 0, 0, 1], [-1, 0, 0, 1], [0, 2, 0, 1], [0, -2, 0, 1]], np.float32)
+    q = np.array([[0, 0, 0, 1]], np.float32)
+    ids, d2 = oracle.knn(ref, q, 2, dim=3, max_radius=1.0)
+    assert np.array_equal(d2, [[1.0, 1.0]]) and set(ids[0]) == {0, 1}
+    ids, d2 = oracle.knn(ref, q, 2, dim=3, max_radius=1.0, strict=True)
+    assert np.isinf(d2).all() and (ids == -1).all()
+    ids, d2 = oracle.knn(ref, np.repeat(q, 2, 0), 1, dim=3, max_radii=[0.5, 2.5])  # per-point radii replace maxDist
+    assert np.isinf(d2[0, 0]) and d2[1, 0] == 1.0
+    # bit 1: Median factor applied to the distance (factor^2 on the squared distances) -- a different, larger inlier set
+    a = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("median", 1.5),), minimizer="point_to_plane", max_iteration_count=1)
+    b = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("median", 1.5),), minimizer="point_to_plane", max_iteration_count=1, conventions=2)
+    c = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("median", 2.25),), minimizer="point_to_plane", max_iteration_count=1)
+    _, (_, Ta, ra, _, _) = _run(oracle, a, pair3d)
+    _, (_, Tb, rb, _, _) = _run(oracle, b, pair3d)
+    _, (_, Tc, rc_, _, _) = _run(oracle, c, pair3d)
+    assert rb.pairs_last_iter > ra.pairs_last_iter and rb.pairs_last_iter == rc_.pairs_last_iter and np.array_equal(Tb, Tc)
