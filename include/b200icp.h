@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200ICP_ABI_VERSION 4
+#define B200ICP_ABI_VERSION 5
 
 typedef enum b200icp_status {
     B200ICP_OK = 0,
@@ -403,16 +403,66 @@ int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t
 int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_rows, int64_t* n,
                              const b200icp_filter* chain, int32_t n_filters);
 
+/* The map's other descriptors: everything a libpointmatcher cloud carries besides `normals` and `probabilityDynamic` (the bundled
+ * scans have intensity, t, ring ...; PointDistanceMapperModule.cpp:49 / OctreeMapperModule.cpp:37 concatenate them into the map).
+ * The device keeps them as one point-major block of extra_rows floats per point == the reference's column-major extra_rows x N
+ * matrix; their names and row ranges live with the caller (host/DataPoints.h), which also applies DataPoints::concatenate's
+ * rule -- only descriptors present in BOTH clouds survive -- by selecting the surviving rows on both sides before an insert
+ * (b200icp_map_select_extra / b200icp_scan_select_extra).  set_extra
+ * attaches the block to the map given by the last b200icp_set_map (insertion order, host pointer). */
+#define B200ICP_MAX_EXTRA_ROWS 32
+int32_t b200icp_map_set_extra(b200icp_ctx* ctx, const float* extra, int32_t extra_rows);
+int32_t b200icp_map_extra_rows(const b200icp_ctx* ctx);
+int32_t b200icp_map_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t n_rows);
+int32_t b200icp_map_download_extra(b200icp_ctx* ctx, int32_t global, float* extra, int64_t capacity);
+
+/* `localPointCloud = cloud`: what a MapperModule written against the reference's host signature (MapperModules/MapperModule.h:20-29,
+ * inPlaceUpdateMap(const DataPoints& input, DataPoints& map, pose)) leaves in `map` replaces the loaded points of the device map;
+ * parked cells stay.  Host pointers; normals / prob / extra may be NULL.  Does not rebuild the index (b200icp_map_commit). */
+int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, const float* normals,
+                                  const float* prob, const float* extra, int32_t extra_rows);
+
+/* b200icp_map_insert_point_distance for an input that carries `probabilityDynamic` (the chain DynamicPointsMapperModule +
+ * PointDistanceMapperModule: map.concatenate keeps the descriptor because both clouds have it). */
+int32_t b200icp_map_insert_point_distance_prob(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                                               const float* input_normals, const float* input_prob, float min_dist_new_point,
+                                               int64_t* n_added, uint8_t* keep_out);
+
 /* ---- the device-resident scan slot (no reference counterpart: it removes the host round trips between the steps of
- * Mapper::processInput, Mapper.cpp:194-238).  The scan is uploaded once; RigidTransformation (Mapper.cpp:197,221),
- * icp(input) (:213) and PointDistanceMapperModule::inPlaceUpdateMap (via Map.cpp:502-534) then run on that copy,
- * stream-ordered.  The slot holds features only (the reference's raw scans carry no normals). */
+ * Mapper::applyInputFilters + Mapper::processInput, Mapper.cpp:187-238).  The raw scan is uploaded ONCE, with its descriptors;
+ * the `input:` filter chain (Mapper.cpp:187-191), RigidTransformation (Mapper.cpp:197,221), icp(input) (:213) and the
+ * MapperModules' inPlaceUpdateMap (via Map.cpp:502-534) then run on that copy, stream-ordered.
+ *   upload            features only; clears the descriptors of the previous scan
+ *   set_descriptors   normals (dim x n), probabilityDynamic (1 x n), the other descriptors (extra_rows x n); any may be NULL.
+ *                     rotating_rows lists the first rows of the dim-row descriptors inside `extra` that rotate with the cloud
+ *                     (libpointmatcher rotates `normals` and `observationDirections`)
+ *   filter            DataPointsFilters::apply of the BoundingBox / DistanceLimit / RandomSampling chain, descriptors follow
+ *   add_prob          AddDescriptorDataPointsFilter{probabilityDynamic, 1, [constant]} (examples/config.yaml:19-23)
+ *   surface_normals   SurfaceNormalDataPointsFilter{knn} on the scan
+ *   select_extra      keep the listed rows of `extra`, in that order
+ *   transform         RigidTransformation::compute in place (features; normals and rotating descriptors by R)
+ *   register          icp(scan); the scan's normals, if any, go to SurfaceNormalOutlierFilter
+ *   insert_point_distance / append / octree / dynamic_points
+ *                     PointDistanceMapperModule / `map.concatenate(scan)` / OctreeMapperModule / DynamicPointsMapperModule
+ *                     ::inPlaceUpdateMap with the scan as `input` (map frame)
+ *   download*         host copies (tests, modules without a device entry point) */
 int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n);
+int32_t b200icp_scan_set_descriptors(b200icp_ctx* ctx, const float* normals, const float* prob, const float* extra, int32_t extra_rows,
+                                     const int32_t* rotating_rows, int32_t n_rotating);
 int64_t b200icp_scan_size(const b200icp_ctx* ctx);
+int32_t b200icp_scan_info(const b200icp_ctx* ctx, int32_t* has_normals, int32_t* has_prob, int32_t* extra_rows);
+int32_t b200icp_scan_filter(b200icp_ctx* ctx, const b200icp_filter* chain, int32_t n_filters, int64_t* n_out);
+int32_t b200icp_scan_add_prob(b200icp_ctx* ctx, float constant);
+int32_t b200icp_scan_surface_normals(b200icp_ctx* ctx, int32_t knn);
+int32_t b200icp_scan_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t n_rows);
 int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T);
 int32_t b200icp_scan_register(b200icp_ctx* ctx, const float* T_init, float* T_out, b200icp_result* result);
 int32_t b200icp_scan_insert_point_distance(b200icp_ctx* ctx, float min_dist_new_point, int64_t* n_added);
+int32_t b200icp_scan_append(b200icp_ctx* ctx, int64_t* n_added);
+int32_t b200icp_scan_octree(b200icp_ctx* ctx, float max_size_by_node, int32_t max_point_by_node, int32_t sampling_method, int64_t* n_after);
+int32_t b200icp_scan_dynamic_points(b200icp_ctx* ctx, const float* pose, const b200icp_dynamic_params* prm);
 int32_t b200icp_scan_download(b200icp_ctx* ctx, float* features, int64_t capacity, int64_t* n_out);
+int32_t b200icp_scan_download_descriptors(b200icp_ctx* ctx, float* normals, float* prob, float* extra, int64_t capacity);
 
 /* Device-pointer variant of b200icp_transform (features/normals live on ctx's device). */
 int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows,

@@ -61,11 +61,20 @@ int32_t b200mapper_apply_input_filters(b200mapper* m, float* features, int32_t f
 /* Mapper::processInput -- Mapper.cpp:194-238; status codes of b200icp.h (exceptions of the C++ class) */
 int32_t b200mapper_process_input(b200mapper* m, const float* features_sensor_frame, int32_t feature_rows, int64_t n,
                                  const float* estimated_pose, double time_stamp_seconds);
+/* applyInputFilters + processInput on a RAW scan with one host-to-device copy: the filter chain, the descriptors it attaches, the
+ * transforms, icp(input) and the map update all work on the device-resident copy (Mapper::setDeviceResidentInput).  *n_filtered
+ * (optional) receives the point count after the `input:` chain. */
+int32_t b200mapper_process_raw_input(b200mapper* m, const float* features_sensor_frame, int32_t feature_rows, int64_t n,
+                                     const float* estimated_pose, double time_stamp_seconds, int64_t* n_filtered);
 int32_t b200mapper_get_pose(b200mapper* m, float* pose);                       /* Mapper::getPose        */
 int32_t b200mapper_get_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n); /* getMap */
 int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n,
                                      int32_t* available);                      /* Mapper::getNewLocalMap */
 int32_t b200mapper_set_map(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, int64_t n);
+/* Mapper::setMap for a map that carries probabilityDynamic (a map saved by a DynamicPointsMapperModule run): prob may be NULL */
+int32_t b200mapper_set_map_descriptors(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, const float* prob, int64_t n);
+/* the probabilityDynamic descriptor of Mapper::getMap(); *n = 0 when the map does not carry it */
+int32_t b200mapper_get_map_prob(b200mapper* m, float* prob, int64_t capacity, int64_t* n);
 int32_t b200mapper_get_is_mapping(const b200mapper* m);
 int32_t b200mapper_set_is_mapping(b200mapper* m, int32_t is_mapping);
 int64_t b200mapper_trajectory_size(b200mapper* m);                             /* Mapper::getTrajectory  */

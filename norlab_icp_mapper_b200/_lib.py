@@ -25,7 +25,11 @@ SYMBOLS = [
     "b200icp_map_surface_normals", "b200icp_cloud_surface_normals", "b200icp_map_window", "b200icp_map_commit", "b200icp_map_counts",
     "b200icp_map_has_normals", "b200icp_map_download", "b200icp_map_set_prob", "b200icp_map_has_prob",
     "b200icp_map_download_prob", "b200icp_map_append", "b200icp_map_reserve", "b200icp_filter_cloud", "b200icp_scan_upload", "b200icp_scan_size", "b200icp_scan_transform", "b200icp_scan_register",
-    "b200icp_scan_insert_point_distance", "b200icp_scan_download", "b200icp_map_octree", "b200icp_map_cut_at_threshold", "b200icp_map_dynamic_points",
+    "b200icp_scan_insert_point_distance", "b200icp_scan_download", "b200icp_scan_set_descriptors", "b200icp_scan_info", "b200icp_scan_filter",
+    "b200icp_scan_add_prob", "b200icp_scan_surface_normals", "b200icp_scan_select_extra", "b200icp_scan_append", "b200icp_scan_octree",
+    "b200icp_scan_dynamic_points", "b200icp_scan_download_descriptors", "b200icp_map_set_extra", "b200icp_map_extra_rows",
+    "b200icp_map_select_extra", "b200icp_map_download_extra", "b200icp_map_replace_local", "b200icp_map_insert_point_distance_prob",
+    "b200icp_map_octree", "b200icp_map_cut_at_threshold", "b200icp_map_dynamic_points",
 ]
 
 _lib = None
@@ -93,6 +97,30 @@ def load():
     L.b200icp_map_octree.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, i32, C.POINTER(i64)]
     L.b200icp_map_cut_at_threshold.argtypes = [vp, f32, i32, C.POINTER(i64)]
     L.b200icp_map_dynamic_points.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    L.b200icp_cloud_surface_normals.argtypes = [vp, vp, i32, i64, i32, vp]
+    L.b200icp_map_insert_point_distance_prob.argtypes = [vp, vp, i32, i64, vp, vp, f32, C.POINTER(i64), vp]
+    L.b200icp_map_set_extra.argtypes = [vp, vp, i32]
+    L.b200icp_map_extra_rows.argtypes = [vp]
+    L.b200icp_map_select_extra.argtypes = [vp, vp, i32]
+    L.b200icp_map_download_extra.argtypes = [vp, i32, vp, i64]
+    L.b200icp_map_replace_local.argtypes = [vp, vp, i32, i64, vp, vp, vp, i32]
+    L.b200icp_scan_upload.argtypes = [vp, vp, i32, i64]
+    L.b200icp_scan_set_descriptors.argtypes = [vp, vp, vp, vp, i32, vp, i32]
+    L.b200icp_scan_size.argtypes = [vp]
+    L.b200icp_scan_size.restype = i64
+    L.b200icp_scan_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.b200icp_scan_filter.argtypes = [vp, vp, i32, C.POINTER(i64)]
+    L.b200icp_scan_add_prob.argtypes = [vp, f32]
+    L.b200icp_scan_surface_normals.argtypes = [vp, i32]
+    L.b200icp_scan_select_extra.argtypes = [vp, vp, i32]
+    L.b200icp_scan_transform.argtypes = [vp, vp]
+    L.b200icp_scan_register.argtypes = [vp, vp, vp, C.POINTER(Result)]
+    L.b200icp_scan_insert_point_distance.argtypes = [vp, f32, C.POINTER(i64)]
+    L.b200icp_scan_append.argtypes = [vp, C.POINTER(i64)]
+    L.b200icp_scan_octree.argtypes = [vp, f32, i32, i32, C.POINTER(i64)]
+    L.b200icp_scan_dynamic_points.argtypes = [vp, vp, vp]
+    L.b200icp_scan_download.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.b200icp_scan_download_descriptors.argtypes = [vp, vp, vp, vp, i64]
     if L.b200icp_abi_version() != _abi.ABI_VERSION:
         raise ImportError("libb200icp.so ABI version mismatch")
     _lib = L

@@ -42,8 +42,16 @@ struct b200icp_ctx {
     unsigned* d_bar_counter = nullptr;
     int n_sms = 148;
     int sm_share = 0;  // b200icp_set_sm_share: CTAs (= SMs) the persistent loop kernel may occupy; 0 = all of them
-    float* d_scan = nullptr;     // the device-resident scan slot (b200icp_scan_*)
-    int64_t cap_scan = 0, n_scan = 0;
+    // the device-resident scan slot (b200icp_scan_*): a whole DataPoints -- features + descriptors -- uploaded once; the steps of
+    // Mapper::processInput work on it in place.  Two buffer sets: ordered compaction (input filters) goes from one to the other.
+    struct ScanSlot {
+        float *feat[2] = {nullptr, nullptr}, *nrm[2] = {nullptr, nullptr}, *prob[2] = {nullptr, nullptr}, *extra[2] = {nullptr, nullptr};
+        int cur = 0;
+        int64_t cap = 0, cap_extra = 0, n = 0;
+        bool has_nrm = false, has_prob = false;
+        int extra_rows = 0;
+        int n_rot = 0, rot_row[4] = {0, 0, 0, 0};  // descriptors in `extra` that rotate with the cloud (observationDirections)
+    } scan;
     float* d_kth = nullptr;      // incremental SurfaceNormal: squared k-th neighbour distance per store point
     int64_t cap_kth = 0;
     uint8_t* d_dirty = nullptr;  // ... dirty flags (store order, then index order)
@@ -441,7 +449,12 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     B200_CUDA_FREE(b.state);
     B200_CUDA_FREE(b.trace);
     var_trimmed_free(ctx->var_scratch);
-    B200_CUDA_FREE(ctx->d_scan);
+    for (int i = 0; i < 2; ++i) {
+        B200_CUDA_FREE(ctx->scan.feat[i]);
+        B200_CUDA_FREE(ctx->scan.nrm[i]);
+        B200_CUDA_FREE(ctx->scan.prob[i]);
+        B200_CUDA_FREE(ctx->scan.extra[i]);
+    }
     B200_CUDA_FREE(ctx->d_kth);
     B200_CUDA_FREE(ctx->d_dirty);
     B200_CUDA_FREE(ctx->d_list);
@@ -557,7 +570,12 @@ int32_t b200icp_set_map_device(b200icp_ctx* ctx, const float* d_features, int32_
     if (n == 0) return B200ICP_OK;  // LPM: "Ignoring attempt to create a map from an empty cloud"
     if (!d_features) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null features");
     CK(cudaSetDevice(ctx->device));
-    CK(store_set(ctx->store, d_features, feature_rows, ctx->cfg.dim, d_normals, n, ctx->stream));
+    DevCloud c;
+    c.feat = d_features;
+    c.rows = feature_rows;
+    c.n = n;
+    c.nrm = d_normals;
+    CK(store_set(ctx->store, c, ctx->cfg.dim, ctx->stream));
     return commit_index(ctx);
 }
 
@@ -777,6 +795,23 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     }
 }
 
+static int32_t ensure_reading_normals(b200icp_ctx* ctx, int64_t nq) {
+    IcpBuffers& b = ctx->buf;
+    if (nq <= b.cap_rnrm) return B200ICP_OK;
+    B200_CUDA_FREE(b.rnrm_in);
+    B200_CUDA_FREE(b.rnrm);
+    B200_CUDA_FREE(b.rnrm_tmp);
+    b.rnrm_in = nullptr;
+    b.rnrm = b.rnrm_tmp = nullptr;
+    b.cap_rnrm = 0;
+    const int64_t cap = grow_capacity(nq);
+    CK(B200_CUDA_MALLOC((void**)&b.rnrm_in, (size_t)cap * ctx->cfg.dim * sizeof(float)));
+    CK(B200_CUDA_MALLOC((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
+    CK(B200_CUDA_MALLOC((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
+    b.cap_rnrm = cap;
+    return B200ICP_OK;
+}
+
 static int32_t register_checks(b200icp_ctx* ctx, const float* reading, int32_t rows, int64_t nq, float* T_out) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     if (!T_out) return fail(ctx, B200ICP_ERR_INVALID_ARG, "null T_out");
@@ -815,19 +850,8 @@ int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t
     if (eb != B200ICP_OK) return eb;
     IcpBuffers& b = ctx->buf;
     const int dim = ctx->cfg.dim;
-    if (nq > b.cap_rnrm) {
-        B200_CUDA_FREE(b.rnrm_in);
-        B200_CUDA_FREE(b.rnrm);
-        B200_CUDA_FREE(b.rnrm_tmp);
-        b.rnrm_in = nullptr;
-        b.rnrm = b.rnrm_tmp = nullptr;
-        b.cap_rnrm = 0;
-        const int64_t cap = grow_capacity(nq);
-        CK(B200_CUDA_MALLOC((void**)&b.rnrm_in, (size_t)cap * dim * sizeof(float)));
-        CK(B200_CUDA_MALLOC((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
-        CK(B200_CUDA_MALLOC((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
-        b.cap_rnrm = cap;
-    }
+    const int32_t en = ensure_reading_normals(ctx, nq);
+    if (en != B200ICP_OK) return en;
     CK(cudaMemcpyAsync(b.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(b.rnrm_in, reading_normals, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     return register_on_device(ctx, b.reading_in, feature_rows, nq, T_init, T_out, result, b.rnrm_in);
@@ -851,18 +875,9 @@ int32_t b200icp_register_descriptors(b200icp_ctx* ctx, const float* reading, int
         CK(B200_CUDA_MALLOC((void**)&b.rmax_in, (size_t)grow_capacity(nq) * sizeof(float)));
         b.cap_rmax = grow_capacity(nq);
     }
-    if (reading_normals && nq > b.cap_rnrm) {
-        B200_CUDA_FREE(b.rnrm_in);
-        B200_CUDA_FREE(b.rnrm);
-        B200_CUDA_FREE(b.rnrm_tmp);
-        b.rnrm_in = nullptr;
-        b.rnrm = b.rnrm_tmp = nullptr;
-        b.cap_rnrm = 0;
-        const int64_t cap = grow_capacity(nq);
-        CK(B200_CUDA_MALLOC((void**)&b.rnrm_in, (size_t)cap * dim * sizeof(float)));
-        CK(B200_CUDA_MALLOC((void**)&b.rnrm, (size_t)cap * sizeof(float4)));
-        CK(B200_CUDA_MALLOC((void**)&b.rnrm_tmp, (size_t)cap * sizeof(float4)));
-        b.cap_rnrm = cap;
+    if (reading_normals) {
+        const int32_t en = ensure_reading_normals(ctx, nq);
+        if (en != B200ICP_OK) return en;
     }
     CK(cudaMemcpyAsync(b.reading_in, reading, (size_t)nq * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(b.rmax_in, reading_max_search_dist, (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1100,12 +1115,11 @@ int32_t b200icp_map_counts(const b200icp_ctx* ctx, int64_t* n_local, int64_t* n_
 int32_t b200icp_map_has_normals(const b200icp_ctx* ctx) { return (ctx && ctx->store.has_normals) ? 1 : 0; }
 
 // PointDistance insert of a cloud that is already on the device (map frame)
-static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, const float* d_in_nrm, int32_t feature_rows, int64_t n_in,
-                                         float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
+static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const DevCloud& in, float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
     const int dim = ctx->cfg.dim;
     cudaStream_t s = ctx->stream;
     MapStore& st = ctx->store;
-    const float* input_normals = d_in_nrm;  // (only its presence matters below)
+    const int64_t n_in = in.n;
     const int32_t eb = ensure_query_buffers(ctx, n_in, 1);
     if (eb != B200ICP_OK) return eb;
     if (st.n_active > 0) {
@@ -1113,7 +1127,7 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, co
         float Tpre[16];
         mat4_identity(Tpre);
         for (int d = 0; d < dim; ++d) Tpre[12 + d] = -ctx->map.mean[d];
-        CK(launch_prep_reading(d_in, feature_rows, dim, Tpre, ctx->d_q4, nullptr, nullptr, nullptr, n_in, s));
+        CK(launch_prep_reading(in.feat, in.rows, dim, Tpre, ctx->d_q4, nullptr, nullptr, nullptr, n_in, s));
         int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
         *h_nq = (int)n_in;
         CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1121,7 +1135,6 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, co
                       /*want_original_ids=*/1, ctx->cfg.nn_variant, s));
     } else {  // createMap: the first cloud is taken as it is (PointDistanceMapperModule.cpp:9-19)
         CK(cudaMemsetAsync(ctx->d_out_ids, 0xff, (size_t)n_in * sizeof(int32_t), s));
-        if (st.n == 0) st.has_normals = input_normals != nullptr;
     }
     if (keep_out && n_in > ctx->cap_keep) {
         B200_CUDA_FREE(ctx->d_keep);
@@ -1131,11 +1144,7 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, co
         ctx->cap_keep = n_in + n_in / 4 + 1024;
     }
     int64_t kept = 0;
-    const bool first = st.n == 0;
-    if (first) CK(store_reserve(st, dim, n_in, s));
-    if (first && input_normals) st.has_normals = true;  // nothing to intersect descriptors with yet
-    CK(store_insert_point_distance(st, ctx->map, d_in, feature_rows, dim, d_in_nrm, n_in, ctx->d_out_ids, min_dist_new_point, &kept,
-                                   keep_out ? ctx->d_keep : nullptr, s));
+    CK(store_insert_point_distance(st, ctx->map, in, dim, ctx->d_out_ids, min_dist_new_point, &kept, keep_out ? ctx->d_keep : nullptr, s));
     if (keep_out) CK(cudaMemcpyAsync(keep_out, ctx->d_keep, (size_t)n_in, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (kept > 0) ctx->index_stale = true;
@@ -1143,8 +1152,37 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const float* d_in, co
     return B200ICP_OK;
 }
 
+// host cloud (features + the two descriptors the host-pointer entry points know) -> the upload staging buffer
+static int32_t upload_input(b200icp_ctx* ctx, const float* input, int rows, int64_t n_in, const float* nrm, const float* prob, DevCloud* out) {
+    const int dim = ctx->cfg.dim;
+    const size_t fb = (((size_t)n_in * rows * sizeof(float)) + 255) / 256 * 256;
+    const size_t nb = (((size_t)n_in * dim * sizeof(float)) + 255) / 256 * 256;
+    const size_t pb = (((size_t)n_in * sizeof(float)) + 255) / 256 * 256;
+    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + pb + 256));
+    char* base = reinterpret_cast<char*>(ctx->d_stage_a);
+    float* d_in = reinterpret_cast<float*>(base);
+    float* d_nrm = nrm ? reinterpret_cast<float*>(base + fb) : nullptr;
+    float* d_prob = prob ? reinterpret_cast<float*>(base + fb + nb) : nullptr;
+    CK(cudaMemcpyAsync(d_in, input, (size_t)n_in * rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (nrm) CK(cudaMemcpyAsync(d_nrm, nrm, (size_t)n_in * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (prob) CK(cudaMemcpyAsync(d_prob, prob, (size_t)n_in * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    *out = DevCloud();
+    out->feat = d_in;
+    out->rows = rows;
+    out->n = n_in;
+    out->nrm = d_nrm;
+    out->prob = d_prob;
+    return B200ICP_OK;
+}
+
 int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
                                           const float* input_normals, float min_dist_new_point, int64_t* n_added, uint8_t* keep_out) {
+    return b200icp_map_insert_point_distance_prob(ctx, input, feature_rows, n_in, input_normals, nullptr, min_dist_new_point, n_added, keep_out);
+}
+
+int32_t b200icp_map_insert_point_distance_prob(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,
+                                               const float* input_normals, const float* input_prob, float min_dist_new_point,
+                                               int64_t* n_added, uint8_t* keep_out) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
@@ -1152,39 +1190,115 @@ int32_t b200icp_map_insert_point_distance(b200icp_ctx* ctx, const float* input, 
     if (n_added) *n_added = 0;
     if (n_in == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
     if (ctx->store.n_active > 0 && ctx->index_stale) {
         const int32_t rc = commit_index(ctx);
         if (rc != B200ICP_OK) return rc;
     }
-    const size_t fb = (size_t)n_in * feature_rows * sizeof(float), nb = (size_t)n_in * dim * sizeof(float);
-    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + 256));
-    float* d_in = ctx->d_stage_a;
-    float* d_in_nrm = input_normals ? ctx->d_stage_a + ((fb + 255) / 256) * 64 : nullptr;
-    CK(cudaMemcpyAsync(d_in, input, fb, cudaMemcpyHostToDevice, s));
-    if (input_normals) CK(cudaMemcpyAsync(d_in_nrm, input_normals, nb, cudaMemcpyHostToDevice, s));
-    return insert_point_distance_dev(ctx, d_in, d_in_nrm, feature_rows, n_in, min_dist_new_point, n_added, keep_out);
+    DevCloud in;
+    const int32_t rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &in);
+    if (rc != B200ICP_OK) return rc;
+    return insert_point_distance_dev(ctx, in, min_dist_new_point, n_added, keep_out);
 }
 
-/* ---- the device-resident scan slot: Mapper::processInput uploads the scan ONCE; the rigid transforms
- * (Mapper.cpp:197,221), icp(input) (:213) and the PointDistance insert (Map.cpp:502-534) then run on that copy ---- */
+/* ---- the device-resident scan slot: the raw scan is uploaded ONCE with its descriptors; the `input:` filter
+ * chain (Mapper.cpp:187-191), the rigid transforms (Mapper.cpp:197,221), icp(input) (:213) and the MapperModules
+ * (Map.cpp:502-534) then run on that copy ---- */
+static int32_t scan_reserve(b200icp_ctx* ctx, int64_t n, int extra_rows) {
+    auto& sc = ctx->scan;
+    const int dim = ctx->cfg.dim;
+    if (n > sc.cap) {
+        const int64_t cap = grow_capacity(n);
+        for (int i = 0; i < 2; ++i) {
+            B200_CUDA_FREE(sc.feat[i]);
+            B200_CUDA_FREE(sc.nrm[i]);
+            B200_CUDA_FREE(sc.prob[i]);
+            B200_CUDA_FREE(sc.extra[i]);
+            sc.feat[i] = sc.nrm[i] = sc.prob[i] = sc.extra[i] = nullptr;
+        }
+        sc.cap = 0;
+        sc.cap_extra = 0;
+        for (int i = 0; i < 2; ++i) {
+            CK(B200_CUDA_MALLOC((void**)&sc.feat[i], (size_t)cap * (dim + 1) * sizeof(float)));
+            CK(B200_CUDA_MALLOC((void**)&sc.nrm[i], (size_t)cap * dim * sizeof(float)));
+            CK(B200_CUDA_MALLOC((void**)&sc.prob[i], (size_t)cap * sizeof(float)));
+        }
+        sc.cap = cap;
+    }
+    if (extra_rows > 0 && sc.cap * extra_rows > sc.cap_extra) {
+        for (int i = 0; i < 2; ++i) {
+            B200_CUDA_FREE(sc.extra[i]);
+            sc.extra[i] = nullptr;
+        }
+        sc.cap_extra = 0;
+        for (int i = 0; i < 2; ++i) CK(B200_CUDA_MALLOC((void**)&sc.extra[i], (size_t)sc.cap * extra_rows * sizeof(float)));
+        sc.cap_extra = sc.cap * extra_rows;
+    }
+    return B200ICP_OK;
+}
+
+static DevCloud scan_cloud(const b200icp_ctx* ctx) {
+    const auto& sc = ctx->scan;
+    DevCloud c;
+    c.feat = sc.feat[sc.cur];
+    c.rows = ctx->cfg.dim + 1;
+    c.n = sc.n;
+    c.nrm = sc.has_nrm ? sc.nrm[sc.cur] : nullptr;
+    c.prob = sc.has_prob ? sc.prob[sc.cur] : nullptr;
+    c.extra = sc.extra_rows > 0 ? sc.extra[sc.cur] : nullptr;
+    c.extra_rows = sc.extra_rows;
+    return c;
+}
+
 int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     if (feature_rows != ctx->cfg.dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad scan");
     CK(cudaSetDevice(ctx->device));
-    if (n > ctx->cap_scan) {
-        B200_CUDA_FREE(ctx->d_scan);
-        ctx->d_scan = nullptr;
-        ctx->cap_scan = 0;
-        CK(B200_CUDA_MALLOC((void**)&ctx->d_scan, (size_t)grow_capacity(n) * feature_rows * sizeof(float)));
-        ctx->cap_scan = grow_capacity(n);
-    }
-    if (n > 0) CK(cudaMemcpyAsync(ctx->d_scan, features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->n_scan = n;
+    const int32_t rc = scan_reserve(ctx, n, 0);
+    if (rc != B200ICP_OK) return rc;
+    auto& sc = ctx->scan;
+    if (n > 0) CK(cudaMemcpyAsync(sc.feat[sc.cur], features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    sc.n = n;
+    sc.has_nrm = sc.has_prob = false;  // a new cloud: the previous scan's descriptors are gone
+    sc.extra_rows = 0;
+    sc.n_rot = 0;
     return B200ICP_OK;
 }
 
-int64_t b200icp_scan_size(const b200icp_ctx* ctx) { return ctx ? ctx->n_scan : 0; }
+int32_t b200icp_scan_set_descriptors(b200icp_ctx* ctx, const float* normals, const float* prob, const float* extra, int32_t extra_rows,
+                                     const int32_t* rotating_rows, int32_t n_rotating) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (extra && (extra_rows < 1 || extra_rows > B200ICP_MAX_EXTRA_ROWS)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "extra_rows out of range");
+    if (n_rotating < 0 || n_rotating > 4 || (n_rotating > 0 && (!rotating_rows || !extra)))
+        return fail(ctx, B200ICP_ERR_INVALID_ARG, "at most 4 rotating descriptors, inside `extra`");
+    for (int i = 0; i < n_rotating; ++i)
+        if (rotating_rows[i] < 0 || rotating_rows[i] + dim > extra_rows) return fail(ctx, B200ICP_ERR_INVALID_ARG, "rotating descriptor outside `extra`");
+    CK(cudaSetDevice(ctx->device));
+    auto& sc = ctx->scan;
+    const int32_t rc = scan_reserve(ctx, sc.n, extra ? extra_rows : 0);
+    if (rc != B200ICP_OK) return rc;
+    cudaStream_t s = ctx->stream;
+    const int64_t n = sc.n;
+    if (normals && n > 0) CK(cudaMemcpyAsync(sc.nrm[sc.cur], normals, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (prob && n > 0) CK(cudaMemcpyAsync(sc.prob[sc.cur], prob, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (extra && n > 0) CK(cudaMemcpyAsync(sc.extra[sc.cur], extra, (size_t)n * extra_rows * sizeof(float), cudaMemcpyHostToDevice, s));
+    sc.has_nrm = normals != nullptr;
+    sc.has_prob = prob != nullptr;
+    sc.extra_rows = extra ? extra_rows : 0;
+    sc.n_rot = extra ? n_rotating : 0;
+    for (int i = 0; i < sc.n_rot; ++i) sc.rot_row[i] = rotating_rows[i];
+    return B200ICP_OK;
+}
+
+int64_t b200icp_scan_size(const b200icp_ctx* ctx) { return ctx ? ctx->scan.n : 0; }
+
+int32_t b200icp_scan_info(const b200icp_ctx* ctx, int32_t* has_normals, int32_t* has_prob, int32_t* extra_rows) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (has_normals) *has_normals = ctx->scan.has_nrm ? 1 : 0;
+    if (has_prob) *has_prob = ctx->scan.has_prob ? 1 : 0;
+    if (extra_rows) *extra_rows = ctx->scan.extra_rows;
+    return B200ICP_OK;
+}
 
 int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T) {
     if (!ctx || !T) return B200ICP_ERR_INVALID_ARG;
@@ -1193,38 +1307,166 @@ int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T) {
     embed(T, dim, M);
     if (std::fabs(1.f - det3(M)) > 1e-3f)
         return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
-    if (ctx->n_scan == 0) return B200ICP_OK;
+    auto& sc = ctx->scan;
+    if (sc.n == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
-    CK(launch_transform(ctx->d_scan, dim + 1, dim, nullptr, ctx->n_scan, M, ctx->stream));  // stream-ordered: no sync needed here
+    // stream-ordered: no sync needed here
+    CK(launch_transform(sc.feat[sc.cur], dim + 1, dim, sc.has_nrm ? sc.nrm[sc.cur] : nullptr, sc.n, M, ctx->stream));
+    // descriptors named `observationDirections` rotate like normals (LPM TransformationsImpl.cpp); the others are left alone
+    for (int i = 0; i < sc.n_rot; ++i) CK(launch_rotate_rows(sc.extra[sc.cur], sc.extra_rows, sc.rot_row[i], dim, sc.n, M, ctx->stream));
     return B200ICP_OK;
 }
 
 int32_t b200icp_scan_register(b200icp_ctx* ctx, const float* T_init, float* T_out, b200icp_result* result) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
-    return b200icp_register_device(ctx, ctx->d_scan, ctx->cfg.dim + 1, ctx->n_scan, T_init, T_out, result);
+    auto& sc = ctx->scan;
+    if (!sc.has_nrm) return b200icp_register_device(ctx, sc.feat[sc.cur], ctx->cfg.dim + 1, sc.n, T_init, T_out, result);
+    // the reading carries `normals` (SurfaceNormalOutlierFilter compares them with the map's)
+    if (result) memset(result, 0, sizeof(*result));
+    const int32_t rc = register_checks(ctx, sc.feat[sc.cur], ctx->cfg.dim + 1, sc.n, T_out);
+    if (rc != B200ICP_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    int32_t eb = ensure_icp_buffers(ctx, sc.n);
+    if (eb != B200ICP_OK) return eb;
+    eb = ensure_reading_normals(ctx, sc.n);
+    if (eb != B200ICP_OK) return eb;
+    return register_on_device(ctx, sc.feat[sc.cur], ctx->cfg.dim + 1, sc.n, T_init, T_out, result, sc.nrm[sc.cur]);
+}
+
+static int32_t check_filter_chain(b200icp_ctx* ctx, const b200icp_filter* chain, int32_t n_filters) {
+    if (n_filters < 0 || n_filters > 8 || (n_filters > 0 && !chain)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad filter chain (at most 8 entries)");
+    for (int i = 0; i < n_filters; ++i)
+        if (chain[i].kind != B200ICP_FILTER_BOUNDING_BOX && chain[i].kind != B200ICP_FILTER_DISTANCE_LIMIT &&
+            chain[i].kind != B200ICP_FILTER_RANDOM_SAMPLING)
+            return fail(ctx, B200ICP_ERR_INVALID_ARG, "unknown input filter");
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_filter(b200icp_ctx* ctx, const b200icp_filter* chain, int32_t n_filters, int64_t* n_out) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int32_t rc = check_filter_chain(ctx, chain, n_filters);
+    if (rc != B200ICP_OK) return rc;
+    auto& sc = ctx->scan;
+    if (n_out) *n_out = sc.n;
+    if (sc.n == 0 || n_filters == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int o = sc.cur ^ 1;
+    int64_t kept = 0;
+    CK(filter_cloud_device(ctx->store, ctx->map, scan_cloud(ctx), ctx->cfg.dim, chain, n_filters, sc.feat[o], sc.nrm[o], sc.prob[o],
+                           sc.extra_rows > 0 ? sc.extra[o] : nullptr, &kept, ctx->stream));
+    sc.cur = o;
+    sc.n = kept;
+    if (n_out) *n_out = kept;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_add_prob(b200icp_ctx* ctx, float constant) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    auto& sc = ctx->scan;
+    CK(cudaSetDevice(ctx->device));
+    if (sc.n > 0) CK(launch_fill(sc.prob[sc.cur], constant, sc.n, ctx->stream));
+    sc.has_prob = true;
+    return B200ICP_OK;
+}
+
+// SurfaceNormalDataPointsFilter{knn} on a device cloud: grid over the cloud, self k-NN, covariance, smallest eigenvector -> d_nrm (cloud order)
+static int32_t cloud_normals_dev(b200icp_ctx* ctx, const float* d_in, int rows, int64_t n, int knn, float* d_nrm) {
+    const int dim = ctx->cfg.dim;
+    cudaStream_t s = ctx->stream;
+    CK(grid_build(ctx->aux, d_in, rows, dim, nullptr, n, /*centre=*/false, 0.f, s));
+    const int32_t eb = ensure_query_buffers(ctx, n, knn);
+    if (eb != B200ICP_OK) return eb;
+    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+    *h_nq = (int)n;
+    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(launch_knn(ctx->aux.view, ctx->aux.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+                  /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+    // d_q4 (n float4, sized by ensure_query_buffers) receives the cell-sorted copy nobody needs; d_nrm the cloud-order normals
+    CK(launch_normals(ctx->aux.view, dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->d_q4, d_nrm, nullptr, s));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_surface_normals(b200icp_ctx* ctx, int32_t knn) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (knn < 1 || knn > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "knn must be in [1, 32]");
+    auto& sc = ctx->scan;
+    CK(cudaSetDevice(ctx->device));
+    if (sc.n > 0) {
+        const int32_t rc = cloud_normals_dev(ctx, sc.feat[sc.cur], ctx->cfg.dim + 1, sc.n, knn, sc.nrm[sc.cur]);
+        if (rc != B200ICP_OK) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));  // (h_nq is reused by the next call)
+    }
+    sc.has_nrm = true;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t n_rows) {
+    if (!ctx || n_rows < 0 || n_rows > B200ICP_MAX_EXTRA_ROWS || (n_rows > 0 && !rows)) return B200ICP_ERR_INVALID_ARG;
+    auto& sc = ctx->scan;
+    for (int i = 0; i < n_rows; ++i)
+        if (rows[i] < 0 || rows[i] >= sc.extra_rows) return fail(ctx, B200ICP_ERR_INVALID_ARG, "descriptor row outside `extra`");
+    CK(cudaSetDevice(ctx->device));
+    if (n_rows > 0 && sc.n > 0) {
+        // (the other buffer set may hold a different row count: both were sized for the larger, original one)
+        CK(launch_select_rows(sc.extra[sc.cur], sc.extra_rows, sc.n, sc.extra[sc.cur ^ 1], n_rows, rows, ctx->stream));
+        std::swap(sc.extra[0], sc.extra[1]);
+    }
+    // rotating descriptors keep rotating if all their rows survive contiguously
+    int nr = 0, rr[4];
+    for (int i = 0; i < sc.n_rot; ++i)
+        for (int j = 0; j + ctx->cfg.dim <= n_rows; ++j) {
+            bool ok = true;
+            for (int c = 0; c < ctx->cfg.dim; ++c) ok = ok && rows[j + c] == sc.rot_row[i] + c;
+            if (ok) {
+                rr[nr++] = j;
+                break;
+            }
+        }
+    sc.n_rot = nr;
+    for (int i = 0; i < nr; ++i) sc.rot_row[i] = rr[i];
+    sc.extra_rows = n_rows;
+    return B200ICP_OK;
 }
 
 int32_t b200icp_scan_insert_point_distance(b200icp_ctx* ctx, float min_dist_new_point, int64_t* n_added) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     if (n_added) *n_added = 0;
-    if (ctx->n_scan == 0) return B200ICP_OK;
+    if (ctx->scan.n == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     if (ctx->store.n_active > 0 && ctx->index_stale) {
         const int32_t rc = commit_index(ctx);
         if (rc != B200ICP_OK) return rc;
     }
-    return insert_point_distance_dev(ctx, ctx->d_scan, nullptr, ctx->cfg.dim + 1, ctx->n_scan, min_dist_new_point, n_added, nullptr);
+    return insert_point_distance_dev(ctx, scan_cloud(ctx), min_dist_new_point, n_added, nullptr);
 }
 
 int32_t b200icp_scan_download(b200icp_ctx* ctx, float* features, int64_t capacity, int64_t* n_out) {
     if (!ctx || !n_out) return B200ICP_ERR_INVALID_ARG;
-    *n_out = ctx->n_scan;
+    auto& sc = ctx->scan;
+    *n_out = sc.n;
     if (!features) return B200ICP_OK;
-    if (capacity < ctx->n_scan) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
+    if (capacity < sc.n) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->n_scan > 0)
-        CK(cudaMemcpyAsync(features, ctx->d_scan, (size_t)ctx->n_scan * (ctx->cfg.dim + 1) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sc.n > 0)
+        CK(cudaMemcpyAsync(features, sc.feat[sc.cur], (size_t)sc.n * (ctx->cfg.dim + 1) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_download_descriptors(b200icp_ctx* ctx, float* normals, float* prob, float* extra, int64_t capacity) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    auto& sc = ctx->scan;
+    if (capacity < sc.n) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
+    if ((normals && !sc.has_nrm) || (prob && !sc.has_prob) || (extra && sc.extra_rows == 0))
+        return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the scan does not carry that descriptor");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (sc.n > 0) {
+        if (normals) CK(cudaMemcpyAsync(normals, sc.nrm[sc.cur], (size_t)sc.n * ctx->cfg.dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (prob) CK(cudaMemcpyAsync(prob, sc.prob[sc.cur], (size_t)sc.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (extra) CK(cudaMemcpyAsync(extra, sc.extra[sc.cur], (size_t)sc.n * sc.extra_rows * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
     return B200ICP_OK;
 }
 
@@ -1381,16 +1623,8 @@ int32_t b200icp_cloud_surface_normals(b200icp_ctx* ctx, const float* features, i
     float* d_in = ctx->d_stage_a;
     float* d_nrm = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->d_stage_a) + fb);
     CK(cudaMemcpyAsync(d_in, features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, s));
-    CK(grid_build(ctx->aux, d_in, feature_rows, dim, nullptr, n, /*centre=*/false, 0.f, s));
-    const int32_t eb = ensure_query_buffers(ctx, n, knn);
-    if (eb != B200ICP_OK) return eb;
-    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
-    *h_nq = (int)n;
-    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-    CK(launch_knn(ctx->aux.view, ctx->aux.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
-                  /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
-    // d_q4 (n float4, sized by ensure_query_buffers) receives the cell-sorted copy nobody needs; d_nrm the cloud-order normals
-    CK(launch_normals(ctx->aux.view, dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->d_q4, d_nrm, nullptr, s));
+    const int32_t rc = cloud_normals_dev(ctx, d_in, feature_rows, n, knn, d_nrm);
+    if (rc != B200ICP_OK) return rc;
     CK(cudaMemcpyAsync(normals_out, d_nrm, nb, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return B200ICP_OK;
@@ -1457,11 +1691,8 @@ int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_
     if (!ctx || !n) return B200ICP_ERR_INVALID_ARG;
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || *n < 0 || (*n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
-    if (n_filters < 0 || n_filters > 8 || (n_filters > 0 && !chain)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad filter chain (at most 8 entries)");
-    for (int i = 0; i < n_filters; ++i)
-        if (chain[i].kind != B200ICP_FILTER_BOUNDING_BOX && chain[i].kind != B200ICP_FILTER_DISTANCE_LIMIT &&
-            chain[i].kind != B200ICP_FILTER_RANDOM_SAMPLING)
-            return fail(ctx, B200ICP_ERR_INVALID_ARG, "unknown input filter");
+    const int32_t rc = check_filter_chain(ctx, chain, n_filters);
+    if (rc != B200ICP_OK) return rc;
     if (*n == 0 || n_filters == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
@@ -1471,7 +1702,11 @@ int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_
     float* d_out = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->d_stage_a) + fb);
     CK(cudaMemcpyAsync(d_in, features, (size_t)*n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, s));
     int64_t kept = 0;
-    CK(filter_cloud_device(ctx->store, ctx->map, d_in, feature_rows, dim, *n, chain, n_filters, d_out, &kept, s));
+    DevCloud in;
+    in.feat = d_in;
+    in.rows = feature_rows;
+    in.n = *n;
+    CK(filter_cloud_device(ctx->store, ctx->map, in, dim, chain, n_filters, d_out, nullptr, nullptr, nullptr, &kept, s));
     if (kept > 0) CK(cudaMemcpyAsync(features, d_out, (size_t)kept * feature_rows * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *n = kept;
@@ -1486,50 +1721,75 @@ int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant
     if (prob) {
         CK(cudaMemcpyAsync(st.prob, prob, (size_t)st.n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     } else {
-        std::vector<float> v((size_t)st.n, constant);
-        CK(cudaMemcpyAsync(st.prob, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));  // (v goes out of scope)
+        CK(launch_fill(st.prob, constant, st.n, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     st.has_prob = true;
     return B200ICP_OK;
 }
 
-int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob, int64_t capacity) {
-    if (!ctx || !prob) return B200ICP_ERR_INVALID_ARG;
-    CK(cudaSetDevice(ctx->device));
+// host copy of a per-point store array, compacted to the loaded points unless `global`
+static int32_t download_rows(b200icp_ctx* ctx, const float* d_src, int rows, int32_t global, float* out, int64_t capacity) {
     MapStore& st = ctx->store;
-    if (!st.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map has no probabilityDynamic descriptor");
-    std::vector<float> p((size_t)st.n);
+    std::vector<float> p((size_t)st.n * rows);
     std::vector<uint8_t> l((size_t)st.n);
-    CK(cudaMemcpyAsync(p.data(), st.prob, p.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    // (copies on the context's own non-blocking stream: the legacy default stream does not order against it)
+    CK(cudaMemcpyAsync(p.data(), d_src, p.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(l.data(), st.loaded, l.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     int64_t o = 0;
     for (int64_t i = 0; i < st.n; ++i) {
         if (!global && !l[i]) continue;
         if (o >= capacity) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
-        prob[o++] = p[i];
+        for (int c = 0; c < rows; ++c) out[o * rows + c] = p[i * rows + c];
+        ++o;
     }
     return B200ICP_OK;
 }
 
+int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob, int64_t capacity) {
+    if (!ctx || !prob) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->store.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map has no probabilityDynamic descriptor");
+    return download_rows(ctx, ctx->store.prob, 1, global, prob, capacity);
+}
+
 int32_t b200icp_map_has_prob(const b200icp_ctx* ctx) { return (ctx && ctx->store.has_prob) ? 1 : 0; }
 
-static int32_t upload_input(b200icp_ctx* ctx, const float* input, int rows, int64_t n_in, const float* nrm, const float* prob, float** d_in,
-                            float** d_nrm, float** d_prob) {
-    const int dim = ctx->cfg.dim;
-    const size_t fb = (((size_t)n_in * rows * sizeof(float)) + 255) / 256 * 256;
-    const size_t nb = (((size_t)n_in * dim * sizeof(float)) + 255) / 256 * 256;
-    const size_t pb = (((size_t)n_in * sizeof(float)) + 255) / 256 * 256;
-    CK(grow(ctx->d_stage_a, ctx->stage_a_bytes, fb + nb + pb + 256));
-    char* base = reinterpret_cast<char*>(ctx->d_stage_a);
-    *d_in = reinterpret_cast<float*>(base);
-    *d_nrm = nrm ? reinterpret_cast<float*>(base + fb) : nullptr;
-    *d_prob = prob ? reinterpret_cast<float*>(base + fb + nb) : nullptr;
-    CK(cudaMemcpyAsync(*d_in, input, (size_t)n_in * rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if (nrm) CK(cudaMemcpyAsync(*d_nrm, nrm, (size_t)n_in * dim * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if (prob) CK(cudaMemcpyAsync(*d_prob, prob, (size_t)n_in * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+/* the map's other descriptors (everything but normals / probabilityDynamic), extra_rows floats per point, insertion order */
+int32_t b200icp_map_set_extra(b200icp_ctx* ctx, const float* extra, int32_t extra_rows) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (extra_rows < 0 || extra_rows > B200ICP_MAX_EXTRA_ROWS || (extra_rows > 0 && !extra)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad descriptor block");
+    CK(cudaSetDevice(ctx->device));
+    MapStore& st = ctx->store;
+    CK(store_set_extra_rows(st, extra_rows, ctx->stream));
+    if (extra_rows > 0 && st.n > 0) CK(cudaMemcpyAsync(st.extra, extra, (size_t)st.n * extra_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_extra_rows(const b200icp_ctx* ctx) { return ctx ? ctx->store.extra_rows : 0; }
+
+int32_t b200icp_map_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t n_rows) {
+    if (!ctx || n_rows < 0 || (n_rows > 0 && !rows)) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(store_select_extra(ctx->store, rows, n_rows, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_download_extra(b200icp_ctx* ctx, int32_t global, float* extra, int64_t capacity) {
+    if (!ctx || !extra) return B200ICP_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->store.extra_rows == 0) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map carries no other descriptor");
+    return download_rows(ctx, ctx->store.extra, ctx->store.extra_rows, global, extra, capacity);
+}
+
+static int32_t append_dev(b200icp_ctx* ctx, const DevCloud& in, int64_t* n_added) {
+    CK(store_append_all(ctx->store, in, ctx->cfg.dim, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->index_stale = true;
+    if (n_added) *n_added = in.n;
     return B200ICP_OK;
 }
 
@@ -1541,13 +1801,70 @@ int32_t b200icp_map_append(b200icp_ctx* ctx, const float* input, int32_t feature
     if (n_added) *n_added = 0;
     if (n_in == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
-    float *d_in, *d_nrm, *d_prob;
-    const int32_t rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &d_in, &d_nrm, &d_prob);
+    DevCloud in;
+    const int32_t rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &in);
     if (rc != B200ICP_OK) return rc;
-    CK(store_append_all(ctx->store, d_in, feature_rows, dim, d_nrm, d_prob, n_in, ctx->stream));
+    return append_dev(ctx, in, n_added);
+}
+
+int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, const float* normals,
+                                  const float* prob, const float* extra, int32_t extra_rows) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
+    if (extra && (extra_rows < 1 || extra_rows > B200ICP_MAX_EXTRA_ROWS)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "extra_rows out of range");
+    CK(cudaSetDevice(ctx->device));
+    DevCloud in;
+    if (n > 0) {
+        const int32_t rc = upload_input(ctx, features, feature_rows, n, normals, prob, &in);
+        if (rc != B200ICP_OK) return rc;
+        if (extra) {
+            CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, (size_t)n * extra_rows * sizeof(float)));
+            CK(cudaMemcpyAsync(ctx->d_stage_b, extra, (size_t)n * extra_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            in.extra = ctx->d_stage_b;
+            in.extra_rows = extra_rows;
+        }
+    }
+    MapStore& st = ctx->store;
+    if (st.n_active == st.n) {  // nothing parked: the cloud's descriptor set becomes the map's
+        st.n = 0;
+        st.n_active = 0;
+    }
+    CK(store_replace_loaded(st, ctx->map, in, dim, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->index_stale = true;
-    if (n_added) *n_added = n_in;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_scan_append(b200icp_ctx* ctx, int64_t* n_added) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    if (n_added) *n_added = 0;
+    if (ctx->scan.n == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    return append_dev(ctx, scan_cloud(ctx), n_added);
+}
+
+static int32_t octree_checks(b200icp_ctx* ctx, float max_size_by_node, int32_t max_point_by_node, int32_t sampling_method) {
+    if (!(max_size_by_node > 0.f)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "maxSizeByNode must be positive");
+    if (max_point_by_node != 1) return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "OctreeGrid: only maxPointByNode = 1 (the LPM default) is implemented");
+    if (sampling_method < 0 || sampling_method > 3)
+        return fail(ctx, B200ICP_ERR_INVALID_ARG, "OctreeGrid: samplingMethod must be 0 (first), 1 (random), 2 (centroid) or 3 (medoid)");
+    return B200ICP_OK;
+}
+
+static int32_t octree_dev(b200icp_ctx* ctx, const DevCloud* in, float max_size_by_node, int32_t sampling_method, int64_t* n_after) {
+    cudaStream_t s = ctx->stream;
+    MapStore& st = ctx->store;
+    if (in && in->n > 0) CK(store_append_all(st, *in, ctx->cfg.dim, s));  // map.concatenate(input)
+    int64_t removed = 0;
+    // the random sampler is reproducible: same base seed + same call count -> same survivors (B200ICP_OCTREE_SEED sets the base)
+    uint64_t seed = 0x0c7ee5eedull;
+    if (const char* env = getenv("B200ICP_OCTREE_SEED")) seed = strtoull(env, nullptr, 0);
+    seed += ctx->octree_calls++;
+    CK(store_octree_filter(st, ctx->map, ctx->cfg.dim, max_size_by_node, sampling_method, seed, &removed, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->index_stale = true;
+    if (n_after) *n_after = st.n_active;
     return B200ICP_OK;
 }
 
@@ -1557,29 +1874,24 @@ int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
-    if (!(max_size_by_node > 0.f)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "maxSizeByNode must be positive");
-    if (max_point_by_node != 1) return fail(ctx, B200ICP_ERR_NOT_IMPLEMENTED, "OctreeGrid: only maxPointByNode = 1 (the LPM default) is implemented");
-    if (sampling_method < 0 || sampling_method > 3)
-        return fail(ctx, B200ICP_ERR_INVALID_ARG, "OctreeGrid: samplingMethod must be 0 (first), 1 (random), 2 (centroid) or 3 (medoid)");
+    int32_t rc = octree_checks(ctx, max_size_by_node, max_point_by_node, sampling_method);
+    if (rc != B200ICP_OK) return rc;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    MapStore& st = ctx->store;
+    DevCloud in;
     if (n_in > 0) {
-        float *d_in, *d_nrm, *d_prob;
-        const int32_t rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &d_in, &d_nrm, &d_prob);
+        rc = upload_input(ctx, input, feature_rows, n_in, input_normals, input_prob, &in);
         if (rc != B200ICP_OK) return rc;
-        CK(store_append_all(st, d_in, feature_rows, dim, d_nrm, d_prob, n_in, s));  // map.concatenate(input)
     }
-    int64_t removed = 0;
-    // the random sampler is reproducible: same base seed + same call count -> same survivors (B200ICP_OCTREE_SEED sets the base)
-    uint64_t seed = 0x0c7ee5eedull;
-    if (const char* env = getenv("B200ICP_OCTREE_SEED")) seed = strtoull(env, nullptr, 0);
-    seed += ctx->octree_calls++;
-    CK(store_octree_filter(st, ctx->map, dim, max_size_by_node, sampling_method, seed, &removed, s));
-    CK(cudaStreamSynchronize(s));
-    ctx->index_stale = true;
-    if (n_after) *n_after = st.n_active;
-    return B200ICP_OK;
+    return octree_dev(ctx, n_in > 0 ? &in : nullptr, max_size_by_node, sampling_method, n_after);
+}
+
+int32_t b200icp_scan_octree(b200icp_ctx* ctx, float max_size_by_node, int32_t max_point_by_node, int32_t sampling_method, int64_t* n_after) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    const int32_t rc = octree_checks(ctx, max_size_by_node, max_point_by_node, sampling_method);
+    if (rc != B200ICP_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const DevCloud in = scan_cloud(ctx);
+    return octree_dev(ctx, &in, max_size_by_node, sampling_method, n_after);
 }
 
 int32_t b200icp_map_cut_at_threshold(b200icp_ctx* ctx, float threshold, int32_t use_larger_than, int64_t* n_removed) {
@@ -1593,19 +1905,21 @@ int32_t b200icp_map_cut_at_threshold(b200icp_ctx* ctx, float threshold, int32_t 
     return B200ICP_OK;
 }
 
-int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_prob,
-                                   const float* pose, const b200icp_dynamic_params* prm) {
-    if (!ctx || !prm || !pose) return B200ICP_ERR_INVALID_ARG;
-    const int dim = ctx->cfg.dim;
-    if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+static int32_t dynamic_points_checks(b200icp_ctx* ctx, bool input_has_prob) {
     MapStore& st = ctx->store;
-    if (!input_prob)
+    if (!input_has_prob)
         return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Missing field 'probabilityDynamic' in input point cloud. You can add it with the AddDescriptorDataPointsFilter in your input filters.");
     if (!st.has_normals)
         return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Missing field 'normals' in map point cloud. You can add it with the SurfaceNormalDataPointsFilter in your post filters.");
     if (!st.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "Missing field 'probabilityDynamic' in map point cloud.");
-    if (n_in == 0 || st.n_active == 0) return B200ICP_OK;
-    CK(cudaSetDevice(ctx->device));
+    return B200ICP_OK;
+}
+
+// `in`: the scan in the map frame, on the device
+static int32_t dynamic_points_dev(b200icp_ctx* ctx, const DevCloud& in, const float* pose, const b200icp_dynamic_params* prm) {
+    const int dim = ctx->cfg.dim;
+    MapStore& st = ctx->store;
+    const int64_t n_in = in.n;
     cudaStream_t s = ctx->stream;
     // pose.inverse(): rigid inverse, computed in double
     float P[16], Tinv[16];
@@ -1619,14 +1933,11 @@ int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t
         Tinv[12 + r] = (float)(-acc);
     }
     if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, ctx->map, s));
-    float *d_in, *d_nrm, *d_prob;
-    const int32_t rc = upload_input(ctx, input, feature_rows, n_in, nullptr, nullptr, &d_in, &d_nrm, &d_prob);
-    if (rc != B200ICP_OK) return rc;
     // scratch: input in the sensor frame (float4) + its angles (2 floats)
     CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, (size_t)n_in * (sizeof(float4) + 2 * sizeof(float)) + 512));
     float4* d_in_sensor = reinterpret_cast<float4*>(ctx->d_stage_b);
     float* d_angles = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->d_stage_b) + (((size_t)n_in * sizeof(float4)) + 255) / 256 * 256);
-    CK(launch_dyn_input(d_in, feature_rows, dim, Tinv, n_in, d_in_sensor, d_angles, s));
+    CK(launch_dyn_input(in.feat, in.rows, dim, Tinv, n_in, d_in_sensor, d_angles, s));
     // Nabo::NNS::create(inputInSensorFrameAngles) + knn(map angles, 1, 0, ALLOW_SELF_MATCH, 2 * beamHalfAngle) -- :75-78
     CK(grid_build(ctx->aux, d_angles, 2, 2, nullptr, n_in, /*centre=*/false, 0.f, s));
     const int64_t na = st.n_active;
@@ -1643,6 +1954,30 @@ int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t
     CK(launch_dyn_update(st, dim, Tinv, dp, d_in_sensor, ctx->d_out_ids, ctx->d_out_d2, s));
     CK(cudaStreamSynchronize(s));
     return B200ICP_OK;
+}
+
+int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_prob,
+                                   const float* pose, const b200icp_dynamic_params* prm) {
+    if (!ctx || !prm || !pose) return B200ICP_ERR_INVALID_ARG;
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
+    int32_t rc = dynamic_points_checks(ctx, input_prob != nullptr);
+    if (rc != B200ICP_OK) return rc;
+    if (n_in == 0 || ctx->store.n_active == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevCloud in;
+    rc = upload_input(ctx, input, feature_rows, n_in, nullptr, nullptr, &in);
+    if (rc != B200ICP_OK) return rc;
+    return dynamic_points_dev(ctx, in, pose, prm);
+}
+
+int32_t b200icp_scan_dynamic_points(b200icp_ctx* ctx, const float* pose, const b200icp_dynamic_params* prm) {
+    if (!ctx || !prm || !pose) return B200ICP_ERR_INVALID_ARG;
+    const int32_t rc = dynamic_points_checks(ctx, ctx->scan.has_prob);
+    if (rc != B200ICP_OK) return rc;
+    if (ctx->scan.n == 0 || ctx->store.n_active == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    return dynamic_points_dev(ctx, scan_cloud(ctx), pose, prm);
 }
 
 }  // extern "C"

@@ -184,10 +184,27 @@ cudaError_t sort_pairs(GridIndex& scratch_owner, uint32_t* keys_in, uint32_t* ke
 // ---- mapupd.cu -----------------------------------------------------------------------------
 // Device-resident map: every point ever inserted, in insertion order, map frame. `loaded` marks
 // membership of Map::localPointCloud; the rest is what the reference parks in its CellManager.
+// A cloud on the device, by pointers (PM::DataPoints): features `rows` floats per point, optional descriptors.  `extra` stacks
+// every descriptor other than `normals` / `probabilityDynamic` (intensity, t, ring, observationDirections ...): extra_rows
+// floats per point, point-major (== the reference's column-major extra_rows x n block); their names live on the host.
+struct DevCloud {
+    const float* feat = nullptr;
+    int rows = 0;
+    int64_t n = 0;
+    const float* nrm = nullptr;
+    const float* prob = nullptr;
+    const float* extra = nullptr;
+    int extra_rows = 0;
+};
+
 struct MapStore {
     float4* feat = nullptr;      // (x, y, z, 1)
     float* nrm = nullptr;        // dim floats per point
     float* prob = nullptr;       // `probabilityDynamic` descriptor (DynamicPointsMapperModule), 1 float per point
+    float* extra = nullptr;      // the other descriptors, extra_rows floats per point (DataPoints::concatenate keeps the common ones:
+    float* extra2 = nullptr;     //   the host mirror maps labels to rows and keeps both sides' layouts equal)
+    int extra_rows = 0;
+    int64_t cap_extra = 0;       // floats
     uint8_t* loaded = nullptr;
     uint8_t* touched = nullptr;  // loaded flag flipped since the last SurfaceNormal pass (incremental normals)
     uint32_t* active = nullptr;  // indices of the loaded points (valid after store_compact_active)
@@ -215,23 +232,30 @@ struct MapStore {
 void store_free(MapStore& m);
 cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s);
 cudaError_t store_reserve_scratch(MapStore& m, int64_t n);
-cudaError_t store_set(MapStore& m, const float* d_in, int rows, int dim, const float* d_normals, int64_t n, cudaStream_t s);
+cudaError_t store_set(MapStore& m, const DevCloud& in, int dim, cudaStream_t s);
+// resize / (re)allocate the `extra` block for `rows` floats per point (content dropped when the row count changes)
+cudaError_t store_set_extra_rows(MapStore& m, int rows, cudaStream_t s);
+// keep only the listed rows of `extra`, in that order (DataPoints::concatenate with a cloud that lacks some descriptors)
+cudaError_t store_select_extra(MapStore& m, const int* rows, int n_rows, cudaStream_t s);
 cudaError_t store_compact_active(MapStore& m, GridIndex& scratch, cudaStream_t s);
 cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* changed, cudaStream_t s);
-cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const float* d_in, int rows, int dim,
-                                        const float* d_in_nrm, int64_t n_in, const int32_t* d_nn_id, float min_dist,
+cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const DevCloud& in, int dim, const int32_t* d_nn_id, float min_dist,
                                         int64_t* n_kept, uint8_t* d_keep_out, cudaStream_t s);
 // map.concatenate(input): append every input point (descriptors survive only if both clouds have them)
-cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, const float* d_in_nrm, const float* d_in_prob,
-                             int64_t n_in, cudaStream_t s);
+cudaError_t store_append_all(MapStore& m, const DevCloud& in, int dim, cudaStream_t s);
 // OctreeGridDataPointsFilter{maxPointByNode 1, maxSizeByNode, samplingMethod 0 first | 1 random | 2 centroid | 3 medoid} over the loaded points
 cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float max_size_by_node, int sampling_method, uint64_t seed,
                                 int64_t* n_removed, cudaStream_t s);
 // CutAtDescriptorThresholdDataPointsFilter{probabilityDynamic, useLargerThan, threshold} over the loaded points
 cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s);
 // input filter chain on a device cloud (rows floats per point): keep flags -> ordered compaction
-cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, float* d_feat, int rows, int dim, int64_t n, const b200icp_filter* chain,
-                                int n_filters, float* d_out, int64_t* n_out, cudaStream_t s);
+// `in` and the `out_*` buffers must not alias; descriptors of `in` that have an output buffer are compacted with the points
+cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, const DevCloud& in, int dim, const b200icp_filter* chain, int n_filters,
+                                float* out_feat, float* out_nrm, float* out_prob, float* out_extra, int64_t* n_out, cudaStream_t s);
+cudaError_t store_replace_loaded(MapStore& m, GridIndex& scratch, const DevCloud& in, int dim, cudaStream_t s);
+// out[i * out_rows + c] = in[i * in_rows + rows[c]]
+cudaError_t launch_select_rows(const float* d_in, int in_rows, int64_t n, float* d_out, int out_rows, const int* rows, cudaStream_t s);
+cudaError_t launch_fill(float* d_out, float value, int64_t n, cudaStream_t s);
 struct DynParams {  // DynamicPointsMapperModule parameters (DynamicPointsMapperModule.h:33-44)
     float thresholdDynamic, alpha, beta, beamHalfAngle, epsilonA, epsilonD, sensorMaxRange;
 };
@@ -320,6 +344,8 @@ void icp_loop_workspace_zero_range(size_t* offset, size_t* bytes);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).
 cudaError_t launch_iteration_tail(const IcpParams& p, const GridIndex& g, IcpBuffers& b, int it,
                                   cudaStream_t s, int* launches, cudaEvent_t ev_mid, VarTrimScratch* var_scratch);
+// rotate the `dim` rows starting at row `offset` of a point-major block with `stride` floats per point (observationDirections)
+cudaError_t launch_rotate_rows(float* d_block, int stride, int offset, int dim, int64_t n, const float* T16, cudaStream_t s);
 cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals, int64_t n,
                              const float* T16 /*host, 4x4*/, cudaStream_t s);
 

@@ -113,6 +113,18 @@ __global__ void __launch_bounds__(256) transform_kernel(float* __restrict__ feat
     }
 }
 
+// descriptors that rotate with the cloud (`observationDirections`): same arithmetic as the normals above
+__global__ void __launch_bounds__(256) rotate_rows_kernel(float* __restrict__ block, int stride, int offset, int dim, long long n, Mat4 T) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* v = block + i * stride + offset;
+    const float vx = v[0], vy = v[1], vz = (dim == 3) ? v[2] : 0.f;
+    const float* M = T.m;
+    v[0] = __fmaf_rn(M[8], vz, __fmaf_rn(M[4], vy, __fmul_rn(M[0], vx)));
+    v[1] = __fmaf_rn(M[9], vz, __fmaf_rn(M[5], vy, __fmul_rn(M[1], vx)));
+    if (dim == 3) v[2] = __fmaf_rn(M[10], vz, __fmaf_rn(M[6], vy, __fmul_rn(M[2], vx)));
+}
+
 // ---- exact quantile of the finite squared distances (LPM Matches::getDistsQuantile) -------------
 // One thread-block cluster of kSelCtas CTAs does the whole 3-pass radix select in ONE launch: each
 // CTA keeps its slice of the distances in shared memory (read from L2 once), builds a shared-memory
@@ -383,6 +395,14 @@ cudaError_t launch_transform(float* d_feat, int rows, int dim, float* d_normals,
     Mat4 T;
     memcpy(T.m, T16, sizeof(T.m));
     transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_feat, rows, dim, d_normals, (long long)n, T);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rotate_rows(float* d_block, int stride, int offset, int dim, int64_t n, const float* T16, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    Mat4 T;
+    memcpy(T.m, T16, sizeof(T.m));
+    rotate_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_block, stride, offset, dim, (long long)n, T);
     return cudaGetLastError();
 }
 

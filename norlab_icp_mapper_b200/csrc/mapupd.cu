@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(256) pd_append_kernel(const float* __restrict_
                                                         long long n_in, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offs,
                                                         long long base, float4* __restrict__ store, float* __restrict__ store_nrm,
                                                         const float* __restrict__ in_prob, float* __restrict__ store_prob,
-                                                        uint8_t* __restrict__ loaded, uint8_t* __restrict__ keep_out) {
+                                                        uint8_t* __restrict__ loaded, uint8_t* __restrict__ keep_out,
+                                                        const float* __restrict__ in_extra, float* __restrict__ store_extra, int extra_rows) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n_in) return;
     if (keep_out) keep_out[i] = (uint8_t)keep[i];
@@ -61,6 +62,8 @@ __global__ void __launch_bounds__(256) pd_append_kernel(const float* __restrict_
     if (store_nrm && in_nrm)
         for (int c = 0; c < dim; ++c) store_nrm[dst * dim + c] = in_nrm[i * dim + c];
     if (store_prob && in_prob) store_prob[dst] = in_prob[i];
+    if (store_extra && in_extra)
+        for (int c = 0; c < extra_rows; ++c) store_extra[dst * extra_rows + c] = in_extra[i * extra_rows + c];
 }
 
 // unload: loaded points inside the slab's metric AABB leave the local cloud (Map.cpp:161-174);
@@ -276,6 +279,8 @@ void store_free(MapStore& m) {
     B200_CUDA_FREE(m.feat);
     B200_CUDA_FREE(m.nrm);
     B200_CUDA_FREE(m.prob);
+    B200_CUDA_FREE(m.extra);
+    B200_CUDA_FREE(m.extra2);
     B200_CUDA_FREE(m.loaded);
     B200_CUDA_FREE(m.touched);
     B200_CUDA_FREE(m.feat2);
@@ -320,6 +325,14 @@ cudaError_t store_reserve(MapStore& m, int dim, int64_t n, cudaStream_t s) {
         if ((e = B200_CUDA_MALLOC((void**)&m.active, (size_t)cap * sizeof(uint32_t))) != cudaSuccess) return e;
         m.cap = cap;
     }
+    if (m.extra_rows > 0 && m.cap * m.extra_rows > m.cap_extra) {
+        const int64_t want = m.cap * m.extra_rows;
+        if ((e = regrow(m.extra, m.n * m.extra_rows, want, s)) != cudaSuccess) return e;
+        B200_CUDA_FREE(m.extra2);
+        m.extra2 = nullptr;
+        if ((e = B200_CUDA_MALLOC((void**)&m.extra2, (size_t)want * sizeof(float))) != cudaSuccess) return e;
+        m.cap_extra = want;
+    }
     if (!m.d_counter)
         if ((e = B200_CUDA_MALLOC((void**)&m.d_counter, 64)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -357,16 +370,84 @@ static cudaError_t exclusive_sum(GridIndex& scratch, const uint32_t* in, uint32_
     return cub::DeviceScan::ExclusiveSum(scratch.cub_tmp, bytes, in, out, (int)n, s);
 }
 
-cudaError_t store_set(MapStore& m, const float* d_in, int rows, int dim, const float* d_normals, int64_t n, cudaStream_t s) {
+cudaError_t store_set_extra_rows(MapStore& m, int rows, cudaStream_t s) {
+    if (rows == m.extra_rows) return cudaSuccess;
+    m.extra_rows = rows;  // (content dropped: the caller refills it)
+    if (rows > 0 && m.cap * rows > m.cap_extra) {
+        B200_CUDA_FREE(m.extra);
+        B200_CUDA_FREE(m.extra2);
+        m.extra = m.extra2 = nullptr;
+        m.cap_extra = 0;
+        const int64_t want = std::max<int64_t>(m.cap, 1) * rows;
+        cudaError_t e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.extra, (size_t)want * sizeof(float))) != cudaSuccess) return e;
+        if ((e = B200_CUDA_MALLOC((void**)&m.extra2, (size_t)want * sizeof(float))) != cudaSuccess) return e;
+        m.cap_extra = want;
+    }
+    (void)s;
+    return cudaSuccess;
+}
+
+namespace {
+struct RowList {
+    int r[B200ICP_MAX_EXTRA_ROWS];
+};
+__global__ void __launch_bounds__(256) select_extra_kernel(const float* __restrict__ in, int in_rows, long long n, float* __restrict__ out, int out_rows,
+                                                           RowList rr) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = 0; c < out_rows; ++c) out[i * out_rows + c] = in[i * in_rows + rr.r[c]];
+}
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ out, float value, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = value;
+}
+}  // namespace
+
+cudaError_t launch_select_rows(const float* d_in, int in_rows, int64_t n, float* d_out, int out_rows, const int* rows, cudaStream_t s) {
+    if (out_rows < 0 || out_rows > B200ICP_MAX_EXTRA_ROWS) return cudaErrorInvalidValue;
+    if (n == 0 || out_rows == 0) return cudaSuccess;
+    RowList rr{};
+    for (int i = 0; i < out_rows; ++i) rr.r[i] = rows[i];
+    select_extra_kernel<<<blocks_for(n), 256, 0, s>>>(d_in, in_rows, (long long)n, d_out, out_rows, rr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill(float* d_out, float value, int64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    fill_kernel<<<blocks_for(n), 256, 0, s>>>(d_out, value, (long long)n);
+    return cudaGetLastError();
+}
+
+cudaError_t store_select_extra(MapStore& m, const int* rows, int n_rows, cudaStream_t s) {
+    if (n_rows < 0 || n_rows > B200ICP_MAX_EXTRA_ROWS) return cudaErrorInvalidValue;
+    for (int i = 0; i < n_rows; ++i)
+        if (rows[i] < 0 || rows[i] >= m.extra_rows) return cudaErrorInvalidValue;
+    if (n_rows > 0 && m.n > 0) {
+        cudaError_t e = launch_select_rows(m.extra, m.extra_rows, m.n, m.extra2, n_rows, rows, s);
+        if (e != cudaSuccess) return e;
+        std::swap(m.extra, m.extra2);
+    }
+    m.extra_rows = n_rows;
+    return cudaSuccess;
+}
+
+cudaError_t store_set(MapStore& m, const DevCloud& in, int dim, cudaStream_t s) {
     cudaError_t e;
     m.n = 0;  // nothing to preserve
+    const int64_t n = in.n;
+    if ((e = store_set_extra_rows(m, in.extra ? in.extra_rows : 0, s)) != cudaSuccess) return e;
     if ((e = store_reserve(m, dim, n, s)) != cudaSuccess) return e;
-    to_store_kernel<<<blocks_for(n), 256, 0, s>>>(d_in, rows, dim, (long long)n, m.feat, m.loaded);
-    m.has_normals = d_normals != nullptr;
+    to_store_kernel<<<blocks_for(n), 256, 0, s>>>(in.feat, in.rows, dim, (long long)n, m.feat, m.loaded);
+    m.has_normals = in.nrm != nullptr;
     m.nrm_epoch_ok = false;
-    if (d_normals)
-        if ((e = cudaMemcpyAsync(m.nrm, d_normals, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
-    m.has_prob = false;
+    if (in.nrm)
+        if ((e = cudaMemcpyAsync(m.nrm, in.nrm, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    m.has_prob = in.prob != nullptr;  // (the reference assigns the whole cloud: every descriptor comes along, Map.cpp:575-588)
+    if (in.prob)
+        if ((e = cudaMemcpyAsync(m.prob, in.prob, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
+    if (m.extra_rows > 0)
+        if ((e = cudaMemcpyAsync(m.extra, in.extra, (size_t)n * m.extra_rows * sizeof(float), cudaMemcpyDeviceToDevice, s)) != cudaSuccess) return e;
     m.n = n;
     m.n_active = n;
     m.all_loaded = true;
@@ -407,26 +488,43 @@ cudaError_t store_window(MapStore& m, int load, const int32_t* slab6, int64_t* c
     return cudaGetLastError();
 }
 
-cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const float* d_in, int rows, int dim, const float* d_in_nrm,
-                                        int64_t n_in, const int32_t* d_nn_id, float min_dist, int64_t* n_kept, uint8_t* d_keep_out,
-                                        cudaStream_t s) {
+// DataPoints::concatenate keeps only descriptors present in both clouds; a first cloud (empty store) brings its own.
+// Returns which descriptors the store keeps and prepares the `extra` block.
+static cudaError_t concat_layout(MapStore& m, const DevCloud& in, bool first, bool& keep_n, bool& keep_p, bool& keep_x, cudaStream_t s) {
+    keep_n = first ? (in.nrm != nullptr) : (m.has_normals && in.nrm != nullptr);
+    keep_p = first ? (in.prob != nullptr) : (m.has_prob && in.prob != nullptr);
+    const int in_rows = in.extra ? in.extra_rows : 0;
+    if (first) {
+        cudaError_t e = store_set_extra_rows(m, in_rows, s);
+        if (e != cudaSuccess) return e;
+    } else if (in_rows != m.extra_rows) {
+        m.extra_rows = 0;  // layouts differ and the caller did not reconcile them (store_select_extra): no common descriptor
+    }
+    keep_x = m.extra_rows > 0;
+    return cudaSuccess;
+}
+
+cudaError_t store_insert_point_distance(MapStore& m, GridIndex& scratch, const DevCloud& in, int dim, const int32_t* d_nn_id, float min_dist,
+                                        int64_t* n_kept, uint8_t* d_keep_out, cudaStream_t s) {
     cudaError_t e;
     *n_kept = 0;
+    const int64_t n_in = in.n;
     if (n_in == 0) return cudaSuccess;
     if ((e = ensure_tmp(m, n_in + 1)) != cudaSuccess) return e;
-    pd_keep_kernel<<<blocks_for(n_in), 256, 0, s>>>(d_in, rows, dim, (long long)n_in, m.feat, d_nn_id, min_dist * min_dist, m.tmp_u32a);
+    pd_keep_kernel<<<blocks_for(n_in), 256, 0, s>>>(in.feat, in.rows, dim, (long long)n_in, m.feat, d_nn_id, min_dist * min_dist, m.tmp_u32a);
     if ((e = cudaMemsetAsync(m.tmp_u32a + n_in, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
     if ((e = exclusive_sum(scratch, m.tmp_u32a, m.tmp_u32b, n_in + 1, s)) != cudaSuccess) return e;
     uint32_t total = 0;
     if ((e = cudaMemcpyAsync(&total, m.tmp_u32b + n_in, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    bool keep_n, keep_p, keep_x;
+    if ((e = concat_layout(m, in, m.n == 0, keep_n, keep_p, keep_x, s)) != cudaSuccess) return e;
     if ((e = store_reserve(m, dim, m.n + total, s)) != cudaSuccess) return e;
-    // DataPoints::concatenate keeps only descriptors present in both clouds
-    const bool keep_normals = m.has_normals && d_in_nrm != nullptr;
-    pd_append_kernel<<<blocks_for(n_in), 256, 0, s>>>(d_in, rows, dim, d_in_nrm, (long long)n_in, m.tmp_u32a, m.tmp_u32b, (long long)m.n,
-                                                      m.feat, keep_normals ? m.nrm : nullptr, nullptr, nullptr, m.loaded, d_keep_out);
-    m.has_normals = keep_normals;
-    m.has_prob = false;  // the PointDistance entry point carries no probabilityDynamic on the input
+    pd_append_kernel<<<blocks_for(n_in), 256, 0, s>>>(in.feat, in.rows, dim, in.nrm, (long long)n_in, m.tmp_u32a, m.tmp_u32b, (long long)m.n, m.feat,
+                                                      keep_n ? m.nrm : nullptr, in.prob, keep_p ? m.prob : nullptr, m.loaded, d_keep_out, in.extra,
+                                                      keep_x ? m.extra : nullptr, m.extra_rows);
+    m.has_normals = keep_n;
+    m.has_prob = keep_p;
     m.n += total;
     m.n_active += total;
     *n_kept = total;
@@ -481,7 +579,8 @@ __device__ __forceinline__ unsigned long long octree_mix64(unsigned long long x)
 //   leaf's centroid (first one on ties).  In modes 1 and 3 the head thread of a run flags the whole run.
 __global__ void __launch_bounds__(256) octree_mark_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                           long long n_active, int dim, int mode, unsigned long long seed, float4* __restrict__ feat,
-                                                          float* __restrict__ nrm, float* __restrict__ prob, uint32_t* __restrict__ remove) {
+                                                          float* __restrict__ nrm, float* __restrict__ prob, uint32_t* __restrict__ remove,
+                                                          float* __restrict__ extra, int extra_rows) {
     const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (j >= n_active) return;
     const bool head = (j == 0) || (keys[j] != keys[j - 1]);
@@ -545,6 +644,11 @@ __global__ void __launch_bounds__(256) octree_mark_kernel(const unsigned long lo
             nrm[(long long)i * dim + 1] = n1 * inv;
             if (dim == 3) nrm[(long long)i * dim + 2] = n2 * inv;
         }
+        for (int c = 0; c < extra_rows; ++c) {  // the centroid sampler averages every descriptor (LPM OctreeGrid CentroidSampler)
+            float sx2 = 0.f;
+            for (long long t = j; t < n_active && keys[t] == keys[j]; ++t) sx2 += extra[(long long)vals[t] * extra_rows + c];
+            extra[(long long)i * extra_rows + c] = sx2 * inv;
+        }
     }
 }
 
@@ -564,7 +668,8 @@ __global__ void __launch_bounds__(256) invert_flags_kernel(uint32_t* __restrict_
 __global__ void __launch_bounds__(256) compact_store_kernel(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ offs, long long n, int dim,
                                                             const float4* __restrict__ feat, const float* __restrict__ nrm, const float* __restrict__ prob,
                                                             const uint8_t* __restrict__ loaded, float4* __restrict__ feat2, float* __restrict__ nrm2,
-                                                            float* __restrict__ prob2, uint8_t* __restrict__ loaded2) {
+                                                            float* __restrict__ prob2, uint8_t* __restrict__ loaded2,
+                                                            const float* __restrict__ extra, float* __restrict__ extra2, int extra_rows) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n || !keep[i]) return;
     const long long d = offs[i];
@@ -573,6 +678,8 @@ __global__ void __launch_bounds__(256) compact_store_kernel(const uint32_t* __re
     if (nrm)
         for (int c = 0; c < dim; ++c) nrm2[d * dim + c] = nrm[i * dim + c];
     if (prob) prob2[d] = prob[i];
+    if (extra)
+        for (int c = 0; c < extra_rows; ++c) extra2[d * extra_rows + c] = extra[i * extra_rows + c];
 }
 
 // remove the store points whose flag in tmp_u32a is 1 (order of the survivors preserved)
@@ -585,12 +692,14 @@ cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64
     uint32_t kept = 0;
     if ((e = cudaMemcpyAsync(&kept, m.tmp_u32b + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     compact_store_kernel<<<blocks_for(n), 256, 0, s>>>(m.tmp_u32a, m.tmp_u32b, (long long)n, dim, m.feat, m.has_normals ? m.nrm : nullptr,
-                                                       m.has_prob ? m.prob : nullptr, m.loaded, m.feat2, m.nrm2, m.prob2, m.loaded2);
+                                                       m.has_prob ? m.prob : nullptr, m.loaded, m.feat2, m.nrm2, m.prob2, m.loaded2,
+                                                       m.extra_rows > 0 ? m.extra : nullptr, m.extra2, m.extra_rows);
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     std::swap(m.feat, m.feat2);
     std::swap(m.nrm, m.nrm2);
     std::swap(m.prob, m.prob2);
     std::swap(m.loaded, m.loaded2);
+    if (m.extra_rows > 0) std::swap(m.extra, m.extra2);
     *n_removed = n - (int64_t)kept;
     m.nrm_epoch_ok = false;  // points moved / vanished: the incremental normals bookkeeping starts over
     m.n = kept;
@@ -647,20 +756,25 @@ __global__ void __launch_bounds__(256) filter_compact_kernel(const float* __rest
 }
 }  // namespace
 
-cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, float* d_feat, int rows, int dim, int64_t n, const b200icp_filter* chain,
-                                int n_filters, float* d_out, int64_t* n_out, cudaStream_t s) {
+cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, const DevCloud& in, int dim, const b200icp_filter* chain, int n_filters,
+                                float* out_feat, float* out_nrm, float* out_prob, float* out_extra, int64_t* n_out, cudaStream_t s) {
     cudaError_t e;
     *n_out = 0;
+    const int64_t n = in.n;
     if (n == 0) return cudaSuccess;
     if (n_filters > 8) return cudaErrorInvalidValue;
     if ((e = ensure_tmp(tmp, n + 1)) != cudaSuccess) return e;
     FilterChain ch;
     ch.n = n_filters;
     for (int i = 0; i < n_filters; ++i) ch.f[i] = chain[i];
-    filter_flags_kernel<<<blocks_for(n), 256, 0, s>>>(d_feat, rows, dim, (long long)n, ch, tmp.tmp_u32a);
+    filter_flags_kernel<<<blocks_for(n), 256, 0, s>>>(in.feat, in.rows, dim, (long long)n, ch, tmp.tmp_u32a);
     if ((e = cudaMemsetAsync(tmp.tmp_u32a + n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
     if ((e = exclusive_sum(scratch, tmp.tmp_u32a, tmp.tmp_u32b, n + 1, s)) != cudaSuccess) return e;
-    filter_compact_kernel<<<blocks_for(n), 256, 0, s>>>(d_feat, rows, (long long)n, tmp.tmp_u32a, tmp.tmp_u32b, d_out);
+    filter_compact_kernel<<<blocks_for(n), 256, 0, s>>>(in.feat, in.rows, (long long)n, tmp.tmp_u32a, tmp.tmp_u32b, out_feat);
+    if (in.nrm && out_nrm) filter_compact_kernel<<<blocks_for(n), 256, 0, s>>>(in.nrm, dim, (long long)n, tmp.tmp_u32a, tmp.tmp_u32b, out_nrm);
+    if (in.prob && out_prob) filter_compact_kernel<<<blocks_for(n), 256, 0, s>>>(in.prob, 1, (long long)n, tmp.tmp_u32a, tmp.tmp_u32b, out_prob);
+    if (in.extra && out_extra && in.extra_rows > 0)
+        filter_compact_kernel<<<blocks_for(n), 256, 0, s>>>(in.extra, in.extra_rows, (long long)n, tmp.tmp_u32a, tmp.tmp_u32b, out_extra);
     uint32_t total = 0;
     if ((e = cudaMemcpyAsync(&total, tmp.tmp_u32b + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
@@ -668,20 +782,18 @@ cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, float* d_feat
     return cudaGetLastError();
 }
 
-cudaError_t store_append_all(MapStore& m, const float* d_in, int rows, int dim, const float* d_in_nrm, const float* d_in_prob,
-                             int64_t n_in, cudaStream_t s) {
+cudaError_t store_append_all(MapStore& m, const DevCloud& in, int dim, cudaStream_t s) {
     cudaError_t e;
+    const int64_t n_in = in.n;
     if (n_in == 0) return cudaSuccess;
-    const bool first = m.n == 0;
+    bool keep_n, keep_p, keep_x;
+    if ((e = concat_layout(m, in, m.n == 0, keep_n, keep_p, keep_x, s)) != cudaSuccess) return e;
     if ((e = store_reserve(m, dim, m.n + n_in, s)) != cudaSuccess) return e;
     if ((e = ensure_tmp(m, n_in + 1)) != cudaSuccess) return e;
-    // DataPoints::concatenate keeps only descriptors present in both clouds; a first cloud brings its own
-    const bool keep_n = first ? (d_in_nrm != nullptr) : (m.has_normals && d_in_nrm != nullptr);
-    const bool keep_p = first ? (d_in_prob != nullptr) : (m.has_prob && d_in_prob != nullptr);
     ones_kernel<<<blocks_for(n_in), 256, 0, s>>>(m.tmp_u32a, m.tmp_u32b, (long long)n_in);
-    pd_append_kernel<<<blocks_for(n_in), 256, 0, s>>>(d_in, rows, dim, d_in_nrm, (long long)n_in, m.tmp_u32a, m.tmp_u32b, (long long)m.n,
-                                                      m.feat, keep_n ? m.nrm : nullptr, d_in_prob, keep_p ? m.prob : nullptr, m.loaded,
-                                                      nullptr);
+    pd_append_kernel<<<blocks_for(n_in), 256, 0, s>>>(in.feat, in.rows, dim, in.nrm, (long long)n_in, m.tmp_u32a, m.tmp_u32b, (long long)m.n, m.feat,
+                                                      keep_n ? m.nrm : nullptr, in.prob, keep_p ? m.prob : nullptr, m.loaded, nullptr, in.extra,
+                                                      keep_x ? m.extra : nullptr, m.extra_rows);
     m.has_normals = keep_n;
     m.has_prob = keep_p;
     m.n += n_in;
@@ -740,8 +852,36 @@ cudaError_t store_octree_filter(MapStore& m, GridIndex& scratch, int dim, float 
         return e;
     if ((e = cudaMemsetAsync(m.tmp_u32a, 0, (size_t)(m.n + 1) * sizeof(uint32_t), s)) != cudaSuccess) return e;
     octree_mark_kernel<<<blocks_for(na), 256, 0, s>>>(m.keys64_b, scratch.vals_out, (long long)na, dim, sampling_method, (unsigned long long)seed, m.feat,
-                                                      m.has_normals ? m.nrm : nullptr, m.has_prob ? m.prob : nullptr, m.tmp_u32a);
+                                                      m.has_normals ? m.nrm : nullptr, m.has_prob ? m.prob : nullptr, m.tmp_u32a,
+                                                      m.extra_rows > 0 ? m.extra : nullptr, m.extra_rows > 0 ? m.extra_rows : 0);
     return store_remove_flagged(m, scratch, dim, n_removed, s);
+}
+
+namespace {
+__global__ void __launch_bounds__(256) loaded_flags_kernel(const uint8_t* __restrict__ loaded, long long n, uint32_t* __restrict__ remove) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) remove[i] = loaded[i] ? 1u : 0u;
+}
+}  // namespace
+
+// localPointCloud = cloud (a host-signature MapperModule returned it): the loaded points go, the cloud's points come, parked points
+// stay.  With nothing parked the cloud's descriptor set becomes the map's; else concatenate's intersection rule applies.
+cudaError_t store_replace_loaded(MapStore& m, GridIndex& scratch, const DevCloud& in, int dim, cudaStream_t s) {
+    cudaError_t e;
+    if (m.n > 0) {
+        if (m.n_active == m.n) {
+            m.n = 0;
+            m.n_active = 0;
+        } else if (m.n_active > 0) {
+            if ((e = ensure_tmp(m, m.n + 1)) != cudaSuccess) return e;
+            loaded_flags_kernel<<<blocks_for(m.n), 256, 0, s>>>(m.loaded, (long long)m.n, m.tmp_u32a);
+            int64_t removed = 0;
+            if ((e = store_remove_flagged(m, scratch, dim, &removed, s)) != cudaSuccess) return e;
+        }
+    }
+    m.nrm_epoch_ok = false;
+    if (in.n == 0) return cudaSuccess;
+    return store_append_all(m, in, dim, s);
 }
 
 cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s) {

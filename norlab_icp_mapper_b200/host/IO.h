@@ -5,8 +5,8 @@
 //     VERTICES n 2n / POINT_DATA n / SCALARS <name> float + LOOKUP_TABLE default ...), ASCII and BINARY;
 //   * the trajectory CSV of the example (same file, :15-172): a header row naming the columns, of which
 //     header.stamp.{sec,nanosec} and pose.pose.{position.{x,y,z},orientation.{x,y,z,w}} are used.
-// Header-only, host-only, no dependencies.  Descriptors other than `normals` and `probabilityDynamic` (the two this
-// path computes with) are parsed and dropped.
+// Header-only, host-only, no dependencies.  Every point-data array becomes a descriptor of the cloud (SCALARS with their
+// component count, VECTORS / NORMALS with three rows); COLOR_SCALARS and FIELD arrays are skipped.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -128,7 +128,7 @@ inline DataPoints loadVTK(const std::string& path, int dim = 3) {
             if (tok != "LOOKUP_TABLE") throw std::runtime_error(path + ": SCALARS without LOOKUP_TABLE");
             in >> tok;  // table name
             const std::vector<float> v = detail::readValues(in, binary, type, n * (size_t)comps);
-            if (name == "probabilityDynamic" && comps == 1) out.probabilityDynamic = v;
+            out.addDescriptor(name, comps, v);  // (`probabilityDynamic` lands in its own member)
         } else if (tok == "NORMALS" || tok == "VECTORS" || tok == "COLOR_SCALARS") {
             std::string name, type = "float";
             size_t comps = 3;
@@ -144,6 +144,12 @@ inline DataPoints loadVTK(const std::string& path, int dim = 3) {
                 out.normals.resize(n * (size_t)dim);
                 for (size_t i = 0; i < n; ++i)
                     for (int d = 0; d < dim; ++d) out.normals[i * dim + d] = v[i * 3 + d];
+            } else if (tok != "COLOR_SCALARS") {
+                // a vector descriptor (observationDirections, eigVectors ...): dim rows, like libpointmatcher keeps them
+                std::vector<float> d2(n * (size_t)dim);
+                for (size_t i = 0; i < n; ++i)
+                    for (int d = 0; d < dim; ++d) d2[i * dim + d] = v[i * 3 + d];
+                out.addDescriptor(name, dim, d2);
             }
         } else if (tok == "FIELD") {
             std::string name;
@@ -211,6 +217,21 @@ inline void saveVTK(const DataPoints& cloud, const std::string& path, bool binar
     if (!cloud.probabilityDynamic.empty()) {
         out << "SCALARS probabilityDynamic float\nLOOKUP_TABLE default\n";
         writeFloats(cloud.probabilityDynamic, 1);
+    }
+    {
+        const int rows = cloud.getDescriptorRows();
+        int r0 = 0;
+        for (const Label& l : cloud.descriptorLabels) {
+            const bool vec = dim == 3 && l.span == 3;  // three-row descriptors are written as VECTORS, the rest as SCALARS
+            std::vector<float> v(n * (size_t)(vec ? 3 : l.span), 0.f);
+            for (size_t i = 0; i < n; ++i)
+                for (int c = 0; c < l.span; ++c) v[i * (vec ? 3 : l.span) + c] = cloud.descriptors[i * rows + r0 + c];
+            if (vec) out << "VECTORS " << l.text << " float\n";
+            else if (l.span == 1) out << "SCALARS " << l.text << " float\nLOOKUP_TABLE default\n";
+            else out << "SCALARS " << l.text << " float " << l.span << "\nLOOKUP_TABLE default\n";
+            writeFloats(v, vec ? 3 : (size_t)l.span);
+            r0 += l.span;
+        }
     }
     if (!out) throw std::runtime_error("write error on " + path);
 }

@@ -64,11 +64,16 @@ void Mapper::applyInputFilters(DataPoints& in) {
     radius.remove_inside = 0;
     chain.push_back(radius);
     chain.insert(chain.end(), inputFilters.begin(), inputFilters.end());
-    if (!in.normals.empty()) throw std::runtime_error("applyInputFilters: descriptors on the raw input are not carried through the device chain");
-    int64_t n = in.getNbPoints();
-    ICPSequence::check(icp.context(), b200icp_filter_cloud(icp.context(), in.features.data(), in.dim + 1, &n, chain.data(), (int32_t)chain.size()));
-    in.features.resize((size_t)n * (in.dim + 1));
-    attachInputDescriptors(in);
+    // The raw scan goes to the device ONCE, with every descriptor it carries; the chain runs on that copy (descriptors follow
+    // the surviving points) and, with setDeviceResidentInput(true), stays there for processInput.
+    DataPoints dev = icp.toDevice(in);
+    int64_t n = dev.deviceCount;
+    ICPSequence::check(icp.context(), b200icp_scan_filter(icp.context(), chain.data(), (int32_t)chain.size(), &n));
+    dev.deviceCount = n;
+    if (addProbabilityDynamic && !icp.scanHas("probabilityDynamic")) ICPSequence::check(icp.context(), b200icp_scan_add_prob(icp.context(), probabilityDynamicValue));
+    if (inputSurfaceNormalKnn > 0 && !icp.scanHas("normals") && n > 0)
+        ICPSequence::check(icp.context(), b200icp_scan_surface_normals(icp.context(), inputSurfaceNormalKnn));
+    in = deviceResidentInput ? dev : icp.materialize(dev);
 }
 
 // Mapper.cpp:194-238
@@ -87,10 +92,10 @@ struct StepTimer {  // B200MAPPER_TIMING=1 prints the wall time of each step of 
 
 void Mapper::processInput(const DataPoints& filteredInputInSensorFrame, const TransformationParameters& estimatedPose, double timeStamp) {
     StepTimer timer;
-    // One upload: the scan goes to the context's device slot and the steps below (two rigid transforms, icp(input), the
-    // map insert) work on that copy.  Scans that carry normals, or B200MAPPER_HOST_SCAN=1, take the host path.
+    // One upload: the scan goes to the context's device slot (it is there already when applyInputFilters left it there) and the
+    // steps below (two rigid transforms, icp(input), the map update) work on that copy.  B200MAPPER_HOST_SCAN=1 takes the host path.
     static const bool hostScan = std::getenv("B200MAPPER_HOST_SCAN") != nullptr;
-    const bool deviceScan = !hostScan && filteredInputInSensorFrame.normals.empty() && filteredInputInSensorFrame.getNbPoints() > 0;
+    const bool deviceScan = filteredInputInSensorFrame.onDevice || (!hostScan && filteredInputInSensorFrame.getNbPoints() > 0);
     DataPoints input = deviceScan ? rigidTransform(icp, icp.toDevice(filteredInputInSensorFrame), estimatedPose)
                                   : rigidTransform(icp, filteredInputInSensorFrame, estimatedPose);
     timer.lap("transform(input, T_est)");

@@ -47,6 +47,7 @@ class Mapper {
     std::mutex poseLock, trajectoryLock;
     MapperModuleRegistrar registrar;
     bool lastInputUpdatedMap = false;
+    bool deviceResidentInput = false;
 
     void fillRegistrar();
     void updateMap(const DataPoints& currentInput, const TransformationParameters& currentPose, double currentTimeStamp);
@@ -55,6 +56,10 @@ class Mapper {
    public:
     Mapper(const MapperConfig& config, bool is3D, bool isOnline, bool isMapping, bool saveMapCellsOnHardDrive, int device = 0);
     void applyInputFilters(DataPoints& inputInSensorFrame);
+    // true: applyInputFilters leaves the filtered scan in the device slot (`onDevice` cloud) and processInput continues on it --
+    // one host-to-device copy per scan.  false (default, the reference's contract): the caller gets the filtered cloud back.
+    void setDeviceResidentInput(bool on) { deviceResidentInput = on; }
+    DataPoints materialize(const DataPoints& cloud) { return icp.materialize(cloud); }
     // the descriptor-producing entries of the `input:` chain: AddDescriptorDataPointsFilter{probabilityDynamic} and
     // SurfaceNormalDataPointsFilter{knn} (normals on the reading, for SurfaceNormalOutlierFilter)
     void attachInputDescriptors(DataPoints& input) {

@@ -23,8 +23,16 @@ class DeviceMap {
    public:
     explicit DeviceMap(ICPSequence& icp_) : icp(icp_) {}
     b200icp_ctx* context() { return icp.context(); }
+    ICPSequence& sequence() { return icp; }
     //! host copy of an input that lives in the device scan slot (no-op for host inputs)
     DataPoints host(const DataPoints& in) { return icp.materialize(in); }
+    //! the input in the device scan slot (uploaded now if it is a host cloud), descriptors reconciled with the map's
+    //! (DataPoints::concatenate keeps the common ones): what every `map.concatenate(input)` of a module starts with
+    DataPoints stage(const DataPoints& in) {
+        DataPoints dev = icp.toDevice(in);
+        icp.reconcileScanWithMap(getNbPointsGlobal() == 0);
+        return dev;
+    }
     int64_t getNbPoints() {
         int64_t nl = 0, ng = 0;
         b200icp_map_counts(icp.context(), &nl, &ng);
@@ -50,7 +58,23 @@ class DeviceMap {
             out.probabilityDynamic.resize((size_t)n);
             ICPSequence::check(icp.context(), b200icp_map_download_prob(icp.context(), global, out.probabilityDynamic.data(), n));
         }
+        const int xr = b200icp_map_extra_rows(icp.context());
+        if (n > 0 && xr > 0) {
+            out.descriptors.resize((size_t)n * xr);
+            out.descriptorLabels = icp.mapLabels;
+            ICPSequence::check(icp.context(), b200icp_map_download_extra(icp.context(), global, out.descriptors.data(), n));
+        }
         return out;
+    }
+    //! the local map becomes `cloud` (all its descriptors); parked cells stay where they are
+    void assignLocal(const DataPoints& cloud) {
+        if (cloud.onDevice) throw std::runtime_error("assignLocal: host cloud expected");
+        ICPSequence::check(icp.context(),
+                           b200icp_map_replace_local(icp.context(), cloud.features.data(), cloud.dim + 1, cloud.getNbPoints(),
+                                                     cloud.normals.empty() ? nullptr : cloud.normals.data(),
+                                                     cloud.probabilityDynamic.empty() ? nullptr : cloud.probabilityDynamic.data(),
+                                                     cloud.descriptors.empty() ? nullptr : cloud.descriptors.data(), cloud.getDescriptorRows()));
+        icp.mapLabels = cloud.descriptors.empty() ? Labels() : cloud.descriptorLabels;
     }
 };
 
@@ -105,14 +129,11 @@ class PointDistanceMapperModule : public MapperModule {
 
    private:
     void insert(const DataPoints& input, DeviceMap& map) {
+        // map.concatenate(inputPointsToKeep) (PointDistanceMapperModule.cpp:49) on the device: the scan is in the slot already
+        // when Mapper::processInput uploaded it, else it goes there now -- with every descriptor it carries
         int64_t added = 0;
-        if (input.onDevice) {  // the scan is already on the device (Mapper::processInput uploaded it once)
-            ICPSequence::check(map.context(), b200icp_scan_insert_point_distance(map.context(), minDistNewPoint, &added));
-            return;
-        }
-        ICPSequence::check(map.context(), b200icp_map_insert_point_distance(map.context(), input.features.data(), input.dim + 1,
-                                                                            input.getNbPoints(), input.normals.empty() ? nullptr : input.normals.data(),
-                                                                            minDistNewPoint, &added, nullptr));
+        map.stage(input);
+        ICPSequence::check(map.context(), b200icp_scan_insert_point_distance(map.context(), minDistNewPoint, &added));
     }
 };
 
@@ -140,15 +161,10 @@ class OctreeMapperModule : public MapperModule {
     void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
         inPlaceUpdateMap(input, map, pose);  // inPlaceUpdateMap(emptyMap, input): concatenate into an empty map, then filter
     }
-    void inPlaceUpdateMap(const DataPoints& input_, DeviceMap& map, const TransformationParameters&) override {
-        const DataPoints hostCopy = input_.onDevice ? map.host(input_) : DataPoints();  // (no device entry point for this module yet)
-        const DataPoints& input = input_.onDevice ? hostCopy : input_;
+    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters&) override {
         int64_t n_after = 0;
-        ICPSequence::check(map.context(),
-                           b200icp_map_octree(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
-                                              input.normals.empty() ? nullptr : input.normals.data(),
-                                              input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(), maxSizeByNode,
-                                              maxPointByNode, samplingMethod, &n_after));
+        map.stage(input);  // map.concatenate(input) (OctreeMapperModule.cpp:37) takes the scan from the slot
+        ICPSequence::check(map.context(), b200icp_scan_octree(map.context(), maxSizeByNode, maxPointByNode, samplingMethod, &n_after));
     }
 };
 
@@ -171,22 +187,46 @@ class DynamicPointsMapperModule : public MapperModule {
             else throw InvalidParameter("DynamicPointsMapperModule: unknown parameter " + kv.first);
         }
     }
-    void inPlaceCreateMap(const DataPoints& input_, DeviceMap& map, const TransformationParameters&) override {
-        const DataPoints hostCopy = input_.onDevice ? map.host(input_) : DataPoints();
-        const DataPoints& input = input_.onDevice ? hostCopy : input_;
+    void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters&) override {
         // createMap copies the input (DynamicPointsMapperModule.cpp:16-25): an unfiltered insert
         int64_t added = 0;
         if (map.getNbPoints() != 0) throw std::runtime_error("DynamicPointsMapperModule::createMap on a non-empty map");
-        ICPSequence::check(map.context(), b200icp_map_append(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
-                                                             input.normals.empty() ? nullptr : input.normals.data(),
-                                                             input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(), &added));
+        map.stage(input);
+        ICPSequence::check(map.context(), b200icp_scan_append(map.context(), &added));
     }
-    void inPlaceUpdateMap(const DataPoints& input_, DeviceMap& map, const TransformationParameters& pose) override {
-        const DataPoints hostCopy = input_.onDevice ? map.host(input_) : DataPoints();
-        const DataPoints& input = input_.onDevice ? hostCopy : input_;
-        ICPSequence::check(map.context(), b200icp_map_dynamic_points(map.context(), input.features.data(), input.dim + 1, input.getNbPoints(),
-                                                                     input.probabilityDynamic.empty() ? nullptr : input.probabilityDynamic.data(),
-                                                                     pose.m, &prm));
+    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
+        // (no concatenation here: the scan's descriptors stay as they are; only its probabilityDynamic is read)
+        map.sequence().toDevice(input);
+        ICPSequence::check(map.context(), b200icp_scan_dynamic_points(map.context(), pose.m, &prm));
+    }
+};
+
+// ---- modules written against the REFERENCE's signature (MapperModules/MapperModule.h:20-29) ----------------------
+// A third-party module that takes and returns host DataPoints drops in through this adapter: the local map is downloaded,
+// handed to the module with the input (map frame) and the pose, and what the module leaves in `map` becomes the new local
+// map on the device (all descriptors included).  It costs two PCIe trips of the local map per update -- the price of running
+// host code on a device-resident map -- and nothing when no such module is configured.
+class HostMapperModule {
+   public:
+    virtual ~HostMapperModule() = default;
+    virtual DataPoints createMap(const DataPoints& input, const TransformationParameters& pose) = 0;
+    virtual void inPlaceCreateMap(DataPoints& input, const TransformationParameters& pose) = 0;
+    virtual DataPoints updateMap(const DataPoints& input, const DataPoints& map, const TransformationParameters& pose) = 0;
+    virtual void inPlaceUpdateMap(const DataPoints& input, DataPoints& map, const TransformationParameters& pose) = 0;
+};
+
+class HostMapperModuleAdapter : public MapperModule {
+    std::shared_ptr<HostMapperModule> inner;
+
+   public:
+    explicit HostMapperModuleAdapter(std::shared_ptr<HostMapperModule> m) : inner(std::move(m)) {}
+    void inPlaceCreateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
+        map.assignLocal(inner->createMap(map.host(input), pose));
+    }
+    void inPlaceUpdateMap(const DataPoints& input, DeviceMap& map, const TransformationParameters& pose) override {
+        DataPoints local = map.download(false, input.dim);
+        inner->inPlaceUpdateMap(map.host(input), local, pose);
+        map.assignLocal(local);
     }
 };
 

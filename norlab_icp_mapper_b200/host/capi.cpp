@@ -129,6 +129,24 @@ int32_t b200mapper_process_input(b200mapper* m, const float* features, int32_t f
     });
 }
 
+int32_t b200mapper_process_raw_input(b200mapper* m, const float* features, int32_t feature_rows, int64_t n, const float* estimated_pose,
+                                     double time_stamp_seconds, int64_t* n_filtered) {
+    if (!m || (n > 0 && !features) || feature_rows != m->dim + 1) return B200ICP_ERR_INVALID_ARG;
+    return guarded(m, [&] {
+        DataPoints in = wrap(features, feature_rows, n, nullptr);
+        m->mapper->setDeviceResidentInput(true);
+        try {
+            m->mapper->applyInputFilters(in);  // upload + filter chain + descriptors, all in the device slot
+            if (n_filtered) *n_filtered = in.getNbPoints();
+            m->mapper->processInput(in, wrapT(estimated_pose, m->dim + 1), time_stamp_seconds);
+        } catch (...) {
+            m->mapper->setDeviceResidentInput(false);
+            throw;
+        }
+        m->mapper->setDeviceResidentInput(false);
+    });
+}
+
 int32_t b200mapper_get_pose(b200mapper* m, float* pose) {
     if (!m || !pose) return B200ICP_ERR_INVALID_ARG;
     const TransformationParameters T = m->mapper->getPose();
@@ -157,8 +175,28 @@ int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* norm
 }
 
 int32_t b200mapper_set_map(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, int64_t n) {
+    return b200mapper_set_map_descriptors(m, features, feature_rows, normals, nullptr, n);
+}
+
+int32_t b200mapper_set_map_descriptors(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, const float* prob, int64_t n) {
     if (!m || (n > 0 && !features) || feature_rows != m->dim + 1) return B200ICP_ERR_INVALID_ARG;
-    return guarded(m, [&] { m->mapper->setMap(wrap(features, feature_rows, n, normals)); });
+    return guarded(m, [&] {
+        DataPoints d = wrap(features, feature_rows, n, normals);
+        if (prob) d.probabilityDynamic.assign(prob, prob + n);
+        m->mapper->setMap(d);
+    });
+}
+
+int32_t b200mapper_get_map_prob(b200mapper* m, float* prob, int64_t capacity, int64_t* n) {
+    if (!m || !n) return B200ICP_ERR_INVALID_ARG;
+    return guarded(m, [&] {
+        const DataPoints d = m->mapper->getMap();
+        *n = (int64_t)d.probabilityDynamic.size();
+        if (prob && *n > 0) {
+            if (capacity < *n) throw InvalidParameter("capacity too small");
+            std::memcpy(prob, d.probabilityDynamic.data(), d.probabilityDynamic.size() * sizeof(float));
+        }
+    });
 }
 
 int32_t b200mapper_get_is_mapping(const b200mapper* m) { return (m && m->mapper->getIsMapping()) ? 1 : 0; }

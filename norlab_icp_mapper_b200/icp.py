@@ -184,7 +184,6 @@ class ICP:
         """SurfaceNormalDataPointsFilter{knn} on a host cloud (N x (dim + 1)); returns N x dim normals."""
         pts = _cloud(features, self.n)
         out = np.zeros((len(pts), self.dim), np.float32)
-        self._L.b200icp_cloud_surface_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]
         self._check(self._L.b200icp_cloud_surface_normals(self._h, pts.ctypes.data, self.n, len(pts), knn, out.ctypes.data))
         return out
 
@@ -267,6 +266,129 @@ class ICP:
         T = _T_to_colmajor(pose, self.n)
         params = params or _abi.DynamicParams()
         self._check(self._L.b200icp_map_dynamic_points(self._h, inp.ctypes.data, self.n, len(inp), pptr, T.ctypes.data, C.byref(params)))
+
+    # -- the map's other descriptors (intensity, t, ring ...) ------------------------------------------
+    def map_set_extra(self, extra):
+        """extra: N x rows (one row of the array per map point), or None to drop them."""
+        if extra is None:
+            self._check(self._L.b200icp_map_set_extra(self._h, None, 0))
+            return
+        extra = np.ascontiguousarray(extra, np.float32)
+        self._check(self._L.b200icp_map_set_extra(self._h, extra.ctypes.data, extra.shape[1]))
+
+    def map_extra_rows(self):
+        return self._L.b200icp_map_extra_rows(self._h)
+
+    def map_select_extra(self, rows):
+        rows = np.ascontiguousarray(rows, np.int32)
+        self._check(self._L.b200icp_map_select_extra(self._h, rows.ctypes.data, len(rows)))
+
+    def map_download_extra(self, global_map=False):
+        n = self.map_counts()[1 if global_map else 0]
+        out = np.zeros((n, self.map_extra_rows()), np.float32)
+        if n and out.shape[1]:
+            self._check(self._L.b200icp_map_download_extra(self._h, int(global_map), out.ctypes.data, n))
+        return out
+
+    def map_replace_local(self, features, normals=None, prob=None, extra=None):
+        """localPointCloud = cloud (what a host-signature MapperModule returned)."""
+        f = _cloud(features, self.n)
+        nrm = None if normals is None else _cloud(normals, self.dim)
+        pr = None if prob is None else np.ascontiguousarray(prob, np.float32)
+        ex = None if extra is None else np.ascontiguousarray(extra, np.float32)
+        self._check(self._L.b200icp_map_replace_local(self._h, f.ctypes.data, self.n, len(f), None if nrm is None else nrm.ctypes.data,
+                                                      None if pr is None else pr.ctypes.data, None if ex is None else ex.ctypes.data,
+                                                      0 if ex is None else ex.shape[1]))
+
+    def map_insert_point_distance_prob(self, input_features, min_dist_new_point, input_normals=None, input_prob=None):
+        inp = _cloud(input_features, self.n)
+        nrm = None if input_normals is None else _cloud(input_normals, self.dim)
+        pr = None if input_prob is None else np.ascontiguousarray(input_prob, np.float32)
+        added = C.c_int64()
+        self._check(self._L.b200icp_map_insert_point_distance_prob(self._h, inp.ctypes.data, self.n, len(inp), None if nrm is None else nrm.ctypes.data,
+                                                                   None if pr is None else pr.ctypes.data, min_dist_new_point, C.byref(added), None))
+        return added.value
+
+    # -- the device-resident scan slot (one upload per scan; b200icp_scan_*) ---------------------------
+    def scan_upload(self, features, normals=None, prob=None, extra=None, rotating_rows=()):
+        f = _cloud(features, self.n)
+        self._check(self._L.b200icp_scan_upload(self._h, f.ctypes.data, self.n, len(f)))
+        if normals is not None or prob is not None or extra is not None:
+            nrm = None if normals is None else _cloud(normals, self.dim)
+            pr = None if prob is None else np.ascontiguousarray(prob, np.float32)
+            ex = None if extra is None else np.ascontiguousarray(extra, np.float32)
+            rot = np.ascontiguousarray(rotating_rows, np.int32)
+            self._check(self._L.b200icp_scan_set_descriptors(self._h, None if nrm is None else nrm.ctypes.data, None if pr is None else pr.ctypes.data,
+                                                             None if ex is None else ex.ctypes.data, 0 if ex is None else ex.shape[1],
+                                                             rot.ctypes.data if len(rot) else None, len(rot)))
+
+    def scan_info(self):
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self._L.b200icp_scan_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"n": self._L.b200icp_scan_size(self._h), "normals": bool(a.value), "prob": bool(b.value), "extra_rows": c.value}
+
+    def scan_filter(self, filters):
+        arr = (type(filters[0]) * len(filters))(*filters) if len(filters) else None
+        n = C.c_int64()
+        self._check(self._L.b200icp_scan_filter(self._h, arr, len(filters), C.byref(n)))
+        return n.value
+
+    def scan_add_prob(self, constant):
+        self._check(self._L.b200icp_scan_add_prob(self._h, constant))
+
+    def scan_surface_normals(self, knn):
+        self._check(self._L.b200icp_scan_surface_normals(self._h, knn))
+
+    def scan_select_extra(self, rows):
+        rows = np.ascontiguousarray(rows, np.int32)
+        self._check(self._L.b200icp_scan_select_extra(self._h, rows.ctypes.data, len(rows)))
+
+    def scan_transform(self, T):
+        T_cm = _T_to_colmajor(T, self.n)
+        self._check(self._L.b200icp_scan_transform(self._h, T_cm.ctypes.data))
+
+    def scan_register(self, T_init=None):
+        T_out = np.zeros(self.n * self.n, np.float32)
+        Ti = None if T_init is None else _T_to_colmajor(T_init, self.n)
+        res = Result()
+        self._check(self._L.b200icp_scan_register(self._h, None if Ti is None else Ti.ctypes.data, T_out.ctypes.data, C.byref(res)))
+        self.last_result = res
+        return T_out.reshape(self.n, self.n).T.copy()
+
+    def scan_insert_point_distance(self, min_dist_new_point):
+        added = C.c_int64()
+        self._check(self._L.b200icp_scan_insert_point_distance(self._h, min_dist_new_point, C.byref(added)))
+        return added.value
+
+    def scan_append(self):
+        added = C.c_int64()
+        self._check(self._L.b200icp_scan_append(self._h, C.byref(added)))
+        return added.value
+
+    def scan_octree(self, max_size_by_node, sampling_method=0, max_point_by_node=1):
+        n_after = C.c_int64()
+        self._check(self._L.b200icp_scan_octree(self._h, max_size_by_node, max_point_by_node, sampling_method, C.byref(n_after)))
+        return n_after.value
+
+    def scan_dynamic_points(self, pose, params=None):
+        T = _T_to_colmajor(pose, self.n)
+        params = params or _abi.DynamicParams()
+        self._check(self._L.b200icp_scan_dynamic_points(self._h, T.ctypes.data, C.byref(params)))
+
+    def scan_download(self):
+        """Returns (features, normals or None, prob or None, extra or None)."""
+        info = self.scan_info()
+        n = info["n"]
+        f = np.zeros((n, self.n), np.float32)
+        got = C.c_int64()
+        self._check(self._L.b200icp_scan_download(self._h, f.ctypes.data, n, C.byref(got)))
+        nrm = np.zeros((n, self.dim), np.float32) if info["normals"] else None
+        pr = np.zeros(n, np.float32) if info["prob"] else None
+        ex = np.zeros((n, info["extra_rows"]), np.float32) if info["extra_rows"] else None
+        if nrm is not None or pr is not None or ex is not None:
+            self._check(self._L.b200icp_scan_download_descriptors(self._h, None if nrm is None else nrm.ctypes.data, None if pr is None else pr.ctypes.data,
+                                                                  None if ex is None else ex.ctypes.data, n))
+        return f, nrm, pr, ex
 
     # -- instrumentation ---------------------------------------------------------------------------
     def stream(self):

@@ -16,7 +16,8 @@ SO_PATH = os.path.join(_HERE, "libb200mapper.so")
 SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "b200mapper_apply_input_filters",
            "b200mapper_process_input", "b200mapper_get_pose", "b200mapper_get_map", "b200mapper_get_new_local_map",
            "b200mapper_set_map", "b200mapper_get_is_mapping", "b200mapper_set_is_mapping", "b200mapper_trajectory_size",
-           "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates"]
+           "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates", "b200mapper_process_raw_input",
+           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob"]
 
 
 class InputFilter(C.Structure):
@@ -84,6 +85,9 @@ def load():
     L.b200mapper_last_error.restype = C.c_char_p
     L.b200mapper_apply_input_filters.argtypes = [vp, vp, i32, C.POINTER(i64)]
     L.b200mapper_process_input.argtypes = [vp, vp, i32, i64, vp, C.c_double]
+    L.b200mapper_process_raw_input.argtypes = [vp, vp, i32, i64, vp, C.c_double, C.POINTER(i64)]
+    L.b200mapper_set_map_descriptors.argtypes = [vp, vp, i32, vp, vp, i64]
+    L.b200mapper_get_map_prob.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.b200mapper_get_pose.argtypes = [vp, vp]
     L.b200mapper_get_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.b200mapper_get_new_local_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
@@ -164,6 +168,15 @@ class Mapper:
         T = np.ascontiguousarray(np.asarray(estimatedPose, np.float32).T).ravel()
         self._check(self._L.b200mapper_process_input(self._h, cloud.ctypes.data, self.n, len(cloud), T.ctypes.data, float(timeStamp)))
 
+    def processRawInput(self, raw_cloud_sensor_frame, estimatedPose, timeStamp):
+        """applyInputFilters + processInput with ONE host-to-device copy (the filter chain runs on the device-resident scan).
+        Returns the point count after the `input:` chain."""
+        cloud = np.ascontiguousarray(raw_cloud_sensor_frame, np.float32)
+        T = np.ascontiguousarray(np.asarray(estimatedPose, np.float32).T).ravel()
+        n = C.c_int64()
+        self._check(self._L.b200mapper_process_raw_input(self._h, cloud.ctypes.data, self.n, len(cloud), T.ctypes.data, float(timeStamp), C.byref(n)))
+        return n.value
+
     def getPose(self):
         T = np.zeros(self.n * self.n, np.float32)
         self._check(self._L.b200mapper_get_pose(self._h, T.ctypes.data))
@@ -178,13 +191,26 @@ class Mapper:
             self._check(self._L.b200mapper_get_map(self._h, feat.ctypes.data, nrm.ctypes.data, n.value, C.byref(n)))
         return feat, (None if np.isnan(nrm).all() else nrm)
 
-    def setMap(self, features, normals=None):
+    def getMapProbabilityDynamic(self):
+        """The probabilityDynamic descriptor of getMap(), or None when the map does not carry it."""
+        n = C.c_int64()
+        self._check(self._L.b200mapper_get_map_prob(self._h, None, 0, C.byref(n)))
+        if n.value == 0:
+            return None
+        out = np.zeros(n.value, np.float32)
+        self._check(self._L.b200mapper_get_map_prob(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def setMap(self, features, normals=None, probabilityDynamic=None):
         features = np.ascontiguousarray(features, np.float32)
-        nptr = None
+        nptr = pptr = None
         if normals is not None:
             normals = np.ascontiguousarray(normals, np.float32)
             nptr = normals.ctypes.data
-        self._check(self._L.b200mapper_set_map(self._h, features.ctypes.data, self.n, nptr, len(features)))
+        if probabilityDynamic is not None:
+            probabilityDynamic = np.ascontiguousarray(probabilityDynamic, np.float32)
+            pptr = probabilityDynamic.ctypes.data
+        self._check(self._L.b200mapper_set_map_descriptors(self._h, features.ctypes.data, self.n, nptr, pptr, len(features)))
 
     def getIsMapping(self):
         return bool(self._L.b200mapper_get_is_mapping(self._h))
