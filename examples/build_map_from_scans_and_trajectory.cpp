@@ -5,11 +5,18 @@
 // examples/config.yaml, spelled out on the MapperConfig struct; `--icp point_to_plane` swaps the example's Identity error
 // minimiser (the shipped config does no registration at all) for the chain of docs/MapperConfiguration.md:172-189.
 //
-//   build_map_from_scans_and_trajectory <dataPath> [--icp identity|point_to_plane] [--io-only] [--binary]
+//   build_map_from_scans_and_trajectory <dataPath> [--icp identity|point_to_plane] [--io-only] [--binary] [--host-module]
+//
+// --host-module swaps the device OctreeMapperModule for a module written against the REFERENCE's plugin signature
+// (MapperModules/MapperModule.h:20-29: host DataPoints in, host DataPoints out), run through HostMapperModuleAdapter: a
+// voxel-grid thinning that keeps the first point of every 15 cm voxel -- a stand-in for a third-party module.
 //
 // --io-only concatenates the scans at their trajectory poses on the host and writes the result: a check of the readers /
 // writer that needs no GPU.
+#include <algorithm>
+#include <array>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
@@ -29,16 +36,66 @@ static b200icp_filter box(float x0, float x1, float y0, float y1, float z0, floa
     return f;
 }
 
+// A third-party style module: reference signature, host clouds only, knows nothing about the device.
+class VoxelFirstHostModule : public HostMapperModule {
+    float voxel;
+
+   public:
+    explicit VoxelFirstHostModule(float v) : voxel(v) {}
+    DataPoints createMap(const DataPoints& input, const TransformationParameters& pose) override {
+        DataPoints out;
+        out.dim = input.dim;
+        inPlaceUpdateMap(input, out, pose);
+        return out;
+    }
+    void inPlaceCreateMap(DataPoints& input, const TransformationParameters& pose) override { input = createMap(input, pose); }
+    DataPoints updateMap(const DataPoints& input, const DataPoints& map, const TransformationParameters& pose) override {
+        DataPoints out = map;
+        inPlaceUpdateMap(input, out, pose);
+        return out;
+    }
+    void inPlaceUpdateMap(const DataPoints& input, DataPoints& map, const TransformationParameters&) override {
+        map.concatenate(input);  // (descriptors both clouds carry survive, like PM::DataPoints::concatenate)
+        const int rows = map.dim + 1, xr = map.getDescriptorRows();
+        const int64_t n = map.getNbPoints();
+        std::vector<std::array<int64_t, 3>> seen;
+        std::vector<int64_t> keep;
+        {
+            std::vector<std::pair<std::array<int64_t, 3>, int64_t>> keyed((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                std::array<int64_t, 3> k{0, 0, 0};
+                for (int d = 0; d < map.dim; ++d) k[d] = (int64_t)std::floor(map.features[i * rows + d] / voxel);
+                keyed[i] = {k, i};
+            }
+            std::sort(keyed.begin(), keyed.end());
+            for (size_t j = 0; j < keyed.size(); ++j)
+                if (j == 0 || keyed[j].first != keyed[j - 1].first) keep.push_back(keyed[j].second);
+            std::sort(keep.begin(), keep.end());
+        }
+        DataPoints out;
+        out.dim = map.dim;
+        out.descriptorLabels = map.descriptorLabels;
+        for (int64_t i : keep) {
+            out.features.insert(out.features.end(), map.features.begin() + i * rows, map.features.begin() + (i + 1) * rows);
+            if (!map.normals.empty()) out.normals.insert(out.normals.end(), map.normals.begin() + i * map.dim, map.normals.begin() + (i + 1) * map.dim);
+            if (!map.probabilityDynamic.empty()) out.probabilityDynamic.push_back(map.probabilityDynamic[i]);
+            if (xr > 0) out.descriptors.insert(out.descriptors.end(), map.descriptors.begin() + i * xr, map.descriptors.begin() + (i + 1) * xr);
+        }
+        map = out;
+    }
+};
+
 int main(int argc, char* argv[]) {
     if (argc < 2) {
         std::cerr << "Please provide a dataPath as an argument." << std::endl;
         return -1;
     }
     const fs::path dataPath = argv[1];
-    bool ioOnly = false, binary = false, pointToPlane = false;
+    bool ioOnly = false, binary = false, pointToPlane = false, hostModule = false;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--io-only")) ioOnly = true;
         else if (!std::strcmp(argv[i], "--binary")) binary = true;
+        else if (!std::strcmp(argv[i], "--host-module")) hostModule = true;
         else if (!std::strcmp(argv[i], "--icp") && i + 1 < argc) pointToPlane = !std::strcmp(argv[++i], "point_to_plane");
     }
     try {
@@ -91,7 +148,13 @@ int main(int argc, char* argv[]) {
                                            {"epsilonA", "0.01"}, {"epsilonD", "0.01"}}},
             {"OctreeMapperModule", {{"buildParallel", "1"}, {"maxSizeByNode", "0.15"}, {"samplingMethod", "1"}}}};
 
+        if (hostModule) {
+            cfg.mapperModules.pop_back();
+            cfg.extraModules.push_back(std::make_shared<HostMapperModuleAdapter>(std::make_shared<VoxelFirstHostModule>(0.15f)));
+        }
+
         Mapper mapper(cfg, /*is3D=*/true, /*isOnline=*/false, /*isMapping=*/true, /*saveMapCellsOnHardDrive=*/false);
+        mapper.setDeviceResidentInput(true);  // the filtered scan stays in the device slot between applyInputFilters and processInput
         const auto t0 = std::chrono::steady_clock::now();
         for (size_t i = 0; i < scans.size(); ++i) {
             DataPoints inputCloud = io::loadVTK(scans[i]);

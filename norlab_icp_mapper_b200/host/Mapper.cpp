@@ -45,10 +45,11 @@ Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMa
     }
     if (config.sensorMaxRange < 0) throw InvalidParameter("Invalid sensor max range: " + std::to_string(config.sensorMaxRange));
     map.setSensorMaxRange(config.sensorMaxRange);
-    if (config.mapperModules.empty()) {  // setDefaultMapperModule (Mapper.cpp:330-336)
+    if (config.mapperModules.empty() && config.extraModules.empty()) {  // setDefaultMapperModule (Mapper.cpp:330-336)
         map.addMapperModule(registrar.create("PointDistanceMapperModule", Parameters{{"minDistNewPoint", "0.15"}}));
     } else {
         for (const auto& m : config.mapperModules) map.addMapperModule(registrar.create(m.first, m.second));
+        for (const auto& m : config.extraModules) map.addMapperModule(m);
     }
 }
 

@@ -25,6 +25,8 @@ struct MapperConfig {
     float mapUpdateValue = 1.0f;                             // ... .value (DEFAULT_MAP_UPDATE_DISTANCE, Mapper.h:20)
     float sensorMaxRange = 200.0f;                           // mapper.sensorMaxRange (Mapper.cpp:152-160)
     std::vector<std::pair<std::string, Parameters>> mapperModules;  // mapper.mapperModule (Mapper.cpp:162-172); empty -> default
+    std::vector<std::shared_ptr<MapperModule>> extraModules;        // ready-made module objects appended after the named ones (third-party
+                                                                     // modules, e.g. a HostMapperModuleAdapter around a reference-signature one)
 };
 
 class Mapper {

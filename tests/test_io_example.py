@@ -126,3 +126,30 @@ def test_example_pipeline_on_the_device(tmp_path):
     assert 5_000 < len(m) <= 80_000
     keys = np.floor(m / 0.075).astype(np.int64)
     assert len(np.unique(keys, axis=0)) > 0.5 * len(m)  # thinned by the octree: few points share a 7.5 cm voxel
+
+
+@pytest.mark.gpu
+def test_example_with_a_reference_signature_module_and_scan_descriptors(tmp_path):
+    """--host-module: a module written against the reference's plugin signature (host DataPoints in and out) runs through
+    HostMapperModuleAdapter on the device-resident map; the scans' own descriptors (`intensity`, `t`, as in the reference's
+    bundled scans) travel through the input filters, both modules and the map download into map.vtk."""
+    _build()
+    from norlab_icp_mapper_b200 import synth
+    world = synth.World3D(seed=3, size=(60.0, 60.0), n_boxes=8)
+    W, _ = world.sample(120_000, np.random.default_rng(1), noise=0.01)
+    _make_dataset(str(tmp_path), n_scans=4, n_pts=20_000, world=W.astype(np.float64), seed=2)
+    r = subprocess.run([EXE, str(tmp_path), "--icp", "point_to_plane", "--host-module"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    txt = open(tmp_path / "map.vtk").read()
+    for tag in ("NORMALS normals float", "SCALARS probabilityDynamic float", "SCALARS intensity float", "SCALARS t float"):
+        assert tag in txt, tag
+    m = _read_map(str(tmp_path / "map.vtk"))
+    assert 5_000 < len(m) <= 80_000
+    keys = np.floor(m.astype(np.float64) / 0.15).astype(np.int64)
+    # the voxel module leaves one point per 15 cm voxel; the CutAtDescriptorThreshold post filter may remove some afterwards
+    assert len(np.unique(keys, axis=0)) >= len(m) - 5  # (fp32 vs fp64 voxel keys may disagree for a point on a voxel face)
+    # descriptor values are the scans' own: intensity in [0, 255], t in [0, 0.1]
+    L = txt.split("\n")
+    i0 = L.index("SCALARS intensity float") + 2
+    inten = np.array(L[i0:i0 + len(m)], dtype=np.float64)
+    assert inten.min() >= 0 and inten.max() <= 255 and inten.std() > 10
