@@ -137,7 +137,9 @@ typedef struct b200icp_config {
                              bit 8 (256) cold k = 1 search: shell-walk kernel even when maxDist is small
                              bit 9 (512) loop kernel: deal the reading to the CTAs in chunks of 8 points whatever its size
                              bits 10..11 loop kernel: value - 1 = log2 of that chunk size (1, 2, 4 points)
-                             bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3) */
+                             bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3)
+                             bit 17 (0x20000) loop kernel: no fine histogram in the two-barrier iteration (window = the whole level-0 bucket)
+                             bit 19 (0x80000) loop kernel: write the per-iteration development record (tools/gpu_loop_record.py) */
     int32_t outlier_mode[B200ICP_MAX_OUTLIER_FILTERS]; /* per filter: B200ICP_ROBUST_MODE(...) for RobustOutlierFilter, else 0 */
     int32_t checker_order; /* position of the Counter in the transformationCheckers list.  libpointmatcher runs the checkers in YAML
                               order and the Counter reports its limit by throwing MaxNumIterationsReached, which skips the checkers

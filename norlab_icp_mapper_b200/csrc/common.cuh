@@ -45,7 +45,7 @@ inline cudaError_t traced_free(void* p, const char* file, int line) {
 inline int64_t grow_capacity(int64_t n) { return n * 2 > (int64_t(1) << 20) ? n * 2 : (int64_t(1) << 20); }
 constexpr int kMaxCells = 1 << 25;  // dense cell table cap (uint32 per cell -> 128 MB)
 constexpr int kHistBins = 2048;  // radix-select: 11 + 11 + 10 bits
-constexpr int kHistWords = 24576; // uint32 words of the histogram / candidate-list buffer (layout in loop.cu)
+constexpr int kHistWords = 36864; // uint32 words of the histogram / candidate-list buffer (layout in loop.cu)
 constexpr int kAccSlots = 32;    // doubles per block partial (29 used by point-to-plane)
 constexpr int kAccBlocks = 128;      // accumulate-kernel grid (one partial each, summed in fixed order)
 constexpr int kLoopMaxBlocks = 192;  // persistent loop kernel: one CTA per SM

@@ -60,8 +60,11 @@ constexpr int kLoopG = 4;                       // lanes per query in the search
 constexpr int kChunkShiftLarge = 5, kChunkShiftSmall = 3;
 constexpr int kSmallReading = 64 * 1024, kTinyReading = 16 * 1024;
 constexpr int kCacheCap = 2048;                 // queries per CTA whose match state lives in shared memory (the rest spills to global)
-// dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[cap]
-constexpr size_t kLoopDynSmem = (size_t)kCacheCap * (3 * sizeof(float4) + sizeof(float) + sizeof(uint32_t));
+// dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[cap] | the fine histogram of a
+// two-barrier iteration
+constexpr size_t kLoopCacheBytes = (size_t)kCacheCap * (3 * sizeof(float4) + sizeof(float) + sizeof(uint32_t));
+constexpr size_t kLoopScratchBytes = 4160 * sizeof(uint32_t);
+constexpr size_t kLoopDynSmem = kLoopCacheBytes + kLoopScratchBytes;
 // Exact quantile inside the loop kernel: level 0 = 12 bits [30:19] of the float pattern (4096 bins,
 // histogrammed while searching, merged through global memory); the bucket that holds the quantile
 // then contains ~1 % of the distances, which every CTA pulls into shared memory as a candidate list
@@ -74,7 +77,7 @@ constexpr int kSelListCap = 4096;
 // [6400] list counter | [8192, 8192 + kSelListCap) candidate list
 constexpr int kHistL1 = 4096, kHistL2 = 6144, kHistCount = 6400, kHistList = 8192;
 constexpr int kHistDebug = 12288;  // 8 words per iteration (first 256 iterations): development record written by CTA 0
-constexpr int kHistStage1 = 16384;  // two more level-0 histograms (4096 words each), used alternately by the two-barrier iteration
+constexpr int kHistStage1 = 16384;  // two more level-0 + fine histograms (kStage1Words each), used alternately by the two-barrier iteration
 constexpr int kHistStat = 16000;   // [0] queries that went through the search phase (all CTAs, whole registration)
 
 // ---- one-barrier iteration ("fast path") --------------------------------------------------------------
@@ -84,28 +87,43 @@ constexpr int kHistStat = 16000;   // [0] queries that went through the search p
 //   dist2 <  win_lo : certainly kept    -> error sums accumulated right away (per-CTA partial)
 //   dist2 in window : candidate         -> (p, n, dot | q) tuple + dist2 bits appended to the CTA's segment
 //   dist2 >  win_hi : certainly dropped -> counted only
-// and publishes {counts, partial sums, candidate segment}.  After ONE device-wide barrier every CTA reads
-// the 148 counts, checks that the quantile's rank really falls among the candidates, pulls the candidate
-// list (~1 % of the pairs) into shared memory, finds the exact limit there (same value the 3-level radix
-// select returns), adds the candidates below the limit in a fixed order, reduces the per-CTA partials in a
-// fixed order and solves -- redundantly and bit-identically in every CTA.  If the prediction fails (rank
-// outside the window, or a segment overflows) all CTAs take the general path below for that iteration.
+// and publishes {counts, sums, candidates} (see below).  After ONE device-wide barrier every CTA reads the three counts,
+// checks that the quantile's rank really falls among the candidates, pulls the candidate list (~0.1 % of the pairs) and
+// finds the exact limit there (same value the 3-level radix select returns), adds the candidates at or below the limit,
+// and solves -- redundantly and bit-identically in every CTA.  If the prediction fails (rank outside the window, or the
+// list overflows) all CTAs take the next stage / the general path below for that iteration.
 // Buffers are double-buffered on the iteration's parity: a CTA can only be one barrier ahead of another.
-constexpr int kSegCap = 64;     // candidate tuples per CTA
-constexpr int kCandCap = 2048;  // candidates in total (2 per thread after the barrier)
-constexpr size_t kFastCountsOff = 0;                                                        // uint4 [2][kLoopMaxBlocks]
-constexpr size_t kFastPartialsOff = kFastCountsOff + 2 * kLoopMaxBlocks * sizeof(uint4);    // double [2][kLoopMaxBlocks][kAccSlots]
-constexpr size_t kFastCandOff = kFastPartialsOff + 2 * (size_t)kLoopMaxBlocks * kAccSlots * sizeof(double);  // float4 [2][kLoopMaxBlocks][kSegCap][2]
-constexpr size_t kFastCandEnd = kFastCandOff + 2 * (size_t)kLoopMaxBlocks * kSegCap * 2 * sizeof(float4);
-// Error sums of the pairs whose fate is certain before the barrier: ONE set of 64-bit fixed-point accumulators in global
-// memory, added to with integer atomics (associative: the result does not depend on the arrival order, so poses stay
-// run-to-run bitwise deterministic) instead of 148 per-CTA records that every CTA had to read back and reduce.  One slot
-// per 128-byte line (the atomics and the read-back of different slots go to different L2 slices), three buffers used
-// round-robin (see the zeroing protocol at the barrier).
+constexpr int kCandCap = 2048;   // entries of the candidate list (2 per thread after the barrier)
+constexpr int kSmallCand = 128;  // up to here the candidates are finished by four warps with rank counting (the usual case)
+// Everything a CTA publishes before the barrier is ORDER-FREE: 64-bit integer accumulators in global memory, added to with
+// atomics, and a candidate list appended to with one atomic per warp that holds candidates.
+//  * error sums of the pairs whose fate is certain: fixed point (associative: the result does not depend on the arrival
+//    order, so poses stay run-to-run bitwise deterministic), instead of 148 per-CTA records every CTA had to read back;
+//  * the three counts (pairs below / inside / above the window) in three more slots of the same array;
+//  * candidates (pairs inside the window): tuple (p, dist2 bits | v) at a position handed out by the `inside` counter.  The
+//    list order depends on arrival, so after the barrier the kept candidates are summed in fixed point as well (a coarser
+//    grid: one 32-bit warp reduction per sum).
+// One slot per 128-byte line (the atomics and the read-back of different slots go to different L2 slices), three buffers
+// used round-robin (see the zeroing protocol at the barrier); the candidate list is double-buffered on the round's parity.
 constexpr int kIsumStride = 16;  // unsigned long long per slot line
 constexpr int kIsumBufs = 3;
-constexpr size_t kFastIsumOff = (kFastCandEnd + 127) / 128 * 128;                           // unsigned long long [3][kAccSlots][16]
-constexpr size_t kFastBytes = kFastIsumOff + (size_t)kIsumBufs * kAccSlots * kIsumStride * sizeof(unsigned long long);
+constexpr int kSlotFlag = kAccSlots - 1;  // a sum left the fixed-point range somewhere
+constexpr int kSlotBelow = kAccSlots, kSlotAbove = kAccSlots + 1, kSlotCand = kAccSlots + 2;
+constexpr int kIsumSlots = kAccSlots + 3;
+constexpr size_t kFastCandOff = 0;                                                          // float4 [2][kCandCap][2]
+constexpr size_t kFastCandEnd = kFastCandOff + 2 * (size_t)kCandCap * 2 * sizeof(float4);
+constexpr size_t kFastIsumOff = (kFastCandEnd + 127) / 128 * 128;                           // unsigned long long [3][kIsumSlots][16]
+constexpr size_t kFastBytes = kFastIsumOff + (size_t)kIsumBufs * kIsumSlots * kIsumStride * sizeof(unsigned long long);
+// Two-barrier iteration: next to the level-0 histogram (bits [30:19]) a FINE histogram (64 bins per level-0 bucket, bits
+// [18:13]) over the 65 level-0 buckets around the previous limit (+- 2 octaves): when the quantile's bucket is among them
+// the window is one fine bin -- a few dozen candidates instead of a thousand -- and the four-warp finish applies.
+constexpr int kFineSpan = 32, kFineBuckets = 2 * kFineSpan + 1, kFineShift = 13, kFineSub = 64;
+constexpr int kFineBins = kFineBuckets * kFineSub;  // 4160
+constexpr int kStage1Words = kSel0Bins + kFineBins;
+static_assert((size_t)kFineBins * sizeof(uint32_t) <= kLoopScratchBytes, "the scratch region of the dynamic shared memory holds the fine histogram");
+
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -254,24 +272,29 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     constexpr int NS = SumLayout<MIN>::N;
     __shared__ IcpState st;
     __shared__ uint32_t sh[kSel0Bins];   // radix level 0 histogram, then staging / the candidate list
-    __shared__ uint32_t sh2[1024];       // local radix levels
+    __shared__ __align__(16) uint32_t sh2[1024];  // local radix levels / the candidates' keys
     __shared__ uint32_t s_warp[kLoopWarps + 1], s_warp2[kLoopWarps];
     __shared__ uint32_t s_bin, s_res, s_cnt, s_stage, s_base;
     __shared__ double s_part[kLoopWarps][NS];
     __shared__ double s_red[kLoopWarps][kAccSlots];
     __shared__ double s_sum[kAccSlots];
     __shared__ float s_scratch[16];
-    __shared__ uint32_t s_off[kLoopMaxBlocks + 1];  // fast path: exclusive prefix of the per-CTA candidate counts
-    __shared__ uint32_t s_tot[4];                   // fast path: totals {below, candidates, above, max candidates per CTA}
+    __shared__ unsigned long long s_isum[kIsumSlots];  // fast path: the published accumulators, read back after the barrier
+    __shared__ uint32_t s_tot[4];                   // fast path: this CTA's counts {below, -, above, -}
+    __shared__ uint32_t s_limit_bits;               // fast path: dist2 bits of the quantile
     __shared__ float s_Tprev[16];                   // T_iter the bounds L of the match cache refer to
     __shared__ uint32_t s_nlist;
     __shared__ double s_scale[kAccSlots], s_inv_scale[kAccSlots];  // fixed-point scale of each error sum (see kFastIsumOff)
+    __shared__ float s_cscale[kAccSlots];                           // ... and the coarser grid of the candidates' products
+    __shared__ double s_inv_cscale[kAccSlots];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     float4* const s_r4 = reinterpret_cast<float4*>(dyn_smem);
     float4* const s_pp = s_r4 + kCacheCap;   // (x, y, z, bit-cast position) of the matched map point
     float4* const s_nv = s_pp + kCacheCap;   // (normal of the matched point, bound L)
     float* const s_d2 = reinterpret_cast<float*>(s_nv + kCacheCap);
     uint32_t* const s_list = reinterpret_cast<uint32_t*>(s_d2 + kCacheCap);
+    unsigned char* const s_big = dyn_smem + kLoopCacheBytes;
+    uint32_t* const s_fine = reinterpret_cast<uint32_t*>(s_big);    // two-barrier iteration: fine histogram (kFineBins words)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < (int)(sizeof(IcpState) / 4); i += kLoopThreads)
@@ -306,6 +329,11 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         const int shift = max(-60, min(60, 50 - e2));
         s_scale[tid] = ldexp(1.0, shift);
         s_inv_scale[tid] = ldexp(1.0, -shift);
+        int eb = 0;
+        frexp(fmax((double)bound, 1e-30), &eb);  // bound <= 2^eb: one product lands below 2^20 nominally, 2^23 is the accepted limit
+        const int cshift = max(-100, min(100, 20 - eb));
+        s_cscale[tid] = (float)ldexp(1.0, cshift);
+        s_inv_cscale[tid] = ldexp(1.0, -cshift);
     }
     unsigned epoch = 0;
     uint32_t n_runs = 0, n_hist = 0;  // publish/finish rounds (stage-1 histograms) so far: parity selects the double buffer
@@ -667,7 +695,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         bool fatal = false;
         uint32_t dbg_path = 0, dbg_ncand = 0, dbg_nbelow = 0;  // development record (CTA 0)
         // ---- the rest of the iteration in ONE barrier (stage 0: quantile window predicted from the last limits) or
-        //      TWO (stage 1: window = the level-0 radix bucket that holds the quantile, found with a histogram pass);
+        //      TWO (stage 1: window = the histogram bin that holds the quantile, found with a histogram pass);
         //      both decisions are identical in every CTA
         for (int stage = 0; stage < 2 && !fast_done; ++stage) {
             uint32_t wlo = 0xffffffffu, whi = 0xffffffffu;
@@ -680,21 +708,35 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 } else {
                     // (Median scales the limit by a factor: the uncertain pairs are not the quantile's bucket -> general path)
                     if ((variant_flags & (64 | 8)) || prm.outlier_kind[prm.quantile_filter] != B200ICP_OUTLIER_TRIMMED_DIST) continue;
-                    // level-0 histogram (bits [30:19] of dist2) of this CTA's slice -> global -> barrier -> bucket of the quantile
+                    // level-0 histogram (bits [30:19] of dist2) of this CTA's slice, and the fine one (64 bins per bucket) over the
+                    // buckets around the previous limit -> global -> barrier -> bin of the quantile
+                    const bool fine_ok = st.have_limit && st.limit > 0.f && st.limit < 1.0e30f && !(variant_flags & 0x20000);
+                    const int fb0 = fine_ok ? (int)(__float_as_uint(st.limit) >> kSel0Shift) - kFineSpan : 0;
                     for (int i = tid; i < kSel0Bins; i += kLoopThreads) sh[i] = 0u;
+                    if (fine_ok)
+                        for (int i = tid; i < kFineBins; i += kLoopThreads) s_fine[i] = 0u;
                     __syncthreads();
                     for (int e = tid; e < n_ent; e += kLoopThreads) {
                         const bool cached = e < kCacheCap;
                         const long long pi = pair_of(e);
                         const int pos = __float_as_int(cached ? s_pp[e].w : sp_pp[pi].w);
                         const float d = cached ? s_d2[e] : md2[pi];
-                        if (pos >= 0 && d < CUDART_INF_F) atomicAdd(&sh[__float_as_uint(d) >> kSel0Shift], 1u);
+                        if (pos >= 0 && d < CUDART_INF_F) {
+                            const uint32_t bits = __float_as_uint(d);
+                            const int b0 = (int)(bits >> kSel0Shift);
+                            atomicAdd(&sh[b0], 1u);
+                            if (fine_ok && b0 >= fb0 && b0 < fb0 + kFineBuckets)
+                                atomicAdd(&s_fine[(b0 - fb0) * kFineSub + (int)((bits >> kFineShift) & (kFineSub - 1))], 1u);
+                        }
                     }
                     __syncthreads();
-                    h1 = hist + kHistStage1 + (n_hist & 1u) * kSel0Bins;  // zeroed again by CTA 0 after this stage's second barrier
+                    h1 = hist + kHistStage1 + (n_hist & 1u) * kStage1Words;  // zeroed again by CTA 0 after this stage's second barrier
                     n_hist += 1;
                     for (int i = tid; i < kSel0Bins; i += kLoopThreads)
                         if (sh[i]) atomicAdd(&h1[i], sh[i]);
+                    if (fine_ok)
+                        for (int i = tid; i < kFineBins; i += kLoopThreads)
+                            if (s_fine[i]) atomicAdd(&h1[kSel0Bins + i], s_fine[i]);
                     if (tid == 0) {
                         s_bin = 0;
                         s_res = 0;
@@ -706,13 +748,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     B200_CTA_STAMP(partials, 3);
                     if (stamper) B200_STAMP(gst, 25);
                     const uint32_t total = loop_pick<false>(h1, kSel0Bins, 0u, true, prm.quantile, &s_bin, &s_res, &s_cnt, s_warp);
-                    const uint32_t b1 = s_bin;
+                    const uint32_t b1 = s_bin, r1 = s_res, c1 = s_cnt;
                     __syncthreads();
                     if (total == 0) {
                         // LPM: ConvergenceError("no outlier to filter"); leave the buffers clean and stop everywhere
                         grid_barrier(bar_counter, epoch);
                         if (blockIdx.x == 0)
-                            for (int i = tid; i < kSel0Bins; i += kLoopThreads) h1[i] = 0u;
+                            for (int i = tid; i < kStage1Words; i += kLoopThreads) h1[i] = 0u;
                         if (tid == 0) {
                             st.status = B200ICP_ERR_CONVERGENCE;
                             st.done = 1;
@@ -723,21 +765,32 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     }
                     wlo = b1 << kSel0Shift;
                     whi = wlo | ((1u << kSel0Shift) - 1u);
+                    if (fine_ok && (int)b1 >= fb0 && (int)b1 < fb0 + kFineBuckets && c1 > 32u) {
+                        // refine: the fine bin of that bucket that holds the quantile (rank r1 inside the bucket)
+                        if (tid == 0) {
+                            s_bin = 0;
+                            s_res = 0;
+                            s_cnt = 0;
+                        }
+                        __syncthreads();
+                        loop_pick<false>(h1 + kSel0Bins + ((int)b1 - fb0) * kFineSub, kFineSub, r1, false, 0.f, &s_bin, &s_res, &s_cnt, s_warp);
+                        wlo |= s_bin << kFineShift;
+                        whi = wlo | ((1u << kFineShift) - 1u);
+                        __syncthreads();
+                    }
                 }
             } else if (stage == 1 || (variant_flags & 16)) {
                 continue;
             }
             const int par = (int)(n_runs & 1u);
             unsigned long long* const isum_base = reinterpret_cast<unsigned long long*>(fastws + kFastIsumOff);
-            unsigned long long* const my_isum = isum_base + (size_t)(n_runs % kIsumBufs) * kAccSlots * kIsumStride;
+            unsigned long long* const my_isum = isum_base + (size_t)(n_runs % kIsumBufs) * kIsumSlots * kIsumStride;
             // (used again in two rounds: every CTA finished reading it before it arrived at THIS round's barrier, and the next
             //  additions to it come after the NEXT round's barrier, which CTA 0 only reaches after this zeroing)
-            unsigned long long* const stale_isum = isum_base + (size_t)((n_runs + 2) % kIsumBufs) * kAccSlots * kIsumStride;
+            unsigned long long* const stale_isum = isum_base + (size_t)((n_runs + 2) % kIsumBufs) * kIsumSlots * kIsumStride;
             n_runs += 1;
-            uint4* my_counts = reinterpret_cast<uint4*>(fastws + kFastCountsOff) + (size_t)par * kLoopMaxBlocks;
-            float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kLoopMaxBlocks * kSegCap * 2;
+            float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kCandCap * 2;
             uint32_t c_below = 0, c_above = 0;
-            uint32_t seg_count = 0;  // uniform: candidates of this CTA so far
             if (tid < 4) s_tot[tid] = 0u;
             if (lane < NS) s_part[warp][lane] = 0.0;
             // C: outlier weights + error sums of what is certain + candidate tuples (thread per entry, from the cache)
@@ -784,22 +837,18 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         }
                     }
                 }
-                if (use_quantile) {  // ordered (deterministic) compaction of this block's candidates into the CTA's segment
+                if (use_quantile) {  // the warp's candidates -> the list, at a position the `inside` counter hands out
                     const unsigned bal = __ballot_sync(0xffffffffu, is_cand);
-                    if (lane == 0) s_warp[warp] = __popc(bal);
-                    __syncthreads();
-                    uint32_t before = 0, total = 0;
-                    block_prefix32(s_warp, lane, warp, before, total);
-                    if (is_cand) {
-                        const uint32_t slot = seg_count + before + __popc(bal & ((1u << lane) - 1u));
-                        if (slot < (uint32_t)kSegCap) {
-                            float4* dst = my_cand + ((size_t)blockIdx.x * kSegCap + slot) * 2;
-                            __stcg(dst, ta);
-                            __stcg(dst + 1, tb);
+                    if (bal) {  // (warp-uniform)
+                        unsigned long long base = 0ull;
+                        if (lane == 0) base = atomicAdd(my_isum + kSlotCand * kIsumStride, (unsigned long long)__popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const unsigned long long slot = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+                        if (is_cand && slot < (unsigned long long)kCandCap) {
+                            __stcg(my_cand + slot * 2, ta);
+                            __stcg(my_cand + slot * 2 + 1, tb);
                         }
                     }
-                    seg_count += total;
-                    __syncthreads();
                 }
                 // this block's sums -> the warp's running partial (fp64 from here on)
                 float v32[32];
@@ -830,159 +879,198 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
 #pragma unroll
                 for (int wv = 0; wv < kLoopWarps; ++wv) v += s_part[wv][tid];
                 const double sv = v * s_scale[tid];
-                if (!(fabs(sv) < 4.0e18)) atomicAdd(my_isum + (kAccSlots - 1) * kIsumStride, 1ull);  // out of range (or NaN): flagged for everyone
+                if (!(fabs(sv) < 4.0e18)) atomicAdd(my_isum + kSlotFlag * kIsumStride, 1ull);  // out of range (or NaN): flagged for everyone
                 else if (v != 0.0) atomicAdd(my_isum + tid * kIsumStride, (unsigned long long)__double2ll_rn(sv));
+            } else if (tid == 32) {
+                if (s_tot[0]) atomicAdd(my_isum + kSlotBelow * kIsumStride, (unsigned long long)s_tot[0]);
+            } else if (tid == 33) {
+                if (s_tot[2]) atomicAdd(my_isum + kSlotAbove * kIsumStride, (unsigned long long)s_tot[2]);
             }
-            if (tid == 0) __stcg(my_counts + blockIdx.x, make_uint4(s_tot[0], seg_count, s_tot[2], 0u));
             if (stamper) B200_STAMP(gst, 22);
             B200_CTA_STAMP(partials, 4);
             grid_barrier(bar_counter, epoch);
             B200_CTA_STAMP(partials, 5);
             if (stamper) B200_STAMP(gst, 23);
             // ---- after the barrier: identical work in every CTA ---------------------------------------
-            const int nblk = (int)gridDim.x;
-            if (blockIdx.x == 0 && tid < kAccSlots) stale_isum[tid * kIsumStride] = 0ull;
-            // the certain pairs' sums (one line per slot; consumed after the select, the load is in flight meanwhile)
-            const unsigned long long isum_mine = tid < kAccSlots ? __ldcg(my_isum + tid * kIsumStride) : 0ull;
-            {
-                uint4 c = make_uint4(0u, 0u, 0u, 0u);
-                if (tid < nblk) c = __ldcg(my_counts + tid);
-                uint32_t incl = c.y, sb = c.x, sa = c.z, mx = c.y;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (lane >= off) incl += v;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sb += __shfl_xor_sync(0xffffffffu, sb, o);
-                    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                }
-                if (tid < 4) s_tot[tid] = 0u;
-                if (lane == 31) s_warp[warp] = incl;
-                __syncthreads();
-                uint32_t before = 0;
-                for (int w = 0; w < warp; ++w) before += s_warp[w];
-                if (tid < nblk) s_off[tid] = before + incl - c.y;
-                if (tid == nblk - 1) s_off[nblk] = before + incl;
-                if (lane == 0 && warp * 32 < nblk) {
-                    atomicAdd(&s_tot[0], sb);
-                    atomicAdd(&s_tot[2], sa);
-                    atomicMax(&s_tot[3], mx);
-                }
-                __syncthreads();
+            if (blockIdx.x == 0 && tid < kIsumSlots) stale_isum[tid * kIsumStride] = 0ull;
+            // one round trip: the accumulators and, speculatively, the head of the candidate list
+            const unsigned long long isum_mine = tid < kIsumSlots ? __ldcg(my_isum + tid * kIsumStride) : 0ull;
+            float4 ca[2], cb[2];
+            ca[0] = ca[1] = cb[0] = cb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (use_quantile && tid < kSmallCand) {
+                ca[0] = __ldcg(my_cand + (size_t)tid * 2);
+                cb[0] = __ldcg(my_cand + (size_t)tid * 2 + 1);
             }
+            if (tid < kIsumSlots) s_isum[tid] = isum_mine;
+            __syncthreads();
             if (stamper) B200_STAMP(gst, 29);
-            const uint32_t n_below = s_tot[0], n_cand = s_off[nblk], n_above = s_tot[2], seg_max = s_tot[3];
+            const uint32_t n_below = (uint32_t)s_isum[kSlotBelow], n_above = (uint32_t)s_isum[kSlotAbove];
+            const uint32_t n_cand = (uint32_t)umin64(s_isum[kSlotCand], 0x7fffffffull);
             const uint32_t total = n_below + n_cand + n_above;
             uint32_t rank = 0;
             bool ok = true;
             if (use_quantile) {
                 rank = (prm.quantile == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * prm.quantile);
                 if (total && rank >= total) rank = total - 1u;
-                ok = total > 0 && seg_max <= (uint32_t)kSegCap && n_cand <= (uint32_t)kCandCap && rank >= n_below && rank < n_below + n_cand;
+                ok = total > 0 && n_cand <= (uint32_t)kCandCap && rank >= n_below && rank < n_below + n_cand;
             }
             dbg_path = dbg_path * 10u + (ok ? (stage == 0 ? 1u : 3u) : (stage == 0 ? 2u : 4u));
             dbg_ncand = n_cand;
             dbg_nbelow = n_below;
-            if (ok) {
-                float acc2[NS];
-#pragma unroll
-                for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
+            // The candidates at or below the limit are summed in FIXED POINT as well (their list order depends on arrival; integer
+            // sums do not): each product is rounded to the grid 2^-cshift of its slot -- 2^-20 of the slot's a-priori magnitude
+            // bound, a deterministic perturbation of ~0.1 % of the pairs far below the fp32 rounding of the other sums -- so that a
+            // warp total is ONE 32-bit REDUX per slot; totals across warps are added as 64-bit integers.
+            if (ok && n_cand <= (uint32_t)kSmallCand) {
+                // ---- the usual case: <= 128 candidates, one per thread of warps 0..3 ----
+                // rank counting: every candidate needs the number of keys below it (`less`) and at or below it (`le`); all 32
+                // warps share that work (candidate = tid % 128, an eighth of the keys each)
+                const bool have = use_quantile && (uint32_t)tid < n_cand;  // (tid < 128 only)
+                const uint32_t mine = __float_as_uint(ca[0].w);
+                if (tid < kSmallCand) {
+                    sh2[tid] = have ? mine : 0xffffffffu;  // (padding: neither below nor equal to any distance)
+                    sh2[kSmallCand + tid] = 0u;            // less | le << 16
+                }
+                __syncthreads();
+                if (stamper) B200_STAMP(gst, 1);
                 if (use_quantile) {
-                    // candidates -> registers (<= 2 tuples per thread; .w of the first half = dist2 bits)
-                    float4 ca[2], cb[2];
-                    bool have[2];
+                    const int c = tid & (kSmallCand - 1), part = tid >> 7;  // 8 parts of 16 keys
+                    const uint32_t key = sh2[c];
+                    if ((uint32_t)c < n_cand && (uint32_t)(part * 16) < n_cand) {
+                        const uint4* keys = reinterpret_cast<const uint4*>(sh2) + part * 4;
+                        uint32_t less = 0, le = 0;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t pos = (uint32_t)tid + (uint32_t)j * kLoopThreads;
-                        have[j] = pos < n_cand;
-                        ca[j] = cb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (have[j]) {
-                            int lo = 0, hi = nblk;  // segment with s_off[seg] <= pos < s_off[seg + 1]
-                            while (hi - lo > 1) {
-                                const int mid = (lo + hi) >> 1;
-                                if (s_off[mid] <= pos) lo = mid; else hi = mid;
-                            }
-                            const float4* src = my_cand + ((size_t)lo * kSegCap + (pos - s_off[lo])) * 2;
-                            ca[j] = __ldcg(src);
-                            cb[j] = __ldcg(src + 1);
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const uint4 o = keys[i4];
+                            less += (o.x < key) + (o.y < key) + (o.z < key) + (o.w < key);
+                            le += (o.x <= key) + (o.y <= key) + (o.z <= key) + (o.w <= key);
                         }
+                        if (less | le) atomicAdd(&sh2[kSmallCand + c], less | (le << 16));
                     }
-                    const uint32_t W = whi - wlo;  // < 2^30 (window construction)
-                    uint32_t r = rank - n_below, prefix = 0;
-                    const bool small_set = n_cand <= 128u;
-                    if (small_set) {
-                        // few candidates: every candidate counts how many precede it (ties: list order); the one whose
-                        // count equals the rank is the quantile.  Two block syncs instead of five per radix level.
-                        if (have[0]) sh2[tid] = __float_as_uint(ca[0].w);
-                        __syncthreads();
-                        if (have[0]) {
-                            const uint32_t mine = __float_as_uint(ca[0].w);
-                            uint32_t less = 0;
-                            for (uint32_t i = 0; i < n_cand; ++i) {
-                                const uint32_t o = sh2[i];
-                                less += (o < mine) || (o == mine && i < (uint32_t)tid);
-                            }
-                            if (less == r) s_bin = mine - wlo;
+                }
+                __syncthreads();
+                if (stamper) B200_STAMP(gst, 2);
+                if (tid < kSmallCand) {
+                    long long mine_tot = 0ll;
+                    if ((uint32_t)(warp * 32) < n_cand && use_quantile) {  // (warp-uniform)
+                        const uint32_t r = rank - n_below;
+                        const uint32_t packed = sh2[kSmallCand + tid];
+                        const uint32_t less = packed & 0xffffu, le = packed >> 16;
+                        // kept: fewer than r + 1 keys are strictly smaller; the quantile is the key with less <= r < le
+                        if (have && less <= r && r < le) s_limit_bits = mine;  // (every such candidate holds the same bits)
+                        const bool kept = have && less <= r && ca[0].x == ca[0].x;
+                        float acc2[NS];
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
+                        if (kept) add_pair<MIN>(acc2, 1.f, make_float3(ca[0].x, ca[0].y, ca[0].z), cb[0]);
+                        bool range_ok = true;
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) {
+                            const float sv = acc2[i] * s_cscale[i];
+                            range_ok = range_ok && (fabsf(sv) < 8388608.f);
+                            const int tot = __reduce_add_sync(0xffffffffu, __float2int_rn(sv));
+                            if (lane == i) mine_tot = (long long)tot;
                         }
-                        __syncthreads();
-                        prefix = s_bin;
-                        __syncthreads();
+                        const bool any_bad = __any_sync(0xffffffffu, !range_ok);
+                        if (lane == kSlotFlag) mine_tot = any_bad ? 1ll : 0ll;
                     }
+                    reinterpret_cast<long long*>(&s_red[0][0])[warp * kAccSlots + lane] = mine_tot;
+                    if (stamper) B200_STAMP(gst, 3);
+                    named_bar_sync(1, kSmallCand);
+                    if (stamper) B200_STAMP(gst, 4);
+                    if (tid < kAccSlots) {
+                        // certain pairs + the candidates at or below the limit: integer totals, order-free
+                        long long cv = 0ll;
+#pragma unroll
+                        for (int part = 0; part < kSmallCand / 32; ++part) cv += reinterpret_cast<const long long*>(&s_red[0][0])[part * kAccSlots + tid];
+                        const long long iv = (long long)s_isum[tid];
+                        s_sum[tid] = (tid == kSlotFlag) ? (double)(iv + cv) : (double)iv * s_inv_scale[tid] + (double)cv * s_inv_cscale[tid];
+                    }
+                    if (stamper) B200_STAMP(gst, 6);
+                }
+                __syncthreads();
+            } else if (ok) {
+                // ---- many candidates (a wide predicted window, or a two-barrier iteration whose bucket could not be refined):
+                //      all warps; <= 2 candidates per thread, local radix select over the window ----
+                bool have[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t pos = (uint32_t)tid + (uint32_t)j * kLoopThreads;
+                    have[j] = pos < n_cand;
+                    if (have[j] && pos >= (uint32_t)kSmallCand) {
+                        ca[j] = __ldcg(my_cand + (size_t)pos * 2);
+                        cb[j] = __ldcg(my_cand + (size_t)pos * 2 + 1);
+                    }
+                }
+                const uint32_t W = whi - wlo;  // < 2^30 (window construction)
+                uint32_t r = rank - n_below, prefix = 0;
 #pragma unroll 1
-                    for (int shift = small_set ? -1 : 20; shift >= 0; shift -= 10) {
-                        if (shift > 0 && (W >> shift) == 0u) continue;
-                        sh2[tid] = 0u;
-                        if (tid == 0) {
-                            s_bin = 0;
-                            s_res = 0;
-                        }
-                        __syncthreads();
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            if (have[j]) {
-                                const uint32_t o = __float_as_uint(ca[j].w) - wlo;
-                                if (((o ^ prefix) >> (shift + 10)) == 0u) atomicAdd(&sh2[(o >> shift) & 1023u], 1u);
-                            }
-                        }
-                        __syncthreads();
-                        loop_pick<true>(sh2, 1024, r, false, 0.f, &s_bin, &s_res, &s_cnt, s_warp);
-                        r = s_res;
-                        prefix |= s_bin << shift;
-                        __syncthreads();
+                for (int shift = 20; shift >= 0; shift -= 10) {
+                    if (shift > 0 && (W >> shift) == 0u) continue;
+                    sh2[tid] = 0u;
+                    if (tid == 0) {
+                        s_bin = 0;
+                        s_res = 0;
                     }
-                    const uint32_t limit_bits = wlo + prefix;
-                    qlimit = __uint_as_float(limit_bits);
+                    __syncthreads();
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        if (have[j] && __float_as_uint(ca[j].w) <= limit_bits && ca[j].x == ca[j].x)
-                            add_pair<MIN>(acc2, 1.f, make_float3(ca[j].x, ca[j].y, ca[j].z), cb[j]);
+                        if (have[j]) {
+                            const uint32_t o = __float_as_uint(ca[j].w) - wlo;
+                            if (((o ^ prefix) >> (shift + 10)) == 0u) atomicAdd(&sh2[(o >> shift) & 1023u], 1u);
+                        }
                     }
+                    __syncthreads();
+                    loop_pick<true>(sh2, 1024, r, false, 0.f, &s_bin, &s_res, &s_cnt, s_warp);
+                    r = s_res;
+                    prefix |= s_bin << shift;
+                    __syncthreads();
                 }
-                if (stamper) B200_STAMP(gst, 27);
-                // fixed-order reduction: candidates' warp totals + the per-CTA partials, identical in every CTA
-                {
-                    float v32[32];
+                const uint32_t limit_bits = wlo + prefix;
+                if (tid == 0) s_limit_bits = limit_bits;
+                long long mine_tot = 0ll;
+                if ((uint32_t)(warp * 32) < n_cand) {  // (warp-uniform)
+                    int f[NS];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v32[i] = (i < NS) ? acc2[i] : 0.f;
-                    // (only the warps that hold candidates have anything to add: warp-uniform skip of the 31-shuffle reduction)
-                    const float tot = (use_quantile && (uint32_t)(warp * 32) < n_cand) ? warp_reduce_32slots(v32, lane) : 0.f;
-                    s_red[warp][lane] = (double)tot;
+                    for (int i = 0; i < NS; ++i) f[i] = 0;
+                    bool range_ok = true;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (have[j] && __float_as_uint(ca[j].w) <= limit_bits && ca[j].x == ca[j].x) {
+                            float acc2[NS];
+#pragma unroll
+                            for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
+                            add_pair<MIN>(acc2, 1.f, make_float3(ca[j].x, ca[j].y, ca[j].z), cb[j]);
+#pragma unroll
+                            for (int i = 0; i < NS; ++i) {
+                                const float sv = acc2[i] * s_cscale[i];
+                                range_ok = range_ok && (fabsf(sv) < 8388608.f);
+                                f[i] += __float2int_rn(sv);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) {
+                        const int tot = __reduce_add_sync(0xffffffffu, f[i]);
+                        if (lane == i) mine_tot = (long long)tot;
+                    }
+                    const bool any_bad = __any_sync(0xffffffffu, !range_ok);
+                    if (lane == kSlotFlag) mine_tot = any_bad ? 1ll : 0ll;
                 }
+                reinterpret_cast<long long*>(&s_red[0][0])[warp * kAccSlots + lane] = mine_tot;
                 __syncthreads();
                 if (tid < kAccSlots) {
-                    // certain pairs (exact integer total, order-free) + the candidates at or below the limit (fixed order)
-                    double v = (double)(long long)isum_mine * s_inv_scale[tid];
-                    if (use_quantile) {
-                        const int nparts = min(kLoopWarps, (int)((n_cand + 31u) >> 5));
-                        for (int part = 0; part < nparts; ++part) v += s_red[part][tid];
-                    }
-                    s_sum[tid] = v;
+                    long long cv = 0ll;
+                    for (int wv = 0; wv < kLoopWarps; ++wv) cv += reinterpret_cast<const long long*>(&s_red[0][0])[wv * kAccSlots + tid];
+                    const long long iv = (long long)s_isum[tid];
+                    s_sum[tid] = (tid == kSlotFlag) ? (double)(iv + cv) : (double)iv * s_inv_scale[tid] + (double)cv * s_inv_cscale[tid];
                 }
                 __syncthreads();
-                if (s_sum[kAccSlots - 1] != 0.0) {  // a sum left the fixed-point range somewhere: same verdict in every CTA
+            }
+            if (ok) {
+                if (use_quantile) qlimit = __uint_as_float(s_limit_bits);
+                if (stamper) B200_STAMP(gst, 27);
+                if (s_sum[kSlotFlag] != 0.0) {  // a sum left the fixed-point range somewhere: same verdict in every CTA
                     if (tid == 0) {
                         st.status = B200ICP_ERR_NOT_IMPLEMENTED;
                         st.done = 1;
@@ -998,8 +1086,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     else st.hist_iters += 1;
                 }
             }
-            if (h1 && blockIdx.x == 0)  // the level-0 histogram was read by every CTA before the barrier above
-                for (int i = tid; i < kSel0Bins; i += kLoopThreads) h1[i] = 0u;
+            if (h1 && blockIdx.x == 0)  // the stage-1 histograms were read by every CTA before the barrier above
+                for (int i = tid; i < kStage1Words; i += kLoopThreads) h1[i] = 0u;
         }
         if (fatal) break;
         if (!fast_done) {
@@ -1207,7 +1295,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             }
             finish_warp(prm, &st, s_sum, NS, blockIdx.x == 0 ? trace : nullptr, s_scratch, stamper ? gst : nullptr);
         }
-        if (stamper && it < 256) {  // {path 0 general / 1 one-barrier / 2 failed attempt, limit, candidates, below, searched so far, next window}
+        if (stamper && it < 256 && (variant_flags & 0x80000)) {  // development record (nn_variant bit 19; its L2 round trip is on CTA 0's critical path): {path 0 general / 1 one-barrier / 2 failed attempt, limit, candidates, below, searched so far, next window}
             uint32_t* rec = hist + kHistDebug + it * 8;
             rec[0] = dbg_path;
             rec[1] = __float_as_uint(qlimit);

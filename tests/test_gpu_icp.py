@@ -156,8 +156,12 @@ def test_quantile_fallback_path_is_identical(pair3d):
             g.set_map(pair3d["map"], pair3d["normals"])
             outs.append((g(pair3d["reading"]), g.last_result.pairs_last_iter))
             g.close()
-    assert np.array_equal(outs[0][0], outs[2][0]) and outs[0][1] == outs[2][1]
-    assert np.array_equal(outs[1][0], outs[3][0]) and outs[1][1] == outs[3][1]
+    # same limit, hence exactly the same kept pairs; the two paths slice the error sums differently (the windowed iteration adds
+    # its ~0.1 % of candidate pairs on a fixed-point grid), so the poses agree to rounding
+    for a, b in ((0, 2), (1, 3)):
+        assert outs[a][1] == outs[b][1]
+        er, et = synth.pose_error(outs[a][0], outs[b][0])
+        assert er <= 1e-6 and et <= 1e-5, (a, b, er, et)
 
 
 @pytest.mark.parametrize("chain", [

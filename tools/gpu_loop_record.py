@@ -7,7 +7,7 @@ import numpy as np
 from norlab_icp_mapper_b200 import synth
 from norlab_icp_mapper_b200.icp import ICP, make_config
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
-variant = int(args[0]) if args else 0
+variant = (int(args[0]) if args else 0) | 0x80000  # bit 19: write the per-iteration record
 if "--cfg1" in sys.argv:
     d = synth.make_pair_3d(n_map=41_400, n_scan=41_339, world_size=(120.0, 120.0), n_boxes=14, scan_radius=60.0, dt=(0.10, -0.05, 0.02), drpy_deg=(0, 0, 1.0))
     cfg = make_config(dim=3, knn=6, max_dist=2.0, outliers=(), minimizer="point_to_plane", max_iteration_count=10, nn_variant=variant)
