@@ -139,6 +139,8 @@ typedef struct b200icp_config {
                              bits 10..11 loop kernel: value - 1 = log2 of that chunk size (1, 2, 4 points)
                              bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3)
                              bit 17 (0x20000) loop kernel: no fine histogram in the two-barrier iteration (window = the whole level-0 bucket)
+                             bit 20 (0x100000) self k-NN (SurfaceNormal filters): TMA-staged candidate tiles (csrc/selfknn.cu) instead of the shell walk
+                             bit 21 (0x200000) SurfaceNormal's neighbour search: no speculative one-cell bound
                              bit 19 (0x80000) loop kernel: write the per-iteration development record (tools/gpu_loop_record.py) */
     int32_t outlier_mode[B200ICP_MAX_OUTLIER_FILTERS]; /* per filter: B200ICP_ROBUST_MODE(...) for RobustOutlierFilter, else 0 */
     int32_t checker_order; /* position of the Counter in the transformationCheckers list.  libpointmatcher runs the checkers in YAML

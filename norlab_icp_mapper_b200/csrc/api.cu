@@ -52,6 +52,14 @@ struct b200icp_ctx {
         int extra_rows = 0;
         int n_rot = 0, rot_row[4] = {0, 0, 0, 0};  // descriptors in `extra` that rotate with the cloud (observationDirections)
     } scan;
+    // self k-NN with staged tiles (selfknn.cu): the queries it could not prove exact, redone by the shell walk
+    uint32_t* d_fb_list = nullptr;
+    unsigned* d_fb_count = nullptr;
+    float4* d_fb_q = nullptr;
+    int32_t* d_fb_ids = nullptr;
+    float* d_fb_d2 = nullptr;
+    int64_t cap_fb = 0, cap_fb_rows = 0;
+    int64_t last_selfknn_redone = -1;  // (introspection: -1 = the staged kernel was not used)
     float* d_kth = nullptr;      // incremental SurfaceNormal: squared k-th neighbour distance per store point
     int64_t cap_kth = 0;
     uint8_t* d_dirty = nullptr;  // ... dirty flags (store order, then index order)
@@ -455,6 +463,11 @@ void b200icp_destroy(b200icp_ctx* ctx) {
         B200_CUDA_FREE(ctx->scan.prob[i]);
         B200_CUDA_FREE(ctx->scan.extra[i]);
     }
+    B200_CUDA_FREE(ctx->d_fb_list);
+    B200_CUDA_FREE(ctx->d_fb_count);
+    B200_CUDA_FREE(ctx->d_fb_q);
+    B200_CUDA_FREE(ctx->d_fb_ids);
+    B200_CUDA_FREE(ctx->d_fb_d2);
     B200_CUDA_FREE(ctx->d_kth);
     B200_CUDA_FREE(ctx->d_dirty);
     B200_CUDA_FREE(ctx->d_list);
@@ -1369,6 +1382,86 @@ int32_t b200icp_scan_add_prob(b200icp_ctx* ctx, float constant) {
     return B200ICP_OK;
 }
 
+// k-NN of SurfaceNormal's neighbour search: `n` queries that are points of the indexed cloud itself (all of them, cell-sorted: the
+// full pass; or a gathered subset: the incremental pass); row i of d_out_ids / d_out_d2 (sized by ensure_query_buffers(n, knn)
+// beforehand) = query i.  The shell walk of knn.cu with a speculative bound of one cell edge (cells are sized for ~4 per point, so
+// the k nearest of a surface point lie well inside it): far fewer insertions into the sorted lists; the few queries that find
+// fewer than k neighbours there are rerun without the bound.  nn_variant bit 20 (0x100000), full pass only: TMA-staged tiles
+// (selfknn.cu) instead -- measured 2.3x SLOWER on a 2 M-point surface map (profiles/r2_tma_ab.md), kept as the tracked A/B of
+// north_star's "TMA-staged point tiles".  nn_variant bit 21 (0x200000): no speculative bound.
+static int32_t self_knn(b200icp_ctx* ctx, const GridView& view, const float4* d_queries, int64_t n, int knn, bool queries_are_all_points) {
+    cudaStream_t s = ctx->stream;
+    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
+    unsigned* h_cnt = reinterpret_cast<unsigned*>(ctx->h_pinned + 2 * kStateBytes + 64);
+    ctx->last_selfknn_redone = -1;
+    const bool staged = queries_are_all_points && knn <= 16 && (ctx->cfg.nn_variant & 0x100000) && n >= 4096;
+    const bool spec = !staged && knn > 1 && !(ctx->cfg.nn_variant & 0x200000) && n >= 4096;
+    bool redo_all = !staged && !spec;
+    if (staged || spec) {
+        const int64_t cap = std::max<int64_t>(n / 4, 4096);
+        if (cap > ctx->cap_fb) {
+            B200_CUDA_FREE(ctx->d_fb_list);
+            B200_CUDA_FREE(ctx->d_fb_q);
+            ctx->d_fb_list = nullptr;
+            ctx->d_fb_q = nullptr;
+            ctx->cap_fb = 0;
+            const int64_t c2 = grow_capacity(cap);
+            CK(B200_CUDA_MALLOC((void**)&ctx->d_fb_list, (size_t)c2 * sizeof(uint32_t)));
+            CK(B200_CUDA_MALLOC((void**)&ctx->d_fb_q, (size_t)c2 * sizeof(float4)));
+            ctx->cap_fb = c2;
+        }
+        if (!ctx->d_fb_count) CK(B200_CUDA_MALLOC((void**)&ctx->d_fb_count, 64));
+        if (staged) {
+            CK(launch_selfknn_tiles(view, knn, ctx->d_out_ids, ctx->d_out_d2, ctx->d_fb_list, ctx->d_fb_count, (unsigned)ctx->cap_fb, s));
+        } else {
+            *h_nq = (int)n;
+            CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+            CK(cudaMemsetAsync(ctx->d_fb_count, 0, sizeof(unsigned), s));
+            KnnSpec ks;
+            float cells = 1.0f;  // B200ICP_SPEC_BOUND: the bound in cell edges (development sweep)
+            if (const char* env = getenv("B200ICP_SPEC_BOUND")) cells = (float)atof(env);
+            ks.bound2 = cells * view.h * cells * view.h;
+            ks.list = ctx->d_fb_list;
+            ks.count = ctx->d_fb_count;
+            ks.capacity = (unsigned)ctx->cap_fb;
+            CK(launch_knn(view, d_queries, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2, /*want_original_ids=*/0,
+                          ctx->cfg.nn_variant & 0xffff, s, ks));
+        }
+        CK(cudaMemcpyAsync(h_cnt, ctx->d_fb_count, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const int64_t redo = *h_cnt;
+        if (redo > ctx->cap_fb) {
+            redo_all = true;  // (a very sparse cloud for its grid: the unbounded shell walk does everything)
+        } else if (redo > 0) {
+            if (redo * knn > ctx->cap_fb_rows) {
+                B200_CUDA_FREE(ctx->d_fb_ids);
+                B200_CUDA_FREE(ctx->d_fb_d2);
+                ctx->d_fb_ids = nullptr;
+                ctx->d_fb_d2 = nullptr;
+                ctx->cap_fb_rows = 0;
+                const int64_t c2 = grow_capacity(redo * knn);
+                CK(B200_CUDA_MALLOC((void**)&ctx->d_fb_ids, (size_t)c2 * sizeof(int32_t)));
+                CK(B200_CUDA_MALLOC((void**)&ctx->d_fb_d2, (size_t)c2 * sizeof(float)));
+                ctx->cap_fb_rows = c2;
+            }
+            // (the list holds query indices: positions for the staged tiles, rows of d_queries for the shell walk -- the same thing
+            //  in the full pass)
+            CK(launch_gather_reading(d_queries, ctx->d_fb_list, ctx->d_fb_q, redo, s));
+            CK(launch_knn(view, ctx->d_fb_q, reinterpret_cast<const int*>(ctx->d_fb_count), (int)redo, nullptr, knn, INFINITY, ctx->d_fb_ids, ctx->d_fb_d2,
+                          /*want_original_ids=*/0, ctx->cfg.nn_variant & 0xffff, s));
+            CK(launch_selfknn_scatter(ctx->d_fb_list, ctx->d_fb_count, (unsigned)redo, knn, ctx->d_fb_ids, ctx->d_fb_d2, ctx->d_out_ids, ctx->d_out_d2, s));
+        }
+        if (!redo_all) ctx->last_selfknn_redone = redo;
+    }
+    if (redo_all) {
+        *h_nq = (int)n;
+        CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
+        CK(launch_knn(view, d_queries, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2, /*want_original_ids=*/0,
+                      ctx->cfg.nn_variant & 0xffff, s));
+    }
+    return B200ICP_OK;
+}
+
 // SurfaceNormalDataPointsFilter{knn} on a device cloud: grid over the cloud, self k-NN, covariance, smallest eigenvector -> d_nrm (cloud order)
 static int32_t cloud_normals_dev(b200icp_ctx* ctx, const float* d_in, int rows, int64_t n, int knn, float* d_nrm) {
     const int dim = ctx->cfg.dim;
@@ -1376,11 +1469,8 @@ static int32_t cloud_normals_dev(b200icp_ctx* ctx, const float* d_in, int rows, 
     CK(grid_build(ctx->aux, d_in, rows, dim, nullptr, n, /*centre=*/false, 0.f, s));
     const int32_t eb = ensure_query_buffers(ctx, n, knn);
     if (eb != B200ICP_OK) return eb;
-    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
-    *h_nq = (int)n;
-    CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-    CK(launch_knn(ctx->aux.view, ctx->aux.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
-                  /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+    const int32_t sk = self_knn(ctx, ctx->aux.view, ctx->aux.pts, n, knn, true);
+    if (sk != B200ICP_OK) return sk;
     // d_q4 (n float4, sized by ensure_query_buffers) receives the cell-sorted copy nobody needs; d_nrm the cloud-order normals
     CK(launch_normals(ctx->aux.view, dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->d_q4, d_nrm, nullptr, s));
     return B200ICP_OK;
@@ -1502,7 +1592,6 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         ctx->d_kth = nk;
         ctx->cap_kth = cap;
     }
-    int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
 
     // ---- incremental pass: only appends since the last pass -> recompute the new points and the old points that have a new
     //      point within their k-th neighbour distance; every other point keeps the neighbours, hence the normal, it had ----
@@ -1579,21 +1668,17 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
             const int32_t eb = ensure_query_buffers(ctx, m, knn);
             if (eb != B200ICP_OK) return eb;
             CK(launch_normals_gather(ctx->map.view, ctx->d_list, d_count, m, ctx->d_q4, s));
-            *h_nq = (int)m;
-            CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-            CK(launch_knn(ctx->map.view, ctx->d_q4, ctx->d_scalar_nq, (int)m, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
-                          /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+            const int32_t sk = self_knn(ctx, ctx->map.view, ctx->d_q4, m, knn, false);
+            if (sk != B200ICP_OK) return sk;
             CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, ctx->d_list, d_count, m, ctx->map.normals, st.nrm,
                               ctx->d_kth, s));
         }
     } else {
         const int32_t eb = ensure_query_buffers(ctx, n, knn);
         if (eb != B200ICP_OK) return eb;
-        *h_nq = (int)n;
-        CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-        // self k-NN: the queries are the cell-sorted map points themselves (neighbouring threads share cells)
-        CK(launch_knn(ctx->map.view, ctx->map.pts, ctx->d_scalar_nq, (int)n, nullptr, knn, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
-                      /*want_original_ids=*/0, ctx->cfg.nn_variant, s));
+        // self k-NN: the queries are the cell-sorted map points themselves (every point of a tile shares its candidates)
+        const int32_t sk = self_knn(ctx, ctx->map.view, ctx->map.pts, n, knn, true);
+        if (sk != B200ICP_OK) return sk;
         CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->map.normals, st.nrm, ctx->d_kth, s));
     }
     CK(store_clear_touched(st, s));
@@ -1632,6 +1717,8 @@ int32_t b200icp_cloud_surface_normals(b200icp_ctx* ctx, const float* features, i
 
 /* development aid / tests (not in the public header): points whose normal the last b200icp_map_surface_normals recomputed */
 int64_t b200icp_debug_normals_recomputed(const b200icp_ctx* ctx) { return ctx ? ctx->last_normals_recomputed : -1; }
+/* ... and how many queries of the last staged self k-NN were redone by the shell walk (-1: the staged kernel was not used) */
+int64_t b200icp_debug_selfknn_redone(const b200icp_ctx* ctx) { return ctx ? ctx->last_selfknn_redone : -1; }
 
 int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed) {
     if (!ctx || !slab6) return B200ICP_ERR_INVALID_ARG;

@@ -278,9 +278,27 @@ cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, con
 // ---- knn.cu --------------------------------------------------------------------------------
 // queries: float4 (x, y, z, *) in the grid's frame, optionally moved by state->T first.
 // out_ids: cell-sorted positions (want_original_ids = 0) or original indices (1); -1 = none.
+// spec (k > 1 only): search inside sqrt(bound2) first; queries with fewer than k neighbours there are appended to `list`
+// (*count of them, at most `capacity` stored) for the caller to rerun without the bound.  Their rows hold what was found.
+struct KnnSpec {
+    float bound2 = 0.f;
+    uint32_t* list = nullptr;
+    unsigned* count = nullptr;
+    unsigned capacity = 0;
+};
 cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_nq, int nq_capacity,
                        const IcpState* d_state_or_null, int k, float max_r2, int32_t* out_ids,
-                       float* out_d2, int want_original_ids, int variant, cudaStream_t s);
+                       float* out_d2, int want_original_ids, int variant, cudaStream_t s, KnnSpec spec = KnnSpec());
+
+// ---- selfknn.cu ----------------------------------------------------------------------------
+// Self k-NN of the cell-sorted cloud (queries = g.pts, row i of the output = position i), k <= 16, with TMA-staged candidate
+// tiles.  Queries whose k-th distance leaves their tile's halo are listed in fb_list (*fb_count of them, possibly more than
+// fb_capacity: then the list is truncated and the caller redoes everything with launch_knn); their rows are redone with
+// launch_knn and put back with launch_selfknn_scatter.
+cudaError_t launch_selfknn_tiles(const GridView& g, int k, int32_t* out_ids, float* out_d2, uint32_t* fb_list, unsigned* fb_count,
+                                 unsigned fb_capacity, cudaStream_t s);
+cudaError_t launch_selfknn_scatter(const uint32_t* list, const unsigned* n_list, unsigned capacity, int k, const int32_t* ids, const float* d2,
+                                   int32_t* out_ids, float* out_d2, cudaStream_t s);
 
 // Warm k = 1 search for ICP iterations >= 1: match_pos holds the previous matches on entry.
 cudaError_t launch_nn1_warm(const GridView& g, const float4* d_reading, int nq_capacity, const IcpState* st,

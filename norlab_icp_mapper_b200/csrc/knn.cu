@@ -26,7 +26,7 @@ template <int G, typename Acc>
 __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __restrict__ queries, const int* __restrict__ d_nq,
                                                   const IcpState* __restrict__ state, int k, float max_r2,
                                                   int32_t* __restrict__ out_ids, float* __restrict__ out_d2,
-                                                  int want_original_ids, int variant, int warm) {
+                                                  int want_original_ids, int variant, int warm, KnnSpec spec) {
     if (state && state->done) return;
     const int nq = *d_nq;
     const int lane = threadIdx.x & 31;
@@ -59,11 +59,21 @@ __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __re
         for (int o = G / 2; o > 0; o >>= 1) dj = fmaxf(dj, __shfl_xor_sync(gmask, dj, o));
         if (dj < CUDART_INF_F) bound = __uint_as_float(__float_as_uint(dj) + 1u);  // next float up: ties with the bound stay accepted
     }
+    // speculative bound (k > 1, cold): the k nearest are expected within sqrt(spec.bound2); only closer candidates enter the list
+    // and the walk stops there.  k points found inside it ARE the k nearest; a query that finds fewer is listed for an unbounded rerun.
+    if (Acc::kPerLaneOutput && spec.list) bound = fminf(bound, spec.bound2);
     acc.init(k, bound);
     search_shells<G, Acc>(g, acc, qx, qy, qz, max_r2, variant, lig, gmask);
     float od;
     int op;
     acc.finish(gmask, lig, k, max_r2, od, op);
+    if (Acc::kPerLaneOutput && spec.list) {
+        const int op_k = __shfl_sync(gmask, op, k - 1, G);
+        if (op_k < 0 && lig == 0) {
+            const unsigned slot = atomicAdd(spec.count, 1u);
+            if (slot < spec.capacity) spec.list[slot] = (uint32_t)qi;
+        }
+    }
     const int n_out = (Acc::kPerLaneOutput) ? k : 1;
     if (lig < n_out) {
         int id = op;
@@ -188,11 +198,11 @@ cudaError_t launch_warm_one(const GridView& g, const float4* reading, int cap, c
 
 template <int G, typename Acc>
 cudaError_t launch_one(const GridView& g, const float4* q, const int* d_nq, int cap, const IcpState* st, int k, float max_r2,
-                       int32_t* ids, float* d2, int want_orig, int variant, cudaStream_t s, int warm = 0) {
+                       int32_t* ids, float* d2, int want_orig, int variant, cudaStream_t s, int warm = 0, KnnSpec spec = KnnSpec()) {
     const int per_block = 256 / G;
     const int blocks = (cap + per_block - 1) / per_block;
     if (blocks <= 0) return cudaSuccess;
-    knn_kernel<G, Acc><<<blocks, 256, 0, s>>>(g, q, d_nq, st, k, max_r2, ids, d2, want_orig, variant, warm);
+    knn_kernel<G, Acc><<<blocks, 256, 0, s>>>(g, q, d_nq, st, k, max_r2, ids, d2, want_orig, variant, warm, spec);
     return cudaGetLastError();
 }
 
@@ -200,7 +210,7 @@ cudaError_t launch_one(const GridView& g, const float4* q, const int* d_nq, int 
 
 cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_nq, int nq_capacity,
                        const IcpState* st, int k, float max_r2, int32_t* out_ids, float* out_d2, int want_original_ids,
-                       int variant, cudaStream_t s) {
+                       int variant, cudaStream_t s, KnnSpec spec) {
     if (k < 1 || k > 32) return cudaErrorInvalidValue;
     if (k == 1 && max_r2 < 3.0e38f && !(variant & 256) && sqrtf(max_r2) * g.inv_h <= 4.0f) {  // (bit 8: the shell-walk kernel instead)
         const int blocks = (nq_capacity + 63) / 64;
@@ -214,9 +224,9 @@ cudaError_t launch_knn(const GridView& g, const float4* d_queries, const int* d_
     // is left to cut when the whole batch does not even fill the SMs (10 k queries x 8 lanes = a quarter of the B200)
     int lanes = k <= 8 ? 8 : (k <= 16 ? 16 : 32);
     while (lanes < 32 && (long long)nq_capacity * lanes * 2 <= (long long)kSMs * 2048) lanes *= 2;
-    if (lanes == 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
-    if (lanes == 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
-    return launch_one<32, AccK<32>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm);
+    if (lanes == 8) return launch_one<8, AccK<8>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm, spec);
+    if (lanes == 16) return launch_one<16, AccK<16>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm, spec);
+    return launch_one<32, AccK<32>>(g, d_queries, d_nq, nq_capacity, st, k, max_r2, out_ids, out_d2, want_original_ids, variant, s, warm, spec);
 }
 
 cudaError_t launch_nn1_warm(const GridView& g, const float4* d_reading, int nq_capacity, const IcpState* st, float max_r2,

@@ -180,6 +180,12 @@ class ICP:
     def map_surface_normals(self, knn):
         self._check(self._L.b200icp_map_surface_normals(self._h, knn))
 
+    def debug_selfknn_redone(self):
+        """Queries of the last staged self k-NN (selfknn.cu) that the shell walk had to redo; -1 = staged kernel not used."""
+        self._L.b200icp_debug_selfknn_redone.argtypes = [C.c_void_p]
+        self._L.b200icp_debug_selfknn_redone.restype = C.c_int64
+        return self._L.b200icp_debug_selfknn_redone(self._h)
+
     def cloud_surface_normals(self, features, knn):
         """SurfaceNormalDataPointsFilter{knn} on a host cloud (N x (dim + 1)); returns N x dim normals."""
         pts = _cloud(features, self.n)

@@ -213,3 +213,39 @@ def test_cloud_surface_normals_for_the_input_chain(gpu, oracle, pair):
     cosang = np.abs(np.einsum("ij,ij->i", nrm, onrm))
     assert np.median(cosang) > 0.999999 and (cosang > 0.9999).mean() > 0.99, (np.median(cosang), (cosang > 0.9999).mean())
     assert gpu.map_counts() == before
+
+
+@pytest.mark.parametrize("case", ["surface3d", "dense2d", "sparse3d"])
+def test_staged_self_knn_equals_the_shell_walk(case):
+    """SurfaceNormal's neighbour search with TMA-staged candidate tiles (selfknn.cu, nn_variant bit 20) against the per-query shell
+    walk (the default): same neighbours in the same order, hence bit-identical normals and k-th distances -- on a surface map, on a dense
+    2-D map (regions larger than a stage, tiles with more points than threads) and on a sparse cloud where most queries
+    leave their halo and are redone by the shell walk."""
+    from norlab_icp_mapper_b200.icp import ICP
+    rng = np.random.default_rng(12)
+    if case == "surface3d":
+        d = synth.make_pair_3d(n_map=200_000, n_scan=1000)
+        pts, dim, knn = d["map"], 3, 10
+    elif case == "dense2d":
+        d = synth.make_pair_2d(n_map=120_000, n_scan=1000)
+        pts, dim, knn = d["map"], 2, 8
+    else:
+        pts = synth.homog(rng.uniform(-30, 30, (20_000, 3)))
+        dim, knn = 3, 12
+    outs = {}
+    for variant in (0, 0x100000, 0x200000):  # default (speculative one-cell bound + rerun list), staged tiles, plain shell walk
+        g = ICP(make_config(dim=dim, knn=1, max_dist=1.0, outliers=(), minimizer="point_to_point", max_iteration_count=5, nn_variant=variant))
+        g.set_map(pts, None)
+        g.map_surface_normals(knn)
+        _, nrm = g.map_download()
+        outs[variant] = (nrm, g.debug_selfknn_redone())
+        # the same search behind the `input:` chain's SurfaceNormal filter
+        outs[(variant, "cloud")] = g.cloud_surface_normals(pts[:50_000], knn)
+        g.close()
+    assert outs[0x200000][1] == -1 and outs[0x100000][1] >= 0 and outs[0][1] >= -1
+    assert np.array_equal(outs[0][0], outs[0x200000][0]) and np.array_equal(outs[(0, "cloud")], outs[(0x200000, "cloud")])
+    if case != "sparse3d":  # (sparse: most queries leave their halo and are redone, or the truncated list falls back wholesale)
+        assert outs[0x100000][1] < 0.25 * len(pts), outs[0x100000][1]
+    assert np.isfinite(outs[0][0]).all()
+    assert np.array_equal(outs[0][0], outs[0x100000][0])
+    assert np.array_equal(outs[(0, "cloud")], outs[(0x100000, "cloud")])
