@@ -5,7 +5,10 @@
 // examples/config.yaml, spelled out on the MapperConfig struct; `--icp point_to_plane` swaps the example's Identity error
 // minimiser (the shipped config does no registration at all) for the chain of docs/MapperConfiguration.md:172-189.
 //
-//   build_map_from_scans_and_trajectory <dataPath> [--icp identity|point_to_plane] [--io-only] [--binary] [--host-module]
+//   build_map_from_scans_and_trajectory <dataPath> [config.yaml] [--icp identity|point_to_plane] [--io-only] [--binary] [--host-module]
+//
+// With a YAML file as second argument -- the reference's own command line -- the configuration is read from it
+// (host/YamlConfig.h; /root/reference/examples/config.yaml loads unmodified); without one the same configuration is built in code.
 //
 // --host-module swaps the device OctreeMapperModule for a module written against the REFERENCE's plugin signature
 // (MapperModules/MapperModule.h:20-29: host DataPoints in, host DataPoints out), run through HostMapperModuleAdapter: a
@@ -24,6 +27,7 @@
 
 #include "../norlab_icp_mapper_b200/host/IO.h"
 #include "../norlab_icp_mapper_b200/host/Mapper.h"
+#include "../norlab_icp_mapper_b200/host/YamlConfig.h"
 
 namespace fs = std::filesystem;
 using namespace norlab_icp_mapper_b200;
@@ -92,7 +96,12 @@ int main(int argc, char* argv[]) {
     }
     const fs::path dataPath = argv[1];
     bool ioOnly = false, binary = false, pointToPlane = false, hostModule = false;
+    std::string configYaml;
     for (int i = 2; i < argc; ++i) {
+        if (argv[i][0] != '-') {
+            configYaml = argv[i];
+            continue;
+        }
         if (!std::strcmp(argv[i], "--io-only")) ioOnly = true;
         else if (!std::strcmp(argv[i], "--binary")) binary = true;
         else if (!std::strcmp(argv[i], "--host-module")) hostModule = true;
@@ -148,6 +157,10 @@ int main(int argc, char* argv[]) {
                                            {"epsilonA", "0.01"}, {"epsilonD", "0.01"}}},
             {"OctreeMapperModule", {{"buildParallel", "1"}, {"maxSizeByNode", "0.15"}, {"samplingMethod", "1"}}}};
 
+        if (!configYaml.empty()) {
+            cfg = loadYamlConfig(configYaml, /*is3D=*/true);
+            if (pointToPlane) cfg.icp.minimizer = B200ICP_MIN_POINT_TO_PLANE;
+        }
         if (hostModule) {
             cfg.mapperModules.pop_back();
             cfg.extraModules.push_back(std::make_shared<HostMapperModuleAdapter>(std::make_shared<VoxelFirstHostModule>(0.15f)));

@@ -54,6 +54,13 @@ typedef struct b200mapper_stats {
 
 /* Mapper::Mapper(config, is3D, isOnline, isMapping, saveMapCellsOnHardDrive) -- Mapper.cpp:15-33 */
 int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapper** out);
+/* The reference's constructor signature: Mapper(configFilePath, is3D, isOnline, isMapping, saveMapCellsOnHardDrive) with the YAML
+ * file of Mapper::loadYamlConfig (Mapper.cpp:59-185; /root/reference/examples/config.yaml loads unmodified).  Unknown filter / module
+ * / parameter names fail with B200ICP_ERR_INVALID_ARG and the message libpointmatcher's registrar would give. */
+int32_t b200mapper_create_from_yaml(const char* config_file_path, int32_t is_3d, int32_t is_online, int32_t is_mapping,
+                                    int32_t save_map_cells_on_hard_drive, int32_t device, int32_t reserve_points, b200mapper** out);
+/* What host/YamlConfig.h reads from a configuration file, as `key=value` lines (tests; needs no GPU). */
+int32_t b200mapper_yaml_summary(const char* config_file_path, int32_t is_3d, char* out, int32_t capacity);
 void b200mapper_destroy(b200mapper* m);
 const char* b200mapper_last_error(const b200mapper* m);
 /* Mapper::applyInputFilters -- Mapper.cpp:187-191; in place, returns the new point count in *n */

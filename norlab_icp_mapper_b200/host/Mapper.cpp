@@ -1,6 +1,8 @@
 // Mapper.cpp -- see Mapper.h.  Reference: /root/reference/norlab_icp_mapper/Mapper.cpp.
 #include "Mapper.h"
 
+#include "YamlConfig.h"
+
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -52,6 +54,9 @@ Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMa
         for (const auto& m : config.extraModules) map.addMapperModule(m);
     }
 }
+
+Mapper::Mapper(const std::string& configFilePath, bool is3D_, bool isOnline_, bool isMapping_, bool saveMapCellsOnHardDrive, int device)
+    : Mapper(loadYamlConfig(configFilePath, is3D_), is3D_, isOnline_, isMapping_, saveMapCellsOnHardDrive, device) {}
 
 // Mapper.cpp:187-191: radiusFilter = DistanceLimitDataPointsFilter{dim -1, dist sensorMaxRange,
 // removeInside 0} (built at Mapper.cpp:27-31), then the YAML `input:` chain -- one predicate kernel +

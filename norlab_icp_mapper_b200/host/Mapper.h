@@ -1,7 +1,7 @@
 // Mapper.h -- host mirror of norlab_icp_mapper::Mapper (reference Mapper.{h,cpp}): same public
 // methods, same processInput / shouldUpdateMap / updateMap sequence, the heavy steps delegated to
-// libb200icp.so.  YAML parsing is out of scope: the configuration arrives as the
-// struct the reference's loadYamlConfig would produce.
+// libb200icp.so.  The configuration arrives as the struct the reference's loadYamlConfig would produce, or as the path of
+// the YAML file itself (host/YamlConfig.h reads the subset of YAML the reference's configuration files use).
 #pragma once
 #include <atomic>
 #include <memory>
@@ -57,6 +57,8 @@ class Mapper {
 
    public:
     Mapper(const MapperConfig& config, bool is3D, bool isOnline, bool isMapping, bool saveMapCellsOnHardDrive, int device = 0);
+    // the reference's signature (Mapper.cpp:15-33): configFilePath is the YAML file of Mapper::loadYamlConfig, read by host/YamlConfig.h
+    Mapper(const std::string& configFilePath, bool is3D, bool isOnline, bool isMapping, bool saveMapCellsOnHardDrive, int device = 0);
     void applyInputFilters(DataPoints& inputInSensorFrame);
     // true: applyInputFilters leaves the filtered scan in the device slot (`onDevice` cloud) and processInput continues on it --
     // one host-to-device copy per scan.  false (default, the reference's contract): the caller gets the filtered cloud back.

@@ -2,7 +2,10 @@
 #include <cstring>
 #include <string>
 
+#include <sstream>
+
 #include "Mapper.h"
+#include "YamlConfig.h"
 #include "b200mapper.h"
 
 using namespace norlab_icp_mapper_b200;
@@ -104,6 +107,60 @@ int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapp
     }
     *out = m;
     return B200ICP_OK;
+}
+
+int32_t b200mapper_create_from_yaml(const char* config_file_path, int32_t is_3d, int32_t is_online, int32_t is_mapping,
+                                    int32_t save_map_cells_on_hard_drive, int32_t device, int32_t reserve_points, b200mapper** out) {
+    if (!config_file_path || !out) return B200ICP_ERR_INVALID_ARG;
+    *out = nullptr;
+    b200mapper* m = new b200mapper();
+    const int32_t rc = guarded(nullptr, [&] {
+        m->dim = is_3d ? 3 : 2;
+        m->mapper.reset(new Mapper(std::string(config_file_path), is_3d != 0, is_online != 0, is_mapping != 0, save_map_cells_on_hard_drive != 0, device));
+        if (reserve_points > 0)
+            ICPSequence::check(m->mapper->getICP().context(), b200icp_map_reserve(m->mapper->getICP().context(), reserve_points, 10));
+    });
+    if (rc != B200ICP_OK) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return B200ICP_OK;
+}
+
+int32_t b200mapper_yaml_summary(const char* config_file_path, int32_t is_3d, char* out, int32_t capacity) {
+    if (!config_file_path || !out || capacity < 1) return B200ICP_ERR_INVALID_ARG;
+    out[0] = 0;
+    return guarded(nullptr, [&] {
+        const MapperConfig c = loadYamlConfig(std::string(config_file_path), is_3d != 0);
+        std::ostringstream o;
+        o << "icp.knn=" << c.icp.knn << "\nicp.maxDist=" << c.icp.max_dist << "\nicp.epsilon=" << c.icp.epsilon << "\nicp.minimizer=" << c.icp.minimizer
+          << "\nicp.minimizerFlags=" << c.icp.minimizer_flags << "\nicp.nOutlier=" << c.icp.n_outlier;
+        for (int i = 0; i < c.icp.n_outlier; ++i)
+            o << "\nicp.outlier" << i << "=" << c.icp.outlier_kind[i] << "," << c.icp.outlier_param[i] << "," << c.icp.outlier_param2[i] << ","
+              << c.icp.outlier_param3[i] << "," << c.icp.outlier_mode[i];
+        o << "\nicp.counter=" << c.icp.max_iteration_count << "\nicp.differential=" << c.icp.use_differential << "," << c.icp.min_diff_rot_err << ","
+          << c.icp.min_diff_trans_err << "," << c.icp.smooth_length << "\nicp.bound=" << c.icp.use_bound << "," << c.icp.max_rotation_norm << ","
+          << c.icp.max_translation_norm << "\nicp.checkerOrder=" << c.icp.checker_order;
+        o << "\ninput.n=" << c.inputFilters.size();
+        for (size_t i = 0; i < c.inputFilters.size(); ++i) {
+            const b200icp_filter& f = c.inputFilters[i];
+            o << "\ninput" << i << "=" << f.kind << "," << f.lo[0] << "," << f.hi[0] << "," << f.lo[1] << "," << f.hi[1] << "," << f.lo[2] << "," << f.hi[2] << ","
+              << f.dim << "," << f.dist << "," << f.remove_inside;
+        }
+        o << "\ninput.addProbabilityDynamic=" << (c.addProbabilityDynamic ? 1 : 0) << "," << c.probabilityDynamicValue
+          << "\ninput.surfaceNormalKnn=" << c.inputSurfaceNormalKnn << "\npost.surfaceNormalKnn=" << c.post.surfaceNormalKnn
+          << "\npost.cut=" << (c.post.cutAtThreshold ? 1 : 0) << "," << (c.post.cutUseLargerThan ? 1 : 0) << "," << c.post.cutThreshold
+          << "\nmapper.updateCondition=" << c.mapUpdateCondition << "," << c.mapUpdateValue << "\nmapper.sensorMaxRange=" << c.sensorMaxRange
+          << "\nmapper.nModules=" << c.mapperModules.size();
+        for (size_t i = 0; i < c.mapperModules.size(); ++i) {
+            o << "\nmodule" << i << "=" << c.mapperModules[i].first;
+            for (const auto& kv : c.mapperModules[i].second) o << ";" << kv.first << "=" << kv.second;
+        }
+        const std::string t = o.str();
+        if ((int)t.size() + 1 > capacity) throw InvalidParameter("summary buffer too small");
+        std::memcpy(out, t.c_str(), t.size() + 1);
+    });
 }
 
 void b200mapper_destroy(b200mapper* m) { delete m; }

@@ -17,7 +17,7 @@ SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "
            "b200mapper_process_input", "b200mapper_get_pose", "b200mapper_get_map", "b200mapper_get_new_local_map",
            "b200mapper_set_map", "b200mapper_get_is_mapping", "b200mapper_set_is_mapping", "b200mapper_trajectory_size",
            "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates", "b200mapper_process_raw_input",
-           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob"]
+           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob", "b200mapper_create_from_yaml", "b200mapper_yaml_summary"]
 
 
 class InputFilter(C.Structure):
@@ -79,6 +79,7 @@ def load():
     L = C.CDLL(SO_PATH)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.b200mapper_create.argtypes = [C.POINTER(MapperConfig), i32, C.POINTER(vp)]
+    L.b200mapper_create_from_yaml.argtypes = [C.c_char_p, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]
     L.b200mapper_destroy.argtypes = [vp]
     L.b200mapper_destroy.restype = None
     L.b200mapper_last_error.argtypes = [vp]
@@ -103,6 +104,17 @@ def load():
     return L
 
 
+def yaml_summary(path, is3D=True):
+    """What the C++ reader (host/YamlConfig.h) makes of a Mapper configuration file: dict of key -> value strings.  No GPU needed."""
+    L = load()
+    L.b200mapper_yaml_summary.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+    buf = C.create_string_buffer(16384)
+    rc = L.b200mapper_yaml_summary(os.fspath(path).encode(), int(is3D), buf, len(buf))
+    if rc != _abi.OK:
+        raise B200ICPError(rc, L.b200mapper_last_error(None).decode())
+    return dict(line.split("=", 1) for line in buf.value.decode().split("\n") if line)
+
+
 class Mapper:
     CONDITIONS = {"distance": 0, "delay": 1, "overlap": 2}
 
@@ -113,6 +125,19 @@ class Mapper:
         """dynamicPoints: _abi.DynamicParams or None; octree: (maxSizeByNode, samplingMethod) or None (then PointDistance);
         cutAtThreshold: threshold or None; inputFilters: InputFilter list; addProbabilityDynamic: value or None."""
         self._L = load()
+        self.dim = 3 if is3D else 2
+        self.n = self.dim + 1
+        if isinstance(icp_config, (str, bytes, os.PathLike)):
+            # the reference's signature: Mapper(configFilePath, is3D, isOnline, isMapping, saveMapCellsOnHardDrive) with the YAML
+            # file of Mapper::loadYamlConfig (python/src/mapper.cpp:23); the keyword arguments below do not apply
+            h = C.c_void_p()
+            rc = self._L.b200mapper_create_from_yaml(os.fspath(icp_config).encode() if not isinstance(icp_config, bytes) else icp_config,
+                                                     int(is3D), int(isOnline), int(isMapping), int(saveMapCellsOnHardDrive), device,
+                                                     int(reservePoints), C.byref(h))
+            if rc != _abi.OK:
+                raise B200ICPError(rc, self._L.b200mapper_last_error(None).decode())
+            self._h = h
+            return
         cfg = MapperConfig()
         cfg.icp = icp_config
         cfg.update_condition = self.CONDITIONS.get(updateCondition[0], 99)
