@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200ICP_ABI_VERSION 5
+#define B200ICP_ABI_VERSION 6
 
 typedef enum b200icp_status {
     B200ICP_OK = 0,
@@ -348,6 +348,22 @@ int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_
 /* icp.setMap(localPointCloud): rebuild the index over the loaded points.  An empty local cloud is
  * ignored like LPM does (the previous index stays). */
 int32_t b200icp_map_commit(b200icp_ctx* ctx);
+
+/* ---- online mapping (Mapper isOnline: Mapper.cpp:225-228,248-255,280-283; Map.cpp:29-57,482-494) ----
+ * The reference hands Map::updateLocalPointCloud to a std::async worker and keeps registering scans against the OLD map until
+ * the worker's final icp.setMap(localPointCloud) (Map.cpp:527-529).  Here: every entry point of a context is atomic with
+ * respect to the others (any host thread may call; a registration waits for at most one update STEP, never for the update),
+ * and between begin_update and end_update the update steps (module inserts, b200icp_map_commit, the post filters) build a second
+ * index from the store while b200icp_register* / b200icp_match keep using the live one; end_update publishes it.
+ *   b200icp_scan_snapshot   caller thread, before dispatching the worker: the scan in the slot becomes the worker's input
+ *                           (the reference copies `currentInput` into the async call); the caller's slot is empty afterwards
+ *   b200icp_map_begin_update   worker thread: from here on this thread's b200icp_scan_* calls see the snapshot
+ *   b200icp_map_end_update     worker thread, under the caller's icpMapLock: swap the indexes
+ * Without begin_update nothing changes: b200icp_map_commit rebuilds the live index in place. */
+int32_t b200icp_scan_snapshot(b200icp_ctx* ctx);
+int32_t b200icp_map_begin_update(b200icp_ctx* ctx);
+int32_t b200icp_map_end_update(b200icp_ctx* ctx);
+int32_t b200icp_map_update_in_progress(const b200icp_ctx* ctx);
 
 /* Point counts: local (Map::localPointCloud) and global (local + parked cells, Map.cpp:538-562). */
 int32_t b200icp_map_counts(const b200icp_ctx* ctx, int64_t* n_local, int64_t* n_global);

@@ -73,6 +73,11 @@ int32_t b200mapper_process_input(b200mapper* m, const float* features_sensor_fra
  * (optional) receives the point count after the `input:` chain. */
 int32_t b200mapper_process_raw_input(b200mapper* m, const float* features_sensor_frame, int32_t feature_rows, int64_t n,
                                      const float* estimated_pose, double time_stamp_seconds, int64_t* n_filtered);
+/* isOnline (Mapper.cpp:280-283): processInput hands the map update to a worker and returns; these two expose the future the
+ * reference keeps in `mapUpdateFuture`: is an update still running / block until it (and the queued cell-window updates) are done,
+ * reporting the update's error if it failed. */
+int32_t b200mapper_map_update_in_flight(b200mapper* m);
+int32_t b200mapper_wait_for_map_update(b200mapper* m);
 int32_t b200mapper_get_pose(b200mapper* m, float* pose);                       /* Mapper::getPose        */
 int32_t b200mapper_get_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n); /* getMap */
 int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n,

@@ -2,7 +2,7 @@
 product binding (icp.py) and by the tests' oracle binding so both speak the same config."""
 import ctypes as C
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_OUTLIER_FILTERS = 4
 
 # b200icp_status

@@ -21,7 +21,13 @@ struct b200icp_ctx {
     IcpParams prm{};
     int device = 0;
     cudaStream_t stream = nullptr;
-    GridIndex map;
+    GridIndex map;   // the LIVE index: what icp(input) / match search (icp.setMap's last argument)
+    // Online mapping (Mapper isOnline, Mapper.cpp:280-283): between b200icp_map_begin_update and b200icp_map_end_update the update
+    // steps build and refine a second index (`work`) from the store while registrations keep using `map`; end_update swaps them --
+    // the reference's icp.setMap(localPointCloud) at the end of Map::updateLocalPointCloud (Map.cpp:527-529).
+    GridIndex work;
+    bool updating = false, work_valid = false;
+    mutable std::recursive_mutex api_mutex;  // entry points are atomic with respect to each other (caller thread, update thread, window thread)
     bool has_map = false;
     int64_t map_n = 0;
     MapStore store;  // the device-resident map the index is built from
@@ -51,7 +57,7 @@ struct b200icp_ctx {
         bool has_nrm = false, has_prob = false;
         int extra_rows = 0;
         int n_rot = 0, rot_row[4] = {0, 0, 0, 0};  // descriptors in `extra` that rotate with the cloud (observationDirections)
-    } scan;
+    } scan, scan_upd;  // scan_upd: the snapshot an asynchronous map update works on (b200icp_scan_snapshot) while the next scan arrives
     // self k-NN with staged tiles (selfknn.cu): the queries it could not prove exact, redone by the shell walk
     uint32_t* d_fb_list = nullptr;
     unsigned* d_fb_count = nullptr;
@@ -83,6 +89,16 @@ namespace {
 
 std::string g_create_error;
 std::mutex g_create_mutex;
+
+// the context whose snapshot slot (scan_upd) this thread's b200icp_scan_* calls work on: set by b200icp_map_begin_update, cleared by
+// b200icp_map_end_update -- "the thread that runs the asynchronous update sees the scan it was handed"
+thread_local const b200icp_ctx* t_update_ctx = nullptr;
+b200icp_ctx::ScanSlot& scan_slot(b200icp_ctx* ctx) { return t_update_ctx == ctx ? ctx->scan_upd : ctx->scan; }
+const b200icp_ctx::ScanSlot& scan_slot(const b200icp_ctx* ctx) { return t_update_ctx == ctx ? ctx->scan_upd : ctx->scan; }
+// where commit builds (and whose sort scratch the update-side steps borrow) / the index that is in step with the store
+GridIndex& build_index(b200icp_ctx* ctx) { return ctx->updating ? ctx->work : ctx->map; }
+GridIndex& synced_index(b200icp_ctx* ctx) { return (ctx->updating && ctx->work_valid) ? ctx->work : ctx->map; }
+#define B200_LOCK(ctx) std::lock_guard<std::recursive_mutex> api_guard_((ctx)->api_mutex)
 
 int32_t fail(b200icp_ctx* ctx, int32_t code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -277,7 +293,8 @@ int bits_for(uint64_t v) {
 int32_t commit_index(b200icp_ctx* ctx) {
     MapStore& st = ctx->store;
     cudaStream_t s = ctx->stream;
-    if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, ctx->map, s));
+    GridIndex& idx = build_index(ctx);
+    if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, idx, s));
     ctx->index_stale = false;
     if (st.n_active == 0) return B200ICP_OK;  // LPM: "Ignoring attempt to create a map from an empty cloud"
     float cell_hint = 0.f;
@@ -286,16 +303,20 @@ int32_t commit_index(b200icp_ctx* ctx) {
     // (normals of the points that already had some are carried along even when the cloud formally lost the descriptor to a
     //  concatenate: the incremental SurfaceNormal pass reuses them; has_normals below keeps the formal truth)
     const bool carry_normals = st.has_normals || (st.nrm_epoch_ok && st.nrm != nullptr);
-    CK(grid_build(ctx->map, reinterpret_cast<const float*>(st.feat), 4, ctx->cfg.dim, carry_normals ? st.nrm : nullptr, st.n_active,
+    CK(grid_build(idx, reinterpret_cast<const float*>(st.feat), 4, ctx->cfg.dim, carry_normals ? st.nrm : nullptr, st.n_active,
                   /*centre=*/true, cell_hint, s, st.all_loaded ? nullptr : st.active));
-    ctx->map.has_normals = st.has_normals;
+    idx.has_normals = st.has_normals;
     CK(cudaEventRecord(ctx->ev_map1, s));
     CK(cudaStreamSynchronize(s));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_map0, ctx->ev_map1);
     ctx->timing.setmap_ms = ms;
-    ctx->has_map = true;
-    ctx->map_n = st.n_active;
+    if (ctx->updating) {
+        ctx->work_valid = true;  // (published by b200icp_map_end_update)
+    } else {
+        ctx->has_map = true;
+        ctx->map_n = st.n_active;
+    }
     return B200ICP_OK;
 }
 
@@ -439,6 +460,7 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     grid_free(ctx->map);
+    grid_free(ctx->work);
     grid_free(ctx->aux);
     store_free(ctx->store);
     B200_CUDA_FREE(ctx->d_keep);
@@ -458,10 +480,12 @@ void b200icp_destroy(b200icp_ctx* ctx) {
     B200_CUDA_FREE(b.trace);
     var_trimmed_free(ctx->var_scratch);
     for (int i = 0; i < 2; ++i) {
-        B200_CUDA_FREE(ctx->scan.feat[i]);
-        B200_CUDA_FREE(ctx->scan.nrm[i]);
-        B200_CUDA_FREE(ctx->scan.prob[i]);
-        B200_CUDA_FREE(ctx->scan.extra[i]);
+        for (b200icp_ctx::ScanSlot* sl : {&ctx->scan, &ctx->scan_upd}) {
+            B200_CUDA_FREE(sl->feat[i]);
+            B200_CUDA_FREE(sl->nrm[i]);
+            B200_CUDA_FREE(sl->prob[i]);
+            B200_CUDA_FREE(sl->extra[i]);
+        }
     }
     B200_CUDA_FREE(ctx->d_fb_list);
     B200_CUDA_FREE(ctx->d_fb_count);
@@ -497,12 +521,14 @@ void* b200icp_stream(b200icp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullp
 
 int32_t b200icp_set_profiling(b200icp_ctx* ctx, int32_t on) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     ctx->profiling = on != 0;
     return B200ICP_OK;
 }
 
 int32_t b200icp_set_sm_share(b200icp_ctx* ctx, int32_t n_sms) {
     if (!ctx || n_sms < 0) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     ctx->sm_share = n_sms;
     return B200ICP_OK;
 }
@@ -515,6 +541,7 @@ int32_t b200icp_get_timing(const b200icp_ctx* ctx, b200icp_timing* out) {
 
 int32_t b200icp_set_trace(b200icp_ctx* ctx, int32_t on) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     ctx->want_trace = on != 0;
     return B200ICP_OK;
 }
@@ -540,6 +567,7 @@ int32_t b200icp_debug_stamps(const b200icp_ctx* ctx, unsigned long long* out32) 
  * window, queries searched so far (all CTAs), next window lo, hi, iteration time in ns on CTA 0} */
 int32_t b200icp_debug_loop_record(b200icp_ctx* ctx, uint32_t* out, int32_t iterations) {
     if (!ctx || !out || iterations < 0 || iterations > 256 || !ctx->buf.hist) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(out, ctx->buf.hist + 12288, (size_t)iterations * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -550,6 +578,7 @@ int32_t b200icp_debug_loop_record(b200icp_ctx* ctx, uint32_t* out, int32_t itera
  * the loop kernel's last iteration */
 int32_t b200icp_debug_cta_stamps(b200icp_ctx* ctx, unsigned long long* out, int32_t n_ctas) {
     if (!ctx || !out || n_ctas < 0 || n_ctas > kMaxAccBlocks || !ctx->buf.partials) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(out, ctx->buf.partials, (size_t)n_ctas * kAccSlots * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -578,6 +607,7 @@ int32_t b200icp_get_grid_info(const b200icp_ctx* ctx, float* cell_edge, int32_t*
 int32_t b200icp_set_map_device(b200icp_ctx* ctx, const float* d_features, int32_t feature_rows, const float* d_normals,
                                int64_t n) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (feature_rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
     if (n < 0 || n > (int64_t)INT32_MAX - 1024) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad point count");
     if (n == 0) return B200ICP_OK;  // LPM: "Ignoring attempt to create a map from an empty cloud"
@@ -594,6 +624,7 @@ int32_t b200icp_set_map_device(b200icp_ctx* ctx, const float* d_features, int32_
 
 int32_t b200icp_set_map(b200icp_ctx* ctx, const float* features, int32_t feature_rows, const float* normals, int64_t n) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (feature_rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
     if (n < 0 || n > (int64_t)INT32_MAX - 1024) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad point count");
     if (n == 0) return B200ICP_OK;
@@ -846,6 +877,7 @@ int32_t b200icp_register_device(b200icp_ctx* ctx, const float* d_reading, int32_
     if (result) memset(result, 0, sizeof(*result));
     const int32_t rc = register_checks(ctx, d_reading, feature_rows, nq, T_out);
     if (rc != B200ICP_OK) return rc;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     const int32_t eb = ensure_icp_buffers(ctx, nq);
     if (eb != B200ICP_OK) return eb;
@@ -858,6 +890,7 @@ int32_t b200icp_register_normals(b200icp_ctx* ctx, const float* reading, int32_t
     if (result) memset(result, 0, sizeof(*result));
     const int32_t rc = register_checks(ctx, reading, feature_rows, nq, T_out);
     if (rc != B200ICP_OK) return rc;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     const int32_t eb = ensure_icp_buffers(ctx, nq);
     if (eb != B200ICP_OK) return eb;
@@ -876,6 +909,7 @@ int32_t b200icp_register_descriptors(b200icp_ctx* ctx, const float* reading, int
     if (result) memset(result, 0, sizeof(*result));
     const int32_t rc = register_checks(ctx, reading, feature_rows, nq, T_out);
     if (rc != B200ICP_OK) return rc;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     const int32_t eb = ensure_icp_buffers(ctx, nq);
     if (eb != B200ICP_OK) return eb;
@@ -903,6 +937,7 @@ int32_t b200icp_register(b200icp_ctx* ctx, const float* reading, int32_t feature
     if (result) memset(result, 0, sizeof(*result));
     const int32_t rc = register_checks(ctx, reading, feature_rows, nq, T_out);
     if (rc != B200ICP_OK) return rc;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     const int32_t eb = ensure_icp_buffers(ctx, nq);
     if (eb != B200ICP_OK) return eb;
@@ -988,6 +1023,7 @@ static int32_t run_queries(b200icp_ctx* ctx, GridIndex& g, const float* queries,
 
 int32_t b200icp_match(b200icp_ctx* ctx, const float* queries, int32_t feature_rows, int64_t nq, int32_t* ids, float* dists2) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (feature_rows != ctx->cfg.dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
     if (nq < 0 || (nq > 0 && (!queries || !ids || !dists2))) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad arguments");
     if (!ctx->has_map) return fail(ctx, B200ICP_ERR_NO_MAP, "no map: call b200icp_set_map first");
@@ -999,6 +1035,7 @@ int32_t b200icp_match(b200icp_ctx* ctx, const float* queries, int32_t feature_ro
 int32_t b200icp_knn(b200icp_ctx* ctx, const float* ref, int32_t ref_rows, int64_t nref, const float* queries, int32_t query_rows,
                     int64_t nq, int32_t dim, int32_t k, float max_radius, int32_t* ids, float* dists2) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if ((dim != 2 && dim != 3) || ref_rows < dim || query_rows < dim) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad dim / rows");
     if (k < 1 || k > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "k must be in [1, 32]");
     if (nref <= 0 || nref > (int64_t)INT32_MAX - 1024 || !ref) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad reference cloud");
@@ -1016,6 +1053,7 @@ int32_t b200icp_knn(b200icp_ctx* ctx, const float* ref, int32_t ref_rows, int64_
 
 int32_t b200icp_transform(b200icp_ctx* ctx, float* features, int32_t feature_rows, float* normals, int64_t n, const float* T) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = feature_rows - 1;
     if ((dim != 2 && dim != 3) || !T || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad arguments");
     float M[16];
@@ -1042,6 +1080,7 @@ int32_t b200icp_transform(b200icp_ctx* ctx, float* features, int32_t feature_row
 int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t feature_rows, float* d_normals, int64_t n,
                                  const float* T) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = feature_rows - 1;
     if ((dim != 2 && dim != 3) || !T || n < 0 || (n > 0 && !d_features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad arguments");
     float M[16];
@@ -1058,6 +1097,7 @@ int32_t b200icp_transform_device(b200icp_ctx* ctx, float* d_features, int32_t fe
 
 int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_knn) {
     if (!ctx || n_points < 0 || n_points > (int64_t)INT32_MAX / 2) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     const int dim = ctx->cfg.dim;
     CK(store_reserve(ctx->store, dim, n_points, ctx->stream));
@@ -1114,8 +1154,63 @@ int32_t b200icp_map_reserve(b200icp_ctx* ctx, int64_t n_points, int32_t normals_
 
 int32_t b200icp_map_commit(b200icp_ctx* ctx) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     return commit_index(ctx);
+}
+
+/* Online mapping: see the comment on b200icp_ctx::work. */
+int32_t b200icp_map_begin_update(b200icp_ctx* ctx) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
+    if (ctx->updating) return fail(ctx, B200ICP_ERR_INVALID_ARG, "a map update is already in progress on this context");
+    ctx->updating = true;
+    ctx->work_valid = false;
+    t_update_ctx = ctx;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_end_update(b200icp_ctx* ctx) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
+    if (!ctx->updating) return fail(ctx, B200ICP_ERR_INVALID_ARG, "no map update in progress");
+    if (t_update_ctx == ctx) t_update_ctx = nullptr;
+    if (ctx->index_stale && ctx->store.n_active > 0) {  // (the steps left the index behind the store: the published map is the final one)
+        const int32_t rc = commit_index(ctx);
+        if (rc != B200ICP_OK) {
+            ctx->updating = false;
+            ctx->work_valid = false;
+            return rc;
+        }
+    }
+    if (ctx->work_valid) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::swap(ctx->map, ctx->work);  // icp.setMap(localPointCloud): registrations see the new map from here on
+        ctx->has_map = true;
+        ctx->map_n = ctx->store.n_active;
+    }
+    ctx->updating = false;
+    ctx->work_valid = false;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_update_in_progress(const b200icp_ctx* ctx) { return (ctx && ctx->updating) ? 1 : 0; }
+
+/* The scan in the slot becomes the input of an asynchronous map update (the reference copies `currentInput` into the std::async
+ * call, Mapper.cpp:282): the thread that calls b200icp_map_begin_update works on it through the b200icp_scan_* module entry
+ * points while the caller thread is free to upload the next scan.  O(1): the two slots trade places; the caller's slot is empty
+ * afterwards. */
+int32_t b200icp_scan_snapshot(b200icp_ctx* ctx) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
+    if (ctx->updating) return fail(ctx, B200ICP_ERR_INVALID_ARG, "the previous snapshot is still in use by a map update");
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::swap(ctx->scan, ctx->scan_upd);
+    ctx->scan.n = 0;
+    ctx->scan.has_nrm = ctx->scan.has_prob = false;
+    ctx->scan.extra_rows = 0;
+    ctx->scan.n_rot = 0;
+    return B200ICP_OK;
 }
 
 int32_t b200icp_map_counts(const b200icp_ctx* ctx, int64_t* n_local, int64_t* n_global) {
@@ -1139,12 +1234,12 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const DevCloud& in, f
         // Nabo::NNS::knn(input, k = 1, eps = 0, no radius) against the map -- on the live index
         float Tpre[16];
         mat4_identity(Tpre);
-        for (int d = 0; d < dim; ++d) Tpre[12 + d] = -ctx->map.mean[d];
+        for (int d = 0; d < dim; ++d) Tpre[12 + d] = -synced_index(ctx).mean[d];
         CK(launch_prep_reading(in.feat, in.rows, dim, Tpre, ctx->d_q4, nullptr, nullptr, nullptr, n_in, s));
         int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
         *h_nq = (int)n_in;
         CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-        CK(launch_knn(ctx->map.view, ctx->d_q4, ctx->d_scalar_nq, (int)n_in, nullptr, 1, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
+        CK(launch_knn(synced_index(ctx).view, ctx->d_q4, ctx->d_scalar_nq, (int)n_in, nullptr, 1, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
                       /*want_original_ids=*/1, ctx->cfg.nn_variant, s));
     } else {  // createMap: the first cloud is taken as it is (PointDistanceMapperModule.cpp:9-19)
         CK(cudaMemsetAsync(ctx->d_out_ids, 0xff, (size_t)n_in * sizeof(int32_t), s));
@@ -1157,7 +1252,7 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const DevCloud& in, f
         ctx->cap_keep = n_in + n_in / 4 + 1024;
     }
     int64_t kept = 0;
-    CK(store_insert_point_distance(st, ctx->map, in, dim, ctx->d_out_ids, min_dist_new_point, &kept, keep_out ? ctx->d_keep : nullptr, s));
+    CK(store_insert_point_distance(st, build_index(ctx), in, dim, ctx->d_out_ids, min_dist_new_point, &kept, keep_out ? ctx->d_keep : nullptr, s));
     if (keep_out) CK(cudaMemcpyAsync(keep_out, ctx->d_keep, (size_t)n_in, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (kept > 0) ctx->index_stale = true;
@@ -1197,6 +1292,7 @@ int32_t b200icp_map_insert_point_distance_prob(b200icp_ctx* ctx, const float* in
                                                const float* input_normals, const float* input_prob, float min_dist_new_point,
                                                int64_t* n_added, uint8_t* keep_out) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1) return fail(ctx, B200ICP_ERR_INVALID_ARG, "feature_rows must be dim + 1");
     if (n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
@@ -1217,7 +1313,7 @@ int32_t b200icp_map_insert_point_distance_prob(b200icp_ctx* ctx, const float* in
  * chain (Mapper.cpp:187-191), the rigid transforms (Mapper.cpp:197,221), icp(input) (:213) and the MapperModules
  * (Map.cpp:502-534) then run on that copy ---- */
 static int32_t scan_reserve(b200icp_ctx* ctx, int64_t n, int extra_rows) {
-    auto& sc = ctx->scan;
+    auto& sc = scan_slot(ctx);
     const int dim = ctx->cfg.dim;
     if (n > sc.cap) {
         const int64_t cap = grow_capacity(n);
@@ -1250,7 +1346,7 @@ static int32_t scan_reserve(b200icp_ctx* ctx, int64_t n, int extra_rows) {
 }
 
 static DevCloud scan_cloud(const b200icp_ctx* ctx) {
-    const auto& sc = ctx->scan;
+    const auto& sc = scan_slot(ctx);
     DevCloud c;
     c.feat = sc.feat[sc.cur];
     c.rows = ctx->cfg.dim + 1;
@@ -1264,11 +1360,12 @@ static DevCloud scan_cloud(const b200icp_ctx* ctx) {
 
 int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (feature_rows != ctx->cfg.dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad scan");
     CK(cudaSetDevice(ctx->device));
     const int32_t rc = scan_reserve(ctx, n, 0);
     if (rc != B200ICP_OK) return rc;
-    auto& sc = ctx->scan;
+    auto& sc = scan_slot(ctx);
     if (n > 0) CK(cudaMemcpyAsync(sc.feat[sc.cur], features, (size_t)n * feature_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     sc.n = n;
     sc.has_nrm = sc.has_prob = false;  // a new cloud: the previous scan's descriptors are gone
@@ -1280,6 +1377,7 @@ int32_t b200icp_scan_upload(b200icp_ctx* ctx, const float* features, int32_t fea
 int32_t b200icp_scan_set_descriptors(b200icp_ctx* ctx, const float* normals, const float* prob, const float* extra, int32_t extra_rows,
                                      const int32_t* rotating_rows, int32_t n_rotating) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (extra && (extra_rows < 1 || extra_rows > B200ICP_MAX_EXTRA_ROWS)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "extra_rows out of range");
     if (n_rotating < 0 || n_rotating > 4 || (n_rotating > 0 && (!rotating_rows || !extra)))
@@ -1287,7 +1385,7 @@ int32_t b200icp_scan_set_descriptors(b200icp_ctx* ctx, const float* normals, con
     for (int i = 0; i < n_rotating; ++i)
         if (rotating_rows[i] < 0 || rotating_rows[i] + dim > extra_rows) return fail(ctx, B200ICP_ERR_INVALID_ARG, "rotating descriptor outside `extra`");
     CK(cudaSetDevice(ctx->device));
-    auto& sc = ctx->scan;
+    auto& sc = scan_slot(ctx);
     const int32_t rc = scan_reserve(ctx, sc.n, extra ? extra_rows : 0);
     if (rc != B200ICP_OK) return rc;
     cudaStream_t s = ctx->stream;
@@ -1303,24 +1401,25 @@ int32_t b200icp_scan_set_descriptors(b200icp_ctx* ctx, const float* normals, con
     return B200ICP_OK;
 }
 
-int64_t b200icp_scan_size(const b200icp_ctx* ctx) { return ctx ? ctx->scan.n : 0; }
+int64_t b200icp_scan_size(const b200icp_ctx* ctx) { return ctx ? scan_slot(ctx).n : 0; }
 
 int32_t b200icp_scan_info(const b200icp_ctx* ctx, int32_t* has_normals, int32_t* has_prob, int32_t* extra_rows) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
-    if (has_normals) *has_normals = ctx->scan.has_nrm ? 1 : 0;
-    if (has_prob) *has_prob = ctx->scan.has_prob ? 1 : 0;
-    if (extra_rows) *extra_rows = ctx->scan.extra_rows;
+    if (has_normals) *has_normals = scan_slot(ctx).has_nrm ? 1 : 0;
+    if (has_prob) *has_prob = scan_slot(ctx).has_prob ? 1 : 0;
+    if (extra_rows) *extra_rows = scan_slot(ctx).extra_rows;
     return B200ICP_OK;
 }
 
 int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T) {
     if (!ctx || !T) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     float M[16];
     embed(T, dim, M);
     if (std::fabs(1.f - det3(M)) > 1e-3f)
         return fail(ctx, B200ICP_ERR_TRANSFORM, "RigidTransformation: Error, rotation matrix is not orthogonal.");
-    auto& sc = ctx->scan;
+    auto& sc = scan_slot(ctx);
     if (sc.n == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     // stream-ordered: no sync needed here
@@ -1332,7 +1431,8 @@ int32_t b200icp_scan_transform(b200icp_ctx* ctx, const float* T) {
 
 int32_t b200icp_scan_register(b200icp_ctx* ctx, const float* T_init, float* T_out, b200icp_result* result) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
-    auto& sc = ctx->scan;
+    B200_LOCK(ctx);
+    auto& sc = scan_slot(ctx);
     if (!sc.has_nrm) return b200icp_register_device(ctx, sc.feat[sc.cur], ctx->cfg.dim + 1, sc.n, T_init, T_out, result);
     // the reading carries `normals` (SurfaceNormalOutlierFilter compares them with the map's)
     if (result) memset(result, 0, sizeof(*result));
@@ -1357,15 +1457,16 @@ static int32_t check_filter_chain(b200icp_ctx* ctx, const b200icp_filter* chain,
 
 int32_t b200icp_scan_filter(b200icp_ctx* ctx, const b200icp_filter* chain, int32_t n_filters, int64_t* n_out) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int32_t rc = check_filter_chain(ctx, chain, n_filters);
     if (rc != B200ICP_OK) return rc;
-    auto& sc = ctx->scan;
+    auto& sc = scan_slot(ctx);
     if (n_out) *n_out = sc.n;
     if (sc.n == 0 || n_filters == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     const int o = sc.cur ^ 1;
     int64_t kept = 0;
-    CK(filter_cloud_device(ctx->store, ctx->map, scan_cloud(ctx), ctx->cfg.dim, chain, n_filters, sc.feat[o], sc.nrm[o], sc.prob[o],
+    CK(filter_cloud_device(ctx->store, build_index(ctx), scan_cloud(ctx), ctx->cfg.dim, chain, n_filters, sc.feat[o], sc.nrm[o], sc.prob[o],
                            sc.extra_rows > 0 ? sc.extra[o] : nullptr, &kept, ctx->stream));
     sc.cur = o;
     sc.n = kept;
@@ -1375,7 +1476,8 @@ int32_t b200icp_scan_filter(b200icp_ctx* ctx, const b200icp_filter* chain, int32
 
 int32_t b200icp_scan_add_prob(b200icp_ctx* ctx, float constant) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
-    auto& sc = ctx->scan;
+    B200_LOCK(ctx);
+    auto& sc = scan_slot(ctx);
     CK(cudaSetDevice(ctx->device));
     if (sc.n > 0) CK(launch_fill(sc.prob[sc.cur], constant, sc.n, ctx->stream));
     sc.has_prob = true;
@@ -1478,8 +1580,9 @@ static int32_t cloud_normals_dev(b200icp_ctx* ctx, const float* d_in, int rows, 
 
 int32_t b200icp_scan_surface_normals(b200icp_ctx* ctx, int32_t knn) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (knn < 1 || knn > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "knn must be in [1, 32]");
-    auto& sc = ctx->scan;
+    auto& sc = scan_slot(ctx);
     CK(cudaSetDevice(ctx->device));
     if (sc.n > 0) {
         const int32_t rc = cloud_normals_dev(ctx, sc.feat[sc.cur], ctx->cfg.dim + 1, sc.n, knn, sc.nrm[sc.cur]);
@@ -1492,7 +1595,8 @@ int32_t b200icp_scan_surface_normals(b200icp_ctx* ctx, int32_t knn) {
 
 int32_t b200icp_scan_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t n_rows) {
     if (!ctx || n_rows < 0 || n_rows > B200ICP_MAX_EXTRA_ROWS || (n_rows > 0 && !rows)) return B200ICP_ERR_INVALID_ARG;
-    auto& sc = ctx->scan;
+    B200_LOCK(ctx);
+    auto& sc = scan_slot(ctx);
     for (int i = 0; i < n_rows; ++i)
         if (rows[i] < 0 || rows[i] >= sc.extra_rows) return fail(ctx, B200ICP_ERR_INVALID_ARG, "descriptor row outside `extra`");
     CK(cudaSetDevice(ctx->device));
@@ -1520,8 +1624,9 @@ int32_t b200icp_scan_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t
 
 int32_t b200icp_scan_insert_point_distance(b200icp_ctx* ctx, float min_dist_new_point, int64_t* n_added) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (n_added) *n_added = 0;
-    if (ctx->scan.n == 0) return B200ICP_OK;
+    if (scan_slot(ctx).n == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     if (ctx->store.n_active > 0 && ctx->index_stale) {
         const int32_t rc = commit_index(ctx);
@@ -1532,7 +1637,8 @@ int32_t b200icp_scan_insert_point_distance(b200icp_ctx* ctx, float min_dist_new_
 
 int32_t b200icp_scan_download(b200icp_ctx* ctx, float* features, int64_t capacity, int64_t* n_out) {
     if (!ctx || !n_out) return B200ICP_ERR_INVALID_ARG;
-    auto& sc = ctx->scan;
+    B200_LOCK(ctx);
+    auto& sc = scan_slot(ctx);
     *n_out = sc.n;
     if (!features) return B200ICP_OK;
     if (capacity < sc.n) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
@@ -1545,7 +1651,8 @@ int32_t b200icp_scan_download(b200icp_ctx* ctx, float* features, int64_t capacit
 
 int32_t b200icp_scan_download_descriptors(b200icp_ctx* ctx, float* normals, float* prob, float* extra, int64_t capacity) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
-    auto& sc = ctx->scan;
+    B200_LOCK(ctx);
+    auto& sc = scan_slot(ctx);
     if (capacity < sc.n) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
     if ((normals && !sc.has_nrm) || (prob && !sc.has_prob) || (extra && sc.extra_rows == 0))
         return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the scan does not carry that descriptor");
@@ -1562,23 +1669,25 @@ int32_t b200icp_scan_download_descriptors(b200icp_ctx* ctx, float* normals, floa
 
 int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (knn < 1 || knn > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "knn must be in [1, 32]");
     CK(cudaSetDevice(ctx->device));
     MapStore& st = ctx->store;
     if (st.n_active == 0) return B200ICP_OK;
-    if (ctx->index_stale || !ctx->has_map) {
+    if (ctx->index_stale || !(ctx->updating ? ctx->work_valid : ctx->has_map)) {
         const int32_t rc = commit_index(ctx);
         if (rc != B200ICP_OK) return rc;
     }
     cudaStream_t s = ctx->stream;
-    const int64_t n = ctx->map.view.n;
-    if (n > ctx->map.cap_normals) {
+    GridIndex& idx = synced_index(ctx);  // (the commit above built it)
+    const int64_t n = idx.view.n;
+    if (n > idx.cap_normals) {
         // (the index was built without normals: nothing to preserve)
-        B200_CUDA_FREE(ctx->map.normals);
-        ctx->map.normals = nullptr;
-        ctx->map.cap_normals = 0;
-        CK(B200_CUDA_MALLOC((void**)&ctx->map.normals, (size_t)grow_capacity(n) * sizeof(float4)));
-        ctx->map.cap_normals = grow_capacity(n);
+        B200_CUDA_FREE(idx.normals);
+        idx.normals = nullptr;
+        idx.cap_normals = 0;
+        CK(B200_CUDA_MALLOC((void**)&idx.normals, (size_t)grow_capacity(n) * sizeof(float4)));
+        idx.cap_normals = grow_capacity(n);
     }
     // k-th neighbour distance per store point (incremental bookkeeping); grows with the store, content preserved
     if (st.n > ctx->cap_kth) {
@@ -1618,15 +1727,15 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         size_t need = 0;
         thrust::counting_iterator<uint32_t> counting(0u);
         cub::DeviceSelect::Flagged(nullptr, need, counting, ctx->d_dirty, ctx->d_list, d_count, (int)st.n);
-        if (need > ctx->map.cub_tmp_bytes) {
-            B200_CUDA_FREE(ctx->map.cub_tmp);
-            ctx->map.cub_tmp = nullptr;
-            ctx->map.cub_tmp_bytes = 0;
-            CK(B200_CUDA_MALLOC(&ctx->map.cub_tmp, need + 256));
-            ctx->map.cub_tmp_bytes = need + 256;
+        if (need > idx.cub_tmp_bytes) {
+            B200_CUDA_FREE(idx.cub_tmp);
+            idx.cub_tmp = nullptr;
+            idx.cub_tmp_bytes = 0;
+            CK(B200_CUDA_MALLOC(&idx.cub_tmp, need + 256));
+            idx.cub_tmp_bytes = need + 256;
         }
-        size_t bytes = ctx->map.cub_tmp_bytes;
-        CK(cub::DeviceSelect::Flagged(ctx->map.cub_tmp, bytes, counting, ctx->d_dirty, ctx->d_list, d_count, (int)st.n, s));
+        size_t bytes = idx.cub_tmp_bytes;
+        CK(cub::DeviceSelect::Flagged(idx.cub_tmp, bytes, counting, ctx->d_dirty, ctx->d_list, d_count, (int)st.n, s));
         unsigned int c = 0;
         CK(cudaMemcpyAsync(&c, d_count, sizeof(c), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1647,19 +1756,19 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         uint8_t* d_dirty = ctx->d_dirty;         // per store index
         uint8_t* d_flag = ctx->d_dirty + st.n;   // per cell-sorted position of the live index
         CK(launch_normals_dirty(ctx->aux.view, st, ctx->d_kth, st.nrm_epoch_n, d_dirty, s));
-        CK(launch_normals_positions(ctx->map.view, d_dirty, d_flag, s));
+        CK(launch_normals_positions(idx.view, d_dirty, d_flag, s));
         size_t need = 0;
         thrust::counting_iterator<uint32_t> counting(0u);
         cub::DeviceSelect::Flagged(nullptr, need, counting, d_flag, ctx->d_list, d_count, (int)n);
-        if (need > ctx->map.cub_tmp_bytes) {
-            B200_CUDA_FREE(ctx->map.cub_tmp);
-            ctx->map.cub_tmp = nullptr;
-            ctx->map.cub_tmp_bytes = 0;
-            CK(B200_CUDA_MALLOC(&ctx->map.cub_tmp, need + 256));
-            ctx->map.cub_tmp_bytes = need + 256;
+        if (need > idx.cub_tmp_bytes) {
+            B200_CUDA_FREE(idx.cub_tmp);
+            idx.cub_tmp = nullptr;
+            idx.cub_tmp_bytes = 0;
+            CK(B200_CUDA_MALLOC(&idx.cub_tmp, need + 256));
+            idx.cub_tmp_bytes = need + 256;
         }
-        size_t bytes = ctx->map.cub_tmp_bytes;
-        CK(cub::DeviceSelect::Flagged(ctx->map.cub_tmp, bytes, counting, d_flag, ctx->d_list, d_count, (int)n, s));
+        size_t bytes = idx.cub_tmp_bytes;
+        CK(cub::DeviceSelect::Flagged(idx.cub_tmp, bytes, counting, d_flag, ctx->d_list, d_count, (int)n, s));
         unsigned int m = 0;
         CK(cudaMemcpyAsync(&m, d_count, sizeof(m), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1667,23 +1776,23 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         if (m > 0) {
             const int32_t eb = ensure_query_buffers(ctx, m, knn);
             if (eb != B200ICP_OK) return eb;
-            CK(launch_normals_gather(ctx->map.view, ctx->d_list, d_count, m, ctx->d_q4, s));
-            const int32_t sk = self_knn(ctx, ctx->map.view, ctx->d_q4, m, knn, false);
+            CK(launch_normals_gather(idx.view, ctx->d_list, d_count, m, ctx->d_q4, s));
+            const int32_t sk = self_knn(ctx, idx.view, ctx->d_q4, m, knn, false);
             if (sk != B200ICP_OK) return sk;
-            CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, ctx->d_list, d_count, m, ctx->map.normals, st.nrm,
+            CK(launch_normals(idx.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, ctx->d_list, d_count, m, idx.normals, st.nrm,
                               ctx->d_kth, s));
         }
     } else {
         const int32_t eb = ensure_query_buffers(ctx, n, knn);
         if (eb != B200ICP_OK) return eb;
         // self k-NN: the queries are the cell-sorted map points themselves (every point of a tile shares its candidates)
-        const int32_t sk = self_knn(ctx, ctx->map.view, ctx->map.pts, n, knn, true);
+        const int32_t sk = self_knn(ctx, idx.view, idx.pts, n, knn, true);
         if (sk != B200ICP_OK) return sk;
-        CK(launch_normals(ctx->map.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, ctx->map.normals, st.nrm, ctx->d_kth, s));
+        CK(launch_normals(idx.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, nullptr, nullptr, 0, idx.normals, st.nrm, ctx->d_kth, s));
     }
     CK(store_clear_touched(st, s));
     CK(cudaStreamSynchronize(s));
-    ctx->map.has_normals = true;
+    idx.has_normals = true;
     st.has_normals = true;
     // bookkeeping valid when every store point is in the index (parked points keep what they had and are recomputed
     // wholesale when the window moves: store_window invalidates)
@@ -1697,6 +1806,7 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
  * the reading, e.g. for SurfaceNormalOutlierFilter): grid over the cloud, self k-NN, covariance, smallest eigenvector. */
 int32_t b200icp_cloud_surface_normals(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, int32_t knn, float* normals_out) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || n < 0 || (n > 0 && (!features || !normals_out))) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
     if (knn < 1 || knn > 32) return fail(ctx, B200ICP_ERR_INVALID_ARG, "knn must be in [1, 32]");
@@ -1722,6 +1832,7 @@ int64_t b200icp_debug_selfknn_redone(const b200icp_ctx* ctx) { return ctx ? ctx-
 
 int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6, int64_t* n_changed) {
     if (!ctx || !slab6) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     int32_t slab[6];
     memcpy(slab, slab6, sizeof(slab));
@@ -1739,6 +1850,7 @@ int32_t b200icp_map_window(b200icp_ctx* ctx, int32_t load, const int32_t* slab6,
 
 int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, float* normals, int64_t capacity, int64_t* n_out) {
     if (!ctx || !n_out) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     MapStore& st = ctx->store;
     const int dim = ctx->cfg.dim, rows = dim + 1;
@@ -1776,6 +1888,7 @@ int32_t b200icp_map_download(b200icp_ctx* ctx, int32_t global, float* features, 
 int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_rows, int64_t* n, const b200icp_filter* chain,
                              int32_t n_filters) {
     if (!ctx || !n) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || *n < 0 || (*n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
     const int32_t rc = check_filter_chain(ctx, chain, n_filters);
@@ -1793,7 +1906,7 @@ int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_
     in.feat = d_in;
     in.rows = feature_rows;
     in.n = *n;
-    CK(filter_cloud_device(ctx->store, ctx->map, in, dim, chain, n_filters, d_out, nullptr, nullptr, nullptr, &kept, s));
+    CK(filter_cloud_device(ctx->store, build_index(ctx), in, dim, chain, n_filters, d_out, nullptr, nullptr, nullptr, &kept, s));
     if (kept > 0) CK(cudaMemcpyAsync(features, d_out, (size_t)kept * feature_rows * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *n = kept;
@@ -1802,6 +1915,7 @@ int32_t b200icp_filter_cloud(b200icp_ctx* ctx, float* features, int32_t feature_
 
 int32_t b200icp_map_set_prob(b200icp_ctx* ctx, const float* prob, float constant) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     MapStore& st = ctx->store;
     if (st.n == 0) return B200ICP_OK;
@@ -1836,6 +1950,7 @@ static int32_t download_rows(b200icp_ctx* ctx, const float* d_src, int rows, int
 
 int32_t b200icp_map_download_prob(b200icp_ctx* ctx, int32_t global, float* prob, int64_t capacity) {
     if (!ctx || !prob) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     if (!ctx->store.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map has no probabilityDynamic descriptor");
     return download_rows(ctx, ctx->store.prob, 1, global, prob, capacity);
@@ -1846,6 +1961,7 @@ int32_t b200icp_map_has_prob(const b200icp_ctx* ctx) { return (ctx && ctx->store
 /* the map's other descriptors (everything but normals / probabilityDynamic), extra_rows floats per point, insertion order */
 int32_t b200icp_map_set_extra(b200icp_ctx* ctx, const float* extra, int32_t extra_rows) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (extra_rows < 0 || extra_rows > B200ICP_MAX_EXTRA_ROWS || (extra_rows > 0 && !extra)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad descriptor block");
     CK(cudaSetDevice(ctx->device));
     MapStore& st = ctx->store;
@@ -1859,6 +1975,7 @@ int32_t b200icp_map_extra_rows(const b200icp_ctx* ctx) { return ctx ? ctx->store
 
 int32_t b200icp_map_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t n_rows) {
     if (!ctx || n_rows < 0 || (n_rows > 0 && !rows)) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     CK(store_select_extra(ctx->store, rows, n_rows, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1867,6 +1984,7 @@ int32_t b200icp_map_select_extra(b200icp_ctx* ctx, const int32_t* rows, int32_t 
 
 int32_t b200icp_map_download_extra(b200icp_ctx* ctx, int32_t global, float* extra, int64_t capacity) {
     if (!ctx || !extra) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     CK(cudaSetDevice(ctx->device));
     if (ctx->store.extra_rows == 0) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map carries no other descriptor");
     return download_rows(ctx, ctx->store.extra, ctx->store.extra_rows, global, extra, capacity);
@@ -1883,6 +2001,7 @@ static int32_t append_dev(b200icp_ctx* ctx, const DevCloud& in, int64_t* n_added
 int32_t b200icp_map_append(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_normals,
                            const float* input_prob, int64_t* n_added) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
     if (n_added) *n_added = 0;
@@ -1897,6 +2016,7 @@ int32_t b200icp_map_append(b200icp_ctx* ctx, const float* input, int32_t feature
 int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, const float* normals,
                                   const float* prob, const float* extra, int32_t extra_rows) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
     if (extra && (extra_rows < 1 || extra_rows > B200ICP_MAX_EXTRA_ROWS)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "extra_rows out of range");
@@ -1917,7 +2037,7 @@ int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32
         st.n = 0;
         st.n_active = 0;
     }
-    CK(store_replace_loaded(st, ctx->map, in, dim, ctx->stream));
+    CK(store_replace_loaded(st, build_index(ctx), in, dim, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->index_stale = true;
     return B200ICP_OK;
@@ -1925,8 +2045,9 @@ int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32
 
 int32_t b200icp_scan_append(b200icp_ctx* ctx, int64_t* n_added) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (n_added) *n_added = 0;
-    if (ctx->scan.n == 0) return B200ICP_OK;
+    if (scan_slot(ctx).n == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     return append_dev(ctx, scan_cloud(ctx), n_added);
 }
@@ -1948,7 +2069,7 @@ static int32_t octree_dev(b200icp_ctx* ctx, const DevCloud* in, float max_size_b
     uint64_t seed = 0x0c7ee5eedull;
     if (const char* env = getenv("B200ICP_OCTREE_SEED")) seed = strtoull(env, nullptr, 0);
     seed += ctx->octree_calls++;
-    CK(store_octree_filter(st, ctx->map, ctx->cfg.dim, max_size_by_node, sampling_method, seed, &removed, s));
+    CK(store_octree_filter(st, build_index(ctx), ctx->cfg.dim, max_size_by_node, sampling_method, seed, &removed, s));
     CK(cudaStreamSynchronize(s));
     ctx->index_stale = true;
     if (n_after) *n_after = st.n_active;
@@ -1959,6 +2080,7 @@ int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature
                            const float* input_prob, float max_size_by_node, int32_t max_point_by_node, int32_t sampling_method,
                            int64_t* n_after) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
     int32_t rc = octree_checks(ctx, max_size_by_node, max_point_by_node, sampling_method);
@@ -1974,6 +2096,7 @@ int32_t b200icp_map_octree(b200icp_ctx* ctx, const float* input, int32_t feature
 
 int32_t b200icp_scan_octree(b200icp_ctx* ctx, float max_size_by_node, int32_t max_point_by_node, int32_t sampling_method, int64_t* n_after) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int32_t rc = octree_checks(ctx, max_size_by_node, max_point_by_node, sampling_method);
     if (rc != B200ICP_OK) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -1983,10 +2106,11 @@ int32_t b200icp_scan_octree(b200icp_ctx* ctx, float max_size_by_node, int32_t ma
 
 int32_t b200icp_map_cut_at_threshold(b200icp_ctx* ctx, float threshold, int32_t use_larger_than, int64_t* n_removed) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     if (!ctx->store.has_prob) return fail(ctx, B200ICP_ERR_INVALID_FIELD, "CutAtDescriptorThreshold: descriptor probabilityDynamic not found");
     CK(cudaSetDevice(ctx->device));
     int64_t removed = 0;
-    CK(store_cut_prob(ctx->store, ctx->map, ctx->cfg.dim, threshold, use_larger_than, &removed, ctx->stream));
+    CK(store_cut_prob(ctx->store, build_index(ctx), ctx->cfg.dim, threshold, use_larger_than, &removed, ctx->stream));
     if (removed > 0) ctx->index_stale = true;
     if (n_removed) *n_removed = removed;
     return B200ICP_OK;
@@ -2019,7 +2143,7 @@ static int32_t dynamic_points_dev(b200icp_ctx* ctx, const DevCloud& in, const fl
         for (int c = 0; c < 3; ++c) acc += (double)P[r * 4 + c] * (double)P[12 + c];
         Tinv[12 + r] = (float)(-acc);
     }
-    if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, ctx->map, s));
+    if (!st.all_loaded || st.n_active != st.n) CK(store_compact_active(st, build_index(ctx), s));
     // scratch: input in the sensor frame (float4) + its angles (2 floats)
     CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, (size_t)n_in * (sizeof(float4) + 2 * sizeof(float)) + 512));
     float4* d_in_sensor = reinterpret_cast<float4*>(ctx->d_stage_b);
@@ -2046,6 +2170,7 @@ static int32_t dynamic_points_dev(b200icp_ctx* ctx, const DevCloud& in, const fl
 int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in, const float* input_prob,
                                    const float* pose, const b200icp_dynamic_params* prm) {
     if (!ctx || !prm || !pose) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
     const int dim = ctx->cfg.dim;
     if (feature_rows != dim + 1 || n_in < 0 || (n_in > 0 && !input)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad input cloud");
     int32_t rc = dynamic_points_checks(ctx, input_prob != nullptr);
@@ -2060,9 +2185,10 @@ int32_t b200icp_map_dynamic_points(b200icp_ctx* ctx, const float* input, int32_t
 
 int32_t b200icp_scan_dynamic_points(b200icp_ctx* ctx, const float* pose, const b200icp_dynamic_params* prm) {
     if (!ctx || !prm || !pose) return B200ICP_ERR_INVALID_ARG;
-    const int32_t rc = dynamic_points_checks(ctx, ctx->scan.has_prob);
+    B200_LOCK(ctx);
+    const int32_t rc = dynamic_points_checks(ctx, scan_slot(ctx).has_prob);
     if (rc != B200ICP_OK) return rc;
-    if (ctx->scan.n == 0 || ctx->store.n_active == 0) return B200ICP_OK;
+    if (scan_slot(ctx).n == 0 || ctx->store.n_active == 0) return B200ICP_OK;
     CK(cudaSetDevice(ctx->device));
     return dynamic_points_dev(ctx, scan_cloud(ctx), pose, prm);
 }

@@ -47,14 +47,32 @@ class ICPSequence {
         return map.getNbPoints() > 0;
     }
     // ---- the scan slot: ONE device-resident cloud per context; `scanLabels` names the rows of its `extra` block ----
-    Labels scanLabels;  // descriptors of the scan slot other than normals / probabilityDynamic
+    // descriptors of the scan slot other than normals / probabilityDynamic: the caller's slot, and the snapshot an asynchronous map
+    // update works on (the worker thread marks itself with UpdateThreadScope, mirroring b200icp_map_begin_update's routing)
+    Labels scanLabelsMain, scanLabelsUpd;
     Labels mapLabels;   // the same for the device-resident map
+    static bool& onUpdateThread() {
+        static thread_local bool flag = false;
+        return flag;
+    }
+    struct UpdateThreadScope {
+        UpdateThreadScope() { onUpdateThread() = true; }
+        ~UpdateThreadScope() { onUpdateThread() = false; }
+    };
+    Labels& scanLabelsRef() { return onUpdateThread() ? scanLabelsUpd : scanLabelsMain; }
+    const Labels& scanLabelsRef() const { return onUpdateThread() ? scanLabelsUpd : scanLabelsMain; }
+    // the scan in the slot becomes the input of an asynchronous update (Mapper::updateMap, isOnline)
+    void snapshotScan() {
+        check(ctx, b200icp_scan_snapshot(ctx));
+        scanLabelsUpd = scanLabelsMain;
+        scanLabelsMain.clear();
+    }
     bool scanHas(const std::string& name) const {
         int32_t hn = 0, hp = 0;
         b200icp_scan_info(ctx, &hn, &hp, nullptr);
         if (name == "normals") return hn != 0;
         if (name == "probabilityDynamic") return hp != 0;
-        return labelStartingRow(scanLabels, name) >= 0;
+        return labelStartingRow(scanLabelsRef(), name) >= 0;
     }
     // host copy of a device-resident scan (modules without a device entry point use it)
     DataPoints materialize(const DataPoints& cloud) {
@@ -69,7 +87,7 @@ class ICPSequence {
         if (hn) out.normals.resize((size_t)n * dim);
         if (hp) out.probabilityDynamic.resize((size_t)n);
         if (xr) out.descriptors.resize((size_t)n * xr);
-        out.descriptorLabels = scanLabels;
+        out.descriptorLabels = scanLabelsRef();
         if (n > 0 && (hn || hp || xr))
             check(ctx, b200icp_scan_download_descriptors(ctx, hn ? out.normals.data() : nullptr, hp ? out.probabilityDynamic.data() : nullptr,
                                                          xr ? out.descriptors.data() : nullptr, n));
@@ -86,7 +104,7 @@ class ICPSequence {
                                                 cloud.probabilityDynamic.empty() ? nullptr : cloud.probabilityDynamic.data(),
                                                 cloud.descriptors.empty() ? nullptr : cloud.descriptors.data(), cloud.getDescriptorRows(),
                                                 rotating.empty() ? nullptr : rotating.data(), (int32_t)rotating.size()));
-        scanLabels = cloud.descriptors.empty() ? Labels() : cloud.descriptorLabels;
+        scanLabelsRef() = cloud.descriptors.empty() ? Labels() : cloud.descriptorLabels;
         DataPoints out;
         out.dim = cloud.dim;
         out.onDevice = true;
@@ -96,6 +114,7 @@ class ICPSequence {
     // DataPoints::concatenate's descriptor rule ahead of `map.concatenate(scan)` on the device: both sides keep the descriptors
     // they have in common, in the map's order (an empty map takes the scan's)
     void reconcileScanWithMap(bool mapIsEmpty) {
+        Labels& scanLabels = scanLabelsRef();
         if (mapIsEmpty) {
             mapLabels = scanLabels;
             return;

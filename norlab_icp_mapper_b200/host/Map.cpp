@@ -1,6 +1,7 @@
 // Map.cpp -- see Map.h.  Reference: /root/reference/norlab_icp_mapper/Map.cpp.
 #include "Map.h"
 
+#include <chrono>
 #include <cmath>
 #include <limits>
 
@@ -8,9 +9,52 @@ namespace norlab_icp_mapper_b200 {
 
 Map::Map(bool is3D_, bool isOnline_, ICPSequence& icp_, std::mutex& icpMapLock_)
     : is3D(is3D_), isOnline(isOnline_), icp(icp_), icpMapLock(icpMapLock_), localPointCloud(icp_) {
-    // isOnline: the reference runs window updates on `updateThread` (Map.cpp:29-57); here they are a
-    // flag kernel + one index rebuild (milliseconds), applied inline in both modes.
-    (void)isOnline;
+    if (isOnline) updateThread = std::thread(&Map::updateThreadFunction, this);  // Map.cpp:29-32
+}
+
+Map::~Map() {  // Map.cpp:34-41
+    if (isOnline) {
+        updateThreadLooping.store(false);
+        if (updateThread.joinable()) updateThread.join();
+    }
+}
+
+// Map.cpp:43-57.  loadCells / unloadCells end with icp.setMap(localPointCloud) (Map.cpp:110-112,177-179): here one index rebuild once
+// the queue has drained, under the same two locks.
+void Map::updateThreadFunction() {
+    while (updateThreadLooping.load()) {
+        Update update{};
+        bool have = false, last = false;
+        {
+            std::lock_guard<std::mutex> lock(updateListLock);
+            if (!updateList.empty()) {
+                update = updateList.front();
+                updateList.pop_front();
+                have = true;
+                last = updateList.empty();
+            }
+        }
+        if (have) {
+            try {
+                applyUpdate(update);
+                if (last) {
+                    std::lock_guard<std::mutex> l1(localPointCloudLock);
+                    std::lock_guard<std::mutex> l2(icpMapLock);
+                    ICPSequence::check(icp.context(), b200icp_map_commit(icp.context()));
+                    localPointCloudEmpty.store(localPointCloud.getNbPoints() == 0);
+                }
+            } catch (const std::exception&) {
+                // (a failed window update leaves the previous window in place; the next registration reports device errors)
+            }
+            updatesInFlight.fetch_sub(1);
+        } else {
+            std::this_thread::sleep_for(std::chrono::duration<float>(0.01f));
+        }
+    }
+}
+
+void Map::waitForWindowUpdates() {
+    while (updatesInFlight.load() > 0) std::this_thread::sleep_for(std::chrono::milliseconds(1));
 }
 
 // Map.cpp:472-480
@@ -28,7 +72,15 @@ void Map::applyUpdate(const Update& u) {
     appliedUpdates.push_back(u);
 }
 
-void Map::scheduleUpdate(const Update& update) { applyUpdate(update); }  // Map.cpp:482-494
+void Map::scheduleUpdate(const Update& update) {  // Map.cpp:482-494
+    if (isOnline) {
+        updatesInFlight.fetch_add(1);
+        std::lock_guard<std::mutex> lock(updateListLock);
+        updateList.push_back(update);
+    } else {
+        applyUpdate(update);
+    }
+}
 
 // Map.cpp:246-460.  Per axis a (row, column, aisle) the window is [inferior - BUFFER, superior + BUFFER]
 // in 20 m cells; an edge that moved by >= 2 cells loads / unloads the slab it swept, spanning the
@@ -36,7 +88,10 @@ void Map::scheduleUpdate(const Update& update) { applyUpdate(update); }  // Map.
 void Map::updatePose(const TransformationParameters& pose) {
     const int positionColumn = is3D ? 3 : 2;
     const int axes = is3D ? 3 : 2;
-    appliedUpdates.clear();
+    {
+        std::lock_guard<std::mutex> lock(localPointCloudLock);
+        appliedUpdates.clear();
+    }
     if (firstPoseUpdate.load()) {
         for (int a = 0; a < axes; ++a) {
             inferiorLastUpdateIndex[a] = toInferiorGridCoordinate(pose(a, positionColumn), sensorMaxRange);
@@ -81,7 +136,7 @@ void Map::updatePose(const TransformationParameters& pose) {
             }
         }
     }
-    if (!appliedUpdates.empty()) {
+    if (!isOnline && !appliedUpdates.empty()) {  // (isOnline: the update thread rebuilds once its queue has drained)
         // icp.setMap(localPointCloud) of loadCells / unloadCells (Map.cpp:110-112,177-179), once for all slabs
         std::lock_guard<std::mutex> l1(localPointCloudLock);
         std::lock_guard<std::mutex> l2(icpMapLock);
@@ -96,8 +151,21 @@ DataPoints Map::getLocalPointCloud() {
 }
 
 // Map.cpp:502-534
-void Map::updateLocalPointCloud(const DataPoints& input, const TransformationParameters& pose, const PostFilters& postFilters) {
+void Map::updateLocalPointCloud(DataPoints input, TransformationParameters pose, PostFilters postFilters, bool asynchronous) {
     std::lock_guard<std::mutex> lock(localPointCloudLock);
+    // asynchronous: this thread works on the scan snapshot and on a second index until the final setMap
+    std::unique_ptr<ICPSequence::UpdateThreadScope> scope;
+    struct EndUpdate {  // (also on the way out of an exception: the context must not stay in update mode)
+        b200icp_ctx* ctx = nullptr;
+        ~EndUpdate() {
+            if (ctx && b200icp_map_update_in_progress(ctx)) b200icp_map_end_update(ctx);
+        }
+    } endUpdate;
+    if (asynchronous) {
+        scope.reset(new ICPSequence::UpdateThreadScope());
+        ICPSequence::check(icp.context(), b200icp_map_begin_update(icp.context()));
+        endUpdate.ctx = icp.context();
+    }
     if (isLocalPointCloudEmpty()) {
         auto iter = mapperModuleVec.begin();
         (*iter)->inPlaceCreateMap(input, localPointCloud, pose);
@@ -119,6 +187,10 @@ void Map::updateLocalPointCloud(const DataPoints& input, const TransformationPar
             ICPSequence::check(icp.context(), b200icp_map_cut_at_threshold(icp.context(), postFilters.cutThreshold,
                                                                            postFilters.cutUseLargerThan ? 1 : 0, &removed));
             if (removed > 0) ICPSequence::check(icp.context(), b200icp_map_commit(icp.context()));
+        }
+        if (asynchronous) {  // icp.setMap(localPointCloud): the new index goes live
+            ICPSequence::check(icp.context(), b200icp_map_end_update(icp.context()));
+            endUpdate.ctx = nullptr;
         }
     }
     localPointCloudEmpty.store(localPointCloud.getNbPoints() == 0);

@@ -4,6 +4,8 @@
 #pragma once
 #include <array>
 #include <atomic>
+#include <list>
+#include <thread>
 #include <memory>
 #include <mutex>
 #include <vector>
@@ -42,6 +44,13 @@ class Map {
     std::atomic_bool firstPoseUpdate{true};
     std::vector<std::shared_ptr<MapperModule>> mapperModuleVec;
     std::vector<Update> appliedUpdates;  // log of the slabs of the last updatePose (tests)
+    // isOnline: cell-window updates are queued and applied by `updateThread` (Map.cpp:29-57,482-494)
+    std::list<Update> updateList;
+    std::mutex updateListLock;
+    std::atomic_bool updateThreadLooping{true};
+    std::atomic_int updatesInFlight{0};
+    std::thread updateThread;
+    void updateThreadFunction();
 
     void applyUpdate(const Update& update);
     int toInferiorGridCoordinate(float worldCoordinate, float range) const;
@@ -50,9 +59,14 @@ class Map {
 
    public:
     Map(bool is3D, bool isOnline, ICPSequence& icp, std::mutex& icpMapLock);
+    ~Map();
     void updatePose(const TransformationParameters& pose);
     DataPoints getLocalPointCloud();
-    void updateLocalPointCloud(const DataPoints& input, const TransformationParameters& pose, const PostFilters& postFilters);
+    // asynchronous = true: called on a worker thread while registrations go on (Mapper::updateMap, isOnline): the update steps build a
+    // second index that replaces the live one in the final icp.setMap (b200icp_map_begin_update / b200icp_map_end_update)
+    void updateLocalPointCloud(DataPoints input, TransformationParameters pose, PostFilters postFilters, bool asynchronous = false);
+    //! isOnline: block until the queued cell-window updates have been applied (tests, orderly shutdown)
+    void waitForWindowUpdates();
     bool getNewLocalPointCloud(DataPoints& localPointCloudOut);
     DataPoints getGlobalPointCloud();
     void setGlobalPointCloud(const DataPoints& newLocalPointCloud);

@@ -129,6 +129,9 @@ void Mapper::processInput(const DataPoints& filteredInputInSensorFrame, const Tr
             timer.lap("updateMap");
         }
     }
+    // Mapper.cpp:225-228: collect a finished asynchronous update (its exceptions surface here).  The reference waits up to 1 ms for
+    // it -- nothing next to a CPU registration, but as long as a whole registration here: a poll instead.
+    if (mapUpdateFuture.valid() && mapUpdateFuture.wait_for(std::chrono::milliseconds(0)) == std::future_status::ready) mapUpdateFuture.get();
     {
         std::lock_guard<std::mutex> lock(poseLock);
         pose = correctedPose;
@@ -142,7 +145,8 @@ void Mapper::processInput(const DataPoints& filteredInputInSensorFrame, const Tr
 // Mapper.cpp:240-272
 bool Mapper::shouldUpdateMap(double currentTime, const TransformationParameters& currentPose, float currentOverlap) const {
     if (!isMapping.load()) return false;
-    // isOnline: "previous update is not over" never holds -- updates complete inside updateMap
+    // Mapper.cpp:248-255: if previous update is not over
+    if (isOnline && mapUpdateInFlight()) return false;
     if (mapUpdateCondition == "overlap") return currentOverlap < mapUpdateOverlap;
     if (mapUpdateCondition == "delay") return (currentTime - lastTimeMapWasUpdated) > (double)mapUpdateDelay;
     const int euclideanDim = is3D ? 3 : 2;
@@ -158,9 +162,15 @@ bool Mapper::shouldUpdateMap(double currentTime, const TransformationParameters&
 void Mapper::updateMap(const DataPoints& currentInput, const TransformationParameters& currentPose, double currentTimeStamp) {
     lastTimeMapWasUpdated = currentTimeStamp;
     lastPoseWhereMapWasUpdated = currentPose;
-    // isOnline && map non-empty: the reference hands this to std::async; the device update takes
-    // milliseconds, so it is done in line (async overlap on a second stream: SURVEY 8f rank 3)
-    map.updateLocalPointCloud(currentInput, currentPose, mapPostFilters);
+    if (isOnline && !map.isLocalPointCloudEmpty()) {  // Mapper.cpp:280-283
+        if (mapUpdateFuture.valid()) mapUpdateFuture.get();  // (ready: shouldUpdateMap saw to that)
+        // the reference copies currentInput into the async call: the device-resident scan is handed over as a snapshot, so the next
+        // processInput can upload into the slot while the worker still reads this one
+        if (currentInput.onDevice) icp.snapshotScan();
+        mapUpdateFuture = std::async(std::launch::async, &Map::updateLocalPointCloud, &map, currentInput, currentPose, mapPostFilters, true);
+    } else {
+        map.updateLocalPointCloud(currentInput, currentPose, mapPostFilters);
+    }
     lastInputUpdatedMap = true;
 }
 

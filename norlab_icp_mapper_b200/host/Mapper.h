@@ -4,9 +4,11 @@
 // the YAML file itself (host/YamlConfig.h reads the subset of YAML the reference's configuration files use).
 #pragma once
 #include <atomic>
+#include <future>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <utility>
 #include <vector>
 
@@ -50,6 +52,7 @@ class Mapper {
     MapperModuleRegistrar registrar;
     bool lastInputUpdatedMap = false;
     bool deviceResidentInput = false;
+    mutable std::future<void> mapUpdateFuture;  // isOnline: the asynchronous Map::updateLocalPointCloud in flight (Mapper.h, Mapper.cpp:282)
 
     void fillRegistrar();
     void updateMap(const DataPoints& currentInput, const TransformationParameters& currentPose, double currentTimeStamp);
@@ -86,6 +89,17 @@ class Mapper {
     Map& getMapObject() { return map; }
     ICPSequence& getICP() { return icp; }
     bool lastInputTriggeredMapUpdate() const { return lastInputUpdatedMap; }
+    //! isOnline: block until the map update in flight (if any) and the queued cell-window updates are done; rethrows the update's exception
+    void waitForMapUpdate() {
+        if (mapUpdateFuture.valid()) mapUpdateFuture.get();
+        map.waitForWindowUpdates();
+    }
+    bool mapUpdateInFlight() const {
+        return mapUpdateFuture.valid() && mapUpdateFuture.wait_for(std::chrono::milliseconds(0)) != std::future_status::ready;
+    }
+    ~Mapper() {
+        if (mapUpdateFuture.valid()) mapUpdateFuture.wait();
+    }
 };
 
 }  // namespace norlab_icp_mapper_b200

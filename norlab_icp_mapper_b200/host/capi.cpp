@@ -204,6 +204,13 @@ int32_t b200mapper_process_raw_input(b200mapper* m, const float* features, int32
     });
 }
 
+int32_t b200mapper_wait_for_map_update(b200mapper* m) {
+    if (!m) return B200ICP_ERR_INVALID_ARG;
+    return guarded(m, [&] { m->mapper->waitForMapUpdate(); });
+}
+
+int32_t b200mapper_map_update_in_flight(b200mapper* m) { return (m && m->mapper->mapUpdateInFlight()) ? 1 : 0; }
+
 int32_t b200mapper_get_pose(b200mapper* m, float* pose) {
     if (!m || !pose) return B200ICP_ERR_INVALID_ARG;
     const TransformationParameters T = m->mapper->getPose();

@@ -17,7 +17,7 @@ SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "
            "b200mapper_process_input", "b200mapper_get_pose", "b200mapper_get_map", "b200mapper_get_new_local_map",
            "b200mapper_set_map", "b200mapper_get_is_mapping", "b200mapper_set_is_mapping", "b200mapper_trajectory_size",
            "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates", "b200mapper_process_raw_input",
-           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob", "b200mapper_create_from_yaml", "b200mapper_yaml_summary"]
+           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob", "b200mapper_create_from_yaml", "b200mapper_yaml_summary", "b200mapper_map_update_in_flight", "b200mapper_wait_for_map_update"]
 
 
 class InputFilter(C.Structure):
@@ -89,6 +89,8 @@ def load():
     L.b200mapper_process_raw_input.argtypes = [vp, vp, i32, i64, vp, C.c_double, C.POINTER(i64)]
     L.b200mapper_set_map_descriptors.argtypes = [vp, vp, i32, vp, vp, i64]
     L.b200mapper_get_map_prob.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.b200mapper_map_update_in_flight.argtypes = [vp]
+    L.b200mapper_wait_for_map_update.argtypes = [vp]
     L.b200mapper_get_pose.argtypes = [vp, vp]
     L.b200mapper_get_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.b200mapper_get_new_local_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
@@ -201,6 +203,14 @@ class Mapper:
         n = C.c_int64()
         self._check(self._L.b200mapper_process_raw_input(self._h, cloud.ctypes.data, self.n, len(cloud), T.ctypes.data, float(timeStamp), C.byref(n)))
         return n.value
+
+    def mapUpdateInFlight(self):
+        """isOnline: the asynchronous map update dispatched by an earlier processInput is still running."""
+        return bool(self._L.b200mapper_map_update_in_flight(self._h))
+
+    def waitForMapUpdate(self):
+        """isOnline: block until the map update in flight and the queued cell-window updates are done."""
+        self._check(self._L.b200mapper_wait_for_map_update(self._h))
 
     def getPose(self):
         T = np.zeros(self.n * self.n, np.float32)

@@ -221,3 +221,57 @@ def test_mapper_with_reading_normals_and_surface_normal_outlier_filter():
         assert n > 30_000 and np.isfinite(nrm).all()
     # the overlap (weighted ratio of used pairs) is lower with the normal filter: it really rejects pairs
     assert np.mean(outs["with"][1][1:]) < np.mean(outs["without"][1][1:]) - 0.01, (outs["with"][1], outs["without"][1])
+
+
+def _drive(n_scans, n_pts, seed=40):
+    world = synth.World3D(seed=seed, size=(120.0, 120.0), n_boxes=14)
+    rng = np.random.default_rng(seed)
+    for i in range(n_scans):
+        T_true = synth.make_T((1.2 * i, 0.3 * i, 1.5), (0, 0, 1.5 * i))
+        S, _ = world.sample(n_pts, np.random.default_rng(1000 + seed + i), noise=0.01, center=T_true[:3, 3], radius=55.0)
+        scan = synth.homog(synth.apply_T(np.linalg.inv(T_true), S))
+        T_est = T_true @ synth.make_T(rng.normal(0, 0.03, 3), rng.normal(0, 0.3, 3)) if i else T_true
+        yield scan, T_true, T_est.astype(np.float32)
+
+
+def test_online_mapper_runs_the_map_update_asynchronously():
+    """isOnline (Mapper.cpp:225-228,248-255,280-283; Map.cpp:29-57): processInput dispatches Map::updateLocalPointCloud to a worker
+    and returns; registrations go on against the old map until the worker's final setMap; a new update is refused while one is
+    running.  (1) Waiting for each update before the next scan reproduces the offline run bit for bit.  (2) Free running with scans
+    arriving at sensor rate: the processInput latency no longer contains the update (the worker does it between two scans; the device
+    work of one context is serialised, so back-to-back scans would queue behind it), every pose stays on the truth."""
+    import time
+    from norlab_icp_mapper_b200.mapper import Mapper
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=20)
+    kw = dict(updateCondition=("distance", 0.5), sensorMaxRange=80.0, minDistNewPoint=0.05, surfaceNormalKnn=10, reservePoints=1_500_000)
+    scans = list(_drive(14, 60_000))
+    runs = {}
+    for mode in ("offline", "online_stepwise", "online_free"):
+        m = Mapper(cfg, True, mode != "offline", True, False, **kw)
+        lat, errs, updated, in_flight_seen = [], [], 0, 0
+        for i, (scan, T_true, T_est) in enumerate(scans):
+            t0 = time.perf_counter()
+            m.processRawInput(scan, T_est, 0.1 * i)
+            lat.append((time.perf_counter() - t0) * 1e3)
+            updated += int(m.stats().map_updated)
+            in_flight_seen += int(m.mapUpdateInFlight())
+            if mode == "online_stepwise":
+                m.waitForMapUpdate()
+            elif mode == "online_free":
+                time.sleep(0.004)  # scans arrive at sensor rate: the worker updates the map between two scans
+            errs.append(synth.pose_error(m.getPose(), T_true))
+        m.waitForMapUpdate()
+        feat, nrm = m.getMap()
+        runs[mode] = dict(lat=np.array(lat), errs=errs, updated=updated, seen=in_flight_seen, feat=feat, nrm=nrm, traj=m.getTrajectory()[0])
+        m.close()
+    off, step, free = runs["offline"], runs["online_stepwise"], runs["online_free"]
+    # (1) same sequence of maps and poses when every update is awaited
+    assert step["updated"] == off["updated"] == len(scans)
+    assert np.array_equal(step["traj"], off["traj"])
+    assert np.array_equal(step["feat"], off["feat"]) and np.array_equal(step["nrm"], off["nrm"])
+    # (2) free running: poses on the truth; the update is off the caller's path
+    assert max(e[0] for e in free["errs"]) < 3e-3 and max(e[1] for e in free["errs"]) < 0.05, free["errs"]
+    assert free["updated"] <= len(scans) and len(free["feat"]) > 0.5 * len(off["feat"])
+    steady = slice(3, None)  # (the first scans create the map synchronously and warm the allocator)
+    assert np.median(free["lat"][steady]) < 0.8 * np.median(off["lat"][steady]), (np.median(free["lat"][steady]), np.median(off["lat"][steady]))
+    assert free["seen"] > 0  # an update really was in flight when processInput returned
