@@ -442,6 +442,19 @@ int32_t b200icp_map_download_extra(b200icp_ctx* ctx, int32_t global, float* extr
 int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, const float* normals,
                                   const float* prob, const float* extra, int32_t extra_rows);
 
+/* ---- spill tier under the device grid: the CellManager seam (CellManager.h:15-18; RAMCellManager.cpp, HardDriveCellManager.cpp) ----
+ * By default the cells the window leaves stay in HBM with their `loaded` flag cleared.  A Map configured with a CellManager
+ * (host RAM or disk, host/CellManager.h) moves them out instead: after b200icp_map_window(load = 0) it calls
+ *   b200icp_map_evict_parked   copy the parked points (every point with loaded = 0, insertion order) to host buffers and remove
+ *                              them from the device store; with features == NULL only *n_out (their count) is written
+ * groups them by 20 m cell id "row_col_aisle" and hands them to CellManager::saveCell; when the window comes back it
+ * concatenates CellManager::retrieveCell(id) into the local map with
+ *   b200icp_map_append_cloud   map.concatenate(cloud) for a host cloud with all its descriptors (loaded = 1). */
+int32_t b200icp_map_evict_parked(b200icp_ctx* ctx, float* features, float* normals, float* prob, float* extra, int64_t capacity,
+                                 int64_t* n_out);
+int32_t b200icp_map_append_cloud(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, const float* normals,
+                                 const float* prob, const float* extra, int32_t extra_rows, int64_t* n_added);
+
 /* b200icp_map_insert_point_distance for an input that carries `probabilityDynamic` (the chain DynamicPointsMapperModule +
  * PointDistanceMapperModule: map.concatenate keeps the descriptor because both clouds have it). */
 int32_t b200icp_map_insert_point_distance_prob(b200icp_ctx* ctx, const float* input, int32_t feature_rows, int64_t n_in,

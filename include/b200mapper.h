@@ -41,7 +41,10 @@ typedef struct b200mapper_config {
     float probability_dynamic_value;
     int32_t reserve_points;    /* > 0: pre-size the device map for this many points (no reference counterpart) */
     int32_t input_surface_normal_knn; /* input: SurfaceNormalDataPointsFilter{knn} on the reading (for SurfaceNormalOutlierFilter); 0 = absent */
-    int32_t reserved[2];
+    int32_t cell_spill;        /* where the cells the window leaves go: 0 stay in device memory (flag only; default), 1 RAMCellManager
+                                  (host memory), 2 HardDriveCellManager (the constructor's saveMapCellsOnHardDrive = true)        */
+    int32_t reserved[1];
+    char cell_folder[128];     /* HardDriveCellManager: folder of cell_<id>.vtk; empty = "/tmp/" like the reference                */
 } b200mapper_config;
 
 typedef struct b200mapper_stats {
@@ -80,6 +83,7 @@ int32_t b200mapper_map_update_in_flight(b200mapper* m);
 int32_t b200mapper_wait_for_map_update(b200mapper* m);
 int32_t b200mapper_get_pose(b200mapper* m, float* pose);                       /* Mapper::getPose        */
 int32_t b200mapper_get_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n); /* getMap */
+int32_t b200mapper_get_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n); /* Map::getLocalPointCloud */
 int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n,
                                      int32_t* available);                      /* Mapper::getNewLocalMap */
 int32_t b200mapper_set_map(b200mapper* m, const float* features, int32_t feature_rows, const float* normals, int64_t n);

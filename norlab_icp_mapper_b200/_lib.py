@@ -29,7 +29,7 @@ SYMBOLS = [
     "b200icp_scan_add_prob", "b200icp_scan_surface_normals", "b200icp_scan_select_extra", "b200icp_scan_append", "b200icp_scan_octree",
     "b200icp_scan_dynamic_points", "b200icp_scan_download_descriptors", "b200icp_map_set_extra", "b200icp_map_extra_rows",
     "b200icp_map_select_extra", "b200icp_map_download_extra", "b200icp_map_replace_local", "b200icp_map_insert_point_distance_prob",
-    "b200icp_scan_snapshot", "b200icp_map_begin_update", "b200icp_map_end_update", "b200icp_map_update_in_progress",
+    "b200icp_map_evict_parked", "b200icp_map_append_cloud", "b200icp_scan_snapshot", "b200icp_map_begin_update", "b200icp_map_end_update", "b200icp_map_update_in_progress",
     "b200icp_map_octree", "b200icp_map_cut_at_threshold", "b200icp_map_dynamic_points",
 ]
 
@@ -122,6 +122,8 @@ def load():
     L.b200icp_scan_dynamic_points.argtypes = [vp, vp, vp]
     L.b200icp_scan_download.argtypes = [vp, vp, i64, C.POINTER(i64)]
     L.b200icp_scan_download_descriptors.argtypes = [vp, vp, vp, vp, i64]
+    L.b200icp_map_evict_parked.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(i64)]
+    L.b200icp_map_append_cloud.argtypes = [vp, vp, i32, i64, vp, vp, vp, i32, C.POINTER(i64)]
     for name in ("b200icp_scan_snapshot", "b200icp_map_begin_update", "b200icp_map_end_update", "b200icp_map_update_in_progress"):
         getattr(L, name).argtypes = [vp]
     if L.b200icp_abi_version() != _abi.ABI_VERSION:

@@ -2043,6 +2043,60 @@ int32_t b200icp_map_replace_local(b200icp_ctx* ctx, const float* features, int32
     return B200ICP_OK;
 }
 
+/* ---- spill tier under the device grid (the CellManager seam, CellManager.h:15-18) ---- */
+int32_t b200icp_map_evict_parked(b200icp_ctx* ctx, float* features, float* normals, float* prob, float* extra, int64_t capacity, int64_t* n_out) {
+    if (!ctx || !n_out) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
+    MapStore& st = ctx->store;
+    *n_out = st.n - st.n_active;
+    if (!features || *n_out == 0) return B200ICP_OK;  // (count query)
+    if (capacity < *n_out) return fail(ctx, B200ICP_ERR_INVALID_ARG, "capacity too small");
+    if ((normals && !st.has_normals) || (prob && !st.has_prob) || (extra && st.extra_rows == 0))
+        return fail(ctx, B200ICP_ERR_INVALID_FIELD, "the map does not carry that descriptor");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int dim = ctx->cfg.dim, rows = dim + 1;
+    int64_t np = 0;
+    CK(store_extract_parked(st, build_index(ctx), dim, &np, s));
+    std::vector<float4> f((size_t)np);
+    CK(cudaMemcpyAsync(f.data(), st.feat2, f.size() * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    if (normals) CK(cudaMemcpyAsync(normals, st.nrm2, (size_t)np * dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (prob) CK(cudaMemcpyAsync(prob, st.prob2, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (extra) CK(cudaMemcpyAsync(extra, st.extra2, (size_t)np * st.extra_rows * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < np; ++i) {
+        features[i * rows + 0] = f[i].x;
+        features[i * rows + 1] = f[i].y;
+        if (dim == 3) features[i * rows + 2] = f[i].z;
+        features[i * rows + dim] = 1.f;
+    }
+    CK(store_remove_parked(st, build_index(ctx), dim, s));
+    *n_out = np;
+    return B200ICP_OK;
+}
+
+int32_t b200icp_map_append_cloud(b200icp_ctx* ctx, const float* features, int32_t feature_rows, int64_t n, const float* normals,
+                                 const float* prob, const float* extra, int32_t extra_rows, int64_t* n_added) {
+    if (!ctx) return B200ICP_ERR_INVALID_ARG;
+    B200_LOCK(ctx);
+    const int dim = ctx->cfg.dim;
+    if (feature_rows != dim + 1 || n < 0 || (n > 0 && !features)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "bad cloud");
+    if (extra && (extra_rows < 1 || extra_rows > B200ICP_MAX_EXTRA_ROWS)) return fail(ctx, B200ICP_ERR_INVALID_ARG, "extra_rows out of range");
+    if (n_added) *n_added = 0;
+    if (n == 0) return B200ICP_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevCloud in;
+    const int32_t rc = upload_input(ctx, features, feature_rows, n, normals, prob, &in);
+    if (rc != B200ICP_OK) return rc;
+    if (extra) {
+        CK(grow(ctx->d_stage_b, ctx->stage_b_bytes, (size_t)n * extra_rows * sizeof(float)));
+        CK(cudaMemcpyAsync(ctx->d_stage_b, extra, (size_t)n * extra_rows * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        in.extra = ctx->d_stage_b;
+        in.extra_rows = extra_rows;
+    }
+    return append_dev(ctx, in, n_added);
+}
+
 int32_t b200icp_scan_append(b200icp_ctx* ctx, int64_t* n_added) {
     if (!ctx) return B200ICP_ERR_INVALID_ARG;
     B200_LOCK(ctx);

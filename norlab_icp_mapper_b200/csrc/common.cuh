@@ -252,6 +252,8 @@ cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float thres
 // `in` and the `out_*` buffers must not alias; descriptors of `in` that have an output buffer are compacted with the points
 cudaError_t filter_cloud_device(MapStore& tmp, GridIndex& scratch, const DevCloud& in, int dim, const b200icp_filter* chain, int n_filters,
                                 float* out_feat, float* out_nrm, float* out_prob, float* out_extra, int64_t* n_out, cudaStream_t s);
+cudaError_t store_extract_parked(MapStore& m, GridIndex& scratch, int dim, int64_t* n_parked, cudaStream_t s);
+cudaError_t store_remove_parked(MapStore& m, GridIndex& scratch, int dim, cudaStream_t s);
 cudaError_t store_replace_loaded(MapStore& m, GridIndex& scratch, const DevCloud& in, int dim, cudaStream_t s);
 // out[i * out_rows + c] = in[i * in_rows + rows[c]]
 cudaError_t launch_select_rows(const float* d_in, int in_rows, int64_t n, float* d_out, int out_rows, const int* rows, cudaStream_t s);

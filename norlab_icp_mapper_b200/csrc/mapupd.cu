@@ -682,8 +682,8 @@ __global__ void __launch_bounds__(256) compact_store_kernel(const uint32_t* __re
         for (int c = 0; c < extra_rows; ++c) extra2[d * extra_rows + c] = extra[i * extra_rows + c];
 }
 
-// remove the store points whose flag in tmp_u32a is 1 (order of the survivors preserved)
-cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64_t* n_removed, cudaStream_t s) {
+// remove the store points whose flag in tmp_u32a is 1 (order of the survivors preserved); flagged_are_loaded: they count in n_active
+cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64_t* n_removed, cudaStream_t s, bool flagged_are_loaded = true) {
     cudaError_t e;
     const int64_t n = m.n;
     invert_flags_kernel<<<blocks_for(n), 256, 0, s>>>(m.tmp_u32a, (long long)n);  // now: keep flags
@@ -703,7 +703,7 @@ cudaError_t store_remove_flagged(MapStore& m, GridIndex& scratch, int dim, int64
     *n_removed = n - (int64_t)kept;
     m.nrm_epoch_ok = false;  // points moved / vanished: the incremental normals bookkeeping starts over
     m.n = kept;
-    m.n_active -= *n_removed;  // only loaded points are ever flagged
+    if (flagged_are_loaded) m.n_active -= *n_removed;
     return cudaGetLastError();
 }
 
@@ -882,6 +882,43 @@ cudaError_t store_replace_loaded(MapStore& m, GridIndex& scratch, const DevCloud
     m.nrm_epoch_ok = false;
     if (in.n == 0) return cudaSuccess;
     return store_append_all(m, in, dim, s);
+}
+
+namespace {
+__global__ void __launch_bounds__(256) parked_flags_kernel(const uint8_t* __restrict__ loaded, long long n, uint32_t* __restrict__ flag) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = loaded[i] ? 0u : 1u;
+}
+}  // namespace
+
+// Spill tier under the device grid (CellManager seam): the parked points (loaded = 0), compacted in insertion order into the
+// secondary buffers feat2 / nrm2 / prob2 / extra2 for the caller to copy out ...
+cudaError_t store_extract_parked(MapStore& m, GridIndex& scratch, int dim, int64_t* n_parked, cudaStream_t s) {
+    cudaError_t e;
+    *n_parked = 0;
+    if (m.n == 0 || m.n_active == m.n) return cudaSuccess;
+    const int64_t n = m.n;
+    if ((e = ensure_tmp(m, n + 1)) != cudaSuccess) return e;
+    parked_flags_kernel<<<blocks_for(n), 256, 0, s>>>(m.loaded, (long long)n, m.tmp_u32a);
+    if ((e = cudaMemsetAsync(m.tmp_u32a + n, 0, sizeof(uint32_t), s)) != cudaSuccess) return e;
+    if ((e = exclusive_sum(scratch, m.tmp_u32a, m.tmp_u32b, n + 1, s)) != cudaSuccess) return e;
+    uint32_t total = 0;
+    if ((e = cudaMemcpyAsync(&total, m.tmp_u32b + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    compact_store_kernel<<<blocks_for(n), 256, 0, s>>>(m.tmp_u32a, m.tmp_u32b, (long long)n, dim, m.feat, m.has_normals ? m.nrm : nullptr,
+                                                       m.has_prob ? m.prob : nullptr, m.loaded, m.feat2, m.nrm2, m.prob2, m.loaded2,
+                                                       m.extra_rows > 0 ? m.extra : nullptr, m.extra2, m.extra_rows);
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    *n_parked = total;
+    return cudaGetLastError();
+}
+
+// ... and their removal from the store (tmp_u32a still holds the flags of store_extract_parked)
+cudaError_t store_remove_parked(MapStore& m, GridIndex& scratch, int dim, cudaStream_t s) {
+    if (m.n == 0 || m.n_active == m.n) return cudaSuccess;
+    int64_t removed = 0;
+    cudaError_t e = store_remove_flagged(m, scratch, dim, &removed, s, /*flagged_are_loaded=*/false);
+    if (e == cudaSuccess) m.all_loaded = true;
+    return e;
 }
 
 cudaError_t store_cut_prob(MapStore& m, GridIndex& scratch, int dim, float threshold, int use_larger_than, int64_t* n_removed, cudaStream_t s) {

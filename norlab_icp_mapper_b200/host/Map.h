@@ -10,6 +10,9 @@
 #include <mutex>
 #include <vector>
 
+#include <unordered_set>
+
+#include "CellManager.h"
 #include "MapperModule.h"
 
 namespace norlab_icp_mapper_b200 {
@@ -43,6 +46,13 @@ class Map {
     std::atomic_bool localPointCloudEmpty{true};
     std::atomic_bool firstPoseUpdate{true};
     std::vector<std::shared_ptr<MapperModule>> mapperModuleVec;
+    // Spill tier (Map.cpp:20-27): null = the cells the window leaves stay in device memory (flag only); else they move to this
+    // manager when unloaded and come back through it when loaded.  loadedCellIds as in the reference (Map.h:44, Map.cpp:79-99).
+    std::unique_ptr<CellManager> cellManager;
+    std::mutex cellManagerLock;
+    std::unordered_set<std::string> loadedCellIds;
+    void spillUnloaded();
+    void loadSpilledCells(const Update& update);
     std::vector<Update> appliedUpdates;  // log of the slabs of the last updatePose (tests)
     // isOnline: cell-window updates are queued and applied by `updateThread` (Map.cpp:29-57,482-494)
     std::list<Update> updateList;
@@ -58,7 +68,8 @@ class Map {
     void scheduleUpdate(const Update& update);
 
    public:
-    Map(bool is3D, bool isOnline, ICPSequence& icp, std::mutex& icpMapLock);
+    Map(bool is3D, bool isOnline, ICPSequence& icp, std::mutex& icpMapLock, std::unique_ptr<CellManager> cellManager = nullptr);
+    CellManager* getCellManager() { return cellManager.get(); }
     ~Map();
     void updatePose(const TransformationParameters& pose);
     DataPoints getLocalPointCloud();

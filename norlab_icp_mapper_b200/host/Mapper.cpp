@@ -16,7 +16,7 @@ void Mapper::fillRegistrar() {  // Mapper.cpp:9-13
     registrar.add("DynamicPointsMapperModule", [](const Parameters& p) { return std::make_shared<DynamicPointsMapperModule>(p); });
 }
 
-Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMapping_, bool /*saveMapCellsOnHardDrive*/, int device)
+Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMapping_, bool saveMapCellsOnHardDrive, int device)
     : icp(config.icp, device),
       mapPostFilters(config.post),
       inputFilters(config.inputFilters),
@@ -27,7 +27,9 @@ Mapper::Mapper(const MapperConfig& config, bool is3D_, bool isOnline_, bool isMa
       is3D(is3D_),
       isOnline(isOnline_),
       isMapping(isMapping_),
-      map(is3D_, isOnline_, icp, icpMapLock),
+      map(is3D_, isOnline_, icp, icpMapLock,
+          saveMapCellsOnHardDrive ? std::unique_ptr<CellManager>(new HardDriveCellManager(is3D_ ? 3 : 2, config.cellFolder))
+                                  : (config.spillCellsToHostRam ? std::unique_ptr<CellManager>(new RAMCellManager()) : nullptr)),
       pose(TransformationParameters::Identity(is3D_ ? 4 : 3)),
       lastPoseWhereMapWasUpdated(TransformationParameters::Identity(is3D_ ? 4 : 3)) {
     if ((config.icp.dim == 3) != is3D_) throw InvalidParameter("icp.dim does not match is3D");

@@ -27,6 +27,9 @@ struct MapperConfig {
     float mapUpdateValue = 1.0f;                             // ... .value (DEFAULT_MAP_UPDATE_DISTANCE, Mapper.h:20)
     float sensorMaxRange = 200.0f;                           // mapper.sensorMaxRange (Mapper.cpp:152-160)
     std::vector<std::pair<std::string, Parameters>> mapperModules;  // mapper.mapperModule (Mapper.cpp:162-172); empty -> default
+    bool spillCellsToHostRam = false;  // cells the window leaves move to a RAMCellManager (host memory) instead of staying in HBM;
+                                       // the constructor's saveMapCellsOnHardDrive = true selects the HardDriveCellManager
+    std::string cellFolder = "/tmp/";  // ... and this is where it writes cell_<id>.vtk (HardDriveCellManager.h)
     std::vector<std::shared_ptr<MapperModule>> extraModules;        // ready-made module objects appended after the named ones (third-party
                                                                      // modules, e.g. a HostMapperModuleAdapter around a reference-signature one)
 };

@@ -97,7 +97,9 @@ int32_t b200mapper_create(const b200mapper_config* cfg, int32_t device, b200mapp
         mc.probabilityDynamicValue = cfg->probability_dynamic_value;
         mc.inputSurfaceNormalKnn = cfg->input_surface_normal_knn;
         m->dim = cfg->is_3d ? 3 : 2;
-        m->mapper.reset(new Mapper(mc, cfg->is_3d != 0, cfg->is_online != 0, cfg->is_mapping != 0, false, device));
+        mc.spillCellsToHostRam = cfg->cell_spill == 1;
+        if (cfg->cell_folder[0]) mc.cellFolder = cfg->cell_folder;
+        m->mapper.reset(new Mapper(mc, cfg->is_3d != 0, cfg->is_online != 0, cfg->is_mapping != 0, /*saveMapCellsOnHardDrive=*/cfg->cell_spill == 2, device));
         if (cfg->reserve_points > 0)
             ICPSequence::check(m->mapper->getICP().context(), b200icp_map_reserve(m->mapper->getICP().context(), cfg->reserve_points, cfg->surface_normal_knn));
     });
@@ -222,6 +224,13 @@ int32_t b200mapper_get_map(b200mapper* m, float* features, float* normals, int64
     if (!m || !n) return B200ICP_ERR_INVALID_ARG;
     int32_t rc2 = B200ICP_OK;
     const int32_t rc = guarded(m, [&] { rc2 = copy_out(m->mapper->getMap(), features, normals, capacity, n); });
+    return rc != B200ICP_OK ? rc : rc2;
+}
+
+int32_t b200mapper_get_local_map(b200mapper* m, float* features, float* normals, int64_t capacity, int64_t* n) {
+    if (!m || !n) return B200ICP_ERR_INVALID_ARG;
+    int32_t rc2 = B200ICP_OK;
+    const int32_t rc = guarded(m, [&] { rc2 = copy_out(m->mapper->getMapObject().getLocalPointCloud(), features, normals, capacity, n); });
     return rc != B200ICP_OK ? rc : rc2;
 }
 

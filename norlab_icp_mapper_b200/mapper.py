@@ -17,7 +17,7 @@ SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "
            "b200mapper_process_input", "b200mapper_get_pose", "b200mapper_get_map", "b200mapper_get_new_local_map",
            "b200mapper_set_map", "b200mapper_get_is_mapping", "b200mapper_set_is_mapping", "b200mapper_trajectory_size",
            "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates", "b200mapper_process_raw_input",
-           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob", "b200mapper_create_from_yaml", "b200mapper_yaml_summary", "b200mapper_map_update_in_flight", "b200mapper_wait_for_map_update"]
+           "b200mapper_set_map_descriptors", "b200mapper_get_map_prob", "b200mapper_create_from_yaml", "b200mapper_yaml_summary", "b200mapper_map_update_in_flight", "b200mapper_wait_for_map_update", "b200mapper_get_local_map"]
 
 
 class InputFilter(C.Structure):
@@ -58,7 +58,8 @@ class MapperConfig(C.Structure):
                 ("use_cut_at_threshold", C.c_int32), ("cut_threshold", C.c_float),
                 ("n_input_filters", C.c_int32), ("input_filters", InputFilter * 6),
                 ("add_probability_dynamic", C.c_int32), ("probability_dynamic_value", C.c_float),
-                ("reserve_points", C.c_int32), ("input_surface_normal_knn", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("reserve_points", C.c_int32), ("input_surface_normal_knn", C.c_int32), ("cell_spill", C.c_int32), ("reserved", C.c_int32 * 1),
+                ("cell_folder", C.c_char * 128)]
 
 
 class MapperStats(C.Structure):
@@ -89,6 +90,7 @@ def load():
     L.b200mapper_process_raw_input.argtypes = [vp, vp, i32, i64, vp, C.c_double, C.POINTER(i64)]
     L.b200mapper_set_map_descriptors.argtypes = [vp, vp, i32, vp, vp, i64]
     L.b200mapper_get_map_prob.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.b200mapper_get_local_map.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.b200mapper_map_update_in_flight.argtypes = [vp]
     L.b200mapper_wait_for_map_update.argtypes = [vp]
     L.b200mapper_get_pose.argtypes = [vp, vp]
@@ -123,7 +125,7 @@ class Mapper:
     def __init__(self, icp_config, is3D=True, isOnline=False, isMapping=True, saveMapCellsOnHardDrive=False, *,
                  updateCondition=("distance", 1.0), sensorMaxRange=200.0, minDistNewPoint=0.15, surfaceNormalKnn=0,
                  dynamicPoints=None, octree=None, cutAtThreshold=None, inputFilters=(), addProbabilityDynamic=None, reservePoints=0,
-                 inputSurfaceNormalKnn=0, device=0):
+                 inputSurfaceNormalKnn=0, cellSpill="device", cellFolder="", device=0):
         """dynamicPoints: _abi.DynamicParams or None; octree: (maxSizeByNode, samplingMethod) or None (then PointDistance);
         cutAtThreshold: threshold or None; inputFilters: InputFilter list; addProbabilityDynamic: value or None."""
         self._L = load()
@@ -161,6 +163,9 @@ class Mapper:
             cfg.add_probability_dynamic, cfg.probability_dynamic_value = 1, addProbabilityDynamic
         cfg.reserve_points = int(reservePoints)
         cfg.input_surface_normal_knn = int(inputSurfaceNormalKnn)  # input: SurfaceNormalDataPointsFilter{knn} on the reading
+        # cells the window leaves: stay in HBM ("device"), RAMCellManager ("ram"), HardDriveCellManager ("disk" / saveMapCellsOnHardDrive)
+        cfg.cell_spill = 2 if saveMapCellsOnHardDrive else {"device": 0, "ram": 1, "disk": 2}[cellSpill]
+        cfg.cell_folder = os.fspath(cellFolder).encode()
         self.dim = 3 if is3D else 2
         self.n = self.dim + 1
         h = C.c_void_p()
@@ -225,6 +230,15 @@ class Mapper:
         if n.value:
             self._check(self._L.b200mapper_get_map(self._h, feat.ctypes.data, nrm.ctypes.data, n.value, C.byref(n)))
         return feat, (None if np.isnan(nrm).all() else nrm)
+
+    def getLocalMap(self):
+        """Map::getLocalPointCloud as arrays: (features, normals or None)."""
+        st = self.stats()
+        n = C.c_int64()
+        feat = np.zeros((st.n_local, self.n), np.float32)
+        nrm = np.full((st.n_local, self.dim), np.nan, np.float32)
+        self._check(self._L.b200mapper_get_local_map(self._h, feat.ctypes.data, nrm.ctypes.data, st.n_local, C.byref(n)))
+        return feat[:n.value], (None if np.isnan(nrm).all() else nrm[:n.value])
 
     def getMapProbabilityDynamic(self):
         """The probabilityDynamic descriptor of getMap(), or None when the map does not carry it."""

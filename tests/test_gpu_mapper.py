@@ -275,3 +275,52 @@ def test_online_mapper_runs_the_map_update_asynchronously():
     steady = slice(3, None)  # (the first scans create the map synchronously and warm the allocator)
     assert np.median(free["lat"][steady]) < 0.8 * np.median(off["lat"][steady]), (np.median(free["lat"][steady]), np.median(off["lat"][steady]))
     assert free["seen"] > 0  # an update really was in flight when processInput returned
+
+
+def test_cell_manager_spill_tiers_hold_the_same_map(tmp_path):
+    """The CellManager seam (CellManager.h:15-18): with a RAMCellManager or the HardDriveCellManager the cells the window leaves
+    move out of device memory (b200icp_map_evict_parked) and come back when the window returns (b200icp_map_append_cloud); the local
+    map after every scan and the global map at the end are the same point sets as with the default, where they stay in HBM."""
+    from norlab_icp_mapper_b200.mapper import Mapper
+    cfg = make_config(dim=3, knn=1, max_dist=2.0, outliers=(("trimmed", 0.85),), minimizer="identity", max_iteration_count=1)
+    rng = np.random.default_rng(3)
+    pts = synth.homog(np.c_[rng.uniform(-250, 250, 120_000), rng.uniform(-250, 250, 120_000), rng.uniform(-30, 30, 120_000)])
+    nrm = rng.normal(size=(len(pts), 3)).astype(np.float32)
+    scan = synth.homog(rng.normal(0, 5, (500, 3)))
+    # out and back: cells are spilled, then loaded again
+    path = [(-200 + 26.0 * k, -150 + 18.0 * k, 0.0) for k in range(16)] + [(190 - 26.0 * k, 120 - 18.0 * k, 0.0) for k in range(16)]
+    ms = {"device": Mapper(cfg, True, False, False, False, sensorMaxRange=30.0),
+          "ram": Mapper(cfg, True, False, False, False, sensorMaxRange=30.0, cellSpill="ram"),
+          "disk": Mapper(cfg, True, False, False, True, sensorMaxRange=30.0, cellFolder=str(tmp_path))}
+    for m in ms.values():
+        m.setMap(pts, nrm)
+
+    def canon(feat, normals):
+        order = np.lexsort(feat[:, :3].T)
+        return feat[order], normals[order]
+    files_seen = 0
+    for k, pos in enumerate(path):
+        T = synth.make_T(pos, (0, 0, 5.0 * k)).astype(np.float32)
+        st = {}
+        for name, m in ms.items():
+            m.processInput(scan, T, 0.1 * k)
+            st[name] = m.stats()
+        files_seen = max(files_seen, len(list(tmp_path.glob("cell_*.vtk"))))
+        assert st["ram"].n_local == st["disk"].n_local == st["device"].n_local
+        assert st["device"].n_global == len(pts)                      # parked cells stay in HBM
+        assert st["ram"].n_global == st["ram"].n_local                 # ... or leave it
+        assert st["disk"].n_global == st["disk"].n_local
+        if k % 5 == 0:
+            ref = canon(*ms["device"].getLocalMap())
+            for name in ("ram", "disk"):
+                got = canon(*ms[name].getLocalMap())
+                assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), (k, name)
+    assert files_seen > 10  # the hard-drive manager really wrote cell_<row>_<col>_<aisle>.vtk files
+    ref = canon(*ms["device"].getMap())
+    assert len(ref[0]) == len(pts)
+    for name in ("ram", "disk"):
+        got = canon(*ms[name].getMap())
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), name
+    for m in ms.values():
+        m.close()
+    assert not list(tmp_path.glob("cell_*.vtk"))  # ~HardDriveCellManager removes its files (HardDriveCellManager.cpp:4-7)
