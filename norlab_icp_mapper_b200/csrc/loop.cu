@@ -99,7 +99,7 @@ constexpr int kSmallCand = 128;  // up to here the candidates are finished by fo
 // atomics, and a candidate list appended to with one atomic per warp that holds candidates.
 //  * error sums of the pairs whose fate is certain: fixed point (associative: the result does not depend on the arrival
 //    order, so poses stay run-to-run bitwise deterministic), instead of 148 per-CTA records every CTA had to read back;
-//  * the three counts (pairs below / inside / above the window) in three more slots of the same array;
+//  * the counts (pairs below / inside / above the quantile's window, list entries) in four more slots of the same array;
 //  * candidates (pairs inside the window): tuple (p, dist2 bits | v) at a position handed out by the `inside` counter.  The
 //    list order depends on arrival, so after the barrier the kept candidates are summed in fixed point as well (a coarser
 //    grid: one 32-bit warp reduction per sum).
@@ -108,8 +108,8 @@ constexpr int kSmallCand = 128;  // up to here the candidates are finished by fo
 constexpr int kIsumStride = 16;  // unsigned long long per slot line
 constexpr int kIsumBufs = 3;
 constexpr int kSlotFlag = kAccSlots - 1;  // a sum left the fixed-point range somewhere
-constexpr int kSlotBelow = kAccSlots, kSlotAbove = kAccSlots + 1, kSlotCand = kAccSlots + 2;
-constexpr int kIsumSlots = kAccSlots + 3;
+constexpr int kSlotBelow = kAccSlots, kSlotAbove = kAccSlots + 1, kSlotCand = kAccSlots + 2, kSlotRank = kAccSlots + 3;
+constexpr int kIsumSlots = kAccSlots + 4;
 constexpr size_t kFastCandOff = 0;                                                          // float4 [2][kCandCap][2]
 constexpr size_t kFastCandEnd = kFastCandOff + 2 * (size_t)kCandCap * 2 * sizeof(float4);
 constexpr size_t kFastIsumOff = (kFastCandEnd + 127) / 128 * 128;                           // unsigned long long [3][kIsumSlots][16]
@@ -706,8 +706,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     wlo = st.win_lo;
                     whi = st.win_hi;
                 } else {
-                    // (Median scales the limit by a factor: the uncertain pairs are not the quantile's bucket -> general path)
-                    if ((variant_flags & (64 | 8)) || prm.outlier_kind[prm.quantile_filter] != B200ICP_OUTLIER_TRIMMED_DIST) continue;
+                    if ((variant_flags & (64 | 8)) || (prm.outlier_kind[prm.quantile_filter] != B200ICP_OUTLIER_TRIMMED_DIST &&
+                                                       prm.outlier_kind[prm.quantile_filter] != B200ICP_OUTLIER_MEDIAN_DIST))
+                        continue;
                     // level-0 histogram (bits [30:19] of dist2) of this CTA's slice, and the fine one (64 bins per bucket) over the
                     // buckets around the previous limit -> global -> barrier -> bin of the quantile
                     const bool fine_ok = st.have_limit && st.limit > 0.f && st.limit < 1.0e30f && !(variant_flags & 0x20000);
@@ -790,7 +791,18 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             unsigned long long* const stale_isum = isum_base + (size_t)((n_runs + 2) % kIsumBufs) * kIsumSlots * kIsumStride;
             n_runs += 1;
             float4* my_cand = reinterpret_cast<float4*>(fastws + kFastCandOff) + (size_t)par * kCandCap * 2;
-            uint32_t c_below = 0, c_above = 0;
+            // Two windows: [wlo, whi] holds the QUANTILE (its rank is counted), [llo, lhi] holds the LIMIT below which a pair is kept.
+            // Trimmed: the same window.  Median: limit = factor * median, so the limit's window is the median's scaled (one ulp wider
+            // on each side than the rounded products: fp32 multiplication is monotonic).  A pair in either window is a candidate.
+            const bool is_median = use_quantile && prm.outlier_kind[prm.quantile_filter] == B200ICP_OUTLIER_MEDIAN_DIST;
+            const float mfac = is_median ? prm.outlier_param[prm.quantile_filter] : 1.f;
+            uint32_t llo = wlo, lhi = whi;
+            if (is_median) {
+                const uint32_t a = __float_as_uint(mfac * __uint_as_float(wlo)), b = __float_as_uint(mfac * __uint_as_float(whi));
+                llo = a > 0u ? a - 1u : 0u;
+                lhi = b < 0x7f800000u ? b + 1u : 0x7f800000u;
+            }
+            uint32_t c_below = 0, c_above = 0, c_rank = 0;
             if (tid < 4) s_tot[tid] = 0u;
             if (lane < NS) s_part[warp][lane] = 0.0;
             // C: outlier weights + error sums of what is certain + candidate tuples (thread per entry, from the cache)
@@ -813,10 +825,12 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     const int pos = __float_as_int(pp.w);
                     if (pos >= 0 && d < CUDART_INF_F) {
                         const uint32_t bits = __float_as_uint(d);
-                        const int cls = bits < wlo ? 0 : (bits <= whi ? 1 : 2);
-                        c_below += cls == 0;
-                        c_above += cls == 2;
-                        if (cls != 2) {
+                        const int cls = bits < llo ? 0 : (bits <= lhi ? 1 : 2);  // kept for sure / candidate for the limit / dropped for sure
+                        const bool in_rank = bits >= wlo && bits <= whi;         // candidate for the quantile
+                        c_below += bits < wlo;
+                        c_above += bits > whi;
+                        c_rank += in_rank;
+                        if (cls != 2 || in_rank) {
                             const float wo = other_filters_weight(prm, d, st.T, sn_active ? prm.rnrm + qi : nullptr, nv);
                             float3 p = make_float3(CUDART_NAN_F, 0.f, 0.f);
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -829,7 +843,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                                     v = pp;
                                 if (cls == 0) add_pair<MIN>(acc, wo, p, v);
                             }
-                            if (cls == 1) {  // a candidate dropped by another filter still takes part in the quantile: p.x = NaN marks it
+                            if (cls == 1 || in_rank) {  // a candidate dropped by another filter still takes part in the quantile: p.x = NaN marks it
                                 is_cand = true;
                                 ta = make_float4(p.x, p.y, p.z, __uint_as_float(bits));
                                 tb = v;
@@ -862,15 +876,17 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             // ---- publish, ONE barrier, finish redundantly ---------------------------------------------
             if (stamper) B200_STAMP(gst, 28);
             {
-                uint32_t a = c_below, c = c_above;
+                uint32_t a = c_below, c = c_above, r = c_rank;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     a += __shfl_xor_sync(0xffffffffu, a, o);
                     c += __shfl_xor_sync(0xffffffffu, c, o);
+                    r += __shfl_xor_sync(0xffffffffu, r, o);
                 }
                 if (lane == 0) {
                     if (a) atomicAdd(&s_tot[0], a);
                     if (c) atomicAdd(&s_tot[2], c);
+                    if (r) atomicAdd(&s_tot[1], r);
                 }
             }
             __syncthreads();
@@ -885,6 +901,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 if (s_tot[0]) atomicAdd(my_isum + kSlotBelow * kIsumStride, (unsigned long long)s_tot[0]);
             } else if (tid == 33) {
                 if (s_tot[2]) atomicAdd(my_isum + kSlotAbove * kIsumStride, (unsigned long long)s_tot[2]);
+            } else if (tid == 34) {
+                if (s_tot[1]) atomicAdd(my_isum + kSlotRank * kIsumStride, (unsigned long long)s_tot[1]);
             }
             if (stamper) B200_STAMP(gst, 22);
             B200_CTA_STAMP(partials, 4);
@@ -905,14 +923,15 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             __syncthreads();
             if (stamper) B200_STAMP(gst, 29);
             const uint32_t n_below = (uint32_t)s_isum[kSlotBelow], n_above = (uint32_t)s_isum[kSlotAbove];
-            const uint32_t n_cand = (uint32_t)umin64(s_isum[kSlotCand], 0x7fffffffull);
-            const uint32_t total = n_below + n_cand + n_above;
+            const uint32_t n_cand = (uint32_t)umin64(s_isum[kSlotCand], 0x7fffffffull);  // list entries (either window)
+            const uint32_t n_rank = (uint32_t)s_isum[kSlotRank];                          // pairs inside the quantile's window
+            const uint32_t total = n_below + n_rank + n_above;
             uint32_t rank = 0;
             bool ok = true;
             if (use_quantile) {
                 rank = (prm.quantile == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * prm.quantile);
                 if (total && rank >= total) rank = total - 1u;
-                ok = total > 0 && n_cand <= (uint32_t)kCandCap && rank >= n_below && rank < n_below + n_cand;
+                ok = total > 0 && n_cand <= (uint32_t)kCandCap && rank >= n_below && rank < n_below + n_rank;
             }
             dbg_path = dbg_path * 10u + (ok ? (stage == 0 ? 1u : 3u) : (stage == 0 ? 2u : 4u));
             dbg_ncand = n_cand;
@@ -927,16 +946,17 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 // warps share that work (candidate = tid % 128, an eighth of the keys each)
                 const bool have = use_quantile && (uint32_t)tid < n_cand;  // (tid < 128 only)
                 const uint32_t mine = __float_as_uint(ca[0].w);
+                const bool rank_role = have && mine >= wlo && mine <= whi, sum_role = have && mine >= llo && mine <= lhi;
                 if (tid < kSmallCand) {
-                    sh2[tid] = have ? mine : 0xffffffffu;  // (padding: neither below nor equal to any distance)
-                    sh2[kSmallCand + tid] = 0u;            // less | le << 16
+                    sh2[tid] = rank_role ? mine : 0xffffffffu;  // (padding: neither below nor equal to any distance)
+                    sh2[kSmallCand + tid] = 0u;                 // less | le << 16
                 }
                 __syncthreads();
                 if (stamper) B200_STAMP(gst, 1);
                 if (use_quantile) {
                     const int c = tid & (kSmallCand - 1), part = tid >> 7;  // 8 parts of 16 keys
                     const uint32_t key = sh2[c];
-                    if ((uint32_t)c < n_cand && (uint32_t)(part * 16) < n_cand) {
+                    if (key != 0xffffffffu && (uint32_t)(part * 16) < n_cand) {
                         const uint4* keys = reinterpret_cast<const uint4*>(sh2) + part * 4;
                         uint32_t less = 0, le = 0;
 #pragma unroll
@@ -952,13 +972,19 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 if (stamper) B200_STAMP(gst, 2);
                 if (tid < kSmallCand) {
                     long long mine_tot = 0ll;
-                    if ((uint32_t)(warp * 32) < n_cand && use_quantile) {  // (warp-uniform)
+                    if (use_quantile) {
                         const uint32_t r = rank - n_below;
                         const uint32_t packed = sh2[kSmallCand + tid];
                         const uint32_t less = packed & 0xffffu, le = packed >> 16;
-                        // kept: fewer than r + 1 keys are strictly smaller; the quantile is the key with less <= r < le
-                        if (have && less <= r && r < le) s_limit_bits = mine;  // (every such candidate holds the same bits)
-                        const bool kept = have && less <= r && ca[0].x == ca[0].x;
+                        // the quantile is the key with less <= r < le (every such candidate holds the same bits)
+                        if (rank_role && less <= r && r < le) s_limit_bits = mine;
+                    }
+                    named_bar_sync(1, kSmallCand);
+                    if ((uint32_t)(warp * 32) < n_cand && use_quantile) {  // (warp-uniform)
+                        // kept: at or below the limit -- the quantile itself (Trimmed) or factor x the median (Median)
+                        const uint32_t q_bits = s_limit_bits;
+                        const uint32_t limit_bits = is_median ? __float_as_uint(mfac * __uint_as_float(q_bits)) : q_bits;
+                        const bool kept = sum_role && mine <= limit_bits && ca[0].x == ca[0].x;
                         float acc2[NS];
 #pragma unroll
                         for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
@@ -1015,7 +1041,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     __syncthreads();
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        if (have[j]) {
+                        if (have[j] && __float_as_uint(ca[j].w) >= wlo && __float_as_uint(ca[j].w) <= whi) {  // (the quantile's candidates)
                             const uint32_t o = __float_as_uint(ca[j].w) - wlo;
                             if (((o ^ prefix) >> (shift + 10)) == 0u) atomicAdd(&sh2[(o >> shift) & 1023u], 1u);
                         }
@@ -1026,8 +1052,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     prefix |= s_bin << shift;
                     __syncthreads();
                 }
-                const uint32_t limit_bits = wlo + prefix;
-                if (tid == 0) s_limit_bits = limit_bits;
+                const uint32_t q_bits = wlo + prefix;
+                if (tid == 0) s_limit_bits = q_bits;
+                const uint32_t limit_bits = is_median ? __float_as_uint(mfac * __uint_as_float(q_bits)) : q_bits;
                 long long mine_tot = 0ll;
                 if ((uint32_t)(warp * 32) < n_cand) {  // (warp-uniform)
                     int f[NS];
@@ -1036,7 +1063,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     bool range_ok = true;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        if (have[j] && __float_as_uint(ca[j].w) <= limit_bits && ca[j].x == ca[j].x) {
+                        if (have[j] && __float_as_uint(ca[j].w) >= llo && __float_as_uint(ca[j].w) <= limit_bits && ca[j].x == ca[j].x) {
                             float acc2[NS];
 #pragma unroll
                             for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
@@ -1277,11 +1304,12 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         }  // !fast_done
         if (tid < 32) {
             if (tid == 0) {
-                // window for the next iteration's one-barrier attempt: centred on this limit, half-width from
-                // the last change of the limit (Trimmed only: Median scales the limit by a factor)
+                // window for the next iteration's one-barrier attempt: centred on this quantile (Trimmed: the limit itself; Median:
+                // the median, the limit's window follows from it), half-width from its last change
                 const float prev = st.limit;
                 st.win_valid = 0;
-                if (use_quantile && prm.outlier_kind[prm.quantile_filter] == B200ICP_OUTLIER_TRIMMED_DIST && st.have_limit &&
+                if (use_quantile && (prm.outlier_kind[prm.quantile_filter] == B200ICP_OUTLIER_TRIMMED_DIST ||
+                                     prm.outlier_kind[prm.quantile_filter] == B200ICP_OUTLIER_MEDIAN_DIST) && st.have_limit &&
                     qlimit > 0.f && qlimit < 1.0e30f) {
                     const float a = fmaxf(win_gain * fabsf(qlimit - prev), win_floor * qlimit);
                     if (a <= win_max * qlimit) {

@@ -170,6 +170,8 @@ def test_quantile_fallback_path_is_identical(pair3d):
     dict(outliers=(("min_dist", 0.01), ("trimmed", 0.9)), minimizer="point_to_plane", max_iteration_count=20),
     dict(outliers=(("max_dist", 0.5),), minimizer="point_to_plane", max_iteration_count=20),
     dict(outliers=(), minimizer="point_to_point", max_iteration_count=15),
+    dict(outliers=(("median", 3.0),), minimizer="point_to_plane", max_iteration_count=12),
+    dict(outliers=(("median", 0.8), ("max_dist", 0.9)), minimizer="point_to_plane", max_iteration_count=12),
 ])
 def test_one_barrier_iterations(pair3d, chain, monkeypatch):
     """The loop kernel's one-barrier iteration (quantile window predicted from the previous limit), its
@@ -178,7 +180,7 @@ def test_one_barrier_iterations(pair3d, chain, monkeypatch):
     pairs -- also when the window policy is made so narrow that most predictions fail and the kernel falls
     back mid-iteration; poses agree to summation-order rounding."""
     from norlab_icp_mapper_b200.icp import ICP
-    has_quantile = any(k == "trimmed" for k, _ in chain["outliers"])
+    has_quantile = any(k in ("trimmed", "median") for k, _ in chain["outliers"])  # (Median: the limit's window is the median's, scaled)
     outs = {}
     for name, variant, window in (("fast", 0, None), ("general", 16, None), ("narrow", 0, "0.0,0.00001,1.0"), ("wide", 0, "8.0,0.05,0.5"),
                                   ("always_search", 32, None), ("three_barrier", 16 | 64, None)):
@@ -201,7 +203,7 @@ def test_one_barrier_iterations(pair3d, chain, monkeypatch):
     # the match cache only skips searches whose outcome is proven: with it disabled (bit 5) every bit is the same
     assert np.array_equal(outs["fast"][0], outs["always_search"][0]) and outs["fast"][1:5] == outs["always_search"][1:5]
     assert outs["always_search"][5] >= (outs["fast"][4] - 1) * len(pair3d["reading"]) > outs["fast"][5] > 0
-    assert outs["fast"][3] > (5 if has_quantile else 0), outs["fast"]
+    assert outs["fast"][3] + outs["fast"][6] > (5 if has_quantile else 0), outs["fast"]  # windowed iterations (one or two barriers)
     for name in ("fast", "narrow", "wide", "three_barrier"):
         er, et = synth.pose_error(outs[name][0], outs["general"][0])
         assert er <= 1e-6 and et <= 1e-5, (name, er, et)
