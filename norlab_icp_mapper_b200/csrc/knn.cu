@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) nn1_cold_kernel(GridView g, const float4*
     float bd = CUDART_INF_F, sd = CUDART_INF_F;
     int bp = -1;
     const bool finite_q = (fabsf(qx) < 3.0e38f) && (fabsf(qy) < 3.0e38f) && (fabsf(qz) < 3.0e38f);
-    if (finite_q) search_ball4(g, qx, qy, qz, max_r2, 0.f, bd, bp, sd, lig, gmask);
+    if (finite_q) search_ball4<4>(g, qx, qy, qz, max_r2, 0.f, bd, bp, sd, lig, gmask);
 #pragma unroll
     for (int o = 2; o > 0; o >>= 1) {
         const float od = __shfl_xor_sync(gmask, bd, o);

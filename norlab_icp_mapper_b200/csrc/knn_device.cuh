@@ -412,32 +412,38 @@ __device__ __forceinline__ float row_gap2(const GridView& g, float uy, float uz,
     return gy * gy + gz * gz;
 }
 
-// The runs [s, e) the four lanes of a group hold (one cell row each, possibly empty), concatenated, are scanned by the
-// four lanes together: balanced, and a lane quartet reads 64 contiguous bytes.  Returns the group-wide best distance.
-__device__ __forceinline__ float scan_runs4(const GridView& g, float qx, float qy, float qz, uint32_t s, uint32_t e, float& bd, int& bp, float& sd,
-                                            int lig, unsigned gmask) {
-    constexpr int G = 4;
+// The runs [s, e) the four ROW lanes of a group hold (one cell row each, possibly empty), concatenated, are scanned by the
+// SL lanes of the group together: balanced, and neighbouring lanes read contiguous bytes.  Returns the group-wide best distance.
+// SL = 4: a lane quartet per query (the row lanes are the scanning lanes).  SL = 32: a whole warp per query, rows still described
+// by its lanes 0..3 -- one round trip for a run of up to 32 points instead of one per 4, for the handful of queries a converged
+// iteration still has to search (their latency is what every other CTA waits for at the barrier).
+template <int SL>
+__device__ __forceinline__ float scan_runs(const GridView& g, float qx, float qy, float qz, uint32_t s, uint32_t e, float& bd, int& bp, float& sd,
+                                           int lane_s, unsigned gmask) {
     const uint32_t n = e - s;
-    const uint32_t n0 = __shfl_sync(gmask, n, 0, G), n1 = __shfl_sync(gmask, n, 1, G), n2 = __shfl_sync(gmask, n, 2, G), n3 = __shfl_sync(gmask, n, 3, G);
+    const uint32_t n0 = __shfl_sync(gmask, n, 0, SL), n1 = __shfl_sync(gmask, n, 1, SL), n2 = __shfl_sync(gmask, n, 2, SL), n3 = __shfl_sync(gmask, n, 3, SL);
     const uint32_t p1 = n0, p2 = p1 + n1, p3 = p2 + n2, N = p3 + n3;
-    const uint32_t o0 = __shfl_sync(gmask, s, 0, G), o1 = __shfl_sync(gmask, s, 1, G) - p1, o2 = __shfl_sync(gmask, s, 2, G) - p2,
-                   o3 = __shfl_sync(gmask, s, 3, G) - p3;
+    const uint32_t o0 = __shfl_sync(gmask, s, 0, SL), o1 = __shfl_sync(gmask, s, 1, SL) - p1, o2 = __shfl_sync(gmask, s, 2, SL) - p2,
+                   o3 = __shfl_sync(gmask, s, 3, SL) - p3;
 #pragma unroll 2
-    for (uint32_t k = (uint32_t)lig; k < N; k += G) {
+    for (uint32_t k = (uint32_t)lane_s; k < N; k += SL) {
         const uint32_t j = k + (k >= p2 ? (k >= p3 ? o3 : o2) : (k >= p1 ? o1 : o0));
         test_point(qx, qy, qz, __ldg(g.pts + j), j, bd, bp, sd);
     }
     float v = bd;
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
+    for (int o = SL / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(gmask, v, o));
     return v;
 }
 
 // bd / bp / sd start at inf / -1 / inf in every lane: the previous match only bounds the ball (tau0) and is found
 // again by the scan like any other point.
+template <int SL>
 __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float qy, float qz, float tau0, float m, float& bd, int& bp,
-                                             float& sd, int lig, unsigned gmask) {
-    constexpr int G = 4;
+                                             float& sd, int lane_s, unsigned gmask) {
+    constexpr int G = 4;  // rows described per round
+    const int lig = lane_s;
+    const bool row_lane = lane_s < G;
     const float lim = 1.0e8f;
     const float ux = fminf(fmaxf((qx - g.ox) * g.inv_h, -lim), lim);
     const float uy = fminf(fmaxf((qy - g.oy) * g.inv_h, -lim), lim);
@@ -451,12 +457,12 @@ __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float 
     {
         const int y = (lig & 1) ? y1 : cy, z = (lig & 2) ? z1 : cz;
         uint32_t s = 0, e = 0;
-        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+        if (row_lane && y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
             const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
             const float cov = sqrtf(gb) + m;
             if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
         }
-        gb = fminf(scan_runs4(g, qx, qy, qz, s, e, bd, bp, sd, lig, gmask), tau0);
+        gb = fminf(scan_runs<SL>(g, qx, qy, qz, s, e, bd, bp, sd, lane_s, gmask), tau0);
     }
     // phase 2: the rest of the (tightened) ball's cover -- usually nothing; four rows at a time, same scan
     const float rt = fminf((sqrtf(gb) + m) * g.inv_h + slack, 3.0e8f);
@@ -471,7 +477,7 @@ __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float 
     for (int base = 0; base < nrows; base += G) {  // group-uniform trip count
         const int r = base + lig;
         uint32_t s = 0, e = 0;
-        if (r < nrows) {
+        if (row_lane && r < nrows) {
             const int y = ylo + r % wy, z = zlo + r / wy;
             if (!((y == cy || y == y1) && (z == cz || z == z1))) {  // (those were phase 1)
                 const float gyz2 = row_gap2(g, uy, uz, slack, y, z);
@@ -479,7 +485,7 @@ __device__ __forceinline__ void search_ball4(const GridView& g, float qx, float 
                 if (gyz2 <= cov * cov) row_run(g, ux, slack, y, z, gyz2, cov * cov, s, e);
             }
         }
-        gb = fminf(scan_runs4(g, qx, qy, qz, s, e, bd, bp, sd, lig, gmask), tau0);
+        gb = fminf(scan_runs<SL>(g, qx, qy, qz, s, e, bd, bp, sd, lane_s, gmask), tau0);
     }
 }
 

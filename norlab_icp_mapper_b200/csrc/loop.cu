@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <type_traits>
 
 #include "icp_device.cuh"
 #include "knn_device.cuh"
@@ -602,14 +603,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 // groups' instruction paths per round, not their sum -- this phase is issue-bound, not memory-bound.
                 // Batches of 8 consecutive list entries are handed to whole warps dynamically (difficulty is spatially
                 // coherent, a static deal leaves the CTA waiting for its unluckiest warp).
-                while (true) {
-                    uint32_t i0 = 0;
-                    if (lane == 0) i0 = atomicAdd(&s_nlist, 32u / kLoopG);
-                    i0 = __shfl_sync(0xffffffffu, i0, 0);
-                    if (i0 >= n_list) break;  // warp-uniform
-                    const uint32_t i = i0 + (uint32_t)(lane / kLoopG);
-                    if (i < n_list) {
-                    const int es = (int)s_list[i];
+                // one listed query, searched by SL lanes (lane_s = this lane's index among them, smask = their mask)
+                auto search_entry = [&](auto sl_tag, int es, int lane_s, unsigned smask) {
+                    constexpr int SL = decltype(sl_tag)::value;
                     const bool cs = es < kCacheCap;
                     const long long qs = qi_of(es);
                     const float4 r4 = cs ? s_r4[es] : __ldg(reading + qs);
@@ -629,13 +625,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     const float m = want <= margin_max ? fmaxf(want, margin_min) : 0.f;
                     float bd = CUDART_INF_F, sd = CUDART_INF_F;
                     int bp = -1;
-                    search_ball4(g, qn.x, qn.y, qn.z, tau0, m, bd, bp, sd, lig, gmask);
+                    search_ball4<SL>(g, qn.x, qn.y, qn.z, tau0, m, bd, bp, sd, lane_s, smask);
                     float gbd = bd;
                     int gbp = bp;
 #pragma unroll
-                    for (int o = kLoopG / 2; o > 0; o >>= 1) {
-                        const float od = __shfl_xor_sync(gmask, gbd, o);
-                        const int op = __shfl_xor_sync(gmask, gbp, o);
+                    for (int o = SL / 2; o > 0; o >>= 1) {
+                        const float od = __shfl_xor_sync(smask, gbd, o);
+                        const int op = __shfl_xor_sync(smask, gbp, o);
                         if (od < gbd || (od == gbd && (unsigned)op < (unsigned)gbp)) {
                             gbd = od;
                             gbp = op;
@@ -643,14 +639,14 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     }
                     float gsd = (bp != gbp) ? bd : sd;  // a lane whose best lost is looking at another point (and bd <= sd)
 #pragma unroll
-                    for (int o = kLoopG / 2; o > 0; o >>= 1) gsd = fminf(gsd, __shfl_xor_sync(gmask, gsd, o));
+                    for (int o = SL / 2; o > 0; o >>= 1) gsd = fminf(gsd, __shfl_xor_sync(smask, gsd, o));
                     const float cover = sqrtf(fminf(gbd, tau0)) + m;  // every lane covered at least this radius
                     if (!(gbd <= prm.max_r2)) {  // nothing within maxDist: whatever was seen beyond it is an "other" point
                         gsd = fminf(gsd, gbd);
                         gbd = CUDART_INF_F;
                         gbp = -1;
                     }
-                    if (lig == 0) {
+                    if (lane_s == 0) {
                         float L = fminf(sqrtf(gsd), cover);
                         L -= 2e-6f * L;
                         if (gbp < 0 || gbp == pos) {
@@ -666,7 +662,19 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         }
                         *pd2 = gbd;
                     }
-                    }
+                };
+                if (n_list <= (uint32_t)kLoopWarps && !(variant_flags & 0x400000)) {
+                    // a handful of queries (converged iterations): one per warp, all 32 lanes scanning -- their latency is what the
+                    // other 147 CTAs wait for at the barrier
+                    if ((uint32_t)warp < n_list) search_entry(std::integral_constant<int, 32>(), (int)s_list[warp], lane, 0xffffffffu);
+                } else
+                while (true) {
+                    uint32_t i0 = 0;
+                    if (lane == 0) i0 = atomicAdd(&s_nlist, 32u / kLoopG);
+                    i0 = __shfl_sync(0xffffffffu, i0, 0);
+                    if (i0 >= n_list) break;  // warp-uniform
+                    const uint32_t i = i0 + (uint32_t)(lane / kLoopG);
+                    if (i < n_list) search_entry(std::integral_constant<int, kLoopG>(), (int)s_list[i], lig, gmask);
                     __syncwarp();
                 }
                 if (stamper) B200_STAMP(gst, 18);
