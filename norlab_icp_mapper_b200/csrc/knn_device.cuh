@@ -161,6 +161,86 @@ struct AccK {
     }
 };
 
+// ---- k > 1, warm (loop.cu): COLLECT the points inside a fixed bound, select afterwards --------------------------
+// The cached k matches bound the new k-th distance, and the ball of that radius holds little more than k points.  Inserting
+// them one by one into a sorted list (AccK) is a chain of ~10 dependent cross-lane operations per point; here every lane
+// just keeps what it saw below the bound in C register slots (no cross-lane traffic during the scan), and the k nearest
+// are picked afterwards by rank counting (AccCollect::select): every collected point is broadcast once and each lane counts,
+// for its own points, how many precede them on (distance, position).  A lane that runs out of slots flags the query for the
+// AccK path.  `sd` as in AccK<.., TRACK>: the smallest distance tested and refused.
+template <int G, int C>
+struct AccCollect {
+    static constexpr bool kPerLaneOutput = true;
+    float cd[C];
+    int cp[C];
+    int cnt;
+    bool ovf;
+    float kth;  // the fixed gate (group-uniform)
+    float margin, sd;
+    int k;
+    __device__ __forceinline__ void init(int k_, float bound_, float margin_ = 0.f) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            cd[c] = CUDART_INF_F;
+            cp[c] = -1;
+        }
+        cnt = 0;
+        ovf = false;
+        kth = bound_;
+        margin = margin_;
+        sd = CUDART_INF_F;
+        k = k_;
+    }
+    __device__ __forceinline__ void consume(float d, uint32_t j, int, unsigned, float max_r2) {
+        if ((d < kth) && (d <= max_r2)) {
+            if (cnt < C) {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (c == cnt) {
+                        cd[c] = d;
+                        cp[c] = (int)j;
+                    }
+                cnt += 1;
+            } else {
+                ovf = true;
+            }
+        } else {
+            sd = fminf(sd, d);
+        }
+    }
+    __device__ __forceinline__ void scan(const float4* __restrict__ pts, uint32_t s, uint32_t e, float qx, float qy, float qz, int lig, unsigned gmask,
+                                         float max_r2) {
+#pragma unroll 2
+        for (uint32_t j = s + (uint32_t)lig; j < e; j += G) consume(dist2_exact(qx, qy, qz, __ldg(pts + j)), j, lig, gmask, max_r2);
+    }
+    __device__ __forceinline__ float tau(unsigned, float max_r2) const {
+        const float r = sqrtf(fminf(kth, max_r2)) + margin;
+        return r * r;
+    }
+    // rank of each of this lane's points among all collected points of the group ((distance, position) ascending); returns the
+    // number collected.  rank[c] is meaningful for c < cnt.
+    __device__ __forceinline__ int select(int (&rank)[C], int lig, unsigned gmask) const {
+#pragma unroll
+        for (int c = 0; c < C; ++c) rank[c] = 0;
+        int total = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            unsigned m = __ballot_sync(gmask, c < cnt) & gmask;  // lanes that hold a point in slot c (group-uniform loop below)
+            total += __popc(m);
+            while (m) {
+                const int src = __ffs(m) - 1;  // absolute lane
+                m &= m - 1;
+                const float nd = __shfl_sync(gmask, cd[c], src);
+                const int np = __shfl_sync(gmask, cp[c], src);
+#pragma unroll
+                for (int s = 0; s < C; ++s) rank[s] += (nd < cd[s]) || (nd == cd[s] && (unsigned)np < (unsigned)cp[s]);
+            }
+        }
+        (void)lig;
+        return total;
+    }
+};
+
 // One shell of cells with Chebyshev distance in (Rprev, R] around (cx, cy, cz), pruned by tau.
 template <int G, typename Acc>
 __device__ __forceinline__ void visit_shell(const GridView& g, Acc& acc, float qx, float qy, float qz, float ux, float uy,

@@ -483,6 +483,55 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         for (int o = GK / 2; o > 0; o >>= 1) dj = fmaxf(dj, __shfl_xor_sync(gmaskk, dj, o));
                         float bound = CUDART_INF_F;
                         if (dj < CUDART_INF_F) bound = __uint_as_float(__float_as_uint(dj) + 1u);  // next float up: ties with the bound stay accepted
+                        bool collected = false;
+                        if (dj <= prm.max_r2 && !(variant_flags & 128) && (variant_flags & 0x800000)) {
+                            // EXPERIMENT (nn_variant bit 23, off by default: measured slower -- cfg 4 loop 0.96 -> 1.07 ms):
+                            // ONE pass over the ball the cached matches bound, collecting what lies inside it (AccCollect: no
+                            // cross-lane traffic while scanning), then the k nearest by rank counting
+                            constexpr int CS = 4;
+                            AccCollect<GK, CS> col;
+                            col.init(K, bound, m);
+                            search_ball_k<GK, AccCollect<GK, CS>>(g, col, qn.x, qn.y, qn.z, prm.max_r2, ligk, gmaskk);
+                            if (!__any_sync(gmaskk, col.ovf)) {  // (a lane out of slots: the sorted-list search below redoes the query)
+                                int rank[CS];
+                                const int total = col.select(rank, ligk, gmaskk);
+                                float rej = col.sd;  // smallest distance tested and not kept: refused at the gate, or ranked k or worse
+#pragma unroll
+                                for (int c = 0; c < CS; ++c)
+                                    if (c < col.cnt && rank[c] >= K) rej = fminf(rej, col.cd[c]);
+#pragma unroll
+                                for (int o = GK / 2; o > 0; o >>= 1) rej = fminf(rej, __shfl_xor_sync(gmaskk, rej, o));
+                                // every point within sqrt(min(bound, maxDist^2)) + m was tested: the others are at least L away
+                                float L = fminf(sqrtf(rej), sqrtf(fminf(bound, prm.max_r2)) + m);
+                                L = fminf(L - 2e-6f * L, 1.0e18f);
+                                auto put = [&](int r, int op, float od) {  // cache entry of rank r
+                                    const int e2 = qs * K + r;
+                                    const long long pi2 = qq * K + r;
+                                    float4 pt = make_float4(0.f, 0.f, 0.f, 0.f), nn = pt;
+                                    if (op >= 0) {
+                                        pt = __ldg(g.pts + op);
+                                        if (MIN == 0 || sn_active) nn = __ldg(nrm + op);
+                                    }
+                                    pt.w = __int_as_float(op);
+                                    nn.w = L;  // (read from the first entry only)
+                                    if (e2 < kCacheCap) {
+                                        s_pp[e2] = pt;
+                                        s_nv[e2] = nn;
+                                        s_d2[e2] = od;
+                                    } else {
+                                        sp_pp[pi2] = pt;
+                                        sp_nv[pi2] = nn;
+                                        md2[pi2] = od;
+                                    }
+                                };
+#pragma unroll
+                                for (int c = 0; c < CS; ++c)
+                                    if (c < col.cnt && rank[c] < K) put(rank[c], col.cp[c], col.cd[c]);
+                                if (ligk >= total && ligk < K) put(ligk, -1, CUDART_INF_F);  // fewer than k points within maxDist
+                                collected = true;
+                            }
+                        }
+                        if (!collected) {
                         AccK<GK, true> acc;
                         acc.init(K, bound, m);
                         // all k cached matches still within maxDist: the ball they bound is searched in one pass
@@ -515,6 +564,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                                 sp_nv[pi] = nn;
                                 md2[pi] = od;
                             }
+                        }
                         }
                     }
                     __syncwarp();
