@@ -74,7 +74,7 @@ struct b200icp_ctx {
     int64_t last_normals_recomputed = 0;
     uint64_t octree_calls = 0;  // advances the random sampler's seed from one b200icp_map_octree call to the next
     float margin3[3] = {3.0f, 0.002f, 0.25f};  // search margin of the loop kernel's match cache; B200ICP_MARGIN="gain,min[m],max[cells]"
-    float win3[3] = {2.0f, 0.0015f, 0.003f};  // quantile-window policy of the one-barrier iteration (loop.cu); B200ICP_WINDOW="gain,floor,max"
+    float win3[3] = {2.0f, 0.0015f, 0.01f};  // quantile-window policy of the one-barrier iteration (loop.cu); B200ICP_WINDOW="gain,floor,max"
     char* h_pinned = nullptr;  // [0, 1024): state image to upload, [1024, 2048): state read back, [2048..): ints
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_map0 = nullptr, ev_map1 = nullptr, ev_loop0 = nullptr, ev_loop1 = nullptr;
     std::vector<cudaEvent_t> nn_events;
