@@ -152,9 +152,9 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
 #pragma unroll
         for (int j = 0; j < k; ++j) d -= L[k * (k + 1) / 2 + j] * L[k * (k + 1) / 2 + j];
         if (!(d > thr)) ok = false;
-        const float sq = sqrtf(d);
-        invd[k] = 1.0f / sq;
-        L[k * (k + 1) / 2 + k] = sq;
+        // only 1 / L_kk is ever used below: one correctly rounded reciprocal square root instead of an IEEE square root followed
+        // by an IEEE division (this chain of six is on the critical path of every ICP iteration)
+        invd[k] = __frsqrt_rn(d);
 #pragma unroll
         for (int i = k + 1; i < 6; ++i) {
             float v = L[i * (i + 1) / 2 + k];
@@ -228,7 +228,8 @@ __device__ __forceinline__ void delta_from_x(const float* x, int dim, float* dT,
             ax1 = x[1] / ang;
             ax2 = x[2] / ang;
         }
-        const float s = sinf(ang), c = cosf(ang);
+        float s, c;
+        sincosf(ang, &s, &c);
         const float sx = s * ax0, sy = s * ax1, sz = s * ax2;
         const float cx = (1.f - c) * ax0, cy = (1.f - c) * ax1, cz = (1.f - c) * ax2;
         float R[9];  // column-major
