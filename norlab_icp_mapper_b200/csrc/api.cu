@@ -1239,8 +1239,12 @@ static int32_t insert_point_distance_dev(b200icp_ctx* ctx, const DevCloud& in, f
         int* h_nq = reinterpret_cast<int*>(ctx->h_pinned + 2 * kStateBytes);
         *h_nq = (int)n_in;
         CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
-        CK(launch_knn(synced_index(ctx).view, ctx->d_q4, ctx->d_scalar_nq, (int)n_in, nullptr, 1, INFINITY, ctx->d_out_ids, ctx->d_out_d2,
-                      /*want_original_ids=*/1, ctx->cfg.nn_variant, s));
+        // Only "is there a map point closer than minDistNewPoint" matters (the keep test below re-evaluates the distance to the point
+        // found, in map-frame coordinates): the search is bounded by that radius, 0.1 % wider than the threshold so that the rounding
+        // of the centred frame cannot hide a point the exact test would reject.  No neighbour inside = keep, as with an unbounded search.
+        const float r2 = min_dist_new_point > 0.f ? min_dist_new_point * min_dist_new_point * 1.001f + 1e-30f : 0.f;
+        CK(launch_knn(synced_index(ctx).view, ctx->d_q4, ctx->d_scalar_nq, (int)n_in, nullptr, 1, (ctx->cfg.nn_variant & 0x2000000) ? INFINITY : r2,
+                      ctx->d_out_ids, ctx->d_out_d2, /*want_original_ids=*/1, ctx->cfg.nn_variant & 0xffff, s));
     } else {  // createMap: the first cloud is taken as it is (PointDistanceMapperModule.cpp:9-19)
         CK(cudaMemsetAsync(ctx->d_out_ids, 0xff, (size_t)n_in * sizeof(int32_t), s));
     }
