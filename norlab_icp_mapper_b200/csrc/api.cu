@@ -1524,9 +1524,11 @@ static int32_t self_knn(b200icp_ctx* ctx, const GridView& view, const float4* d_
             CK(cudaMemcpyAsync(ctx->d_scalar_nq, h_nq, sizeof(int), cudaMemcpyHostToDevice, s));
             CK(cudaMemsetAsync(ctx->d_fb_count, 0, sizeof(unsigned), s));
             KnnSpec ks;
-            float cells = 1.0f;  // B200ICP_SPEC_BOUND: the bound in cell edges (development sweep)
-            if (const char* env = getenv("B200ICP_SPEC_BOUND")) cells = (float)atof(env);
-            ks.bound2 = cells * view.h * cells * view.h;
+            // the bound: from the density around each query (at most one cell edge); B200ICP_SPEC_BOUND=<cell edges> fixes it instead
+            // (development sweep).  Gathered queries of the incremental pass bring the k-th distance they had in .w.
+            ks.bound2 = 0.f;
+            if (const char* env = getenv("B200ICP_SPEC_BOUND")) ks.bound2 = (float)atof(env) * view.h * (float)atof(env) * view.h;
+            ks.per_query = queries_are_all_points ? 0 : 1;
             ks.list = ctx->d_fb_list;
             ks.count = ctx->d_fb_count;
             ks.capacity = (unsigned)ctx->cap_fb;
@@ -1780,7 +1782,7 @@ int32_t b200icp_map_surface_normals(b200icp_ctx* ctx, int32_t knn) {
         if (m > 0) {
             const int32_t eb = ensure_query_buffers(ctx, m, knn);
             if (eb != B200ICP_OK) return eb;
-            CK(launch_normals_gather(idx.view, ctx->d_list, d_count, m, ctx->d_q4, s));
+            CK(launch_normals_gather(idx.view, ctx->d_list, d_count, m, ctx->d_q4, s, ctx->d_kth, st.nrm_epoch_ok ? st.nrm_epoch_n : 0));
             const int32_t sk = self_knn(ctx, idx.view, ctx->d_q4, m, knn, false);
             if (sk != B200ICP_OK) return sk;
             CK(launch_normals(idx.view, ctx->cfg.dim, knn, ctx->d_out_ids, ctx->d_out_d2, ctx->d_list, d_count, m, idx.normals, st.nrm,

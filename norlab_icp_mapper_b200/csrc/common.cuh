@@ -275,15 +275,19 @@ cudaError_t launch_normals_dirty(const GridView& new_points, const MapStore& m, 
 cudaError_t launch_normals_changed(const MapStore& m, int64_t n_old, uint8_t* d_flag, cudaStream_t s);
 cudaError_t store_clear_touched(MapStore& m, cudaStream_t s);
 cudaError_t launch_normals_positions(const GridView& g, const uint8_t* d_dirty, uint8_t* d_flag, cudaStream_t s);
-cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s);
+cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s,
+                                  const float* d_kth = nullptr, long long n_old = 0);
 
 // ---- knn.cu --------------------------------------------------------------------------------
 // queries: float4 (x, y, z, *) in the grid's frame, optionally moved by state->T first.
 // out_ids: cell-sorted positions (want_original_ids = 0) or original indices (1); -1 = none.
 // spec (k > 1 only): search inside sqrt(bound2) first; queries with fewer than k neighbours there are appended to `list`
 // (*count of them, at most `capacity` stored) for the caller to rerun without the bound.  Their rows hold what was found.
+// bound2 > 0: that bound for every query.  bound2 == 0: a bound from the density around the query (the radius expected to hold 2.5 k
+// points of a surface sampled like the query's own cell).  per_query: a query whose .w is positive brings its own bound in it.
 struct KnnSpec {
     float bound2 = 0.f;
+    int per_query = 0;
     uint32_t* list = nullptr;
     unsigned* count = nullptr;
     unsigned capacity = 0;

@@ -61,7 +61,20 @@ __global__ void __launch_bounds__(256) knn_kernel(GridView g, const float4* __re
     }
     // speculative bound (k > 1, cold): the k nearest are expected within sqrt(spec.bound2); only closer candidates enter the list
     // and the walk stops there.  k points found inside it ARE the k nearest; a query that finds fewer is listed for an unbounded rerun.
-    if (Acc::kPerLaneOutput && spec.list) bound = fminf(bound, spec.bound2);
+    if (Acc::kPerLaneOutput && spec.list) {
+        float b2 = spec.bound2;
+        if (spec.per_query && q4.w > 0.f) {
+            b2 = q4.w;
+        } else if (!(b2 > 0.f)) {
+            // points of the query's own cell -> surface density -> radius expected to hold 2.5 k of them, at most one cell edge
+            const int cx = min(max((int)floorf((qx - g.ox) * g.inv_h), 0), g.nx - 1), cy = min(max((int)floorf((qy - g.oy) * g.inv_h), 0), g.ny - 1);
+            const int cz = min(max((int)floorf((qz - g.oz) * g.inv_h), 0), g.nz - 1);
+            const uint32_t* cell = g.cell_start + ((size_t)cz * g.ny + cy) * (size_t)g.nx + cx;
+            const float c0 = fmaxf((float)(__ldg(cell + 1) - __ldg(cell)), 1.f);
+            b2 = g.h * g.h * fminf(1.0f, fmaxf(0.02f, (2.5f * (float)k) / (3.14159265f * c0)));
+        }
+        bound = fminf(bound, b2);
+    }
     acc.init(k, bound);
     search_shells<G, Acc>(g, acc, qx, qy, qz, max_r2, variant, lig, gmask);
     float od;

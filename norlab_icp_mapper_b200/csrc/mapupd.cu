@@ -249,10 +249,21 @@ __global__ void __launch_bounds__(256) normals_flag_positions_kernel(GridView g,
     flag[j] = dirty[__float_as_int(__ldg(g.pts + j).w)];
 }
 
+// kth (optional, per store index, valid below n_old): the point's squared k-th neighbour distance of the last pass -- appends can only
+// shrink it, so it bounds the new search (written to .w, one ulp up so that a tie at the bound stays accepted); -1 = no bound known
 __global__ void __launch_bounds__(256) normals_gather_queries_kernel(GridView g, const uint32_t* __restrict__ list, const unsigned int* __restrict__ n_list,
-                                                                     float4* __restrict__ q) {
+                                                                     float4* __restrict__ q, const float* __restrict__ kth, long long n_old) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < (long long)*n_list) q[i] = __ldg(g.pts + list[i]);
+    if (i >= (long long)*n_list) return;
+    float4 p = __ldg(g.pts + list[i]);
+    const long long orig = __float_as_int(p.w);
+    float b = -1.f;
+    if (kth && orig < n_old) {
+        const float v = kth[orig];
+        if (v > 0.f && v < 3.0e38f) b = __uint_as_float(__float_as_uint(v) + 1u);
+    }
+    p.w = b;
+    q[i] = p;
 }
 
 template <typename T>
@@ -1099,9 +1110,10 @@ cudaError_t launch_normals_positions(const GridView& g, const uint8_t* d_dirty, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s) {
+cudaError_t launch_normals_gather(const GridView& g, const uint32_t* d_list, const unsigned int* d_n_list, long long capacity, float4* d_q, cudaStream_t s,
+                                  const float* d_kth, long long n_old) {
     if (capacity <= 0) return cudaSuccess;
-    normals_gather_queries_kernel<<<blocks_for(capacity), 256, 0, s>>>(g, d_list, d_n_list, d_q);
+    normals_gather_queries_kernel<<<blocks_for(capacity), 256, 0, s>>>(g, d_list, d_n_list, d_q, d_kth, n_old);
     return cudaGetLastError();
 }
 
