@@ -349,30 +349,39 @@ class Env:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def gather_pose(self, T, overlap, iters):
-        """The only collective of the batched mode: all_gather of this rank's pose record (inside the timed step)."""
+    def gather_poses(self, recs):
+        """The only collective of the replicated / batched modes: ONE all_gather of this rank's pose records (K x 18 floats) at the
+        end of the K timed steps, inside the timed region -- north_star: "NCCL only to gather final poses"."""
         from norlab_icp_mapper_b200 import batched
-        rec = np.zeros((1, 18), np.float32)
-        rec[0, :T.size] = np.asarray(T, np.float32).ravel()
-        rec[0, 16], rec[0, 17] = overlap, iters
-        return batched.gather_records(rec, self.world, self.dist, self.device)
+        return batched.gather_records(np.ascontiguousarray(recs, np.float32), self.world, self.dist, self.device)
 
-    def timed(self, fn, steps, ext):
-        """Per-step CUDA events (start on the library's stream, end on torch's current stream after the pose gather); L2
-        flushed between steps, outside the events.  Returns (device ms, wall ms) summed over the steps."""
+    def timed(self, fn, steps, ext, records=None):
+        """Per-step CUDA events (start on the library's stream, end on torch's current stream); L2 flushed between steps, outside
+        the events.  With several ranks the K pose records are all_gathered once after the last step; that collective is timed
+        (host wall clock around the blocking call: NCCL launch + transfer + read-back) and added.  Returns (device ms, wall ms)
+        summed over the steps (+ the gather)."""
         torch = self.torch
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         wall = 0.0
-        for a, b in evs:
+        for i, (a, b) in enumerate(evs):
             self.flush.fill_(1)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             a.record(ext)
-            fn()
+            rec = fn()
             b.record()
             b.synchronize()
             wall += time.perf_counter() - t0
+            if records is not None and rec is not None:
+                records[i] = rec
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if self.world > 1 and records is not None:
+            t0 = time.perf_counter()
+            self.last_gather = self.gather_poses(records)
+            torch.cuda.synchronize()
+            g = (time.perf_counter() - t0) * 1e3
+            dev_ms += g
+            wall += g * 1e-3
         return dev_ms, wall * 1e3
 
 
@@ -396,29 +405,34 @@ def bench_pair(env, w, data, args, steps, warmup, with_roofline=True):
     nn = rows * rows
     state = {}
 
-    def finish_step():
-        if env.world > 1:
-            state["all"] = env.gather_pose(T_out[:nn], res.overlap, res.iterations)
+    def finish_step():  # this step's pose record (gathered over the ranks once, after the last timed step)
+        rec = np.zeros(18, np.float32)
+        rec[:nn] = T_out[:nn]
+        rec[16], rec[17] = res.overlap, res.iterations
+        return rec
 
     def step_device():
         rc = icp._L.b200icp_register_device(icp._h, d_reading.data_ptr(), rows, nq, None, T_out.ctypes.data, ctypes.byref(res))
         if rc != 0:
             raise RuntimeError(icp._L.b200icp_last_error(icp._h).decode())
-        finish_step()
+        return finish_step()
 
     def make_e2e(ptr):
         def step():
             rc = icp._L.b200icp_register(icp._h, ptr, rows, nq, None, T_out.ctypes.data, ctypes.byref(res))
             if rc != 0:
                 raise RuntimeError(icp._L.b200icp_last_error(icp._h).decode())
-            finish_step()
+            return finish_step()
         return step
 
     for _ in range(max(warmup, 3)):
         step_device()
+    records = np.zeros((steps, 18), np.float32)
+    if env.world > 1:
+        env.gather_poses(records)  # (warm-up of the collective too: NCCL sets its connections up on first use)
     torch.cuda.synchronize()
     env.barrier()
-    dev_ms, wall_ms = env.timed(step_device, steps, ext)
+    dev_ms, wall_ms = env.timed(step_device, steps, ext, records)
     env.barrier()
     launches_per_step = icp.timing().kernel_launches
     T = T_out[:nn].reshape(rows, rows).T.copy()
@@ -431,7 +445,7 @@ def bench_pair(env, w, data, args, steps, warmup, with_roofline=True):
         for _ in range(3):
             step()
         env.barrier()
-        d, wl = env.timed(step, steps, ext)
+        d, wl = env.timed(step, steps, ext, records)
         env.barrier()
         out["e2e_%s_ms" % key] = env.max_over_ranks(max(d, wl)) / steps
 
@@ -714,8 +728,8 @@ def run_b200(args):
             "config": workload_config(w),
             "run": {"l2": "flushed between steps (256 MiB fill, outside the timed events); within a step the 96 MB index stays "
                           "L2-resident across the 30 iterations by design",
-                    "parallelism": "one process per GPU; every rank registers its own scan against its own map (independent pairs), the "
-                                   "poses are all_gathered over NCCL inside every timed step" if world > 1 else "single GPU",
+                    "parallelism": "one process per GPU; every rank registers its own scan against its own map (independent pairs), the K "
+                                   "poses of the timed steps are all_gathered over NCCL once, inside the timed region" if world > 1 else "single GPU",
                     "host_cores": host_cores()},
             "e2e": {"value": world * 1e3 / r["e2e_pinned_ms"], "unit": UNIT, "h2d_bytes_per_step": 4 * (w["dim"] + 1) * nq,
                     "d2h_bytes_per_step": 512, "ms_per_step": r["e2e_pinned_ms"], "host_memory": "pinned",

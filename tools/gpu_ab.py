@@ -6,7 +6,8 @@ import numpy as np
 import torch
 from norlab_icp_mapper_b200 import synth
 from norlab_icp_mapper_b200.icp import ICP, make_config
-d = synth.make_pair_3d(drpy_deg=(1.0, -1.0, 3.0)) if os.environ.get("HARD") else synth.make_pair_3d()  # HARD=1: SURVEY 8d's initial error
+_seed = int(os.environ.get("SEED", "1234"))
+d = synth.make_pair_3d(seed=_seed, drpy_deg=(1.0, -1.0, 3.0)) if os.environ.get("HARD") else synth.make_pair_3d(seed=_seed)  # HARD=1: SURVEY 8d's initial error
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 variants = [int(a) for a in sys.argv[1:] if not a.startswith("--")] or [0]
 sort_modes = (1, 0) if "--sort" in sys.argv else (1,)
