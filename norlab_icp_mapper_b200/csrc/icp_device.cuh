@@ -124,7 +124,8 @@ __device__ __forceinline__ int solve_mask(int dim, int min_flags) {
     return (dim == 2 || (min_flags & 1)) ? 0x23 : ((min_flags & 2) ? 0x03 : 0);
 }
 
-__device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/, int min_flags = 0) {
+__device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, float* x /*[6]*/, float* s_x /*smem[8]*/, int min_flags = 0, IcpState* stamp_to = nullptr) {
+    if (stamp_to && lane == 0) B200_STAMP(stamp_to, 5);
     float L[21], bv[6];  // lower triangle, L[i * (i + 1) / 2 + j] = (i, j), j <= i
 #pragma unroll
     for (int i = 0; i < 21; ++i) L[i] = (float)S[i];
@@ -144,6 +145,7 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
 #pragma unroll
     for (int i = 0; i < 6; ++i) maxdiag = fmaxf(maxdiag, fabsf(L[i * (i + 1) / 2 + i]));
     const float thr = 6.0f * 1.1920929e-7f * maxdiag;
+    if (stamp_to && lane == 0) B200_STAMP(stamp_to, 7);
     bool ok = true;
     float invd[6];
 #pragma unroll
@@ -163,6 +165,7 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
             L[i * (i + 1) / 2 + k] = v * invd[k];
         }
     }
+    if (stamp_to && lane == 0) B200_STAMP(stamp_to, 8);
     float y[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {  // L y = b
@@ -178,6 +181,7 @@ __device__ __forceinline__ void solve6_warp(const double* S, int dim, int lane, 
         for (int j = i + 1; j < 6; ++j) v -= L[j * (j + 1) / 2 + i] * x[j];
         x[i] = v * invd[i];
     }
+    if (stamp_to && lane == 0) B200_STAMP(stamp_to, 9);
     bool bad = !ok;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
@@ -528,7 +532,7 @@ __device__ __forceinline__ void finish_warp(const IcpParams& prm, IcpState* st, 
     float dT[12];
     if (prm.minimizer == B200ICP_MIN_POINT_TO_PLANE) {
         float x[6];
-        solve6_warp(S, prm.dim, lane, x, s_scratch, prm.min_flags);
+        solve6_warp(S, prm.dim, lane, x, s_scratch, prm.min_flags, stamp_to);
         if (stamp_to && lane == 0) B200_STAMP(stamp_to, 15);
         delta_from_x(x, prm.dim, dT, prm.min_flags);
         if (stamp_to && lane == 0) B200_STAMP(stamp_to, 16);
@@ -567,15 +571,16 @@ struct SumLayout<2> {
 
 // Sum 32 per-lane values v[0..31] across the 32 lanes of a warp with 31 shuffles (butterfly
 // transpose): on return every lane holds the warp total of ONE slot, namely slot `lane_slot(lane)`.
-// fp32 pairwise tree over the lanes, deterministic.
-__device__ __forceinline__ float warp_reduce_32slots(float (&v)[32], int lane) {
+// fp32: pairwise tree over the lanes, deterministic; int: exact.
+template <typename V>
+__device__ __forceinline__ V warp_reduce_32slots(V (&v)[32], int lane) {
 #pragma unroll
     for (int half = 16; half >= 1; half >>= 1) {
         const bool upper = (lane & half) != 0;
 #pragma unroll
         for (int j = 0; j < half; ++j) {
-            const float send = upper ? v[j] : v[j + half];
-            const float keep = upper ? v[j + half] : v[j];
+            const V send = upper ? v[j] : v[j + half];
+            const V keep = upper ? v[j + half] : v[j];
             v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
         }
     }

@@ -1048,13 +1048,16 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
                         if (kept) add_pair<MIN>(acc2, 1.f, make_float3(ca[0].x, ca[0].y, ca[0].z), cb[0]);
                         bool range_ok = true;
+                        int f[32];
 #pragma unroll
-                        for (int i = 0; i < NS; ++i) {
-                            const float sv = acc2[i] * s_cscale[i];
+                        for (int i = 0; i < 32; ++i) {
+                            const float sv = i < NS ? acc2[i] * s_cscale[i] : 0.f;
                             range_ok = range_ok && (fabsf(sv) < 8388608.f);
-                            const int tot = __reduce_add_sync(0xffffffffu, __float2int_rn(sv));
-                            if (lane == i) mine_tot = (long long)tot;
+                            f[i] = __float2int_rn(sv);
                         }
+                        // 31 shuffles for all the slots together (lane l ends with slot l); a REDUX per slot was 2 x slower
+                        const int tot = warp_reduce_32slots(f, lane);
+                        if (lane < NS) mine_tot = (long long)tot;
                         const bool any_bad = __any_sync(0xffffffffu, !range_ok);
                         if (lane == kSlotFlag) mine_tot = any_bad ? 1ll : 0ll;
                     }
@@ -1134,10 +1137,12 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             }
                         }
                     }
+                    {
+                        int f32[32];
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) {
-                        const int tot = __reduce_add_sync(0xffffffffu, f[i]);
-                        if (lane == i) mine_tot = (long long)tot;
+                        for (int i = 0; i < 32; ++i) f32[i] = i < NS ? f[i] : 0;
+                        const int tot = warp_reduce_32slots(f32, lane);
+                        if (lane < NS) mine_tot = (long long)tot;
                     }
                     const bool any_bad = __any_sync(0xffffffffu, !range_ok);
                     if (lane == kSlotFlag) mine_tot = any_bad ? 1ll : 0ll;
@@ -1360,8 +1365,8 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         __syncthreads();
         if (stamper) B200_STAMP(gst, 13);
         }  // !fast_done
-        if (tid < 32) {
-            if (tid == 0) {
+        if (tid == 32) {  // (warp 1, beside the solve on warp 0)
+            {
                 // window for the next iteration's one-barrier attempt: centred on this quantile (Trimmed: the limit itself; Median:
                 // the median, the limit's window follows from it), half-width from its last change
                 const float prev = st.limit;
@@ -1379,8 +1384,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                 st.have_limit = use_quantile ? 1 : 0;
                 st.limit = qlimit;
             }
+        }
+        if (tid < 32) {
             finish_warp(prm, &st, s_sum, NS, blockIdx.x == 0 ? trace : nullptr, s_scratch, stamper ? gst : nullptr);
         }
+        __syncthreads();
+        if (stamper) B200_STAMP(gst, 14);
+        B200_CTA_STAMP(partials, 6);
         if (stamper && it < 256 && (variant_flags & 0x80000)) {  // development record (nn_variant bit 19; its L2 round trip is on CTA 0's critical path): {path 0 general / 1 one-barrier / 2 failed attempt, limit, candidates, below, searched so far, next window}
             uint32_t* rec = hist + kHistDebug + it * 8;
             rec[0] = dbg_path;
@@ -1394,9 +1404,6 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
             rec[7] = (uint32_t)(tn - t_iter0);
         }
-        __syncthreads();
-        if (stamper) B200_STAMP(gst, 14);
-        B200_CTA_STAMP(partials, 6);
     }
     if (blockIdx.x == 0) {
         if (tid == 0) {

@@ -14,7 +14,7 @@ names = {0: "sel start", 1: "sel p0 hist", 2: "sel p0 sync", 3: "sel p0 pick", 4
 if "--loop" in sys.argv:
     names = {20: "iter start", 21: "nn done", 22: "published / level-0 hist flushed", 23: "barrier 1", 24: "pick 0", 25: "candidates gathered", 26: "barrier 2",
              27: "select done", 31: "acc partial written", 12: "acc barrier", 13: "reduced", 14: "finished", 28: "classified", 29: "counts read", 15: "solved", 16: "delta built", 17: "V + list done", 18: "S done (warp 0)", 19: "S done (CTA 0)", 30: "new matches fetched (thread 0)",
-             1: "finish: keys shared", 2: "finish: ranked", 3: "finish: candidates summed (REDUX)", 4: "finish: warp totals shared", 6: "finish: totals"}
+             1: "finish: keys shared", 2: "finish: ranked", 3: "finish: candidates summed (REDUX)", 4: "finish: warp totals shared", 6: "finish: totals", 5: "solve: entered", 7: "solve: sums loaded", 8: "solve: factorised", 9: "solve: substituted"}
 for rep in range(3):
     g(d["reading"])
     st = np.zeros(32, np.uint64)
