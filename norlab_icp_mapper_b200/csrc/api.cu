@@ -734,9 +734,13 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     // Cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
     // (Per-kernel profiling and nn_variant bit 2 select the kernel-per-step path below instead.)
     const bool var_trimmed = p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST;
+    // RobustOutlierFilter runs inside the loop kernel (its mad / berg scale through exact selects between grid barriers) unless
+    // the chain also holds a quantile filter (the loop's candidate tuples carry no weight) or the scale is the standard deviation
     bool robust = false;
-    for (int f = 0; f < p.n_outlier; ++f) robust = robust || p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST;
-    // (VarTrimmed and Robust estimate their ratio / scale with device-wide sorts between the steps: kernel-per-step path)
+    for (int f = 0; f < p.n_outlier; ++f)
+        if (p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST)
+            robust = robust || p.quantile_filter >= 0 || ((p.outlier_mode[f] >> 8) & 15) == B200ICP_SCALE_STD || (ctx->cfg.nn_variant & 0x4000000);
+    // (VarTrimmed -- and Robust in those cases -- estimate their ratio / scale with device-wide sorts between the steps: kernel-per-step path)
     // (a reading with a `maxSearchDist` descriptor: per-point radii ride in the reading's .w, which only the stand-alone search
     //  kernels read -- the sentinel max_r2 = -1 tells them to)
     const float search_r2 = d_reading_max_dist ? -1.f : p.max_r2;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void block_prefix32(const uint32_t* s_cnt32, int lane
 // kShared: the histogram lives in shared memory (plain loads) instead of global memory (L2 loads).
 template <bool kShared>
 __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bool rank_is_fraction, float q, uint32_t* s_bin,
-                              uint32_t* s_res, uint32_t* s_cnt, uint32_t* s_warp) {
+                              uint32_t* s_res, uint32_t* s_cnt, uint32_t* s_warp, bool rank_is_half = false) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (nbins + kLoopThreads - 1) / kLoopThreads;  // 1..4
     uint32_t loc[4];
@@ -191,6 +191,7 @@ __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bo
         rank = (q == 1.0f) ? (total ? total - 1u : 0u) : (uint32_t)((float)total * q);
         if (total && rank >= total) rank = total - 1u;
     }
+    if (rank_is_half) rank = total >> 1;  // element n / 2 of the sorted values (Matches::getMedianAbsDeviation)
     const uint32_t excl = incl - sum;
     if (total && rank >= excl && rank < incl) {
         uint32_t run = excl;
@@ -206,6 +207,156 @@ __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bo
     }
     __syncthreads();
     return total;
+}
+
+// ---- RobustOutlierFilter's scale inside the loop kernel -----------------------------------------------
+// What the kernel-per-step path gets from two device-wide sorts (outlier.cu launch_robust_scale): the element of rank n / 2
+// among the n finite match distances (mode 0), or among their absolute deviations from `centre` (mode 1).  Exact radix
+// select over the keys' float bit patterns, every CTA in lockstep and with the same result: level 0 (bits [30:19]) of each
+// CTA's slice -> `h0` in global memory -> barrier -> bucket of the rank; when that bucket holds <= kSelListCap keys they are
+// gathered into one list (second barrier) and every CTA finishes locally, else two more global levels (bits [18:8], [7:0]).
+// Zeroing protocol: a region is zeroed by CTA 0 after a barrier every CTA has passed having finished reading it, and written
+// again only after a later barrier, which CTA 0 reaches after the zeroing; the level-2 region is handed over to the caller
+// (`l2_dirty`: zeroed after the next barrier).  Returns false when there is no finite distance (buffers left clean).
+struct LoopSelCtx {
+    const float4* s_pp;   // match cache: (x, y, z, bit-cast position) ...
+    const float* s_d2;    // ... and squared distance of the entries below kCacheCap
+    const float4* sp_pp;  // the same for the spilled entries (global memory, indexed by match row)
+    const float* md2;
+    uint32_t *sh, *sh2, *s_bin, *s_res, *s_cnt, *s_stage, *s_base, *s_warp;
+    uint32_t* hist;
+    unsigned* bar_counter;
+    int n_ent, K, cshift;
+};
+
+__device__ __noinline__ bool loop_exact_median(const LoopSelCtx& c, int mode, float centre, uint32_t* h0, unsigned& epoch, bool& l2_dirty,
+                                               uint32_t& out_bits) {
+    const int tid = threadIdx.x;
+    auto key_of = [&](int e) -> uint32_t {  // 0xffffffff: not a finite match distance
+        int pos;
+        float d;
+        if (e < kCacheCap) {
+            pos = __float_as_int(c.s_pp[e].w);
+            d = c.s_d2[e];
+        } else {
+            const int ql = c.K == 1 ? e : e / c.K;
+            const long long qi = (((long long)(ql >> c.cshift) * gridDim.x + blockIdx.x) << c.cshift) + (ql & ((1 << c.cshift) - 1));
+            const long long pi = c.K == 1 ? qi : qi * c.K + (e - ql * c.K);
+            pos = __float_as_int(c.sp_pp[pi].w);
+            d = c.md2[pi];
+        }
+        if (!(pos >= 0 && d < CUDART_INF_F)) return 0xffffffffu;
+        return __float_as_uint(mode ? fabsf(d - centre) : d);
+    };
+    for (int i = tid; i < kSel0Bins; i += kLoopThreads) c.sh[i] = 0u;
+    if (tid == 0) {
+        *c.s_bin = 0;
+        *c.s_res = 0;
+        *c.s_cnt = 0;
+        *c.s_stage = 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < c.n_ent; e += kLoopThreads) {
+        const uint32_t k = key_of(e);
+        if (k != 0xffffffffu) atomicAdd(&c.sh[k >> kSel0Shift], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < kSel0Bins; i += kLoopThreads)
+        if (c.sh[i]) atomicAdd(&h0[i], c.sh[i]);
+    grid_barrier(c.bar_counter, epoch);
+    if (l2_dirty) {  // (an earlier select's last level: everybody has read it by now)
+        if (blockIdx.x == 0)
+            for (int i = tid; i < 256; i += kLoopThreads) c.hist[kHistL2 + i] = 0u;
+        l2_dirty = false;
+    }
+    const uint32_t total = loop_pick<false>(h0, kSel0Bins, 0u, false, 0.f, c.s_bin, c.s_res, c.s_cnt, c.s_warp, /*rank_is_half=*/true);
+    const uint32_t b1 = *c.s_bin, r1 = *c.s_res, c1 = *c.s_cnt;
+    __syncthreads();
+    if (total == 0) {
+        grid_barrier(c.bar_counter, epoch);
+        if (blockIdx.x == 0)
+            for (int i = tid; i < kSel0Bins; i += kLoopThreads) h0[i] = 0u;
+        return false;
+    }
+    uint32_t low = 0;  // the 19 low bits
+    if (c1 <= (uint32_t)kSelListCap) {
+        for (int e = tid; e < c.n_ent; e += kLoopThreads) {
+            const uint32_t k = key_of(e);
+            if (k != 0xffffffffu && (k >> kSel0Shift) == b1) c.sh[atomicAdd(c.s_stage, 1u)] = k;
+        }
+        __syncthreads();
+        if (tid == 0) *c.s_base = *c.s_stage ? atomicAdd(&c.hist[kHistCount], *c.s_stage) : 0u;
+        __syncthreads();
+        for (uint32_t i = tid; i < *c.s_stage; i += kLoopThreads) c.hist[kHistList + *c.s_base + i] = c.sh[i];
+        grid_barrier(c.bar_counter, epoch);
+        if (blockIdx.x == 0) {
+            for (int i = tid; i < kSel0Bins; i += kLoopThreads) h0[i] = 0u;
+            if (tid == 0) c.hist[kHistCount] = 0u;
+        }
+        for (uint32_t i = tid; i < c1; i += kLoopThreads) c.sh[i] = __ldcg(c.hist + kHistList + i);
+        c.sh2[tid] = 0u;  // local level 1: bits [18:9]
+        if (tid == 0) {
+            *c.s_bin = 0;
+            *c.s_res = 0;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < c1; i += kLoopThreads) atomicAdd(&c.sh2[(c.sh[i] >> 9) & 1023u], 1u);
+        __syncthreads();
+        loop_pick<true>(c.sh2, 1024, r1, false, 0.f, c.s_bin, c.s_res, c.s_cnt, c.s_warp);
+        const uint32_t b2 = *c.s_bin, r2 = *c.s_res;
+        __syncthreads();
+        if (tid < 512) c.sh2[tid] = 0u;  // local level 2: bits [8:0]
+        if (tid == 0) {
+            *c.s_bin = 0;
+            *c.s_res = 0;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < c1; i += kLoopThreads)
+            if (((c.sh[i] >> 9) & 1023u) == b2) atomicAdd(&c.sh2[c.sh[i] & 511u], 1u);
+        __syncthreads();
+        loop_pick<true>(c.sh2, 512, r2, false, 0.f, c.s_bin, c.s_res, c.s_cnt, c.s_warp);
+        low = (b2 << 9) | *c.s_bin;
+        __syncthreads();
+    } else {
+        uint32_t rank = r1, pre = b1;
+        for (int pass = 1; pass <= 2; ++pass) {
+            const int nbins = (pass == 1) ? 2048 : 256;
+            uint32_t* gh = c.hist + (pass == 1 ? kHistL1 : kHistL2);
+            for (int i = tid; i < nbins; i += kLoopThreads) c.sh[i] = 0u;
+            if (tid == 0) {
+                *c.s_bin = 0;
+                *c.s_res = 0;
+            }
+            __syncthreads();
+            for (int e = tid; e < c.n_ent; e += kLoopThreads) {
+                const uint32_t k = key_of(e);
+                if (k == 0xffffffffu) continue;
+                if (pass == 1) {
+                    if ((k >> kSel0Shift) == pre) atomicAdd(&c.sh[(k >> 8) & 2047u], 1u);
+                } else {
+                    if ((k >> 8) == pre) atomicAdd(&c.sh[k & 255u], 1u);
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < nbins; i += kLoopThreads)
+                if (c.sh[i]) atomicAdd(&gh[i], c.sh[i]);
+            grid_barrier(c.bar_counter, epoch);
+            if (blockIdx.x == 0) {  // the previous level is no longer read by anyone
+                if (pass == 1)
+                    for (int i = tid; i < kSel0Bins; i += kLoopThreads) h0[i] = 0u;
+                else
+                    for (int i = tid; i < 2048; i += kLoopThreads) c.hist[kHistL1 + i] = 0u;
+            }
+            loop_pick<false>(gh, nbins, rank, false, 0.f, c.s_bin, c.s_res, c.s_cnt, c.s_warp);
+            rank = *c.s_res;
+            pre = (pass == 1) ? ((pre << 11) | *c.s_bin) : ((pre << 8) | *c.s_bin);
+            __syncthreads();
+        }
+        l2_dirty = true;
+        low = pre & ((1u << kSel0Shift) - 1u);
+    }
+    out_bits = (b1 << kSel0Shift) | low;
+    return true;
 }
 
 // Product of the weights of every outlier filter EXCEPT the quantile-based one (fast path: that one is
@@ -339,6 +490,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     unsigned epoch = 0;
     uint32_t n_runs = 0, n_hist = 0;  // publish/finish rounds (stage-1 histograms) so far: parity selects the double buffer
     const bool use_quantile = prm.quantile_filter >= 0;
+    int robust_f = -1;  // the chain's RobustOutlierFilter (at most one)
+    for (int f = 0; f < prm.n_outlier; ++f)
+        if (prm.outlier_kind[f] == B200ICP_OUTLIER_ROBUST) robust_f = f;
+    bool l2_dirty = false;  // the last level of a three-level median select waits for its zeroing (loop_exact_median)
     const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
@@ -751,6 +906,56 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         float qlimit = 0.f;
         bool fast_done = false;
         bool fatal = false;
+        // ---- RobustOutlierFilter: this iteration's scale (LPM RobustOutlierFilter::robustFiltering; outlier.cu for the
+        //      kernel-per-step path).  mad: sqrt(median |d - median d|), two exact selects of two barriers each; berg: 1.9 sqrt(median d)
+        //      in the first iteration, then the recursion; none: nothing to do.  (std stays on the kernel-per-step path.)
+        if (robust_f >= 0) {
+            const int mode = prm.outlier_mode[robust_f];
+            const int estimator = (mode >> 8) & 15, nb = (mode >> 16) & 0x7fff;
+            const int iteration = st.iter + 1;  // LPM counts from 1
+            if (estimator != B200ICP_SCALE_NONE && (iteration <= nb || nb == 0)) {
+                if (estimator == B200ICP_SCALE_BERG && iteration > 1) {
+                    if (tid == 0) st.robust_scale = 0.85f * (st.robust_scale - prm.outlier_param[robust_f]) + prm.outlier_param[robust_f];
+                } else {
+                    LoopSelCtx sc;
+                    sc.s_pp = s_pp;
+                    sc.s_d2 = s_d2;
+                    sc.sp_pp = sp_pp;
+                    sc.md2 = md2;
+                    sc.sh = sh;
+                    sc.sh2 = sh2;
+                    sc.s_bin = &s_bin;
+                    sc.s_res = &s_res;
+                    sc.s_cnt = &s_cnt;
+                    sc.s_stage = &s_stage;
+                    sc.s_base = &s_base;
+                    sc.s_warp = s_warp;
+                    sc.hist = hist;
+                    sc.bar_counter = bar_counter;
+                    sc.n_ent = n_ent;
+                    sc.K = K;
+                    sc.cshift = cshift;
+                    uint32_t med_bits = 0, dev_bits = 0;
+                    bool have = loop_exact_median(sc, 0, 0.f, hist, epoch, l2_dirty, med_bits);
+                    if (have && estimator == B200ICP_SCALE_MAD) {
+                        uint32_t* hb = hist + kHistStage1 + (n_hist & 1u) * kStage1Words;  // (the level-0 region may still be being zeroed)
+                        n_hist += 1;
+                        have = loop_exact_median(sc, 1, __uint_as_float(med_bits), hb, epoch, l2_dirty, dev_bits);
+                    }
+                    if (!have) {  // LPM: ConvergenceError("no outlier to filter")
+                        if (tid == 0) {
+                            st.status = B200ICP_ERR_CONVERGENCE;
+                            st.done = 1;
+                        }
+                        __syncthreads();
+                        break;
+                    }
+                    if (tid == 0)
+                        st.robust_scale = estimator == B200ICP_SCALE_BERG ? 1.9f * sqrtf(__uint_as_float(med_bits)) : sqrtf(__uint_as_float(dev_bits));
+                }
+                __syncthreads();
+            }
+        }
         uint32_t dbg_path = 0, dbg_ncand = 0, dbg_nbelow = 0;  // development record (CTA 0)
         // ---- the rest of the iteration in ONE barrier (stage 0: quantile window predicted from the last limits) or
         //      TWO (stage 1: window = the histogram bin that holds the quantile, found with a histogram pass);
@@ -899,7 +1104,19 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                                                                                           : (p.x - pp.x) * nv.x + (p.y - pp.y) * nv.y + (p.z - pp.z) * nv.z);
                                 else
                                     v = pp;
-                                if (cls == 0) add_pair<MIN>(acc, wo, p, v);
+                                float w = wo;
+                                if (robust_f >= 0) {  // (never next to a quantile filter here: the candidates' weight is one)
+                                    const int mode = prm.outlier_mode[robust_f];
+                                    float dist = d;
+                                    if ((mode >> 12) & 1) {  // point2plane: (n . (p - q))^2, n normalised (the host checked the map has normals)
+                                        const float4 nm = (MIN == 0 || sn_active) ? nv : __ldg(nrm + pos);
+                                        const float inv = 1.f / sqrtf(nm.x * nm.x + nm.y * nm.y + nm.z * nm.z);
+                                        const float dot = (nm.x * inv) * (p.x - pp.x) + (nm.y * inv) * (p.y - pp.y) + (nm.z * inv) * (p.z - pp.z);
+                                        dist = dot * dot;
+                                    }
+                                    w *= robust_weight(mode, prm.outlier_param[robust_f], prm.outlier_param2[robust_f], st.robust_scale, dist);
+                                }
+                                if (cls == 0 && w != 0.f) add_pair<MIN>(acc, w, p, v);
                             }
                             if (cls == 1 || in_rank) {  // a candidate dropped by another filter still takes part in the quantile: p.x = NaN marks it
                                 is_cand = true;
@@ -967,6 +1184,11 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             grid_barrier(bar_counter, epoch);
             B200_CTA_STAMP(partials, 5);
             if (stamper) B200_STAMP(gst, 23);
+            if (l2_dirty) {
+                if (blockIdx.x == 0)
+                    for (int i = tid; i < 256; i += kLoopThreads) hist[kHistL2 + i] = 0u;
+                l2_dirty = false;
+            }
             // ---- after the barrier: identical work in every CTA ---------------------------------------
             if (blockIdx.x == 0 && tid < kIsumSlots) stale_isum[tid * kIsumStride] = 0ull;
             // one round trip: the accumulators and, speculatively, the head of the candidate list
@@ -1324,7 +1546,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
             for (int i = 0; i < 16; ++i) T[i] = st.T[i];
             for (int e = tid; e < n_ent; e += kLoopThreads) {
                 const long long pi = pair_of(e);
-                accumulate_entry<MIN>(acc, prm, T, g, nrm, reading, pi, K, mpos[pi], md2[pi], qlimit);
+                accumulate_entry<MIN>(acc, prm, T, g, nrm, reading, pi, K, mpos[pi], md2[pi], qlimit, st.robust_scale);
             }
         }
         {
@@ -1346,8 +1568,9 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
         if (stamper) B200_STAMP(gst, 31);
         grid_barrier(bar_counter, epoch);
         if (stamper) B200_STAMP(gst, 12);
-        if (fallback_used && blockIdx.x == 0)
+        if ((fallback_used || l2_dirty) && blockIdx.x == 0)
             for (int i = tid; i < 256; i += kLoopThreads) hist[kHistL2 + i] = 0u;
+        l2_dirty = false;
         // ---- fixed-order reduction of the per-CTA partials, done identically by every CTA -----------
         {
             const int slot = tid & 31, part = tid >> 5;  // 32 parts

@@ -349,6 +349,61 @@ def test_robust_outlier_filter(oracle, pair3d, minimizer, knn, max_dist, rp):
     assert res_g.overlap == pytest.approx(res_o.overlap, rel=2e-3)
 
 
+ROBUST_LOOP_CASES = [
+    ("point_to_plane", 1, dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),
+    ("point_to_plane", 3, dict(robustFct="huber", tuning=1.5, scaleEstimator="mad", nbIterationForScale=3)),
+    ("point_to_point", 1, dict(robustFct="welsch", tuning=2.0, scaleEstimator="mad", distanceType="point2plane")),
+    ("point_to_plane", 1, dict(robustFct="cauchy", tuning=0.05, scaleEstimator="berg")),
+    ("point_to_point", 1, dict(robustFct="tukey", tuning=3.0, scaleEstimator="none", approximation=0.9)),
+]
+
+
+@pytest.mark.parametrize("minimizer,knn,rp", ROBUST_LOOP_CASES)
+def test_robust_scale_in_the_loop_kernel(pair3d, minimizer, knn, rp):
+    """RobustOutlierFilter inside the persistent loop kernel (mad / berg scale through exact radix selects between grid barriers,
+    loop.cu loop_exact_median) against the kernel-per-step path (two device sorts, outlier.cu; nn_variant bit 26): the same
+    order statistics, so the same scale bit for bit -- poses agree to the fixed-point rounding of the loop's sums."""
+    from norlab_icp_mapper_b200.icp import ICP
+    outs = {}
+    for name, variant in (("loop", 0), ("steps", 0x4000000)):
+        cfg = make_config(dim=3, knn=knn, max_dist=1.0, outliers=(("robust", rp),), minimizer=minimizer, max_iteration_count=12, nn_variant=variant)
+        g = ICP(cfg)
+        g.set_trace(True)
+        g.set_map(pair3d["map"], pair3d["normals"])
+        T = g(pair3d["reading"])
+        outs[name] = (T, g.last_result, g.trace(), g.timing())
+        g.close()
+    assert outs["loop"][3].loop_iterations > 0 and outs["steps"][3].loop_iterations == 0  # (each really took its path)
+    assert outs["loop"][1].iterations == outs["steps"][1].iterations == 12
+    assert outs["loop"][1].pairs_last_iter == outs["steps"][1].pairs_last_iter
+    for a, b in zip(outs["loop"][2], outs["steps"][2]):  # every iteration's T_iter
+        er, et = synth.pose_error(a, b)
+        assert er <= 1e-6 and et <= 1e-5, (er, et)
+    assert outs["loop"][1].overlap == pytest.approx(outs["steps"][1].overlap, rel=1e-5)
+
+
+def test_robust_scale_in_the_loop_kernel_three_level_select():
+    """A reading large enough that the median's radix bucket overflows the in-kernel candidate list (4096 keys): the select
+    falls back to its two further global levels.  Same poses as the kernel-per-step path."""
+    from norlab_icp_mapper_b200.icp import ICP
+    d = synth.make_pair_3d(n_map=400_000, n_scan=400_000, seed=77)
+    outs = {}
+    for name, variant in (("loop", 0), ("steps", 0x4000000)):
+        cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("robust", dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),),
+                          minimizer="point_to_plane", max_iteration_count=6, nn_variant=variant)
+        g = ICP(cfg)
+        g.set_trace(True)
+        g.set_map(d["map"], d["normals"])
+        for rep in range(2):  # (twice: the select's histogram regions must come back clean)
+            T = g(d["reading"])
+        outs[name] = (T, g.last_result, g.trace())
+        g.close()
+    assert outs["loop"][1].pairs_last_iter == outs["steps"][1].pairs_last_iter
+    for a, b in zip(outs["loop"][2], outs["steps"][2]):
+        er, et = synth.pose_error(a, b)
+        assert er <= 1e-6 and et <= 1e-5, (er, et)
+
+
 def test_robust_point2plane_needs_reference_normals(pair3d):
     from norlab_icp_mapper_b200.icp import ICP, B200ICPError
     cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("robust", dict(distanceType="point2plane")),), minimizer="point_to_point",
