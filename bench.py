@@ -19,12 +19,13 @@ the 2 000 000-point map already installed by setMap.  Prints ONE JSON line (rank
             (b200icp_register_batch, two contexts per GPU): 64 pairs (200k-pt scan vs 1M-pt submap),
             pair j on rank j mod N -- STRONG scaling, the pose all_gather inside the timed region
   extra     (N = 1) the other configurations: cfg2_hard (SURVEY 8d's 1/-1/3 degree perturbation),
-            cfg1-like, cfg4 (2-D, knn 8), cfg3 (500-scan online mapping), the search kernel on a
-            10 M-point map (> L2)
+            cfg2_robust (RobustOutlierFilter cauchy / mad instead of TrimmedDist), cfg1-like, cfg4 (2-D,
+            knn 8), cfg3 (500-scan online mapping), the search kernel on a 10 M-point map (> L2)
 
 N > 1 (torchrun): the headline stays config 2: every rank registers its own scan against its own map
-through the same entry points (independent pairs, no data-path collective) and the poses are
-all_gathered (NCCL) INSIDE every timed step; value = all scans / max-over-ranks time ("weak").
+through the same entry points (independent pairs, no data-path collective) and the K poses of the
+timed steps are all_gathered (NCCL) once, INSIDE the timed region; value = all scans / max-over-ranks
+time ("weak").
 
 --impl reference times the CPU oracle alone (the reference's own libpointmatcher build cannot be
 compiled here: its dependencies are absent), rank 0 only, with ALL host cores
@@ -61,7 +62,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg2_hard", "cfg1", "cfg4"],
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg2_hard", "cfg2_robust", "cfg1", "cfg4"],
                     help="the pair workload of the main line (default: BASELINE.json config 2)")
     ap.add_argument("--n-map", type=int, default=None)
     ap.add_argument("--n-scan", type=int, default=None)
@@ -82,7 +83,7 @@ WORKLOADS = {
                  dim=3, n_map=2_000_000, n_scan=100_000, iters=30, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),),
                  minimizer="point_to_plane", gen={},
                  icp="KDTreeMatcher{knn 1, maxDist 1.0, eps 0} + TrimmedDist{0.85} + PointToPlane + Counter{%d}",
-                 world="seed 1234+10*rank: 200x200 m ground + 40 boxes + 4 walls, 1 cm noise; scan within 80 m; "
+                 world="world and map seed 1234, scan seed 1235+10*rank: 200x200 m ground + 40 boxes + 4 walls, 1 cm noise; scan within 80 m; "
                        "initial error (0.30,-0.20,0.10) m / (0.3,-0.3,1.0) deg = 0.37 m / 1.1 deg"),
     "cfg2_hard": dict(label="cfg2_hard: as cfg2 with SURVEY 8d's initial error (0.30,-0.20,0.10) m / (1,-1,3) deg",
                       dim=3, n_map=2_000_000, n_scan=100_000, iters=30, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),),
@@ -90,6 +91,12 @@ WORKLOADS = {
                       icp="KDTreeMatcher{knn 1, maxDist 1.0, eps 0} + TrimmedDist{0.85} + PointToPlane + Counter{%d}",
                       world="as cfg2; initial error 0.37 m / 3.3 deg (4 m at 80 m range against maxDist 1 m: the reference "
                             "algorithm itself does not converge in 30 iterations)"),
+    "cfg2_robust": dict(label="cfg2_robust: as cfg2 with libpointmatcher's RobustOutlierFilter defaults instead of TrimmedDist",
+                        dim=3, n_map=2_000_000, n_scan=100_000, iters=30, knn=1, max_dist=1.0,
+                        outliers=(("robust", dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")),),
+                        minimizer="point_to_plane", gen={},
+                        icp="KDTreeMatcher{knn 1, maxDist 1.0, eps 0} + RobustOutlierFilter{cauchy, tuning 1, scaleEstimator mad} + PointToPlane + Counter{%d}",
+                        world="as cfg2 (two exact medians per iteration for the mad scale, inside the loop kernel)"),
     "cfg1": dict(label="cfg1-like: 41k-pt scan vs 41k-pt map, knn 6, maxDist 2, point-to-plane, 10 iters "
                        "(docs/MapperConfiguration.md:172-189 on synthetic clouds of the bundled scans' size)",
                  dim=3, n_map=41_400, n_scan=41_339, iters=10, knn=6, max_dist=2.0, outliers=(), minimizer="point_to_plane",
@@ -130,7 +137,8 @@ def make_data(w, rank=0):
     from norlab_icp_mapper_b200 import synth
     if w["dim"] == 2:
         return synth.make_pair_2d(n_map=w["n_map"], n_scan=w["n_scan"], seed=3000 + 10 * rank)
-    return synth.make_pair_3d(n_map=w["n_map"], n_scan=w["n_scan"], seed=1234 + 10 * rank, **w["gen"])
+    # every rank: the same world and map, its own scan of it (equal work per GPU: the weak-scaling figure measures the GPUs, not the scenes)
+    return synth.make_pair_3d(n_map=w["n_map"], n_scan=w["n_scan"], seed=1234, scan_seed=1235 + 10 * rank, **w["gen"])
 
 
 def _gen_cfg5_pair(j):
@@ -667,6 +675,8 @@ def run_b200(args):
     big_chunks = pool_map(_gen_map_chunk, [(9000 + i, 1_250_000) for i in range(8)]) if full_extras else None
     extra_data = {name: make_data(resolve(args, name), rank) for name in ("cfg2_hard", "cfg1", "cfg4")
                   if full_extras and name != args.workload}
+    if full_extras and args.workload == "cfg2":
+        extra_data["cfg2_robust"] = data  # (the same clouds, another outlier filter)
 
     env = Env()
     torch = env.torch

@@ -139,7 +139,7 @@ class World3D:
 
 def make_pair_3d(n_map=2_000_000, n_scan=100_000, seed=1234, world_size=(200.0, 200.0), n_boxes=40,
                  sensor=(3.0, -2.0, 1.5), sensor_rpy_deg=(0.0, 0.0, 20.0), scan_radius=80.0,
-                 dt=(0.30, -0.20, 0.10), drpy_deg=(0.3, -0.3, 1.0), noise=0.01):
+                 dt=(0.30, -0.20, 0.10), drpy_deg=(0.3, -0.3, 1.0), noise=0.01, scan_seed=None):
     """BASELINE.json config 2 (SURVEY.md 8d cfg 2) at the default sizes.
 
     Returns a dict with
@@ -151,7 +151,7 @@ def make_pair_3d(n_map=2_000_000, n_scan=100_000, seed=1234, world_size=(200.0, 
     """
     world = World3D(seed=seed, size=world_size, n_boxes=n_boxes)
     rng_m = np.random.default_rng(seed)
-    rng_s = np.random.default_rng(seed + 1)
+    rng_s = np.random.default_rng(seed + 1 if scan_seed is None else scan_seed)  # (scan_seed: another scan of the same world and map)
     P, N = world.sample(n_map, rng_m, noise=noise)
     T_true = make_T(sensor, sensor_rpy_deg)
     S, _ = world.sample(n_scan, rng_s, noise=noise, center=sensor, radius=scan_radius)
