@@ -129,6 +129,10 @@ def gather_records(rec, world, dist, device):
         return rec[None]
     import torch
     local = torch.from_numpy(rec).to(device)
+    if local.is_cuda:  # NCCL: one flat output, one kernel, one read-back
+        out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local)
+        return out.cpu().numpy()
     gathered = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     return np.stack([g.cpu().numpy() for g in gathered])  # [world, per_rank, n*n+2]
