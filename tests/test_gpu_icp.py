@@ -404,6 +404,52 @@ def test_robust_scale_in_the_loop_kernel_three_level_select():
         assert er <= 1e-6 and et <= 1e-5, (er, et)
 
 
+def test_robust_scale_in_the_loop_kernel_edge_cases(oracle):
+    """The in-kernel scale selects on the shapes the loop kernel treats specially: k > 1 with entries spilled out of the shared
+    memory cache (130 k points x knn 3), a 2-D reading, a reading smaller than the grid (one point per CTA, CTAs without any)
+    and a reading without a single neighbour within maxDist (ConvergenceError, as the kernel-per-step path and the oracle)."""
+    from norlab_icp_mapper_b200.icp import ICP
+    from norlab_icp_mapper_b200._lib import B200ICPError
+    rp = dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")
+    cases = [
+        ("spill", synth.make_pair_3d(n_map=200_000, n_scan=130_000, seed=78), dict(dim=3, knn=3, max_dist=1.0, minimizer="point_to_plane")),
+        ("2d", synth.make_pair_2d(n_map=50_000, n_scan=4_000, seed=3100), dict(dim=2, knn=2, max_dist=0.5, minimizer="point_to_point")),
+        ("tiny", synth.make_pair_3d(n_map=60_000, n_scan=100, seed=79), dict(dim=3, knn=1, max_dist=1.0, minimizer="point_to_plane")),
+    ]
+    for name, d, kw in cases:
+        outs = {}
+        for variant in (0, 0x4000000):
+            g = ICP(make_config(outliers=(("robust", rp),), max_iteration_count=8, nn_variant=variant, **kw))
+            g.set_map(d["map"], d.get("normals"))
+            for rep in range(2):
+                T = g(d["reading"])
+            outs[variant] = (T, g.last_result.pairs_last_iter, g.last_result.overlap, g.timing().loop_iterations)
+            g.close()
+        assert outs[0][3] > 0 and outs[0x4000000][3] == 0, name
+        assert outs[0][1] == outs[0x4000000][1], name
+        er, et = synth.pose_error(outs[0][0], outs[0x4000000][0])
+        assert er <= 1e-6 and et <= 1e-5, (name, er, et)
+        o = oracle.OracleICP(make_config(outliers=(("robust", rp),), max_iteration_count=8, **kw))
+        o.set_map(d["map"], d.get("normals"))
+        rc, T_o, res_o, _, _ = o.register(d["reading"])
+        er, et = synth.pose_error(outs[0][0], T_o)
+        assert rc == _abi.OK and er <= TOL_RAD and et <= TOL_M, (name, er, et)
+    # nothing within maxDist: the select finds no finite distance
+    d = cases[2][1]
+    far = d["reading"].copy()
+    far[:, :3] += 500.0
+    for variant in (0, 0x4000000):
+        g = ICP(make_config(dim=3, knn=1, max_dist=1.0, outliers=(("robust", rp),), minimizer="point_to_plane", max_iteration_count=8, nn_variant=variant))
+        g.set_map(d["map"], d["normals"])
+        with pytest.raises(B200ICPError) as ei:
+            g(far)
+        assert ei.value.status == _abi.ERR_CONVERGENCE
+        T = g(d["reading"])  # (and the context is usable afterwards: buffers left clean)
+        er, et = synth.pose_error(T, d["correction_true"])
+        assert er < 2e-2 and et < 0.3
+        g.close()
+
+
 def test_robust_point2plane_needs_reference_normals(pair3d):
     from norlab_icp_mapper_b200.icp import ICP, B200ICPError
     cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("robust", dict(distanceType="point2plane")),), minimizer="point_to_point",
