@@ -145,6 +145,7 @@ typedef struct b200icp_config {
                              bit 23 (0x800000) loop kernel, k > 1: collect-then-rank selection instead of the sorted-list insertion (slower; A/B)
                              bit 25 (0x2000000) PointDistance insert: unbounded 1-NN instead of the search bounded by minDistNewPoint
                              bit 26 (0x4000000) RobustOutlierFilter chains on the kernel-per-step path (scale from two device sorts) instead of the loop kernel
+                             bit 27 (0x8000000) loop kernel, RobustOutlierFilter: no one-barrier (predicted window) median select
                              bit 19 (0x80000) loop kernel: write the per-iteration development record (tools/gpu_loop_record.py) */
     int32_t outlier_mode[B200ICP_MAX_OUTLIER_FILTERS]; /* per filter: B200ICP_ROBUST_MODE(...) for RobustOutlierFilter, else 0 */
     int32_t checker_order; /* position of the Counter in the transformationCheckers list.  libpointmatcher runs the checkers in YAML

@@ -113,8 +113,12 @@ constexpr int kSlotBelow = kAccSlots, kSlotAbove = kAccSlots + 1, kSlotCand = kA
 constexpr int kIsumSlots = kAccSlots + 4;
 constexpr size_t kFastCandOff = 0;                                                          // float4 [2][kCandCap][2]
 constexpr size_t kFastCandEnd = kFastCandOff + 2 * (size_t)kCandCap * 2 * sizeof(float4);
-constexpr size_t kFastIsumOff = (kFastCandEnd + 127) / 128 * 128;                           // unsigned long long [3][kIsumSlots][16]
-constexpr size_t kFastBytes = kFastIsumOff + (size_t)kIsumBufs * kIsumSlots * kIsumStride * sizeof(unsigned long long);
+// (Robust's windowed median select, loop_window_median: key lists [2][kRselCap] before, counters [3][4 slots][16] after the accumulators)
+constexpr int kRselCap = 4096;
+constexpr size_t kFastRselListOff = (kFastCandEnd + 127) / 128 * 128;                       // uint32 [2][kRselCap]
+constexpr size_t kFastIsumOff = kFastRselListOff + 2 * (size_t)kRselCap * sizeof(uint32_t);  // unsigned long long [3][kIsumSlots][16]
+constexpr size_t kFastRselCntOff = kFastIsumOff + (size_t)kIsumBufs * kIsumSlots * kIsumStride * sizeof(unsigned long long);  // ull [3][4][16]
+constexpr size_t kFastBytes = kFastRselCntOff + (size_t)kIsumBufs * 4 * kIsumStride * sizeof(unsigned long long);
 // Two-barrier iteration: next to the level-0 histogram (bits [30:19]) a FINE histogram (64 bins per level-0 bucket, bits
 // [18:13]) over the 65 level-0 buckets around the previous limit (+- 2 octaves): when the quantile's bucket is among them
 // the window is one fine bin -- a few dozen candidates instead of a thousand -- and the four-warp finish applies.
@@ -359,6 +363,100 @@ __device__ __noinline__ bool loop_exact_median(const LoopSelCtx& c, int mode, fl
     return true;
 }
 
+// The same order statistic with ONE barrier when the previous iterations predict where it lies: keys below / above the window
+// [wlo, whi] (float bit patterns) are only counted, the keys inside are appended to a global list; after the barrier every CTA
+// reads the three counts, and -- if the rank n / 2 falls inside the window and the list did not overflow -- pulls the list and
+// selects locally.  Returns false when the prediction failed (the caller runs loop_exact_median).  `cnt` = this select's counter
+// set {below, inside, above} (one 128-byte line each), `cnt_stale` the set of the select before the previous one, zeroed here by
+// CTA 0 (three sets round-robin, as for the error sums); `list` is double-buffered on the select's parity.
+__device__ __noinline__ bool loop_window_median(const LoopSelCtx& c, int mode, float centre, uint32_t wlo, uint32_t whi, unsigned long long* cnt,
+                                                unsigned long long* cnt_stale, uint32_t* list, unsigned& epoch, uint32_t& out_bits) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    auto key_of = [&](int e) -> uint32_t {
+        int pos;
+        float d;
+        if (e < kCacheCap) {
+            pos = __float_as_int(c.s_pp[e].w);
+            d = c.s_d2[e];
+        } else {
+            const int ql = c.K == 1 ? e : e / c.K;
+            const long long qi = (((long long)(ql >> c.cshift) * gridDim.x + blockIdx.x) << c.cshift) + (ql & ((1 << c.cshift) - 1));
+            const long long pi = c.K == 1 ? qi : qi * c.K + (e - ql * c.K);
+            pos = __float_as_int(c.sp_pp[pi].w);
+            d = c.md2[pi];
+        }
+        if (!(pos >= 0 && d < CUDART_INF_F)) return 0xffffffffu;
+        return __float_as_uint(mode ? fabsf(d - centre) : d);
+    };
+    if (tid == 0) {
+        *c.s_res = 0;  // this CTA's keys below the window ...
+        *c.s_cnt = 0;  // ... and above it
+    }
+    __syncthreads();
+    uint32_t nb = 0, na = 0;
+    for (int e0 = 0; e0 < c.n_ent; e0 += kLoopThreads) {
+        const int e = e0 + tid;
+        const uint32_t k = e < c.n_ent ? key_of(e) : 0xffffffffu;
+        const bool counted = k != 0xffffffffu, inside = counted && k >= wlo && k <= whi;
+        nb += counted && k < wlo;
+        na += counted && k > whi;
+        const unsigned bal = __ballot_sync(0xffffffffu, inside);
+        if (bal) {  // (warp-uniform)
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(cnt + 1 * kIsumStride, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned long long slot = base + (unsigned long long)__popc(bal & ((1u << lane) - 1u));
+            if (inside && slot < (unsigned long long)kRselCap) __stcg(list + slot, k);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        na += __shfl_xor_sync(0xffffffffu, na, o);
+    }
+    if (lane == 0) {
+        if (nb) atomicAdd(c.s_res, nb);
+        if (na) atomicAdd(c.s_cnt, na);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (*c.s_res) atomicAdd(cnt + 0 * kIsumStride, (unsigned long long)*c.s_res);
+    } else if (tid == 32) {
+        if (*c.s_cnt) atomicAdd(cnt + 2 * kIsumStride, (unsigned long long)*c.s_cnt);
+    }
+    grid_barrier(c.bar_counter, epoch);
+    if (blockIdx.x == 0 && tid < 3) cnt_stale[tid * kIsumStride] = 0ull;
+    const uint32_t n_below = (uint32_t)umin64(__ldcg(cnt + 0 * kIsumStride), 0xffffffffull);
+    const uint32_t n_in = (uint32_t)umin64(__ldcg(cnt + 1 * kIsumStride), 0xffffffffull);
+    const uint32_t n_above = (uint32_t)umin64(__ldcg(cnt + 2 * kIsumStride), 0xffffffffull);
+    const uint32_t total = n_below + n_in + n_above, rank = total >> 1;
+    if (total == 0 || n_in > (uint32_t)kRselCap || rank < n_below || rank >= n_below + n_in) return false;  // (the same verdict in every CTA)
+    for (uint32_t i = tid; i < n_in; i += kLoopThreads) c.sh[i] = __ldcg(list + i);
+    const uint32_t W = whi - wlo;  // < 2^30 (window construction)
+    uint32_t r = rank - n_below, prefix = 0;
+#pragma unroll 1
+    for (int shift = 20; shift >= 0; shift -= 10) {
+        if (shift > 0 && (W >> shift) == 0u) continue;
+        c.sh2[tid] = 0u;
+        if (tid == 0) {
+            *c.s_bin = 0;
+            *c.s_res = 0;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n_in; i += kLoopThreads) {
+            const uint32_t o = c.sh[i] - wlo;
+            if (((o ^ prefix) >> (shift + 10)) == 0u) atomicAdd(&c.sh2[(o >> shift) & 1023u], 1u);
+        }
+        __syncthreads();
+        loop_pick<true>(c.sh2, 1024, r, false, 0.f, c.s_bin, c.s_res, c.s_cnt, c.s_warp);
+        r = *c.s_res;
+        prefix |= *c.s_bin << shift;
+        __syncthreads();
+    }
+    out_bits = wlo + prefix;
+    return true;
+}
+
 // Product of the weights of every outlier filter EXCEPT the quantile-based one (fast path: that one is
 // decided after the barrier).
 __device__ __forceinline__ float other_filters_weight(const IcpParams& prm, float d, const float* T, const float4* rn, const float4& fn) {
@@ -494,6 +592,16 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     for (int f = 0; f < prm.n_outlier; ++f)
         if (prm.outlier_kind[f] == B200ICP_OUTLIER_ROBUST) robust_f = f;
     bool l2_dirty = false;  // the last level of a three-level median select waits for its zeroing (loop_exact_median)
+    // Robust's two medians (of the distances, of their absolute deviations): the last value and the window predicted for the next
+    // iteration, the same in every CTA; n_rsel counts the windowed selects (counter set / list buffer in use)
+    // (shared memory, written by thread 0: registers are what this kernel is short of)
+    __shared__ float rsel_prev[2];
+    __shared__ uint32_t rsel_lo[2], rsel_hi[2], rsel_have[2], rsel_valid[2], n_rsel;
+    if (tid < 2) {
+        rsel_prev[tid] = 0.f;
+        rsel_lo[tid] = rsel_hi[tid] = rsel_have[tid] = rsel_valid[tid] = 0u;
+        n_rsel = 0u;
+    }
     const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
@@ -936,11 +1044,47 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     sc.K = K;
                     sc.cshift = cshift;
                     uint32_t med_bits = 0, dev_bits = 0;
-                    bool have = loop_exact_median(sc, 0, 0.f, hist, epoch, l2_dirty, med_bits);
-                    if (have && estimator == B200ICP_SCALE_MAD) {
-                        uint32_t* hb = hist + kHistStage1 + (n_hist & 1u) * kStage1Words;  // (the level-0 region may still be being zeroed)
-                        n_hist += 1;
-                        have = loop_exact_median(sc, 1, __uint_as_float(med_bits), hb, epoch, l2_dirty, dev_bits);
+                    unsigned long long* const rcnt = reinterpret_cast<unsigned long long*>(fastws + kFastRselCntOff);
+                    uint32_t* const rlist = reinterpret_cast<uint32_t*>(fastws + kFastRselListOff);
+                    bool have = true;
+                    for (int j = 0; j < 2 && have; ++j) {  // 0: median of the distances, 1: of their absolute deviations from it
+                        if (j == 1 && estimator != B200ICP_SCALE_MAD) break;
+                        uint32_t& bits = j ? dev_bits : med_bits;
+                        const float centre = j ? __uint_as_float(med_bits) : 0.f;
+                        bool done = false;
+                        if (rsel_valid[j] && !(variant_flags & 0x8000000)) {  // one barrier, when the window holds
+                            const uint32_t nr = n_rsel;
+                            done = loop_window_median(sc, j, centre, rsel_lo[j], rsel_hi[j], rcnt + (size_t)(nr % kIsumBufs) * 4 * kIsumStride,
+                                                      rcnt + (size_t)((nr + 2) % kIsumBufs) * 4 * kIsumStride, rlist + (size_t)(nr & 1u) * kRselCap,
+                                                      epoch, bits);
+                            __syncthreads();
+                            if (tid == 0) n_rsel = nr + 1;
+                        }
+                        if (!done) {
+                            uint32_t* h0 = hist;
+                            if (j) {  // (the level-0 region may still be being zeroed after the first select)
+                                h0 = hist + kHistStage1 + (n_hist & 1u) * kStage1Words;
+                                n_hist += 1;
+                            }
+                            have = loop_exact_median(sc, j, centre, h0, epoch, l2_dirty, bits);
+                            if (tid == 0) st.hist_iters += 1;  // (Robust chains: the selects that took two or more barriers)
+                        }
+                        __syncthreads();
+                        if (have && tid == 0) {  // next iteration's window: centred on this value, half-width from its last change
+                            const float v = __uint_as_float(bits);
+                            rsel_valid[j] = 0u;
+                            if (rsel_have[j] && v > 0.f && v < 1.0e30f) {
+                                const float a = fmaxf(win_gain * fabsf(v - rsel_prev[j]), 4.f * win_floor * v);
+                                if (a <= 2.f * win_max * v) {
+                                    rsel_lo[j] = __float_as_uint(fmaxf(v - a, 0.f));
+                                    rsel_hi[j] = __float_as_uint(v + a);
+                                    rsel_valid[j] = (rsel_hi[j] - rsel_lo[j]) < (1u << 30) ? 1u : 0u;
+                                }
+                            }
+                            rsel_have[j] = 1u;
+                            rsel_prev[j] = v;
+                        }
+                        __syncthreads();
                     }
                     if (!have) {  // LPM: ConvergenceError("no outlier to filter")
                         if (tid == 0) {
