@@ -734,12 +734,14 @@ static int32_t register_on_device(b200icp_ctx* ctx, const float* d_reading, int3
     // Cold search for iteration 0, then the whole loop in one persistent cooperative kernel.
     // (Per-kernel profiling and nn_variant bit 2 select the kernel-per-step path below instead.)
     const bool var_trimmed = p.quantile_filter >= 0 && p.outlier_kind[p.quantile_filter] == B200ICP_OUTLIER_VAR_TRIMMED_DIST;
-    // RobustOutlierFilter runs inside the loop kernel (its mad / berg scale through exact selects between grid barriers) unless
-    // the chain also holds a quantile filter (the loop's candidate tuples carry no weight) or the scale is the standard deviation
+    // RobustOutlierFilter runs inside the loop kernel (its mad / berg scale through exact selects between grid barriers) unless the
+    // scale is the standard deviation, or the chain also holds a quantile filter while the robust distance is point2plane under another
+    // minimiser (the candidate tuples of the windowed iterations then carry no normal to recompute the weight from)
     bool robust = false;
     for (int f = 0; f < p.n_outlier; ++f)
         if (p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST)
-            robust = robust || p.quantile_filter >= 0 || ((p.outlier_mode[f] >> 8) & 15) == B200ICP_SCALE_STD || (ctx->cfg.nn_variant & 0x4000000);
+            robust = robust || ((p.outlier_mode[f] >> 8) & 15) == B200ICP_SCALE_STD || (ctx->cfg.nn_variant & 0x4000000) ||
+                     (p.quantile_filter >= 0 && ((p.outlier_mode[f] >> 12) & 1) && p.minimizer != B200ICP_MIN_POINT_TO_PLANE);
     // (VarTrimmed -- and Robust in those cases -- estimate their ratio / scale with device-wide sorts between the steps: kernel-per-step path)
     // (a reading with a `maxSearchDist` descriptor: per-point radii ride in the reading's .w, which only the stand-alone search
     //  kernels read -- the sentinel max_r2 = -1 tells them to)

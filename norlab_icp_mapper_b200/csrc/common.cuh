@@ -363,6 +363,9 @@ size_t icp_loop_workspace_bytes();
 // margin3 = {gain, min [m], max [cell edges]}: extra search radius = clamp(gain * the query's last motion, min, max * h)
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
                             int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s);
+// the same with RobustOutlierFilter compiled in (loop_robust.cu); launch_icp_loop forwards the chains that hold one
+cudaError_t launch_icp_loop_robust(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
+                            int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s);
 // the part of the loop workspace that must be zero when the kernel starts (offset, bytes): cudaMemsetAsync before every launch
 void icp_loop_workspace_zero_range(size_t* offset, size_t* bytes);
 // ev_mid (optional): recorded between the select and the accumulate kernel (profiling).

@@ -53,6 +53,14 @@ namespace {
 #define B200_CTA_STAMP(buf, k) do { } while (0)
 #endif
 
+// This file is compiled twice: as loop.cu (chains without a RobustOutlierFilter: its scale selects and weights are compiled out,
+// which is worth 2 % of the headline kernel in registers and spills) and, through loop_robust.cu, with B200ICP_LOOP_ROBUST defined
+// (launch_icp_loop_robust, to which launch_icp_loop hands the chains that hold one).
+#ifdef B200ICP_LOOP_ROBUST
+constexpr bool kLoopRobust = true;
+#else
+constexpr bool kLoopRobust = false;
+#endif
 constexpr int kLoopThreads = 1024;
 constexpr int kLoopWarps = kLoopThreads / 32;
 constexpr int kLoopG = 4;                       // lanes per query in the search phase
@@ -477,6 +485,18 @@ __device__ __forceinline__ float other_filters_weight(const IcpParams& prm, floa
     return w;
 }
 
+// RobustOutlierFilter's weight of a CANDIDATE pair, recomputed after the barrier from its tuple (ta = (p, dist2 bits), tb = v):
+// point2point distances are the tuple's own bits; point2plane (point-to-plane minimiser only: v = (n, (p - q) . n)) divides the
+// residual by |n|.  Out of line: the finish paths are short of registers and this runs for a few dozen pairs per iteration.
+__device__ __noinline__ float robust_candidate_weight(int mode, float tuning, float approximation, float scale, float4 ta, float4 tb) {
+    float dist = ta.w;
+    if ((mode >> 12) & 1) {
+        const float dot = tb.w / sqrtf(tb.x * tb.x + tb.y * tb.y + tb.z * tb.z);
+        dist = dot * dot;
+    }
+    return robust_weight(mode, tuning, approximation, scale, dist);
+}
+
 // The error-minimiser products of one kept pair (same expressions as accumulate_entry).
 // MIN 0: v = (n.x, n.y, n.z, (p - q).n);  MIN 1: v = (q.x, q.y, q.z, *).
 template <int MIN>
@@ -588,9 +608,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     unsigned epoch = 0;
     uint32_t n_runs = 0, n_hist = 0;  // publish/finish rounds (stage-1 histograms) so far: parity selects the double buffer
     const bool use_quantile = prm.quantile_filter >= 0;
-    int robust_f = -1;  // the chain's RobustOutlierFilter (at most one)
-    for (int f = 0; f < prm.n_outlier; ++f)
-        if (prm.outlier_kind[f] == B200ICP_OUTLIER_ROBUST) robust_f = f;
+    int robust_f = -1;  // the chain's RobustOutlierFilter (at most one); compiled in only in loop_robust.cu's copy of this kernel
+    if (kLoopRobust)
+        for (int f = 0; f < prm.n_outlier; ++f)
+            if (prm.outlier_kind[f] == B200ICP_OUTLIER_ROBUST) robust_f = f;
     bool l2_dirty = false;  // the last level of a three-level median select waits for its zeroing (loop_exact_median)
     // Robust's two medians (of the distances, of their absolute deviations): the last value and the window predicted for the next
     // iteration, the same in every CTA; n_rsel counts the windowed selects (counter set / list buffer in use)
@@ -1249,7 +1270,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                                 else
                                     v = pp;
                                 float w = wo;
-                                if (robust_f >= 0) {  // (never next to a quantile filter here: the candidates' weight is one)
+                                if (robust_f >= 0) {  // (candidates: recomputed after the barrier, robust_candidate_weight)
                                     const int mode = prm.outlier_mode[robust_f];
                                     float dist = d;
                                     if ((mode >> 12) & 1) {  // point2plane: (n . (p - q))^2, n normalised (the host checked the map has normals)
@@ -1261,6 +1282,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                                     w *= robust_weight(mode, prm.outlier_param[robust_f], prm.outlier_param2[robust_f], st.robust_scale, dist);
                                 }
                                 if (cls == 0 && w != 0.f) add_pair<MIN>(acc, w, p, v);
+                                if (w == 0.f) p.x = CUDART_NAN_F;  // (a candidate the robust function drops: counted for the quantile only)
                             }
                             if (cls == 1 || in_rank) {  // a candidate dropped by another filter still takes part in the quantile: p.x = NaN marks it
                                 is_cand = true;
@@ -1412,7 +1434,13 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                         float acc2[NS];
 #pragma unroll
                         for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
-                        if (kept) add_pair<MIN>(acc2, 1.f, make_float3(ca[0].x, ca[0].y, ca[0].z), cb[0]);
+                        if (kept) {
+                            float cw = 1.f;
+                            if (robust_f >= 0)
+                                cw = robust_candidate_weight(prm.outlier_mode[robust_f], prm.outlier_param[robust_f], prm.outlier_param2[robust_f],
+                                                             st.robust_scale, make_float4(0.f, 0.f, 0.f, __uint_as_float(mine)), cb[0]);
+                            if (cw != 0.f) add_pair<MIN>(acc2, cw, make_float3(ca[0].x, ca[0].y, ca[0].z), cb[0]);
+                        }
                         bool range_ok = true;
                         int f[32];
 #pragma unroll
@@ -1494,7 +1522,11 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                             float acc2[NS];
 #pragma unroll
                             for (int i = 0; i < NS; ++i) acc2[i] = 0.f;
-                            add_pair<MIN>(acc2, 1.f, make_float3(ca[j].x, ca[j].y, ca[j].z), cb[j]);
+                            float cw = 1.f;
+                            if (robust_f >= 0)
+                                cw = robust_candidate_weight(prm.outlier_mode[robust_f], prm.outlier_param[robust_f], prm.outlier_param2[robust_f],
+                                                             st.robust_scale, make_float4(0.f, 0.f, 0.f, ca[j].w), cb[j]);
+                            if (cw != 0.f) add_pair<MIN>(acc2, cw, make_float3(ca[j].x, ca[j].y, ca[j].z), cb[j]);
 #pragma unroll
                             for (int i = 0; i < NS; ++i) {
                                 const float sv = acc2[i] * s_cscale[i];
@@ -1844,11 +1876,13 @@ cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
 
 }  // namespace
 
+#ifndef B200ICP_LOOP_ROBUST
 size_t icp_loop_workspace_bytes() { return kFastBytes; }
 void icp_loop_workspace_zero_range(size_t* offset, size_t* bytes) {
     *offset = kFastIsumOff;
     *bytes = kFastBytes - kFastIsumOff;
 }
+#endif
 
 template <int GK>
 cudaError_t launch_loop_g(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
@@ -1858,8 +1892,16 @@ cudaError_t launch_loop_g(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
     return launch_loop_t<2, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
 }
 
+#ifdef B200ICP_LOOP_ROBUST
+cudaError_t launch_icp_loop_robust(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
+                                   int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s) {
+#else
 cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
                             int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s) {
+    for (int f = 0; f < p.n_outlier; ++f)
+        if (p.outlier_kind[f] == B200ICP_OUTLIER_ROBUST)
+            return launch_icp_loop_robust(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
+#endif
     if (p.knn < 1 || p.knn > 32 || !b.fastws || !b.spill_pp || !b.spill_nv) return cudaErrorInvalidValue;
     if (p.knn == 1) return launch_loop_g<4>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
     // k > 1: lanes per query >= k (lane j holds the j-th best); a reading too small to fill the SMs gets more lanes per query

@@ -382,6 +382,39 @@ def test_robust_scale_in_the_loop_kernel(pair3d, minimizer, knn, rp):
     assert outs["loop"][1].overlap == pytest.approx(outs["steps"][1].overlap, rel=1e-5)
 
 
+def test_robust_next_to_a_quantile_filter_in_the_loop_kernel(oracle, pair3d):
+    """TrimmedDist / MedianDist + RobustOutlierFilter in one chain: the windowed iterations recompute the M-estimator weight of
+    their candidate pairs after the barrier (robust_candidate_weight).  Same poses as the kernel-per-step path and the oracle."""
+    from norlab_icp_mapper_b200.icp import ICP
+    chains = [
+        ("point_to_plane", (("trimmed", 0.8), ("robust", dict(robustFct="cauchy", tuning=1.0, scaleEstimator="mad")))),
+        ("point_to_plane", (("robust", dict(robustFct="tukey", tuning=2.5, scaleEstimator="mad", distanceType="point2plane")), ("median", 3.0))),
+        ("point_to_point", (("trimmed", 0.9), ("robust", dict(robustFct="huber", tuning=1.5, scaleEstimator="berg")))),
+    ]
+    for minimizer, chain in chains:
+        outs = {}
+        for name, variant in (("loop", 0), ("steps", 0x4000000)):
+            cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=chain, minimizer=minimizer, max_iteration_count=14, nn_variant=variant)
+            g = ICP(cfg)
+            g.set_trace(True)
+            g.set_map(pair3d["map"], pair3d["normals"])
+            T = g(pair3d["reading"])
+            outs[name] = (T, g.last_result, g.trace(), g.timing())
+            g.close()
+        tm = outs["loop"][3]
+        assert tm.loop_iterations > 0 and outs["steps"][3].loop_iterations == 0
+        assert tm.loop_fast_iterations > 0  # (one-barrier iterations with candidates took part)
+        assert abs(outs["loop"][1].pairs_last_iter - outs["steps"][1].pairs_last_iter) <= 2
+        for a, b in zip(outs["loop"][2], outs["steps"][2]):
+            er, et = synth.pose_error(a, b)
+            assert er <= 2e-6 and et <= 2e-5, (chain, er, et)
+        o = oracle.OracleICP(make_config(dim=3, knn=1, max_dist=1.0, outliers=chain, minimizer=minimizer, max_iteration_count=14))
+        o.set_map(pair3d["map"], pair3d["normals"])
+        rc, T_o, res_o, _, _ = o.register(pair3d["reading"])
+        er, et = synth.pose_error(outs["loop"][0], T_o)
+        assert rc == _abi.OK and er <= TOL_RAD and et <= TOL_M, (chain, er, et)
+
+
 def test_robust_scale_in_the_loop_kernel_three_level_select():
     """A reading large enough that the median's radix bucket overflows the in-kernel candidate list (4096 keys): the select
     falls back to its two further global levels.  Same poses as the kernel-per-step path."""
