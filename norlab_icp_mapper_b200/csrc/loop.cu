@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cmath>
 #include <type_traits>
 
@@ -68,10 +69,16 @@ constexpr int kLoopG = 4;                       // lanes per query in the search
 // 32 a 10 k-point reading gives 17 of the 148 CTAs 96 points and the others 64, and everybody waits for those 17)
 constexpr int kChunkShiftLarge = 5, kChunkShiftSmall = 3;
 constexpr int kSmallReading = 64 * 1024, kTinyReading = 16 * 1024;
-constexpr int kCacheCap = 2048;                 // queries per CTA whose match state lives in shared memory (the rest spills to global)
-// dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[cap] | the fine histogram of a
+constexpr int kCacheCapMax = 2048;              // entries per CTA whose match state can live in shared memory (the rest spills to global)
+// The cache is sized per launch (`cache_cap` = the entries a CTA of this registration owns, rounded up to 32, at most kCacheCapMax):
+// the shared memory it does not take stays L1 -- cfg 2 needs 704 of the 2048 entries (55 KB instead of 128 KB dynamic), which
+// more than doubles the L1 the search phase's point loads go through (hard variant: loop 1.40 -> 1.35 ms).
+// dynamic shared memory: float4 r4[cap] | float4 pp[cap] | float4 nv[cap] | float d2[cap] | uint32 list[1024] | the fine histogram of a
 // two-barrier iteration
-constexpr size_t kLoopCacheBytes = (size_t)kCacheCap * (3 * sizeof(float4) + sizeof(float) + sizeof(uint32_t));
+constexpr size_t kLoopEntryBytes = 3 * sizeof(float4) + sizeof(float);
+constexpr size_t kLoopListBytes = (size_t)kLoopThreads * sizeof(uint32_t);  // the search phase's work list (one block of entries)
+constexpr size_t kLoopCacheBytes = (size_t)kCacheCapMax * kLoopEntryBytes + kLoopListBytes;
+__host__ __device__ constexpr size_t loop_cache_bytes(int cache_cap) { return (size_t)cache_cap * kLoopEntryBytes + kLoopListBytes; }
 constexpr size_t kLoopScratchBytes = 4160 * sizeof(uint32_t);
 constexpr size_t kLoopDynSmem = kLoopCacheBytes + kLoopScratchBytes;
 // Exact quantile inside the loop kernel: level 0 = 12 bits [30:19] of the float pattern (4096 bins,
@@ -134,6 +141,14 @@ constexpr int kFineSpan = 32, kFineBuckets = 2 * kFineSpan + 1, kFineShift = 13,
 constexpr int kFineBins = kFineBuckets * kFineSub;  // 4160
 constexpr int kStage1Words = kSel0Bins + kFineBins;
 static_assert((size_t)kFineBins * sizeof(uint32_t) <= kLoopScratchBytes, "the scratch region of the dynamic shared memory holds the fine histogram");
+
+// log2 of the chunk of consecutive reading points the CTAs are dealt (host: sizes the match cache; device: the dealing itself)
+__host__ __device__ inline int loop_chunk_shift(long long nq, int variant_flags) {
+    int cshift = (nq <= kSmallReading || (variant_flags & 512)) ? kChunkShiftSmall : kChunkShiftLarge;
+    if (nq <= kTinyReading) cshift = 0;  // plain round-robin (cfg 4, 10 k points: another -3.6 %)
+    if ((variant_flags >> 10) & 3) cshift = ((variant_flags >> 10) & 3) - 1;  // development: chunks of 1 / 2 / 4
+    return cshift;
+}
 
 __device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -232,13 +247,13 @@ __device__ uint32_t loop_pick(const uint32_t* hist, int nbins, uint32_t rank, bo
 // (`l2_dirty`: zeroed after the next barrier).  Returns false when there is no finite distance (buffers left clean).
 struct LoopSelCtx {
     const float4* s_pp;   // match cache: (x, y, z, bit-cast position) ...
-    const float* s_d2;    // ... and squared distance of the entries below kCacheCap
+    const float* s_d2;    // ... and squared distance of the entries below cache_cap
     const float4* sp_pp;  // the same for the spilled entries (global memory, indexed by match row)
     const float* md2;
     uint32_t *sh, *sh2, *s_bin, *s_res, *s_cnt, *s_stage, *s_base, *s_warp;
     uint32_t* hist;
     unsigned* bar_counter;
-    int n_ent, K, cshift;
+    int n_ent, K, cshift, cache_cap;
 };
 
 __device__ __noinline__ bool loop_exact_median(const LoopSelCtx& c, int mode, float centre, uint32_t* h0, unsigned& epoch, bool& l2_dirty,
@@ -247,7 +262,7 @@ __device__ __noinline__ bool loop_exact_median(const LoopSelCtx& c, int mode, fl
     auto key_of = [&](int e) -> uint32_t {  // 0xffffffff: not a finite match distance
         int pos;
         float d;
-        if (e < kCacheCap) {
+        if (e < c.cache_cap) {
             pos = __float_as_int(c.s_pp[e].w);
             d = c.s_d2[e];
         } else {
@@ -383,7 +398,7 @@ __device__ __noinline__ bool loop_window_median(const LoopSelCtx& c, int mode, f
     auto key_of = [&](int e) -> uint32_t {
         int pos;
         float d;
-        if (e < kCacheCap) {
+        if (e < c.cache_cap) {
             pos = __float_as_int(c.s_pp[e].w);
             d = c.s_d2[e];
         } else {
@@ -538,8 +553,10 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     int32_t* __restrict__ mpos, float* __restrict__ md2, IcpState* __restrict__ gst, uint32_t* __restrict__ hist,
                     double* __restrict__ partials, unsigned* __restrict__ bar_counter, float* __restrict__ trace, int max_iters,
                     int variant_flags, char* __restrict__ fastws, float win_gain, float win_floor, float win_max,
-                    float4* __restrict__ sp_pp, float4* __restrict__ sp_nv, float margin_gain, float margin_min, float margin_max, float q_bound) {
+                    float4* __restrict__ sp_pp, float4* __restrict__ sp_nv, float margin_gain, float margin_min, float margin_max, float q_bound,
+                    int cache_cap) {
     constexpr int NS = SumLayout<MIN>::N;
+    const int kCacheCap = cache_cap;  // (a launch parameter: see kCacheCapMax)
     __shared__ IcpState st;
     __shared__ uint32_t sh[kSel0Bins];   // radix level 0 histogram, then staging / the candidate list
     __shared__ __align__(16) uint32_t sh2[1024];  // local radix levels / the candidates' keys
@@ -563,7 +580,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     float4* const s_nv = s_pp + kCacheCap;   // (normal of the matched point, bound L)
     float* const s_d2 = reinterpret_cast<float*>(s_nv + kCacheCap);
     uint32_t* const s_list = reinterpret_cast<uint32_t*>(s_d2 + kCacheCap);
-    unsigned char* const s_big = dyn_smem + kLoopCacheBytes;
+    unsigned char* const s_big = dyn_smem + loop_cache_bytes(cache_cap);
     uint32_t* const s_fine = reinterpret_cast<uint32_t*>(s_big);    // two-barrier iteration: fine histogram (kFineBins words)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -626,9 +643,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
     const bool sn_active = prm.rnrm != nullptr && nrm != nullptr;  // SurfaceNormalOutlierFilter has what it needs (else: all ones)
     const int lig = lane & (kLoopG - 1);
     const unsigned gmask = group_mask<kLoopG>(lane);
-    int cshift = (nq <= kSmallReading || (variant_flags & 512)) ? kChunkShiftSmall : kChunkShiftLarge;
-    if (nq <= kTinyReading) cshift = 0;  // plain round-robin (cfg 4, 10 k points: another -3.6 %)
-    if ((variant_flags >> 10) & 3) cshift = ((variant_flags >> 10) & 3) - 1;  // development: chunks of 1 / 2 / 4
+    const int cshift = loop_chunk_shift(nq, variant_flags);
     const int kChunk = 1 << cshift;
     // This CTA's slice: n_ql reading points (chunks of kChunk consecutive points, dealt round-robin: only the globally last
     // chunk is partial, so local query ql <-> reading point qi_of(ql) is contiguous) and K entries each -- one per neighbour.
@@ -1064,6 +1079,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
                     sc.n_ent = n_ent;
                     sc.K = K;
                     sc.cshift = cshift;
+                    sc.cache_cap = cache_cap;
                     uint32_t med_bits = 0, dev_bits = 0;
                     unsigned long long* const rcnt = reinterpret_cast<unsigned long long*>(fastws + kFastRselCntOff);
                     uint32_t* const rlist = reinterpret_cast<uint32_t*>(fastws + kFastRselListOff);
@@ -1820,7 +1836,7 @@ __global__ void __launch_bounds__(kLoopThreads, 1)
 
 template <int MIN, int GK>
 cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                          int variant_flags, const float* win3, const float* margin3, cudaStream_t s) {
+                          int variant_flags, const float* win3, const float* margin3, int64_t nq, cudaStream_t s) {
     // Function attributes are PER DEVICE: one flag per (instantiation, device ordinal).  Contexts on different GPUs of one
     // process (b200icp_register_batch) each need the opt-in; concurrent contexts may race to set it, which is harmless
     // (same value, idempotent call), hence atomics only to keep the flags themselves well-defined.
@@ -1869,9 +1885,40 @@ cudaError_t launch_loop_t(const IcpParams& p, const GridIndex& g, IcpBuffers& b,
         }
         q_bound = (float)std::sqrt(q2) + 1.f;
     }
+    // match cache: as many entries as the busiest CTA owns (chunks dealt round-robin, k entries per point), the rest of the
+    // shared memory stays L1; the carve-out hint follows (per function and device, re-set only when the need changes)
+    int cache_cap = kCacheCapMax;
+    {
+        const int cshift = loop_chunk_shift(nq, variant_flags);
+        const long long chunks_total = ((long long)nq + (1ll << cshift) - 1) >> cshift;
+        const long long per_cta = ((chunks_total + blocks - 1) / blocks) << cshift;
+        const long long entries = per_cta * std::max(p.knn, 1);
+        cache_cap = (int)std::min<long long>(kCacheCapMax, std::max<long long>(32, (entries + 31) / 32 * 32));
+        static const bool full_cache = getenv("B200ICP_FULL_CACHE") != nullptr;  // development: always the largest cache (A/B)
+        if (full_cache) cache_cap = kCacheCapMax;
+    }
+    const size_t dyn_smem = loop_cache_bytes(cache_cap) + kLoopScratchBytes;
+    {
+        static std::atomic<int> carveout_of[kMaxDevices];  // last hint + 1
+        cudaFuncAttributes fa;
+        static std::atomic<int> static_smem{-1};
+        int ss = static_smem.load(std::memory_order_acquire);
+        if (ss < 0) {
+            cudaError_t e = cudaFuncGetAttributes(&fa, icp_loop_kernel<MIN, GK>);
+            if (e != cudaSuccess) return e;
+            ss = (int)fa.sharedSizeBytes;
+            static_smem.store(ss, std::memory_order_release);
+        }
+        const int pct = (int)std::min<size_t>(100, ((size_t)ss + dyn_smem + 1024) * 100 / (228 * 1024) + 1);
+        if (!cacheable || carveout_of[dev].load(std::memory_order_acquire) != pct + 1) {
+            cudaError_t e = cudaFuncSetAttribute(icp_loop_kernel<MIN, GK>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            if (e != cudaSuccess) return e;
+            if (cacheable) carveout_of[dev].store(pct + 1, std::memory_order_release);
+        }
+    }
     void* args[] = {&prm, &view, &nrm, &reading, &mpos, &md2, &st, &hist, &partials, &bar_counter, &trace, &max_iters, &variant_flags,
-                    &fastws, &win_gain, &win_floor, &win_max, &sp_pp, &sp_nv, &margin_gain, &margin_min, &margin_max, &q_bound};
-    return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN, GK>, dim3(blocks), dim3(kLoopThreads), args, kLoopDynSmem, s);
+                    &fastws, &win_gain, &win_floor, &win_max, &sp_pp, &sp_nv, &margin_gain, &margin_min, &margin_max, &q_bound, &cache_cap};
+    return cudaLaunchCooperativeKernel((void*)icp_loop_kernel<MIN, GK>, dim3(blocks), dim3(kLoopThreads), args, dyn_smem, s);
 }
 
 }  // namespace
@@ -1886,10 +1933,10 @@ void icp_loop_workspace_zero_range(size_t* offset, size_t* bytes) {
 
 template <int GK>
 cudaError_t launch_loop_g(const IcpParams& p, const GridIndex& g, IcpBuffers& b, unsigned* bar_counter, int max_iters, int n_sms,
-                          int variant, const float* win3, const float* margin3, cudaStream_t s) {
-    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE) return launch_loop_t<0, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
-    if (p.minimizer == B200ICP_MIN_POINT_TO_POINT) return launch_loop_t<1, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
-    return launch_loop_t<2, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+                          int variant, const float* win3, const float* margin3, int64_t nq, cudaStream_t s) {
+    if (p.minimizer == B200ICP_MIN_POINT_TO_PLANE) return launch_loop_t<0, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
+    if (p.minimizer == B200ICP_MIN_POINT_TO_POINT) return launch_loop_t<1, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
+    return launch_loop_t<2, GK>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
 }
 
 #ifdef B200ICP_LOOP_ROBUST
@@ -1903,13 +1950,13 @@ cudaError_t launch_icp_loop(const IcpParams& p, const GridIndex& g, IcpBuffers& 
             return launch_icp_loop_robust(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
 #endif
     if (p.knn < 1 || p.knn > 32 || !b.fastws || !b.spill_pp || !b.spill_nv) return cudaErrorInvalidValue;
-    if (p.knn == 1) return launch_loop_g<4>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    if (p.knn == 1) return launch_loop_g<4>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
     // k > 1: lanes per query >= k (lane j holds the j-th best); a reading too small to fill the SMs gets more lanes per query
     int lanes = p.knn <= 8 ? 8 : (p.knn <= 16 ? 16 : 32);
     while (lanes < 32 && nq * lanes <= (int64_t)n_sms * kLoopThreads) lanes *= 2;
-    if (lanes == 8) return launch_loop_g<8>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
-    if (lanes == 16) return launch_loop_g<16>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
-    return launch_loop_g<32>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, s);
+    if (lanes == 8) return launch_loop_g<8>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
+    if (lanes == 16) return launch_loop_g<16>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
+    return launch_loop_g<32>(p, g, b, bar_counter, max_iters, n_sms, variant, win3, margin3, nq, s);
 }
 
 }  // namespace b200
