@@ -16,7 +16,7 @@ the 2 000 000-point map already installed by setMap.  Prints ONE JSON line (rank
             libnabo) on the same host: all cores and one thread, per-phase times, and a
             scipy cKDTree(workers=-1) cross-check of the oracle's nearest-neighbour speed
   batched   BASELINE.json config 5 through the product's batched entry point
-            (b200icp_register_batch, two contexts per GPU): 64 pairs (200k-pt scan vs 1M-pt submap),
+            (b200icp_register_batch, four contexts per GPU, two when a rank holds fewer than 32 pairs): 64 pairs (200k-pt scan vs 1M-pt submap),
             pair j on rank j mod N -- STRONG scaling, the pose all_gather inside the timed region
   extra     (N = 1) the other configurations: cfg2_hard (SURVEY 8d's 1/-1/3 degree perturbation),
             cfg2_robust (RobustOutlierFilter cauchy / mad instead of TrimmedDist), cfg1-like, cfg4 (2-D,
@@ -523,8 +523,12 @@ def bench_batched(env, pairs_host, n_pairs_total, passes=3):
     assert len(idx) == len(mine)
     by_j = dict(zip(idx, mine))
     results = {}
-    default_ctx = int(os.environ.get("B200ICP_BATCH_CONTEXTS", "2"))
-    for n_ctx in (default_ctx, 1, 3, 4):
+    # four contexts per GPU: uploads, index builds, cold searches and loop kernels (each on a quarter of the SMs) of different pairs
+    # overlap -- 1 / 2 / 3 / 4 contexts: 562 / 800 / 950 / 990 pairs/s on one GPU (the sweep is part of the N = 1 line)
+    # (with fewer than 8 pairs per context the fill and drain of the pipeline outweigh the overlap: 16 pairs per rank at N = 4 ran
+    #  3118 pairs/s on two contexts and 2560-3240 on four)
+    default_ctx = int(os.environ.get("B200ICP_BATCH_CONTEXTS", "4" if len(mine) >= 32 else "2"))
+    for n_ctx in (default_ctx, 1, 2, 3):
         if n_ctx in results:
             continue
         eng = batched.BatchEngine(cfg, devices=(env.local_rank,), contexts_per_device=n_ctx)
