@@ -185,7 +185,8 @@ typedef struct b200icp_timing {
     float loop_total_ms;      /* ... first iteration start to last iteration end (%globaltimer)        */
     int32_t loop_fast_iterations; /* ... iterations that ran with ONE device-wide barrier (predicted quantile window) */
     int32_t loop_searched_queries; /* ... queries (summed over the iterations) that needed a search; the others were proven unchanged */
-    int32_t loop_two_barrier_iterations; /* ... iterations that ran with TWO barriers (quantile bucket found by a histogram pass) */
+    int32_t loop_two_barrier_iterations; /* ... iterations that ran with TWO barriers (quantile bucket found by a histogram pass);
+                                            RobustOutlierFilter chains add their scale selects that needed more than one barrier */
     float loop_kernel_ms;     /* ... duration of the loop kernel's launch, CUDA events on ctx's stream */
 } b200icp_timing;
 
