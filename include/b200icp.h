@@ -136,7 +136,7 @@ typedef struct b200icp_config {
                              bit 7 (128) loop kernel: work list in plain entry order (no cost classes); k > 1: shell walk instead of the ball pass
                              bit 8 (256) cold k = 1 search: shell-walk kernel even when maxDist is small
                              bit 9 (512) loop kernel: deal the reading to the CTAs in chunks of 8 points whatever its size
-                             bits 10..11 loop kernel: value - 1 = log2 of that chunk size (1, 2, 4 points)
+                             bits 10..11 loop kernel: chunk size 1, 2 or 16 points (values 1, 2, 3)
                              bits 12..14 reading sort key: value - 1 = block shift (1 = full cell id; default shift 3)
                              bit 17 (0x20000) loop kernel: no fine histogram in the two-barrier iteration (window = the whole level-0 bucket)
                              bit 20 (0x100000) self k-NN (SurfaceNormal filters): TMA-staged candidate tiles (csrc/selfknn.cu) instead of the shell walk

@@ -146,7 +146,7 @@ static_assert((size_t)kFineBins * sizeof(uint32_t) <= kLoopScratchBytes, "the sc
 __host__ __device__ inline int loop_chunk_shift(long long nq, int variant_flags) {
     int cshift = (nq <= kSmallReading || (variant_flags & 512)) ? kChunkShiftSmall : kChunkShiftLarge;
     if (nq <= kTinyReading) cshift = 0;  // plain round-robin (cfg 4, 10 k points: another -3.6 %)
-    if ((variant_flags >> 10) & 3) cshift = ((variant_flags >> 10) & 3) - 1;  // development: chunks of 1 / 2 / 4
+    if ((variant_flags >> 10) & 3) cshift = ((variant_flags >> 10) & 3) == 3 ? 4 : ((variant_flags >> 10) & 3) - 1;  // development: chunks of 1 / 2 / 16
     return cshift;
 }
 
