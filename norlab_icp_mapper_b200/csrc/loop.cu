@@ -345,6 +345,9 @@ __device__ __noinline__ bool loop_exact_median(const LoopSelCtx& c, int mode, fl
         low = (b2 << 9) | *c.s_bin;
         __syncthreads();
     } else {
+#ifdef B200ICP_STAMPS
+        if (blockIdx.x == 0 && tid == 0) printf("loop_exact_median: three-level select (mode %d, bucket of %u keys)\n", mode, c1);
+#endif
         uint32_t rank = r1, pre = b1;
         for (int pass = 1; pass <= 2; ++pass) {
             const int nbins = (pass == 1) ? 2048 : 256;

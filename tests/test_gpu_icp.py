@@ -417,7 +417,8 @@ def test_robust_next_to_a_quantile_filter_in_the_loop_kernel(oracle, pair3d):
 
 def test_robust_scale_in_the_loop_kernel_three_level_select():
     """A reading large enough that the median's radix bucket overflows the in-kernel candidate list (4096 keys): the select
-    falls back to its two further global levels.  Same poses as the kernel-per-step path."""
+    falls back to its two further global levels (the stamped development build prints it: buckets of 4 900-7 300 keys, twelve
+    such selects per registration here).  Same poses as the kernel-per-step path."""
     from norlab_icp_mapper_b200.icp import ICP
     d = synth.make_pair_3d(n_map=400_000, n_scan=400_000, seed=77)
     outs = {}
