@@ -240,6 +240,19 @@ class Mapper:
         self._check(self._L.b200mapper_get_local_map(self._h, feat.ctypes.data, nrm.ctypes.data, st.n_local, C.byref(n)))
         return feat[:n.value], (None if np.isnan(nrm).all() else nrm[:n.value])
 
+    def getNewLocalMap(self):
+        """Mapper::getNewLocalMap (python/src/mapper.cpp:16): (True, features, normals or None) when the local map changed since
+        the last call (the flag is consumed, as upstream), else (False, None, None)."""
+        cap = int(self.stats().n_local) + 1024
+        n, avail = C.c_int64(), C.c_int32()
+        feat = np.zeros((cap, self.n), np.float32)
+        nrm = np.full((cap, self.dim), np.nan, np.float32)
+        self._check(self._L.b200mapper_get_new_local_map(self._h, feat.ctypes.data, nrm.ctypes.data, cap, C.byref(n), C.byref(avail)))
+        if not avail.value:
+            return False, None, None
+        nrm = nrm[:n.value]
+        return True, feat[:n.value].copy(), (None if np.isnan(nrm).all() else nrm.copy())
+
     def getMapProbabilityDynamic(self):
         """The probabilityDynamic descriptor of getMap(), or None when the map does not carry it."""
         n = C.c_int64()

@@ -72,6 +72,28 @@ def test_is_mapping_false_only_localises(oracle):
     m.close()
 
 
+def test_get_new_local_map_flag_is_consumed():
+    """Mapper::getNewLocalMap (Mapper.cpp / python/src/mapper.cpp:16): true with the local map once after an update, false until
+    the next one; a scan that only localises (isMapping off) does not raise the flag."""
+    from norlab_icp_mapper_b200.mapper import Mapper
+    cfg = make_config(dim=3, knn=1, max_dist=1.0, outliers=(("trimmed", 0.85),), minimizer="point_to_plane", max_iteration_count=15)
+    m = Mapper(cfg, True, False, True, False, surfaceNormalKnn=10)
+    scans = _scans(3)
+    m.processInput(scans[0][0], scans[0][2], 0.0)
+    ok, feat, nrm = m.getNewLocalMap()
+    assert ok and len(feat) == m.stats().n_local and nrm is not None and nrm.shape == (len(feat), 3)
+    local, _ = m.getLocalMap()
+    assert np.array_equal(feat, local)
+    assert m.getNewLocalMap() == (False, None, None)
+    m.setIsMapping(False)
+    m.processInput(scans[1][0], scans[1][2], 0.1)
+    assert m.getNewLocalMap()[0] is False
+    m.setIsMapping(True)
+    m.processInput(scans[2][0], scans[2][2], 0.2)
+    assert (m.stats().map_updated == 1) == m.getNewLocalMap()[0]
+    m.close()
+
+
 def test_update_conditions_and_validation():
     from norlab_icp_mapper_b200.mapper import Mapper
     from norlab_icp_mapper_b200._lib import B200ICPError
