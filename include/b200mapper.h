@@ -99,6 +99,15 @@ int32_t b200mapper_get_stats(b200mapper* m, b200mapper_stats* out);
 /* slabs applied by the last Map::updatePose, 7 ints each (see Map::lastUpdates) */
 int32_t b200mapper_get_window_updates(b200mapper* m, int32_t* out7, int32_t capacity);
 
+/* DataPoints::save / DataPoints::load for legacy VTK POLYDATA (host/IO.h) -- the disk format of maps, scans and map cells
+ * (examples/build_map_from_scans_and_trajectory.cpp:50,94; HardDriveCellManager.cpp:14-27).  No GPU involved; errors go to
+ * b200mapper_last_error(NULL).  save: normals / prob may be NULL.  load: call with features == NULL for *n and the flags, then
+ * with buffers of that capacity (normals, prob: NULL to skip; rows of NaN are never written -- check the flags). */
+int32_t b200mapper_vtk_save(const char* path, const float* features, int32_t feature_rows, int64_t n, const float* normals,
+                            const float* prob, int32_t binary);
+int32_t b200mapper_vtk_load(const char* path, int32_t dim, float* features, float* normals, float* prob, int64_t capacity, int64_t* n,
+                            int32_t* has_normals, int32_t* has_prob);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@
 
 #include <sstream>
 
+#include "IO.h"
 #include "Mapper.h"
 #include "YamlConfig.h"
 #include "b200mapper.h"
@@ -243,6 +244,31 @@ int32_t b200mapper_get_new_local_map(b200mapper* m, float* features, float* norm
         *available = m->mapper->getNewLocalMap(d) ? 1 : 0;
         *n = 0;
         if (*available) rc2 = copy_out(d, features, normals, capacity, n);
+    });
+    return rc != B200ICP_OK ? rc : rc2;
+}
+
+int32_t b200mapper_vtk_save(const char* path, const float* features, int32_t feature_rows, int64_t n, const float* normals,
+                            const float* prob, int32_t binary) {
+    if (!path || n < 0 || (n > 0 && !features) || (feature_rows != 3 && feature_rows != 4)) return B200ICP_ERR_INVALID_ARG;
+    return guarded(nullptr, [&] {
+        DataPoints d = wrap(features, feature_rows, n, normals);
+        if (prob) d.probabilityDynamic.assign(prob, prob + n);
+        io::saveVTK(d, std::string(path), binary != 0);
+    });
+}
+
+int32_t b200mapper_vtk_load(const char* path, int32_t dim, float* features, float* normals, float* prob, int64_t capacity, int64_t* n,
+                            int32_t* has_normals, int32_t* has_prob) {
+    if (!path || !n || (dim != 2 && dim != 3)) return B200ICP_ERR_INVALID_ARG;
+    int32_t rc2 = B200ICP_OK;
+    const int32_t rc = guarded(nullptr, [&] {
+        const DataPoints d = io::loadVTK(std::string(path), dim);
+        if (has_normals) *has_normals = d.normals.empty() ? 0 : 1;
+        if (has_prob) *has_prob = d.probabilityDynamic.empty() ? 0 : 1;
+        rc2 = copy_out(d, features, normals, capacity, n);
+        if (rc2 == B200ICP_OK && features && prob && !d.probabilityDynamic.empty())
+            std::memcpy(prob, d.probabilityDynamic.data(), d.probabilityDynamic.size() * sizeof(float));
     });
     return rc != B200ICP_OK ? rc : rc2;
 }

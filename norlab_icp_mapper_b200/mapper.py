@@ -17,6 +17,7 @@ SYMBOLS = ["b200mapper_create", "b200mapper_destroy", "b200mapper_last_error", "
            "b200mapper_process_input", "b200mapper_get_pose", "b200mapper_get_map", "b200mapper_get_new_local_map",
            "b200mapper_set_map", "b200mapper_get_is_mapping", "b200mapper_set_is_mapping", "b200mapper_trajectory_size",
            "b200mapper_get_trajectory", "b200mapper_get_stats", "b200mapper_get_window_updates", "b200mapper_process_raw_input",
+           "b200mapper_vtk_save", "b200mapper_vtk_load",
            "b200mapper_set_map_descriptors", "b200mapper_get_map_prob", "b200mapper_create_from_yaml", "b200mapper_yaml_summary", "b200mapper_map_update_in_flight", "b200mapper_wait_for_map_update", "b200mapper_get_local_map"]
 
 
@@ -104,6 +105,8 @@ def load():
     L.b200mapper_get_trajectory.argtypes = [vp, vp, vp, i64]
     L.b200mapper_get_stats.argtypes = [vp, C.POINTER(MapperStats)]
     L.b200mapper_get_window_updates.argtypes = [vp, vp, i32]
+    L.b200mapper_vtk_save.argtypes = [C.c_char_p, vp, i32, i64, vp, vp, i32]
+    L.b200mapper_vtk_load.argtypes = [C.c_char_p, i32, vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L
 
